@@ -1,0 +1,173 @@
+"""Mission / Utf8Filter: host-side mirror of the reference's scanner parameters.
+
+Mirrors (names, meaning, defaults) of
+  * `Utf8Filter`  /root/reference/src/mission.rs:308-349
+  * `Mission`     /root/reference/src/mission.rs:382-421
+  * filter constants `AF_*` mission.rs:225-253, `UBF_*` mission.rs:72-161
+  * default filters mission.rs:32-50 and the `ascii` emulation mission.rs:623-679
+  * option defaults /root/reference/src/options.rs:17-33
+
+Only *resolved* missions are modelled here: parsing of the `-e ENC,MIN,AF,UBF,GREP`
+mini-language (mission.rs:514-749) is CLI work and out of scope.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+# ---- ASCII filters (u128 bitmaps indexed by ASCII code), mission.rs:225-253
+AF_ALL = 0xFFFF_FFFF_FFFF_FFFF_FFFF_FFFF_FFFF_FFFE
+AF_NONE = 0
+AF_CTRL = 0x8000_0000_0000_0000_0000_0000_FFFF_FFFF
+AF_WHITESPACE = 0x0000_0000_0000_0000_0000_0001_0000_1E00
+AF_DEFAULT = AF_ALL & ~AF_CTRL
+
+# ---- Unicode block filters (u64 bitmaps indexed by utf8_lead_byte & 0x3f), mission.rs:72-161
+UBF_ALL = 0xFFFF_FFFF_FFFF_FFFF
+UBF_NONE = 0
+UBF_INVALID = 0xFFE0_0000_0000_0003
+UBF_ALL_VALID = UBF_ALL & ~UBF_INVALID
+UBF_LATIN = 0x0000_0000_0000_01FC
+UBF_ACCENTS = 0x0000_0000_0000_3000
+UBF_GREEK = 0x0000_0000_0000_C000
+UBF_IPA = 0x0000_0000_0000_0700
+UBF_CYRILLIC = 0x0000_0000_001F_0000
+UBF_ARMENIAN = 0x0000_0000_0020_0000
+UBF_HEBREW = 0x0000_0000_00C0_0000
+UBF_ARABIC = 0x0000_0000_2F00_0000
+UBF_SYRIAC = 0x0000_0000_1000_0000
+UBF_AFRICAN = 0x0000_0000_FFE0_0000
+UBF_COMMON = 0x0000_0000_FFFF_FFFC
+UBF_KANA = 0x0000_0008_0000_0000
+UBF_CJK = 0x0000_03F0_0000_0000
+UBF_HANGUL = 0x0000_3800_0000_0000
+UBF_ASIAN = 0x0000_3FFC_0000_0000
+UBF_PUA = 0x0010_4000_0000_0000
+UBF_MISC = 0x0000_8006_0000_0000
+UBF_UNCOMMON = 0x000F_0000_0000_0000
+
+# options.rs:17-33
+ENCODING_DEFAULT = "UTF-8"
+CHARS_MIN_DEFAULT = 4
+COUNTER_OFFSET_DEFAULT = 0
+OUTPUT_LINE_CHAR_NB_MAX_DEFAULT = 64
+OUTPUT_LINE_CHAR_NB_MIN = 6
+ASCII_ENC_LABEL = "ascii"
+
+# Resolved encoding ids shared with include/stringsext_b200.h (SX_ENC_*).
+ENC_X_USER_DEFINED = 0
+ENC_UTF_8 = 1
+ENC_UTF_16LE = 2
+ENC_UTF_16BE = 3
+ENC_SINGLE_BYTE = 4
+ENC_UTF_32LE = 5  # extension: the reference has no UTF-32 (mission.rs:681-688)
+ENC_UTF_32BE = 6  # extension
+
+# label -> (encoding id, canonical name as printed by Encoding::name(), single-byte table key)
+_LABELS = {
+    "ascii": (ENC_X_USER_DEFINED, "x-user-defined", None),
+    "x-user-defined": (ENC_X_USER_DEFINED, "x-user-defined", None),
+    "utf-8": (ENC_UTF_8, "UTF-8", None),
+    "utf8": (ENC_UTF_8, "UTF-8", None),
+    "utf-16le": (ENC_UTF_16LE, "UTF-16LE", None),
+    "utf-16": (ENC_UTF_16LE, "UTF-16LE", None),
+    "utf-16be": (ENC_UTF_16BE, "UTF-16BE", None),
+    "utf-32le": (ENC_UTF_32LE, "UTF-32LE", None),
+    "utf-32be": (ENC_UTF_32BE, "UTF-32BE", None),
+    "koi8-r": (ENC_SINGLE_BYTE, "KOI8-R", "koi8-r"),
+    "ibm866": (ENC_SINGLE_BYTE, "IBM866", "ibm866"),
+    "iso-8859-5": (ENC_SINGLE_BYTE, "ISO-8859-5", "iso-8859-5"),
+    "windows-1251": (ENC_SINGLE_BYTE, "windows-1251", "windows-1251"),
+    "windows-1252": (ENC_SINGLE_BYTE, "windows-1252", "windows-1252"),
+}
+
+
+@dataclass(frozen=True)
+class Utf8Filter:
+    """mission.rs:308-327."""
+
+    af: int = AF_DEFAULT
+    ubf: int = UBF_COMMON
+    grep_char: Optional[int] = None
+
+    def pass_af_filter(self, b: int) -> bool:  # mission.rs:333-337
+        assert b & 0x80 == 0
+        return (1 << b) & self.af != 0
+
+    def pass_ubf_filter(self, b: int) -> bool:  # mission.rs:341-348
+        assert b & 0x80 == 0x80
+        return (1 << (b & 0x3F)) & self.ubf != 0
+
+
+UTF8_FILTER_ASCII_MODE_DEFAULT = Utf8Filter(AF_ALL & ~AF_CTRL, UBF_NONE, None)  # mission.rs:32-36
+UTF8_FILTER_NON_ASCII_MODE_DEFAULT = Utf8Filter(AF_ALL & ~AF_CTRL, UBF_COMMON, None)  # mission.rs:46-50
+UTF8_FILTER_ALL_VALID = Utf8Filter(AF_ALL, UBF_ALL & ~UBF_INVALID, None)  # mission.rs:55-59 (cfg(test))
+UTF8_FILTER_LATIN = Utf8Filter(AF_ALL & ~AF_CTRL | AF_WHITESPACE, UBF_LATIN | UBF_ACCENTS, None)  # :64-68
+
+
+@dataclass(frozen=True)
+class Mission:
+    """mission.rs:382-421 with `encoding` resolved to an id (+ table for single-byte encodings)."""
+
+    encoding_id: int = ENC_UTF_8
+    encoding_name: str = "UTF-8"
+    chars_min_nb: int = CHARS_MIN_DEFAULT
+    require_same_unicode_block: bool = False
+    filter: Utf8Filter = field(default_factory=lambda: UTF8_FILTER_NON_ASCII_MODE_DEFAULT)
+    output_line_char_nb_max: int = OUTPUT_LINE_CHAR_NB_MAX_DEFAULT
+    counter_offset: int = COUNTER_OFFSET_DEFAULT
+    mission_id: int = 0
+    print_encoding_as_ascii: bool = False
+    sb_table: Optional[Tuple[int, ...]] = None  # 128 code points for bytes 0x80..0xFF, 0 = unmapped
+
+    @staticmethod
+    def for_label(
+        label: str,
+        chars_min_nb: Optional[int] = None,
+        af: Optional[int] = None,
+        ubf: Optional[int] = None,
+        grep_char: Optional[int] = None,
+        output_line_char_nb_max: Optional[int] = None,
+        require_same_unicode_block: bool = False,
+        counter_offset: int = COUNTER_OFFSET_DEFAULT,
+        mission_id: int = 0,
+    ) -> "Mission":
+        """The defaulting rules of Missions::new (mission.rs:583-699) for one resolved `-e` item."""
+        key = label.strip().lower()
+        if key not in _LABELS:
+            raise ValueError(f"invalid input encoding name `{label}`")  # mission.rs:681-688
+        enc_id, name, table_key = _LABELS[key]
+        is_ascii = key == ASCII_ENC_LABEL
+        dflt = UTF8_FILTER_ASCII_MODE_DEFAULT if is_ascii else UTF8_FILTER_NON_ASCII_MODE_DEFAULT
+        if grep_char is not None and grep_char > 127:
+            raise ValueError("you can only grep for ASCII codes < 128")  # mission.rs:657-667
+        q = OUTPUT_LINE_CHAR_NB_MAX_DEFAULT if output_line_char_nb_max is None else output_line_char_nb_max
+        if q < OUTPUT_LINE_CHAR_NB_MIN:
+            raise ValueError(f"minimum for `--output-line-len` is `{OUTPUT_LINE_CHAR_NB_MIN}`")  # :612-621
+        table = None
+        if table_key is not None:
+            from .sb_tables import SINGLE_BYTE_TABLES
+
+            table = SINGLE_BYTE_TABLES[table_key]
+        return Mission(
+            encoding_id=enc_id,
+            encoding_name=name,
+            chars_min_nb=CHARS_MIN_DEFAULT if chars_min_nb is None else chars_min_nb,
+            require_same_unicode_block=require_same_unicode_block,
+            filter=Utf8Filter(
+                dflt.af if af is None else af, dflt.ubf if ubf is None else ubf, grep_char
+            ),
+            output_line_char_nb_max=q,
+            counter_offset=counter_offset,
+            mission_id=mission_id,
+            print_encoding_as_ascii=is_ascii,
+            sb_table=table,
+        )
+
+    @property
+    def printed_encoding_name(self) -> str:  # finding.rs:144-148
+        return ASCII_ENC_LABEL if self.print_encoding_as_ascii else self.encoding_name
+
+
+def known_labels() -> Sequence[str]:
+    return sorted(_LABELS)
