@@ -1,0 +1,146 @@
+/*
+ * stringsext_b200.h -- C ABI of the B200-native stringsext scanner hot path.
+ *
+ * Drop-in boundary: the Rust function boundary the reference's driver uses at
+ * /root/reference/src/main.rs:150-161, i.e.
+ *     ScannerState::new(&'static Mission) -> ScannerState            scanner.rs:73-88
+ *     FindingCollection::from(&mut ScannerState, Option<u8>, &[u8], bool)
+ *             -> Pin<Box<FindingCollection>>                          finding_collection.rs:84-89
+ *     fc.v[i].{position, position_precision, s, s_completes_previous_s, mission, input_file_id}
+ *     fc.first_byte_position, fc.str_buf_overflow                     finding_collection.rs:31-50
+ * Each entry point below names the reference interface it replaces.  All scanning runs in
+ * hand-written sm_100a CUDA kernels; there is NO CPU fallback -- without a CUDA device every
+ * scanning call fails and sx_last_error() says why.  INTEGRATION.md shows the Rust FFI stub.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.
+ */
+#ifndef STRINGSEXT_B200_H
+#define STRINGSEXT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Resolved encodings (Mission.encoding, mission.rs:397; `ascii` is x-user-defined + filter,
+ * mission.rs:623-679).  Label parsing stays with the caller (CLI, out of scope). */
+enum {
+    SX_ENC_X_USER_DEFINED = 0,
+    SX_ENC_UTF_8 = 1,
+    SX_ENC_UTF_16LE = 2,
+    SX_ENC_UTF_16BE = 3,
+    SX_ENC_SINGLE_BYTE = 4, /* sb_table gives the upper half (koi8-r, ibm866, windows-125x, ...) */
+    SX_ENC_UTF_32LE = 5,    /* extension: the reference rejects utf-32 (mission.rs:681-688) */
+    SX_ENC_UTF_32BE = 6
+};
+
+/* finding.rs:34-46 Precision */
+enum { SX_PRECISION_BEFORE = 0, SX_PRECISION_EXACT = 1, SX_PRECISION_AFTER = 2 };
+
+/* error codes returned by sx_last_error_code() */
+enum {
+    SX_OK = 0,
+    SX_ERR_NO_DEVICE = 1,    /* no CUDA device / driver: the product never falls back to the CPU */
+    SX_ERR_CUDA = 2,         /* a CUDA runtime call failed */
+    SX_ERR_UNSUPPORTED = 3,  /* mission or geometry outside what the kernels implement */
+    SX_ERR_ARGUMENT = 4
+};
+
+/* mission.rs:382-421 Mission + mission.rs:308-327 Utf8Filter, as plain data. */
+typedef struct {
+    uint8_t mission_id;
+    uint64_t counter_offset;
+    uint32_t encoding_id; /* SX_ENC_* */
+    uint8_t chars_min_nb;
+    uint8_t require_same_unicode_block;
+    uint64_t af_lo, af_hi; /* Utf8Filter.af (u128): bit b set = ASCII code b passes */
+    uint64_t ubf;          /* Utf8Filter.ubf: bit (utf8_lead_byte & 0x3f) set = passes */
+    int16_t grep_char;     /* Utf8Filter.grep_char, -1 = None */
+    uint32_t output_line_char_nb_max;
+    uint8_t print_encoding_as_ascii;
+    uint16_t sb_table[128]; /* SX_ENC_SINGLE_BYTE: code point of byte 0x80+i, 0 = unmapped */
+} sx_mission;
+
+/* finding.rs:51-74 Finding.  `s` points into the owning collection. */
+typedef struct {
+    uint64_t position;
+    uint8_t precision;          /* SX_PRECISION_* */
+    uint8_t completes_previous; /* s_completes_previous_s */
+    int16_t input_file_id;      /* Option<u8>: -1 = None */
+    uint8_t mission_id;
+    const uint8_t* s; /* UTF-8, not NUL terminated */
+    uint32_t s_len;
+    int64_t in_start; /* extension: contiguous input range of the text, relative to the call's buffer */
+    uint32_t in_len;
+} sx_finding;
+
+typedef struct sx_scanner_state sx_scanner_state;
+typedef struct sx_finding_collection sx_finding_collection;
+
+/* Number of CUDA devices usable by the library; 0 when there is no driver/device. */
+int sx_device_count(void);
+
+/* ScannerState::new (scanner.rs:73-88).  `device`: CUDA ordinal the state's scans run on.
+ * Returns NULL (and sets sx_last_error) for missions the kernels do not implement:
+ * grep_char != None, require_same_unicode_block, chars_min_nb == 0 or > output_line_char_nb_max,
+ * output_line_char_nb_max < 6 (options.rs:33) or > 8192. */
+sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device);
+void sx_scanner_state_free(sx_scanner_state*);
+
+/* ScannerState fields (scanner.rs:55-68). */
+uint64_t sx_scanner_state_consumed_bytes(const sx_scanner_state*);
+int sx_scanner_state_maybe_cut(const sx_scanner_state*); /* last_run_str_was_printed_and_is_maybe_cut_str */
+size_t sx_scanner_state_leftover(const sx_scanner_state*, const uint8_t** utf8); /* last_scan_run_leftover */
+
+/* FindingCollection::from (finding_collection.rs:84-89): ONE slice (<= 4096 bytes in the
+ * reference, input.rs:22), host pointer, exact reference semantics -- executed on the GPU. */
+sx_finding_collection* sx_finding_collection_from(sx_scanner_state*, int input_file_id, const uint8_t* buf,
+                                                  size_t len, int is_last_input_buffer);
+
+/* Batched form, the GPU entry point: semantically the fold of sx_finding_collection_from over
+ * consecutive slice_len pieces of buf (main.rs:153-167 for one mission), findings concatenated,
+ * `is_last` applied to the final slice.  buf is a host pointer (buf_is_device == 0; the copy to
+ * the device is part of the call) or a device pointer on the state's device.
+ * cuda_stream: a cudaStream_t or NULL for the default stream.
+ * Leaves the state exactly as the fold would, so calls chain (across buffers and files). */
+sx_finding_collection* sx_scan_stream(sx_scanner_state*, int input_file_id, const void* buf, size_t len,
+                                      size_t slice_len, int buf_is_device, int is_last, void* cuda_stream);
+
+/* FindingCollection accessors (finding_collection.rs:31-50, :371-415). */
+size_t sx_fc_len(const sx_finding_collection*);
+const sx_finding* sx_fc_get(const sx_finding_collection*, size_t i);
+const sx_finding* sx_fc_data(const sx_finding_collection*); /* contiguous array of sx_fc_len() findings */
+uint64_t sx_fc_first_byte_position(const sx_finding_collection*);
+int sx_fc_str_buf_overflow(const sx_finding_collection*);
+void sx_fc_free(sx_finding_collection*);
+
+/* k-way merge of the collections of one slice batch in the order of `impl PartialOrd for
+ * Finding` (finding.rs:92-109) as used by main.rs:133: fills `out` (capacity = sum of lengths)
+ * with pointers to the findings; returns the count. */
+size_t sx_merge(const sx_finding_collection* const* fcs, size_t n, const sx_finding** out);
+
+/* Instrumentation of the most recent sx_scan_stream on this state (CUDA-event times of the
+ * library's own kernels, measured on the stream they were launched on). */
+typedef struct {
+    float scan_kernel_ms;        /* sx_scan_kernel (the hot path) */
+    float materialize_kernel_ms; /* sx_materialize_kernel (finding text) */
+    uint32_t kernel_launches;    /* launches of library kernels in the call */
+    uint32_t relaunches;         /* scan kernel re-runs caused by an output buffer that was too small */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t n_records, text_bytes;
+} sx_scan_stats;
+void sx_scanner_state_last_stats(const sx_scanner_state*, sx_scan_stats* out);
+
+/* Test / benchmark support: fill a device buffer with the library's reproducible synthetic
+ * corpus bytes (counter based; byte i depends on (seed, i) only; see bench.py). */
+int sx_fill_random(void* device_buf, size_t len, uint64_t seed, uint64_t stream_offset, int device,
+                   void* cuda_stream);
+
+int sx_last_error_code(void);
+const char* sx_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

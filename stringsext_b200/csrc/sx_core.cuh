@@ -1,0 +1,827 @@
+// sx_core.cuh -- per-window scanner automaton shared by the CUDA kernels (sx_kernels.cu).
+//
+// One "window" is one decoder_input_window of the reference (2 * output_line_char_nb_max input
+// bytes, /root/reference/src/finding_collection.rs:120-131).  The reference walks windows
+// strictly sequentially; here every window is processed independently by one GPU lane:
+//
+//   * the decoder state at the window start is re-derived from the <= 5 preceding bytes
+//     (UTF-8 / UTF-16 are self-synchronising under the WHATWG decoders, see Dec*::init),
+//   * the scanner carry between windows (`Carry`: leftover run or "cut" flag, i.e.
+//     ScannerState.last_scan_run_leftover / last_run_str_was_printed_and_is_maybe_cut_str,
+//     /root/reference/src/scanner.rs:45-68) is resolved by the tile-level transfer-function
+//     pass in sx_kernels.cu,
+//   * the SplitStr iterator (/root/reference/src/helper.rs:210-432) and the chunk loop of
+//     FindingCollection::from (finding_collection.rs:246-290) are restated as ONE streaming
+//     automaton over decoder events (`WinAuto`), so no decoded text is ever materialised.
+//
+// The automaton supports missions with grep_char == None, require_same_unicode_block == false
+// and 1 <= chars_min_nb <= output_line_char_nb_max (everything else is rejected loudly by
+// the C ABI; see DESIGN.md "Scope").
+//
+// Everything is SX_HD so the host-side *test* harness (tests/emul/) can run the same code on
+// the CPU to debug the decomposition without a GPU.  The product never does that.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SX_HD __host__ __device__ __forceinline__
+#else
+#define SX_HD inline
+#endif
+
+namespace sx {
+
+enum : uint32_t {
+    ENC_XUD = 0,      // x-user-defined (also the `ascii` emulation, mission.rs:623-679)
+    ENC_UTF8 = 1,
+    ENC_UTF16LE = 2,
+    ENC_UTF16BE = 3,
+    ENC_SB = 4,       // single-byte, table driven
+    ENC_UTF32LE = 5,  // extension (no reference semantics)
+    ENC_UTF32BE = 6
+};
+
+enum : uint8_t { PREC_BEFORE = 0, PREC_EXACT = 1, PREC_AFTER = 2 };  // finding.rs:34-46
+
+// Carry between segments / windows / slices.
+enum : uint8_t { K_L = 0, K_C = 1, K_UNKNOWN = 2 };
+enum : uint8_t { CF_HOSTCARRY = 1 };  // leftover starts with text carried in the host ScannerState
+struct Carry {
+    uint8_t kind;        // K_L: leftover of k chars (k may be 0) and cut == false; K_C: cut == true
+    uint8_t flags;
+    uint16_t k;          // chars in the leftover
+    uint32_t in_bytes;   // distance from the leftover's first input byte to the boundary
+    uint32_t out_bytes;  // UTF-8 bytes of the leftover (device-decoded part only)
+};
+SX_HD Carry carry_none() { return Carry{K_L, 0, 0, 0, 0}; }
+SX_HD Carry carry_cut() { return Carry{K_C, 0, 0, 0, 0}; }
+SX_HD Carry carry_unknown() { return Carry{K_UNKNOWN, 0, 0, 0, 0}; }
+SX_HD bool carry_is_null(const Carry& c) { return c.kind == K_L && c.k == 0; }
+
+// One finding as it leaves the GPU (before text materialisation).
+enum : uint32_t { RF_COMPLETES = 1, RF_HOSTCARRY = 2, RF_LEFTOVER = 4 };
+struct Record {
+    uint64_t position;  // Finding.position (absolute, includes counter_offset)   finding.rs:61
+    int64_t in_start;   // first input byte of the text, buffer-relative (may reach into the virtual prefix)
+    uint64_t text_off;  // offset of the UTF-8 text in the text arena
+    uint32_t in_len;    // contiguous input range holding exactly the chars of the text
+    uint32_t text_len;  // UTF-8 bytes (device-decoded part)
+    uint32_t flags;     // RF_*
+    uint32_t precision; // PREC_*
+};
+
+struct ScanParams {
+    const uint8_t* in;  // device pointer to stream offset 0 of this call
+    int64_t len;
+    uint32_t slice_len, W, q, n;
+    uint32_t enc;
+    uint32_t align;      // UTF-16/32: units start at offsets o with (o - align) % unit == 0
+    uint64_t af_lo, af_hi, ubf;
+    uint64_t base_consumed;  // ScannerState.consumed_bytes at offset 0
+    int32_t npend;           // virtual prefix: raw bytes still inside the decoder at offset 0
+    int32_t is_last;
+    uint8_t pend[8];         // pend[8-npend .. 8) are the bytes at offsets [-npend, 0)
+    uint8_t carry_text8[8];  // first bytes of the host-carried leftover text (Precision::Before probe)
+    uint32_t carry_text_len;
+    Carry k0;                // carry at offset 0
+    uint16_t sb_table[128];
+};
+
+// Byte source over the whole stream incl. the virtual prefix.  Used on the rare paths
+// (look-back across tiles, probe, text materialisation); the hot loop reads shared memory.
+struct GlobalSrc {
+    const uint8_t* in;
+    const uint8_t* pend;  // 8 bytes
+    SX_HD uint8_t get(int64_t off) const { return off >= 0 ? in[off] : pend[8 + off]; }
+};
+
+SX_HD bool pass_filter(const ScanParams& P, uint32_t lb) {
+    // Utf8Filter::pass_af_filter / pass_ubf_filter, mission.rs:333-348
+    if (lb < 0x80) return ((lb < 64 ? (P.af_lo >> lb) : (P.af_hi >> (lb - 64))) & 1) != 0;
+    return ((P.ubf >> (lb & 0x3f)) & 1) != 0;
+}
+SX_HD uint32_t utf8_len_of_cp(uint32_t c) { return c < 0x80 ? 1 : c < 0x800 ? 2 : c < 0x10000 ? 3 : 4; }
+SX_HD uint32_t utf8_lead_of_cp(uint32_t c) {
+    return c < 0x80 ? c : c < 0x800 ? (0xC0 | (c >> 6)) : c < 0x10000 ? (0xE0 | (c >> 12)) : (0xF0 | (c >> 18));
+}
+SX_HD uint32_t put_utf8(uint8_t* d, uint32_t c) {
+    if (c < 0x80) { d[0] = (uint8_t)c; return 1; }
+    if (c < 0x800) { d[0] = (uint8_t)(0xC0 | (c >> 6)); d[1] = (uint8_t)(0x80 | (c & 0x3F)); return 2; }
+    if (c < 0x10000) {
+        d[0] = (uint8_t)(0xE0 | (c >> 12)); d[1] = (uint8_t)(0x80 | ((c >> 6) & 0x3F));
+        d[2] = (uint8_t)(0x80 | (c & 0x3F)); return 3;
+    }
+    d[0] = (uint8_t)(0xF0 | (c >> 18)); d[1] = (uint8_t)(0x80 | ((c >> 12) & 0x3F));
+    d[2] = (uint8_t)(0x80 | ((c >> 6) & 0x3F)); d[3] = (uint8_t)(0x80 | (c & 0x3F)); return 4;
+}
+
+// ------------------------------------------------------------------------------------------
+// Window summary (stage A) -> transfer-function descriptor used by the tile-level resolve.
+// ------------------------------------------------------------------------------------------
+enum : uint8_t { WT_CONST = 0, WT_CASEB = 1, WT_DEP = 2 };
+struct WinDesc {
+    uint8_t type;        // WT_*
+    uint8_t pad;
+    uint16_t a;          // chars of the run touching the window's left boundary (capped)
+    uint16_t t_out;      // WT_CASEB: UTF-8 bytes of the window's text
+    uint16_t nrec;       // yields under the null carry
+    uint32_t ntext;      // UTF-8 bytes of those yields
+    Carry null_out;      // carry out under the null carry
+};
+
+struct WinResult {
+    Carry out;
+    uint32_t nrec;
+    uint32_t ntext;
+    int32_t npend_out;  // bytes still inside the decoder at the window end
+};
+
+enum : int { MODE_STATE = 0, MODE_COUNT = 1, MODE_WRITE = 2 };
+
+// ------------------------------------------------------------------------------------------
+// The streaming SplitStr + chunk-loop automaton.
+// ------------------------------------------------------------------------------------------
+struct WinAuto {
+    const ScanParams* P;
+    int mode;
+    Record* wr;        // MODE_WRITE: next record slot
+    uint64_t text_off; // MODE_WRITE: next text offset
+    int64_t slice_start;
+    bool probe_possible;  // stateful decoder: the Precision::Before probe can fire
+
+    // segment / SplitStr state
+    int64_t seg_pos;
+    uint8_t prec;
+    bool probe_pending;
+    bool last_cut;   // SplitStr.last_s_was_maybe_cut
+    bool at_left;    // ok_s_p == inp_start_p for the current run
+    bool cut;        // last_window_str_was_printed_and_is_maybe_cut_str
+    bool run_hostcarry;
+    uint32_t run_n, run_out;
+    int64_t run_in_start, run_in_end;
+    // leftover produced by an `again` chunk
+    bool has_left, left_hostcarry;
+    uint32_t left_k, left_out;
+    int64_t left_in_start;
+    // probe context: leftover present at the slice start (its text may sit at out[0..])
+    bool slice_left_present;
+    Carry slice_left;
+
+    // outputs
+    uint32_t nrec, ntext;
+
+    // summary instrumentation
+    uint32_t m;             // segments so far
+    uint32_t a;             // chars in the first run of segment 1
+    uint32_t s1_out;        // UTF-8 bytes of passing chars in segment 1
+    bool in_first_run;      // still inside the first run of segment 1
+    bool s1_all_pass, s1_later_yield, s2_all_pass;
+
+    SX_HD void init(const ScanParams* p, int md, int64_t slice_st, bool probe_ok) {
+        P = p; mode = md; wr = nullptr; text_off = 0; slice_start = slice_st; probe_possible = probe_ok;
+        cut = false; has_left = false; left_hostcarry = false; left_k = left_out = 0; left_in_start = 0;
+        nrec = ntext = 0; m = 0; a = 0; s1_out = 0; in_first_run = false;
+        s1_all_pass = true; s1_later_yield = false; s2_all_pass = true;
+        slice_left_present = false; slice_left = carry_none();
+        run_n = run_out = 0; run_in_start = run_in_end = 0; run_hostcarry = false;
+        seg_pos = 0; prec = PREC_EXACT; probe_pending = false; last_cut = false; at_left = true;
+    }
+
+    // finding_collection.rs:211-241 + helper.rs:171-200.  `kin` only for the first segment of a window.
+    SX_HD void segment_start(int64_t pos, const Carry* kin, int32_t pend_len) {
+        seg_pos = pos;
+        m++;
+        if (kin) cut = (kin->kind == K_C);
+        const bool cont = cut;  // finding_collection.rs:240-241: used once
+        cut = false;
+        last_cut = cont;
+        at_left = true;
+        run_n = 0; run_out = 0; run_hostcarry = false;
+        prec = PREC_EXACT;
+        probe_pending = probe_possible && (pos == slice_start);
+        has_left = false;
+        if (kin && kin->kind == K_L && kin->k > 0) {  // finding_collection.rs:214-221
+            run_n = kin->k;
+            run_out = kin->out_bytes;
+            run_in_start = pos - (int64_t)kin->in_bytes;
+            run_in_end = pos - pend_len;
+            run_hostcarry = (kin->flags & CF_HOSTCARRY) != 0;
+            prec = PREC_BEFORE;
+        }
+        if (m == 1) in_first_run = true;
+    }
+
+    SX_HD void yield(bool completes, bool maybe_cut) {
+        if (m == 1 && !in_first_run) s1_later_yield = true;
+        if (mode == MODE_WRITE) {
+            Record r;
+            r.position = P->base_consumed + (uint64_t)seg_pos;  // finding_collection.rs:260
+            r.in_start = run_in_start;
+            r.in_len = (uint32_t)(run_in_end - run_in_start);
+            r.text_len = run_out;
+            r.text_off = text_off;
+            r.flags = (completes ? RF_COMPLETES : 0u) | (run_hostcarry ? RF_HOSTCARRY : 0u);
+            r.precision = prec;
+            *wr++ = r;
+            text_off += run_out;
+        }
+        nrec++;
+        ntext += run_out;
+        cut = maybe_cut;     // finding_collection.rs:268
+        prec = PREC_AFTER;   // finding_collection.rs:289
+        has_left = false;
+    }
+
+    template <class ProbeFn>
+    SX_HD void on_char(uint32_t lb, uint32_t ul, int64_t cstart, int64_t cend, ProbeFn&& probe) {
+        if (probe_pending) {  // finding_collection.rs:176: only the first char of the segment matters
+            probe_pending = false;
+            if (lb >= 0x80 && mode != MODE_STATE) {
+                if (probe(*this)) prec = PREC_BEFORE;
+            }
+        }
+        const bool pass = pass_filter(*P, lb);
+        if (pass) {
+            if (run_n == 0) { run_in_start = cstart; }
+            run_n++;
+            run_out += ul;
+            run_in_end = cend;
+            if (m == 1) { s1_out += ul; if (in_first_run && a < 0xFFFFu) a++; }
+            if (run_n >= P->q) {
+                // helper.rs:237 loop exit 2 -> :353-355, :418-421: cut the run here
+                yield(at_left && last_cut, true);
+                at_left = true;   // inp_start_p = p
+                last_cut = true;
+                run_n = 0; run_out = 0; run_hostcarry = false;
+            }
+        } else {
+            if (m == 1) { s1_all_pass = false; }
+            if (m == 2) s2_all_pass = false;
+            if (run_n > 0) {
+                // helper.rs:315-322 exit 3 / exit 4
+                if ((last_cut && at_left) || run_n >= P->n) {
+                    yield(at_left && last_cut, false);
+                    last_cut = false;
+                }
+            }
+            if (m == 1) in_first_run = false;
+            run_n = 0; run_out = 0; run_hostcarry = false;
+            at_left = false;
+        }
+    }
+
+    // End of the segment text.  invalid_after: finding_collection.rs:234-237.
+    SX_HD void segment_end(bool invalid_after) {
+        if (run_n > 0) {
+            const bool completes = at_left && last_cut;
+            const bool again = !completes && !invalid_after;  // helper.rs:389-392 (run_n < q here)
+            if (again) {                                      // finding_collection.rs:281-284
+                if (m == 1 && !in_first_run) s1_later_yield = true;
+                has_left = true;
+                left_k = run_n; left_out = run_out; left_in_start = run_in_start; left_hostcarry = run_hostcarry;
+                cut = false;
+            } else if (completes || run_n >= P->n) {
+                yield(completes, !invalid_after);             // helper.rs:353-354
+            }
+        }
+        if (m == 1) in_first_run = false;
+        run_n = 0; run_out = 0;
+    }
+
+    SX_HD void on_malformed(int64_t next) {
+        segment_end(true);
+        segment_start(next, nullptr, 0);
+    }
+
+    SX_HD Carry carry_out(int64_t boundary) const {
+        if (cut) return carry_cut();
+        if (has_left) {
+            Carry c;
+            c.kind = K_L; c.flags = left_hostcarry ? CF_HOSTCARRY : 0; c.k = (uint16_t)left_k;
+            c.in_bytes = (uint32_t)(boundary - left_in_start);
+            c.out_bytes = left_out;
+            return c;
+        }
+        return carry_none();
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Decoders (restating encoding_rs 0.8.34 semantics event-wise; see DESIGN.md section "Decoders").
+// step(b, pos, emit): emit.ch(lb, ul, cstart, cend) for a decoded char, emit.mal(next) for a
+// malformed sequence after which the next decoder call (segment) starts at `next`.
+// ------------------------------------------------------------------------------------------
+struct DecXud {
+    template <class S> SX_HD void init(const ScanParams&, const S&, int64_t) {}
+    SX_HD int32_t pending_len() const { return 0; }
+    static constexpr bool kStateful = false;
+    template <class E> SX_HD void step(const ScanParams&, uint32_t b, int64_t pos, E& e) {
+        if (b < 0x80) e.ch(b, 1, pos, pos + 1);
+        else e.ch(0xEF, 3, pos, pos + 1);  // U+F780 + (b - 0x80): UTF-8 lead byte 0xEF
+    }
+    template <class E> SX_HD void eof(E&) {}
+};
+
+struct DecSb {
+    template <class S> SX_HD void init(const ScanParams&, const S&, int64_t) {}
+    SX_HD int32_t pending_len() const { return 0; }
+    static constexpr bool kStateful = false;
+    template <class E> SX_HD void step(const ScanParams& P, uint32_t b, int64_t pos, E& e) {
+        if (b < 0x80) { e.ch(b, 1, pos, pos + 1); return; }
+        const uint32_t cp = P.sb_table[b - 0x80];
+        if (cp == 0) e.mal(pos + 1);
+        else e.ch(utf8_lead_of_cp(cp), utf8_len_of_cp(cp), pos, pos + 1);
+    }
+    template <class E> SX_HD void eof(E&) {}
+};
+
+struct DecUtf8 {
+    uint32_t need, seen, lead, lo, hi;
+    static constexpr bool kStateful = true;
+    SX_HD void reset() { need = 0; seen = 0; lead = 0; lo = 0x80; hi = 0xBF; }
+    SX_HD int32_t pending_len() const { return need ? (int32_t)seen + 1 : 0; }
+    SX_HD void start(uint32_t b) {  // b is a valid lead byte C2..F4
+        lead = b; seen = 0; lo = 0x80; hi = 0xBF;
+        if (b < 0xE0) need = 1;
+        else if (b < 0xF0) { need = 2; if (b == 0xE0) lo = 0xA0; else if (b == 0xED) hi = 0x9F; }
+        else { need = 3; if (b == 0xF0) lo = 0x90; else if (b == 0xF4) hi = 0x8F; }
+    }
+    // Decoder state at `ws` from the <= 3 preceding bytes: the WHATWG UTF-8 decoder is in the
+    // neutral state after any byte outside 0x80..0xBF that is not a lead, and a lead byte is
+    // always (re-)read in the neutral state, so the state only depends on the bytes since the
+    // last non-continuation byte.
+    template <class S> SX_HD void init(const ScanParams& P, const S& src, int64_t ws) {
+        reset();
+        const int64_t lo_off = -(int64_t)P.npend;
+        for (int j = 1; j <= 3; ++j) {
+            const int64_t o = ws - j;
+            if (o < lo_off) return;
+            const uint32_t b = src.get(o);
+            if ((b & 0xC0) == 0x80) continue;  // continuation byte: keep looking for the start byte
+            if (b < 0xC2 || b > 0xF4) return;  // ASCII or invalid lead: neutral
+            start(b);
+            if ((int)need < j) { reset(); return; }  // sequence already complete (or overrun)
+            for (int i = j - 1; i >= 1; --i) {       // replay the j-1 continuation bytes
+                const uint32_t c = src.get(ws - i);
+                if (c < lo || c > hi) { reset(); return; }
+                lo = 0x80; hi = 0xBF; seen++;
+            }
+            if (seen == need) reset();
+            return;
+        }
+    }
+    template <class E> SX_HD void step(const ScanParams&, uint32_t b, int64_t pos, E& e) {
+        if (need != 0) {
+            if (b >= lo && b <= hi) {
+                lo = 0x80; hi = 0xBF; seen++;
+                if (seen == need) { const uint32_t l = lead, nn = need; reset(); e.ch(l, nn + 1, pos - nn, pos + 1); }
+                return;
+            }
+            reset();
+            e.mal(pos);  // the offending byte is not consumed: it starts the next segment
+        }
+        if (b < 0x80) { e.ch(b, 1, pos, pos + 1); return; }
+        if (b < 0xC2 || b > 0xF4) { e.mal(pos + 1); return; }
+        start(b);
+    }
+    template <class E> SX_HD void eof(E&) { reset(); }
+};
+
+template <bool BE>
+struct DecUtf16 {
+    uint32_t has_lead, lead_byte, lead_sur;  // lead_sur != 0: pending high surrogate
+    static constexpr bool kStateful = true;
+    SX_HD int32_t pending_len() const { return (lead_sur ? 2 : 0) + (has_lead ? 1 : 0); }
+    SX_HD static uint32_t unit(uint32_t first, uint32_t second) { return BE ? ((first << 8) | second) : ((second << 8) | first); }
+    // The unit grid is global ((o - align) even); a high surrogate is always pending after it has
+    // been processed, whatever preceded it; a pending BMP unit never survives a decoder call
+    // boundary because the reference flushes it with an empty call (finding_collection.rs:134-143).
+    template <class S> SX_HD void init(const ScanParams& P, const S& src, int64_t ws) {
+        has_lead = 0; lead_byte = 0; lead_sur = 0;
+        const int64_t lo_off = -(int64_t)P.npend;
+        int64_t ub = ws;  // start of the unit containing / following ws
+        if (((ws - (int64_t)P.align) & 1) != 0) {
+            if (ws - 1 >= lo_off) { has_lead = 1; lead_byte = src.get(ws - 1); ub = ws - 1; }
+        }
+        if (ub - 2 >= lo_off) {
+            const uint32_t u = unit(src.get(ub - 2), src.get(ub - 1));
+            if ((u & 0xFC00) == 0xD800) lead_sur = u;
+        }
+    }
+    template <class E> SX_HD void step(const ScanParams&, uint32_t b, int64_t pos, E& e) {
+        if (!has_lead) { has_lead = 1; lead_byte = b; return; }
+        has_lead = 0;
+        const uint32_t cu = unit(lead_byte, b);
+        const uint32_t hb = cu & 0xFC00;
+        if (hb == 0xD800) {
+            if (lead_sur) { lead_sur = cu; e.mal(pos + 1); return; }
+            lead_sur = cu;
+            return;
+        }
+        if (hb == 0xDC00) {
+            if (!lead_sur) { e.mal(pos + 1); return; }
+            const uint32_t cp = 0x10000u + ((lead_sur - 0xD800u) << 10) + (cu - 0xDC00u);
+            lead_sur = 0;
+            e.ch(0xF0 | (cp >> 18), 4, pos - 3, pos + 1);
+            return;
+        }
+        if (lead_sur) {
+            // Malformed(2,2): the BMP unit is consumed and written first thing by the next call
+            lead_sur = 0;
+            e.mal(pos + 1);
+            e.ch(utf8_lead_of_cp(cu), utf8_len_of_cp(cu), pos - 1, pos + 1);
+            return;
+        }
+        e.ch(utf8_lead_of_cp(cu), utf8_len_of_cp(cu), pos - 1, pos + 1);
+    }
+    template <class E> SX_HD void eof(E&) { has_lead = 0; lead_sur = 0; }
+};
+
+
+template <bool BE>
+struct DecUtf32 {  // EXTENSION: no reference semantics (mission.rs:681-688 rejects utf-32)
+    uint32_t nb, acc;
+    static constexpr bool kStateful = true;
+    SX_HD int32_t pending_len() const { return (int32_t)nb; }
+    template <class S> SX_HD void init(const ScanParams& P, const S& src, int64_t ws) {
+        nb = 0; acc = 0;
+        const int64_t lo_off = -(int64_t)P.npend;
+        int64_t r = (ws - (int64_t)P.align) & 3;  // bytes of the current unit already before ws
+        if (ws - r < lo_off) r = ws - lo_off;     // stream start inside the unit (cannot happen with a sane align)
+        for (int64_t o = ws - r; o < ws; ++o) push(src.get(o));
+    }
+    SX_HD void push(uint32_t b) { acc = BE ? ((acc << 8) | b) : (acc | (b << (8 * nb))); nb++; }
+    template <class E> SX_HD void step(const ScanParams&, uint32_t b, int64_t pos, E& e) {
+        push(b);
+        if (nb < 4) return;
+        const uint32_t c = acc;
+        nb = 0; acc = 0;
+        if (c > 0x10FFFF || (c >= 0xD800 && c <= 0xDFFF)) { e.mal(pos + 1); return; }
+        e.ch(utf8_lead_of_cp(c), utf8_len_of_cp(c), pos - 3, pos + 1);
+    }
+    template <class E> SX_HD void eof(E&) { nb = 0; acc = 0; }
+};
+
+// ------------------------------------------------------------------------------------------
+// Precision::Before probe (finding_collection.rs:176-207), literal emulation of the 8-byte
+// re-decode with a fresh decoder.  Only reached for the first char of a segment that starts
+// at a slice start and whose first decoded byte is >= 0x80 -- rare, so clarity over speed.
+// ------------------------------------------------------------------------------------------
+SX_HD uint32_t utf8_valid_up_to8(const uint8_t* s, uint32_t n) {
+    uint32_t i = 0;
+    while (i < n) {
+        const uint32_t b = s[i];
+        if (b < 0x80) { i++; continue; }
+        if (b < 0xC2) return i;
+        if (b < 0xE0) { if (i + 1 >= n || (s[i + 1] & 0xC0) != 0x80) return i; i += 2; continue; }
+        if (b < 0xF0) {
+            const uint32_t lo = b == 0xE0 ? 0xA0 : 0x80, hi = b == 0xED ? 0x9F : 0xBF;
+            if (i + 2 >= n || s[i + 1] < lo || s[i + 1] > hi || (s[i + 2] & 0xC0) != 0x80) return i;
+            i += 3; continue;
+        }
+        if (b < 0xF5) {
+            const uint32_t lo = b == 0xF0 ? 0x90 : 0x80, hi = b == 0xF4 ? 0x8F : 0xBF;
+            if (i + 3 >= n || s[i + 1] < lo || s[i + 1] > hi || (s[i + 2] & 0xC0) != 0x80 || (s[i + 3] & 0xC0) != 0x80) return i;
+            i += 4; continue;
+        }
+        return i;
+    }
+    return i;
+}
+
+// `written` of a fresh encoding_rs UTF-8 decoder over src[0..slen) into an 8-byte buffer, last = true.
+// For UTF-8 the output equals the input bytes, so only the count is needed.
+SX_HD uint32_t utf8_fresh_written8(const uint8_t* src, uint32_t slen) {
+    uint32_t sp = 0, dp = 0, need = 0, seen = 0, lo = 0x80, hi = 0xBF;
+    for (;;) {
+        if (need == 0) {
+            const uint32_t n = (slen - sp) < (8 - dp) ? (slen - sp) : (8 - dp);
+            const uint32_t v = utf8_valid_up_to8(src + sp, n);
+            sp += v; dp += v;
+        }
+        if (sp >= slen) return dp;
+        if (!(dp + 3 < 8)) return dp;
+        const uint32_t b = src[sp++];
+        if (need == 0) {
+            if (b < 0x80) { dp++; continue; }
+            if (b < 0xC2 || b > 0xF4) return dp;
+            seen = 0; lo = 0x80; hi = 0xBF;
+            if (b < 0xE0) need = 1;
+            else if (b < 0xF0) { need = 2; if (b == 0xE0) lo = 0xA0; else if (b == 0xED) hi = 0x9F; }
+            else { need = 3; if (b == 0xF0) lo = 0x90; else if (b == 0xF4) hi = 0x8F; }
+            continue;
+        }
+        if (b < lo || b > hi) return dp;
+        lo = 0x80; hi = 0xBF; seen++;
+        if (seen == need) { dp += need + 1; need = 0; }
+    }
+}
+
+// UTF-8 probe.  `first_segment`: the probing segment is the first one of the slice.
+// Returns true for Precision::Before.
+SX_HD bool probe_utf8(const ScanParams& P, const GlobalSrc& g, int64_t slice_start, int64_t slice_end, bool first_segment,
+                      int32_t slice_pending, const Carry& slice_left) {
+    const bool has_left = slice_left.kind == K_L && slice_left.k > 0;
+    if (first_segment) return has_left || slice_pending > 0;  // fresh decoder hits a continuation byte: written == 0
+    if (!has_left) return false;  // same bytes, same neutral state: identical
+    // Second segment at offset 0 (after a Malformed with read == 0): the stale leftover text still
+    // sits at out[0..], the new text follows it.  Compare literally.
+    uint8_t src8[16], out8[24];
+    uint32_t sl = 0;
+    for (; sl < 16 && slice_start + sl < slice_end; ++sl) src8[sl] = g.get(slice_start + sl);
+    const uint32_t w2 = utf8_fresh_written8(src8, sl);
+    if (w2 == 0) return true;
+    uint32_t ol = 0;
+    if (slice_left.flags & CF_HOSTCARRY)
+        for (uint32_t i = 0; i < P.carry_text_len && i < 8 && ol < 8; ++i) out8[ol++] = P.carry_text8[i];
+    // device part of the leftover text = raw input bytes (UTF-8 -> UTF-8)
+    {
+        const int64_t ls = slice_start - (int64_t)slice_left.in_bytes;
+        for (uint32_t i = 0; i < slice_left.out_bytes && ol < 8; ++i) out8[ol++] = g.get(ls + i);
+    }
+    for (uint32_t i = 0; ol < 8 && i < sl; ++i) out8[ol++] = src8[i];  // (over-)approximates the new text; only w2 valid bytes are compared
+    for (uint32_t i = 0; i < w2; ++i)
+        if ((i < ol ? out8[i] : 0) != src8[i]) return true;
+    return false;
+}
+
+// Decode UTF-16 units from `pos` with the given decoder state into at most `cap` bytes the way
+// encoding_rs does (space check dp + 3 < cap before every byte read when `checked`), stopping at
+// the first malformed sequence or `end`.  Returns bytes written.
+template <bool BE>
+SX_HD uint32_t utf16_decode_some(const GlobalSrc& g, int64_t pos, int64_t end, uint32_t has_lead, uint32_t lead_byte,
+                                 uint32_t lead_sur, uint8_t* dst, uint32_t cap, bool checked) {
+    uint32_t dp = 0;
+    for (; pos < end; ++pos) {
+        if (checked ? !(dp + 3 < cap) : (dp + 4 > cap)) break;
+        const uint32_t b = g.get(pos);
+        if (!has_lead) { has_lead = 1; lead_byte = b; continue; }
+        has_lead = 0;
+        const uint32_t cu = BE ? ((lead_byte << 8) | b) : ((b << 8) | lead_byte);
+        const uint32_t hb = cu & 0xFC00;
+        if (hb == 0xD800) { if (lead_sur) break; lead_sur = cu; continue; }
+        if (hb == 0xDC00) {
+            if (!lead_sur) break;
+            dp += put_utf8(dst + dp, 0x10000u + ((lead_sur - 0xD800u) << 10) + (cu - 0xDC00u));
+            lead_sur = 0;
+            continue;
+        }
+        if (lead_sur) break;
+        dp += put_utf8(dst + dp, cu);
+    }
+    return dp;
+}
+
+template <bool BE>
+SX_HD bool probe_utf16(const ScanParams& P, const GlobalSrc& g, int64_t slice_start, int64_t slice_end, int64_t win_end,
+                       uint32_t has_lead, uint32_t lead_byte, uint32_t lead_sur, const Carry& slice_left) {
+    (void)P;
+    if (slice_left.kind == K_L && slice_left.k > 0) return true;  // leftover prepended: Before anyway
+    if (!has_lead && !lead_sur) return false;                     // aligned and neutral: identical
+    uint8_t fb[16], ob[16];
+    for (int i = 0; i < 16; ++i) { fb[i] = 0; ob[i] = 0; }
+    const uint32_t w2 = utf16_decode_some<BE>(g, slice_start, slice_end, 0, 0, 0, fb, 8, true);
+    if (w2 == 0) return true;
+    // the real first decoder call of the slice covers the first window only
+    (void)utf16_decode_some<BE>(g, slice_start, win_end, has_lead, lead_byte, lead_sur, ob, 12, false);
+    for (uint32_t i = 0; i < w2; ++i)
+        if (ob[i] != fb[i]) return true;
+    return false;
+}
+
+template <bool BE>
+SX_HD bool probe_utf32(const GlobalSrc& g, int64_t slice_start, int64_t slice_end, int64_t win_end, uint32_t nb,
+                       const Carry& slice_left) {
+    if (slice_left.kind == K_L && slice_left.k > 0) return true;
+    if (nb == 0 && win_end - slice_start >= 20) return false;  // aligned, and the window covers all the probe reads
+    // decode both ways (fresh: 4-byte units from the slice start into an 8-byte buffer; real: first
+    // decoder call of the slice = first window only, the rest of `out` is still zero)
+    uint8_t fb[16], ob[16];
+    for (int i = 0; i < 16; ++i) { fb[i] = 0; ob[i] = 0; }
+    uint32_t w2 = 0;
+    {
+        uint32_t dp = 0, k = 0, acc = 0;
+        for (int64_t p = slice_start; p < slice_end; ++p) {
+            if (!(dp + 3 < 8)) break;
+            const uint32_t b = g.get(p);
+            acc = BE ? ((acc << 8) | b) : (acc | (b << (8 * k)));
+            if (++k < 4) continue;
+            const uint32_t c = acc; k = 0; acc = 0;
+            if (c > 0x10FFFF || (c >= 0xD800 && c <= 0xDFFF)) break;
+            dp += put_utf8(fb + dp, c);
+        }
+        w2 = dp;
+    }
+    if (w2 == 0) return true;
+    {
+        uint32_t dp = 0, k = 0, acc = 0;
+        for (int64_t p = slice_start - nb; p < win_end && dp + 4 <= 12; ++p) {
+            const uint32_t b = g.get(p);
+            acc = BE ? ((acc << 8) | b) : (acc | (b << (8 * k)));
+            if (++k < 4) continue;
+            const uint32_t c = acc; k = 0; acc = 0;
+            if (c > 0x10FFFF || (c >= 0xD800 && c <= 0xDFFF)) break;
+            dp += put_utf8(ob + dp, c);
+        }
+    }
+    for (uint32_t i = 0; i < w2; ++i)
+        if (ob[i] != fb[i]) return true;
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// Window driver.
+// ------------------------------------------------------------------------------------------
+struct WinGeom {
+    int64_t ws, we;                 // window [ws, we) in buffer offsets
+    int64_t slice_start, slice_end; // enclosing slice
+    bool final_last;                // last window of the stream and is_last_input_buffer
+};
+
+template <class Dec>
+struct ProbeCtx {
+    const ScanParams* P;
+    const GlobalSrc* g;
+    const WinGeom* geo;
+    // decoder state at the slice start (only meaningful when geo->ws == geo->slice_start)
+    int32_t pend0;
+    uint32_t s0, s1, s2;
+};
+
+template <class Dec> struct ProbeImpl {
+    SX_HD static bool run(const ProbeCtx<Dec>&, const WinAuto&) { return false; }
+};
+template <> struct ProbeImpl<DecUtf8> {
+    SX_HD static bool run(const ProbeCtx<DecUtf8>& c, const WinAuto& A) {
+        return probe_utf8(*c.P, *c.g, c.geo->slice_start, c.geo->slice_end, A.m == 1, c.pend0, A.slice_left);
+    }
+};
+template <bool BE> struct ProbeImpl<DecUtf16<BE>> {
+    SX_HD static bool run(const ProbeCtx<DecUtf16<BE>>& c, const WinAuto& A) {
+        return probe_utf16<BE>(*c.P, *c.g, c.geo->slice_start, c.geo->slice_end, c.geo->we, c.s0, c.s1, c.s2, A.slice_left);
+    }
+};
+template <bool BE> struct ProbeImpl<DecUtf32<BE>> {
+    SX_HD static bool run(const ProbeCtx<DecUtf32<BE>>& c, const WinAuto& A) {
+        return probe_utf32<BE>(*c.g, c.geo->slice_start, c.geo->slice_end, c.geo->we, c.s0, A.slice_left);
+    }
+};
+
+template <class Dec> SX_HD void probe_capture(ProbeCtx<Dec>& c, const Dec& d) { (void)c; (void)d; }
+SX_HD void probe_capture(ProbeCtx<DecUtf8>& c, const DecUtf8& d) { c.pend0 = d.pending_len(); }
+template <bool BE> SX_HD void probe_capture(ProbeCtx<DecUtf16<BE>>& c, const DecUtf16<BE>& d) {
+    c.s0 = d.has_lead; c.s1 = d.lead_byte; c.s2 = d.lead_sur;
+}
+template <bool BE> SX_HD void probe_capture(ProbeCtx<DecUtf32<BE>>& c, const DecUtf32<BE>& d) { c.s0 = d.nb; }
+
+template <class Dec>
+struct Emit {
+    WinAuto* A;
+    const ProbeCtx<Dec>* pc;
+    SX_HD void ch(uint32_t lb, uint32_t ul, int64_t cs, int64_t ce) {
+        const ProbeCtx<Dec>* c = pc;
+        A->on_char(lb, ul, cs, ce, [c](const WinAuto& a) { return ProbeImpl<Dec>::run(*c, a); });
+    }
+    SX_HD void mal(int64_t next) { A->on_malformed(next); }
+};
+
+// TileSrc concept: uint8_t get(int64_t off) for any stream offset; load16(int64_t off16, uint32_t w[4])
+// loads the aligned 16-byte chunk starting at tile-relative-aligned offset (off16 % 16 == 0 relative
+// to the tile base) -- both provided by the kernel / the emulation harness.
+template <class Dec, class TileSrc>
+SX_HD void scan_window(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
+                       int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
+    Dec dec;
+    dec.init(P, tsrc, geo.ws);
+    ProbeCtx<Dec> pc;
+    pc.P = &P; pc.g = &g; pc.geo = &geo; pc.pend0 = 0; pc.s0 = pc.s1 = pc.s2 = 0;
+    probe_capture(pc, dec);
+    WinAuto A;
+    A.init(&P, mode, geo.slice_start, Dec::kStateful);
+    A.wr = wr; A.text_off = text_off;
+    if (geo.ws == geo.slice_start) { A.slice_left_present = true; A.slice_left = kin; }
+    A.segment_start(geo.ws, &kin, dec.pending_len());
+    Emit<Dec> em{&A, &pc};
+    tsrc.for_each_byte(geo.ws, geo.we, [&](uint32_t b, int64_t pos) { dec.step(P, b, pos, em); });
+    if (geo.final_last) {
+        // finding_collection.rs:234-237 / :298-304: invalid_after for every segment of the last window,
+        // then one flush round whose only lasting effects are a reset decoder and cut == false.
+        A.segment_end(true);
+        dec.eof(em);
+        A.cut = false;
+        A.has_left = false;
+        res.npend_out = 0;
+    } else {
+        A.segment_end(false);
+        res.npend_out = dec.pending_len();
+    }
+    res.out = A.carry_out(geo.we);
+    res.nrec = A.nrec;
+    res.ntext = A.ntext;
+    if (desc) {
+        desc->a = (uint16_t)A.a;
+        desc->nrec = (uint16_t)(A.nrec > 0xFFFFu ? 0xFFFFu : A.nrec);
+        desc->ntext = A.ntext;
+        desc->null_out = res.out;
+        desc->t_out = 0;
+        desc->pad = 0;
+        const bool single_all_pass = (A.m == 1 && A.s1_all_pass);
+        if (geo.final_last) desc->type = WT_CONST;
+        else if (single_all_pass) {
+            if (A.a < P.q) { desc->type = WT_CASEB; desc->t_out = (uint16_t)A.s1_out; }
+            else desc->type = WT_CONST;
+        } else if (A.a > 0 && !A.s1_later_yield && (A.m == 1 || (A.m == 2 && A.s2_all_pass))) desc->type = WT_DEP;
+        else desc->type = WT_CONST;
+    }
+}
+
+// Transfer function of a WT_CASEB window (single segment, every char passes, t = a < q chars).
+SX_HD Carry eval_caseb(const ScanParams& P, const WinDesc& d, const Carry& kin, uint32_t wlen) {
+    if (kin.kind == K_UNKNOWN) return kin;
+    if (kin.kind == K_C) return d.a >= 1 ? carry_cut() : carry_none();
+    if (kin.k == 0) return d.null_out;
+    if ((uint32_t)kin.k + d.a < P.q) {
+        Carry c = kin;
+        c.k = (uint16_t)(kin.k + d.a);
+        c.in_bytes = kin.in_bytes + wlen;
+        c.out_bytes = kin.out_bytes + d.t_out;
+        return c;
+    }
+    return carry_cut();
+}
+
+// Does window `d` emit anything given its real carry-in?  (see DESIGN.md "Emit rule")
+SX_HD bool needs_emit(const ScanParams& P, const WinDesc& d, const Carry& kin) {
+    if (d.nrec > 0) return true;
+    if (kin.kind == K_C) return d.a > 0;
+    return kin.k > 0 && (uint32_t)kin.k + d.a >= P.n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Text materialisation: decode input[in_start, in_start + in_len) (whole chars only) to UTF-8.
+// ------------------------------------------------------------------------------------------
+SX_HD uint32_t transcode_range(const ScanParams& P, const GlobalSrc& g, int64_t s, uint32_t len, uint8_t* dst) {
+    uint32_t dp = 0;
+    const int64_t e = s + len;
+    switch (P.enc) {
+    case ENC_UTF8:
+        for (int64_t p = s; p < e; ++p) dst[dp++] = g.get(p);
+        break;
+    case ENC_XUD:
+        for (int64_t p = s; p < e; ++p) { const uint32_t b = g.get(p); dp += put_utf8(dst + dp, b < 0x80 ? b : b + 0xF700u); }
+        break;
+    case ENC_SB:
+        for (int64_t p = s; p < e; ++p) { const uint32_t b = g.get(p); dp += put_utf8(dst + dp, b < 0x80 ? b : P.sb_table[b - 0x80]); }
+        break;
+    case ENC_UTF16LE:
+    case ENC_UTF16BE: {
+        const bool be = P.enc == ENC_UTF16BE;
+        uint32_t hs = 0;
+        for (int64_t p = s; p + 1 < e; p += 2) {
+            const uint32_t b0 = g.get(p), b1 = g.get(p + 1);
+            const uint32_t cu = be ? ((b0 << 8) | b1) : ((b1 << 8) | b0);
+            if ((cu & 0xFC00) == 0xD800) { hs = cu; continue; }
+            if ((cu & 0xFC00) == 0xDC00) { dp += put_utf8(dst + dp, 0x10000u + ((hs - 0xD800u) << 10) + (cu - 0xDC00u)); hs = 0; continue; }
+            dp += put_utf8(dst + dp, cu);
+        }
+        break;
+    }
+    case ENC_UTF32LE:
+    case ENC_UTF32BE: {
+        const bool be = P.enc == ENC_UTF32BE;
+        for (int64_t p = s; p + 3 < e; p += 4) {
+            const uint32_t b0 = g.get(p), b1 = g.get(p + 1), b2 = g.get(p + 2), b3 = g.get(p + 3);
+            const uint32_t c = be ? ((b0 << 24) | (b1 << 16) | (b2 << 8) | b3) : ((b3 << 24) | (b2 << 16) | (b1 << 8) | b0);
+            dp += put_utf8(dst + dp, c);
+        }
+        break;
+    }
+    }
+    return dp;
+}
+
+// Window / slice geometry (finding_collection.rs:124-131, input.rs:22).
+struct Geometry {
+    int64_t len;
+    uint32_t slice_len, W, wps;  // wps = windows per full slice
+    int32_t is_last;
+    SX_HD void init(const ScanParams& P) {
+        len = P.len; slice_len = P.slice_len; W = P.W; is_last = P.is_last;
+        wps = (slice_len + W - 1) / W;
+    }
+    // window index -> geometry; false when the window lies beyond the stream
+    SX_HD bool window(int64_t widx, WinGeom& g) const {
+        const int64_t s = widx / wps;
+        const int64_t j = widx - s * wps;
+        g.slice_start = s * (int64_t)slice_len;
+        if (g.slice_start >= len) return false;
+        g.slice_end = g.slice_start + slice_len < len ? g.slice_start + slice_len : len;
+        g.ws = g.slice_start + j * (int64_t)W;
+        if (g.ws >= g.slice_end) return false;
+        g.we = g.ws + W < g.slice_end ? g.ws + W : g.slice_end;
+        g.final_last = is_last && g.we == len;
+        return true;
+    }
+};
+
+}  // namespace sx

@@ -1,0 +1,335 @@
+"""ScannerState / FindingCollection / Finding: Python mirror of the reference's scanner API,
+bound to the CUDA library through its C ABI (include/stringsext_b200.h).
+
+Reference interface mirrored here:
+  * `ScannerState::new(mission)`                         /root/reference/src/scanner.rs:73-88
+  * `FindingCollection::from(ss, file_id, buf, is_last)` /root/reference/src/finding_collection.rs:84-89
+  * `Finding` / `Precision`                              /root/reference/src/finding.rs:34-74
+  * merge order (`impl PartialOrd for Finding`)          /root/reference/src/finding.rs:92-109
+  * `Finding::print`                                     /root/reference/src/finding.rs:112-155
+
+All scanning happens in the CUDA kernels; if the library or a CUDA device is missing the calls
+raise -- there is deliberately no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+from .mission import Mission
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstringsext_b200.so")
+
+
+class ScannerError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"stringsext_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Precision(enum.IntEnum):  # finding.rs:34-46
+    Before = 0
+    Exact = 1
+    After = 2
+
+
+class _CMission(C.Structure):
+    _fields_ = [
+        ("mission_id", C.c_uint8),
+        ("counter_offset", C.c_uint64),
+        ("encoding_id", C.c_uint32),
+        ("chars_min_nb", C.c_uint8),
+        ("require_same_unicode_block", C.c_uint8),
+        ("af_lo", C.c_uint64),
+        ("af_hi", C.c_uint64),
+        ("ubf", C.c_uint64),
+        ("grep_char", C.c_int16),
+        ("output_line_char_nb_max", C.c_uint32),
+        ("print_encoding_as_ascii", C.c_uint8),
+        ("sb_table", C.c_uint16 * 128),
+    ]
+
+
+class _CFinding(C.Structure):
+    _fields_ = [
+        ("position", C.c_uint64),
+        ("precision", C.c_uint8),
+        ("completes_previous", C.c_uint8),
+        ("input_file_id", C.c_int16),
+        ("mission_id", C.c_uint8),
+        ("s", C.POINTER(C.c_uint8)),
+        ("s_len", C.c_uint32),
+        ("in_start", C.c_int64),
+        ("in_len", C.c_uint32),
+    ]
+
+
+class ScanStats(C.Structure):
+    _fields_ = [
+        ("scan_kernel_ms", C.c_float),
+        ("materialize_kernel_ms", C.c_float),
+        ("kernel_launches", C.c_uint32),
+        ("relaunches", C.c_uint32),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
+        ("n_records", C.c_uint64),
+        ("text_bytes", C.c_uint64),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ScannerError(2, f"{LIB_PATH} is missing: build it with `python -m stringsext_b200.build` "
+                              "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.sx_device_count.restype = C.c_int
+    L.sx_scanner_state_new.restype = C.c_void_p
+    L.sx_scanner_state_new.argtypes = [C.POINTER(_CMission), C.c_int]
+    L.sx_scanner_state_free.argtypes = [C.c_void_p]
+    L.sx_scanner_state_consumed_bytes.restype = C.c_uint64
+    L.sx_scanner_state_consumed_bytes.argtypes = [C.c_void_p]
+    L.sx_scanner_state_maybe_cut.argtypes = [C.c_void_p]
+    L.sx_scanner_state_leftover.restype = C.c_size_t
+    L.sx_scanner_state_leftover.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint8))]
+    L.sx_scanner_state_last_stats.argtypes = [C.c_void_p, C.POINTER(ScanStats)]
+    L.sx_finding_collection_from.restype = C.c_void_p
+    L.sx_finding_collection_from.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_int]
+    L.sx_scan_stream.restype = C.c_void_p
+    L.sx_scan_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    L.sx_fc_len.restype = C.c_size_t
+    L.sx_fc_len.argtypes = [C.c_void_p]
+    L.sx_fc_get.restype = C.POINTER(_CFinding)
+    L.sx_fc_get.argtypes = [C.c_void_p, C.c_size_t]
+    L.sx_fc_data.restype = C.POINTER(_CFinding)
+    L.sx_fc_data.argtypes = [C.c_void_p]
+    L.sx_fc_first_byte_position.restype = C.c_uint64
+    L.sx_fc_first_byte_position.argtypes = [C.c_void_p]
+    L.sx_fc_str_buf_overflow.argtypes = [C.c_void_p]
+    L.sx_fc_free.argtypes = [C.c_void_p]
+    L.sx_merge.restype = C.c_size_t
+    L.sx_merge.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.POINTER(_CFinding))]
+    L.sx_fill_random.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    L.sx_last_error_code.restype = C.c_int
+    L.sx_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _raise_last():
+    L = load_library()
+    raise ScannerError(L.sx_last_error_code(), (L.sx_last_error() or b"").decode())
+
+
+def device_count() -> int:
+    return load_library().sx_device_count()
+
+
+def exported_symbols() -> List[str]:
+    """Entry points declared in include/stringsext_b200.h (used by the ABI load test)."""
+    return [
+        "sx_device_count", "sx_scanner_state_new", "sx_scanner_state_free", "sx_scanner_state_consumed_bytes",
+        "sx_scanner_state_maybe_cut", "sx_scanner_state_leftover", "sx_finding_collection_from", "sx_scan_stream",
+        "sx_fc_len", "sx_fc_get", "sx_fc_data", "sx_fc_first_byte_position", "sx_fc_str_buf_overflow", "sx_fc_free",
+        "sx_merge", "sx_scanner_state_last_stats", "sx_fill_random", "sx_last_error_code", "sx_last_error",
+    ]
+
+
+@dataclass
+class Finding:  # finding.rs:51-74
+    position: int
+    position_precision: Precision
+    s: bytes
+    s_completes_previous_s: bool
+    mission: Mission
+    input_file_id: Optional[int] = None
+    in_start: int = 0
+    in_len: int = 0
+
+    def sort_key(self):  # finding.rs:92-109
+        return (self.position, self.mission.mission_id, self.mission.filter.ubf, self.mission.filter.af)
+
+    def print(self, n_inputs: int = 1, n_missions: int = 1, radix: Optional[str] = None,
+              no_metadata: bool = False) -> bytes:
+        """finding.rs:112-155 (the global ARGS become parameters)."""
+        out = bytearray(b"\n")
+        if not no_metadata:
+            if n_inputs > 1 and self.input_file_id is not None:
+                out += bytes([self.input_file_id + 64, 0x20])
+            if radix is not None:
+                out += {Precision.After: b">", Precision.Exact: b" ", Precision.Before: b"<"}[self.position_precision]
+                out += {"x": "%x", "d": "%d", "o": "%o"}[radix.lower()].encode() % self.position
+                out += b"+\t" if self.s_completes_previous_s else b" \t"
+            if n_missions > 1:
+                out += b"(" + bytes([self.mission.mission_id + 97]) + b" " + self.mission.printed_encoding_name.encode() + b")\t"
+        out += self.s
+        return bytes(out)
+
+
+class FindingCollection:  # finding_collection.rs:31-50
+    def __init__(self, v: List[Finding], first_byte_position: int, str_buf_overflow: bool):
+        self.v = v
+        self.first_byte_position = first_byte_position
+        self.str_buf_overflow = str_buf_overflow
+
+    def __iter__(self):
+        return iter(self.v)
+
+    def __len__(self):
+        return len(self.v)
+
+
+class ScannerState:
+    """scanner.rs:40-89.  One per mission; scans run on CUDA device `device`."""
+
+    def __init__(self, mission: Mission, device: int = 0):
+        L = load_library()
+        self.mission = mission
+        self.device = device
+        cm = _CMission()
+        cm.mission_id = mission.mission_id
+        cm.counter_offset = mission.counter_offset
+        cm.encoding_id = mission.encoding_id
+        cm.chars_min_nb = mission.chars_min_nb
+        cm.require_same_unicode_block = 1 if mission.require_same_unicode_block else 0
+        cm.af_lo = mission.filter.af & 0xFFFFFFFFFFFFFFFF
+        cm.af_hi = (mission.filter.af >> 64) & 0xFFFFFFFFFFFFFFFF
+        cm.ubf = mission.filter.ubf
+        cm.grep_char = -1 if mission.filter.grep_char is None else mission.filter.grep_char
+        cm.output_line_char_nb_max = mission.output_line_char_nb_max
+        cm.print_encoding_as_ascii = 1 if mission.print_encoding_as_ascii else 0
+        if mission.sb_table is not None:
+            for i, v in enumerate(mission.sb_table):
+                cm.sb_table[i] = v
+        self._h = L.sx_scanner_state_new(C.byref(cm), device)
+        if not self._h:
+            _raise_last()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().sx_scanner_state_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- ScannerState fields -----------------------------------------------------------------
+    @property
+    def consumed_bytes(self) -> int:
+        return load_library().sx_scanner_state_consumed_bytes(self._h)
+
+    @property
+    def last_run_str_was_printed_and_is_maybe_cut_str(self) -> bool:
+        return bool(load_library().sx_scanner_state_maybe_cut(self._h))
+
+    @property
+    def last_scan_run_leftover(self) -> bytes:
+        p = C.POINTER(C.c_uint8)()
+        n = load_library().sx_scanner_state_leftover(self._h, C.byref(p))
+        return C.string_at(p, n) if n else b""
+
+    @property
+    def last_stats(self) -> ScanStats:
+        st = ScanStats()
+        load_library().sx_scanner_state_last_stats(self._h, C.byref(st))
+        return st
+
+    # -- scanning ------------------------------------------------------------------------------
+    def _collect(self, fc, file_id) -> FindingCollection:
+        L = load_library()
+        if not fc:
+            _raise_last()
+        n = L.sx_fc_len(fc)
+        arr = L.sx_fc_data(fc)
+        v = []
+        m = self.mission
+        for i in range(n):
+            f = arr[i]
+            v.append(Finding(f.position, Precision(f.precision), C.string_at(f.s, f.s_len), bool(f.completes_previous),
+                             m, None if f.input_file_id < 0 else f.input_file_id, f.in_start, f.in_len))
+        out = FindingCollection(v, L.sx_fc_first_byte_position(fc), bool(L.sx_fc_str_buf_overflow(fc)))
+        L.sx_fc_free(fc)
+        return out
+
+    def scan(self, input_buffer: bytes, is_last_input_buffer: bool, input_file_id: Optional[int] = None) -> FindingCollection:
+        """FindingCollection::from: one slice, exact reference semantics, executed on the GPU."""
+        L = load_library()
+        fid = -1 if input_file_id is None else input_file_id
+        b = bytes(input_buffer)
+        return self._collect(L.sx_finding_collection_from(self._h, fid, b, len(b), 1 if is_last_input_buffer else 0), fid)
+
+    def scan_stream(self, buf, is_last: bool = False, slice_len: int = 4096, input_file_id: Optional[int] = None,
+                    device_ptr: Optional[int] = None, length: Optional[int] = None, cuda_stream: int = 0,
+                    raw: bool = False):
+        """The fold of `scan` over slice_len pieces.  `buf`: bytes / numpy uint8 array (host) or, with
+        `device_ptr`+`length`, a device pointer on this state's device.  raw=True returns the C
+        collection handle wrapped in RawCollection (no per-finding Python objects)."""
+        L = load_library()
+        fid = -1 if input_file_id is None else input_file_id
+        keep = None
+        if device_ptr is not None:
+            p, n, isdev = C.c_void_p(device_ptr), int(length), 1
+        elif isinstance(buf, (bytes, bytearray)):
+            keep = bytes(buf)
+            p, n, isdev = C.cast(C.c_char_p(keep), C.c_void_p), len(keep), 0
+        else:  # numpy array or anything with ctypes.data / nbytes
+            p, n, isdev = C.c_void_p(buf.ctypes.data), int(buf.nbytes if length is None else length), 0
+        fc = L.sx_scan_stream(self._h, fid, p, n, slice_len, isdev, 1 if is_last else 0, C.c_void_p(cuda_stream))
+        del keep
+        if raw:
+            if not fc:
+                _raise_last()
+            return RawCollection(fc)
+        return self._collect(fc, fid)
+
+
+class RawCollection:
+    """Thin owner of a C sx_finding_collection (for large result sets / benchmarks)."""
+
+    def __init__(self, h):
+        self._h = h
+
+    def __len__(self):
+        return load_library().sx_fc_len(self._h)
+
+    def get(self, i: int):
+        f = load_library().sx_fc_get(self._h, i).contents
+        return (f.position, f.precision, C.string_at(f.s, f.s_len), bool(f.completes_previous))
+
+    def all(self):
+        L = load_library()
+        n = L.sx_fc_len(self._h)
+        arr = L.sx_fc_data(self._h)
+        return [(arr[i].position, arr[i].precision, C.string_at(arr[i].s, arr[i].s_len), bool(arr[i].completes_previous))
+                for i in range(n)]
+
+    def close(self):
+        if self._h:
+            load_library().sx_fc_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def merge(collections: Sequence[FindingCollection]) -> List[Finding]:
+    """itertools::kmerge over one slice batch (main.rs:133) in `impl PartialOrd for Finding` order."""
+    allf = [f for fc in collections for f in fc.v]
+    allf.sort(key=lambda f: (f.position, f.mission.mission_id))  # stable: keeps each mission's emission order
+    return allf

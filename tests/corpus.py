@@ -1,0 +1,146 @@
+"""Synthetic corpora shared by the CPU and GPU tests and by bench.py.
+
+`sx_mix_bytes` reproduces on the host (numpy) exactly what `sx_fill_random` writes on the device:
+byte i of the stream is byte (i & 7), little endian, of splitmix64(seed, i >> 3).
+`plant` overwrites a sparse, seeded set of positions with strings in the mission's encoding so
+that encodings which find nothing in random bytes (UTF-16/32) still have parity
+to check; placements straddle window and slice boundaries on purpose.
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+
+_M64 = (1 << 64) - 1
+
+
+def sx_mix_bytes(seed: int, offset: int, length: int) -> np.ndarray:
+    """uint8 array: bytes [offset, offset+length) of the stream with the given seed."""
+    w0 = offset >> 3
+    w1 = (offset + length + 7) >> 3
+    idx = np.arange(w0, w1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & _M64) + (idx + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    b = z.astype("<u8").view(np.uint8)
+    s = offset - (w0 << 3)
+    return b[s : s + length].copy()
+
+
+_WORDS = ["hello", "world", "straße", "naïve", "€uro", "日本語", "😀", "a", "xy", "longer-word-here", "ΑΒΓ", "привет",
+          "Հայերեն", "עברית", "العربية"]
+
+
+def encode_for(enc_id: int, s: str) -> bytes:
+    if enc_id == 2:
+        return s.encode("utf-16le")
+    if enc_id == 3:
+        return s.encode("utf-16be")
+    if enc_id == 5:
+        return s.encode("utf-32le")
+    if enc_id == 6:
+        return s.encode("utf-32be")
+    if enc_id == 4:
+        return s.encode("koi8-r", errors="replace")
+    if enc_id == 0:
+        return s.encode("ascii", errors="replace")
+    return s.encode("utf-8")
+
+
+def planted_strings(rng: random.Random, enc_id: int, n: int, q: int):
+    """Strings of the lengths SURVEY.md 8(d) lists, in the mission's encoding."""
+    out = []
+    alphabets = ["abcdefghijklmnopqrstuvwxyz0123456789 /-_.", "äöüßéèàç", "€日本語", "😀🎉", "բարևՀայ", "שלום", "مرحبا"]
+    for ln in (n - 1, n, n + 1, q - 1, q, q + 1, 2 * q - 1, 2 * q, 2 * q + 1, 5 * q):
+        if ln <= 0:
+            continue
+        for _ in range(2):
+            k = rng.random()
+            alpha = alphabets[0] if k < 0.4 else alphabets[0] + rng.choice(alphabets[1:])
+            if enc_id in (0,):
+                alpha = alphabets[0]
+            if enc_id == 4:
+                alpha = alphabets[0] + "абвгдежзийклмноп"
+            s = "".join(rng.choice(alpha) for _ in range(ln))
+            out.append(encode_for(enc_id, s))
+    return out
+
+
+def plant(buf: np.ndarray, seed: int, enc_id: int, n: int, q: int, slice_len: int = 4096, density: int = 1 << 16):
+    """Overwrite ~len/density positions (at least a dozen) with planted strings, in place."""
+    rng = random.Random(seed * 7919 + enc_id)
+    ln = len(buf)
+    strings = planted_strings(rng, enc_id, n, q)
+    W = 2 * q
+    count = max(12, ln // density)
+    for i in range(count):
+        s = strings[i % len(strings)]
+        if len(s) + 8 >= ln:
+            continue
+        kind = i % 6
+        base = rng.randrange(0, max(1, ln - len(s) - 8))
+        if kind == 1:  # straddle a window boundary
+            base = (base // W) * W + W - rng.randrange(1, max(2, min(len(s), W)))
+        elif kind == 2:  # straddle a slice boundary
+            base = (base // slice_len) * slice_len + slice_len - rng.randrange(1, max(2, min(len(s), slice_len)))
+        elif kind == 3:  # odd offset
+            base |= 1
+        elif kind == 4:  # right after a malformed byte
+            if base > 0:
+                buf[base - 1] = 0xFF
+        elif kind == 5:  # ends exactly at a malformed byte
+            if base + len(s) < ln:
+                buf[base + len(s)] = 0xC0
+        base = max(0, min(base, ln - len(s)))
+        buf[base : base + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    return buf
+
+
+def gen(rng: random.Random, kind: str, n: int, enc: int) -> bytes:
+    """Small adversarial buffers for differential fuzzing."""
+    if n <= 0:
+        return b""
+    if kind == "rand":
+        return bytes(rng.getrandbits(8) for _ in range(n))
+    if kind == "lowent":
+        alpha = rng.choice([b"ab\x00", b"abc \x00\xc3\xa9\xe2\x82\xac", b"a\x00", bytes(range(0x20, 0x7F)) + b"\x00\x01\xff",
+                            b"\xc3\xa9\xc3a\x80", b"a\x00b\x00\xd8\x00\xdc\x3d\xd8", b"\xe2\x82\xac\xf0\x9f\x98\x80a\x00"])
+        return bytes(rng.choice(alpha) for _ in range(n))
+    if kind == "text":
+        s = ""
+        while len(s) < n:
+            s += rng.choice(_WORDS) + rng.choice([" ", " ", "\n", "\x00", "", "\t"])
+        b = encode_for(enc, s)
+        off = rng.randrange(0, 4)
+        return (bytes(rng.getrandbits(8) for _ in range(off)) + b)[:n]
+    if kind == "runs":
+        out = bytearray()
+        while len(out) < n:
+            c = rng.choice([b"a", b"\xc3\xa9", b"\xe2\x82\xac", b"\xf0\x9f\x98\x80", b"a\x00", b"\x00a", b"\x00", b"\xff",
+                            b"\xc0", b" ", b"\xe9"])
+            out += c * rng.randrange(1, 300)
+        return bytes(out[:n])
+    out = bytearray()  # mixed
+    while len(out) < n:
+        out += gen(rng, rng.choice(["rand", "lowent", "text", "runs"]), rng.randrange(1, 400), enc)
+    return bytes(out[:n])
+
+
+KINDS = ["rand", "lowent", "text", "mixed", "runs"]
+LABELS = {0: "ascii", 1: "utf-8", 2: "utf-16le", 3: "utf-16be", 4: "koi8-r", 5: "utf-32le", 6: "utf-32be"}
+
+
+def random_mission(rng: random.Random, enc: int, M):
+    q = rng.choice([6, 7, 10, 16, 32, 64, 64, 100])
+    n = min(rng.choice([1, 2, 3, 4, 4, 6, 10, q]), q)
+    af = rng.choice([M.AF_DEFAULT, M.AF_ALL, M.AF_DEFAULT | M.AF_WHITESPACE])
+    ubf = rng.choice([M.UBF_COMMON, M.UBF_NONE, M.UBF_ALL_VALID, M.UBF_LATIN | M.UBF_ACCENTS, M.UBF_AFRICAN, M.UBF_ALL])
+    label = LABELS[enc]
+    if enc == 4:
+        label = rng.choice(["koi8-r", "windows-1251", "windows-1252", "ibm866", "iso-8859-5"])
+    if enc == 0 and rng.random() < 0.5:
+        ubf = M.UBF_NONE
+    return M.Mission.for_label(label, n, af, ubf, None, q, counter_offset=rng.choice([0, 10000]))

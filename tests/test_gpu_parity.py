@@ -1,0 +1,187 @@
+"""GPU parity tests: the CUDA scanner, called through the C ABI, against the CPU oracle.
+
+Bit-exact bar: identical (position, precision, text, completes) lists in identical order, and an
+identical ScannerState (leftover, cut flag, consumed bytes) after every call.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import corpus
+import reference_vectors as RV
+import stringsext_b200 as sx
+from helpers import M, O, oracle_state, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_findings(fc):
+    return [(f.position, int(f.position_precision), f.s, f.s_completes_previous_s) for f in fc.v]
+
+
+def oracle_findings(oc):
+    return [(f.position, f.precision, f.s, f.completes) for f in oc.v]
+
+
+def check_state(gs, os_):
+    assert gs.last_scan_run_leftover == os_.leftover
+    assert gs.last_run_str_was_printed_and_is_maybe_cut_str == os_.cut
+    assert gs.consumed_bytes == os_.consumed_bytes
+
+
+def test_library_is_the_cuda_one():
+    assert sx.device_count() >= 1
+    st = sx.ScannerState(sx.Mission.for_label("utf-8"))
+    st.scan_stream(b"hello world, this is a test\x00" * 100)
+    assert st.last_stats.kernel_launches >= 1
+
+
+@pytest.mark.parametrize("name,mission_factory,calls", [s for s in RV.SCENARIOS if "grep" not in s[0]],
+                         ids=lambda v: v.split(" ")[0] if isinstance(v, str) else None)
+def test_reference_unit_vectors(name, mission_factory, calls):
+    """scanner.rs:193-531, finding_collection.rs:431-502 through FindingCollection::from on the GPU."""
+    m = mission_factory()
+    gs, os_ = sx.ScannerState(m), oracle_state(m)
+    for c in calls:
+        fc = gs.scan(c["inp"], c["last"], 0)
+        got = gpu_findings(fc)
+        if c.get("findings") is not None:
+            assert [(p, pr, s) for p, pr, s, _ in got] == c["findings"]
+        if c.get("first") is not None:
+            assert fc.first_byte_position == c["first"]
+        assert not fc.str_buf_overflow
+        oc = os_.scan(c["inp"], c["last"], 0)
+        assert got == oracle_findings(oc)
+        check_state(gs, os_)
+        if c.get("consumed") is not None:
+            assert gs.consumed_bytes == c["consumed"]
+        if c.get("leftover") is not None:
+            assert gs.last_scan_run_leftover == c["leftover"]
+
+
+def test_unsupported_missions_fail_loudly():
+    with pytest.raises(sx.ScannerError) as e:
+        sx.ScannerState(RV.SCENARIOS[3][1]())  # grep_char = 42
+    assert e.value.code == 3
+
+
+def test_field_with_zeros():
+    factory, inp = RV.FIELD_WITH_ZEROS
+    assert len(sx.ScannerState(factory()).scan(inp, False, 0).v) != 1
+
+
+def test_cli_golden3(golden_dir):
+    """run-tests:33-41: -a None -u None over input1 input2 -> only BOM + newline."""
+    missions = [M.Mission.for_label(lbl, None, M.AF_NONE, M.UBF_NONE, None, 32, mission_id=i)
+                for i, lbl in enumerate(["UTF-8", "utf-16le", "utf-16be"])]
+    states = [sx.ScannerState(m) for m in missions]
+    out = bytearray(b"\xef\xbb\xbf")
+    for fid, name in enumerate(["input1", "input2"], start=1):
+        data = open(os.path.join(golden_dir, name), "rb").read()
+        fcs = [s.scan_stream(data, False, 4096, fid) for s in states]
+        for f in sx.merge(fcs):
+            out += f.print(2, 3, "x")
+    out += b"\n"
+    assert bytes(out) == open(os.path.join(golden_dir, "expected_output3"), "rb").read()
+
+
+@pytest.mark.parametrize("label,n,q,ubf", [
+    ("UTF-8", 4, 16, M.UBF_COMMON), ("utf-16le", 4, 16, M.UBF_COMMON), ("utf-16be", 10, 32, M.UBF_COMMON),
+    ("ascii", 4, 64, None), ("utf-8", 10, 64, M.UBF_ALL_VALID), ("utf-16le", 6, 64, M.UBF_ALL_VALID),
+    ("koi8-r", 6, 64, None),
+])
+def test_reference_fixture_files(golden_dir, label, n, q, ubf):
+    """The reference's functional-test inputs (text + EFI binary), multi-file stream with carry across files."""
+    m = M.Mission.for_label(label, n, None, ubf, None, q)
+    gs, os_ = sx.ScannerState(m), oracle_state(m)
+    for fid, name in enumerate(["input1", "input2"], start=1):
+        data = open(os.path.join(golden_dir, name), "rb").read()
+        got = gpu_findings(gs.scan_stream(data, False, 4096, fid))
+        exp = oracle_findings(os_.scan_stream(data, False, 4096, fid))
+        assert got == exp
+        check_state(gs, os_)
+
+
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+def test_differential_fuzz(enc):
+    rng = random.Random(4242 + enc)
+    for _ in range(40):
+        m = corpus.random_mission(rng, enc, M)
+        slice_len = rng.choice([4096, 4096, 4096, 1024, 256, 100, 33, 17, 8192])
+        gs, os_ = sx.ScannerState(m), oracle_state(m)
+        ncalls = rng.choice([1, 1, 2, 3])
+        for c in range(ncalls):
+            ln = rng.choice([0, 1, 2, 3, 5, 50, 500, 5000]) if rng.random() < 0.5 else rng.randrange(1, 70000)
+            buf = corpus.gen(rng, rng.choice(corpus.KINDS), ln, enc)
+            last = (c == ncalls - 1) and rng.random() < 0.3
+            got = gpu_findings(gs.scan_stream(buf, last, slice_len))
+            exp = oracle_findings(os_.scan_stream(buf, last, slice_len)) if ln else []
+            assert got == exp, (enc, m, slice_len, ln, last)
+            check_state(gs, os_)
+
+
+@pytest.mark.parametrize("label,n,size_mib,seed", [
+    ("ascii", 4, 64, 1),      # BASELINE config 1
+    ("utf-8", 10, 64, 2),     # config 2 at an oracle-friendly size
+    ("utf-16le", 10, 16, 3),  # config 3 (ubf African), planted corpus carries the parity
+    ("utf-16be", 10, 16, 3),
+    ("koi8-r", 6, 16, 5),     # config 5 member with heavy output
+    ("utf-32le", 6, 16, 5),   # extension
+])
+def test_baseline_configs_vs_oracle(label, n, size_mib, seed):
+    ubf = M.UBF_AFRICAN if label.startswith("utf-16") else None
+    m = M.Mission.for_label(label, n, ubf=ubf)
+    size = size_mib << 20
+    buf = corpus.sx_mix_bytes(seed, 0, size)
+    corpus.plant(buf, seed, m.encoding_id, n, 64)
+    gs, os_ = sx.ScannerState(m), oracle_state(m)
+    raw = gs.scan_stream(buf, False, 4096, raw=True)
+    got = raw.all()
+    exp = oracle_findings(os_.scan_stream(buf, False, 4096))
+    assert len(got) == len(exp)
+    assert got == exp
+    check_state(gs, os_)
+    assert len(exp) > 0
+
+
+def test_chained_calls_equal_one_call():
+    """State hand-off: one sx_scan_stream call == k chained calls cut at slice multiples (and at odd places)."""
+    m = M.Mission.for_label("utf-8", 4, ubf=M.UBF_ALL_VALID)
+    buf = corpus.sx_mix_bytes(9, 0, 1 << 20)
+    corpus.plant(buf, 9, 1, 4, 64, density=1 << 12)
+    one = gpu_findings(sx.ScannerState(m).scan_stream(buf, False, 4096))
+    gs = sx.ScannerState(m)
+    parts = []
+    cuts = [0, 4096 * 3, 4096 * 64, 4096 * 65, 4096 * 200, len(buf)]
+    for a, b in zip(cuts, cuts[1:]):
+        parts += gpu_findings(gs.scan_stream(buf[a:b], False, 4096))
+    assert parts == one
+    # cut at non-slice multiples: compare with the oracle run the same way (the slice grid restarts per call)
+    gs, os_ = sx.ScannerState(m), oracle_state(m)
+    cuts = [0, 1000, 1001, 5000, 70001, len(buf)]
+    for a, b in zip(cuts, cuts[1:]):
+        got = gpu_findings(gs.scan_stream(buf[a:b], False, 4096))
+        exp = oracle_findings(os_.scan_stream(buf[a:b], False, 4096))
+        assert got == exp
+        check_state(gs, os_)
+
+
+def test_device_resident_input_and_fill():
+    """Device-pointer entry + sx_fill_random reproduces corpus.sx_mix_bytes."""
+    import torch
+
+    n = (8 << 20) + 123
+    t = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    L = sx.load_library()
+    assert L.sx_fill_random(t.data_ptr(), n, 77, 0, 0, None) == 0
+    torch.cuda.synchronize()
+    host = t.cpu().numpy()
+    assert np.array_equal(host, corpus.sx_mix_bytes(77, 0, n))
+    m = M.Mission.for_label("utf-8", 6)
+    gs, os_ = sx.ScannerState(m), oracle_state(m)
+    got = gpu_findings(gs.scan_stream(None, False, 4096, device_ptr=t.data_ptr(), length=n))
+    exp = oracle_findings(os_.scan_stream(host, False, 4096))
+    assert got == exp and len(exp) > 100
+    check_state(gs, os_)
