@@ -46,9 +46,12 @@ struct ScanOut {
     FinalState* final_state;
 };
 
+// A tile is a run of `nwin_tile` consecutive windows (<= kTileBytes of contiguous input; exactly
+// 8 slices of 4096 B at the default geometry).
 struct TileCfg {
     long long ntiles;
-    uint32_t tile_slices, nwin_tile, tile_bytes, wpt;
+    long long total_windows;
+    uint32_t nwin_tile, wpt;
 };
 
 struct SmemLayout {
@@ -165,33 +168,26 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
     __syncthreads();
 }
 
-// Number of valid windows of tile `tile` (valid windows form a prefix of the tile's window slots).
-__device__ __forceinline__ uint32_t tile_valid_windows(const Geometry& geo, const TileCfg& cfg, long long tile) {
-    const int64_t first_slice = (int64_t)tile * cfg.tile_slices;
-    uint32_t n = 0;
-    for (uint32_t s = 0; s < cfg.tile_slices; ++s) {
-        const int64_t ss = (first_slice + s) * (int64_t)geo.slice_len;
-        if (ss >= geo.len) break;
-        const int64_t ls = (geo.len - ss) < (int64_t)geo.slice_len ? (geo.len - ss) : (int64_t)geo.slice_len;
-        n += (uint32_t)((ls + geo.W - 1) / geo.W);
-    }
-    return n;
-}
-
 template <class Dec>
 __device__ Carry tile_pass(const ScanParams& P, const ScanOut& O, const TileCfg& cfg, const Geometry& geo,
                            const SmemLayout& S, long long tile, bool full, Carry carry_in) {
     const uint32_t tid = threadIdx.x;
-    const int64_t lo = (int64_t)tile * cfg.tile_bytes;
-    const int64_t hi = (lo + cfg.tile_bytes) < P.len ? (lo + cfg.tile_bytes) : P.len;
     const GlobalSrc g{P.in, P.pend};
+    const int64_t w0 = (int64_t)tile * cfg.nwin_tile;
+    const uint32_t nvalid = (uint32_t)((cfg.total_windows - w0) < (long long)cfg.nwin_tile ? (cfg.total_windows - w0) : (long long)cfg.nwin_tile);
+    int64_t lo, hi;
+    {
+        WinGeom wa, wb;
+        geo.window(w0, wa);
+        geo.window(w0 + nvalid - 1, wb);
+        lo = wa.ws;
+        hi = wb.we;
+    }
 
     load_tile(S.data, P, lo, hi);
     __syncthreads();
 
     const SmemTile ts{S.data, lo, hi, g};
-    const int64_t w0 = (int64_t)tile * cfg.nwin_tile;
-    const uint32_t nvalid = tile_valid_windows(geo, cfg, tile);
     const bool last_tile = (tile == cfg.ntiles - 1);
 
     // ---- stage A: per-window summary under the null carry -------------------------------------
@@ -560,9 +556,8 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     if (len > 0 && !buf) { set_err(SX_ERR_ARGUMENT, "buf is NULL"); return fail; }
     const uint32_t q = ss->m.output_line_char_nb_max;
     const uint32_t W = 2 * q;
-    if (slice_len == 0 || slice_len > (size_t)kTileBytes) { set_err(SX_ERR_UNSUPPORTED, "slice_len must be in 1..32768"); return fail; }
+    if (slice_len == 0 || slice_len > 0x7FFFFFFFull) { set_err(SX_ERR_ARGUMENT, "slice_len must be in 1..2^31-1"); return fail; }
     const uint32_t wps = (uint32_t)((slice_len + W - 1) / W);
-    if (wps > (uint32_t)kMaxWin) { set_err(SX_ERR_UNSUPPORTED, "slice_len / (2*output_line_char_nb_max) exceeds 512 windows per slice"); return fail; }
     memset(&ss->stats, 0, sizeof ss->stats);
     sx_finding_collection* fc = new sx_finding_collection();
     fc->first_byte_position = ss->consumed;
@@ -605,11 +600,14 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     memcpy(P.sb_table, ss->m.sb_table, sizeof P.sb_table);
 
     TileCfg cfg;
-    cfg.tile_slices = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(kTileBytes / slice_len), (uint32_t)kMaxWin / wps));
-    cfg.tile_bytes = cfg.tile_slices * (uint32_t)slice_len;
-    cfg.nwin_tile = cfg.tile_slices * wps;
+    {
+        const long long full = (long long)(len / slice_len);
+        const size_t rest = len - (size_t)full * slice_len;
+        cfg.total_windows = full * wps + (long long)((rest + W - 1) / W);
+    }
+    cfg.nwin_tile = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)kMaxWin, (uint32_t)kTileBytes / W));
     cfg.wpt = (cfg.nwin_tile + kThreads - 1) / kThreads;
-    cfg.ntiles = (long long)((len + cfg.tile_bytes - 1) / cfg.tile_bytes);
+    cfg.ntiles = (cfg.total_windows + cfg.nwin_tile - 1) / cfg.nwin_tile;
     if (cfg.ntiles > 0xFFFFFFFFLL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const int grid = (int)std::min<long long>(cfg.ntiles, (long long)ss->num_sms * 2);
 
@@ -745,10 +743,6 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
 
 extern "C" sx_finding_collection* sx_finding_collection_from(sx_scanner_state* ss, int input_file_id, const uint8_t* buf,
                                                              size_t len, int is_last) {
-    if (len > (size_t)kTileBytes) {
-        set_err(SX_ERR_ARGUMENT, "sx_finding_collection_from takes one slice (<= 32768 bytes); use sx_scan_stream");
-        return nullptr;
-    }
     return sx_scan_stream(ss, input_file_id, buf, len, len ? len : 1, 0, is_last, nullptr);
 }
 
