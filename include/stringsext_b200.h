@@ -123,14 +123,26 @@ size_t sx_merge(const sx_finding_collection* const* fcs, size_t n, const sx_find
 /* Instrumentation of the most recent sx_scan_stream on this state (CUDA-event times of the
  * library's own kernels, measured on the stream they were launched on). */
 typedef struct {
-    float scan_kernel_ms;        /* sx_scan_kernel (the hot path) */
+    float scan_kernel_ms;        /* prefilter + list + exact kernels, first launch to last */
+    float prefilter_kernel_ms;   /* sx_prefilter_kernel: the one pass over every input byte (HBM bound) */
+    float list_kernels_ms;       /* sx_list_scan_kernel + sx_list_expand_kernel */
+    float exact_kernel_ms;       /* sx_exact_kernel: automaton over the listed windows */
     float materialize_kernel_ms; /* sx_materialize_kernel (finding text) */
     uint32_t kernel_launches;    /* launches of library kernels in the call */
-    uint32_t relaunches;         /* scan kernel re-runs caused by an output buffer that was too small */
+    uint32_t relaunches;         /* pipeline re-runs caused by an output buffer that was too small */
+    uint32_t prefilter_used;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t n_records, text_bytes;
+    uint64_t windows_total, windows_listed;
 } sx_scan_stats;
 void sx_scanner_state_last_stats(const sx_scanner_state*, sx_scan_stats* out);
+
+/* Tuning / test hooks.  The prefilter never changes results (tests compare both settings). */
+void sx_scanner_state_set_prefilter(sx_scanner_state*, int enabled);
+/* Copies the window list the prefilter built in the most recent call (ascending window indices,
+ * window = decoder_input_window of finding_collection.rs:120-131) into out[0..cap); returns the
+ * list length, 0 when the prefilter did not run. */
+size_t sx_scanner_state_last_window_list(const sx_scanner_state*, uint32_t* out, size_t cap);
 
 /* Test / benchmark support: fill a device buffer with the library's reproducible synthetic
  * corpus bytes (counter based; byte i depends on (seed, i) only; see bench.py). */

@@ -824,4 +824,148 @@ struct Geometry {
     }
 };
 
+
+// ------------------------------------------------------------------------------------------
+// Prefilter (kernel sx_prefilter_kernel): a conservative per-byte "could belong to a passing
+// char" flag G at 32-byte-block granularity of the byte value (top 3 bits), cheap enough for
+// SWAR.  A window is INTERESTING when a run of >= T good bytes (T = chars_min_nb * unit) can
+// exist in it or across its left boundary; only interesting windows, their two neighbours and
+// the first/last window of every 256-window tile are handed to the exact kernel.  See
+// DESIGN.md "Prefilter" for the proof that every other window emits nothing and does not
+// influence any carry.
+// ------------------------------------------------------------------------------------------
+enum : uint32_t { PF_BYTE = 0, PF_UTF8 = 1, PF_UNIT = 2 };
+constexpr uint32_t kPrefTileWin = 256;
+struct PrefCfg {
+    uint32_t enabled;
+    uint32_t family;  // PF_*
+    uint32_t blkA;    // bit k: bytes of block k (k = byte >> 5, k < 4) may be passing ASCII
+    uint32_t blkH;    // PF_BYTE: blocks 4..7 that may map to passing chars; PF_UTF8: lead blocks 6,7 that may pass;
+                      // PF_UNIT: blocks of the most significant unit byte that may belong to a passing char
+    uint32_t multi;   // PF_UTF8: 3/4-byte leads may pass (a continuation byte may follow a continuation byte)
+    uint32_t T;       // run threshold in bytes
+    uint32_t unit;    // PF_UNIT: 2 or 4
+    uint32_t hi_pos;  // PF_UNIT: offset of the most significant byte inside a unit
+};
+
+// Reference (byte-wise) definition of G; the SWAR kernel must produce exactly these flags.
+template <class S>
+SX_HD bool pref_good(const ScanParams& P, const PrefCfg& c, const S& src, int64_t i, int64_t ws, int64_t we) {
+    const uint32_t b = src.get(i);
+    if (c.family == PF_BYTE) return (((b < 0x80 ? c.blkA : c.blkH) >> (b >> 5)) & 1u) != 0;
+    if (c.family == PF_UTF8) {
+        if (b < 0x80) return ((c.blkA >> (b >> 5)) & 1u) != 0;
+        const bool is_cn = b < 0xC0;
+        if (!is_cn) {  // lead candidate: good when its block may pass and a continuation byte follows
+            if (!((c.blkH >> (b >> 5)) & 1u)) return false;
+            if (i + 1 >= we) return true;
+            const uint32_t nb = src.get(i + 1);
+            return nb >= 0x80 && nb < 0xC0;
+        }
+        if (i - 1 < ws) return true;
+        const uint32_t pb = src.get(i - 1);
+        if (pb >= 0xC0) return ((c.blkH >> (pb >> 5)) & 1u) != 0;
+        return c.multi && pb >= 0x80;
+    }
+    // PF_UNIT
+    int64_t rel = i - (int64_t)P.align;
+    int64_t k = rel >= 0 ? rel / (int64_t)c.unit : -((-rel + (int64_t)c.unit - 1) / (int64_t)c.unit);
+    const int64_t t = (int64_t)P.align + k * (int64_t)c.unit + (int64_t)c.hi_pos;
+    if (t < ws || t >= we) return true;
+    return ((c.blkH >> (src.get(t) >> 5)) & 1u) != 0;
+}
+
+struct PrefWin { uint32_t lead, trail, maxrun; };
+template <class S>
+SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& src, int64_t ws, int64_t we) {
+    PrefWin r{0, 0, 0};
+    uint32_t run = 0;
+    bool seen_bad = false;
+    for (int64_t i = ws; i < we; ++i) {
+        if (pref_good(P, c, src, i, ws, we)) {
+            run++;
+            if (run > r.maxrun) r.maxrun = run;
+        } else {
+            if (!seen_bad) { r.lead = run; seen_bad = true; }
+            run = 0;
+        }
+    }
+    if (!seen_bad) r.lead = run;
+    r.trail = run;
+    return r;
+}
+
+
+// Host-side: derive the prefilter configuration of a mission (used by the C ABI and by the
+// test harness, so both classify identically).
+inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned) {
+    PrefCfg c;
+    c.enabled = 0; c.family = PF_BYTE; c.blkA = 0; c.blkH = 0; c.multi = 0; c.T = P.n; c.unit = 1; c.hi_pos = 0;
+    for (uint32_t k = 0; k < 4; ++k) {
+        const uint64_t word = k < 2 ? P.af_lo : P.af_hi;
+        if ((word >> ((k & 1) * 32)) & 0xFFFFFFFFull) c.blkA |= 1u << k;
+    }
+    auto pass_lead = [&](uint32_t lead) { return ((P.ubf >> (lead & 0x3f)) & 1ull) != 0; };
+    auto pass_cp = [&](uint32_t cp) { return cp < 0x80 ? pass_filter(P, cp) : pass_lead(utf8_lead_of_cp(cp)); };
+    switch (P.enc) {
+    case ENC_XUD:
+        c.family = PF_BYTE;
+        c.blkH = pass_lead(0xEF) ? 0xF0u : 0u;
+        break;
+    case ENC_SB:
+        c.family = PF_BYTE;
+        for (uint32_t b = 0x80; b < 0x100; ++b) {
+            const uint32_t cp = P.sb_table[b - 0x80];
+            if (cp != 0 && pass_cp(cp)) c.blkH |= 1u << (b >> 5);
+        }
+        break;
+    case ENC_UTF8:
+        c.family = PF_UTF8;
+        if (P.ubf & 0xFFFFFFFFull) c.blkH |= 1u << 6;
+        if (P.ubf >> 32) { c.blkH |= 1u << 7; c.multi = 1; }
+        break;
+    case ENC_UTF16LE:
+    case ENC_UTF16BE: {
+        c.family = PF_UNIT; c.unit = 2; c.hi_pos = P.enc == ENC_UTF16LE ? 1 : 0;
+        const bool astral = ((P.ubf >> 48) & 0x1Full) != 0;
+        for (uint32_t hi = 0; hi < 0x100; ++hi) {
+            bool good = false;
+            if (hi >= 0xD8 && hi <= 0xDF) good = astral;
+            else for (uint32_t lo = 0; lo < 0x100 && !good; ++lo) good = pass_cp((hi << 8) | lo);
+            if (good) c.blkH |= 1u << (hi >> 5);
+        }
+        break;
+    }
+    case ENC_UTF32LE:
+    case ENC_UTF32BE:
+        c.family = PF_UNIT; c.unit = 4; c.hi_pos = P.enc == ENC_UTF32LE ? 3 : 0;
+        c.blkH = (P.af_lo | P.af_hi | P.ubf) ? 1u : 0u;
+        break;
+    }
+    c.T = P.n * c.unit;
+    if (c.T > P.W) c.T = P.W;  // a run covering a whole window is always interesting
+    c.enabled = (P.W % 16 == 0 && P.W <= 128 && P.slice_len % P.W == 0 && input_16b_aligned) ? 1u : 0u;
+    return c;
+}
+
+// Reference INTERESTING / E classification for window `w` of a stream (spec of the SWAR kernel).
+// forced: first and last window of the stream, windows shorter than W, the is_last final window.
+struct PrefPlan {
+    int64_t total_windows;
+};
+template <class S>
+SX_HD bool pref_interesting_ref(const ScanParams& P, const PrefCfg& c, const Geometry& geo, const S& src, int64_t w,
+                                int64_t total_windows) {
+    WinGeom g;
+    if (!geo.window(w, g)) return false;
+    if (w == 0 || w == total_windows - 1 || (uint32_t)(g.we - g.ws) < P.W || g.final_last) return true;
+    const PrefWin a = pref_window_ref(P, c, src, g.ws, g.we);
+    if (a.maxrun >= c.T) return true;
+    if ((w % kPrefTileWin) == 0) return a.lead >= 1;
+    WinGeom gp;
+    geo.window(w - 1, gp);
+    const PrefWin b = pref_window_ref(P, c, src, gp.ws, gp.we);
+    return b.trail + a.lead >= c.T;
+}
+
 }  // namespace sx

@@ -1,15 +1,14 @@
 // sx_scan.cu -- sm_100a kernels of the scanner hot path + the C ABI (include/stringsext_b200.h).
 //
-// sx_scan_kernel<Dec>: persistent CTAs, each owning a contiguous range of tiles of the input
-// stream (a tile = 8 reference slices of 4096 B at the default geometry, input.rs:22).  Per tile:
-//   stage 0  the tile is staged from HBM into shared memory in a 128-byte-swizzled layout (lane l
-//            reading 16-byte chunk c of window l is then bank-conflict free),
-//   stage A  one lane per window: decoder + SplitStr automaton under the null carry
-//            -> transfer-function descriptor (WinDesc, sx_core.cuh),
-//   stage B  carries are resolved across the tile (constant / accumulate / replay),
-//   stage C  windows that emit are counted, a block scan + one atomicAdd per tile reserves record
-//            and text space, and the records are written in stream order inside the tile.
-// sx_materialize_kernel: transcodes each record's input range to UTF-8 text.
+// sx_prefilter_kernel<FAMILY>  one streaming pass over the whole input (the HBM-bound kernel):
+//     tiles of 256 windows staged into swizzled shared memory, one lane per window, SWAR block
+//     classification -> 128-bit "good byte" mask -> INTERESTING flag; output: a bit mask of the
+//     windows the exact kernel has to look at (interesting windows, their neighbours, tile edges).
+// sx_list_scan_kernel / sx_list_expand_kernel  turn the per-tile masks into an ordered window list.
+// sx_exact_kernel<Dec>  one list entry per thread: decoder + SplitStr automaton (sx_core.cuh),
+//     transfer-function carry resolution along runs of adjacent windows, count / reserve (one
+//     atomicAdd per block) / write of the finding records in stream order.
+// sx_materialize_kernel  transcodes each record's input range to UTF-8 text.
 //
 // There is no CPU scanning path in this file: without a CUDA device every call fails.
 #include "../../include/stringsext_b200.h"
@@ -26,10 +25,8 @@
 
 namespace sx {
 
-constexpr int kThreads = 256;
-constexpr int kTileBytes = 32768;
-constexpr int kMaxWin = 512;  // windows per tile
-constexpr int kMaxWpt = kMaxWin / kThreads;
+constexpr int kThreads = 256;      // exact kernel: one list entry per thread
+constexpr int kPrefThreads = 256;  // prefilter kernel: one window per thread, 256 windows per tile
 
 struct FinalState {
     Carry carry;
@@ -41,73 +38,22 @@ struct ScanOut {
     Record* recs;
     unsigned long long rec_cap;
     unsigned long long text_cap;
-    uint2* tile_desc;              // per tile {first record, record count}
-    unsigned long long* counters;  // [0] records, [1] text bytes
+    uint2* block_desc;             // per exact-kernel block {first record, record count}
+    unsigned long long* counters;  // [0] records, [1] text bytes, [2] list entries
     FinalState* final_state;
 };
 
-// A tile is a run of `nwin_tile` consecutive windows (<= kTileBytes of contiguous input; exactly
-// 8 slices of 4096 B at the default geometry).
-struct TileCfg {
-    long long ntiles;
+// Work list of the exact kernel: the windows the prefilter kept, in stream order
+// (list == nullptr: every window, entry e is window e).
+struct ExactCfg {
+    const uint32_t* list;
+    const unsigned long long* ne_ptr;  // device: number of list entries (list != nullptr)
+    long long ne_static;               // list == nullptr
     long long total_windows;
-    uint32_t nwin_tile, wpt;
+    uint32_t in_aligned16;
 };
-
-struct SmemLayout {
-    uint8_t* data;               // kTileBytes
-    WinDesc* desc;               // kMaxWin
-    Carry* kin;                  // kMaxWin + 1
-    uint8_t* done;               // kMaxWin + 1
-    uint32_t* warp_a;            // 8
-    uint32_t* warp_b;            // 8
-    unsigned long long* bases;   // 2
-    int32_t* misc;               // [0] npend at the end of the tile's last window
-};
-constexpr size_t kSmemBytes =
-    kTileBytes + sizeof(WinDesc) * kMaxWin + sizeof(Carry) * (kMaxWin + 4) + (kMaxWin + 16) + 64 + 64 + 16 + 16;
-
-__device__ __forceinline__ SmemLayout carve(uint8_t* p) {
-    SmemLayout S;
-    S.data = p; p += kTileBytes;
-    S.desc = reinterpret_cast<WinDesc*>(p); p += sizeof(WinDesc) * kMaxWin;
-    S.kin = reinterpret_cast<Carry*>(p); p += sizeof(Carry) * (kMaxWin + 4);
-    S.warp_a = reinterpret_cast<uint32_t*>(p); p += 32;
-    S.warp_b = reinterpret_cast<uint32_t*>(p); p += 32;
-    S.bases = reinterpret_cast<unsigned long long*>(p); p += 16;
-    S.misc = reinterpret_cast<int32_t*>(p); p += 16;
-    S.done = p;
-    return S;
-}
 
 __device__ __forceinline__ uint32_t swz(uint32_t r) { return r ^ (((r >> 7) & 7u) << 4); }
-
-struct SmemTile {
-    const uint8_t* sm;
-    int64_t lo, hi;
-    GlobalSrc g;
-    __device__ __forceinline__ uint8_t get(int64_t off) const {
-        if (off >= lo && off < hi) return sm[swz((uint32_t)(off - lo))];
-        return g.get(off);
-    }
-    template <class F>
-    __device__ __forceinline__ void for_each_byte(int64_t ws, int64_t we, F&& f) const {
-        uint32_t r = (uint32_t)(ws - lo);
-        const uint32_t rend = (uint32_t)(we - lo);
-        while (r < rend) {
-            const uint32_t r16 = r & ~15u;
-            const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(r16));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            const uint32_t i0 = r - r16;
-            const uint32_t i1 = (rend - r16) < 16u ? (rend - r16) : 16u;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if ((uint32_t)i >= i0 && (uint32_t)i < i1) f((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu, lo + (int64_t)(r16 + i));
-            }
-            r = r16 + 16;
-        }
-    }
-};
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
@@ -117,26 +63,39 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     return r;
 }
 
-// Tile loader: coalesced 16-byte streaming loads, swizzled 16-byte shared stores.
-__device__ __forceinline__ void load_tile(uint8_t* sm, const ScanParams& P, int64_t lo, int64_t hi) {
-    const uint32_t nbytes = (uint32_t)(hi - lo);
-    const uint32_t nchunks = (nbytes + 15u) >> 4;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(P.in) + (uintptr_t)lo) & 15u) == 0;
-    for (uint32_t c = threadIdx.x; c < nchunks; c += kThreads) {
-        uint4 v;
-        if (aligned && (c + 1) * 16u <= nbytes) {
-            v = ldg_stream(reinterpret_cast<const uint4*>(P.in + lo) + c);
-        } else {
-            uint32_t w[4] = {0, 0, 0, 0};
-            for (uint32_t i = 0; i < 16; ++i) {
-                const uint32_t o = c * 16u + i;
-                if (o < nbytes) w[i >> 2] |= (uint32_t)P.in[lo + o] << ((i & 3) * 8);
+// Byte source of the exact kernel: the listed windows are sparse, so they are read straight from
+// global memory (L2) with 16-byte vector loads per lane.
+struct GlobalTile {
+    GlobalSrc g;
+    int64_t len;
+    bool aligned16;
+    __device__ __forceinline__ uint8_t get(int64_t off) const { return g.get(off); }
+    template <class F>
+    __device__ __forceinline__ void for_each_byte(int64_t ws, int64_t we, F&& f) const {
+        int64_t pos = ws;
+        while (pos < we) {
+            const int64_t r16 = pos & ~(int64_t)15;
+            uint32_t w[4];
+            if (aligned16 && r16 >= 0 && r16 + 16 <= len) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(g.in + r16));
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            } else {
+                w[0] = w[1] = w[2] = w[3] = 0;
+                for (int i = 0; i < 16; ++i) {
+                    const int64_t o = r16 + i;
+                    if (o >= ws && o < we) w[i >> 2] |= (uint32_t)g.get(o) << ((i & 3) * 8);
+                }
             }
-            v = make_uint4(w[0], w[1], w[2], w[3]);
+            const uint32_t i0 = (uint32_t)(pos - r16);
+            const uint32_t i1 = (we - r16) < 16 ? (uint32_t)(we - r16) : 16u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if ((uint32_t)i >= i0 && (uint32_t)i < i1) f((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu, r16 + i);
+            }
+            pos = r16 + 16;
         }
-        *reinterpret_cast<uint4*>(sm + swz(c * 16u)) = v;
     }
-}
+};
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     const uint32_t lane = threadIdx.x & 31;
@@ -168,61 +127,64 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
     __syncthreads();
 }
 
+struct ExactSmem {
+    WinDesc desc[kThreads];
+    Carry kin[kThreads + 1];
+    Carry kout[kThreads];
+    uint8_t in_known[kThreads + 1];
+    uint8_t out_done[kThreads];
+    uint32_t warp_a[8], warp_b[8];
+    unsigned long long bases[2];
+    int32_t last_npend;
+};
+
+__device__ __forceinline__ long long list_window(const ExactCfg& X, long long e) { return X.list ? (long long)X.list[e] : e; }
+
+// One pass over list entries [e0, e0 + nblk): summary, carry resolution and (full) emission.
+// Returns the carry out of the last entry.
 template <class Dec>
-__device__ Carry tile_pass(const ScanParams& P, const ScanOut& O, const TileCfg& cfg, const Geometry& geo,
-                           const SmemLayout& S, long long tile, bool full, Carry carry_in) {
-    const uint32_t tid = threadIdx.x;
+__device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const Geometry& geo, ExactSmem& S,
+                            long long NE, long long e0, uint32_t nblk, bool full, Carry carry_in, long long block_id) {
+    const uint32_t i = threadIdx.x;
     const GlobalSrc g{P.in, P.pend};
-    const int64_t w0 = (int64_t)tile * cfg.nwin_tile;
-    const uint32_t nvalid = (uint32_t)((cfg.total_windows - w0) < (long long)cfg.nwin_tile ? (cfg.total_windows - w0) : (long long)cfg.nwin_tile);
-    int64_t lo, hi;
-    {
-        WinGeom wa, wb;
-        geo.window(w0, wa);
-        geo.window(w0 + nvalid - 1, wb);
-        lo = wa.ws;
-        hi = wb.we;
-    }
+    const GlobalTile ts{g, P.len, X.in_aligned16 != 0};
+    const bool active = i < nblk;
+    long long w = -1;
+    bool adj = false, next_adj = false;
+    WinGeom wg;
+    WinDesc d;
+    d.type = WT_CONST; d.nrec = 0; d.ntext = 0; d.a = 0; d.t_out = 0; d.pad = 0; d.null_out = carry_none();
 
-    load_tile(S.data, P, lo, hi);
+    // ---- stage A: per-entry summary under the null carry ------------------------------------------
+    if (active) {
+        const long long e = e0 + i;
+        w = list_window(X, e);
+        adj = e > 0 && list_window(X, e - 1) == w - 1;
+        next_adj = e + 1 < NE && list_window(X, e + 1) == w + 1;
+        geo.window(w, wg);
+        WinResult r;
+        scan_window<Dec>(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
+        S.desc[i] = d;
+        if (!adj) { S.kin[i] = (w == 0) ? P.k0 : carry_none(); S.in_known[i] = 1; }
+        else if (i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
+        else S.in_known[i] = 0;
+        S.out_done[i] = 0;
+        if (i == nblk - 1) S.last_npend = r.npend_out;
+    }
+    __syncthreads();
+    if (active && d.type == WT_CONST) {
+        S.kout[i] = d.null_out;
+        S.out_done[i] = 1;
+        if (next_adj && i + 1 < nblk) { S.kin[i + 1] = d.null_out; S.in_known[i + 1] = 1; }
+    }
     __syncthreads();
 
-    const SmemTile ts{S.data, lo, hi, g};
-    const bool last_tile = (tile == cfg.ntiles - 1);
-
-    // ---- stage A: per-window summary under the null carry -------------------------------------
-    for (uint32_t k = 0; k < cfg.wpt; ++k) {
-        const uint32_t i = tid * cfg.wpt + k;
-        if (i < nvalid) {
-            WinGeom wg;
-            geo.window(w0 + i, wg);
-            WinResult r;
-            WinDesc d;
-            scan_window<Dec>(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
-            S.desc[i] = d;
-            if (d.type == WT_CONST) { S.kin[i + 1] = d.null_out; S.done[i + 1] = 1; }
-            else S.done[i + 1] = 0;
-            if (i == nvalid - 1) S.misc[0] = r.npend_out;
-        }
-    }
-    if (tid == 0) { S.kin[0] = carry_in; S.done[0] = 1; }
-    __syncthreads();
-
-    // ---- stage B: resolve the carries ----------------------------------------------------------
+    // ---- stage B: resolve the carries along runs of adjacent windows -------------------------------
     for (;;) {
-        uint32_t rdy = 0;
-        for (uint32_t k = 0; k < cfg.wpt; ++k) {
-            const uint32_t i = tid * cfg.wpt + k;
-            if (i < nvalid && !S.done[i + 1] && S.done[i]) rdy |= 1u << k;
-        }
+        const bool rdy = active && !S.out_done[i] && S.in_known[i];
         __syncthreads();
-        for (uint32_t k = 0; k < cfg.wpt; ++k) {
-            if (!((rdy >> k) & 1u)) continue;
-            const uint32_t i = tid * cfg.wpt + k;
+        if (rdy) {
             const Carry kin = S.kin[i];
-            const WinDesc d = S.desc[i];
-            WinGeom wg;
-            geo.window(w0 + i, wg);
             Carry out;
             if (kin.kind == K_UNKNOWN) out = kin;
             else if (d.type == WT_CASEB) out = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws));
@@ -231,115 +193,407 @@ __device__ Carry tile_pass(const ScanParams& P, const ScanOut& O, const TileCfg&
                 scan_window<Dec>(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, r, nullptr);
                 out = r.out;
             }
-            S.kin[i + 1] = out;
-            S.done[i + 1] = 1;
+            S.kout[i] = out;
+            S.out_done[i] = 1;
+            if (next_adj && i + 1 < nblk) { S.kin[i + 1] = out; S.in_known[i + 1] = 1; }
         }
-        if (!__syncthreads_or(rdy != 0)) break;
+        if (!__syncthreads_or(rdy)) break;
     }
-    const Carry carry_out = S.kin[nvalid];
+    const Carry carry_out = S.kout[nblk - 1];
     if (!full) {
         __syncthreads();
         return carry_out;
     }
 
-    // ---- stage C: count, reserve, write --------------------------------------------------------
-    uint32_t cr[kMaxWpt], ct[kMaxWpt];
-    uint32_t emit_mask = 0;
-    uint32_t sum_r = 0, sum_t = 0;
-    for (uint32_t k = 0; k < cfg.wpt; ++k) {
-        cr[k] = 0; ct[k] = 0;
-        const uint32_t i = tid * cfg.wpt + k;
-        if (i >= nvalid) continue;
-        const Carry kin = S.kin[i];
-        const WinDesc d = S.desc[i];
-        if (needs_emit(P, d, kin)) {
-            emit_mask |= 1u << k;
-            if (carry_is_null(kin) && d.nrec != 0xFFFFu) { cr[k] = d.nrec; ct[k] = d.ntext; }
+    // ---- stage C: count, reserve, write --------------------------------------------------------------
+    uint32_t cr = 0, ct = 0, xr = 0, xt = 0;
+    bool emit = false, ext = false;
+    Carry kin = carry_none(), kout = carry_none();
+    WinGeom xg;
+    if (active) {
+        kin = S.kin[i];
+        kout = S.kout[i];
+        emit = needs_emit(P, d, kin);
+        if (emit) {
+            if (carry_is_null(kin) && d.nrec != 0xFFFFu) { cr = d.nrec; ct = d.ntext; }
             else {
-                WinGeom wg;
-                geo.window(w0 + i, wg);
                 WinResult r;
                 scan_window<Dec>(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, r, nullptr);
-                cr[k] = r.nrec; ct[k] = r.ntext;
+                cr = r.nrec; ct = r.ntext;
             }
         }
-        sum_r += cr[k]; sum_t += ct[k];
+        // a "cut" carry out of a listed window reaches an unlisted successor: it may print a continuation
+        ext = kout.kind == K_C && !next_adj && (w + 1) < X.total_windows;
+        if (ext) {
+            geo.window(w + 1, xg);
+            WinResult r;
+            scan_window<Dec>(P, ts, g, xg, kout, MODE_COUNT, nullptr, 0, r, nullptr);
+            xr = r.nrec; xt = r.ntext;
+        }
     }
-    // the scanner's final leftover travels as one extra pseudo record at the very end of the stream
-    const bool owns_last = last_tile && nvalid > 0 && ((nvalid - 1) / cfg.wpt == tid);
-    const bool extra = owns_last && carry_out.kind == K_L && carry_out.k > 0;
-    if (extra) { sum_r += 1; sum_t += carry_out.out_bytes; }
-
+    const bool is_final = active && (e0 + i == NE - 1);
+    const bool extra = is_final && kout.kind == K_L && kout.k > 0;  // the scanner's final leftover as a pseudo record
+    uint32_t sum_r = cr + xr + (extra ? 1u : 0u), sum_t = ct + xt + (extra ? kout.out_bytes : 0u);
     uint32_t er, et, tr, tt;
     block_excl_scan2(sum_r, sum_t, S.warp_a, S.warp_b, er, et, tr, tt);
-    if (tid == 0) {
+    if (i == 0) {
         unsigned long long br = 0, bt = 0;
         if (tr) br = atomicAdd(&O.counters[0], (unsigned long long)tr);
         if (tt) bt = atomicAdd(&O.counters[1], (unsigned long long)tt);
         S.bases[0] = br;
         S.bases[1] = bt;
-        O.tile_desc[tile] = make_uint2((uint32_t)br, tr);
+        O.block_desc[block_id] = make_uint2((uint32_t)br, tr);
         if (br + tr > O.rec_cap || bt + tt > O.text_cap) O.final_state->overflow = 1;
-        if (last_tile) { O.final_state->carry = carry_out; O.final_state->npend = S.misc[0]; }
     }
     __syncthreads();
     const unsigned long long br = S.bases[0], bt = S.bases[1];
-    const bool fits = (br + tr <= O.rec_cap) && (bt + tt <= O.text_cap);
-    if (fits) {
+    if ((br + tr <= O.rec_cap) && (bt + tt <= O.text_cap)) {
         uint32_t ro = er, to = et;
-        for (uint32_t k = 0; k < cfg.wpt; ++k) {
-            if ((emit_mask >> k) & 1u) {
-                const uint32_t i = tid * cfg.wpt + k;
-                WinGeom wg;
-                geo.window(w0 + i, wg);
-                WinResult r;
-                scan_window<Dec>(P, ts, g, wg, S.kin[i], MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
-            }
-            ro += cr[k]; to += ct[k];
+        if (emit && cr) {
+            WinResult r;
+            scan_window<Dec>(P, ts, g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
         }
+        ro += cr; to += ct;
+        if (ext && xr) {
+            WinResult r;
+            scan_window<Dec>(P, ts, g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+        }
+        ro += xr; to += xt;
         if (extra) {
             Record r;
             r.position = 0;
-            r.in_start = P.len - (int64_t)carry_out.in_bytes;
-            r.in_len = carry_out.in_bytes - (uint32_t)S.misc[0];
-            r.text_len = carry_out.out_bytes;
+            r.in_start = P.len - (int64_t)kout.in_bytes;
+            r.in_len = kout.in_bytes - (uint32_t)S.last_npend;
+            r.text_len = kout.out_bytes;
             r.text_off = bt + to;
-            r.flags = RF_LEFTOVER | ((carry_out.flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u);
+            r.flags = RF_LEFTOVER | ((kout.flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u);
             r.precision = 0;
             O.recs[br + ro] = r;
         }
     }
+    if (is_final) { O.final_state->carry = kout; O.final_state->npend = S.last_npend; }
     __syncthreads();
     return carry_out;
 }
 
 template <class Dec>
 __global__ void __launch_bounds__(kThreads, 2)
-sx_scan_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const TileCfg cfg) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const SmemLayout S = carve(smem_raw);
+sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X) {
+    __shared__ ExactSmem S;
     Geometry geo;
     geo.init(P);
-    const long long per = (cfg.ntiles + gridDim.x - 1) / gridDim.x;
-    const long long t0 = (long long)blockIdx.x * per;
-    const long long t1 = (t0 + per) < cfg.ntiles ? (t0 + per) : cfg.ntiles;
-    if (t0 >= t1) return;
-    Carry c;
-    if (t0 == 0) c = P.k0;
-    else {
-        // Warm-up: find the carry at the range start by replaying preceding tiles in state-only mode
-        // from an unknown carry; almost always one tile suffices (it ends in a constant window).
-        long long back = 1;
+    const long long NE = X.list ? (long long)*X.ne_ptr : X.ne_static;
+    const long long e0 = (long long)blockIdx.x * kThreads;
+    if (e0 >= NE) return;
+    const uint32_t nblk = (uint32_t)((NE - e0) < (long long)kThreads ? (NE - e0) : (long long)kThreads);
+    Carry c = carry_none();
+    const bool first_adj = e0 > 0 && list_window(X, e0 - 1) == list_window(X, e0) - 1;
+    if (first_adj) {
+        // Warm-up: the block starts inside a run of adjacent windows.  Replay preceding entries in
+        // state-only mode; a non-adjacent entry or a constant window makes the carry known.
+        long long back = 8;
         for (;;) {
-            long long ts_ = t0 - back;
-            if (ts_ <= 0) { ts_ = 0; c = P.k0; }
-            else c = carry_unknown();
-            for (long long t = ts_; t < t0; ++t) c = tile_pass<Dec>(P, O, cfg, geo, S, t, false, c);
-            if (c.kind != K_UNKNOWN) break;
-            back *= 2;
+            long long es = e0 - back;
+            if (es < 0) es = 0;
+            c = carry_unknown();
+            for (long long e = es; e < e0; e += kThreads) {
+                const uint32_t n = (uint32_t)((e0 - e) < (long long)kThreads ? (e0 - e) : (long long)kThreads);
+                c = block_pass<Dec>(P, O, X, geo, S, NE, e, n, false, c, 0);
+            }
+            if (c.kind != K_UNKNOWN || es == 0) break;
+            back *= 4;
         }
     }
-    for (long long t = t0; t < t1; ++t) c = tile_pass<Dec>(P, O, cfg, geo, S, t, true, c);
+    block_pass<Dec>(P, O, X, geo, S, NE, e0, nblk, true, c, (long long)blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prefilter: one streaming pass over the input (HBM bound).  256 windows per tile, one lane per
+// window; each lane classifies its window's bytes with SWAR block tests, packs the "good byte"
+// flags into a 128-bit mask and decides INTERESTING from the mask (sx_core.cuh, pref_*_ref is the
+// byte-wise specification of exactly what is computed here).
+// ---------------------------------------------------------------------------------------------
+struct PrefOut {
+    uint32_t* emask;       // 8 words per tile: windows handed to the exact kernel
+    uint32_t* tile_count;  // listed windows per tile
+};
+
+struct PrefK {
+    // runtime block-function coefficients (0 or 0xFFFFFFFF): K[k] = block k may be good
+    uint32_t ka[4];  // bytes < 0x80, blocks 0..3
+    uint32_t kh[4];  // bytes >= 0x80, blocks 4..7 (PF_UTF8: lead blocks, only [2],[3] used)
+    uint32_t multi;  // PF_UTF8
+    uint32_t hi_mask[4];   // PF_UNIT: bit i of the 128-bit mask is the most significant byte of a unit
+    uint32_t edge_mask[4]; // PF_UNIT: bytes of units whose tested byte lies outside the window
+    uint32_t spread_left;  // PF_UNIT: spread the tested flag towards lower addresses (LE) or higher (BE)
+};
+
+#define LOP3_SEL 0xCA  // a ? b : c
+
+__device__ __forceinline__ uint32_t lop3_sel(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// g(b6,b5) with b6 at bit 7 of x1 and b5 at bit 7 of x2; k0..k3 = value for (b6,b5) = 00,01,10,11
+__device__ __forceinline__ uint32_t blk2(uint32_t x1, uint32_t x2, const uint32_t* k) {
+    return lop3_sel(x1, lop3_sel(x2, k[3], k[2]), lop3_sel(x2, k[1], k[0]));
+}
+__device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// 128-bit helpers on uint32_t m[4] (bit i of the mask = byte i of the window)
+__device__ __forceinline__ void shr128(const uint32_t* m, uint32_t s, uint32_t* o) {
+    const uint32_t wsft = s >> 5, bs = s & 31;
+    uint32_t t[8] = {m[0], m[1], m[2], m[3], 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // static indexing only
+            if ((uint32_t)j == wsft) { lo = t[k + j]; hi = t[k + j + 1]; }
+        }
+        o[k] = __funnelshift_r(lo, hi, bs);
+    }
+}
+__device__ __forceinline__ uint32_t ctz128(const uint32_t* m) {  // 128 when zero
+    if (m[0]) return __ffs(m[0]) - 1;
+    if (m[1]) return 32 + __ffs(m[1]) - 1;
+    if (m[2]) return 64 + __ffs(m[2]) - 1;
+    if (m[3]) return 96 + __ffs(m[3]) - 1;
+    return 128;
+}
+__device__ __forceinline__ uint32_t clz128(const uint32_t* m) {
+    if (m[3]) return __clz(m[3]);
+    if (m[2]) return 32 + __clz(m[2]);
+    if (m[1]) return 64 + __clz(m[1]);
+    if (m[0]) return 96 + __clz(m[0]);
+    return 128;
+}
+// exists a run of >= T set bits (1 <= T <= 128)
+__device__ __forceinline__ bool has_run128(const uint32_t* m, uint32_t T) {
+    uint32_t r[4] = {m[0], m[1], m[2], m[3]};
+    uint32_t have = 1;
+    while (have * 2 <= T) {
+        uint32_t s[4];
+        shr128(r, have, s);
+        r[0] &= s[0]; r[1] &= s[1]; r[2] &= s[2]; r[3] &= s[3];
+        have *= 2;
+    }
+    if (T > have) {
+        uint32_t s[4];
+        shr128(r, T - have, s);
+        r[0] &= s[0]; r[1] &= s[1]; r[2] &= s[2]; r[3] &= s[3];
+    }
+    return (r[0] | r[1] | r[2] | r[3]) != 0;
+}
+
+template <int FAMILY>
+__global__ void __launch_bounds__(kPrefThreads, 3)
+sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const __grid_constant__ PrefK K, const PrefOut O,
+                    long long total_windows, long long ntiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* sm = smem_raw;                                      // tile bytes, swizzled
+    uint32_t* s_trail = reinterpret_cast<uint32_t*>(sm + 32768);  // 256
+    uint32_t* s_iw = s_trail + 256;                               // 8 words of INTERESTING flags
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t W = P.W, nchunk = W >> 4;
+    const uint32_t tile_bytes = kPrefTileWin * W;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t lo = (int64_t)tile * tile_bytes;
+        const int64_t hi = (lo + tile_bytes) < P.len ? (lo + tile_bytes) : P.len;
+        // ---- stage the tile: coalesced 16-byte streaming loads, swizzled shared stores ------------------
+        {
+            const uint32_t nbytes = (uint32_t)(hi - lo);
+            const uint32_t nfull = nbytes >> 4;
+            const uint4* src = reinterpret_cast<const uint4*>(P.in + lo);
+            for (uint32_t c = tid; c < nfull; c += kPrefThreads) *reinterpret_cast<uint4*>(sm + swz(c * 16u)) = ldg_stream(src + c);
+            if ((nbytes & 15u) && tid == 0) {  // ragged stream tail: zero padded
+                uint32_t w4[4] = {0, 0, 0, 0};
+                for (uint32_t k = 0; k < (nbytes & 15u); ++k) w4[k >> 2] |= (uint32_t)P.in[lo + nfull * 16u + k] << ((k & 3) * 8);
+                *reinterpret_cast<uint4*>(sm + swz(nfull * 16u)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+        }
+        __syncthreads();
+
+        // ---- per-window classification -----------------------------------------------------------------
+        const long long w = tile * kPrefTileWin + tid;
+        const int64_t ws = lo + (int64_t)tid * W;
+        bool valid = w < total_windows;
+        uint32_t wlen = 0;
+        if (valid) wlen = (uint32_t)(((ws + W) < P.len ? (ws + W) : P.len) - ws);
+        uint32_t m[4] = {0, 0, 0, 0};
+        if (valid) {
+            uint32_t acc = 0;        // dp4a accumulator: 8 flags (two words) per byte lane, scaled by 0x80
+            uint32_t pA = 0, pL = 0, pC = 0, ppLC = 0xFFFFFFFFu;  // previous word's classes; left edge favourable
+            bool have_prev = false;
+            uint32_t widx = 0;       // index of the word being finalised
+            auto finalize = [&](uint32_t gflags) {
+                // gflags: bit 7 of byte j set = byte j of word `widx` is good
+                const uint32_t wt = (widx & 1) ? 0x80402010u : 0x08040201u;
+                acc = dp4a_u(gflags & 0x80808080u, wt, acc);
+                if (widx & 1) {  // two words done: one byte of mask
+                    const uint32_t byte8 = (acc >> 7) & 0xFFu;
+                    const uint32_t bi = widx >> 1;  // mask byte index 0..15
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        if ((bi >> 2) == (uint32_t)q4) m[q4] |= byte8 << ((bi & 3) * 8);
+                    acc = 0;
+                }
+                widx++;
+            };
+#pragma unroll 1
+            for (uint32_t c = 0; c < nchunk; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(tid * W + c * 16u));
+                const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t x = xs[j];
+                    const uint32_t x1 = x << 1, x2 = x << 2;
+                    if (FAMILY == PF_UTF8) {
+                        const uint32_t cn = x & ~x1;                                  // 10xxxxxx
+                        const uint32_t lp = x & x1 & lop3_sel(x2, K.kh[3], K.kh[2]);  // 11xxxxxx in a passing lead block
+                        const uint32_t ap = ~x & blk2(x1, x2, K.ka);
+                        if (have_prev) {
+                            const uint32_t ncn = __funnelshift_r(pC, cn, 8);   // byte i: Cn(i + 1)
+                            const uint32_t lcp = pL | (pC & K.multi);
+                            const uint32_t pl = __funnelshift_l(ppLC, lcp, 8);  // byte i: LC(i - 1)
+                            finalize(pA | (pL & ncn) | (pC & pl));
+                            ppLC = lcp;
+                        }
+                        pA = ap; pL = lp; pC = cn;
+                        have_prev = true;
+                    } else {
+                        const uint32_t f = lop3_sel(x, blk2(x1, x2, K.kh), blk2(x1, x2, K.ka));
+                        finalize(f);
+                    }
+                }
+            }
+            if (FAMILY == PF_UTF8) {  // flush the last word: right edge favourable
+                const uint32_t ncn = __funnelshift_r(pC, 0xFFFFFFFFu, 8);
+                const uint32_t pl = __funnelshift_l(ppLC, pL | (pC & K.multi), 8);
+                finalize(pA | (pL & ncn) | (pC & pl));
+            }
+            if (FAMILY == PF_UNIT) {
+                // keep the flag of each unit's most significant byte and spread it over the unit
+                uint32_t fh[4] = {m[0] & K.hi_mask[0], m[1] & K.hi_mask[1], m[2] & K.hi_mask[2], m[3] & K.hi_mask[3]};
+                uint32_t gm[4] = {fh[0], fh[1], fh[2], fh[3]};
+                for (uint32_t s = 1; s < C.unit; ++s) {
+                    uint32_t t[4];
+                    if (K.spread_left) shr128(fh, s, t);
+                    else {  // shift left by s
+                        t[0] = fh[0] << s;
+                        t[1] = __funnelshift_l(fh[0], fh[1], s);
+                        t[2] = __funnelshift_l(fh[1], fh[2], s);
+                        t[3] = __funnelshift_l(fh[2], fh[3], s);
+                    }
+                    gm[0] |= t[0]; gm[1] |= t[1]; gm[2] |= t[2]; gm[3] |= t[3];
+                }
+                m[0] = gm[0] | K.edge_mask[0]; m[1] = gm[1] | K.edge_mask[1];
+                m[2] = gm[2] | K.edge_mask[2]; m[3] = gm[3] | K.edge_mask[3];
+            }
+            // bits beyond the window (W < 128 or the ragged last window) are not bytes of the window
+            if (wlen < 128) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int lo_bit = q4 * 32;
+                    if ((int)wlen <= lo_bit) m[q4] = 0;
+                    else if ((int)wlen < lo_bit + 32) m[q4] &= (1u << (wlen - lo_bit)) - 1u;
+                }
+            }
+        }
+        uint32_t lead = 0, trail = 0;
+        bool longrun = false;
+        if (valid) {
+            uint32_t nm[4] = {~m[0], ~m[1], ~m[2], ~m[3]};  // bad bytes of the window
+            if (wlen < 128) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int lo_bit = q4 * 32;
+                    if ((int)wlen <= lo_bit) nm[q4] = 0;
+                    else if ((int)wlen < lo_bit + 32) nm[q4] &= (1u << (wlen - lo_bit)) - 1u;
+                }
+            }
+            if ((nm[0] | nm[1] | nm[2] | nm[3]) == 0) { lead = wlen; trail = wlen; }
+            else { lead = ctz128(nm); trail = wlen - 128u + clz128(nm); }
+            longrun = has_run128(m, C.T);
+        }
+        s_trail[tid] = trail;
+        __syncthreads();
+        bool interesting = false;
+        if (valid) {
+            const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
+            if (forced || longrun) interesting = true;
+            else if (tid == 0) interesting = lead >= 1;
+            else interesting = s_trail[tid - 1] + lead >= C.T;
+        }
+        const uint32_t ib = __ballot_sync(0xffffffffu, interesting);
+        if (lane == 0) s_iw[warp] = ib;
+        __syncthreads();
+        if (tid < 8) {
+            const uint32_t cur = s_iw[tid];
+            const uint32_t prv = tid > 0 ? s_iw[tid - 1] : 0u;
+            const uint32_t nxt = tid < 7 ? s_iw[tid + 1] : 0u;
+            uint32_t e = cur | (cur << 1) | (prv >> 31) | (cur >> 1) | (nxt << 31);
+            if (tid == 0) e |= 1u;
+            if (tid == 7) e |= 0x80000000u;
+            // drop slots beyond the stream
+            const long long base_w = tile * kPrefTileWin + (long long)tid * 32;
+            const long long remain = total_windows - base_w;
+            if (remain <= 0) e = 0;
+            else if (remain < 32) e &= (1u << remain) - 1u;
+            O.emask[tile * 8 + tid] = e;
+            uint32_t cnt = __popc(e);
+            cnt += __shfl_down_sync(0xffu, cnt, 4);
+            cnt += __shfl_down_sync(0xffu, cnt, 2);
+            cnt += __shfl_down_sync(0xffu, cnt, 1);
+            if (tid == 0) O.tile_count[tile] = cnt;
+        }
+        __syncthreads();
+    }
+}
+
+// exclusive scan of the per-tile counts (single block) -> tile offsets, total -> counters[2]
+__global__ void __launch_bounds__(1024) sx_list_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_off,
+                                                            long long ntiles, unsigned long long* counters) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t tid = threadIdx.x;
+    const long long per = (ntiles + 1023) / 1024;
+    const long long b = (long long)tid * per, e = (b + per) < ntiles ? (b + per) : ntiles;
+    unsigned long long s = 0;
+    for (long long t = b; t < e; ++t) s += tile_count[t];
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int k = 0; k < 1024; ++k) { const unsigned long long v = part[k]; part[k] = run; run += v; }
+        counters[2] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[tid];
+    for (long long t = b; t < e; ++t) { tile_off[t] = (uint32_t)run; run += tile_count[t]; }
+}
+
+// expand the per-tile bit masks into the ordered window list
+__global__ void __launch_bounds__(256) sx_list_expand_kernel(const uint32_t* __restrict__ emask, const uint32_t* __restrict__ tile_off,
+                                                             long long ntiles, uint32_t* __restrict__ list) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (tile, word)
+    if (idx >= ntiles * 8) return;
+    const long long tile = idx >> 3;
+    const uint32_t j = (uint32_t)(idx & 7);
+    uint32_t off = tile_off[tile];
+    for (uint32_t k = 0; k < j; ++k) off += __popc(emask[tile * 8 + k]);
+    uint32_t e = emask[idx];
+    const uint32_t base_w = (uint32_t)(tile * kPrefTileWin + j * 32);
+    while (e) {
+        const uint32_t b = __ffs(e) - 1;
+        e &= e - 1;
+        list[off++] = base_w + b;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -418,10 +672,15 @@ struct sx_scanner_state {
     uint8_t* d_in = nullptr; size_t d_in_cap = 0;
     Record* d_recs = nullptr; size_t rec_cap = 0;
     uint8_t* d_text = nullptr; size_t text_cap = 0;
-    uint2* d_tile = nullptr; size_t tile_cap = 0;
+    uint2* d_blocks = nullptr; size_t blocks_cap = 0;
+    uint32_t* d_emask = nullptr; size_t emask_cap = 0;
+    uint32_t* d_tcount = nullptr; size_t tcount_cap = 0;
+    uint32_t* d_toff = nullptr; size_t toff_cap = 0;
+    uint32_t* d_list = nullptr; size_t list_cap = 0;
+    int use_prefilter = 1;
     unsigned long long* d_counters = nullptr;
     FinalState* d_final = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int num_sms = 0;
     double rec_per_byte = 1.0 / 1024, text_per_byte = 1.0 / 64;
     sx_scan_stats stats;
@@ -471,9 +730,9 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
     cudaDeviceProp prop;
     if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete ss; return fail; }
     ss->num_sms = prop.multiProcessorCount;
-    bool ok = cuda_ok(cudaMalloc(&ss->d_counters, 2 * sizeof(unsigned long long)), "cudaMalloc") &&
+    bool ok = cuda_ok(cudaMalloc(&ss->d_counters, 4 * sizeof(unsigned long long)), "cudaMalloc") &&
               cuda_ok(cudaMalloc(&ss->d_final, sizeof(FinalState)), "cudaMalloc");
-    for (int i = 0; ok && i < 4; ++i) ok = cuda_ok(cudaEventCreate(&ss->ev[i]), "cudaEventCreate");
+    for (int i = 0; ok && i < 6; ++i) ok = cuda_ok(cudaEventCreate(&ss->ev[i]), "cudaEventCreate");
     if (!ok) { sx_scanner_state_free(ss); return fail; }
     return ss;
 }
@@ -481,7 +740,7 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
 void sx_scanner_state_free(sx_scanner_state* ss) {
     if (!ss) return;
     cudaSetDevice(ss->device);
-    cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_tile);
+    cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_blocks); cudaFree(ss->d_emask); cudaFree(ss->d_tcount); cudaFree(ss->d_toff); cudaFree(ss->d_list);
     cudaFree(ss->d_counters); cudaFree(ss->d_final);
     for (auto e : ss->ev) if (e) cudaEventDestroy(e);
     delete ss;
@@ -494,6 +753,17 @@ size_t sx_scanner_state_leftover(const sx_scanner_state* ss, const uint8_t** p) 
     return ss->leftover.size();
 }
 void sx_scanner_state_last_stats(const sx_scanner_state* ss, sx_scan_stats* out) { *out = ss->stats; }
+void sx_scanner_state_set_prefilter(sx_scanner_state* ss, int enabled) { ss->use_prefilter = enabled ? 1 : 0; }
+size_t sx_scanner_state_last_window_list(const sx_scanner_state* ss, uint32_t* out, size_t cap) {
+    if (!ss->stats.prefilter_used) return 0;
+    const size_t n = (size_t)ss->stats.windows_listed;
+    const size_t k = n < cap ? n : cap;
+    if (k && out) {
+        cudaSetDevice(ss->device);
+        if (cudaMemcpy(out, ss->d_list, k * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    }
+    return n;
+}
 
 size_t sx_fc_len(const sx_finding_collection* fc) { return fc->v.size(); }
 const sx_finding* sx_fc_get(const sx_finding_collection* fc, size_t i) { return &fc->v[i]; }
@@ -517,30 +787,56 @@ static bool grow(T** p, size_t* cap, size_t need) {
 }
 
 template <class Dec>
-static cudaError_t launch_scan(const ScanParams& P, const ScanOut& O, const TileCfg& cfg, int grid, cudaStream_t st) {
-    static thread_local bool attr_done[16] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 16 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(sx_scan_kernel<Dec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_done[dev] = true;
-    }
-    sx_scan_kernel<Dec><<<grid, kThreads, kSmemBytes, st>>>(P, O, cfg);
+static cudaError_t launch_exact(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st) {
+    sx_exact_kernel<Dec><<<grid, kThreads, 0, st>>>(P, O, X);
     return cudaGetLastError();
 }
 
-static cudaError_t launch_scan_enc(const ScanParams& P, const ScanOut& O, const TileCfg& cfg, int grid, cudaStream_t st) {
+static cudaError_t launch_exact_enc(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st) {
     switch (P.enc) {
-    case ENC_XUD: return launch_scan<DecXud>(P, O, cfg, grid, st);
-    case ENC_UTF8: return launch_scan<DecUtf8>(P, O, cfg, grid, st);
-    case ENC_UTF16LE: return launch_scan<DecUtf16<false>>(P, O, cfg, grid, st);
-    case ENC_UTF16BE: return launch_scan<DecUtf16<true>>(P, O, cfg, grid, st);
-    case ENC_SB: return launch_scan<DecSb>(P, O, cfg, grid, st);
-    case ENC_UTF32LE: return launch_scan<DecUtf32<false>>(P, O, cfg, grid, st);
-    case ENC_UTF32BE: return launch_scan<DecUtf32<true>>(P, O, cfg, grid, st);
+    case ENC_XUD: return launch_exact<DecXud>(P, O, X, grid, st);
+    case ENC_UTF8: return launch_exact<DecUtf8>(P, O, X, grid, st);
+    case ENC_UTF16LE: return launch_exact<DecUtf16<false>>(P, O, X, grid, st);
+    case ENC_UTF16BE: return launch_exact<DecUtf16<true>>(P, O, X, grid, st);
+    case ENC_SB: return launch_exact<DecSb>(P, O, X, grid, st);
+    case ENC_UTF32LE: return launch_exact<DecUtf32<false>>(P, O, X, grid, st);
+    case ENC_UTF32BE: return launch_exact<DecUtf32<true>>(P, O, X, grid, st);
     }
     return cudaErrorInvalidValue;
+}
+
+static PrefK make_pref_k(const ScanParams& P, const PrefCfg& c) {
+    PrefK k;
+    memset(&k, 0, sizeof k);
+    const uint32_t lowsrc = c.family == PF_UNIT ? c.blkH : c.blkA;
+    for (int b = 0; b < 4; ++b) {
+        k.ka[b] = ((lowsrc >> b) & 1u) ? 0xFFFFFFFFu : 0u;
+        k.kh[b] = ((c.blkH >> (4 + b)) & 1u) ? 0xFFFFFFFFu : 0u;
+    }
+    k.multi = c.multi ? 0xFFFFFFFFu : 0u;
+    if (c.family == PF_UNIT) {
+        // window starts are multiples of 16, so byte i of any window sits at (i - align) mod unit of its unit
+        k.spread_left = c.hi_pos != 0;  // little endian: the tested byte is the unit's last byte
+        for (uint32_t i = 0; i < 128; ++i) {
+            const int64_t rel = (int64_t)i - (int64_t)P.align;
+            const int64_t u0 = rel >= 0 ? (rel / c.unit) * c.unit : -(((-rel) + c.unit - 1) / c.unit) * (int64_t)c.unit;
+            const int64_t t = (int64_t)P.align + u0 + c.hi_pos;  // tested byte of the unit holding byte i
+            if (t == (int64_t)i) k.hi_mask[i >> 5] |= 1u << (i & 31);
+            if (t < 0 || t >= (int64_t)P.W) k.edge_mask[i >> 5] |= 1u << (i & 31);
+        }
+    }
+    return k;
+}
+
+static cudaError_t launch_prefilter(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
+                                    long long ntiles, int grid, cudaStream_t st) {
+    const size_t smem = 32768 + 1024 + 64;
+    switch (c.family) {
+    case PF_BYTE: sx_prefilter_kernel<PF_BYTE><<<grid, kPrefThreads, smem, st>>>(P, c, k, o, total_windows, ntiles); break;
+    case PF_UTF8: sx_prefilter_kernel<PF_UTF8><<<grid, kPrefThreads, smem, st>>>(P, c, k, o, total_windows, ntiles); break;
+    default: sx_prefilter_kernel<PF_UNIT><<<grid, kPrefThreads, smem, st>>>(P, c, k, o, total_windows, ntiles); break;
+    }
+    return cudaGetLastError();
 }
 
 static size_t utf8_char_count(const std::vector<uint8_t>& s) {
@@ -599,31 +895,64 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     else P.k0 = carry_none();
     memcpy(P.sb_table, ss->m.sb_table, sizeof P.sb_table);
 
-    TileCfg cfg;
+    long long total_windows;
     {
         const long long full = (long long)(len / slice_len);
         const size_t rest = len - (size_t)full * slice_len;
-        cfg.total_windows = full * wps + (long long)((rest + W - 1) / W);
+        total_windows = full * wps + (long long)((rest + W - 1) / W);
     }
-    cfg.nwin_tile = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)kMaxWin, (uint32_t)kTileBytes / W));
-    cfg.wpt = (cfg.nwin_tile + kThreads - 1) / kThreads;
-    cfg.ntiles = (cfg.total_windows + cfg.nwin_tile - 1) / cfg.nwin_tile;
-    if (cfg.ntiles > 0xFFFFFFFFLL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
-    const int grid = (int)std::min<long long>(cfg.ntiles, (long long)ss->num_sms * 2);
+    if (total_windows > 0xFFFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
+    const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
+    PrefCfg pc = make_pref_cfg(P, in_aligned16);
+    if (!ss->use_prefilter) pc.enabled = 0;
+    const long long ntiles = (total_windows + kPrefTileWin - 1) / kPrefTileWin;
+    const long long max_blocks = (total_windows + kThreads - 1) / kThreads;
 
-    if (!grow(&ss->d_tile, &ss->tile_cap, (size_t)cfg.ntiles)) return fail;
+    if (!grow(&ss->d_blocks, &ss->blocks_cap, (size_t)max_blocks)) return fail;
+    if (pc.enabled) {
+        if (!grow(&ss->d_emask, &ss->emask_cap, (size_t)ntiles * 8)) return fail;
+        if (!grow(&ss->d_tcount, &ss->tcount_cap, (size_t)ntiles)) return fail;
+        if (!grow(&ss->d_toff, &ss->toff_cap, (size_t)ntiles)) return fail;
+        if (!grow(&ss->d_list, &ss->list_cap, (size_t)total_windows)) return fail;
+    }
     size_t need_recs = (size_t)(len * ss->rec_per_byte) + 4096;
     size_t need_text = (size_t)(len * ss->text_per_byte) + 65536;
-    unsigned long long counters[2] = {0, 0};
+    unsigned long long counters[4] = {0, 0, 0, 0};
     FinalState fin;
     for (int attempt = 0;; ++attempt) {
         if (!grow(&ss->d_recs, &ss->rec_cap, need_recs)) return fail;
         if (!grow(&ss->d_text, &ss->text_cap, need_text)) return fail;
-        CK(cudaMemsetAsync(ss->d_counters, 0, 2 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ss->d_counters, 0, 4 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(ss->d_final, 0, sizeof(FinalState), st));
-        ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_tile, ss->d_counters, ss->d_final};
+        CK(cudaMemsetAsync(ss->d_blocks, 0, (size_t)max_blocks * sizeof(uint2), st));
+        ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final};
+        ExactCfg X;
+        X.total_windows = total_windows;
+        X.in_aligned16 = in_aligned16 ? 1u : 0u;
         CK(cudaEventRecord(ss->ev[0], st));
-        CK(launch_scan_enc(P, O, cfg, grid, st));
+        if (pc.enabled) {
+            const PrefK pk = make_pref_k(P, pc);
+            const PrefOut po{ss->d_emask, ss->d_tcount};
+            const int pgrid = (int)std::min<long long>(ntiles, (long long)ss->num_sms * 3);
+            CK(launch_prefilter(P, pc, pk, po, total_windows, ntiles, pgrid, st));
+            CK(cudaEventRecord(ss->ev[4], st));
+            sx_list_scan_kernel<<<1, 1024, 0, st>>>(ss->d_tcount, ss->d_toff, ntiles, ss->d_counters);
+            CK(cudaGetLastError());
+            sx_list_expand_kernel<<<(unsigned)((ntiles * 8 + 255) / 256), 256, 0, st>>>(ss->d_emask, ss->d_toff, ntiles, ss->d_list);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ss->ev[5], st));
+            ss->stats.kernel_launches += 3;
+            X.list = ss->d_list;
+            X.ne_ptr = ss->d_counters + 2;
+            X.ne_static = 0;
+        } else {
+            CK(cudaEventRecord(ss->ev[4], st));
+            CK(cudaEventRecord(ss->ev[5], st));
+            X.list = nullptr;
+            X.ne_ptr = nullptr;
+            X.ne_static = total_windows;
+        }
+        CK(launch_exact_enc(P, O, X, (unsigned)max_blocks, st));
         CK(cudaEventRecord(ss->ev[1], st));
         ss->stats.kernel_launches++;
         CK(cudaMemcpyAsync(counters, ss->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
@@ -635,6 +964,19 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         need_recs = (size_t)counters[0] + 1024;
         need_text = (size_t)counters[1] + 4096;
         ss->stats.relaunches++;
+    }
+    if (!pc.enabled) counters[2] = (unsigned long long)total_windows;
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ss->ev[0], ss->ev[4]);
+        ss->stats.prefilter_kernel_ms = pc.enabled ? ms : 0.f;
+        cudaEventElapsedTime(&ms, ss->ev[4], ss->ev[5]);
+        ss->stats.list_kernels_ms = pc.enabled ? ms : 0.f;
+        cudaEventElapsedTime(&ms, ss->ev[5], ss->ev[1]);
+        ss->stats.exact_kernel_ms = ms;
+        ss->stats.windows_total = (uint64_t)total_windows;
+        ss->stats.windows_listed = counters[2];
+        ss->stats.prefilter_used = pc.enabled;
     }
     {
         float ms = 0;
@@ -651,7 +993,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     // ---- text + download ---------------------------------------------------------------------------
     std::vector<Record> recs(nrec);
     std::vector<uint8_t> text(ntext);
-    std::vector<uint2> tiles((size_t)cfg.ntiles);
+    std::vector<uint2> tiles((size_t)((counters[2] + kThreads - 1) / kThreads));
     if (nrec) {
         const int mgrid = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ss->num_sms * 8);
         CK(cudaEventRecord(ss->ev[2], st));
@@ -661,7 +1003,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ss->stats.kernel_launches++;
         CK(cudaMemcpyAsync(recs.data(), ss->d_recs, nrec * sizeof(Record), cudaMemcpyDeviceToHost, st));
         if (ntext) CK(cudaMemcpyAsync(text.data(), ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(tiles.data(), ss->d_tile, tiles.size() * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(tiles.data(), ss->d_blocks, tiles.size() * sizeof(uint2), cudaMemcpyDeviceToHost, st));
         ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + tiles.size() * sizeof(uint2);
     }
     // bytes that stay inside the decoder: the last npend bytes of (old pend ++ buffer)

@@ -41,7 +41,8 @@ class Record(C.Structure):
 
 class EmulOut(C.Structure):
     _fields_ = [("recs", C.POINTER(Record)), ("nrecs", C.c_size_t), ("text", C.POINTER(C.c_uint8)),
-                ("ntext", C.c_size_t), ("final_carry", Carry), ("final_npend", C.c_int32), ("stats", C.c_uint64 * 8)]
+                ("ntext", C.c_size_t), ("final_carry", Carry), ("final_npend", C.c_int32), ("stats", C.c_uint64 * 8),
+                ("list", C.POINTER(C.c_uint32)), ("nlist", C.c_size_t)]
 
 
 _lib = None
@@ -56,7 +57,7 @@ def lib():
             os.makedirs(os.path.dirname(LIB), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", LIB, src])
         L = C.CDLL(LIB)
-        L.sx_emul_scan.argtypes = [C.POINTER(ScanParams), C.POINTER(EmulOut)]
+        L.sx_emul_scan.argtypes = [C.POINTER(ScanParams), C.c_int, C.POINTER(EmulOut)]
         L.sx_emul_sizeof_params.restype = C.c_size_t
         assert L.sx_emul_sizeof_params() == C.sizeof(ScanParams)
         _lib = L
@@ -70,8 +71,12 @@ def char_count(s: bytes) -> int:
 class EmulState:
     """ScannerState for the emulated product path."""
 
-    def __init__(self, m):
+    def __init__(self, m, use_pref=True):
         self.m = m
+        self.use_pref = use_pref
+        self.last_list = []
+        self.windows_total = 0
+        self.windows_listed = 0
         self.consumed = m.counter_offset
         self.leftover = b""
         self.cut = False
@@ -116,7 +121,7 @@ class EmulState:
             for i, v in enumerate(m.sb_table):
                 P.sb_table[i] = v
         out = EmulOut()
-        rc = lib().sx_emul_scan(C.byref(P), C.byref(out))
+        rc = lib().sx_emul_scan(C.byref(P), 1 if self.use_pref else 0, C.byref(out))
         assert rc == 0
         text = C.string_at(out.text, out.ntext) if out.ntext else b""
         findings = []
@@ -130,8 +135,11 @@ class EmulState:
                 new_left = t
                 continue
             findings.append((r.position, r.precision, t, bool(r.flags & 1)))
-        for i in range(8):
+        for i in range(7):
             self.stats[i] += out.stats[i]
+        self.stats[7] = out.stats[7]
+        self.last_list = [out.list[i] for i in range(out.nlist)] if out.nlist < 200000 else None
+        self.windows_listed += out.nlist
         fc = out.final_carry
         self.cut = fc.kind == 1
         self.leftover = new_left if fc.kind == 0 and fc.k > 0 else b""

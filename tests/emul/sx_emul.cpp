@@ -18,66 +18,48 @@ struct HostTile {
     }
 };
 
+// Mirrors the device pipeline: [prefilter -> E list] -> exact processing of the listed windows
+// (adjacent entries chain their carries, a non-adjacent entry starts from the null carry, a
+// window whose carry-out is "cut" extends into an unlisted successor).
 template <class Dec>
-static void run(const ScanParams& P, std::vector<Record>& recs, std::vector<uint8_t>& text, Carry* final_carry,
-                int32_t* final_npend, uint64_t* stats) {
+static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, std::vector<uint8_t>& text,
+                Carry* final_carry, int32_t* final_npend, uint64_t* stats, std::vector<uint32_t>& list) {
     GlobalSrc g{P.in, P.pend};
     HostTile ts{g};
     Geometry geo;
     geo.init(P);
-    const int64_t nslices = (P.len + P.slice_len - 1) / P.slice_len;
-    const int64_t nwin_max = nslices * geo.wps;
-    std::vector<WinDesc> desc;
-    std::vector<WinGeom> geos;
-    std::vector<int32_t> npend;
-    for (int64_t w = 0; w < nwin_max; ++w) {
-        WinGeom wg;
-        if (!geo.window(w, wg)) continue;
-        WinResult r;
-        WinDesc d;
-        scan_window<Dec>(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
-        desc.push_back(d);
-        geos.push_back(wg);
-        npend.push_back(r.npend_out);
-    }
-    const size_t nw = desc.size();
-    std::vector<Carry> kin(nw + 1);
-    kin[0] = P.k0;
-    for (size_t i = 0; i < nw; ++i) {
-        const WinDesc& d = desc[i];
-        if (d.type == WT_CONST) kin[i + 1] = d.null_out;
-        else if (d.type == WT_CASEB) kin[i + 1] = eval_caseb(P, d, kin[i], (uint32_t)(geos[i].we - geos[i].ws));
-        else {
-            WinResult r;
-            scan_window<Dec>(P, ts, g, geos[i], kin[i], MODE_STATE, nullptr, 0, r, nullptr);
-            kin[i + 1] = r.out;
-            stats[1]++;
+    const int64_t full = P.len / P.slice_len;
+    const int64_t rest = P.len - full * (int64_t)P.slice_len;
+    const int64_t total = full * geo.wps + (rest + P.W - 1) / P.W;
+    PrefCfg pc = make_pref_cfg(P, true);
+    if (!use_pref) pc.enabled = 0;
+    stats[7] = pc.enabled;
+    list.clear();
+    if (pc.enabled) {
+        std::vector<uint8_t> I((size_t)total), E((size_t)total);
+        for (int64_t w = 0; w < total; ++w) I[(size_t)w] = pref_interesting_ref(P, pc, geo, ts, w, total);
+        for (int64_t w = 0; w < total; ++w) {
+            bool e = I[(size_t)w] || (w > 0 && I[(size_t)w - 1]) || (w + 1 < total && I[(size_t)w + 1]);
+            const int64_t tw = w % kPrefTileWin;
+            // tile-edge windows are always listed; neighbours are only looked up inside the tile
+            if (tw == 0 || tw == (int64_t)kPrefTileWin - 1) e = true;
+            if (e) list.push_back((uint32_t)w);
         }
-        stats[0]++;
-        if (d.type == WT_CASEB) stats[2]++;
-        // self-check: the classification must agree with a replay
-        {
-            WinResult r;
-            scan_window<Dec>(P, ts, g, geos[i], kin[i], MODE_STATE, nullptr, 0, r, nullptr);
-            if (memcmp(&r.out, &kin[i + 1], sizeof(Carry)) != 0) {
-                stats[3]++;
-                kin[i + 1] = r.out;
-            }
-        }
+    } else {
+        for (int64_t w = 0; w < total; ++w) list.push_back((uint32_t)w);
     }
-    for (size_t i = 0; i < nw; ++i) {
-        const bool e = needs_emit(P, desc[i], kin[i]);
+    const size_t ne = list.size();
+    Carry kprev = carry_none();
+    int32_t last_npend = P.npend;
+    auto emit_window = [&](const WinGeom& wg, const Carry& kin, WinResult& rstate) {
         WinResult rc;
-        scan_window<Dec>(P, ts, g, geos[i], kin[i], MODE_COUNT, nullptr, 0, rc, nullptr);
-        if (!e) {
-            if (rc.nrec != 0) stats[4]++;  // emit rule missed a yielding window
-            continue;
-        }
-        if (carry_is_null(kin[i]) && desc[i].nrec != 0xFFFF && (rc.nrec != desc[i].nrec || rc.ntext != desc[i].ntext)) stats[5]++;
+        scan_window<Dec>(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, rc, nullptr);
+        rstate = rc;
+        if (rc.nrec == 0) return;
         const size_t base = recs.size();
         recs.resize(base + rc.nrec);
         WinResult rw;
-        scan_window<Dec>(P, ts, g, geos[i], kin[i], MODE_WRITE, recs.data() + base, text.size(), rw, nullptr);
+        scan_window<Dec>(P, ts, g, wg, kin, MODE_WRITE, recs.data() + base, text.size(), rw, nullptr);
         const size_t tb = text.size();
         text.resize(tb + rc.ntext + 8);
         for (size_t k = base; k < recs.size(); ++k) {
@@ -86,16 +68,50 @@ static void run(const ScanParams& P, std::vector<Record>& recs, std::vector<uint
             if (n != r.text_len) stats[6]++;
         }
         text.resize(tb + rc.ntext);
+    };
+    for (size_t e = 0; e < ne; ++e) {
+        const int64_t w = list[e];
+        WinGeom wg;
+        geo.window(w, wg);
+        const bool adjacent = e > 0 && (int64_t)list[e - 1] == w - 1;
+        const Carry kin = adjacent ? kprev : (w == 0 ? P.k0 : carry_none());
+        // summary under the null carry + classification self-check
+        WinResult r0;
+        WinDesc d;
+        scan_window<Dec>(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r0, &d);
+        WinResult rs;
+        scan_window<Dec>(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, rs, nullptr);
+        Carry kout;
+        if (d.type == WT_CONST) kout = d.null_out;
+        else if (d.type == WT_CASEB) { kout = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws)); stats[2]++; }
+        else { kout = rs.out; stats[1]++; }
+        stats[0]++;
+        if (memcmp(&rs.out, &kout, sizeof(Carry)) != 0) { stats[3]++; kout = rs.out; }
+        WinResult rc;
+        emit_window(wg, kin, rc);
+        if (!needs_emit(P, d, kin) && rc.nrec != 0) stats[4]++;
+        if (carry_is_null(kin) && d.nrec != 0xFFFF && (rc.nrec != d.nrec || rc.ntext != d.ntext)) stats[5]++;
+        last_npend = rs.npend_out;
+        kprev = kout;
+        // extension: a "cut" carry reaches an unlisted successor
+        const bool next_adjacent = e + 1 < ne && (int64_t)list[e + 1] == w + 1;
+        if (kout.kind == K_C && !next_adjacent && w + 1 < total) {
+            WinGeom xg;
+            geo.window(w + 1, xg);
+            WinResult rx;
+            emit_window(xg, kout, rx);
+            if (rx.out.kind == K_C) stats[3] += 1000;  // must never happen
+        }
     }
-    *final_carry = nw ? kin[nw] : P.k0;
-    *final_npend = nw ? npend[nw - 1] : P.npend;
+    *final_carry = ne ? kprev : P.k0;
+    *final_npend = last_npend;
     if (final_carry->kind == K_L && final_carry->k > 0) {
         Record r{};
         r.in_start = P.len - (int64_t)final_carry->in_bytes;
         r.in_len = final_carry->in_bytes - (uint32_t)*final_npend;
         r.text_len = final_carry->out_bytes;
         r.text_off = text.size();
-        r.flags = RF_LEFTOVER | ((final_carry->flags & CF_HOSTCARRY) ? RF_HOSTCARRY : 0);
+        r.flags = RF_LEFTOVER | ((final_carry->flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u);
         text.resize(text.size() + r.text_len + 8);
         transcode_range(P, g, r.in_start, r.in_len, text.data() + r.text_off);
         text.resize(text.size() - 8);
@@ -112,21 +128,24 @@ struct emul_out {
     Carry final_carry;
     int32_t final_npend;
     uint64_t stats[8];
+    uint32_t* list;
+    size_t nlist;
 };
 
 // Returns 0 on success.  `params` is a fully populated ScanParams (in = host pointer).
-int sx_emul_scan(const ScanParams* P, emul_out* out) {
+int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
+    std::vector<uint32_t> list;
     std::vector<Record> recs;
     std::vector<uint8_t> text;
     memset(out->stats, 0, sizeof out->stats);
     switch (P->enc) {
-    case ENC_XUD: run<DecXud>(*P, recs, text, &out->final_carry, &out->final_npend, out->stats); break;
-    case ENC_UTF8: run<DecUtf8>(*P, recs, text, &out->final_carry, &out->final_npend, out->stats); break;
-    case ENC_UTF16LE: run<DecUtf16<false>>(*P, recs, text, &out->final_carry, &out->final_npend, out->stats); break;
-    case ENC_UTF16BE: run<DecUtf16<true>>(*P, recs, text, &out->final_carry, &out->final_npend, out->stats); break;
-    case ENC_SB: run<DecSb>(*P, recs, text, &out->final_carry, &out->final_npend, out->stats); break;
-    case ENC_UTF32LE: run<DecUtf32<false>>(*P, recs, text, &out->final_carry, &out->final_npend, out->stats); break;
-    case ENC_UTF32BE: run<DecUtf32<true>>(*P, recs, text, &out->final_carry, &out->final_npend, out->stats); break;
+    case ENC_XUD: run<DecXud>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
+    case ENC_UTF8: run<DecUtf8>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
+    case ENC_UTF16LE: run<DecUtf16<false>>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
+    case ENC_UTF16BE: run<DecUtf16<true>>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
+    case ENC_SB: run<DecSb>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
+    case ENC_UTF32LE: run<DecUtf32<false>>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
+    case ENC_UTF32BE: run<DecUtf32<true>>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
     default: return 1;
     }
     out->nrecs = recs.size();
@@ -135,8 +154,11 @@ int sx_emul_scan(const ScanParams* P, emul_out* out) {
     out->ntext = text.size();
     out->text = (uint8_t*)malloc(text.size() + 1);
     memcpy(out->text, text.data(), text.size());
+    out->nlist = list.size();
+    out->list = (uint32_t*)malloc(sizeof(uint32_t) * (list.size() + 1));
+    memcpy(out->list, list.data(), sizeof(uint32_t) * list.size());
     return 0;
 }
-void sx_emul_free(emul_out* o) { free(o->recs); free(o->text); }
+void sx_emul_free(emul_out* o) { free(o->recs); free(o->text); free(o->list); }
 size_t sx_emul_sizeof_params() { return sizeof(ScanParams); }
 }

@@ -185,3 +185,62 @@ def test_device_resident_input_and_fill():
     exp = oracle_findings(os_.scan_stream(host, False, 4096))
     assert got == exp and len(exp) > 100
     check_state(gs, os_)
+
+
+# ---- prefilter ---------------------------------------------------------------------------------
+import sys as _sys
+
+_sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+
+
+@pytest.mark.parametrize("label,n,q,ubf,kind", [
+    ("utf-8", 10, 64, None, "rand"), ("utf-8", 6, 64, None, "rand"), ("utf-8", 10, 64, M.UBF_ALL_VALID, "mixed"),
+    ("ascii", 6, 64, None, "rand"), ("utf-16le", 10, 64, M.UBF_AFRICAN, "rand"), ("utf-16be", 6, 32, None, "text"),
+    ("utf-16le", 4, 64, M.UBF_ALL_VALID, "mixed"), ("utf-32le", 6, 64, None, "rand"), ("utf-32be", 4, 16, None, "text"),
+    ("koi8-r", 10, 64, M.UBF_NONE, "rand"), ("windows-1252", 8, 64, None, "mixed"), ("utf-8", 4, 8, None, "mixed"),
+])
+def test_prefilter_window_list_matches_spec(label, n, q, ubf, kind):
+    """The SWAR prefilter must list exactly the windows its byte-wise specification
+    (sx_core.cuh pref_*_ref, run on the CPU by tests/emul) lists."""
+    import emul
+
+    m = M.Mission.for_label(label, n, ubf=ubf, output_line_char_nb_max=q)
+    rng = random.Random(99)
+    size = (1 << 20) + 77
+    if kind == "rand":
+        buf = corpus.sx_mix_bytes(5, 0, size)
+        corpus.plant(buf, 5, m.encoding_id, n, q, density=1 << 13)
+        buf = buf.tobytes()
+    else:
+        buf = corpus.gen(rng, kind, size, m.encoding_id)
+    for pend_prefix in (b"", b"\xe2" if label == "utf-8" else b"\x41"):
+        gs = sx.ScannerState(m)
+        es = emul.EmulState(m, True)
+        if pend_prefix:  # shift the unit grid / leave a pending sequence from a previous call
+            gs.scan_stream(pend_prefix, False, 4096)
+            es.scan_stream(pend_prefix, False, 4096)
+        got = gpu_findings(gs.scan_stream(buf, False, 4096))
+        exp, _ = es.scan_stream(buf, False, 4096)
+        assert gs.last_stats.prefilter_used == 1 and es.stats[7] == 1
+        assert gs.last_window_list() == es.last_list
+        assert got == exp
+
+
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+def test_prefilter_on_off_identical(enc):
+    rng = random.Random(777 + enc)
+    for _ in range(12):
+        m = corpus.random_mission(rng, enc, M)
+        import dataclasses
+
+        q = rng.choice([8, 16, 32, 64, 64])
+        m = dataclasses.replace(m, output_line_char_nb_max=q, chars_min_nb=min(m.chars_min_nb, q))
+        buf = corpus.gen(rng, rng.choice(corpus.KINDS), rng.randrange(1, 300000), enc)
+        a, b = sx.ScannerState(m), sx.ScannerState(m)
+        b.set_prefilter(False)
+        ra = gpu_findings(a.scan_stream(buf, False, 4096))
+        rb = gpu_findings(b.scan_stream(buf, False, 4096))
+        assert a.last_stats.prefilter_used == 1 and b.last_stats.prefilter_used == 0
+        assert ra == rb
+        assert a.last_scan_run_leftover == b.last_scan_run_leftover
+        assert a.last_run_str_was_printed_and_is_maybe_cut_str == b.last_run_str_was_printed_and_is_maybe_cut_str
