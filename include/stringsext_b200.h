@@ -87,6 +87,8 @@ int sx_device_count(void);
  * output_line_char_nb_max < 6 (options.rs:33) or > 8192. */
 sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device);
 void sx_scanner_state_free(sx_scanner_state*);
+/* Back to the state ScannerState::new leaves (scanner.rs:73-88), keeping the device buffers. */
+void sx_scanner_state_reset(sx_scanner_state*);
 
 /* ScannerState fields (scanner.rs:55-68). */
 uint64_t sx_scanner_state_consumed_bytes(const sx_scanner_state*);

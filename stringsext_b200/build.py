@@ -1,19 +1,22 @@
-"""Build the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+"""Build the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU).
+
+The exact kernel is instantiated once per decoder in its own translation unit so the objects
+compile in parallel; everything is linked into stringsext_b200/libstringsext_b200.so.
+"""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libstringsext_b200.so")
-SOURCES = ["sx_scan.cu"]
-DEPS = ["sx_core.cuh", os.path.join("..", "..", "include", "stringsext_b200.h")]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
-]
+DEPS = ["sx_core.cuh", "sx_exact.cuh", "sx_scan.cu", "sx_exact_inst.cu", os.path.join("..", "..", "include", "stringsext_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+N_INST = 7
 
 
 def _nvcc() -> str:
@@ -27,16 +30,32 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + DEPS)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in DEPS)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if force or is_stale():
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
-        if verbose:
-            cmd.insert(1, "-Xptxas")
-            cmd.insert(2, "-v")
-        subprocess.check_call(cmd, cwd=CSRC)
+    if not (force or is_stale()):
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    jobs = [([nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, "sx_scan.cu"), "-o", os.path.join(OBJ, "sx_scan.o")])]
+    for i in range(N_INST):
+        jobs.append([nvcc, *NVCC_FLAGS, *extra, f"-DSX_INST={i}", "-c", os.path.join(CSRC, "sx_exact_inst.cu"), "-o",
+                     os.path.join(OBJ, f"sx_exact_{i}.o")])
+
+    def run(cmd):
+        r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        return r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        logs = list(ex.map(run, jobs))
+    if verbose:
+        print("\n".join(logs))
+    objs = [os.path.join(OBJ, "sx_scan.o")] + [os.path.join(OBJ, f"sx_exact_{i}.o") for i in range(N_INST)]
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB, *objs], cwd=CSRC)
     return LIB
 
 

@@ -1,0 +1,34 @@
+// sx_exact_inst.cu -- one instantiation of sx_exact_kernel<Dec> per translation unit (-DSX_INST=n).
+#include "sx_exact.cuh"
+
+namespace sx {
+#if SX_INST == 0
+#define SX_DEC DecXud
+#define SX_NAME launch_exact_xud
+#elif SX_INST == 1
+#define SX_DEC DecUtf8
+#define SX_NAME launch_exact_utf8
+#elif SX_INST == 2
+#define SX_DEC DecUtf16<false>
+#define SX_NAME launch_exact_utf16le
+#elif SX_INST == 3
+#define SX_DEC DecUtf16<true>
+#define SX_NAME launch_exact_utf16be
+#elif SX_INST == 4
+#define SX_DEC DecSb
+#define SX_NAME launch_exact_sb
+#elif SX_INST == 5
+#define SX_DEC DecUtf32<false>
+#define SX_NAME launch_exact_utf32le
+#elif SX_INST == 6
+#define SX_DEC DecUtf32<true>
+#define SX_NAME launch_exact_utf32be
+#else
+#error "SX_INST must be 0..6"
+#endif
+
+cudaError_t SX_NAME(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st) {
+    sx_exact_kernel<SX_DEC><<<grid, kThreads, 0, st>>>(P, O, X);
+    return cudaGetLastError();
+}
+}  // namespace sx

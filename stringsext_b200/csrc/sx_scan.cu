@@ -12,7 +12,7 @@
 //
 // There is no CPU scanning path in this file: without a CUDA device every call fails.
 #include "../../include/stringsext_b200.h"
-#include "sx_core.cuh"
+#include "sx_exact.cuh"
 
 #include <cuda_runtime.h>
 
@@ -24,288 +24,6 @@
 #include <vector>
 
 namespace sx {
-
-constexpr int kThreads = 256;      // exact kernel: one list entry per thread
-constexpr int kPrefThreads = 256;  // prefilter kernel: one window per thread, 256 windows per tile
-
-struct FinalState {
-    Carry carry;
-    int32_t npend;
-    uint32_t overflow;
-};
-
-struct ScanOut {
-    Record* recs;
-    unsigned long long rec_cap;
-    unsigned long long text_cap;
-    uint2* block_desc;             // per exact-kernel block {first record, record count}
-    unsigned long long* counters;  // [0] records, [1] text bytes, [2] list entries
-    FinalState* final_state;
-};
-
-// Work list of the exact kernel: the windows the prefilter kept, in stream order
-// (list == nullptr: every window, entry e is window e).
-struct ExactCfg {
-    const uint32_t* list;
-    const unsigned long long* ne_ptr;  // device: number of list entries (list != nullptr)
-    long long ne_static;               // list == nullptr
-    long long total_windows;
-    uint32_t in_aligned16;
-};
-
-__device__ __forceinline__ uint32_t swz(uint32_t r) { return r ^ (((r >> 7) & 7u) << 4); }
-
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-// Byte source of the exact kernel: the listed windows are sparse, so they are read straight from
-// global memory (L2) with 16-byte vector loads per lane.
-struct GlobalTile {
-    GlobalSrc g;
-    int64_t len;
-    bool aligned16;
-    __device__ __forceinline__ uint8_t get(int64_t off) const { return g.get(off); }
-    template <class F>
-    __device__ __forceinline__ void for_each_byte(int64_t ws, int64_t we, F&& f) const {
-        int64_t pos = ws;
-        while (pos < we) {
-            const int64_t r16 = pos & ~(int64_t)15;
-            uint32_t w[4];
-            if (aligned16 && r16 >= 0 && r16 + 16 <= len) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(g.in + r16));
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            } else {
-                w[0] = w[1] = w[2] = w[3] = 0;
-                for (int i = 0; i < 16; ++i) {
-                    const int64_t o = r16 + i;
-                    if (o >= ws && o < we) w[i >> 2] |= (uint32_t)g.get(o) << ((i & 3) * 8);
-                }
-            }
-            const uint32_t i0 = (uint32_t)(pos - r16);
-            const uint32_t i1 = (we - r16) < 16 ? (uint32_t)(we - r16) : 16u;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if ((uint32_t)i >= i0 && (uint32_t)i < i1) f((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu, r16 + i);
-            }
-            pos = r16 + 16;
-        }
-    }
-};
-
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-    const uint32_t lane = threadIdx.x & 31;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= (uint32_t)d) v += t;
-    }
-    return v;
-}
-
-// Exclusive block scan of two 32-bit values (thread order); also returns the block totals.
-__device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_t* wa, uint32_t* wb, uint32_t& ea,
-                                                 uint32_t& eb, uint32_t& ta, uint32_t& tb) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t ia = warp_incl_scan(a), ib = warp_incl_scan(b);
-    if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
-    __syncthreads();
-    uint32_t oa = 0, ob = 0;
-    ta = 0; tb = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-        const uint32_t xa = wa[w], xb = wb[w];
-        if ((uint32_t)w < warp) { oa += xa; ob += xb; }
-        ta += xa; tb += xb;
-    }
-    ea = oa + ia - a;
-    eb = ob + ib - b;
-    __syncthreads();
-}
-
-struct ExactSmem {
-    WinDesc desc[kThreads];
-    Carry kin[kThreads + 1];
-    Carry kout[kThreads];
-    uint8_t in_known[kThreads + 1];
-    uint8_t out_done[kThreads];
-    uint32_t warp_a[8], warp_b[8];
-    unsigned long long bases[2];
-    int32_t last_npend;
-};
-
-__device__ __forceinline__ long long list_window(const ExactCfg& X, long long e) { return X.list ? (long long)X.list[e] : e; }
-
-// One pass over list entries [e0, e0 + nblk): summary, carry resolution and (full) emission.
-// Returns the carry out of the last entry.
-template <class Dec>
-__device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const Geometry& geo, ExactSmem& S,
-                            long long NE, long long e0, uint32_t nblk, bool full, Carry carry_in, long long block_id) {
-    const uint32_t i = threadIdx.x;
-    const GlobalSrc g{P.in, P.pend};
-    const GlobalTile ts{g, P.len, X.in_aligned16 != 0};
-    const bool active = i < nblk;
-    long long w = -1;
-    bool adj = false, next_adj = false;
-    WinGeom wg;
-    WinDesc d;
-    d.type = WT_CONST; d.nrec = 0; d.ntext = 0; d.a = 0; d.t_out = 0; d.pad = 0; d.null_out = carry_none();
-
-    // ---- stage A: per-entry summary under the null carry ------------------------------------------
-    if (active) {
-        const long long e = e0 + i;
-        w = list_window(X, e);
-        adj = e > 0 && list_window(X, e - 1) == w - 1;
-        next_adj = e + 1 < NE && list_window(X, e + 1) == w + 1;
-        geo.window(w, wg);
-        WinResult r;
-        scan_window<Dec>(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
-        S.desc[i] = d;
-        if (!adj) { S.kin[i] = (w == 0) ? P.k0 : carry_none(); S.in_known[i] = 1; }
-        else if (i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
-        else S.in_known[i] = 0;
-        S.out_done[i] = 0;
-        if (i == nblk - 1) S.last_npend = r.npend_out;
-    }
-    __syncthreads();
-    if (active && d.type == WT_CONST) {
-        S.kout[i] = d.null_out;
-        S.out_done[i] = 1;
-        if (next_adj && i + 1 < nblk) { S.kin[i + 1] = d.null_out; S.in_known[i + 1] = 1; }
-    }
-    __syncthreads();
-
-    // ---- stage B: resolve the carries along runs of adjacent windows -------------------------------
-    for (;;) {
-        const bool rdy = active && !S.out_done[i] && S.in_known[i];
-        __syncthreads();
-        if (rdy) {
-            const Carry kin = S.kin[i];
-            Carry out;
-            if (kin.kind == K_UNKNOWN) out = kin;
-            else if (d.type == WT_CASEB) out = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws));
-            else {
-                WinResult r;
-                scan_window<Dec>(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, r, nullptr);
-                out = r.out;
-            }
-            S.kout[i] = out;
-            S.out_done[i] = 1;
-            if (next_adj && i + 1 < nblk) { S.kin[i + 1] = out; S.in_known[i + 1] = 1; }
-        }
-        if (!__syncthreads_or(rdy)) break;
-    }
-    const Carry carry_out = S.kout[nblk - 1];
-    if (!full) {
-        __syncthreads();
-        return carry_out;
-    }
-
-    // ---- stage C: count, reserve, write --------------------------------------------------------------
-    uint32_t cr = 0, ct = 0, xr = 0, xt = 0;
-    bool emit = false, ext = false;
-    Carry kin = carry_none(), kout = carry_none();
-    WinGeom xg;
-    if (active) {
-        kin = S.kin[i];
-        kout = S.kout[i];
-        emit = needs_emit(P, d, kin);
-        if (emit) {
-            if (carry_is_null(kin) && d.nrec != 0xFFFFu) { cr = d.nrec; ct = d.ntext; }
-            else {
-                WinResult r;
-                scan_window<Dec>(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, r, nullptr);
-                cr = r.nrec; ct = r.ntext;
-            }
-        }
-        // a "cut" carry out of a listed window reaches an unlisted successor: it may print a continuation
-        ext = kout.kind == K_C && !next_adj && (w + 1) < X.total_windows;
-        if (ext) {
-            geo.window(w + 1, xg);
-            WinResult r;
-            scan_window<Dec>(P, ts, g, xg, kout, MODE_COUNT, nullptr, 0, r, nullptr);
-            xr = r.nrec; xt = r.ntext;
-        }
-    }
-    const bool is_final = active && (e0 + i == NE - 1);
-    const bool extra = is_final && kout.kind == K_L && kout.k > 0;  // the scanner's final leftover as a pseudo record
-    uint32_t sum_r = cr + xr + (extra ? 1u : 0u), sum_t = ct + xt + (extra ? kout.out_bytes : 0u);
-    uint32_t er, et, tr, tt;
-    block_excl_scan2(sum_r, sum_t, S.warp_a, S.warp_b, er, et, tr, tt);
-    if (i == 0) {
-        unsigned long long br = 0, bt = 0;
-        if (tr) br = atomicAdd(&O.counters[0], (unsigned long long)tr);
-        if (tt) bt = atomicAdd(&O.counters[1], (unsigned long long)tt);
-        S.bases[0] = br;
-        S.bases[1] = bt;
-        O.block_desc[block_id] = make_uint2((uint32_t)br, tr);
-        if (br + tr > O.rec_cap || bt + tt > O.text_cap) O.final_state->overflow = 1;
-    }
-    __syncthreads();
-    const unsigned long long br = S.bases[0], bt = S.bases[1];
-    if ((br + tr <= O.rec_cap) && (bt + tt <= O.text_cap)) {
-        uint32_t ro = er, to = et;
-        if (emit && cr) {
-            WinResult r;
-            scan_window<Dec>(P, ts, g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
-        }
-        ro += cr; to += ct;
-        if (ext && xr) {
-            WinResult r;
-            scan_window<Dec>(P, ts, g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
-        }
-        ro += xr; to += xt;
-        if (extra) {
-            Record r;
-            r.position = 0;
-            r.in_start = P.len - (int64_t)kout.in_bytes;
-            r.in_len = kout.in_bytes - (uint32_t)S.last_npend;
-            r.text_len = kout.out_bytes;
-            r.text_off = bt + to;
-            r.flags = RF_LEFTOVER | ((kout.flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u);
-            r.precision = 0;
-            O.recs[br + ro] = r;
-        }
-    }
-    if (is_final) { O.final_state->carry = kout; O.final_state->npend = S.last_npend; }
-    __syncthreads();
-    return carry_out;
-}
-
-template <class Dec>
-__global__ void __launch_bounds__(kThreads, 2)
-sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X) {
-    __shared__ ExactSmem S;
-    Geometry geo;
-    geo.init(P);
-    const long long NE = X.list ? (long long)*X.ne_ptr : X.ne_static;
-    const long long e0 = (long long)blockIdx.x * kThreads;
-    if (e0 >= NE) return;
-    const uint32_t nblk = (uint32_t)((NE - e0) < (long long)kThreads ? (NE - e0) : (long long)kThreads);
-    Carry c = carry_none();
-    const bool first_adj = e0 > 0 && list_window(X, e0 - 1) == list_window(X, e0) - 1;
-    if (first_adj) {
-        // Warm-up: the block starts inside a run of adjacent windows.  Replay preceding entries in
-        // state-only mode; a non-adjacent entry or a constant window makes the carry known.
-        long long back = 8;
-        for (;;) {
-            long long es = e0 - back;
-            if (es < 0) es = 0;
-            c = carry_unknown();
-            for (long long e = es; e < e0; e += kThreads) {
-                const uint32_t n = (uint32_t)((e0 - e) < (long long)kThreads ? (e0 - e) : (long long)kThreads);
-                c = block_pass<Dec>(P, O, X, geo, S, NE, e, n, false, c, 0);
-            }
-            if (c.kind != K_UNKNOWN || es == 0) break;
-            back *= 4;
-        }
-    }
-    block_pass<Dec>(P, O, X, geo, S, NE, e0, nblk, true, c, (long long)blockIdx.x);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Prefilter: one streaming pass over the input (HBM bound).  256 windows per tile, one lane per
@@ -746,6 +464,13 @@ void sx_scanner_state_free(sx_scanner_state* ss) {
     delete ss;
 }
 
+void sx_scanner_state_reset(sx_scanner_state* ss) {
+    ss->consumed = ss->m.counter_offset;
+    ss->cut = false;
+    ss->leftover.clear();
+    ss->npend = 0;
+    memset(ss->pend, 0, sizeof ss->pend);
+}
 uint64_t sx_scanner_state_consumed_bytes(const sx_scanner_state* ss) { return ss->consumed; }
 int sx_scanner_state_maybe_cut(const sx_scanner_state* ss) { return ss->cut ? 1 : 0; }
 size_t sx_scanner_state_leftover(const sx_scanner_state* ss, const uint8_t** p) {
@@ -786,21 +511,15 @@ static bool grow(T** p, size_t* cap, size_t need) {
     return true;
 }
 
-template <class Dec>
-static cudaError_t launch_exact(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st) {
-    sx_exact_kernel<Dec><<<grid, kThreads, 0, st>>>(P, O, X);
-    return cudaGetLastError();
-}
-
 static cudaError_t launch_exact_enc(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st) {
     switch (P.enc) {
-    case ENC_XUD: return launch_exact<DecXud>(P, O, X, grid, st);
-    case ENC_UTF8: return launch_exact<DecUtf8>(P, O, X, grid, st);
-    case ENC_UTF16LE: return launch_exact<DecUtf16<false>>(P, O, X, grid, st);
-    case ENC_UTF16BE: return launch_exact<DecUtf16<true>>(P, O, X, grid, st);
-    case ENC_SB: return launch_exact<DecSb>(P, O, X, grid, st);
-    case ENC_UTF32LE: return launch_exact<DecUtf32<false>>(P, O, X, grid, st);
-    case ENC_UTF32BE: return launch_exact<DecUtf32<true>>(P, O, X, grid, st);
+    case ENC_XUD: return launch_exact_xud(P, O, X, grid, st);
+    case ENC_UTF8: return launch_exact_utf8(P, O, X, grid, st);
+    case ENC_UTF16LE: return launch_exact_utf16le(P, O, X, grid, st);
+    case ENC_UTF16BE: return launch_exact_utf16be(P, O, X, grid, st);
+    case ENC_SB: return launch_exact_sb(P, O, X, grid, st);
+    case ENC_UTF32LE: return launch_exact_utf32le(P, O, X, grid, st);
+    case ENC_UTF32BE: return launch_exact_utf32be(P, O, X, grid, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -103,6 +103,7 @@ def load_library():
     L.sx_scanner_state_new.restype = C.c_void_p
     L.sx_scanner_state_new.argtypes = [C.POINTER(_CMission), C.c_int]
     L.sx_scanner_state_free.argtypes = [C.c_void_p]
+    L.sx_scanner_state_reset.argtypes = [C.c_void_p]
     L.sx_scanner_state_consumed_bytes.restype = C.c_uint64
     L.sx_scanner_state_consumed_bytes.argtypes = [C.c_void_p]
     L.sx_scanner_state_maybe_cut.argtypes = [C.c_void_p]
@@ -147,7 +148,7 @@ def device_count() -> int:
 def exported_symbols() -> List[str]:
     """Entry points declared in include/stringsext_b200.h (used by the ABI load test)."""
     return [
-        "sx_device_count", "sx_scanner_state_new", "sx_scanner_state_free", "sx_scanner_state_consumed_bytes",
+        "sx_device_count", "sx_scanner_state_new", "sx_scanner_state_free", "sx_scanner_state_reset", "sx_scanner_state_consumed_bytes",
         "sx_scanner_state_maybe_cut", "sx_scanner_state_leftover", "sx_finding_collection_from", "sx_scan_stream",
         "sx_fc_len", "sx_fc_get", "sx_fc_data", "sx_fc_first_byte_position", "sx_fc_str_buf_overflow", "sx_fc_free",
         "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
@@ -249,6 +250,9 @@ class ScannerState:
         p = C.POINTER(C.c_uint8)()
         n = load_library().sx_scanner_state_leftover(self._h, C.byref(p))
         return C.string_at(p, n) if n else b""
+
+    def reset(self) -> None:
+        load_library().sx_scanner_state_reset(self._h)
 
     def set_prefilter(self, enabled: bool) -> None:
         load_library().sx_scanner_state_set_prefilter(self._h, 1 if enabled else 0)
