@@ -750,6 +750,51 @@ SX_HD Carry eval_caseb(const ScanParams& P, const WinDesc& d, const Carry& kin, 
     return carry_cut();
 }
 
+// Window / slice geometry (finding_collection.rs:124-131, input.rs:22).
+struct Geometry {
+    int64_t len;
+    uint32_t slice_len, W, wps;  // wps = windows per full slice
+    int32_t is_last;
+    SX_HD void init(const ScanParams& P) {
+        len = P.len; slice_len = P.slice_len; W = P.W; is_last = P.is_last;
+        wps = (slice_len + W - 1) / W;
+    }
+    // window index -> geometry; false when the window lies beyond the stream
+    SX_HD bool window(int64_t widx, WinGeom& g) const {
+        const int64_t s = widx / wps;
+        const int64_t j = widx - s * wps;
+        g.slice_start = s * (int64_t)slice_len;
+        if (g.slice_start >= len) return false;
+        g.slice_end = g.slice_start + slice_len < len ? g.slice_start + slice_len : len;
+        g.ws = g.slice_start + j * (int64_t)W;
+        if (g.ws >= g.slice_end) return false;
+        g.we = g.ws + W < g.slice_end ? g.ws + W : g.slice_end;
+        g.final_last = is_last && g.we == len;
+        return true;
+    }
+};
+
+// Carry into a listed window whose predecessor is NOT listed (prefilter: the predecessor holds no run
+// of >= T good bytes, so a definite breaker lies within its last T bytes and its carry-out does not
+// depend on its own carry-in): replay the predecessor's tail from the null carry.
+template <class Dec, class TileSrc>
+SX_HD Carry preroll_carry(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const Geometry& geo, int64_t w,
+                          uint32_t pre_bytes) {
+    WinGeom pg;
+    geo.window(w - 1, pg);
+    WinGeom rg = pg;
+    if ((int64_t)pre_bytes < pg.we - pg.ws) rg.ws = pg.we - (int64_t)pre_bytes;
+    rg.final_last = false;
+    WinResult r;
+    scan_window<Dec>(P, tsrc, g, rg, carry_none(), MODE_STATE, nullptr, 0, r, nullptr);
+    return r.out;
+}
+
+// A carry-out that can make an UNLISTED successor print something (DESIGN.md "Extension rule").
+SX_HD bool carry_needs_extension(const ScanParams& P, const Carry& k) {
+    return k.kind == K_C || (k.kind == K_L && k.k >= P.n);
+}
+
 // Does window `d` emit anything given its real carry-in?  (see DESIGN.md "Emit rule")
 SX_HD bool needs_emit(const ScanParams& P, const WinDesc& d, const Carry& kin) {
     if (d.nrec > 0) return true;
@@ -800,29 +845,6 @@ SX_HD uint32_t transcode_range(const ScanParams& P, const GlobalSrc& g, int64_t 
     return dp;
 }
 
-// Window / slice geometry (finding_collection.rs:124-131, input.rs:22).
-struct Geometry {
-    int64_t len;
-    uint32_t slice_len, W, wps;  // wps = windows per full slice
-    int32_t is_last;
-    SX_HD void init(const ScanParams& P) {
-        len = P.len; slice_len = P.slice_len; W = P.W; is_last = P.is_last;
-        wps = (slice_len + W - 1) / W;
-    }
-    // window index -> geometry; false when the window lies beyond the stream
-    SX_HD bool window(int64_t widx, WinGeom& g) const {
-        const int64_t s = widx / wps;
-        const int64_t j = widx - s * wps;
-        g.slice_start = s * (int64_t)slice_len;
-        if (g.slice_start >= len) return false;
-        g.slice_end = g.slice_start + slice_len < len ? g.slice_start + slice_len : len;
-        g.ws = g.slice_start + j * (int64_t)W;
-        if (g.ws >= g.slice_end) return false;
-        g.we = g.ws + W < g.slice_end ? g.ws + W : g.slice_end;
-        g.final_last = is_last && g.we == len;
-        return true;
-    }
-};
 
 
 // ------------------------------------------------------------------------------------------

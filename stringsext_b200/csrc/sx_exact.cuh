@@ -33,6 +33,7 @@ struct ExactCfg {
     long long ne_static;               // list == nullptr
     long long total_windows;
     uint32_t in_aligned16;
+    uint32_t pre_bytes;                // pre-roll length for entries whose predecessor window is not listed
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t r) { return r ^ (((r >> 7) & 7u) << 4); }
@@ -147,7 +148,10 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
         WinResult r;
         scan_window<Dec>(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
         S.desc[i] = d;
-        if (!adj) { S.kin[i] = (w == 0) ? P.k0 : carry_none(); S.in_known[i] = 1; }
+        if (!adj) {
+            S.kin[i] = (w == 0) ? P.k0 : preroll_carry<Dec>(P, ts, g, geo, w, X.pre_bytes);
+            S.in_known[i] = 1;
+        }
         else if (i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
         else S.in_known[i] = 0;
         S.out_done[i] = 0;
@@ -204,8 +208,9 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
                 cr = r.nrec; ct = r.ntext;
             }
         }
-        // a "cut" carry out of a listed window reaches an unlisted successor: it may print a continuation
-        ext = kout.kind == K_C && !next_adj && (w + 1) < X.total_windows;
+        // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an
+        // unlisted successor: that window may print a continuation / the leftover
+        ext = carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.total_windows;
         if (ext) {
             geo.window(w + 1, xg);
             WinResult r;

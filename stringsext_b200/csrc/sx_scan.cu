@@ -91,16 +91,30 @@ __device__ __forceinline__ uint32_t clz128(const uint32_t* m) {
     if (m[0]) return 96 + __clz(m[0]);
     return 128;
 }
-// exists a run of >= T set bits (1 <= T <= 128)
+template <int S>
+__device__ __forceinline__ void and_shr128_static(uint32_t* r) {  // r &= r >> S, S a power of two < 128
+    if (S < 32) {
+        r[0] &= __funnelshift_r(r[0], r[1], S);
+        r[1] &= __funnelshift_r(r[1], r[2], S);
+        r[2] &= __funnelshift_r(r[2], r[3], S);
+        r[3] &= r[3] >> S;
+    } else if (S == 32) {
+        r[0] &= r[1]; r[1] &= r[2]; r[2] &= r[3]; r[3] = 0;
+    } else {
+        r[0] &= r[2]; r[1] &= r[3]; r[2] = 0; r[3] = 0;
+    }
+}
+// exists a run of >= T set bits (1 <= T <= 128); T is warp-uniform
 __device__ __forceinline__ bool has_run128(const uint32_t* m, uint32_t T) {
     uint32_t r[4] = {m[0], m[1], m[2], m[3]};
     uint32_t have = 1;
-    while (have * 2 <= T) {
-        uint32_t s[4];
-        shr128(r, have, s);
-        r[0] &= s[0]; r[1] &= s[1]; r[2] &= s[2]; r[3] &= s[3];
-        have *= 2;
-    }
+    if (T >= 2) { and_shr128_static<1>(r); have = 2; }
+    if (T >= 4) { and_shr128_static<2>(r); have = 4; }
+    if (T >= 8) { and_shr128_static<4>(r); have = 8; }
+    if (T >= 16) { and_shr128_static<8>(r); have = 16; }
+    if (T >= 32) { and_shr128_static<16>(r); have = 32; }
+    if (T >= 64) { and_shr128_static<32>(r); have = 64; }
+    if (T >= 128) { and_shr128_static<64>(r); have = 128; }
     if (T > have) {
         uint32_t s[4];
         shr128(r, T - have, s);
@@ -130,10 +144,9 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             const uint32_t nfull = nbytes >> 4;
             const uint4* src = reinterpret_cast<const uint4*>(P.in + lo);
             for (uint32_t c = tid; c < nfull; c += kPrefThreads) *reinterpret_cast<uint4*>(sm + swz(c * 16u)) = ldg_stream(src + c);
-            if ((nbytes & 15u) && tid == 0) {  // ragged stream tail: zero padded
-                uint32_t w4[4] = {0, 0, 0, 0};
-                for (uint32_t k = 0; k < (nbytes & 15u); ++k) w4[k >> 2] |= (uint32_t)P.in[lo + nfull * 16u + k] << ((k & 3) * 8);
-                *reinterpret_cast<uint4*>(sm + swz(nfull * 16u)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            if ((nbytes & 15u) && tid < 16) {  // ragged stream tail: zero padded, byte stores
+                const uint32_t o = nfull * 16u + tid;
+                sm[swz(o)] = o < nbytes ? P.in[lo + o] : (uint8_t)0;
             }
         }
         __syncthreads();
@@ -146,70 +159,75 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         if (valid) wlen = (uint32_t)(((ws + W) < P.len ? (ws + W) : P.len) - ws);
         uint32_t m[4] = {0, 0, 0, 0};
         if (valid) {
-            uint32_t acc = 0;        // dp4a accumulator: 8 flags (two words) per byte lane, scaled by 0x80
-            uint32_t pA = 0, pL = 0, pC = 0, ppLC = 0xFFFFFFFFu;  // previous word's classes; left edge favourable
-            bool have_prev = false;
-            uint32_t widx = 0;       // index of the word being finalised
-            auto finalize = [&](uint32_t gflags) {
-                // gflags: bit 7 of byte j set = byte j of word `widx` is good
-                const uint32_t wt = (widx & 1) ? 0x80402010u : 0x08040201u;
-                acc = dp4a_u(gflags & 0x80808080u, wt, acc);
-                if (widx & 1) {  // two words done: one byte of mask
-                    const uint32_t byte8 = (acc >> 7) & 0xFFu;
-                    const uint32_t bi = widx >> 1;  // mask byte index 0..15
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4)
-                        if ((bi >> 2) == (uint32_t)q4) m[q4] |= byte8 << ((bi & 3) * 8);
-                    acc = 0;
+            // Fully unrolled over the (up to) 8 16-byte chunks of the window: all mask indices are static.
+            // acc[p] collects the flags of data words 2p and 2p+1 of the current 32-byte group (dp4a,
+            // flags sit at bit 7 of each byte, so acc[p] = (8 flags) << 7).
+            uint32_t acc[4] = {0, 0, 0, 0};
+            uint32_t pA = 0, pL = 0, pC = 0, ppLC = 0xFFFFFFFFu;  // PF_UTF8: classes of the word awaiting its right neighbour
+            auto put = [&](int widx, uint32_t gflags) {  // widx is a compile-time constant at every call site
+                const int k = widx & 7;
+                acc[k >> 1] = dp4a_u(gflags & 0x80808080u, (k & 1) ? 0x80402010u : 0x08040201u, acc[k >> 1]);
+                if (k == 7) {
+                    m[widx >> 3] = (acc[0] >> 7) | (acc[1] << 1) | (acc[2] << 9) | (acc[3] << 17);
+                    acc[0] = acc[1] = acc[2] = acc[3] = 0;
                 }
-                widx++;
             };
-#pragma unroll 1
-            for (uint32_t c = 0; c < nchunk; ++c) {
-                const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(tid * W + c * 16u));
-                const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t x = xs[j];
-                    const uint32_t x1 = x << 1, x2 = x << 2;
-                    if (FAMILY == PF_UTF8) {
-                        const uint32_t cn = x & ~x1;                                  // 10xxxxxx
-                        const uint32_t lp = x & x1 & lop3_sel(x2, K.kh[3], K.kh[2]);  // 11xxxxxx in a passing lead block
-                        const uint32_t ap = ~x & blk2(x1, x2, K.ka);
-                        if (have_prev) {
-                            const uint32_t ncn = __funnelshift_r(pC, cn, 8);   // byte i: Cn(i + 1)
-                            const uint32_t lcp = pL | (pC & K.multi);
-                            const uint32_t pl = __funnelshift_l(ppLC, lcp, 8);  // byte i: LC(i - 1)
-                            finalize(pA | (pL & ncn) | (pC & pl));
-                            ppLC = lcp;
+            for (int c = 0; c < 8; ++c) {
+                if ((uint32_t)c < nchunk) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(tid * W + c * 16u));
+                    const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t x = xs[j];
+                        const uint32_t x1 = x << 1, x2 = x << 2;
+                        if (FAMILY == PF_UTF8) {
+                            const uint32_t cn = x & ~x1;                                  // 10xxxxxx
+                            const uint32_t lp = x & x1 & lop3_sel(x2, K.kh[3], K.kh[2]);  // 11xxxxxx in a passing lead block
+                            const uint32_t ap = ~x & blk2(x1, x2, K.ka);
+                            if (c > 0 || j > 0) {
+                                const uint32_t ncn = __funnelshift_r(pC, cn, 8);    // byte i: Cn(i + 1)
+                                const uint32_t lcp = pL | (pC & K.multi);
+                                const uint32_t pl = __funnelshift_l(ppLC, lcp, 8);  // byte i: LC(i - 1)
+                                put(4 * c + j - 1, pA | (pL & ncn) | (pC & pl));
+                                ppLC = lcp;
+                            }
+                            pA = ap; pL = lp; pC = cn;
+                        } else {
+                            put(4 * c + j, lop3_sel(x, blk2(x1, x2, K.kh), blk2(x1, x2, K.ka)));
                         }
-                        pA = ap; pL = lp; pC = cn;
-                        have_prev = true;
-                    } else {
-                        const uint32_t f = lop3_sel(x, blk2(x1, x2, K.kh), blk2(x1, x2, K.ka));
-                        finalize(f);
+                    }
+                    if (FAMILY == PF_UTF8 && (uint32_t)c == nchunk - 1) {  // flush the last word: right edge favourable
+                        const uint32_t ncn = __funnelshift_r(pC, 0xFFFFFFFFu, 8);
+                        const uint32_t pl = __funnelshift_l(ppLC, pL | (pC & K.multi), 8);
+                        put(4 * c + 3, pA | (pL & ncn) | (pC & pl));
+                    }
+                    if ((c & 1) == 0 && (uint32_t)c == nchunk - 1) {  // odd number of chunks: half a mask word is pending
+                        m[c >> 1] = (acc[0] >> 7) | (acc[1] << 1);
                     }
                 }
-            }
-            if (FAMILY == PF_UTF8) {  // flush the last word: right edge favourable
-                const uint32_t ncn = __funnelshift_r(pC, 0xFFFFFFFFu, 8);
-                const uint32_t pl = __funnelshift_l(ppLC, pL | (pC & K.multi), 8);
-                finalize(pA | (pL & ncn) | (pC & pl));
             }
             if (FAMILY == PF_UNIT) {
                 // keep the flag of each unit's most significant byte and spread it over the unit
                 uint32_t fh[4] = {m[0] & K.hi_mask[0], m[1] & K.hi_mask[1], m[2] & K.hi_mask[2], m[3] & K.hi_mask[3]};
                 uint32_t gm[4] = {fh[0], fh[1], fh[2], fh[3]};
-                for (uint32_t s = 1; s < C.unit; ++s) {
-                    uint32_t t[4];
-                    if (K.spread_left) shr128(fh, s, t);
-                    else {  // shift left by s
-                        t[0] = fh[0] << s;
-                        t[1] = __funnelshift_l(fh[0], fh[1], s);
-                        t[2] = __funnelshift_l(fh[1], fh[2], s);
-                        t[3] = __funnelshift_l(fh[2], fh[3], s);
+#pragma unroll
+                for (int s = 1; s < 4; ++s) {
+                    if ((uint32_t)s < C.unit) {
+                        uint32_t t[4];
+                        if (K.spread_left) {
+                            t[0] = __funnelshift_r(fh[0], fh[1], s);
+                            t[1] = __funnelshift_r(fh[1], fh[2], s);
+                            t[2] = __funnelshift_r(fh[2], fh[3], s);
+                            t[3] = fh[3] >> s;
+                        } else {
+                            t[0] = fh[0] << s;
+                            t[1] = __funnelshift_l(fh[0], fh[1], s);
+                            t[2] = __funnelshift_l(fh[1], fh[2], s);
+                            t[3] = __funnelshift_l(fh[2], fh[3], s);
+                        }
+                        gm[0] |= t[0]; gm[1] |= t[1]; gm[2] |= t[2]; gm[3] |= t[3];
                     }
-                    gm[0] |= t[0]; gm[1] |= t[1]; gm[2] |= t[2]; gm[3] |= t[3];
                 }
                 m[0] = gm[0] | K.edge_mask[0]; m[1] = gm[1] | K.edge_mask[1];
                 m[2] = gm[2] | K.edge_mask[2]; m[3] = gm[3] | K.edge_mask[3];
@@ -254,11 +272,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         __syncthreads();
         if (tid < 8) {
             const uint32_t cur = s_iw[tid];
-            const uint32_t prv = tid > 0 ? s_iw[tid - 1] : 0u;
-            const uint32_t nxt = tid < 7 ? s_iw[tid + 1] : 0u;
-            uint32_t e = cur | (cur << 1) | (prv >> 31) | (cur >> 1) | (nxt << 31);
-            if (tid == 0) e |= 1u;
-            if (tid == 7) e |= 0x80000000u;
+            uint32_t e = cur;
             // drop slots beyond the stream
             const long long base_w = tile * kPrefTileWin + (long long)tid * 32;
             const long long remain = total_windows - base_w;
@@ -648,6 +662,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ExactCfg X;
         X.total_windows = total_windows;
         X.in_aligned16 = in_aligned16 ? 1u : 0u;
+        X.pre_bytes = pc.T + 3 + pc.unit;
         CK(cudaEventRecord(ss->ev[0], st));
         if (pc.enabled) {
             const PrefK pk = make_pref_k(P, pc);

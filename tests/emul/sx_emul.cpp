@@ -36,15 +36,8 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
     stats[7] = pc.enabled;
     list.clear();
     if (pc.enabled) {
-        std::vector<uint8_t> I((size_t)total), E((size_t)total);
-        for (int64_t w = 0; w < total; ++w) I[(size_t)w] = pref_interesting_ref(P, pc, geo, ts, w, total);
-        for (int64_t w = 0; w < total; ++w) {
-            bool e = I[(size_t)w] || (w > 0 && I[(size_t)w - 1]) || (w + 1 < total && I[(size_t)w + 1]);
-            const int64_t tw = w % kPrefTileWin;
-            // tile-edge windows are always listed; neighbours are only looked up inside the tile
-            if (tw == 0 || tw == (int64_t)kPrefTileWin - 1) e = true;
-            if (e) list.push_back((uint32_t)w);
-        }
+        for (int64_t w = 0; w < total; ++w)
+            if (pref_interesting_ref(P, pc, geo, ts, w, total)) list.push_back((uint32_t)w);
     } else {
         for (int64_t w = 0; w < total; ++w) list.push_back((uint32_t)w);
     }
@@ -74,7 +67,8 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         WinGeom wg;
         geo.window(w, wg);
         const bool adjacent = e > 0 && (int64_t)list[e - 1] == w - 1;
-        const Carry kin = adjacent ? kprev : (w == 0 ? P.k0 : carry_none());
+        const uint32_t pre_bytes = pc.T + 3 + pc.unit;
+        const Carry kin = adjacent ? kprev : (w == 0 ? P.k0 : preroll_carry<Dec>(P, ts, g, geo, w, pre_bytes));
         // summary under the null carry + classification self-check
         WinResult r0;
         WinDesc d;
@@ -95,12 +89,12 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         kprev = kout;
         // extension: a "cut" carry reaches an unlisted successor
         const bool next_adjacent = e + 1 < ne && (int64_t)list[e + 1] == w + 1;
-        if (kout.kind == K_C && !next_adjacent && w + 1 < total) {
+        if (carry_needs_extension(P, kout) && !next_adjacent && w + 1 < total) {
             WinGeom xg;
             geo.window(w + 1, xg);
             WinResult rx;
             emit_window(xg, kout, rx);
-            if (rx.out.kind == K_C) stats[3] += 1000;  // must never happen
+            if (carry_needs_extension(P, rx.out)) stats[3] += 1000;  // must never happen
         }
     }
     *final_carry = ne ? kprev : P.k0;
