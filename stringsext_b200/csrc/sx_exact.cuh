@@ -7,7 +7,7 @@
 
 namespace sx {
 
-constexpr int kThreads = 256;      // exact kernel: one list entry per thread
+constexpr int kThreads = 128;      // exact kernel: one list entry per thread
 constexpr int kPrefThreads = 256;  // prefilter kernel: one window per thread, 256 windows per tile
 
 struct FinalState {
@@ -53,29 +53,36 @@ struct GlobalTile {
     int64_t len;
     bool aligned16;
     __device__ __forceinline__ uint8_t get(int64_t off) const { return g.get(off); }
+    __device__ __forceinline__ uint4 load_chunk(int64_t r16, int64_t ws, int64_t we) const {
+        if (r16 >= we) return make_uint4(0, 0, 0, 0);
+        if (aligned16 && r16 >= 0 && r16 + 16 <= len) return __ldg(reinterpret_cast<const uint4*>(g.in + r16));
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 16; ++i) {
+            const int64_t o = r16 + i;
+            if (o >= ws && o < we) w[i >> 2] |= (uint32_t)g.get(o) << ((i & 3) * 8);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    // Software-pipelined: three 16-byte chunks are in flight while one is being decoded.
     template <class F>
     __device__ __forceinline__ void for_each_byte(int64_t ws, int64_t we, F&& f) const {
+        int64_t r16 = ws & ~(int64_t)15;
+        uint4 c0 = load_chunk(r16, ws, we);
+        uint4 c1 = load_chunk(r16 + 16, ws, we);
+        uint4 c2 = load_chunk(r16 + 32, ws, we);
         int64_t pos = ws;
         while (pos < we) {
-            const int64_t r16 = pos & ~(int64_t)15;
-            uint32_t w[4];
-            if (aligned16 && r16 >= 0 && r16 + 16 <= len) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(g.in + r16));
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            } else {
-                w[0] = w[1] = w[2] = w[3] = 0;
-                for (int i = 0; i < 16; ++i) {
-                    const int64_t o = r16 + i;
-                    if (o >= ws && o < we) w[i >> 2] |= (uint32_t)g.get(o) << ((i & 3) * 8);
-                }
-            }
+            const uint4 c3 = load_chunk(r16 + 48, ws, we);
+            const uint32_t w[4] = {c0.x, c0.y, c0.z, c0.w};
             const uint32_t i0 = (uint32_t)(pos - r16);
             const uint32_t i1 = (we - r16) < 16 ? (uint32_t)(we - r16) : 16u;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 if ((uint32_t)i >= i0 && (uint32_t)i < i1) f((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu, r16 + i);
             }
-            pos = r16 + 16;
+            r16 += 16;
+            pos = r16;
+            c0 = c1; c1 = c2; c2 = c3;
         }
     }
 };
@@ -264,7 +271,7 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
 }
 
 template <class Dec>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 5)
 sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X) {
     __shared__ ExactSmem S;
     Geometry geo;
