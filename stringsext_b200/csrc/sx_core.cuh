@@ -25,8 +25,10 @@
 
 #if defined(__CUDACC__)
 #define SX_HD __host__ __device__ __forceinline__
+#define SX_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define SX_HD inline
+#define SX_HD_NOINLINE inline
 #endif
 
 namespace sx {
@@ -519,7 +521,7 @@ SX_HD uint32_t utf8_fresh_written8(const uint8_t* src, uint32_t slen) {
 
 // UTF-8 probe.  `first_segment`: the probing segment is the first one of the slice.
 // Returns true for Precision::Before.
-SX_HD bool probe_utf8(const ScanParams& P, const GlobalSrc& g, int64_t slice_start, int64_t slice_end, bool first_segment,
+SX_HD_NOINLINE bool probe_utf8(const ScanParams& P, const GlobalSrc& g, int64_t slice_start, int64_t slice_end, bool first_segment,
                       int32_t slice_pending, const Carry& slice_left) {
     const bool has_left = slice_left.kind == K_L && slice_left.k > 0;
     if (first_segment) return has_left || slice_pending > 0;  // fresh decoder hits a continuation byte: written == 0
@@ -573,7 +575,7 @@ SX_HD uint32_t utf16_decode_some(const GlobalSrc& g, int64_t pos, int64_t end, u
 }
 
 template <bool BE>
-SX_HD bool probe_utf16(const ScanParams& P, const GlobalSrc& g, int64_t slice_start, int64_t slice_end, int64_t win_end,
+SX_HD_NOINLINE bool probe_utf16(const ScanParams& P, const GlobalSrc& g, int64_t slice_start, int64_t slice_end, int64_t win_end,
                        uint32_t has_lead, uint32_t lead_byte, uint32_t lead_sur, const Carry& slice_left) {
     (void)P;
     if (slice_left.kind == K_L && slice_left.k > 0) return true;  // leftover prepended: Before anyway
@@ -590,7 +592,7 @@ SX_HD bool probe_utf16(const ScanParams& P, const GlobalSrc& g, int64_t slice_st
 }
 
 template <bool BE>
-SX_HD bool probe_utf32(const GlobalSrc& g, int64_t slice_start, int64_t slice_end, int64_t win_end, uint32_t nb,
+SX_HD_NOINLINE bool probe_utf32(const GlobalSrc& g, int64_t slice_start, int64_t slice_end, int64_t win_end, uint32_t nb,
                        const Carry& slice_left) {
     if (slice_left.kind == K_L && slice_left.k > 0) return true;
     if (nb == 0 && win_end - slice_start >= 20) return false;  // aligned, and the window covers all the probe reads
@@ -688,8 +690,10 @@ struct Emit {
 // TileSrc concept: uint8_t get(int64_t off) for any stream offset; load16(int64_t off16, uint32_t w[4])
 // loads the aligned 16-byte chunk starting at tile-relative-aligned offset (off16 % 16 == 0 relative
 // to the tile base) -- both provided by the kernel / the emulation harness.
+// NOT inlined on the device: the kernels call it from several places and one copy of the byte loop
+// keeps the hot code inside the instruction cache (ncu: stall_no_instruction dominated otherwise).
 template <class Dec, class TileSrc>
-SX_HD void scan_window(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
+SX_HD_NOINLINE void scan_window(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
                        int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
     Dec dec;
     dec.init(P, tsrc, geo.ws);

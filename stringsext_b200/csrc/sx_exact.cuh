@@ -73,12 +73,17 @@ struct GlobalTile {
         int64_t pos = ws;
         while (pos < we) {
             const uint4 c3 = load_chunk(r16 + 48, ws, we);
-            const uint32_t w[4] = {c0.x, c0.y, c0.z, c0.w};
+            uint32_t w0 = c0.x, w1 = c0.y, w2 = c0.z, w3 = c0.w;
             const uint32_t i0 = (uint32_t)(pos - r16);
             const uint32_t i1 = (we - r16) < 16 ? (uint32_t)(we - r16) : 16u;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if ((uint32_t)i >= i0 && (uint32_t)i < i1) f((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu, r16 + i);
+            // deliberately NOT unrolled: one copy of the automaton body (instruction cache)
+#pragma unroll 1
+            for (uint32_t i = 0; i < i1; ++i) {
+                if (i >= i0) f(w0 & 0xFFu, r16 + i);
+                w0 = __funnelshift_r(w0, w1, 8);
+                w1 = __funnelshift_r(w1, w2, 8);
+                w2 = __funnelshift_r(w2, w3, 8);
+                w3 >>= 8;
             }
             r16 += 16;
             pos = r16;
