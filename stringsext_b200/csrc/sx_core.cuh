@@ -239,7 +239,7 @@ struct WinAuto {
         if (probe_pending) {  // finding_collection.rs:176: only the first char of the segment matters
             probe_pending = false;
             if (lb >= 0x80 && mode != MODE_STATE) {
-                if (probe(*this)) prec = PREC_BEFORE;
+                if (probe(m == 1, slice_left)) prec = PREC_BEFORE;
             }
         }
         const bool pass = pass_filter(*P, lb);
@@ -650,22 +650,24 @@ struct ProbeCtx {
     uint32_t s0, s1, s2;
 };
 
+// The probes are out of line and take plain values, so the automaton state never has its address
+// taken and stays in registers.
 template <class Dec> struct ProbeImpl {
-    SX_HD static bool run(const ProbeCtx<Dec>&, const WinAuto&) { return false; }
+    SX_HD static bool run(const ProbeCtx<Dec>&, bool, const Carry&) { return false; }
 };
 template <> struct ProbeImpl<DecUtf8> {
-    SX_HD static bool run(const ProbeCtx<DecUtf8>& c, const WinAuto& A) {
-        return probe_utf8(*c.P, *c.g, c.geo->slice_start, c.geo->slice_end, A.m == 1, c.pend0, A.slice_left);
+    SX_HD static bool run(const ProbeCtx<DecUtf8>& c, bool first_segment, const Carry& slice_left) {
+        return probe_utf8(*c.P, *c.g, c.geo->slice_start, c.geo->slice_end, first_segment, c.pend0, slice_left);
     }
 };
 template <bool BE> struct ProbeImpl<DecUtf16<BE>> {
-    SX_HD static bool run(const ProbeCtx<DecUtf16<BE>>& c, const WinAuto& A) {
-        return probe_utf16<BE>(*c.P, *c.g, c.geo->slice_start, c.geo->slice_end, c.geo->we, c.s0, c.s1, c.s2, A.slice_left);
+    SX_HD static bool run(const ProbeCtx<DecUtf16<BE>>& c, bool, const Carry& slice_left) {
+        return probe_utf16<BE>(*c.P, *c.g, c.geo->slice_start, c.geo->slice_end, c.geo->we, c.s0, c.s1, c.s2, slice_left);
     }
 };
 template <bool BE> struct ProbeImpl<DecUtf32<BE>> {
-    SX_HD static bool run(const ProbeCtx<DecUtf32<BE>>& c, const WinAuto& A) {
-        return probe_utf32<BE>(*c.g, c.geo->slice_start, c.geo->slice_end, c.geo->we, c.s0, A.slice_left);
+    SX_HD static bool run(const ProbeCtx<DecUtf32<BE>>& c, bool, const Carry& slice_left) {
+        return probe_utf32<BE>(*c.g, c.geo->slice_start, c.geo->slice_end, c.geo->we, c.s0, slice_left);
     }
 };
 
@@ -682,7 +684,7 @@ struct Emit {
     const ProbeCtx<Dec>* pc;
     SX_HD void ch(uint32_t lb, uint32_t ul, int64_t cs, int64_t ce) {
         const ProbeCtx<Dec>* c = pc;
-        A->on_char(lb, ul, cs, ce, [c](const WinAuto& a) { return ProbeImpl<Dec>::run(*c, a); });
+        A->on_char(lb, ul, cs, ce, [c](bool first_segment, Carry slice_left) { return ProbeImpl<Dec>::run(*c, first_segment, slice_left); });
     }
     SX_HD void mal(int64_t next) { A->on_malformed(next); }
 };
@@ -781,17 +783,12 @@ struct Geometry {
 // Carry into a listed window whose predecessor is NOT listed (prefilter: the predecessor holds no run
 // of >= T good bytes, so a definite breaker lies within its last T bytes and its carry-out does not
 // depend on its own carry-in): replay the predecessor's tail from the null carry.
-template <class Dec, class TileSrc>
-SX_HD Carry preroll_carry(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const Geometry& geo, int64_t w,
-                          uint32_t pre_bytes) {
+SX_HD WinGeom preroll_geom(const Geometry& geo, int64_t w, uint32_t pre_bytes) {
     WinGeom pg;
     geo.window(w - 1, pg);
-    WinGeom rg = pg;
-    if ((int64_t)pre_bytes < pg.we - pg.ws) rg.ws = pg.we - (int64_t)pre_bytes;
-    rg.final_last = false;
-    WinResult r;
-    scan_window<Dec>(P, tsrc, g, rg, carry_none(), MODE_STATE, nullptr, 0, r, nullptr);
-    return r.out;
+    if ((int64_t)pre_bytes < pg.we - pg.ws) pg.ws = pg.we - (int64_t)pre_bytes;
+    pg.final_last = false;
+    return pg;
 }
 
 // A carry-out that can make an UNLISTED successor print something (DESIGN.md "Extension rule").

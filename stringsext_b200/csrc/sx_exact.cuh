@@ -2,7 +2,7 @@
 // code in sx_scan.cu.  One instantiation per decoder lives in its own translation unit
 // (sx_exact_inst.cu compiled with -DSX_INST=n) so that the library builds in parallel.
 #pragma once
-#include "sx_core.cuh"
+#include "sx_fast_utf8.cuh"
 #include <cuda_runtime.h>
 
 namespace sx {
@@ -52,6 +52,8 @@ struct GlobalTile {
     GlobalSrc g;
     int64_t len;
     bool aligned16;
+    const Utf8Tables* tab;
+    __device__ __forceinline__ const Utf8Tables* tables() const { return tab; }
     __device__ __forceinline__ uint8_t get(int64_t off) const { return g.get(off); }
     __device__ __forceinline__ uint4 load_chunk(int64_t r16, int64_t ws, int64_t we) const {
         if (r16 >= we) return make_uint4(0, 0, 0, 0);
@@ -131,6 +133,7 @@ struct ExactSmem {
     uint32_t warp_a[8], warp_b[8];
     unsigned long long bases[2];
     int32_t last_npend;
+    Utf8Tables tables;
 };
 
 __device__ __forceinline__ long long list_window(const ExactCfg& X, long long e) { return X.list ? (long long)X.list[e] : e; }
@@ -142,7 +145,7 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
                             long long NE, long long e0, uint32_t nblk, bool full, Carry carry_in, long long block_id) {
     const uint32_t i = threadIdx.x;
     const GlobalSrc g{P.in, P.pend};
-    const GlobalTile ts{g, P.len, X.in_aligned16 != 0};
+    const GlobalTile ts{g, P.len, X.in_aligned16 != 0, P.enc == ENC_UTF8 ? &S.tables : nullptr};
     const bool active = i < nblk;
     long long w = -1;
     bool adj = false, next_adj = false;
@@ -158,10 +161,16 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
         next_adj = e + 1 < NE && list_window(X, e + 1) == w + 1;
         geo.window(w, wg);
         WinResult r;
-        scan_window<Dec>(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
+        WindowEngine<Dec>::run(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
         S.desc[i] = d;
         if (!adj) {
-            S.kin[i] = (w == 0) ? P.k0 : preroll_carry<Dec>(P, ts, g, geo, w, X.pre_bytes);
+            if (w == 0) S.kin[i] = P.k0;
+            else {
+                const WinGeom rg = preroll_geom(geo, w, X.pre_bytes);
+                WinResult rr;
+                WindowEngine<Dec>::run(P, ts, g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
+                S.kin[i] = rr.out;
+            }
             S.in_known[i] = 1;
         }
         else if (i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
@@ -188,7 +197,7 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             else if (d.type == WT_CASEB) out = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws));
             else {
                 WinResult r;
-                scan_window<Dec>(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, r, nullptr);
+                WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, r, nullptr);
                 out = r.out;
             }
             S.kout[i] = out;
@@ -216,7 +225,7 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             if (carry_is_null(kin) && d.nrec != 0xFFFFu) { cr = d.nrec; ct = d.ntext; }
             else {
                 WinResult r;
-                scan_window<Dec>(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, r, nullptr);
+                WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, r, nullptr);
                 cr = r.nrec; ct = r.ntext;
             }
         }
@@ -226,7 +235,7 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
         if (ext) {
             geo.window(w + 1, xg);
             WinResult r;
-            scan_window<Dec>(P, ts, g, xg, kout, MODE_COUNT, nullptr, 0, r, nullptr);
+            WindowEngine<Dec>::run(P, ts, g, xg, kout, MODE_COUNT, nullptr, 0, r, nullptr);
             xr = r.nrec; xt = r.ntext;
         }
     }
@@ -250,12 +259,12 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
         uint32_t ro = er, to = et;
         if (emit && cr) {
             WinResult r;
-            scan_window<Dec>(P, ts, g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+            WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
         }
         ro += cr; to += ct;
         if (ext && xr) {
             WinResult r;
-            scan_window<Dec>(P, ts, g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+            WindowEngine<Dec>::run(P, ts, g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
         }
         ro += xr; to += xt;
         if (extra) {
@@ -276,11 +285,15 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
 }
 
 template <class Dec>
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, 4)
 sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X) {
     __shared__ ExactSmem S;
     Geometry geo;
     geo.init(P);
+    if (P.enc == ENC_UTF8) {
+        for (uint32_t k = threadIdx.x; k < 256; k += kThreads) utf8_tables_fill(P, S.tables, k);
+        __syncthreads();
+    }
     const long long NE = X.list ? (long long)*X.ne_ptr : X.ne_static;
     const long long e0 = (long long)blockIdx.x * kThreads;
     if (e0 >= NE) return;

@@ -2,7 +2,7 @@
 // (stringsext_b200/csrc/sx_core.cuh) sequentially on the CPU so that the window decomposition,
 // transfer-function classification and emit rules can be differential-tested against the oracle
 // without a GPU.  It is NOT part of the product library and nothing in stringsext_b200/ loads it.
-#include "../../stringsext_b200/csrc/sx_core.cuh"
+#include "../../stringsext_b200/csrc/sx_fast_utf8.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -10,8 +10,11 @@
 
 using namespace sx;
 
+static Utf8Tables g_tables;
+static int g_use_fast = 1;
 struct HostTile {
     GlobalSrc g;
+    const Utf8Tables* tables() const { return g_use_fast ? &g_tables : nullptr; }
     uint8_t get(int64_t off) const { return g.get(off); }
     template <class F> void for_each_byte(int64_t ws, int64_t we, F&& f) const {
         for (int64_t p = ws; p < we; ++p) f((uint32_t)g.get(p), p);
@@ -46,13 +49,13 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
     int32_t last_npend = P.npend;
     auto emit_window = [&](const WinGeom& wg, const Carry& kin, WinResult& rstate) {
         WinResult rc;
-        scan_window<Dec>(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, rc, nullptr);
+        WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, rc, nullptr);
         rstate = rc;
         if (rc.nrec == 0) return;
         const size_t base = recs.size();
         recs.resize(base + rc.nrec);
         WinResult rw;
-        scan_window<Dec>(P, ts, g, wg, kin, MODE_WRITE, recs.data() + base, text.size(), rw, nullptr);
+        WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_WRITE, recs.data() + base, text.size(), rw, nullptr);
         const size_t tb = text.size();
         text.resize(tb + rc.ntext + 8);
         for (size_t k = base; k < recs.size(); ++k) {
@@ -68,13 +71,19 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         geo.window(w, wg);
         const bool adjacent = e > 0 && (int64_t)list[e - 1] == w - 1;
         const uint32_t pre_bytes = pc.T + 3 + pc.unit;
-        const Carry kin = adjacent ? kprev : (w == 0 ? P.k0 : preroll_carry<Dec>(P, ts, g, geo, w, pre_bytes));
+        Carry kin = adjacent ? kprev : P.k0;
+        if (!adjacent && w != 0) {
+            const WinGeom rg = preroll_geom(geo, w, pre_bytes);
+            WinResult rr;
+            WindowEngine<Dec>::run(P, ts, g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
+            kin = rr.out;
+        }
         // summary under the null carry + classification self-check
         WinResult r0;
         WinDesc d;
-        scan_window<Dec>(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r0, &d);
+        WindowEngine<Dec>::run(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r0, &d);
         WinResult rs;
-        scan_window<Dec>(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, rs, nullptr);
+        WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, rs, nullptr);
         Carry kout;
         if (d.type == WT_CONST) kout = d.null_out;
         else if (d.type == WT_CASEB) { kout = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws)); stats[2]++; }
@@ -127,7 +136,9 @@ struct emul_out {
 };
 
 // Returns 0 on success.  `params` is a fully populated ScanParams (in = host pointer).
+void sx_emul_set_fast(int on) { g_use_fast = on; }
 int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
+    for (uint32_t i = 0; i < 256; ++i) utf8_tables_fill(*P, g_tables, i);
     std::vector<uint32_t> list;
     std::vector<Record> recs;
     std::vector<uint8_t> text;
