@@ -271,6 +271,7 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, mat_ms, pre_ms, lst_ms, ex_ms, launches, nfind, d2h = [], [], [], [], [], 0, 0, 0
+    host_ms = []
     e0.record(stream)
     for _ in range(args.steps):
         nfind, st = step_device()
@@ -280,6 +281,7 @@ def main():
         lst_ms.append(st.list_kernels_ms)
         ex_ms.append(st.exact_kernel_ms)
         win_total, win_listed = st.windows_total, st.windows_listed
+        host_ms.append((st.host_total_ms, st.host_post_ms))
         launches += st.kernel_launches
         d2h = st.d2h_bytes
     e1.record(stream)
@@ -352,7 +354,8 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": size, "kernel_ms": k_ms, "kernels_ms": kernels,
                          "pipeline_ms": avg(scan_ms), "pipeline_gbs": size / 1e9 / (avg(scan_ms) / 1e3),
-                         "windows_total": int(win_total), "windows_listed": int(win_listed)},
+                         "windows_total": int(win_total), "windows_listed": int(win_listed),
+                         "host_call_ms": avg([h[0] for h in host_ms]), "host_post_ms": avg([h[1] for h in host_ms])},
         }
         if not args.no_cpu:
             from helpers import to_oracle

@@ -136,6 +136,8 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t n_records, text_bytes;
     uint64_t windows_total, windows_listed;
+    float host_total_ms; /* wall clock of the whole call */
+    float host_post_ms;  /* of which: building the collection after the last device sync */
 } sx_scan_stats;
 void sx_scanner_state_last_stats(const sx_scanner_state*, sx_scan_stats* out);
 

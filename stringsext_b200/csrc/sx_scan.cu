@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -410,6 +411,10 @@ struct sx_scanner_state {
     uint32_t* d_toff = nullptr; size_t toff_cap = 0;
     uint32_t* d_list = nullptr; size_t list_cap = 0;
     int use_prefilter = 1;
+    // pinned host staging for result downloads
+    Record* h_recs = nullptr; size_t h_recs_cap = 0;
+    uint8_t* h_text = nullptr; size_t h_text_cap = 0;
+    uint2* h_blocks = nullptr; size_t h_blocks_cap = 0;
     unsigned long long* d_counters = nullptr;
     FinalState* d_final = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -474,6 +479,7 @@ void sx_scanner_state_free(sx_scanner_state* ss) {
     cudaSetDevice(ss->device);
     cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_blocks); cudaFree(ss->d_emask); cudaFree(ss->d_tcount); cudaFree(ss->d_toff); cudaFree(ss->d_list);
     cudaFree(ss->d_counters); cudaFree(ss->d_final);
+    cudaFreeHost(ss->h_recs); cudaFreeHost(ss->h_text); cudaFreeHost(ss->h_blocks);
     for (auto e : ss->ev) if (e) cudaEventDestroy(e);
     delete ss;
 }
@@ -512,6 +518,18 @@ int sx_fc_str_buf_overflow(const sx_finding_collection* fc) { return fc->str_buf
 void sx_fc_free(sx_finding_collection* fc) { delete fc; }
 
 }  // extern "C"
+
+template <class T>
+static bool grow_pinned(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return true;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = need + need / 4 + 256;
+    if (!cuda_ok(cudaMallocHost(p, want * sizeof(T)), "cudaMallocHost")) return false;
+    *cap = want;
+    return true;
+}
 
 template <class T>
 static bool grow(T** p, size_t* cap, size_t need) {
@@ -588,6 +606,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     if (slice_len == 0 || slice_len > 0x7FFFFFFFull) { set_err(SX_ERR_ARGUMENT, "slice_len must be in 1..2^31-1"); return fail; }
     const uint32_t wps = (uint32_t)((slice_len + W - 1) / W);
     memset(&ss->stats, 0, sizeof ss->stats);
+    const auto t_begin = std::chrono::steady_clock::now();
     sx_finding_collection* fc = new sx_finding_collection();
     fc->first_byte_position = ss->consumed;
     if (len == 0) return fc;  // finding_collection.rs:124: the window loop does not run, state untouched
@@ -657,7 +676,6 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         if (!grow(&ss->d_text, &ss->text_cap, need_text)) return fail;
         CK(cudaMemsetAsync(ss->d_counters, 0, 4 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(ss->d_final, 0, sizeof(FinalState), st));
-        CK(cudaMemsetAsync(ss->d_blocks, 0, (size_t)max_blocks * sizeof(uint2), st));
         ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final};
         ExactCfg X;
         X.total_windows = total_windows;
@@ -725,9 +743,13 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     ss->stats.text_bytes = ntext;
 
     // ---- text + download ---------------------------------------------------------------------------
-    std::vector<Record> recs(nrec);
-    std::vector<uint8_t> text(ntext);
-    std::vector<uint2> tiles((size_t)((counters[2] + kThreads - 1) / kThreads));
+    const size_t nblocks = (size_t)((counters[2] + kThreads - 1) / kThreads);
+    if (!grow_pinned(&ss->h_recs, &ss->h_recs_cap, nrec + 1)) return fail;
+    if (!grow_pinned(&ss->h_text, &ss->h_text_cap, ntext + 1)) return fail;
+    if (!grow_pinned(&ss->h_blocks, &ss->h_blocks_cap, nblocks + 1)) return fail;
+    const Record* recs = ss->h_recs;
+    const uint8_t* text = ss->h_text;
+    const uint2* tiles = ss->h_blocks;
     if (nrec) {
         const int mgrid = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ss->num_sms * 8);
         CK(cudaEventRecord(ss->ev[2], st));
@@ -735,10 +757,10 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         CK(cudaGetLastError());
         CK(cudaEventRecord(ss->ev[3], st));
         ss->stats.kernel_launches++;
-        CK(cudaMemcpyAsync(recs.data(), ss->d_recs, nrec * sizeof(Record), cudaMemcpyDeviceToHost, st));
-        if (ntext) CK(cudaMemcpyAsync(text.data(), ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(tiles.data(), ss->d_blocks, tiles.size() * sizeof(uint2), cudaMemcpyDeviceToHost, st));
-        ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + tiles.size() * sizeof(uint2);
+        CK(cudaMemcpyAsync(ss->h_recs, ss->d_recs, nrec * sizeof(Record), cudaMemcpyDeviceToHost, st));
+        if (ntext) CK(cudaMemcpyAsync(ss->h_text, ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ss->h_blocks, ss->d_blocks, nblocks * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+        ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + nblocks * sizeof(uint2);
     }
     // bytes that stay inside the decoder: the last npend bytes of (old pend ++ buffer)
     uint8_t tail[8] = {0};
@@ -752,16 +774,17 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ss->stats.materialize_kernel_ms = ms;
     }
 
+    const auto t_post = std::chrono::steady_clock::now();
     // ---- build the collection in stream order (tiles are contiguous record blocks) -------------------
     size_t extra_text = 0;
-    for (const Record& r : recs) if (r.flags & RF_HOSTCARRY) extra_text += ss->leftover.size() + r.text_len;
+    for (size_t i = 0; i < nrec; ++i) if (recs[i].flags & RF_HOSTCARRY) extra_text += ss->leftover.size() + recs[i].text_len;
     fc->text.resize(ntext + extra_text + 1);
-    if (ntext) memcpy(fc->text.data(), text.data(), ntext);
+    if (ntext) memcpy(fc->text.data(), text, ntext);
     size_t extra_off = ntext;
     fc->v.reserve(nrec);
     std::vector<uint8_t> new_leftover;
     bool have_leftover = false;
-    for (size_t t = 0; t < tiles.size(); ++t) {
+    for (size_t t = 0; t < (nrec ? nblocks : 0); ++t) {
         const size_t b = tiles[t].x, c = tiles[t].y;
         for (size_t i = b; i < b + c && i < nrec; ++i) {
             const Record& r = recs[i];
@@ -813,6 +836,11 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ss->npend = (np > 0 && (size_t)np <= cn) ? np : 0;
     }
     ss->consumed += len;
+    {
+        const auto t_end = std::chrono::steady_clock::now();
+        ss->stats.host_total_ms = std::chrono::duration<float, std::milli>(t_end - t_begin).count();
+        ss->stats.host_post_ms = std::chrono::duration<float, std::milli>(t_end - t_post).count();
+    }
     guard.p = nullptr;
     return fc;
 }

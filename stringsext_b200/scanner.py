@@ -84,6 +84,8 @@ class ScanStats(C.Structure):
         ("text_bytes", C.c_uint64),
         ("windows_total", C.c_uint64),
         ("windows_listed", C.c_uint64),
+        ("host_total_ms", C.c_float),
+        ("host_post_ms", C.c_float),
     ]
 
 
