@@ -7,6 +7,7 @@
 
 namespace sx {
 
+constexpr int kMaxPrefCtas = 1024;  // prefilter CTAs (list regions)
 constexpr int kThreads = 128;      // exact kernel: one list entry per thread
 constexpr int kPrefThreads = 256;  // prefilter kernel: one window per thread, 256 windows per tile
 
@@ -34,6 +35,9 @@ struct ExactCfg {
     long long total_windows;
     uint32_t in_aligned16;
     uint32_t pre_bytes;                // pre-roll length for entries whose predecessor window is not listed
+    const uint32_t* cta_off;           // list != nullptr: entry offsets of the prefilter CTAs' list regions (ncta + 1)
+    uint32_t ncta;
+    unsigned long long region_stride;  // list region of prefilter CTA b starts at b * region_stride
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t r) { return r ^ (((r >> 7) & 7u) << 4); }
@@ -134,9 +138,19 @@ struct ExactSmem {
     unsigned long long bases[2];
     int32_t last_npend;
     Utf8Tables tables;
+    uint32_t cta_off[kMaxPrefCtas + 1];
 };
 
-__device__ __forceinline__ long long list_window(const ExactCfg& X, long long e) { return X.list ? (long long)X.list[e] : e; }
+// entry index -> window index: binary search of the owning prefilter CTA's region (offsets staged in smem)
+__device__ __forceinline__ long long list_window(const ExactCfg& X, const uint32_t* soff, long long e) {
+    if (!X.list) return e;
+    uint32_t lo = 0, hi = X.ncta;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((long long)soff[mid] <= e) lo = mid; else hi = mid;
+    }
+    return (long long)X.list[(unsigned long long)lo * X.region_stride + (unsigned long long)(e - soff[lo])];
+}
 
 // One pass over list entries [e0, e0 + nblk): summary, carry resolution and (full) emission.
 // Returns the carry out of the last entry.
@@ -156,9 +170,9 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
     // ---- stage A: per-entry summary under the null carry ------------------------------------------
     if (active) {
         const long long e = e0 + i;
-        w = list_window(X, e);
-        adj = e > 0 && list_window(X, e - 1) == w - 1;
-        next_adj = e + 1 < NE && list_window(X, e + 1) == w + 1;
+        w = list_window(X, S.cta_off, e);
+        adj = e > 0 && list_window(X, S.cta_off, e - 1) == w - 1;
+        next_adj = e + 1 < NE && list_window(X, S.cta_off, e + 1) == w + 1;
         geo.window(w, wg);
         WinResult r;
         WindowEngine<Dec>::run(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
@@ -290,16 +304,17 @@ sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const Exa
     __shared__ ExactSmem S;
     Geometry geo;
     geo.init(P);
-    if (P.enc == ENC_UTF8) {
+    if (P.enc == ENC_UTF8)
         for (uint32_t k = threadIdx.x; k < 256; k += kThreads) utf8_tables_fill(P, S.tables, k);
-        __syncthreads();
-    }
+    if (X.list)
+        for (uint32_t k = threadIdx.x; k <= X.ncta; k += kThreads) S.cta_off[k] = X.cta_off[k];
+    __syncthreads();
     const long long NE = X.list ? (long long)*X.ne_ptr : X.ne_static;
     const long long e0 = (long long)blockIdx.x * kThreads;
     if (e0 >= NE) return;
     const uint32_t nblk = (uint32_t)((NE - e0) < (long long)kThreads ? (NE - e0) : (long long)kThreads);
     Carry c = carry_none();
-    const bool first_adj = e0 > 0 && list_window(X, e0 - 1) == list_window(X, e0) - 1;
+    const bool first_adj = e0 > 0 && list_window(X, S.cta_off, e0 - 1) == list_window(X, S.cta_off, e0) - 1;
     if (first_adj) {
         // Warm-up: the block starts inside a run of adjacent windows.  Replay preceding entries in
         // state-only mode; a non-adjacent entry or a constant window makes the carry known.

@@ -32,9 +32,12 @@ namespace sx {
 // flags into a 128-bit mask and decides INTERESTING from the mask (sx_core.cuh, pref_*_ref is the
 // byte-wise specification of exactly what is computed here).
 // ---------------------------------------------------------------------------------------------
+// Every prefilter CTA owns a contiguous range of tiles and compacts the windows it keeps into its own
+// region of `list` (region of CTA b starts at b * region_stride); cta_count[b] = how many it kept.
 struct PrefOut {
-    uint32_t* emask;       // 8 words per tile: windows handed to the exact kernel
-    uint32_t* tile_count;  // listed windows per tile
+    uint32_t* list;
+    uint32_t* cta_count;
+    long long tiles_per_cta;
 };
 
 struct PrefK {
@@ -135,8 +138,12 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = P.W, nchunk = W >> 4;
     const uint32_t tile_bytes = kPrefTileWin * W;
+    const long long t_begin = (long long)blockIdx.x * O.tiles_per_cta;
+    const long long t_end = (t_begin + O.tiles_per_cta) < ntiles ? (t_begin + O.tiles_per_cta) : ntiles;
+    uint32_t* const my_list = O.list + (size_t)t_begin * kPrefTileWin;
+    uint32_t kept = 0;  // windows this CTA has listed so far (uniform across the block)
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = t_begin; tile < t_end; ++tile) {
         const int64_t lo = (int64_t)tile * tile_bytes;
         const int64_t hi = (lo + tile_bytes) < P.len ? (lo + tile_bytes) : P.len;
         // ---- stage the tile: coalesced 16-byte streaming loads, swizzled shared stores ------------------
@@ -268,65 +275,51 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             else if (tid == 0) interesting = lead >= 1;
             else interesting = s_trail[tid - 1] + lead >= C.T;
         }
+        // compact: stream order = (warp, lane) order inside the tile
         const uint32_t ib = __ballot_sync(0xffffffffu, interesting);
-        if (lane == 0) s_iw[warp] = ib;
+        if (lane == 0) s_iw[warp] = __popc(ib);
         __syncthreads();
-        if (tid < 8) {
-            const uint32_t cur = s_iw[tid];
-            uint32_t e = cur;
-            // drop slots beyond the stream
-            const long long base_w = tile * kPrefTileWin + (long long)tid * 32;
-            const long long remain = total_windows - base_w;
-            if (remain <= 0) e = 0;
-            else if (remain < 32) e &= (1u << remain) - 1u;
-            O.emask[tile * 8 + tid] = e;
-            uint32_t cnt = __popc(e);
-            cnt += __shfl_down_sync(0xffu, cnt, 4);
-            cnt += __shfl_down_sync(0xffu, cnt, 2);
-            cnt += __shfl_down_sync(0xffu, cnt, 1);
-            if (tid == 0) O.tile_count[tile] = cnt;
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < kPrefThreads / 32; ++k) {
+            const uint32_t c = s_iw[k];
+            if ((uint32_t)k < warp) before += c;
+            total += c;
         }
+        if (interesting) my_list[kept + before + __popc(ib & ((1u << lane) - 1u))] = (uint32_t)w;
+        kept += total;
         __syncthreads();
     }
+    if (tid == 0) O.cta_count[blockIdx.x] = kept;
 }
 
-// exclusive scan of the per-tile counts (single block) -> tile offsets, total -> counters[2]
-__global__ void __launch_bounds__(1024) sx_list_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_off,
-                                                            long long ntiles, unsigned long long* counters) {
-    __shared__ unsigned long long part[1024];
-    const uint32_t tid = threadIdx.x;
-    const long long per = (ntiles + 1023) / 1024;
-    const long long b = (long long)tid * per, e = (b + per) < ntiles ? (b + per) : ntiles;
-    unsigned long long s = 0;
-    for (long long t = b; t < e; ++t) s += tile_count[t];
-    part[tid] = s;
+// exclusive scan of the per-CTA counts (at most 1024 CTAs) -> cta_off[0..ncta], total -> counters[2]
+__global__ void __launch_bounds__(1024) sx_list_offsets_kernel(const uint32_t* __restrict__ cta_count, uint32_t* __restrict__ cta_off,
+                                                               uint32_t ncta, unsigned long long* counters) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t v = tid < ncta ? cta_count[tid] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long run = 0;
-        for (int k = 0; k < 1024; ++k) { const unsigned long long v = part[k]; part[k] = run; run += v; }
-        counters[2] = run;
+    if (warp == 0) {
+        uint32_t x = wsum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= (uint32_t)d) x += t;
+        }
+        wsum[lane] = x;  // inclusive
     }
     __syncthreads();
-    unsigned long long run = part[tid];
-    for (long long t = b; t < e; ++t) { tile_off[t] = (uint32_t)run; run += tile_count[t]; }
-}
-
-// expand the per-tile bit masks into the ordered window list
-__global__ void __launch_bounds__(256) sx_list_expand_kernel(const uint32_t* __restrict__ emask, const uint32_t* __restrict__ tile_off,
-                                                             long long ntiles, uint32_t* __restrict__ list) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (tile, word)
-    if (idx >= ntiles * 8) return;
-    const long long tile = idx >> 3;
-    const uint32_t j = (uint32_t)(idx & 7);
-    uint32_t off = tile_off[tile];
-    for (uint32_t k = 0; k < j; ++k) off += __popc(emask[tile * 8 + k]);
-    uint32_t e = emask[idx];
-    const uint32_t base_w = (uint32_t)(tile * kPrefTileWin + j * 32);
-    while (e) {
-        const uint32_t b = __ffs(e) - 1;
-        e &= e - 1;
-        list[off++] = base_w + b;
-    }
+    const uint32_t base = warp ? wsum[warp - 1] : 0u;
+    if (tid < ncta) cta_off[tid] = base + inc - v;
+    if (tid == 1023) { cta_off[ncta] = base + inc; counters[2] = base + inc; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -406,11 +399,11 @@ struct sx_scanner_state {
     Record* d_recs = nullptr; size_t rec_cap = 0;
     uint8_t* d_text = nullptr; size_t text_cap = 0;
     uint2* d_blocks = nullptr; size_t blocks_cap = 0;
-    uint32_t* d_emask = nullptr; size_t emask_cap = 0;
-    uint32_t* d_tcount = nullptr; size_t tcount_cap = 0;
-    uint32_t* d_toff = nullptr; size_t toff_cap = 0;
+    uint32_t* d_ccount = nullptr; size_t ccount_cap = 0;
+    uint32_t* d_coff = nullptr; size_t coff_cap = 0;
     uint32_t* d_list = nullptr; size_t list_cap = 0;
     int use_prefilter = 1;
+    uint32_t last_ncta = 0; size_t last_region_stride = 0;
     // pinned host staging for result downloads
     Record* h_recs = nullptr; size_t h_recs_cap = 0;
     uint8_t* h_text = nullptr; size_t h_text_cap = 0;
@@ -477,7 +470,7 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
 void sx_scanner_state_free(sx_scanner_state* ss) {
     if (!ss) return;
     cudaSetDevice(ss->device);
-    cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_blocks); cudaFree(ss->d_emask); cudaFree(ss->d_tcount); cudaFree(ss->d_toff); cudaFree(ss->d_list);
+    cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_blocks); cudaFree(ss->d_ccount); cudaFree(ss->d_coff); cudaFree(ss->d_list);
     cudaFree(ss->d_counters); cudaFree(ss->d_final);
     cudaFreeHost(ss->h_recs); cudaFreeHost(ss->h_text); cudaFreeHost(ss->h_blocks);
     for (auto e : ss->ev) if (e) cudaEventDestroy(e);
@@ -505,7 +498,14 @@ size_t sx_scanner_state_last_window_list(const sx_scanner_state* ss, uint32_t* o
     const size_t k = n < cap ? n : cap;
     if (k && out) {
         cudaSetDevice(ss->device);
-        if (cudaMemcpy(out, ss->d_list, k * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+        std::vector<uint32_t> off(ss->last_ncta + 1);
+        if (cudaMemcpy(off.data(), ss->d_coff, off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+        size_t done = 0;
+        for (uint32_t b = 0; b < ss->last_ncta && done < k; ++b) {
+            const size_t c = std::min<size_t>(off[b + 1] - off[b], k - done);
+            if (c && cudaMemcpy(out + done, ss->d_list + (size_t)b * ss->last_region_stride, c * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+            done += c;
+        }
     }
     return n;
 }
@@ -662,10 +662,9 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
 
     if (!grow(&ss->d_blocks, &ss->blocks_cap, (size_t)max_blocks)) return fail;
     if (pc.enabled) {
-        if (!grow(&ss->d_emask, &ss->emask_cap, (size_t)ntiles * 8)) return fail;
-        if (!grow(&ss->d_tcount, &ss->tcount_cap, (size_t)ntiles)) return fail;
-        if (!grow(&ss->d_toff, &ss->toff_cap, (size_t)ntiles)) return fail;
-        if (!grow(&ss->d_list, &ss->list_cap, (size_t)total_windows)) return fail;
+        if (!grow(&ss->d_ccount, &ss->ccount_cap, (size_t)1024)) return fail;
+        if (!grow(&ss->d_coff, &ss->coff_cap, (size_t)1032)) return fail;
+        if (!grow(&ss->d_list, &ss->list_cap, (size_t)ntiles * kPrefTileWin)) return fail;
     }
     size_t need_recs = (size_t)(len * ss->rec_per_byte) + 4096;
     size_t need_text = (size_t)(len * ss->text_per_byte) + 65536;
@@ -684,25 +683,32 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         CK(cudaEventRecord(ss->ev[0], st));
         if (pc.enabled) {
             const PrefK pk = make_pref_k(P, pc);
-            const PrefOut po{ss->d_emask, ss->d_tcount};
-            const int pgrid = (int)std::min<long long>(ntiles, (long long)ss->num_sms * 3);
+            int pgrid = (int)std::min<long long>(ntiles, std::min<long long>(1024, (long long)ss->num_sms * 3));
+            const long long tiles_per_cta = (ntiles + pgrid - 1) / pgrid;
+            pgrid = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
+            const PrefOut po{ss->d_list, ss->d_ccount, tiles_per_cta};
             CK(launch_prefilter(P, pc, pk, po, total_windows, ntiles, pgrid, st));
             CK(cudaEventRecord(ss->ev[4], st));
-            sx_list_scan_kernel<<<1, 1024, 0, st>>>(ss->d_tcount, ss->d_toff, ntiles, ss->d_counters);
-            CK(cudaGetLastError());
-            sx_list_expand_kernel<<<(unsigned)((ntiles * 8 + 255) / 256), 256, 0, st>>>(ss->d_emask, ss->d_toff, ntiles, ss->d_list);
+            sx_list_offsets_kernel<<<1, 1024, 0, st>>>(ss->d_ccount, ss->d_coff, (uint32_t)pgrid, ss->d_counters);
             CK(cudaGetLastError());
             CK(cudaEventRecord(ss->ev[5], st));
-            ss->stats.kernel_launches += 3;
+            ss->stats.kernel_launches += 2;
             X.list = ss->d_list;
             X.ne_ptr = ss->d_counters + 2;
             X.ne_static = 0;
+            X.cta_off = ss->d_coff;
+            X.ncta = (uint32_t)pgrid;
+            X.region_stride = (unsigned long long)tiles_per_cta * kPrefTileWin;
+            ss->last_ncta = (uint32_t)pgrid; ss->last_region_stride = (size_t)X.region_stride;
         } else {
             CK(cudaEventRecord(ss->ev[4], st));
             CK(cudaEventRecord(ss->ev[5], st));
             X.list = nullptr;
             X.ne_ptr = nullptr;
             X.ne_static = total_windows;
+            X.cta_off = nullptr;
+            X.ncta = 0;
+            X.region_stride = 0;
         }
         CK(launch_exact_enc(P, O, X, (unsigned)max_blocks, st));
         CK(cudaEventRecord(ss->ev[1], st));
@@ -776,8 +782,9 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
 
     const auto t_post = std::chrono::steady_clock::now();
     // ---- build the collection in stream order (tiles are contiguous record blocks) -------------------
-    size_t extra_text = 0;
-    for (size_t i = 0; i < nrec; ++i) if (recs[i].flags & RF_HOSTCARRY) extra_text += ss->leftover.size() + recs[i].text_len;
+    // at most two records (the first piece of a run that began in the previous call and the final leftover)
+    // carry host text in front of their device text
+    const size_t extra_text = 2 * (ss->leftover.size() + 8 * (size_t)q + 64);
     fc->text.resize(ntext + extra_text + 1);
     if (ntext) memcpy(fc->text.data(), text, ntext);
     size_t extra_off = ntext;
