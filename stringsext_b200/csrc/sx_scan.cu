@@ -416,9 +416,26 @@ struct sx_scanner_state {
     sx_scan_stats stats;
 };
 
+// uninitialised storage: value-initialising tens of MB per call showed up in the whole-job time
+template <class T>
+struct RawVec {
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+    ~RawVec() { free(p); }
+    void reserve(size_t c) { if (c > cap) { p = (T*)realloc(p, c * sizeof(T)); cap = c; } }
+    void resize(size_t c) { reserve(c); n = c; }
+    void push_back(const T& x) { if (n == cap) reserve(cap ? cap * 2 : 16); p[n++] = x; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    const T* begin() const { return p; }
+    const T* end() const { return p + n; }
+};
 struct sx_finding_collection {
-    std::vector<sx_finding> v;
-    std::vector<uint8_t> text;
+    RawVec<sx_finding> v;
+    RawVec<uint8_t> text;
     uint64_t first_byte_position = 0;
     int str_buf_overflow = 0;
 };
