@@ -75,152 +75,48 @@ SX_HD void utf8_tables_fill(const ScanParams& P, Utf8Tables& T, uint32_t i) {  /
     if (i < 128) T.trans[i] = (uint8_t)(((i & 15) < 12) ? utf8_trans_entry(i >> 4, i & 15) : 0);
 }
 
-struct FastAuto {
+// Cold state: only the out-of-line record writer touches it, so it may live in local memory while the
+// hot automaton state below stays in registers.
+struct FastEmit {
     const ScanParams* P;
-    int64_t base;       // window start (absolute); all *_rel are relative to it
+    int64_t base;  // window start (absolute)
     int mode;
     Record* wr;
     uint64_t text_off;
-    int32_t slice_rel;  // slice start relative to base
-    // segment / SplitStr state
-    int32_t seg_rel;
-    uint32_t prec;
-    bool probe_pending, last_cut, at_left, cut, run_hostcarry;
-    uint32_t run_n;
-    int32_t run_s, run_e;
-    // leftover (`again` chunk)
-    bool has_left, left_hostcarry;
-    uint32_t left_k;
-    int32_t left_s, left_e;
-    Carry slice_left;
-    // outputs
     uint32_t nrec, ntext;
-    // summary
-    uint32_t m, a;
-    bool in_first_run, s1_all_pass, s1_later_yield, s2_all_pass;
+};
+SX_HD_NOINLINE void fast_emit(FastEmit* E, int32_t seg_rel, uint32_t prec, int32_t run_s, int32_t run_e, uint32_t completes,
+                              uint32_t hostcarry) {
+    const uint32_t len = (uint32_t)(run_e - run_s);
+    if (E->mode == MODE_WRITE) {
+        Record r;
+        r.position = E->P->base_consumed + (uint64_t)(E->base + seg_rel);  // finding_collection.rs:260
+        r.in_start = E->base + run_s;
+        r.in_len = len;
+        r.text_len = len;  // UTF-8 -> UTF-8: the text is the input range
+        r.text_off = E->text_off;
+        r.flags = (completes ? RF_COMPLETES : 0u) | (hostcarry ? RF_HOSTCARRY : 0u);
+        r.precision = prec;
+        *E->wr++ = r;
+        E->text_off += len;
+    }
+    E->nrec++;
+    E->ntext += len;
+}
 
-    SX_HD void init(const ScanParams* p, int md, int64_t b, int32_t srel) {
-        P = p; base = b; mode = md; wr = nullptr; text_off = 0; slice_rel = srel;
-        seg_rel = 0; prec = PREC_EXACT; probe_pending = false; last_cut = false; at_left = true; cut = false;
-        run_hostcarry = false; run_n = 0; run_s = run_e = 0;
-        has_left = false; left_hostcarry = false; left_k = 0; left_s = left_e = 0; slice_left = carry_none();
-        nrec = ntext = 0; m = 0; a = 0; in_first_run = false; s1_all_pass = true; s1_later_yield = false; s2_all_pass = true;
-    }
-    // first segment of the window (finding_collection.rs:101-116, :211-241)
-    SX_HD void first_segment(const Carry& kin, int32_t pend_len) {
-        m = 1;
-        const bool cont = (kin.kind == K_C);
-        cut = false;
-        last_cut = cont;
-        at_left = true;
-        run_n = 0; run_hostcarry = false;
-        prec = PREC_EXACT;
-        seg_rel = 0;
-        probe_pending = (slice_rel == 0);
-        has_left = false;
-        in_first_run = true;
-        if (kin.kind == K_L && kin.k > 0) {
-            run_n = kin.k;
-            run_s = -(int32_t)kin.in_bytes;
-            run_e = -pend_len;
-            run_hostcarry = (kin.flags & CF_HOSTCARRY) != 0;
-            prec = PREC_BEFORE;
-        }
-    }
-    // rare paths below stay inline on purpose: taking the automaton's address for a call would push its
-    // state from registers into local memory
-    SX_HD void yield(bool completes, bool maybe_cut) {
-        if (m == 1 && !in_first_run) s1_later_yield = true;
-        const uint32_t len = (uint32_t)(run_e - run_s);
-        if (mode == MODE_WRITE) {
-            Record r;
-            r.position = P->base_consumed + (uint64_t)(base + seg_rel);
-            r.in_start = base + run_s;
-            r.in_len = len;
-            r.text_len = len;  // UTF-8 -> UTF-8: the text is the input range
-            r.text_off = text_off;
-            r.flags = (completes ? RF_COMPLETES : 0u) | (run_hostcarry ? RF_HOSTCARRY : 0u);
-            r.precision = prec;
-            *wr++ = r;
-            text_off += len;
-        }
-        nrec++;
-        ntext += len;
-        cut = maybe_cut;
-        prec = PREC_AFTER;
-        has_left = false;
-    }
-    // end of a segment's text (helper.rs:343-431 for the run touching the right boundary)
-    SX_HD void segment_end(bool invalid_after) {
-        if (run_n > 0) {
-            const bool completes = at_left && last_cut;
-            const bool again = !completes && !invalid_after;
-            if (again) {
-                if (m == 1 && !in_first_run) s1_later_yield = true;
-                has_left = true;
-                left_k = run_n; left_s = run_s; left_e = run_e; left_hostcarry = run_hostcarry;
-                cut = false;
-            } else if (completes || run_n >= P->n) {
-                yield(completes, !invalid_after);
-            }
-        }
-        if (m == 1) in_first_run = false;
-        run_n = 0;
-    }
-    SX_HD void new_segment(int32_t next_rel) {  // finding_collection.rs:240-241 + helper.rs:171-200
-        m++;
-        last_cut = cut;
-        cut = false;
-        at_left = true;
-        run_n = 0; run_hostcarry = false;
-        prec = PREC_EXACT;
-        seg_rel = next_rel;
-        probe_pending = (next_rel == slice_rel);
-        has_left = false;
-    }
-    // a malformed sequence: the segment ends here and the next one starts at next_rel
-    SX_HD void brk(int32_t next_rel) {
-        if (run_n > 0 && (run_n >= P->n || (at_left && last_cut))) segment_end(true);
-        if (m == 1) in_first_run = false;
-        new_segment(next_rel);
-    }
-    SX_HD void qcut() {  // helper.rs:237 exit 2, :353-355, :418-421
-        yield(at_left && last_cut, true);
-        at_left = true;
-        last_cut = true;
-        run_n = 0; run_hostcarry = false;
-    }
-    SX_HD void breaker_yield() {
-        yield(at_left && last_cut, false);
-        last_cut = false;
-    }
-    SX_HD void chr(bool pass, int32_t cs, int32_t ce) {
-        if (pass) {
-            if (run_n == 0) run_s = cs;
-            run_n++;
-            run_e = ce;
-            if (in_first_run && a < 0xFFFFu) a++;
-            if (run_n >= P->q) qcut();
-        } else {
-            if (m == 1) s1_all_pass = false;
-            if (m == 2) s2_all_pass = false;
-            if (run_n > 0 && ((last_cut && at_left) || run_n >= P->n)) breaker_yield();
-            in_first_run = false;
-            run_n = 0; run_hostcarry = false;
-            at_left = false;
-        }
-    }
-    SX_HD Carry carry_out(int32_t boundary_rel) const {
-        if (cut) return carry_cut();
-        if (has_left) {
-            Carry c;
-            c.kind = K_L; c.flags = left_hostcarry ? CF_HOSTCARRY : 0; c.k = (uint16_t)left_k;
-            c.in_bytes = (uint32_t)(boundary_rel - left_s);
-            c.out_bytes = (uint32_t)(left_e - left_s);
-            return c;
-        }
-        return carry_none();
-    }
+// hot-state flag bits
+enum : uint32_t {
+    FF_LASTCUT = 1u << 0,    // SplitStr.last_s_was_maybe_cut
+    FF_ATLEFT = 1u << 1,     // ok_s_p == inp_start_p for the current run
+    FF_CUT = 1u << 2,        // last_window_str_was_printed_and_is_maybe_cut_str
+    FF_PROBE = 1u << 3,      // Precision::Before probe still possible for this segment
+    FF_HOSTCARRY = 1u << 4,  // current run starts with text carried in the host ScannerState
+    FF_INFIRST = 1u << 5,    // inside the first run of segment 1
+    FF_S1ALL = 1u << 6,
+    FF_S1LATER = 1u << 7,
+    FF_S2ALL = 1u << 8,
+    FF_HASLEFT = 1u << 9,
+    FF_LEFTHC = 1u << 10
 };
 
 // TileSrc additionally provides `const Utf8Tables* tables()`.
@@ -229,74 +125,157 @@ SX_HD_NOINLINE void scan_window_fast_utf8(const ScanParams& P, const TileSrc& ts
                                           const Carry& kin, int mode, Record* wr, uint64_t text_off, WinResult& res,
                                           WinDesc* desc) {
     const Utf8Tables& T = *tsrc.tables();
+    const uint32_t n = P.n, q = P.q;
     // decoder state at the window start from the preceding bytes (DecUtf8::init), mapped onto the table DFA
     DecUtf8 d0;
     d0.init(P, tsrc, geo.ws);
-    uint32_t st = 0;
-    bool cur_pass = false;
+    uint32_t st = 0, cur_pass = 0;
     int32_t seq_s = 0;
     const int32_t pend0 = d0.pending_len();
     if (d0.need) {
-        const uint32_t rem = d0.need - d0.seen;
-        if (d0.seen == 0) st = utf8_neutral_entry(utf8_class(d0.lead)) & 7u;
-        else st = rem;  // 1 or 2 plain continuation bytes left
-        cur_pass = T.pass[d0.lead] != 0;
+        st = d0.seen == 0 ? (utf8_neutral_entry(utf8_class(d0.lead)) & 7u) : (d0.need - d0.seen);
+        cur_pass = T.pass[d0.lead];
         seq_s = -pend0;
     }
-    FastAuto A;
-    A.init(&P, mode, geo.ws, (int32_t)(geo.slice_start - geo.ws));
-    A.wr = wr; A.text_off = text_off;
-    if (geo.ws == geo.slice_start) A.slice_left = kin;
-    A.first_segment(kin, pend0);
+    FastEmit E;
+    E.P = &P; E.base = geo.ws; E.mode = mode; E.wr = wr; E.text_off = text_off; E.nrec = 0; E.ntext = 0;
+    const int32_t slice_rel = (int32_t)(geo.slice_start - geo.ws);
     const int32_t wlen = (int32_t)(geo.we - geo.ws);
+    const Carry slice_left = kin;  // only read by the probe when the window starts a slice
+
+    // ---- first segment (finding_collection.rs:101-116, :211-241) ----
+    uint32_t fl = FF_ATLEFT | FF_INFIRST | FF_S1ALL | FF_S2ALL;
+    if (kin.kind == K_C) fl |= FF_LASTCUT;
+    if (slice_rel == 0) fl |= FF_PROBE;
+    uint32_t m = 1, a = 0, run_n = 0, prec = PREC_EXACT;
+    int32_t seg_rel = 0, run_s = 0, run_e = 0;
+    uint32_t left_k = 0;
+    int32_t left_s = 0, left_e = 0;
+    if (kin.kind == K_L && kin.k > 0) {
+        run_n = kin.k;
+        run_s = -(int32_t)kin.in_bytes;
+        run_e = -pend0;
+        if (kin.flags & CF_HOSTCARRY) fl |= FF_HOSTCARRY;
+        prec = PREC_BEFORE;
+    }
+
+#define SX_COMPLETES ((fl & (FF_ATLEFT | FF_LASTCUT)) == (FF_ATLEFT | FF_LASTCUT))
+#define SX_YIELD(completes_, maybe_cut_)                                                              \
+    do {                                                                                              \
+        if (m == 1 && !(fl & FF_INFIRST)) fl |= FF_S1LATER;                                           \
+        fast_emit(&E, seg_rel, prec, run_s, run_e, (completes_) ? 1u : 0u, fl & FF_HOSTCARRY);        \
+        fl = (maybe_cut_) ? (fl | FF_CUT) : (fl & ~FF_CUT);                                           \
+        fl &= ~FF_HASLEFT;                                                                            \
+        prec = PREC_AFTER;                                                                            \
+    } while (0)
+    // a malformed sequence: the segment ends (invalid_after) and the next one starts at next_rel
+#define SX_BRK(next_rel_)                                                                             \
+    do {                                                                                              \
+        if (run_n > 0 && (run_n >= n || SX_COMPLETES)) { const bool c_ = SX_COMPLETES; SX_YIELD(c_, false); } \
+        m++;                                                                                          \
+        fl = (fl & ~(FF_LASTCUT | FF_INFIRST | FF_HOSTCARRY | FF_HASLEFT | FF_PROBE | FF_CUT)) | FF_ATLEFT | \
+             ((fl & FF_CUT) ? FF_LASTCUT : 0u) | (((next_rel_) == slice_rel) ? FF_PROBE : 0u);        \
+        run_n = 0;                                                                                    \
+        prec = PREC_EXACT;                                                                            \
+        seg_rel = (next_rel_);                                                                        \
+    } while (0)
+#define SX_CHR(pass_, cs_, ce_)                                                                       \
+    do {                                                                                              \
+        if (pass_) {                                                                                  \
+            if (run_n == 0) run_s = (cs_);                                                            \
+            run_n++;                                                                                  \
+            run_e = (ce_);                                                                            \
+            if (fl & FF_INFIRST) a++;                                                                 \
+            if (run_n >= q) { /* helper.rs:237 exit 2, :353-355, :418-421 */                          \
+                const bool c_ = SX_COMPLETES;                                                         \
+                SX_YIELD(c_, true);                                                                   \
+                fl = (fl | FF_ATLEFT | FF_LASTCUT) & ~FF_HOSTCARRY;                                   \
+                run_n = 0;                                                                            \
+            }                                                                                         \
+        } else {                                                                                      \
+            if (m == 1) fl &= ~FF_S1ALL;                                                              \
+            if (m == 2) fl &= ~FF_S2ALL;                                                              \
+            if (run_n > 0 && (run_n >= n || SX_COMPLETES)) { /* helper.rs:315-322 */                   \
+                const bool c_ = SX_COMPLETES;                                                         \
+                SX_YIELD(c_, false);                                                                  \
+                fl &= ~FF_LASTCUT;                                                                    \
+            }                                                                                         \
+            fl &= ~(FF_INFIRST | FF_HOSTCARRY | FF_ATLEFT);                                           \
+            run_n = 0;                                                                                \
+        }                                                                                             \
+    } while (0)
+
     tsrc.for_each_byte(geo.ws, geo.we, [&](uint32_t b, int64_t pos) {
         const int32_t p = (int32_t)(pos - geo.ws);
         const uint32_t t = T.trans[(st << 4) | T.cls[b]];
         st = t & 7u;
-        if (t & FT_PRE) A.brk(p);
+        if (t & FT_PRE) SX_BRK(p);
         const uint32_t ev = (t >> 3) & 3u;
         if (ev == FE_ASCII) {
-            A.probe_pending = false;  // an ASCII first char never triggers the probe (finding_collection.rs:176)
-            A.chr(T.pass[b] != 0, p, p + 1);
+            fl &= ~FF_PROBE;  // an ASCII first char never triggers the probe (finding_collection.rs:176)
+            const uint32_t ps = T.pass[b];
+            SX_CHR(ps, p, p + 1);
         } else if (ev == FE_CHAR) {
-            if (A.probe_pending) {
-                A.probe_pending = false;
-                if (mode != MODE_STATE) {
-                    const Carry sl = A.slice_left;  // a copy: the probe is out of line and takes references
-                    if (probe_utf8(P, g, geo.slice_start, geo.slice_end, A.m == 1, pend0, sl)) A.prec = PREC_BEFORE;
-                }
+            if (fl & FF_PROBE) {
+                fl &= ~FF_PROBE;
+                if (mode != MODE_STATE && probe_utf8(P, g, geo.slice_start, geo.slice_end, m == 1, pend0, slice_left))
+                    prec = PREC_BEFORE;
             }
-            A.chr(cur_pass, seq_s, p + 1);
+            SX_CHR(cur_pass, seq_s, p + 1);
         } else if (ev == FE_MAL) {
-            A.brk(p + 1);
+            SX_BRK(p + 1);
         }
-        if (t & FT_LEAD) { cur_pass = T.pass[b] != 0; seq_s = p; }
+        if (t & FT_LEAD) { cur_pass = T.pass[b]; seq_s = p; }
     });
+
+    // ---- end of the window's last segment (helper.rs:343-431 for the run touching the right boundary) ----
+    const bool invalid_after = geo.final_last;
+    if (run_n > 0) {
+        const bool completes = SX_COMPLETES;
+        if (!completes && !invalid_after) {  // `again`: kept as leftover (finding_collection.rs:281-284)
+            if (m == 1 && !(fl & FF_INFIRST)) fl |= FF_S1LATER;
+            fl |= FF_HASLEFT;
+            fl = (fl & FF_HOSTCARRY) ? (fl | FF_LEFTHC) : (fl & ~FF_LEFTHC);
+            left_k = run_n; left_s = run_s; left_e = run_e;
+            fl &= ~FF_CUT;
+        } else if (completes || run_n >= n) {
+            SX_YIELD(completes, !invalid_after);
+        }
+    }
+#undef SX_CHR
+#undef SX_BRK
+#undef SX_YIELD
+#undef SX_COMPLETES
     if (geo.final_last) {
-        A.segment_end(true);
-        A.cut = false;
-        A.has_left = false;
+        // finding_collection.rs:298-304: one flush round; lasting effects: reset decoder, cut == false
+        fl &= ~(FF_CUT | FF_HASLEFT);
         res.npend_out = 0;
     } else {
-        A.segment_end(false);
         res.npend_out = st ? (wlen - seq_s) : 0;
     }
-    res.out = A.carry_out(wlen);
-    res.nrec = A.nrec;
-    res.ntext = A.ntext;
+    if (fl & FF_CUT) res.out = carry_cut();
+    else if (fl & FF_HASLEFT) {
+        Carry c;
+        c.kind = K_L; c.flags = (fl & FF_LEFTHC) ? CF_HOSTCARRY : 0; c.k = (uint16_t)left_k;
+        c.in_bytes = (uint32_t)(wlen - left_s);
+        c.out_bytes = (uint32_t)(left_e - left_s);
+        res.out = c;
+    } else res.out = carry_none();
+    res.nrec = E.nrec;
+    res.ntext = E.ntext;
     if (desc) {
-        desc->a = (uint16_t)A.a;
-        desc->nrec = (uint16_t)(A.nrec > 0xFFFFu ? 0xFFFFu : A.nrec);
-        desc->ntext = A.ntext;
+        desc->a = (uint16_t)(a > 0xFFFFu ? 0xFFFFu : a);
+        desc->nrec = (uint16_t)(E.nrec > 0xFFFFu ? 0xFFFFu : E.nrec);
+        desc->ntext = E.ntext;
         desc->null_out = res.out;
         desc->t_out = 0;
         desc->pad = 0;
-        const bool single_all_pass = (A.m == 1 && A.s1_all_pass);
+        const bool single_all_pass = (m == 1 && (fl & FF_S1ALL));
         if (geo.final_last) desc->type = WT_CONST;
         else if (single_all_pass) {
-            if (A.a < P.q) { desc->type = WT_CASEB; desc->t_out = (uint16_t)(A.has_left ? (A.left_e - A.left_s) : 0); }
+            if (a < q) { desc->type = WT_CASEB; desc->t_out = (uint16_t)((fl & FF_HASLEFT) ? (left_e - left_s) : 0); }
             else desc->type = WT_CONST;
-        } else if (A.a > 0 && !A.s1_later_yield && (A.m == 1 || (A.m == 2 && A.s2_all_pass))) desc->type = WT_DEP;
+        } else if (a > 0 && !(fl & FF_S1LATER) && (m == 1 || (m == 2 && (fl & FF_S2ALL)))) desc->type = WT_DEP;
         else desc->type = WT_CONST;
     }
 }
