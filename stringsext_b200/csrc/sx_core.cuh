@@ -138,7 +138,10 @@ struct WinResult {
     int32_t npend_out;  // bytes still inside the decoder at the window end
 };
 
-enum : int { MODE_STATE = 0, MODE_COUNT = 1, MODE_WRITE = 2 };
+// MODE_BUFFER: count, and also write the first kBufRecs records (text_off relative to the window's first
+// record) into a small per-lane staging buffer, so most windows need no second (write) pass.
+enum : int { MODE_STATE = 0, MODE_COUNT = 1, MODE_WRITE = 2, MODE_BUFFER = 3 };
+constexpr uint32_t kBufRecs = 2;
 
 // ------------------------------------------------------------------------------------------
 // The streaming SplitStr + chunk-loop automaton.
@@ -215,7 +218,7 @@ struct WinAuto {
 
     SX_HD void yield(bool completes, bool maybe_cut) {
         if (m == 1 && !in_first_run) s1_later_yield = true;
-        if (mode == MODE_WRITE) {
+        if (mode == MODE_WRITE || (mode == MODE_BUFFER && nrec < kBufRecs)) {
             Record r;
             r.position = P->base_consumed + (uint64_t)seg_pos;  // finding_collection.rs:260
             r.in_start = run_in_start;

@@ -139,6 +139,10 @@ struct ExactSmem {
     int32_t last_npend;
     Utf8Tables tables;
     uint32_t cta_off[kMaxPrefCtas + 1];
+    Record staged[kThreads][kBufRecs];  // MODE_BUFFER staging, one slot set per lane
+    uint16_t cnt_r[kThreads];           // records / text bytes of the entry under its real carry (isolated entries)
+    uint32_t cnt_t[kThreads];
+    uint8_t have_cnt[kThreads];
 };
 
 // entry index -> window index: binary search of the owning prefilter CTA's region (offsets staged in smem)
@@ -174,23 +178,39 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
         adj = e > 0 && list_window(X, S.cta_off, e - 1) == w - 1;
         next_adj = e + 1 < NE && list_window(X, S.cta_off, e + 1) == w + 1;
         geo.window(w, wg);
-        WinResult r;
-        WindowEngine<Dec>::run(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
-        S.desc[i] = d;
+        S.have_cnt[i] = 0;
+        S.out_done[i] = 0;
         if (!adj) {
-            if (w == 0) S.kin[i] = P.k0;
+            // isolated entry (or the head of a run): the carry-in is known right away, so one pass under the
+            // real carry gives carry-out, counts and (staged) records
+            Carry kin0;
+            if (w == 0) kin0 = P.k0;
             else {
                 const WinGeom rg = preroll_geom(geo, w, X.pre_bytes);
                 WinResult rr;
                 WindowEngine<Dec>::run(P, ts, g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
-                S.kin[i] = rr.out;
+                kin0 = rr.out;
             }
+            WinResult r;
+            WindowEngine<Dec>::run(P, ts, g, wg, kin0, full ? MODE_BUFFER : MODE_STATE, &S.staged[i][0], 0, r, nullptr);
+            S.kin[i] = kin0;
             S.in_known[i] = 1;
+            S.kout[i] = r.out;
+            S.out_done[i] = 1;
+            S.cnt_r[i] = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
+            S.cnt_t[i] = r.ntext;
+            S.have_cnt[i] = 1;
+            d.type = WT_CONST;  // resolved: propagate like a constant window
+            d.null_out = r.out;
+            if (i == nblk - 1) S.last_npend = r.npend_out;
+        } else {
+            WinResult r;
+            WindowEngine<Dec>::run(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
+            if (i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
+            else S.in_known[i] = 0;
+            if (i == nblk - 1) S.last_npend = r.npend_out;
         }
-        else if (i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
-        else S.in_known[i] = 0;
-        S.out_done[i] = 0;
-        if (i == nblk - 1) S.last_npend = r.npend_out;
+        S.desc[i] = d;
     }
     __syncthreads();
     if (active && d.type == WT_CONST) {
@@ -234,13 +254,23 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
     if (active) {
         kin = S.kin[i];
         kout = S.kout[i];
-        emit = needs_emit(P, d, kin);
-        if (emit) {
-            if (carry_is_null(kin) && d.nrec != 0xFFFFu) { cr = d.nrec; ct = d.ntext; }
+        if (S.have_cnt[i]) {
+            if (S.cnt_r[i] != 0xFFFFu) { cr = S.cnt_r[i]; ct = S.cnt_t[i]; }
             else {
                 WinResult r;
                 WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, r, nullptr);
                 cr = r.nrec; ct = r.ntext;
+            }
+            emit = cr != 0;
+        } else {
+            emit = needs_emit(P, d, kin);
+            if (emit) {
+                if (carry_is_null(kin) && d.nrec != 0xFFFFu && !S.have_cnt[i]) { cr = d.nrec; ct = d.ntext; }
+                else {
+                    WinResult r;
+                    WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, r, nullptr);
+                    cr = r.nrec; ct = r.ntext;
+                }
             }
         }
         // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an
@@ -272,8 +302,16 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
     if ((br + tr <= O.rec_cap) && (bt + tt <= O.text_cap)) {
         uint32_t ro = er, to = et;
         if (emit && cr) {
-            WinResult r;
-            WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+            if (S.have_cnt[i] && cr <= kBufRecs) {  // staged by the single pass: patch the text offsets and copy
+                for (uint32_t k = 0; k < cr; ++k) {
+                    Record r = S.staged[i][k];
+                    r.text_off += bt + to;
+                    O.recs[br + ro + k] = r;
+                }
+            } else {
+                WinResult r;
+                WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+            }
         }
         ro += cr; to += ct;
         if (ext && xr) {

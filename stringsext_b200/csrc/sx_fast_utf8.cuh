@@ -88,7 +88,7 @@ struct FastEmit {
 SX_HD_NOINLINE void fast_emit(FastEmit* E, int32_t seg_rel, uint32_t prec, int32_t run_s, int32_t run_e, uint32_t completes,
                               uint32_t hostcarry) {
     const uint32_t len = (uint32_t)(run_e - run_s);
-    if (E->mode == MODE_WRITE) {
+    if (E->mode == MODE_WRITE || (E->mode == MODE_BUFFER && E->nrec < kBufRecs)) {
         Record r;
         r.position = E->P->base_consumed + (uint64_t)(E->base + seg_rel);  // finding_collection.rs:260
         r.in_start = E->base + run_s;
