@@ -180,10 +180,11 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
         geo.window(w, wg);
         S.have_cnt[i] = 0;
         S.out_done[i] = 0;
+        // Isolated entries (and heads of runs) know their carry-in right away (pre-roll of the unlisted
+        // predecessor): ONE pass under the real carry gives carry-out, counts and staged records.  Members of
+        // a run are summarised under the null carry.  Both use the SAME call so the warp stays converged.
+        Carry kin0 = carry_none();
         if (!adj) {
-            // isolated entry (or the head of a run): the carry-in is known right away, so one pass under the
-            // real carry gives carry-out, counts and (staged) records
-            Carry kin0;
             if (w == 0) kin0 = P.k0;
             else {
                 const WinGeom rg = preroll_geom(geo, w, X.pre_bytes);
@@ -191,24 +192,24 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
                 WindowEngine<Dec>::run(P, ts, g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
                 kin0 = rr.out;
             }
-            WinResult r;
-            WindowEngine<Dec>::run(P, ts, g, wg, kin0, full ? MODE_BUFFER : MODE_STATE, &S.staged[i][0], 0, r, nullptr);
+        }
+        WinResult r;
+        WinDesc dsum;
+        const int mode1 = adj ? MODE_COUNT : (full ? MODE_BUFFER : MODE_STATE);
+        WindowEngine<Dec>::run(P, ts, g, wg, kin0, mode1, &S.staged[i][0], 0, r, adj ? &dsum : nullptr);
+        if (i == nblk - 1) S.last_npend = r.npend_out;
+        if (!adj) {
             S.kin[i] = kin0;
             S.in_known[i] = 1;
-            S.kout[i] = r.out;
-            S.out_done[i] = 1;
             S.cnt_r[i] = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
             S.cnt_t[i] = r.ntext;
             S.have_cnt[i] = 1;
-            d.type = WT_CONST;  // resolved: propagate like a constant window
+            d.type = WT_CONST;  // resolved: propagates like a constant window
             d.null_out = r.out;
-            if (i == nblk - 1) S.last_npend = r.npend_out;
         } else {
-            WinResult r;
-            WindowEngine<Dec>::run(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r, &d);
+            d = dsum;
             if (i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
             else S.in_known[i] = 0;
-            if (i == nblk - 1) S.last_npend = r.npend_out;
         }
         S.desc[i] = d;
     }
@@ -342,14 +343,14 @@ sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const Exa
     __shared__ ExactSmem S;
     Geometry geo;
     geo.init(P);
+    const long long NE = X.list ? (long long)*X.ne_ptr : X.ne_static;
+    const long long e0 = (long long)blockIdx.x * kThreads;
+    if (e0 >= NE) return;  // the grid is sized for the worst case (every window listed)
     if (P.enc == ENC_UTF8)
         for (uint32_t k = threadIdx.x; k < 256; k += kThreads) utf8_tables_fill(P, S.tables, k);
     if (X.list)
         for (uint32_t k = threadIdx.x; k <= X.ncta; k += kThreads) S.cta_off[k] = X.cta_off[k];
     __syncthreads();
-    const long long NE = X.list ? (long long)*X.ne_ptr : X.ne_static;
-    const long long e0 = (long long)blockIdx.x * kThreads;
-    if (e0 >= NE) return;
     const uint32_t nblk = (uint32_t)((NE - e0) < (long long)kThreads ? (NE - e0) : (long long)kThreads);
     Carry c = carry_none();
     const bool first_adj = e0 > 0 && list_window(X, S.cta_off, e0 - 1) == list_window(X, S.cta_off, e0) - 1;
