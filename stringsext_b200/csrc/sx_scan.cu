@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace sx {
@@ -798,46 +799,84 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     }
 
     const auto t_post = std::chrono::steady_clock::now();
-    // ---- build the collection in stream order (tiles are contiguous record blocks) -------------------
-    // at most two records (the first piece of a run that began in the previous call and the final leftover)
-    // carry host text in front of their device text
+    // ---- build the collection in stream order (blocks own contiguous record ranges) -------------------
+    // At most two records carry host text in front of their device text: the very first record (a run that
+    // began in the previous call) and the final leftover pseudo record, which is always the last one.
     const size_t extra_text = 2 * (ss->leftover.size() + 8 * (size_t)q + 64);
     fc->text.resize(ntext + extra_text + 1);
-    if (ntext) memcpy(fc->text.data(), text, ntext);
-    size_t extra_off = ntext;
-    fc->v.reserve(nrec);
     std::vector<uint8_t> new_leftover;
     bool have_leftover = false;
-    for (size_t t = 0; t < (nrec ? nblocks : 0); ++t) {
-        const size_t b = tiles[t].x, c = tiles[t].y;
-        for (size_t i = b; i < b + c && i < nrec; ++i) {
-            const Record& r = recs[i];
-            const uint8_t* s = fc->text.data() + r.text_off;
-            size_t s_len = r.text_len;
-            if (r.flags & RF_HOSTCARRY) {  // prepend the text the previous call left in the ScannerState
-                uint8_t* d = fc->text.data() + extra_off;
-                memcpy(d, ss->leftover.data(), ss->leftover.size());
-                memcpy(d + ss->leftover.size(), s, r.text_len);
-                s = d;
-                s_len = ss->leftover.size() + r.text_len;
-                extra_off += s_len;
+    if (nrec) {
+        std::vector<size_t> out_off(nblocks + 1);
+        size_t acc = 0, last_block = 0;
+        for (size_t t = 0; t < nblocks; ++t) { out_off[t] = acc; acc += tiles[t].y; if (tiles[t].y) last_block = t; }
+        out_off[nblocks] = acc;
+        const uint2 lb = tiles[last_block];
+        const bool tail_is_leftover = (recs[(size_t)lb.x + lb.y - 1].flags & RF_LEFTOVER) != 0;
+        const size_t n_out = acc - (tail_is_leftover ? 1 : 0);
+        fc->v.resize(n_out);
+        uint8_t* const tbase = fc->text.data();
+        sx_finding* const out = fc->v.data();
+        const int16_t fid = (int16_t)input_file_id;
+        const uint8_t mid = ss->m.mission_id;
+        auto fill = [&](size_t t0, size_t t1) {
+            for (size_t t = t0; t < t1; ++t) {
+                const Record* r = recs + tiles[t].x;
+                size_t o = out_off[t];
+                for (size_t k = 0; k < tiles[t].y; ++k, ++r, ++o) {
+                    if (o >= n_out) break;  // the trailing leftover pseudo record
+                    sx_finding f;
+                    f.position = r->position;
+                    f.precision = (uint8_t)r->precision;
+                    f.completes_previous = (r->flags & RF_COMPLETES) ? 1 : 0;
+                    f.input_file_id = fid;
+                    f.mission_id = mid;
+                    f.s = tbase + r->text_off;
+                    f.s_len = r->text_len;
+                    f.in_start = r->in_start;
+                    f.in_len = r->in_len;
+                    out[o] = f;
+                }
             }
-            if (r.flags & RF_LEFTOVER) {
-                new_leftover.assign(s, s + s_len);
-                have_leftover = true;
-                continue;
-            }
-            sx_finding f;
-            f.position = r.position;
-            f.precision = (uint8_t)r.precision;
-            f.completes_previous = (r.flags & RF_COMPLETES) ? 1 : 0;
-            f.input_file_id = (int16_t)input_file_id;
-            f.mission_id = ss->m.mission_id;
-            f.s = s;
-            f.s_len = (uint32_t)s_len;
-            f.in_start = r.in_start;
-            f.in_len = r.in_len;
-            fc->v.push_back(f);
+        };
+        const unsigned nthreads = acc > 65536 ? std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        if (nthreads <= 1) {
+            if (ntext) memcpy(tbase, text, ntext);
+            fill(0, nblocks);
+        } else {  // memory bound: split the copy of the text arena and the record conversion over a few threads
+            std::vector<std::thread> th;
+            for (unsigned k = 0; k < nthreads; ++k)
+                th.emplace_back([&, k]() {
+                    const size_t a0 = ntext * k / nthreads, a1 = ntext * (k + 1) / nthreads;
+                    if (a1 > a0) memcpy(tbase + a0, text + a0, a1 - a0);
+                    fill(nblocks * k / nthreads, nblocks * (k + 1) / nthreads);
+                });
+            for (auto& t : th) t.join();
+        }
+        size_t extra_off = ntext;
+        auto with_host_text = [&](const Record& r, const uint8_t** s, size_t* s_len) {
+            uint8_t* d = tbase + extra_off;
+            memcpy(d, ss->leftover.data(), ss->leftover.size());
+            memcpy(d + ss->leftover.size(), tbase + r.text_off, r.text_len);
+            *s = d;
+            *s_len = ss->leftover.size() + r.text_len;
+            extra_off += *s_len;
+        };
+        // first record in stream order
+        size_t fb = 0;
+        while (fb < nblocks && tiles[fb].y == 0) ++fb;
+        if (n_out > 0 && fb < nblocks && (recs[tiles[fb].x].flags & RF_HOSTCARRY)) {
+            const uint8_t* s; size_t sl;
+            with_host_text(recs[tiles[fb].x], &s, &sl);
+            out[0].s = s;
+            out[0].s_len = (uint32_t)sl;
+        }
+        if (tail_is_leftover) {
+            const Record& r = recs[(size_t)lb.x + lb.y - 1];
+            const uint8_t* s = tbase + r.text_off; size_t sl = r.text_len;
+            if (r.flags & RF_HOSTCARRY) with_host_text(r, &s, &sl);
+            new_leftover.assign(s, s + sl);
+            have_leftover = true;
         }
     }
 
