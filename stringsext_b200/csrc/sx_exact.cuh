@@ -57,7 +57,13 @@ struct GlobalTile {
     int64_t len;
     bool aligned16;
     const Utf8Tables* tab;
+    uint32_t tab_smem;  // 32-bit shared-memory address of tab->tt
     __device__ __forceinline__ const Utf8Tables* tables() const { return tab; }
+    __device__ __forceinline__ uint32_t lut(uint32_t i) const {
+        uint32_t v;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(tab_smem + i));
+        return v;
+    }
     __device__ __forceinline__ uint8_t get(int64_t off) const { return g.get(off); }
     __device__ __forceinline__ uint4 load_chunk(int64_t r16, int64_t ws, int64_t we) const {
         if (r16 >= we) return make_uint4(0, 0, 0, 0);
@@ -163,7 +169,8 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
                             long long NE, long long e0, uint32_t nblk, bool full, Carry carry_in, long long block_id) {
     const uint32_t i = threadIdx.x;
     const GlobalSrc g{P.in, P.pend};
-    const GlobalTile ts{g, P.len, X.in_aligned16 != 0, P.enc == ENC_UTF8 ? &S.tables : nullptr};
+    const GlobalTile ts{g, P.len, X.in_aligned16 != 0, P.enc == ENC_UTF8 ? &S.tables : nullptr,
+                        (uint32_t)__cvta_generic_to_shared(&S.tables.tt[0])};
     const bool active = i < nblk;
     long long w = -1;
     bool adj = false, next_adj = false;
@@ -347,7 +354,7 @@ sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const Exa
     const long long e0 = (long long)blockIdx.x * kThreads;
     if (e0 >= NE) return;  // the grid is sized for the worst case (every window listed)
     if (P.enc == ENC_UTF8)
-        for (uint32_t k = threadIdx.x; k < 256; k += kThreads) utf8_tables_fill(P, S.tables, k);
+        for (uint32_t k = threadIdx.x; k < 2048; k += kThreads) utf8_tables_fill(P, S.tables, k);
     if (X.list)
         for (uint32_t k = threadIdx.x; k <= X.ncta; k += kThreads) S.cta_off[k] = X.cta_off[k];
     __syncthreads();

@@ -15,13 +15,14 @@
 
 namespace sx {
 
+// One lookup per byte: tt[state << 8 | byte] = bits 0-2 next state, 3-4 event, 5 pre-malformed (the byte
+// offends a pending sequence: malformed first, then the byte is re-read in the neutral state), 6 lead latch,
+// 7 Utf8Filter verdict for a char whose UTF-8 lead byte is this byte (mission.rs:333-348).
 struct Utf8Tables {
-    uint8_t cls[256];    // byte class 0..11
-    uint8_t pass[256];   // Utf8Filter verdict for a char whose UTF-8 lead byte is b (mission.rs:333-348)
-    uint8_t trans[128];  // [state << 4 | class]: bits 0-2 next state, 3-4 event, 5 pre-malformed, 6 lead latch
+    uint8_t tt[8 * 256];
 };
 enum : uint32_t { FE_NONE = 0, FE_ASCII = 1, FE_CHAR = 2, FE_MAL = 3 };
-enum : uint32_t { FT_PRE = 0x20, FT_LEAD = 0x40 };
+enum : uint32_t { FT_PRE = 0x20, FT_LEAD = 0x40, FT_PASS = 0x80 };
 
 SX_HD uint32_t utf8_class(uint32_t b) {
     if (b < 0x80) return 0;
@@ -67,12 +68,13 @@ SX_HD uint32_t utf8_trans_entry(uint32_t s, uint32_t c) {
     default: ok = c1; ns = 2; break;
     }
     if (ok) return ns | (ev << 3);
-    return utf8_neutral_entry(c) | FT_PRE;  // the offending byte is not consumed: malformed first, then re-read in the neutral state
+    return utf8_neutral_entry(c) | FT_PRE;
 }
-SX_HD void utf8_tables_fill(const ScanParams& P, Utf8Tables& T, uint32_t i) {  // i in 0..255
-    T.cls[i] = (uint8_t)utf8_class(i);
-    T.pass[i] = (i < 0x80 || i >= 0xC0) ? (pass_filter(P, i) ? 1 : 0) : 0;
-    if (i < 128) T.trans[i] = (uint8_t)(((i & 15) < 12) ? utf8_trans_entry(i >> 4, i & 15) : 0);
+SX_HD void utf8_tables_fill(const ScanParams& P, Utf8Tables& T, uint32_t i) {  // i in 0..2047
+    const uint32_t b = i & 255u, st = i >> 8;
+    uint32_t t = utf8_trans_entry(st, utf8_class(b));
+    if ((b < 0x80 || b >= 0xC0) && pass_filter(P, b)) t |= FT_PASS;
+    T.tt[i] = (uint8_t)t;
 }
 
 // Cold state: only the out-of-line record writer touches it, so it may live in local memory while the
@@ -119,12 +121,12 @@ enum : uint32_t {
     FF_LEFTHC = 1u << 10
 };
 
-// TileSrc additionally provides `const Utf8Tables* tables()`.
+// TileSrc additionally provides `const Utf8Tables* tables()`, `lut(i)` (= tables()->tt[i], a 32-bit shared
+// memory load on the device) and `load_chunk(r16, ws, we)` (the 16 input bytes at aligned offset r16).
 template <class TileSrc>
 SX_HD_NOINLINE void scan_window_fast_utf8(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo,
                                           const Carry& kin, int mode, Record* wr, uint64_t text_off, WinResult& res,
                                           WinDesc* desc) {
-    const Utf8Tables& T = *tsrc.tables();
     const uint32_t n = P.n, q = P.q;
     // decoder state at the window start from the preceding bytes (DecUtf8::init), mapped onto the table DFA
     DecUtf8 d0;
@@ -134,7 +136,7 @@ SX_HD_NOINLINE void scan_window_fast_utf8(const ScanParams& P, const TileSrc& ts
     const int32_t pend0 = d0.pending_len();
     if (d0.need) {
         st = d0.seen == 0 ? (utf8_neutral_entry(utf8_class(d0.lead)) & 7u) : (d0.need - d0.seen);
-        cur_pass = T.pass[d0.lead];
+        cur_pass = tsrc.lut(d0.lead) & FT_PASS;
         seq_s = -pend0;
     }
     FastEmit E;
@@ -205,28 +207,49 @@ SX_HD_NOINLINE void scan_window_fast_utf8(const ScanParams& P, const TileSrc& ts
         }                                                                                             \
     } while (0)
 
-    tsrc.for_each_byte(geo.ws, geo.we, [&](uint32_t b, int64_t pos) {
-        const int32_t p = (int32_t)(pos - geo.ws);
-        const uint32_t t = T.trans[(st << 4) | T.cls[b]];
-        st = t & 7u;
-        if (t & FT_PRE) SX_BRK(p);
-        const uint32_t ev = (t >> 3) & 3u;
-        if (ev == FE_ASCII) {
-            fl &= ~FF_PROBE;  // an ASCII first char never triggers the probe (finding_collection.rs:176)
-            const uint32_t ps = T.pass[b];
-            SX_CHR(ps, p, p + 1);
-        } else if (ev == FE_CHAR) {
-            if (fl & FF_PROBE) {
-                fl &= ~FF_PROBE;
-                if (mode != MODE_STATE && probe_utf8(P, g, geo.slice_start, geo.slice_end, m == 1, pend0, slice_left))
-                    prec = PREC_BEFORE;
+    // ---- the byte loop: 16-byte chunks, three in flight, one copy of the body (rolled on purpose) ----
+    {
+        const int64_t ws = geo.ws, we = geo.we;
+        int64_t r16 = ws & ~(int64_t)15;
+        int32_t p = (int32_t)(r16 - ws);  // relative position of the chunk's first byte (may be negative for the head)
+        uint4 c0 = tsrc.load_chunk(r16, ws, we);
+        uint4 c1 = tsrc.load_chunk(r16 + 16, ws, we);
+        uint4 c2 = tsrc.load_chunk(r16 + 32, ws, we);
+        while (p < wlen) {
+            const uint4 c3 = tsrc.load_chunk(r16 + 48, ws, we);
+            uint32_t w0 = c0.x, w1 = c0.y, w2 = c0.z, w3 = c0.w;
+            const int32_t pe = (wlen - p) < 16 ? (wlen - p) : 16;
+#pragma unroll 1
+            for (int32_t i = 0; i < pe; ++i, ++p) {
+                const uint32_t b = w0 & 0xFFu;
+                w0 = (w0 >> 8) | (w1 << 24);  // 128-bit shift right by one byte (SHF on the device)
+                w1 = (w1 >> 8) | (w2 << 24);
+                w2 = (w2 >> 8) | (w3 << 24);
+                w3 >>= 8;
+                if (p < 0) continue;  // bytes before the window inside the first aligned chunk
+                const uint32_t t = tsrc.lut((st << 8) | b);
+                st = t & 7u;
+                if (t & FT_PRE) SX_BRK(p);
+                const uint32_t ev = (t >> 3) & 3u;
+                if (ev == FE_ASCII) {
+                    fl &= ~FF_PROBE;  // an ASCII first char never triggers the probe (finding_collection.rs:176)
+                    SX_CHR(t & FT_PASS, p, p + 1);
+                } else if (ev == FE_CHAR) {
+                    if (fl & FF_PROBE) {
+                        fl &= ~FF_PROBE;
+                        if (mode != MODE_STATE && probe_utf8(P, g, geo.slice_start, geo.slice_end, m == 1, pend0, slice_left))
+                            prec = PREC_BEFORE;
+                    }
+                    SX_CHR(cur_pass, seq_s, p + 1);
+                } else if (ev == FE_MAL) {
+                    SX_BRK(p + 1);
+                }
+                if (t & FT_LEAD) { cur_pass = t & FT_PASS; seq_s = p; }
             }
-            SX_CHR(cur_pass, seq_s, p + 1);
-        } else if (ev == FE_MAL) {
-            SX_BRK(p + 1);
+            r16 += 16;
+            c0 = c1; c1 = c2; c2 = c3;
         }
-        if (t & FT_LEAD) { cur_pass = T.pass[b]; seq_s = p; }
-    });
+    }
 
     // ---- end of the window's last segment (helper.rs:343-431 for the run touching the right boundary) ----
     const bool invalid_after = geo.final_last;

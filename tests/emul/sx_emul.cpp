@@ -2,11 +2,17 @@
 // (stringsext_b200/csrc/sx_core.cuh) sequentially on the CPU so that the window decomposition,
 // transfer-function classification and emit rules can be differential-tested against the oracle
 // without a GPU.  It is NOT part of the product library and nothing in stringsext_b200/ loads it.
+#include <stdint.h>
+#ifndef __CUDACC__
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return s ? (uint32_t)((((uint64_t)hi << 32) | lo) >> s) : lo; }
+#endif
 #include "../../stringsext_b200/csrc/sx_fast_utf8.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+
 
 using namespace sx;
 
@@ -15,6 +21,16 @@ static int g_use_fast = 1;
 struct HostTile {
     GlobalSrc g;
     const Utf8Tables* tables() const { return g_use_fast ? &g_tables : nullptr; }
+    uint32_t lut(uint32_t i) const { return g_tables.tt[i]; }
+    uint4 load_chunk(int64_t r16, int64_t ws, int64_t we) const {
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 16; ++i) {
+            const int64_t o = r16 + i;
+            if (o >= ws && o < we) w[i >> 2] |= (uint32_t)g.get(o) << ((i & 3) * 8);
+        }
+        uint4 v; v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
+        return v;
+    }
     uint8_t get(int64_t off) const { return g.get(off); }
     template <class F> void for_each_byte(int64_t ws, int64_t we, F&& f) const {
         for (int64_t p = ws; p < we; ++p) f((uint32_t)g.get(p), p);
@@ -138,7 +154,7 @@ struct emul_out {
 // Returns 0 on success.  `params` is a fully populated ScanParams (in = host pointer).
 void sx_emul_set_fast(int on) { g_use_fast = on; }
 int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
-    for (uint32_t i = 0; i < 256; ++i) utf8_tables_fill(*P, g_tables, i);
+    for (uint32_t i = 0; i < 2048; ++i) utf8_tables_fill(*P, g_tables, i);
     std::vector<uint32_t> list;
     std::vector<Record> recs;
     std::vector<uint8_t> text;
