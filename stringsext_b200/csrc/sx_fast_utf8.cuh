@@ -229,20 +229,54 @@ SX_HD_NOINLINE void scan_window_fast_utf8(const ScanParams& P, const TileSrc& ts
                 if (p < 0) continue;  // bytes before the window inside the first aligned chunk
                 const uint32_t t = tsrc.lut((st << 8) | b);
                 st = t & 7u;
-                if (t & FT_PRE) SX_BRK(p);
                 const uint32_t ev = (t >> 3) & 3u;
-                if (ev == FE_ASCII) {
-                    fl &= ~FF_PROBE;  // an ASCII first char never triggers the probe (finding_collection.rs:176)
-                    SX_CHR(t & FT_PASS, p, p + 1);
-                } else if (ev == FE_CHAR) {
-                    if (fl & FF_PROBE) {
-                        fl &= ~FF_PROBE;
-                        if (mode != MODE_STATE && probe_utf8(P, g, geo.slice_start, geo.slice_end, m == 1, pend0, slice_left))
-                            prec = PREC_BEFORE;
+                const bool pre = (t & FT_PRE) != 0;
+                const bool is_ascii = ev == FE_ASCII, is_char = ev == FE_CHAR, mal = ev == FE_MAL;
+                const bool pass = (is_ascii && (t & FT_PASS)) || (is_char && cur_pass);
+                const bool fail = (is_ascii || is_char) && !pass;
+                // Anything that prints, cuts or probes takes the (rare) general path below; every other
+                // transition is computed branch-free so that the 32 lanes of a warp stay converged.
+                const bool run_ends = pre || mal || fail;
+                const bool slow = (run_ends && run_n > 0 && (run_n >= n || SX_COMPLETES)) || (pass && !pre && run_n + 1 >= q) ||
+                                  (pass && pre && 1 >= q) || (is_char && (fl & FF_PROBE));
+                if (!slow) {
+                    const uint32_t nbrk = (pre ? 1u : 0u) + (mal ? 1u : 0u);
+                    if (nbrk) {  // malformed sequence(s): new segment (predicated, no yield needed)
+                        const int32_t nx = mal ? p + 1 : p;
+                        m += nbrk;
+                        fl = (fl & ~(FF_LASTCUT | FF_INFIRST | FF_HOSTCARRY | FF_HASLEFT | FF_PROBE | FF_CUT)) | FF_ATLEFT |
+                             ((nbrk == 1 && (fl & FF_CUT)) ? FF_LASTCUT : 0u) | ((nx == slice_rel) ? FF_PROBE : 0u);
+                        run_n = 0;
+                        prec = PREC_EXACT;
+                        seg_rel = nx;
                     }
-                    SX_CHR(cur_pass, seq_s, p + 1);
-                } else if (ev == FE_MAL) {
-                    SX_BRK(p + 1);
+                    if (is_ascii) fl &= ~FF_PROBE;
+                    if (pass) {
+                        const int32_t cs = is_ascii ? p : seq_s;
+                        run_s = run_n == 0 ? cs : run_s;
+                        run_n++;
+                        run_e = p + 1;
+                        a += (fl & FF_INFIRST) ? 1u : 0u;
+                    }
+                    if (fail) {
+                        fl &= ~((m == 1 ? FF_S1ALL : 0u) | (m == 2 ? FF_S2ALL : 0u) | FF_INFIRST | FF_HOSTCARRY | FF_ATLEFT);
+                        run_n = 0;
+                    }
+                } else {
+                    if (t & FT_PRE) SX_BRK(p);
+                    if (ev == FE_ASCII) {
+                        fl &= ~FF_PROBE;  // an ASCII first char never triggers the probe (finding_collection.rs:176)
+                        SX_CHR(t & FT_PASS, p, p + 1);
+                    } else if (ev == FE_CHAR) {
+                        if (fl & FF_PROBE) {
+                            fl &= ~FF_PROBE;
+                            if (mode != MODE_STATE && probe_utf8(P, g, geo.slice_start, geo.slice_end, m == 1, pend0, slice_left))
+                                prec = PREC_BEFORE;
+                        }
+                        SX_CHR(cur_pass, seq_s, p + 1);
+                    } else if (ev == FE_MAL) {
+                        SX_BRK(p + 1);
+                    }
                 }
                 if (t & FT_LEAD) { cur_pass = t & FT_PASS; seq_s = p; }
             }
