@@ -14,6 +14,7 @@
 #include "../../include/stringsext_b200.h"
 #include "sx_exact.cuh"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -128,14 +129,47 @@ __device__ __forceinline__ bool has_run128(const uint32_t* m, uint32_t T) {
     return (r[0] | r[1] | r[2] | r[3]) != 0;
 }
 
-template <int FAMILY>
+// TMA helpers (cp.async.bulk.tensor + mbarrier), sm_90+/sm_100a PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+constexpr uint32_t kPrefStageBytes = 32768;
+constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64;
+
+// DEFSHAPE (PF_UTF8 only): the default filter shape -- ASCII blocks 1..3 may pass, only 2-byte leads
+// (block 6) may pass -- with the block functions folded into single LOP3s.
+template <int FAMILY, bool DEFSHAPE>
 __global__ void __launch_bounds__(kPrefThreads, 3)
 sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const __grid_constant__ PrefK K, const PrefOut O,
-                    long long total_windows, long long ntiles) {
+                    long long total_windows, long long ntiles, const __grid_constant__ CUtensorMap tmap, uint32_t use_tma) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* sm = smem_raw;                                      // tile bytes, swizzled
-    uint32_t* s_trail = reinterpret_cast<uint32_t*>(sm + 32768);  // 256
-    uint32_t* s_iw = s_trail + 256;                               // 8 words of INTERESTING flags
+    // two 32 KiB stages (TMA SWIZZLE_128B layout == swz()), then the per-tile exchange arrays and the mbarriers
+    uint32_t* s_trail = reinterpret_cast<uint32_t*>(smem_raw + 2 * kPrefStageBytes);  // 256
+    uint32_t* s_iw = s_trail + 256;                                                   // 8 words
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_iw + 16);                         // 2 mbarriers
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = P.W, nchunk = W >> 4;
     const uint32_t tile_bytes = kPrefTileWin * W;
@@ -143,11 +177,40 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
     const long long t_end = (t_begin + O.tiles_per_cta) < ntiles ? (t_begin + O.tiles_per_cta) : ntiles;
     uint32_t* const my_list = O.list + (size_t)t_begin * kPrefTileWin;
     uint32_t kept = 0;  // windows this CTA has listed so far (uniform across the block)
+    const int64_t full_rows_bytes = (P.len >> 7) << 7;  // the tensor map covers whole 128-byte rows only
+
+    if (use_tma && t_begin < t_end) {
+        if (tid == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_bar[0], tile_bytes);
+            tma_load_2d(smem_raw, &tmap, &s_bar[0], 0, (int32_t)((t_begin * (long long)tile_bytes) >> 7));
+        }
+        __syncthreads();
+    }
 
     for (long long tile = t_begin; tile < t_end; ++tile) {
         const int64_t lo = (int64_t)tile * tile_bytes;
         const int64_t hi = (lo + tile_bytes) < P.len ? (lo + tile_bytes) : P.len;
-        // ---- stage the tile: coalesced 16-byte streaming loads, swizzled shared stores ------------------
+        const uint32_t it = (uint32_t)(tile - t_begin);
+        uint8_t* const sm = smem_raw + (it & 1u) * kPrefStageBytes;
+        if (use_tma) {
+            // ---- stage the tile with TMA, double buffered: the next tile is in flight while this one is classified
+            if (tid == 0 && tile + 1 < t_end) {
+                mbar_expect_tx(&s_bar[(it + 1) & 1u], tile_bytes);
+                tma_load_2d(smem_raw + ((it + 1) & 1u) * kPrefStageBytes, &tmap, &s_bar[(it + 1) & 1u], 0,
+                            (int32_t)(((tile + 1) * (long long)tile_bytes) >> 7));
+            }
+            mbar_wait(&s_bar[it & 1u], (it >> 1) & 1u);
+            if (hi > full_rows_bytes && lo <= full_rows_bytes) {  // ragged last row of the stream: plain loads
+                const int64_t o = full_rows_bytes + tid;
+                if (tid < 128) sm[swz((uint32_t)(o - lo))] = o < P.len ? P.in[o] : (uint8_t)0;
+                __syncthreads();
+            }
+        } else
+        // ---- fallback: coalesced 16-byte streaming loads, swizzled shared stores --------------------------
         {
             const uint32_t nbytes = (uint32_t)(hi - lo);
             const uint32_t nfull = nbytes >> 4;
@@ -157,8 +220,8 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                 const uint32_t o = nfull * 16u + tid;
                 sm[swz(o)] = o < nbytes ? P.in[lo + o] : (uint8_t)0;
             }
+            __syncthreads();
         }
-        __syncthreads();
 
         // ---- per-window classification -----------------------------------------------------------------
         const long long w = tile * kPrefTileWin + tid;
@@ -191,12 +254,13 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                         const uint32_t x = xs[j];
                         const uint32_t x1 = x << 1, x2 = x << 2;
                         if (FAMILY == PF_UTF8) {
-                            const uint32_t cn = x & ~x1;                                  // 10xxxxxx
-                            const uint32_t lp = x & x1 & lop3_sel(x2, K.kh[3], K.kh[2]);  // 11xxxxxx in a passing lead block
-                            const uint32_t ap = ~x & blk2(x1, x2, K.ka);
+                            const uint32_t cn = x & ~x1;  // 10xxxxxx
+                            // 11xxxxxx in a passing lead block / ASCII in a passing block
+                            const uint32_t lp = DEFSHAPE ? (x & x1 & ~x2) : (x & x1 & lop3_sel(x2, K.kh[3], K.kh[2]));
+                            const uint32_t ap = DEFSHAPE ? (~x & (x1 | x2)) : (~x & blk2(x1, x2, K.ka));
                             if (c > 0 || j > 0) {
                                 const uint32_t ncn = __funnelshift_r(pC, cn, 8);    // byte i: Cn(i + 1)
-                                const uint32_t lcp = pL | (pC & K.multi);
+                                const uint32_t lcp = DEFSHAPE ? pL : (pL | (pC & K.multi));
                                 const uint32_t pl = __funnelshift_l(ppLC, lcp, 8);  // byte i: LC(i - 1)
                                 put(4 * c + j - 1, pA | (pL & ncn) | (pC & pl));
                                 ppLC = lcp;
@@ -208,7 +272,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                     }
                     if (FAMILY == PF_UTF8 && (uint32_t)c == nchunk - 1) {  // flush the last word: right edge favourable
                         const uint32_t ncn = __funnelshift_r(pC, 0xFFFFFFFFu, 8);
-                        const uint32_t pl = __funnelshift_l(ppLC, pL | (pC & K.multi), 8);
+                        const uint32_t pl = __funnelshift_l(ppLC, DEFSHAPE ? pL : (pL | (pC & K.multi)), 8);
                         put(4 * c + 3, pA | (pL & ncn) | (pC & pl));
                     }
                     if ((c & 1) == 0 && (uint32_t)c == nchunk - 1) {  // odd number of chunks: half a mask word is pending
@@ -404,6 +468,7 @@ struct sx_scanner_state {
     uint32_t* d_coff = nullptr; size_t coff_cap = 0;
     uint32_t* d_list = nullptr; size_t list_cap = 0;
     int use_prefilter = 1;
+    int use_tma = 1;
     uint32_t last_ncta = 0; size_t last_region_stride = 0;
     // pinned host staging for result downloads
     Record* h_recs = nullptr; size_t h_recs_cap = 0;
@@ -510,6 +575,7 @@ size_t sx_scanner_state_leftover(const sx_scanner_state* ss, const uint8_t** p) 
 }
 void sx_scanner_state_last_stats(const sx_scanner_state* ss, sx_scan_stats* out) { *out = ss->stats; }
 void sx_scanner_state_set_prefilter(sx_scanner_state* ss, int enabled) { ss->use_prefilter = enabled ? 1 : 0; }
+void sx_scanner_state_set_tma(sx_scanner_state* ss, int enabled) { ss->use_tma = enabled ? 1 : 0; }
 size_t sx_scanner_state_last_window_list(const sx_scanner_state* ss, uint32_t* out, size_t cap) {
     if (!ss->stats.prefilter_used) return 0;
     const size_t n = (size_t)ss->stats.windows_listed;
@@ -597,15 +663,54 @@ static PrefK make_pref_k(const ScanParams& P, const PrefCfg& c) {
     return k;
 }
 
-static cudaError_t launch_prefilter(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
-                                    long long ntiles, int grid, cudaStream_t st) {
-    const size_t smem = 32768 + 1024 + 64;
-    switch (c.family) {
-    case PF_BYTE: sx_prefilter_kernel<PF_BYTE><<<grid, kPrefThreads, smem, st>>>(P, c, k, o, total_windows, ntiles); break;
-    case PF_UTF8: sx_prefilter_kernel<PF_UTF8><<<grid, kPrefThreads, smem, st>>>(P, c, k, o, total_windows, ntiles); break;
-    default: sx_prefilter_kernel<PF_UNIT><<<grid, kPrefThreads, smem, st>>>(P, c, k, o, total_windows, ntiles); break;
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2D view of the input as rows of 128 bytes; one box = one prefilter tile, 128-byte swizzle.
+static bool make_tensor_map(CUtensorMap* tm, const uint8_t* d_in, size_t len, uint32_t tile_bytes) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+        fn = (PFN_encodeTiled)p;
     }
+    const cuuint64_t rows = (cuuint64_t)(len >> 7);
+    if (rows == 0 || (reinterpret_cast<uintptr_t>(d_in) & 15u)) return false;
+    const cuuint64_t gdim[2] = {128, rows};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {128, tile_bytes >> 7};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(d_in), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int FAMILY, bool DEF>
+static cudaError_t launch_prefilter_t(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
+                                      long long ntiles, int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
+    static thread_local bool attr_done[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(sx_prefilter_kernel<FAMILY, DEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrefSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    sx_prefilter_kernel<FAMILY, DEF><<<grid, kPrefThreads, kPrefSmemBytes, st>>>(P, c, k, o, total_windows, ntiles, tm, use_tma);
     return cudaGetLastError();
+}
+
+static cudaError_t launch_prefilter(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
+                                    long long ntiles, int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
+    const bool defshape = c.family == PF_UTF8 && c.blkA == 0xEu && c.blkH == (1u << 6) && !c.multi;
+    switch (c.family) {
+    case PF_BYTE: return launch_prefilter_t<PF_BYTE, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma);
+    case PF_UTF8:
+        return defshape ? launch_prefilter_t<PF_UTF8, true>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma)
+                        : launch_prefilter_t<PF_UTF8, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma);
+    default: return launch_prefilter_t<PF_UNIT, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma);
+    }
 }
 
 static size_t utf8_char_count(const std::vector<uint8_t>& s) {
@@ -705,7 +810,11 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             const long long tiles_per_cta = (ntiles + pgrid - 1) / pgrid;
             pgrid = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
             const PrefOut po{ss->d_list, ss->d_ccount, tiles_per_cta};
-            CK(launch_prefilter(P, pc, pk, po, total_windows, ntiles, pgrid, st));
+            CUtensorMap tmap;
+            memset(&tmap, 0, sizeof tmap);
+            const uint32_t use_tma = (ss->use_tma && make_tensor_map(&tmap, d_in, len, kPrefTileWin * W)) ? 1u : 0u;
+            ss->stats.tma_used = use_tma;
+            CK(launch_prefilter(P, pc, pk, po, total_windows, ntiles, pgrid, st, tmap, use_tma));
             CK(cudaEventRecord(ss->ev[4], st));
             sx_list_offsets_kernel<<<1, 1024, 0, st>>>(ss->d_ccount, ss->d_coff, (uint32_t)pgrid, ss->d_counters);
             CK(cudaGetLastError());

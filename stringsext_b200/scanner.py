@@ -78,6 +78,7 @@ class ScanStats(C.Structure):
         ("kernel_launches", C.c_uint32),
         ("relaunches", C.c_uint32),
         ("prefilter_used", C.c_uint32),
+        ("tma_used", C.c_uint32),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
         ("n_records", C.c_uint64),
@@ -113,6 +114,7 @@ def load_library():
     L.sx_scanner_state_leftover.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint8))]
     L.sx_scanner_state_last_stats.argtypes = [C.c_void_p, C.POINTER(ScanStats)]
     L.sx_scanner_state_set_prefilter.argtypes = [C.c_void_p, C.c_int]
+    L.sx_scanner_state_set_tma.argtypes = [C.c_void_p, C.c_int]
     L.sx_scanner_state_last_window_list.restype = C.c_size_t
     L.sx_scanner_state_last_window_list.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_size_t]
     L.sx_finding_collection_from.restype = C.c_void_p
@@ -153,7 +155,7 @@ def exported_symbols() -> List[str]:
         "sx_device_count", "sx_scanner_state_new", "sx_scanner_state_free", "sx_scanner_state_reset", "sx_scanner_state_consumed_bytes",
         "sx_scanner_state_maybe_cut", "sx_scanner_state_leftover", "sx_finding_collection_from", "sx_scan_stream",
         "sx_fc_len", "sx_fc_get", "sx_fc_data", "sx_fc_first_byte_position", "sx_fc_str_buf_overflow", "sx_fc_free",
-        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
+        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
     ]
 
 
@@ -258,6 +260,9 @@ class ScannerState:
 
     def set_prefilter(self, enabled: bool) -> None:
         load_library().sx_scanner_state_set_prefilter(self._h, 1 if enabled else 0)
+
+    def set_tma(self, enabled: bool) -> None:
+        load_library().sx_scanner_state_set_tma(self._h, 1 if enabled else 0)
 
     def last_window_list(self) -> List[int]:
         L = load_library()

@@ -222,8 +222,16 @@ def test_prefilter_window_list_matches_spec(label, n, q, ubf, kind):
         got = gpu_findings(gs.scan_stream(buf, False, 4096))
         exp, _ = es.scan_stream(buf, False, 4096)
         assert gs.last_stats.prefilter_used == 1 and es.stats[7] == 1
+        assert gs.last_stats.tma_used == 1  # tiles staged with cp.async.bulk.tensor
         assert gs.last_window_list() == es.last_list
         assert got == exp
+        # the plain-load staging path must list the same windows
+        g2 = sx.ScannerState(m)
+        g2.set_tma(False)
+        if pend_prefix:
+            g2.scan_stream(pend_prefix, False, 4096)
+        got2 = gpu_findings(g2.scan_stream(buf, False, 4096))
+        assert g2.last_stats.tma_used == 0 and g2.last_window_list() == es.last_list and got2 == exp
 
 
 @pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
