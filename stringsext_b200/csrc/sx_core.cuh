@@ -872,6 +872,9 @@ struct PrefCfg {
     uint32_t T;       // run threshold in bytes
     uint32_t unit;    // PF_UNIT: 2 or 4
     uint32_t hi_pos;  // PF_UNIT: offset of the most significant byte inside a unit
+    uint32_t n_chars; // chars_min_nb
+    uint32_t refine;  // PF_UTF8: a long good-byte run only counts if it holds >= n_chars non-continuation bytes
+    uint32_t pre_bytes;  // pre-roll length: longest possible trailing good run of an uninteresting window + slack
 };
 
 // Reference (byte-wise) definition of G; the SWAR kernel must produce exactly these flags.
@@ -901,21 +904,26 @@ SX_HD bool pref_good(const ScanParams& P, const PrefCfg& c, const S& src, int64_
     return ((c.blkH >> (src.get(t) >> 5)) & 1u) != 0;
 }
 
-struct PrefWin { uint32_t lead, trail, maxrun; };
+struct PrefWin { uint32_t lead, trail, maxrun, maxchars; };  // maxchars: most non-continuation bytes in a run of >= T bytes
 template <class S>
 SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& src, int64_t ws, int64_t we) {
-    PrefWin r{0, 0, 0};
-    uint32_t run = 0;
+    PrefWin r{0, 0, 0, 0};
+    uint32_t run = 0, chars = 0;
     bool seen_bad = false;
+    auto close_run = [&]() { if (run >= c.T && chars > r.maxchars) r.maxchars = chars; };
     for (int64_t i = ws; i < we; ++i) {
         if (pref_good(P, c, src, i, ws, we)) {
             run++;
+            const uint32_t b = src.get(i);
+            if (!(b >= 0x80 && b < 0xC0)) chars++;
             if (run > r.maxrun) r.maxrun = run;
         } else {
+            close_run();
             if (!seen_bad) { r.lead = run; seen_bad = true; }
-            run = 0;
+            run = 0; chars = 0;
         }
     }
+    close_run();
     if (!seen_bad) r.lead = run;
     r.trail = run;
     return r;
@@ -927,6 +935,7 @@ SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& sr
 inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned) {
     PrefCfg c;
     c.enabled = 0; c.family = PF_BYTE; c.blkA = 0; c.blkH = 0; c.multi = 0; c.T = P.n; c.unit = 1; c.hi_pos = 0;
+    c.n_chars = P.n; c.refine = 0; c.pre_bytes = 0;
     for (uint32_t k = 0; k < 4; ++k) {
         const uint64_t word = k < 2 ? P.af_lo : P.af_hi;
         if ((word >> ((k & 1) * 32)) & 0xFFFFFFFFull) c.blkA |= 1u << k;
@@ -970,6 +979,14 @@ inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned) {
     }
     c.T = P.n * c.unit;
     if (c.T > P.W) c.T = P.W;  // a run covering a whole window is always interesting
+    // UTF-8: a run of good bytes holds at most one char per non-continuation byte, so a long byte run with
+    // fewer than n such bytes cannot hold n chars.  An uninteresting window can then end in a good run of up
+    // to (n-1) chars = (n-1) * maxlen bytes, which the pre-roll has to cover.
+    c.refine = (c.family == PF_UTF8) ? 1u : 0u;
+    {
+        const uint32_t maxlen = c.family == PF_UTF8 ? (c.multi ? 4u : 2u) : 1u;
+        c.pre_bytes = (c.refine ? P.n * maxlen : c.T) + 3 + c.unit;
+    }
     c.enabled = (P.W % 16 == 0 && P.W <= 128 && P.slice_len % P.W == 0 && input_16b_aligned) ? 1u : 0u;
     return c;
 }
@@ -986,7 +1003,7 @@ SX_HD bool pref_interesting_ref(const ScanParams& P, const PrefCfg& c, const Geo
     if (!geo.window(w, g)) return false;
     if (w == 0 || w == total_windows - 1 || (uint32_t)(g.we - g.ws) < P.W || g.final_last) return true;
     const PrefWin a = pref_window_ref(P, c, src, g.ws, g.we);
-    if (a.maxrun >= c.T) return true;
+    if (c.refine ? (a.maxrun >= c.T && a.maxchars >= c.n_chars) : (a.maxrun >= c.T)) return true;
     if ((w % kPrefTileWin) == 0) return a.lead >= 1;
     WinGeom gp;
     geo.window(w - 1, gp);

@@ -238,9 +238,15 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             if (kin.kind == K_UNKNOWN) out = kin;
             else if (d.type == WT_CASEB) out = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws));
             else {
+                // replay under the real carry; in a full pass this also yields the counts and staged records
                 WinResult r;
-                WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, r, nullptr);
+                WindowEngine<Dec>::run(P, ts, g, wg, kin, full ? MODE_BUFFER : MODE_STATE, &S.staged[i][0], 0, r, nullptr);
                 out = r.out;
+                if (full) {
+                    S.cnt_r[i] = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
+                    S.cnt_t[i] = r.ntext;
+                    S.have_cnt[i] = 1;
+                }
             }
             S.kout[i] = out;
             S.out_done[i] = 1;
@@ -271,14 +277,16 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             }
             emit = cr != 0;
         } else {
+            // member of a run whose carry-out came from its descriptor: one pass under the real carry, only
+            // if the window can print at all (records are staged, so usually no write pass follows)
             emit = needs_emit(P, d, kin);
             if (emit) {
-                if (carry_is_null(kin) && d.nrec != 0xFFFFu && !S.have_cnt[i]) { cr = d.nrec; ct = d.ntext; }
-                else {
-                    WinResult r;
-                    WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, r, nullptr);
-                    cr = r.nrec; ct = r.ntext;
-                }
+                WinResult r;
+                WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_BUFFER, &S.staged[i][0], 0, r, nullptr);
+                cr = r.nrec; ct = r.ntext;
+                S.have_cnt[i] = 1;
+                S.cnt_r[i] = (uint16_t)(cr > 0xFFFFu ? 0xFFFFu : cr);
+                emit = cr != 0;
             }
         }
         // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an

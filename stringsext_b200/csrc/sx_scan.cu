@@ -110,9 +110,9 @@ __device__ __forceinline__ void and_shr128_static(uint32_t* r) {  // r &= r >> S
         r[0] &= r[2]; r[1] &= r[3]; r[2] = 0; r[3] = 0;
     }
 }
-// exists a run of >= T set bits (1 <= T <= 128); T is warp-uniform
-__device__ __forceinline__ bool has_run128(const uint32_t* m, uint32_t T) {
-    uint32_t r[4] = {m[0], m[1], m[2], m[3]};
+// r = positions where a run of >= T set bits starts (1 <= T <= 128, warp-uniform); returns r != 0
+__device__ __forceinline__ bool has_run128(const uint32_t* m, uint32_t T, uint32_t* r) {
+    r[0] = m[0]; r[1] = m[1]; r[2] = m[2]; r[3] = m[3];
     uint32_t have = 1;
     if (T >= 2) { and_shr128_static<1>(r); have = 2; }
     if (T >= 4) { and_shr128_static<2>(r); have = 4; }
@@ -329,7 +329,62 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             }
             if ((nm[0] | nm[1] | nm[2] | nm[3]) == 0) { lead = wlen; trail = wlen; }
             else { lead = ctz128(nm); trail = wlen - 128u + clz128(nm); }
-            longrun = has_run128(m, C.T);
+            uint32_t rs[4];
+            longrun = has_run128(m, C.T, rs);
+            if (FAMILY == PF_UTF8 && C.refine && longrun) {
+                // Rare lanes only: a run of >= T good bytes can hold n chars only if it has >= n non-continuation
+                // bytes.  Rebuild the continuation-byte mask of the window and walk its long runs.
+                uint32_t cnm[4] = {0, 0, 0, 0};
+                {
+                    uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if ((uint32_t)c < nchunk) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(tid * W + c * 16u));
+                            const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int k = (4 * c + j) & 7;
+                                acc[k >> 1] = dp4a_u(xs[j] & ~(xs[j] << 1) & 0x80808080u, (k & 1) ? 0x80402010u : 0x08040201u, acc[k >> 1]);
+                                if (k == 7) {
+                                    cnm[(4 * c + j) >> 3] = (acc[0] >> 7) | (acc[1] << 1) | (acc[2] << 9) | (acc[3] << 17);
+                                    acc[0] = acc[1] = acc[2] = acc[3] = 0;
+                                }
+                            }
+                            if ((c & 1) == 0 && (uint32_t)c == nchunk - 1) cnm[c >> 1] = (acc[0] >> 7) | (acc[1] << 1);
+                        }
+                    }
+                }
+                const uint32_t nm2[4] = {~m[0], ~m[1], ~m[2], ~m[3]};
+                const uint32_t mc[4] = {m[0] & ~cnm[0], m[1] & ~cnm[1], m[2] & ~cnm[2], m[3] & ~cnm[3]};
+                bool ok = false;
+                for (int guard = 0; guard < 16 && !ok && (rs[0] | rs[1] | rs[2] | rs[3]); ++guard) {
+                    const uint32_t st0 = ctz128(rs);  // start of a maximal run of >= T good bytes
+                    uint32_t t4[4];
+                    shr128(nm2, st0, t4);
+                    uint32_t rl = ctz128(t4);       // its length (the run may reach bit 127)
+                    if (rl > 128 - st0) rl = 128 - st0;
+                    shr128(mc, st0, t4);
+                    uint32_t chars = 0;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int lo_bit = q4 * 32;
+                        uint32_t wv = t4[q4];
+                        if ((int)rl <= lo_bit) wv = 0;
+                        else if ((int)rl < lo_bit + 32) wv &= (1u << (rl - lo_bit)) - 1u;
+                        chars += __popc(wv);
+                    }
+                    ok = chars >= C.n_chars;
+                    const uint32_t e = st0 + rl;  // drop the run-start bits of this run
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int lo_bit = q4 * 32;
+                        if ((int)e >= lo_bit + 32) rs[q4] = 0;
+                        else if ((int)e > lo_bit) rs[q4] &= ~((1u << (e - lo_bit)) - 1u);
+                    }
+                }
+                longrun = ok;
+            }
         }
         s_trail[tid] = trail;
         __syncthreads();
@@ -802,7 +857,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ExactCfg X;
         X.total_windows = total_windows;
         X.in_aligned16 = in_aligned16 ? 1u : 0u;
-        X.pre_bytes = pc.T + 3 + pc.unit;
+        X.pre_bytes = pc.pre_bytes;
         CK(cudaEventRecord(ss->ev[0], st));
         if (pc.enabled) {
             const PrefK pk = make_pref_k(P, pc);

@@ -86,7 +86,7 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         WinGeom wg;
         geo.window(w, wg);
         const bool adjacent = e > 0 && (int64_t)list[e - 1] == w - 1;
-        const uint32_t pre_bytes = pc.T + 3 + pc.unit;
+        const uint32_t pre_bytes = pc.pre_bytes;
         Carry kin = adjacent ? kprev : P.k0;
         if (!adjacent && w != 0) {
             const WinGeom rg = preroll_geom(geo, w, pre_bytes);
