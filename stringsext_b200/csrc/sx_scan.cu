@@ -129,6 +129,65 @@ __device__ __forceinline__ bool has_run128(const uint32_t* m, uint32_t T, uint32
     return (r[0] | r[1] | r[2] | r[3]) != 0;
 }
 
+// Refinement of a long good-byte run (PF_UTF8, rare): a run of >= T good bytes can hold n chars only if it
+// has >= n non-continuation bytes.  Rebuilds the continuation-byte mask of window `wi` of the staged tile and
+// walks its long runs.  m = good-byte mask of the window.
+__device__ __noinline__ bool pref_refine_utf8(const uint8_t* sm, uint32_t wi, uint32_t W, uint32_t nchunk, const uint32_t* m, uint32_t T,
+                                              uint32_t n_chars) {
+    uint32_t rs[4];
+    if (!has_run128(m, T, rs)) return false;
+    uint32_t cnm[4] = {0, 0, 0, 0};
+    {
+        uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if ((uint32_t)c < nchunk) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(wi * W + c * 16u));
+                const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = (4 * c + j) & 7;
+                    acc[k >> 1] = dp4a_u(xs[j] & ~(xs[j] << 1) & 0x80808080u, (k & 1) ? 0x80402010u : 0x08040201u, acc[k >> 1]);
+                    if (k == 7) {
+                        cnm[(4 * c + j) >> 3] = (acc[0] >> 7) | (acc[1] << 1) | (acc[2] << 9) | (acc[3] << 17);
+                        acc[0] = acc[1] = acc[2] = acc[3] = 0;
+                    }
+                }
+                if ((c & 1) == 0 && (uint32_t)c == nchunk - 1) cnm[c >> 1] = (acc[0] >> 7) | (acc[1] << 1);
+            }
+        }
+    }
+    const uint32_t nm2[4] = {~m[0], ~m[1], ~m[2], ~m[3]};
+    const uint32_t mc[4] = {m[0] & ~cnm[0], m[1] & ~cnm[1], m[2] & ~cnm[2], m[3] & ~cnm[3]};
+    bool ok = false;
+    for (int guard = 0; guard < 16 && !ok && (rs[0] | rs[1] | rs[2] | rs[3]); ++guard) {
+        const uint32_t st0 = ctz128(rs);  // start of a maximal run of >= T good bytes
+        uint32_t t4[4];
+        shr128(nm2, st0, t4);
+        uint32_t rl = ctz128(t4);  // its length (the run may reach bit 127)
+        if (rl > 128 - st0) rl = 128 - st0;
+        shr128(mc, st0, t4);
+        uint32_t chars = 0;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const int lo_bit = q4 * 32;
+            uint32_t wv = t4[q4];
+            if ((int)rl <= lo_bit) wv = 0;
+            else if ((int)rl < lo_bit + 32) wv &= (1u << (rl - lo_bit)) - 1u;
+            chars += __popc(wv);
+        }
+        ok = chars >= n_chars;
+        const uint32_t e = st0 + rl;  // drop the run-start bits of this run
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const int lo_bit = q4 * 32;
+            if ((int)e >= lo_bit + 32) rs[q4] = 0;
+            else if ((int)e > lo_bit) rs[q4] &= ~((1u << (e - lo_bit)) - 1u);
+        }
+    }
+    return ok;
+}
+
 // TMA helpers (cp.async.bulk.tensor + mbarrier), sm_90+/sm_100a PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -157,7 +216,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 }
 
 constexpr uint32_t kPrefStageBytes = 32768;
-constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64;
+constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64 + 32 + 4096 + 1024;
 
 // DEFSHAPE (PF_UTF8 only): the default filter shape -- ASCII blocks 1..3 may pass, only 2-byte leads
 // (block 6) may pass -- with the block functions folded into single LOP3s.
@@ -170,6 +229,9 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
     uint32_t* s_trail = reinterpret_cast<uint32_t*>(smem_raw + 2 * kPrefStageBytes);  // 256
     uint32_t* s_iw = s_trail + 256;                                                   // 8 words
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_iw + 16);                         // 2 mbarriers
+    uint32_t* s_cand = s_iw + 24;                                                     // 8 words: refinement candidates
+    uint32_t* s_m = s_cand + 8;                                                       // 256 x 4: their good-byte masks
+    uint32_t* s_ref = s_m + 1024;                                                     // 256: refined verdicts
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = P.W, nchunk = W >> 4;
     const uint32_t tile_bytes = kPrefTileWin * W;
@@ -331,63 +393,38 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             else { lead = ctz128(nm); trail = wlen - 128u + clz128(nm); }
             uint32_t rs[4];
             longrun = has_run128(m, C.T, rs);
-            if (FAMILY == PF_UTF8 && C.refine && longrun) {
-                // Rare lanes only: a run of >= T good bytes can hold n chars only if it has >= n non-continuation
-                // bytes.  Rebuild the continuation-byte mask of the window and walk its long runs.
-                uint32_t cnm[4] = {0, 0, 0, 0};
-                {
-                    uint32_t acc[4] = {0, 0, 0, 0};
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        if ((uint32_t)c < nchunk) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(tid * W + c * 16u));
-                            const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int k = (4 * c + j) & 7;
-                                acc[k >> 1] = dp4a_u(xs[j] & ~(xs[j] << 1) & 0x80808080u, (k & 1) ? 0x80402010u : 0x08040201u, acc[k >> 1]);
-                                if (k == 7) {
-                                    cnm[(4 * c + j) >> 3] = (acc[0] >> 7) | (acc[1] << 1) | (acc[2] << 9) | (acc[3] << 17);
-                                    acc[0] = acc[1] = acc[2] = acc[3] = 0;
-                                }
-                            }
-                            if ((c & 1) == 0 && (uint32_t)c == nchunk - 1) cnm[c >> 1] = (acc[0] >> 7) | (acc[1] << 1);
-                        }
-                    }
-                }
-                const uint32_t nm2[4] = {~m[0], ~m[1], ~m[2], ~m[3]};
-                const uint32_t mc[4] = {m[0] & ~cnm[0], m[1] & ~cnm[1], m[2] & ~cnm[2], m[3] & ~cnm[3]};
-                bool ok = false;
-                for (int guard = 0; guard < 16 && !ok && (rs[0] | rs[1] | rs[2] | rs[3]); ++guard) {
-                    const uint32_t st0 = ctz128(rs);  // start of a maximal run of >= T good bytes
-                    uint32_t t4[4];
-                    shr128(nm2, st0, t4);
-                    uint32_t rl = ctz128(t4);       // its length (the run may reach bit 127)
-                    if (rl > 128 - st0) rl = 128 - st0;
-                    shr128(mc, st0, t4);
-                    uint32_t chars = 0;
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const int lo_bit = q4 * 32;
-                        uint32_t wv = t4[q4];
-                        if ((int)rl <= lo_bit) wv = 0;
-                        else if ((int)rl < lo_bit + 32) wv &= (1u << (rl - lo_bit)) - 1u;
-                        chars += __popc(wv);
-                    }
-                    ok = chars >= C.n_chars;
-                    const uint32_t e = st0 + rl;  // drop the run-start bits of this run
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const int lo_bit = q4 * 32;
-                        if ((int)e >= lo_bit + 32) rs[q4] = 0;
-                        else if ((int)e > lo_bit) rs[q4] &= ~((1u << (e - lo_bit)) - 1u);
-                    }
-                }
-                longrun = ok;
-            }
+
         }
         s_trail[tid] = trail;
-        __syncthreads();
+        if (FAMILY == PF_UTF8 && C.refine) {
+            // Candidates (a long run of good BYTES) are rare; warp 0 re-examines them one lane per candidate so
+            // that the other warps never diverge into the refinement.
+            const uint32_t cb = __ballot_sync(0xffffffffu, longrun);
+            if (lane == 0) s_cand[warp] = cb;
+            if (longrun) { s_m[tid * 4 + 0] = m[0]; s_m[tid * 4 + 1] = m[1]; s_m[tid * 4 + 2] = m[2]; s_m[tid * 4 + 3] = m[3]; }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t idx = lane;  // lane handles the idx-th, (idx+32)-th ... candidate in tile order
+#pragma unroll 1
+                for (uint32_t wq = 0, seen = 0; wq < kPrefThreads / 32; ++wq) {
+                    uint32_t bits = s_cand[wq];
+                    const uint32_t cnt = __popc(bits);
+                    while (idx < seen + cnt) {
+                        uint32_t k = idx - seen, bb = bits;
+                        for (uint32_t z = 0; z < k; ++z) bb &= bb - 1;  // drop the k lowest set bits
+                        const uint32_t ci = wq * 32 + (__ffs(bb) - 1);
+                        const uint32_t mm[4] = {s_m[ci * 4], s_m[ci * 4 + 1], s_m[ci * 4 + 2], s_m[ci * 4 + 3]};
+                        s_ref[ci] = pref_refine_utf8(sm, ci, W, nchunk, mm, C.T, C.n_chars) ? 1u : 0u;
+                        idx += 32;
+                    }
+                    seen += cnt;
+                }
+            }
+            __syncthreads();
+            if (longrun) longrun = s_ref[tid] != 0;
+        } else {
+            __syncthreads();
+        }
         bool interesting = false;
         if (valid) {
             const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
