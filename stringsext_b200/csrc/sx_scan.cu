@@ -130,9 +130,9 @@ __device__ __forceinline__ bool has_run128(const uint32_t* m, uint32_t T, uint32
 }
 
 // Refinement of a long good-byte run (PF_UTF8, rare): a run of >= T good bytes can hold n chars only if it
-// has >= n non-continuation bytes.  Rebuilds the continuation-byte mask of window `wi` of the staged tile and
-// walks its long runs.  m = good-byte mask of the window.
-__device__ __noinline__ bool pref_refine_utf8(const uint8_t* sm, uint32_t wi, uint32_t W, uint32_t nchunk, const uint32_t* m, uint32_t T,
+// has >= n non-continuation bytes.  Rebuilds the continuation-byte mask of the (full, 16-byte aligned) window at
+// `wbytes` and walks its long runs.  m = good-byte mask of the window.
+__device__ __noinline__ bool pref_refine_utf8(const uint8_t* wbytes, uint32_t nchunk, const uint32_t* m, uint32_t T,
                                               uint32_t n_chars) {
     uint32_t rs[4];
     if (!has_run128(m, T, rs)) return false;
@@ -142,7 +142,7 @@ __device__ __noinline__ bool pref_refine_utf8(const uint8_t* sm, uint32_t wi, ui
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             if ((uint32_t)c < nchunk) {
-                const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(wi * W + c * 16u));
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(wbytes) + c);
                 const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -216,7 +216,8 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 }
 
 constexpr uint32_t kPrefStageBytes = 32768;
-constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64 + 32 + 4096 + 1024;
+constexpr uint32_t kPrefQueueCap = 768;  // flushed as soon as fewer than one tile's worth of slots is free
+constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64 + 32 + kPrefQueueCap * 20;
 
 // DEFSHAPE (PF_UTF8 only): the default filter shape -- ASCII blocks 1..3 may pass, only 2-byte leads
 // (block 6) may pass -- with the block functions folded into single LOP3s.
@@ -229,9 +230,10 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
     uint32_t* s_trail = reinterpret_cast<uint32_t*>(smem_raw + 2 * kPrefStageBytes);  // 256
     uint32_t* s_iw = s_trail + 256;                                                   // 8 words
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_iw + 16);                         // 2 mbarriers
-    uint32_t* s_cand = s_iw + 24;                                                     // 8 words: refinement candidates
-    uint32_t* s_m = s_cand + 8;                                                       // 256 x 4: their good-byte masks
-    uint32_t* s_ref = s_m + 1024;                                                     // 256: refined verdicts
+    uint32_t* s_qw = s_iw + 24;                                                       // queue: window index | candidate flag
+    uint32_t* s_qm = s_qw + kPrefQueueCap;                                            // queue: good-byte masks of candidates
+    const bool do_refine = (FAMILY == PF_UTF8) && C.refine != 0;
+    uint32_t qn = 0;  // queued windows (uniform across the block)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = P.W, nchunk = W >> 4;
     const uint32_t tile_bytes = kPrefTileWin * W;
@@ -396,44 +398,19 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
 
         }
         s_trail[tid] = trail;
-        if (FAMILY == PF_UTF8 && C.refine) {
-            // Candidates (a long run of good BYTES) are rare; warp 0 re-examines them one lane per candidate so
-            // that the other warps never diverge into the refinement.
-            const uint32_t cb = __ballot_sync(0xffffffffu, longrun);
-            if (lane == 0) s_cand[warp] = cb;
-            if (longrun) { s_m[tid * 4 + 0] = m[0]; s_m[tid * 4 + 1] = m[1]; s_m[tid * 4 + 2] = m[2]; s_m[tid * 4 + 3] = m[3]; }
-            __syncthreads();
-            if (warp == 0) {
-                uint32_t idx = lane;  // lane handles the idx-th, (idx+32)-th ... candidate in tile order
-#pragma unroll 1
-                for (uint32_t wq = 0, seen = 0; wq < kPrefThreads / 32; ++wq) {
-                    uint32_t bits = s_cand[wq];
-                    const uint32_t cnt = __popc(bits);
-                    while (idx < seen + cnt) {
-                        uint32_t k = idx - seen, bb = bits;
-                        for (uint32_t z = 0; z < k; ++z) bb &= bb - 1;  // drop the k lowest set bits
-                        const uint32_t ci = wq * 32 + (__ffs(bb) - 1);
-                        const uint32_t mm[4] = {s_m[ci * 4], s_m[ci * 4 + 1], s_m[ci * 4 + 2], s_m[ci * 4 + 3]};
-                        s_ref[ci] = pref_refine_utf8(sm, ci, W, nchunk, mm, C.T, C.n_chars) ? 1u : 0u;
-                        idx += 32;
-                    }
-                    seen += cnt;
-                }
-            }
-            __syncthreads();
-            if (longrun) longrun = s_ref[tid] != 0;
-        } else {
-            __syncthreads();
-        }
-        bool interesting = false;
+        __syncthreads();
+        // sure: listed whatever the refinement says; cand: listed only if a long run holds enough chars
+        bool sure = false, cand = false;
         if (valid) {
             const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
-            if (forced || longrun) interesting = true;
-            else if (tid == 0) interesting = lead >= 1;
-            else interesting = s_trail[tid - 1] + lead >= C.T;
+            if (forced) sure = true;
+            else if (tid == 0) sure = lead >= 1;
+            else sure = s_trail[tid - 1] + lead >= C.T;
+            if (!sure && longrun) { if (do_refine) cand = true; else sure = true; }
         }
-        // compact: stream order = (warp, lane) order inside the tile
-        const uint32_t ib = __ballot_sync(0xffffffffu, interesting);
+        // queue the window (tile order = (warp, lane) order); candidates carry their good-byte mask
+        const bool push = sure || cand;
+        const uint32_t ib = __ballot_sync(0xffffffffu, push);
         if (lane == 0) s_iw[warp] = __popc(ib);
         __syncthreads();
         uint32_t before = 0, total = 0;
@@ -443,9 +420,45 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             if ((uint32_t)k < warp) before += c;
             total += c;
         }
-        if (interesting) my_list[kept + before + __popc(ib & ((1u << lane) - 1u))] = (uint32_t)w;
-        kept += total;
+        if (push) {
+            const uint32_t qi = qn + before + __popc(ib & ((1u << lane) - 1u));
+            s_qw[qi] = (uint32_t)w | (cand ? 0x80000000u : 0u);  // window indices stay below 2^31 (checked on the host)
+            if (cand) { s_qm[qi * 4 + 0] = m[0]; s_qm[qi * 4 + 1] = m[1]; s_qm[qi * 4 + 2] = m[2]; s_qm[qi * 4 + 3] = m[3]; }
+        }
+        qn += total;
         __syncthreads();
+        // flush when another tile might not fit: every thread settles up to two queued windows in parallel
+        if (qn > kPrefQueueCap - kPrefTileWin || tile + 1 == t_end) {
+#pragma unroll 1
+            for (uint32_t base = 0; base < qn; base += kPrefThreads) {
+                const uint32_t qi = base + tid;
+                bool keep = false;
+                uint32_t wq = 0;
+                if (qi < qn) {
+                    const uint32_t e = s_qw[qi];
+                    wq = e & 0x7FFFFFFFu;
+                    keep = true;
+                    if (e & 0x80000000u) {
+                        const uint32_t mm[4] = {s_qm[qi * 4], s_qm[qi * 4 + 1], s_qm[qi * 4 + 2], s_qm[qi * 4 + 3]};
+                        keep = pref_refine_utf8(P.in + (size_t)wq * W, nchunk, mm, C.T, C.n_chars);
+                    }
+                }
+                const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+                if (lane == 0) s_iw[warp] = __popc(kb);
+                __syncthreads();
+                uint32_t bf = 0, tt = 0;
+#pragma unroll
+                for (int k = 0; k < kPrefThreads / 32; ++k) {
+                    const uint32_t c = s_iw[k];
+                    if ((uint32_t)k < warp) bf += c;
+                    tt += c;
+                }
+                if (keep) my_list[kept + bf + __popc(kb & ((1u << lane) - 1u))] = wq;
+                kept += tt;
+                __syncthreads();
+            }
+            qn = 0;
+        }
     }
     if (tid == 0) O.cta_count[blockIdx.x] = kept;
 }
@@ -868,7 +881,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         const size_t rest = len - (size_t)full * slice_len;
         total_windows = full * wps + (long long)((rest + W - 1) / W);
     }
-    if (total_windows > 0xFFFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
+    if (total_windows > 0x7FFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
     PrefCfg pc = make_pref_cfg(P, in_aligned16);
     if (!ss->use_prefilter) pc.enabled = 0;
