@@ -216,7 +216,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 }
 
 constexpr uint32_t kPrefStageBytes = 32768;
-constexpr uint32_t kPrefQueueCap = 768;  // flushed as soon as fewer than one tile's worth of slots is free
+constexpr uint32_t kPrefQueueCap = 448;  // flushed as soon as fewer than one tile's worth of slots is free
 constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64 + 32 + kPrefQueueCap * 20;
 
 // DEFSHAPE (PF_UTF8 only): the default filter shape -- ASCII blocks 1..3 may pass, only 2-byte leads
