@@ -47,17 +47,21 @@ enum : uint8_t { PREC_BEFORE = 0, PREC_EXACT = 1, PREC_AFTER = 2 };  // finding.
 
 // Carry between segments / windows / slices.
 enum : uint8_t { K_L = 0, K_C = 1, K_UNKNOWN = 2 };
-enum : uint8_t { CF_HOSTCARRY = 1 };  // leftover starts with text carried in the host ScannerState
+enum : uint8_t {
+    CF_HOSTCARRY = 1,  // leftover starts with text carried in the host ScannerState
+    CF_GREP = 2        // leftover contains the mission's grep_char (helper.rs:252-254)
+};
 struct Carry {
     uint8_t kind;        // K_L: leftover of k chars (k may be 0) and cut == false; K_C: cut == true
     uint8_t flags;
     uint16_t k;          // chars in the leftover
     uint32_t in_bytes;   // distance from the leftover's first input byte to the boundary
     uint32_t out_bytes;  // UTF-8 bytes of the leftover (device-decoded part only)
+    uint32_t aux;        // UTF-8 lead byte of the leftover's last multi-byte char (same-unicode-block rule), else 0
 };
-SX_HD Carry carry_none() { return Carry{K_L, 0, 0, 0, 0}; }
-SX_HD Carry carry_cut() { return Carry{K_C, 0, 0, 0, 0}; }
-SX_HD Carry carry_unknown() { return Carry{K_UNKNOWN, 0, 0, 0, 0}; }
+SX_HD Carry carry_none() { return Carry{K_L, 0, 0, 0, 0, 0}; }
+SX_HD Carry carry_cut() { return Carry{K_C, 0, 0, 0, 0, 0}; }
+SX_HD Carry carry_unknown() { return Carry{K_UNKNOWN, 0, 0, 0, 0, 0}; }
 SX_HD bool carry_is_null(const Carry& c) { return c.kind == K_L && c.k == 0; }
 
 // One finding as it leaves the GPU (before text materialisation).
@@ -86,6 +90,9 @@ struct ScanParams {
     uint8_t carry_text8[8];  // first bytes of the host-carried leftover text (Precision::Before probe)
     uint32_t carry_text_len;
     Carry k0;                // carry at offset 0
+    int32_t grep_char;       // Utf8Filter.grep_char, -1 = None
+    uint32_t same_block;     // Mission.require_same_unicode_block
+    uint32_t general;        // grep_char / same_block / chars_min_nb > q: general automaton + dual-simulation classification
     uint16_t sb_table[128];
 };
 
@@ -136,6 +143,8 @@ struct WinResult {
     uint32_t nrec;
     uint32_t ntext;
     int32_t npend_out;  // bytes still inside the decoder at the window end
+    uint32_t m;         // segments in the window
+    uint32_t cut1;      // carry flag handed from segment 1 to segment 2
 };
 
 // MODE_BUFFER: count, and also write the first kBufRecs records (text_off relative to the window's first
@@ -153,6 +162,7 @@ struct WinAuto {
     uint64_t text_off; // MODE_WRITE: next text offset
     int64_t slice_start;
     bool probe_possible;  // stateful decoder: the Precision::Before probe can fire
+    int force_s2_cont;    // classification aid: -1, or the `cont` value forced at the start of segment 2
 
     // segment / SplitStr state
     int64_t seg_pos;
@@ -162,11 +172,15 @@ struct WinAuto {
     bool at_left;    // ok_s_p == inp_start_p for the current run
     bool cut;        // last_window_str_was_printed_and_is_maybe_cut_str
     bool run_hostcarry;
+    bool grep_ok;    // helper.rs:215: current run holds the grep_char (always true without one)
+    bool qfull;      // the run reached q chars; whether it touches the right boundary is known at the next event
+    bool dead;       // SplitStr::next returned None (helper.rs:410-415): the rest of the segment is ignored
+    uint32_t last_mb;  // helper.rs:221: lead byte of the run's last multi-byte char (same-unicode-block rule)
     uint32_t run_n, run_out;
     int64_t run_in_start, run_in_end;
     // leftover produced by an `again` chunk
-    bool has_left, left_hostcarry;
-    uint32_t left_k, left_out;
+    bool has_left, left_hostcarry, left_grep;
+    uint32_t left_k, left_out, left_mb;
     int64_t left_in_start;
     // probe context: leftover present at the slice start (its text may sit at out[0..])
     bool slice_left_present;
@@ -181,36 +195,48 @@ struct WinAuto {
     uint32_t s1_out;        // UTF-8 bytes of passing chars in segment 1
     bool in_first_run;      // still inside the first run of segment 1
     bool s1_all_pass, s1_later_yield, s2_all_pass;
+    bool cut1;              // carry flag handed from segment 1 to segment 2 (classification)
 
     SX_HD void init(const ScanParams* p, int md, int64_t slice_st, bool probe_ok) {
         P = p; mode = md; wr = nullptr; text_off = 0; slice_start = slice_st; probe_possible = probe_ok;
-        cut = false; has_left = false; left_hostcarry = false; left_k = left_out = 0; left_in_start = 0;
+        force_s2_cont = -1; cut1 = false;
+        cut = false; has_left = false; left_hostcarry = false; left_grep = false; left_k = left_out = left_mb = 0; left_in_start = 0;
         nrec = ntext = 0; m = 0; a = 0; s1_out = 0; in_first_run = false;
         s1_all_pass = true; s1_later_yield = false; s2_all_pass = true;
         slice_left_present = false; slice_left = carry_none();
         run_n = run_out = 0; run_in_start = run_in_end = 0; run_hostcarry = false;
+        grep_ok = true; qfull = false; dead = false; last_mb = 0;
         seg_pos = 0; prec = PREC_EXACT; probe_pending = false; last_cut = false; at_left = true;
     }
+    SX_HD bool grep_reset() const { return P->grep_char < 0; }  // helper.rs:215 / :330
 
     // finding_collection.rs:211-241 + helper.rs:171-200.  `kin` only for the first segment of a window.
     SX_HD void segment_start(int64_t pos, const Carry* kin, int32_t pend_len) {
         seg_pos = pos;
         m++;
         if (kin) cut = (kin->kind == K_C);
+        if (m == 2) {
+            cut1 = cut;
+            if (force_s2_cont >= 0) cut = force_s2_cont != 0;
+        }
         const bool cont = cut;  // finding_collection.rs:240-241: used once
         cut = false;
         last_cut = cont;
         at_left = true;
         run_n = 0; run_out = 0; run_hostcarry = false;
+        grep_ok = grep_reset(); last_mb = 0; qfull = false; dead = false;
         prec = PREC_EXACT;
         probe_pending = probe_possible && (pos == slice_start);
         has_left = false;
-        if (kin && kin->kind == K_L && kin->k > 0) {  // finding_collection.rs:214-221
+        if (kin && kin->kind == K_L && kin->k > 0) {  // finding_collection.rs:214-221: the leftover is re-scanned
             run_n = kin->k;
             run_out = kin->out_bytes;
             run_in_start = pos - (int64_t)kin->in_bytes;
             run_in_end = pos - pend_len;
             run_hostcarry = (kin->flags & CF_HOSTCARRY) != 0;
+            grep_ok = grep_reset() || (kin->flags & CF_GREP) != 0;
+            last_mb = kin->aux;
+            qfull = run_n >= P->q;  // only possible with a grep_char (helper.rs:389-392)
             prec = PREC_BEFORE;
         }
         if (m == 1) in_first_run = true;
@@ -236,6 +262,32 @@ struct WinAuto {
         prec = PREC_AFTER;   // finding_collection.rs:289
         has_left = false;
     }
+    SX_HD void keep_leftover() {  // an `again` chunk, finding_collection.rs:281-284
+        if (m == 1 && !in_first_run) s1_later_yield = true;
+        has_left = true;
+        left_k = run_n; left_out = run_out; left_in_start = run_in_start; left_hostcarry = run_hostcarry;
+        left_grep = grep_ok && P->grep_char >= 0;
+        left_mb = P->same_block ? last_mb : 0u;  // only the same-unicode-block rule reads it
+        cut = false;
+        prec = PREC_AFTER;
+    }
+    SX_HD void new_run() {  // a fresh SplitStr::next() call
+        run_n = 0; run_out = 0; run_hostcarry = false;
+        grep_ok = grep_reset();
+        last_mb = 0;
+    }
+    // The run holds q chars (helper.rs:237 loop exit 2): evaluate the chunk now that `right` is known.
+    SX_HD void resolve_qfull(bool right, bool invalid_after) {
+        qfull = false;
+        const bool completes = at_left && last_cut;                               // helper.rs:355
+        const bool again = !completes && right && !invalid_after && !grep_ok;     // helper.rs:389-392 (ok_n == q)
+        if (again) { keep_leftover(); run_n = 0; run_out = 0; return; }
+        if (!completes && (!grep_ok || run_n < P->n)) { dead = true; run_n = 0; run_out = 0; return; }  // helper.rs:410-415
+        yield(completes, true);                                                   // helper.rs:353
+        at_left = true;   // helper.rs:418-420: inp_start_p = p
+        last_cut = true;
+        new_run();
+    }
 
     template <class ProbeFn>
     SX_HD void on_char(uint32_t lb, uint32_t ul, int64_t cstart, int64_t cend, ProbeFn&& probe) {
@@ -245,52 +297,74 @@ struct WinAuto {
                 if (probe(m == 1, slice_left)) prec = PREC_BEFORE;
             }
         }
-        const bool pass = pass_filter(*P, lb);
+        if (qfull) resolve_qfull(false, false);
+        if (dead) return;
+        bool pass;
+        if (lb < 0x80) {
+            if (!grep_ok && P->grep_char == (int32_t)lb) grep_ok = true;  // helper.rs:252-254, before the filter
+            pass = pass_filter(*P, lb);
+        } else if (pass_filter(*P, lb)) {
+            if (!P->same_block || lb == last_mb || last_mb == 0) { last_mb = lb; pass = true; }
+            else {
+                // helper.rs:287-292: a passing char of another block ends the run and is scanned again
+                if (m == 1) s1_all_pass = false;
+                if (m == 2) s2_all_pass = false;
+                if (run_n > 0 && ((last_cut && at_left) || (run_n >= P->n && grep_ok))) {
+                    yield(at_left && last_cut, false);
+                    last_cut = false;
+                }
+                if (m == 1) in_first_run = false;
+                at_left = false;
+                new_run();
+                last_mb = lb;
+                pass = true;  // now the first char of a new run
+            }
+        } else {
+            last_mb = 0;
+            pass = false;
+        }
         if (pass) {
             if (run_n == 0) { run_in_start = cstart; }
             run_n++;
             run_out += ul;
             run_in_end = cend;
             if (m == 1) { s1_out += ul; if (in_first_run && a < 0xFFFFu) a++; }
-            if (run_n >= P->q) {
-                // helper.rs:237 loop exit 2 -> :353-355, :418-421: cut the run here
-                yield(at_left && last_cut, true);
-                at_left = true;   // inp_start_p = p
-                last_cut = true;
-                run_n = 0; run_out = 0; run_hostcarry = false;
-            }
+            if (run_n >= P->q) qfull = true;  // decided at the next event (helper.rs:351: touches the right boundary?)
         } else {
             if (m == 1) { s1_all_pass = false; }
             if (m == 2) s2_all_pass = false;
+            bool broke = false;
             if (run_n > 0) {
                 // helper.rs:315-322 exit 3 / exit 4
-                if ((last_cut && at_left) || run_n >= P->n) {
+                if ((last_cut && at_left) || (run_n >= P->n && grep_ok)) {
                     yield(at_left && last_cut, false);
                     last_cut = false;
+                    broke = true;
                 }
             }
             if (m == 1) in_first_run = false;
-            run_n = 0; run_out = 0; run_hostcarry = false;
             at_left = false;
+            // helper.rs:327-330: without a `break` the same next() call goes on and keeps its (possibly stale)
+            // last_multi_char_leading_byte; after a `break` the following next() call starts from 0
+            const uint32_t keep_mb = broke ? 0u : last_mb;
+            new_run();
+            last_mb = keep_mb;
         }
     }
 
     // End of the segment text.  invalid_after: finding_collection.rs:234-237.
     SX_HD void segment_end(bool invalid_after) {
-        if (run_n > 0) {
-            const bool completes = at_left && last_cut;
-            const bool again = !completes && !invalid_after;  // helper.rs:389-392 (run_n < q here)
-            if (again) {                                      // finding_collection.rs:281-284
-                if (m == 1 && !in_first_run) s1_later_yield = true;
-                has_left = true;
-                left_k = run_n; left_out = run_out; left_in_start = run_in_start; left_hostcarry = run_hostcarry;
-                cut = false;
-            } else if (completes || run_n >= P->n) {
-                yield(completes, !invalid_after);             // helper.rs:353-354
+        if (!dead) {
+            if (qfull) resolve_qfull(true, invalid_after);
+            else if (run_n > 0) {
+                const bool completes = at_left && last_cut;
+                const bool again = !completes && !invalid_after;  // helper.rs:389-392 (run_n < q here)
+                if (again) keep_leftover();
+                else if (completes || (run_n >= P->n && grep_ok)) yield(completes, !invalid_after);  // helper.rs:353-354, :410-415
             }
         }
         if (m == 1) in_first_run = false;
-        run_n = 0; run_out = 0;
+        run_n = 0; run_out = 0; qfull = false;
     }
 
     SX_HD void on_malformed(int64_t next) {
@@ -302,9 +376,12 @@ struct WinAuto {
         if (cut) return carry_cut();
         if (has_left) {
             Carry c;
-            c.kind = K_L; c.flags = left_hostcarry ? CF_HOSTCARRY : 0; c.k = (uint16_t)left_k;
+            c.kind = K_L;
+            c.flags = (uint8_t)((left_hostcarry ? CF_HOSTCARRY : 0) | (left_grep ? CF_GREP : 0));
+            c.k = (uint16_t)left_k;
             c.in_bytes = (uint32_t)(boundary - left_in_start);
             c.out_bytes = left_out;
+            c.aux = left_mb;
             return c;
         }
         return carry_none();
@@ -641,6 +718,7 @@ struct WinGeom {
     int64_t ws, we;                 // window [ws, we) in buffer offsets
     int64_t slice_start, slice_end; // enclosing slice
     bool final_last;                // last window of the stream and is_last_input_buffer
+    int force_s2_cont;              // classification aid (general missions): -1 or the carry flag forced into segment 2
 };
 
 template <class Dec>
@@ -708,6 +786,7 @@ SX_HD_NOINLINE void scan_window(const ScanParams& P, const TileSrc& tsrc, const 
     WinAuto A;
     A.init(&P, mode, geo.slice_start, Dec::kStateful);
     A.wr = wr; A.text_off = text_off;
+    A.force_s2_cont = geo.force_s2_cont;
     if (geo.ws == geo.slice_start) { A.slice_left_present = true; A.slice_left = kin; }
     A.segment_start(geo.ws, &kin, dec.pending_len());
     Emit<Dec> em{&A, &pc};
@@ -727,6 +806,8 @@ SX_HD_NOINLINE void scan_window(const ScanParams& P, const TileSrc& tsrc, const 
     res.out = A.carry_out(geo.we);
     res.nrec = A.nrec;
     res.ntext = A.ntext;
+    res.m = A.m;
+    res.cut1 = A.cut1 ? 1u : 0u;
     if (desc) {
         desc->a = (uint16_t)A.a;
         desc->nrec = (uint16_t)(A.nrec > 0xFFFFu ? 0xFFFFu : A.nrec);
@@ -736,6 +817,7 @@ SX_HD_NOINLINE void scan_window(const ScanParams& P, const TileSrc& tsrc, const 
         desc->pad = 0;
         const bool single_all_pass = (A.m == 1 && A.s1_all_pass);
         if (geo.final_last) desc->type = WT_CONST;
+        else if (P.general) desc->type = WT_DEP;  // refined by classify_general() with a second pass
         else if (single_all_pass) {
             if (A.a < P.q) { desc->type = WT_CASEB; desc->t_out = (uint16_t)A.s1_out; }
             else desc->type = WT_CONST;
@@ -779,6 +861,7 @@ struct Geometry {
         if (g.ws >= g.slice_end) return false;
         g.we = g.ws + W < g.slice_end ? g.ws + W : g.slice_end;
         g.final_last = is_last && g.we == len;
+        g.force_s2_cont = -1;
         return true;
     }
 };
@@ -795,6 +878,22 @@ SX_HD WinGeom preroll_geom(const Geometry& geo, int64_t w, uint32_t pre_bytes) {
 }
 
 // A carry-out that can make an UNLISTED successor print something (DESIGN.md "Extension rule").
+// General missions (grep_char, same-unicode-block, chars_min_nb > q): a window with >= 2 segments depends on its
+// carry-in only through the one flag handed from segment 1 to segment 2, so it is CONSTANT iff forcing that
+// flag the other way leaves the carry-out unchanged.  `r1` is the result of the pass under the null carry.
+template <class RunFn>
+SX_HD uint8_t classify_general(const WinGeom& geo, const WinResult& r1, RunFn&& run_forced) {
+    if (geo.final_last) return WT_CONST;
+    if (r1.m < 2) return WT_DEP;
+    WinGeom g2 = geo;
+    g2.force_s2_cont = r1.cut1 ? 0 : 1;
+    const Carry o2 = run_forced(g2);
+    const Carry& o1 = r1.out;
+    const bool same = o1.kind == o2.kind && o1.flags == o2.flags && o1.k == o2.k && o1.in_bytes == o2.in_bytes &&
+                      o1.out_bytes == o2.out_bytes && o1.aux == o2.aux;
+    return same ? WT_CONST : WT_DEP;
+}
+
 SX_HD bool carry_needs_extension(const ScanParams& P, const Carry& k) {
     return k.kind == K_C || (k.kind == K_L && k.k >= P.n);
 }
@@ -802,6 +901,7 @@ SX_HD bool carry_needs_extension(const ScanParams& P, const Carry& k) {
 // Does window `d` emit anything given its real carry-in?  (see DESIGN.md "Emit rule")
 SX_HD bool needs_emit(const ScanParams& P, const WinDesc& d, const Carry& kin) {
     if (d.nrec > 0) return true;
+    if (P.general) return !carry_is_null(kin);  // no closed form with grep_char / same block: just look
     if (kin.kind == K_C) return d.a > 0;
     return kin.k > 0 && (uint32_t)kin.k + d.a >= P.n;
 }

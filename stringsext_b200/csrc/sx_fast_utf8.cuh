@@ -316,10 +316,13 @@ SX_HD_NOINLINE void scan_window_fast_utf8(const ScanParams& P, const TileSrc& ts
         c.kind = K_L; c.flags = (fl & FF_LEFTHC) ? CF_HOSTCARRY : 0; c.k = (uint16_t)left_k;
         c.in_bytes = (uint32_t)(wlen - left_s);
         c.out_bytes = (uint32_t)(left_e - left_s);
+        c.aux = 0;
         res.out = c;
     } else res.out = carry_none();
     res.nrec = E.nrec;
     res.ntext = E.ntext;
+    res.m = m;
+    res.cut1 = 0;
     if (desc) {
         desc->a = (uint16_t)(a > 0xFFFFu ? 0xFFFFu : a);
         desc->nrec = (uint16_t)(E.nrec > 0xFFFFu ? 0xFFFFu : E.nrec);
@@ -349,12 +352,9 @@ template <> struct WindowEngine<DecUtf8> {
     template <class TileSrc>
     SX_HD static void run(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
                           int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
-#if defined(__CUDA_ARCH__)
-        scan_window_fast_utf8(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);  // device: always the convergent engine
-#else
-        if (tsrc.tables()) scan_window_fast_utf8(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
+        // grep_char / same-unicode-block / chars_min_nb > q missions take the general automaton
+        if (tsrc.tables() && !P.general) scan_window_fast_utf8(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
         else scan_window<DecUtf8>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
-#endif
     }
 };
 

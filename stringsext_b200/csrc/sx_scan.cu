@@ -873,6 +873,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     if (ss->cut) P.k0 = carry_cut();
     else if (!ss->leftover.empty()) P.k0 = Carry{K_L, CF_HOSTCARRY, (uint16_t)utf8_char_count(ss->leftover), (uint32_t)ss->npend, 0};
     else P.k0 = carry_none();
+    P.grep_char = -1; P.same_block = 0; P.general = 0;  // such missions are rejected by sx_scanner_state_new for now
     memcpy(P.sb_table, ss->m.sb_table, sizeof P.sb_table);
 
     long long total_windows;

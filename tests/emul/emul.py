@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "_build", "libsx_emul.so")
 
 class Carry(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("flags", C.c_uint8), ("k", C.c_uint16), ("in_bytes", C.c_uint32),
-                ("out_bytes", C.c_uint32)]
+                ("out_bytes", C.c_uint32), ("aux", C.c_uint32)]
 
 
 class ScanParams(C.Structure):
@@ -30,6 +30,7 @@ class ScanParams(C.Structure):
         ("pend", C.c_uint8 * 8), ("carry_text8", C.c_uint8 * 8),
         ("carry_text_len", C.c_uint32),
         ("k0", Carry),
+        ("grep_char", C.c_int32), ("same_block", C.c_uint32), ("general", C.c_uint32),
         ("sb_table", C.c_uint16 * 128),
     ]
 
@@ -104,6 +105,9 @@ class EmulState:
         P.af_hi = (m.filter.af >> 64) & 0xFFFFFFFFFFFFFFFF
         P.ubf = m.filter.ubf
         P.base_consumed = self.consumed
+        P.grep_char = -1
+        P.same_block = 0
+        P.general = 0
         P.npend = len(self.pend)
         P.is_last = 1 if is_last else 0
         for i, b in enumerate(self.pend):
@@ -112,11 +116,11 @@ class EmulState:
             P.carry_text8[i] = b
         P.carry_text_len = len(self.leftover)
         if self.cut:
-            P.k0 = Carry(1, 0, 0, 0, 0)
+            P.k0 = Carry(1, 0, 0, 0, 0, 0)
         elif self.leftover:
-            P.k0 = Carry(0, 1, char_count(self.leftover), len(self.pend), 0)
+            P.k0 = Carry(0, 1, char_count(self.leftover), len(self.pend), 0, 0)
         else:
-            P.k0 = Carry(0, 0, 0, 0, 0)
+            P.k0 = Carry(0, 0, 0, 0, 0, 0)
         if m.sb_table is not None:
             for i, v in enumerate(m.sb_table):
                 P.sb_table[i] = v
