@@ -284,7 +284,7 @@ def main():
         lst_ms.append(st.list_kernels_ms)
         ex_ms.append(st.exact_kernel_ms)
         win_total, win_listed = st.windows_total, st.windows_listed
-        host_ms.append((st.host_total_ms, st.host_post_ms))
+        host_ms.append((st.host_total_ms, st.host_post_ms, *[float(x) for x in st.host_phase_ms]))
         launches += st.kernel_launches
         d2h = st.d2h_bytes
     e1.record(stream)
@@ -368,7 +368,8 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "kernels_ms": kernels,
                          "pipeline_ms": avg(scan_ms), "pipeline_gbs": size / 1e9 / (avg(scan_ms) / 1e3),
                          "windows_total": int(win_total), "windows_listed": int(win_listed),
-                         "host_call_ms": avg([h[0] for h in host_ms]), "host_post_ms": avg([h[1] for h in host_ms])},
+                         "host_call_ms": avg([h[0] for h in host_ms]), "host_post_ms": avg([h[1] for h in host_ms]),
+                         "host_phase_ms": [avg([h[2 + k] for h in host_ms]) for k in range(4)]},
         }
         if not args.no_cpu:
             from helpers import to_oracle

@@ -139,6 +139,8 @@ typedef struct {
     uint64_t windows_total, windows_listed;
     float host_total_ms; /* wall clock of the whole call */
     float host_post_ms;  /* of which: building the collection after the last device sync */
+    float host_phase_ms[4]; /* wall clock: [0] call start -> kernels enqueued, [1] -> counters back (first sync),
+                             * [2] -> results downloaded (second sync), [3] -> collection built */
 } sx_scan_stats;
 void sx_scanner_state_last_stats(const sx_scanner_state*, sx_scan_stats* out);
 

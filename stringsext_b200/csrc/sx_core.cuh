@@ -1108,7 +1108,7 @@ SX_HD bool pref_interesting_ref(const ScanParams& P, const PrefCfg& c, const Geo
     WinGeom gp;
     geo.window(w - 1, gp);
     const PrefWin b = pref_window_ref(P, c, src, gp.ws, gp.we);
-    return b.trail + a.lead >= c.T;
+    return a.lead >= 1 && b.trail + a.lead >= c.T;  // a run of >= T good bytes reaches into this window
 }
 
 }  // namespace sx

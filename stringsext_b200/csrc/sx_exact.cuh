@@ -22,7 +22,7 @@ struct ScanOut {
     unsigned long long rec_cap;
     unsigned long long text_cap;
     uint2* block_desc;             // per exact-kernel block {first record, record count}
-    unsigned long long* counters;  // [0] records, [1] text bytes, [2] list entries
+    unsigned long long* counters;  // [0] records, [1] text bytes, [2] list entries, [3] next block of the exact kernel
     FinalState* final_state;
 };
 
@@ -143,6 +143,7 @@ struct ExactSmem {
     uint32_t warp_a[8], warp_b[8];
     unsigned long long bases[2];
     int32_t last_npend;
+    unsigned long long next_block;
     Utf8Tables tables;
     uint32_t cta_off[kMaxPrefCtas + 1];
     Record staged[kThreads][kBufRecs];  // MODE_BUFFER staging, one slot set per lane
@@ -359,33 +360,42 @@ sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const Exa
     Geometry geo;
     geo.init(P);
     const long long NE = X.list ? (long long)*X.ne_ptr : X.ne_static;
-    const long long e0 = (long long)blockIdx.x * kThreads;
-    if (e0 >= NE) return;  // the grid is sized for the worst case (every window listed)
+    if ((long long)blockIdx.x * kThreads >= NE) return;
     if (P.enc == ENC_UTF8)
         for (uint32_t k = threadIdx.x; k < 2048; k += kThreads) utf8_tables_fill(P, S.tables, k);
     if (X.list)
         for (uint32_t k = threadIdx.x; k <= X.ncta; k += kThreads) S.cta_off[k] = X.cta_off[k];
     __syncthreads();
-    const uint32_t nblk = (uint32_t)((NE - e0) < (long long)kThreads ? (NE - e0) : (long long)kThreads);
-    Carry c = carry_none();
-    const bool first_adj = e0 > 0 && list_window(X, S.cta_off, e0 - 1) == list_window(X, S.cta_off, e0) - 1;
-    if (first_adj) {
-        // Warm-up: the block starts inside a run of adjacent windows.  Replay preceding entries in
-        // state-only mode; a non-adjacent entry or a constant window makes the carry known.
-        long long back = 8;
-        for (;;) {
-            long long es = e0 - back;
-            if (es < 0) es = 0;
-            c = carry_unknown();
-            for (long long e = es; e < e0; e += kThreads) {
-                const uint32_t n = (uint32_t)((e0 - e) < (long long)kThreads ? (e0 - e) : (long long)kThreads);
-                c = block_pass<Dec>(P, O, X, geo, S, NE, e, n, false, c, 0);
+    // Persistent CTAs: the number of list entries is only known on the device, so the grid is a few CTAs per SM
+    // and every CTA claims 128-entry blocks from a device counter (block `b` owns entries [b * 128, b * 128 + 128)).
+    for (;;) {
+        if (threadIdx.x == 0) S.next_block = atomicAdd(&O.counters[3], 1ull);
+        __syncthreads();
+        const long long b = (long long)S.next_block;
+        __syncthreads();
+        if (b * kThreads >= NE) break;
+        const long long e0 = b * kThreads;
+        const uint32_t nblk = (uint32_t)((NE - e0) < (long long)kThreads ? (NE - e0) : (long long)kThreads);
+        Carry c = carry_none();
+        const bool first_adj = e0 > 0 && list_window(X, S.cta_off, e0 - 1) == list_window(X, S.cta_off, e0) - 1;
+        if (first_adj) {
+            // Warm-up: the block starts inside a run of adjacent windows.  Replay preceding entries in
+            // state-only mode; a non-adjacent entry or a constant window makes the carry known.
+            long long back = 8;
+            for (;;) {
+                long long es = e0 - back;
+                if (es < 0) es = 0;
+                c = carry_unknown();
+                for (long long e = es; e < e0; e += kThreads) {
+                    const uint32_t n = (uint32_t)((e0 - e) < (long long)kThreads ? (e0 - e) : (long long)kThreads);
+                    c = block_pass<Dec>(P, O, X, geo, S, NE, e, n, false, c, 0);
+                }
+                if (c.kind != K_UNKNOWN || es == 0) break;
+                back *= 4;
             }
-            if (c.kind != K_UNKNOWN || es == 0) break;
-            back *= 4;
         }
+        block_pass<Dec>(P, O, X, geo, S, NE, e0, nblk, true, c, b);
     }
-    block_pass<Dec>(P, O, X, geo, S, NE, e0, nblk, true, c, (long long)blockIdx.x);
 }
 
 

@@ -69,6 +69,19 @@ __device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
+// a[0..3]: dp4a accumulators, each holding 8 byte flags at bits S..S+7 -> the 32 flags as one mask word.
+// The multiply-adds run on the FMA pipe; one shift on the ALU pipe.
+__device__ __forceinline__ uint32_t mad_u(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+template <int S>
+__device__ __forceinline__ uint32_t pack_plane(const uint32_t* a) {
+    const uint32_t t = mad_u(a[2], 65536u, mad_u(a[1], 256u, a[0]));
+    return mad_u(a[3], 1u << (24 - S), t >> S);
+}
+
 // 128-bit helpers on uint32_t m[4] (bit i of the mask = byte i of the window)
 __device__ __forceinline__ void shr128(const uint32_t* m, uint32_t s, uint32_t* o) {
     const uint32_t wsft = s >> 5, bs = s & 31;
@@ -221,7 +234,12 @@ constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64 + 32 + kP
 
 // DEFSHAPE (PF_UTF8 only): the default filter shape -- ASCII blocks 1..3 may pass, only 2-byte leads
 // (block 6) may pass -- with the block functions folded into single LOP3s.
-template <int FAMILY, bool DEFSHAPE>
+// FAST (W == 128, T <= 32): bit-plane classification.  The top three bits of every byte are gathered into three
+// 128-bit planes with AND + dp4a (the dp4a and the plane assembly run on the FMA pipe, which the old per-word
+// SWAR left idle while the ALU pipe was saturated: ncu, profiles/r01_final_ncu_summary.json), the class logic then
+// costs a few LOP3 per 32 bytes, and the run test works on the window's good-byte mask extended by the last
+// T - 1 flags of the previous window (no lead/trail exchange).  Everything else takes the per-word path.
+template <int FAMILY, bool DEFSHAPE, bool FAST>
 __global__ void __launch_bounds__(kPrefThreads, 3)
 sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const __grid_constant__ PrefK K, const PrefOut O,
                     long long total_windows, long long ntiles, const __grid_constant__ CUtensorMap tmap, uint32_t use_tma) {
@@ -294,6 +312,109 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         uint32_t wlen = 0;
         if (valid) wlen = (uint32_t)(((ws + W) < P.len ? (ws + W) : P.len) - ws);
         uint32_t m[4] = {0, 0, 0, 0};
+        bool sure = false, cand = false;
+        if constexpr (FAST) {
+            // ---- bit planes p7/p6/p5 of the window's 128 bytes (8 conflict-free LDS.128) ----------------------
+            uint32_t p7[4], p6[4], p5[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t a7[4] = {0, 0, 0, 0}, a6[4] = {0, 0, 0, 0}, a5[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(sm + swz(tid * 128u + (2 * g + h) * 16u));
+                    const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = 4 * h + j;  // word inside the 32-byte group; a pair of words shares an accumulator
+                        const uint32_t wt = (k & 1) ? 0x80402010u : 0x08040201u;
+                        a7[k >> 1] = dp4a_u(xs[j] & 0x80808080u, wt, a7[k >> 1]);  // 8 flags at bits 7..14
+                        a6[k >> 1] = dp4a_u(xs[j] & 0x40404040u, wt, a6[k >> 1]);  //            bits 6..13
+                        a5[k >> 1] = dp4a_u(xs[j] & 0x20202020u, wt, a5[k >> 1]);  //            bits 5..12
+                    }
+                }
+                p7[g] = pack_plane<7>(a7);
+                p6[g] = pack_plane<6>(a6);
+                p5[g] = pack_plane<5>(a5);
+            }
+            // ---- class logic on the planes -> good-byte mask m (bit i = byte i of the window) -----------------
+            if (FAMILY == PF_UTF8) {
+                uint32_t cn[4], lp[4], lc[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    cn[g] = p7[g] & ~p6[g];                                                  // 10xxxxxx
+                    lp[g] = DEFSHAPE ? (p7[g] & p6[g] & ~p5[g]) : (p7[g] & p6[g] & lop3_sel(p5[g], K.kh[3], K.kh[2]));
+                    lc[g] = DEFSHAPE ? lp[g] : (lp[g] | (cn[g] & K.multi));
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t ap = DEFSHAPE ? (~p7[g] & (p6[g] | p5[g])) : (~p7[g] & blk2(p6[g], p5[g], K.ka));
+                    // byte i: Cn(i + 1) / LC(i - 1); both window edges are favourable (pref_good)
+                    const uint32_t ncn = __funnelshift_r(cn[g], g < 3 ? cn[g < 3 ? g + 1 : 3] : 0xFFFFFFFFu, 1);
+                    const uint32_t pl = __funnelshift_l(g > 0 ? lc[g > 0 ? g - 1 : 0] : 0xFFFFFFFFu, lc[g], 1);
+                    m[g] = ap | (lp[g] & ncn) | (cn[g] & pl);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) m[g] = lop3_sel(p7[g], blk2(p6[g], p5[g], K.kh), blk2(p6[g], p5[g], K.ka));
+                if (FAMILY == PF_UNIT) {
+                    // keep the flag of each unit's most significant byte and spread it over the unit
+                    uint32_t fh[4] = {m[0] & K.hi_mask[0], m[1] & K.hi_mask[1], m[2] & K.hi_mask[2], m[3] & K.hi_mask[3]};
+                    uint32_t gm[4] = {fh[0], fh[1], fh[2], fh[3]};
+#pragma unroll
+                    for (int sft = 1; sft < 4; ++sft) {
+                        if ((uint32_t)sft < C.unit) {
+                            uint32_t t[4];
+                            if (K.spread_left) {
+                                t[0] = __funnelshift_r(fh[0], fh[1], sft);
+                                t[1] = __funnelshift_r(fh[1], fh[2], sft);
+                                t[2] = __funnelshift_r(fh[2], fh[3], sft);
+                                t[3] = fh[3] >> sft;
+                            } else {
+                                t[0] = fh[0] << sft;
+                                t[1] = __funnelshift_l(fh[0], fh[1], sft);
+                                t[2] = __funnelshift_l(fh[1], fh[2], sft);
+                                t[3] = __funnelshift_l(fh[2], fh[3], sft);
+                            }
+                            gm[0] |= t[0]; gm[1] |= t[1]; gm[2] |= t[2]; gm[3] |= t[3];
+                        }
+                    }
+                    m[0] = gm[0] | K.edge_mask[0]; m[1] = gm[1] | K.edge_mask[1];
+                    m[2] = gm[2] | K.edge_mask[2]; m[3] = gm[3] | K.edge_mask[3];
+                }
+            }
+            // ---- run test on (last T-1 flags of the previous window : m), 160 bits ---------------------------
+            // the window before the tile's first one is not known here: taken as all good (pref_interesting_ref)
+            uint32_t prev_top = __shfl_up_sync(0xffffffffu, m[3], 1);
+            if (lane == 31) s_trail[warp] = m[3];
+            __syncthreads();
+            if (lane == 0) prev_top = warp ? s_trail[warp - 1] : 0xFFFFFFFFu;
+            const uint32_t T = C.T;
+            uint32_t r[5] = {T > 1 ? (prev_top & ~(0xFFFFFFFFu >> (T - 1))) : 0u, m[0], m[1], m[2], m[3]};
+            // r &= r << s marks the END of every run of ones at least (have + s) long
+            auto and_shl = [&](uint32_t sft) {
+                r[4] &= __funnelshift_l(r[3], r[4], sft);
+                r[3] &= __funnelshift_l(r[2], r[3], sft);
+                r[2] &= __funnelshift_l(r[1], r[2], sft);
+                r[1] &= __funnelshift_l(r[0], r[1], sft);
+                r[0] &= r[0] << sft;
+            };
+            uint32_t have = 1;
+            if (T >= 2) { and_shl(1); have = 2; }
+            if (T >= 4) { and_shl(2); have = 4; }
+            if (T >= 8) { and_shl(4); have = 8; }
+            if (T >= 16) { and_shl(8); have = 16; }
+            if (T >= 32) { and_shl(16); have = 32; }
+            if (T > have) and_shl(T - have);
+            // a run that ends inside the first T-1 bytes of the window began in the previous window
+            const uint32_t cross_bits = T > 1 ? (0xFFFFFFFFu >> (33 - T)) : 0u;
+            const bool crossing = (r[1] & cross_bits) != 0;
+            const bool inwin = ((r[1] & ~cross_bits) | r[2] | r[3] | r[4]) != 0;
+            if (valid) {
+                const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
+                sure = forced || crossing;
+                if (!sure && inwin) { if (do_refine) cand = true; else sure = true; }
+            }
+        } else {
         if (valid) {
             // Fully unrolled over the (up to) 8 16-byte chunks of the window: all mask indices are static.
             // acc[p] collects the flags of data words 2p and 2p+1 of the current 32-byte group (dp4a,
@@ -400,13 +521,13 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         s_trail[tid] = trail;
         __syncthreads();
         // sure: listed whatever the refinement says; cand: listed only if a long run holds enough chars
-        bool sure = false, cand = false;
         if (valid) {
             const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
             if (forced) sure = true;
             else if (tid == 0) sure = lead >= 1;
-            else sure = s_trail[tid - 1] + lead >= C.T;
+            else sure = lead >= 1 && s_trail[tid - 1] + lead >= C.T;
             if (!sure && longrun) { if (do_refine) cand = true; else sure = true; }
+        }
         }
         // queue the window (tile order = (warp, lane) order); candidates carry their good-byte mask
         const bool push = sure || cand;
@@ -791,31 +912,33 @@ static bool make_tensor_map(CUtensorMap* tm, const uint8_t* d_in, size_t len, ui
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int FAMILY, bool DEF>
+template <int FAMILY, bool DEF, bool FAST>
 static cudaError_t launch_prefilter_t(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
                                       long long ntiles, int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
     static thread_local bool attr_done[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(sx_prefilter_kernel<FAMILY, DEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrefSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(sx_prefilter_kernel<FAMILY, DEF, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrefSmemBytes);
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
-    sx_prefilter_kernel<FAMILY, DEF><<<grid, kPrefThreads, kPrefSmemBytes, st>>>(P, c, k, o, total_windows, ntiles, tm, use_tma);
+    sx_prefilter_kernel<FAMILY, DEF, FAST><<<grid, kPrefThreads, kPrefSmemBytes, st>>>(P, c, k, o, total_windows, ntiles, tm, use_tma);
     return cudaGetLastError();
 }
 
 static cudaError_t launch_prefilter(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
                                     long long ntiles, int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
     const bool defshape = c.family == PF_UTF8 && c.blkA == 0xEu && c.blkH == (1u << 6) && !c.multi;
+    const bool fast = P.W == 128 && c.T <= 32;
+#define SX_PREF(F, D) (fast ? launch_prefilter_t<F, D, true>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma) \
+                            : launch_prefilter_t<F, D, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma))
     switch (c.family) {
-    case PF_BYTE: return launch_prefilter_t<PF_BYTE, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma);
-    case PF_UTF8:
-        return defshape ? launch_prefilter_t<PF_UTF8, true>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma)
-                        : launch_prefilter_t<PF_UTF8, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma);
-    default: return launch_prefilter_t<PF_UNIT, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma);
+    case PF_BYTE: return SX_PREF(PF_BYTE, false);
+    case PF_UTF8: return defshape ? SX_PREF(PF_UTF8, true) : SX_PREF(PF_UTF8, false);
+    default: return SX_PREF(PF_UNIT, false);
     }
+#undef SX_PREF
 }
 
 static size_t utf8_char_count(const std::vector<uint8_t>& s) {
@@ -943,9 +1066,11 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             X.ncta = 0;
             X.region_stride = 0;
         }
-        CK(launch_exact_enc(P, O, X, (unsigned)max_blocks, st));
+        const unsigned xgrid = (unsigned)std::min<long long>(max_blocks, (long long)ss->num_sms * 4);
+        CK(launch_exact_enc(P, O, X, xgrid, st));
         CK(cudaEventRecord(ss->ev[1], st));
         ss->stats.kernel_launches++;
+        ss->stats.host_phase_ms[0] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         CK(cudaMemcpyAsync(counters, ss->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&fin, ss->d_final, sizeof fin, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -957,6 +1082,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ss->stats.relaunches++;
     }
     if (!pc.enabled) counters[2] = (unsigned long long)total_windows;
+    ss->stats.host_phase_ms[1] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     {
         float ms = 0;
         cudaEventElapsedTime(&ms, ss->ev[0], ss->ev[4]);
@@ -1014,6 +1140,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     }
 
     const auto t_post = std::chrono::steady_clock::now();
+    ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - t_begin).count();
     // ---- build the collection in stream order (blocks own contiguous record ranges) -------------------
     // At most two records carry host text in front of their device text: the very first record (a run that
     // began in the previous call) and the final leftover pseudo record, which is always the last one.
@@ -1118,6 +1245,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         const auto t_end = std::chrono::steady_clock::now();
         ss->stats.host_total_ms = std::chrono::duration<float, std::milli>(t_end - t_begin).count();
         ss->stats.host_post_ms = std::chrono::duration<float, std::milli>(t_end - t_post).count();
+        ss->stats.host_phase_ms[3] = ss->stats.host_total_ms;
     }
     guard.p = nullptr;
     return fc;

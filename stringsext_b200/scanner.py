@@ -87,6 +87,7 @@ class ScanStats(C.Structure):
         ("windows_listed", C.c_uint64),
         ("host_total_ms", C.c_float),
         ("host_post_ms", C.c_float),
+        ("host_phase_ms", C.c_float * 4),
     ]
 
 
