@@ -877,6 +877,19 @@ SX_HD WinGeom preroll_geom(const Geometry& geo, int64_t w, uint32_t pre_bytes) {
     return pg;
 }
 
+// The unlisted successor of a listed window whose carry-out needs an extension: only the run touching its left
+// boundary can print (the carry is consumed by the first segment), and that run is shorter than
+// max(T, chars_min_nb * maxlen) bytes because the window is not listed; the event that ends it follows within one
+// char.  So the extension pass only reads the first `pre_bytes + 8` bytes of the window.
+SX_HD WinGeom ext_geom(const Geometry& geo, int64_t w, uint32_t pre_bytes) {
+    WinGeom xg;
+    geo.window(w, xg);
+    const int64_t lim = xg.ws + (int64_t)pre_bytes + 8;
+    if (lim < xg.we) xg.we = lim;
+    xg.final_last = false;
+    return xg;
+}
+
 // A carry-out that can make an UNLISTED successor print something (DESIGN.md "Extension rule").
 // General missions (grep_char, same-unicode-block, chars_min_nb > q): a window with >= 2 segments depends on its
 // carry-in only through the one flag handed from segment 1 to segment 2, so it is CONSTANT iff forcing that
@@ -1108,7 +1121,9 @@ SX_HD bool pref_interesting_ref(const ScanParams& P, const PrefCfg& c, const Geo
     WinGeom gp;
     geo.window(w - 1, gp);
     const PrefWin b = pref_window_ref(P, c, src, gp.ws, gp.we);
-    return a.lead >= 1 && b.trail + a.lead >= c.T;  // a run of >= T good bytes reaches into this window
+    // a run of >= T good bytes that began in the previous window reaches into this one (a run that only starts at
+    // the window's first byte is an in-window run and subject to the char-count refinement above)
+    return a.lead >= 1 && b.trail >= 1 && b.trail + a.lead >= c.T;
 }
 
 }  // namespace sx

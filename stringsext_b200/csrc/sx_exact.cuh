@@ -135,6 +135,9 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 }
 
 struct ExactSmem {
+    uint32_t win[kThreads];       // window index of every entry of the block
+    uint32_t win_prev, win_next;  // windows of the entries just outside the block (kNoWin: none)
+    uint8_t next_adj[kThreads];
     WinDesc desc[kThreads];
     Carry kin[kThreads + 1];
     Carry kout[kThreads];
@@ -146,11 +149,16 @@ struct ExactSmem {
     unsigned long long next_block;
     Utf8Tables tables;
     uint32_t cta_off[kMaxPrefCtas + 1];
-    Record staged[kThreads][kBufRecs];  // MODE_BUFFER staging, one slot set per lane
-    uint16_t cnt_r[kThreads];           // records / text bytes of the entry under its real carry (isolated entries)
+    Record staged[kThreads][kBufRecs];   // MODE_BUFFER staging of the entry's own records
+    Record xstaged[kThreads][kBufRecs];  // ... and of the records its carry-out prints in an unlisted successor
+    uint16_t cnt_r[kThreads];            // records / text bytes of the entry under its real carry
     uint32_t cnt_t[kThreads];
     uint8_t have_cnt[kThreads];
+    uint16_t xcnt_r[kThreads];           // the same for the extension window
+    uint32_t xcnt_t[kThreads];
+    uint32_t queue[2 * kThreads];        // compacted work items of the divergent stages
 };
+constexpr uint32_t kNoWin = 0xFFFFFFFEu;
 
 // entry index -> window index: binary search of the owning prefilter CTA's region (offsets staged in smem)
 __device__ __forceinline__ long long list_window(const ExactCfg& X, const uint32_t* soff, long long e) {
@@ -161,6 +169,29 @@ __device__ __forceinline__ long long list_window(const ExactCfg& X, const uint32
         if ((long long)soff[mid] <= e) lo = mid; else hi = mid;
     }
     return (long long)X.list[(unsigned long long)lo * X.region_stride + (unsigned long long)(e - soff[lo])];
+}
+
+// Second passes (replays under the real carry, extension windows) concern a minority of the entries; run by the
+// entries' own lanes they would cost every warp a whole window pass for a handful of active lanes.  Instead the
+// lanes queue them and the block's threads take the queued items densely.  Lane i contributes item `ia` (if pa)
+// and item `ib` (if pb); returns the number of items (uniform).  Contains block barriers.
+__device__ __forceinline__ uint32_t block_enqueue(ExactSmem& S, bool pa, uint32_t ia, bool pb, uint32_t ib) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ba = __ballot_sync(0xffffffffu, pa), bb = __ballot_sync(0xffffffffu, pb);
+    if (lane == 0) S.warp_a[warp] = __popc(ba) + __popc(bb);
+    __syncthreads();
+    uint32_t off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+        const uint32_t c = S.warp_a[w];
+        if ((uint32_t)w < warp) off += c;
+        total += c;
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+    if (pa) S.queue[off + __popc(ba & lt)] = ia;
+    if (pb) S.queue[off + __popc(ba) + __popc(bb & lt)] = ib;
+    __syncthreads();
+    return total;
 }
 
 // One pass over list entries [e0, e0 + nblk): summary, carry resolution and (full) emission.
@@ -179,15 +210,25 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
     WinDesc d;
     d.type = WT_CONST; d.nrec = 0; d.ntext = 0; d.a = 0; d.t_out = 0; d.pad = 0; d.null_out = carry_none();
 
-    // ---- stage A: per-entry summary under the null carry ------------------------------------------
     if (active) {
         const long long e = e0 + i;
         w = list_window(X, S.cta_off, e);
-        adj = e > 0 && list_window(X, S.cta_off, e - 1) == w - 1;
-        next_adj = e + 1 < NE && list_window(X, S.cta_off, e + 1) == w + 1;
+        S.win[i] = (uint32_t)w;
+        if (i == 0) S.win_prev = e0 > 0 ? (uint32_t)list_window(X, S.cta_off, e0 - 1) : kNoWin;
+        if (i == nblk - 1) S.win_next = e + 1 < NE ? (uint32_t)list_window(X, S.cta_off, e + 1) : kNoWin;
+    }
+    __syncthreads();
+
+    // ---- stage A: per-entry summary under the null carry ------------------------------------------
+    if (active) {
+        adj = (i > 0 ? S.win[i - 1] : S.win_prev) + 1u == (uint32_t)w;
+        next_adj = (i + 1 < nblk ? S.win[i + 1] : S.win_next) == (uint32_t)w + 1u;
+        S.next_adj[i] = next_adj ? 1 : 0;
         geo.window(w, wg);
         S.have_cnt[i] = 0;
         S.out_done[i] = 0;
+        S.xcnt_r[i] = 0;
+        S.xcnt_t[i] = 0;
         // Isolated entries (and heads of runs) know their carry-in right away (pre-roll of the unlisted
         // predecessor): ONE pass under the real carry gives carry-out, counts and staged records.  Members of
         // a run are summarised under the null carry.  Both use the SAME call so the warp stays converged.
@@ -229,31 +270,36 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
     }
     __syncthreads();
 
-    // ---- stage B: resolve the carries along runs of adjacent windows -------------------------------
+    // ---- stage B: resolve the carries along runs of adjacent windows (compacted replays) ---------------
     for (;;) {
         const bool rdy = active && !S.out_done[i] && S.in_known[i];
-        __syncthreads();
-        if (rdy) {
-            const Carry kin = S.kin[i];
+        const uint32_t nq = block_enqueue(S, rdy, i, false, 0);
+        if (nq == 0) break;
+        if (i < nq) {
+            const uint32_t j = S.queue[i];
+            const Carry kin = S.kin[j];
+            const WinDesc dj = S.desc[j];
+            WinGeom wj;
+            geo.window((long long)S.win[j], wj);
             Carry out;
             if (kin.kind == K_UNKNOWN) out = kin;
-            else if (d.type == WT_CASEB) out = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws));
+            else if (dj.type == WT_CASEB) out = eval_caseb(P, dj, kin, (uint32_t)(wj.we - wj.ws));
             else {
                 // replay under the real carry; in a full pass this also yields the counts and staged records
                 WinResult r;
-                WindowEngine<Dec>::run(P, ts, g, wg, kin, full ? MODE_BUFFER : MODE_STATE, &S.staged[i][0], 0, r, nullptr);
+                WindowEngine<Dec>::run(P, ts, g, wj, kin, full ? MODE_BUFFER : MODE_STATE, &S.staged[j][0], 0, r, nullptr);
                 out = r.out;
                 if (full) {
-                    S.cnt_r[i] = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
-                    S.cnt_t[i] = r.ntext;
-                    S.have_cnt[i] = 1;
+                    S.cnt_r[j] = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
+                    S.cnt_t[j] = r.ntext;
+                    S.have_cnt[j] = 1;
                 }
             }
-            S.kout[i] = out;
-            S.out_done[i] = 1;
-            if (next_adj && i + 1 < nblk) { S.kin[i + 1] = out; S.in_known[i + 1] = 1; }
+            S.kout[j] = out;
+            S.out_done[j] = 1;
+            if (S.next_adj[j] && j + 1 < nblk) { S.kin[j + 1] = out; S.in_known[j + 1] = 1; }
         }
-        if (!__syncthreads_or(rdy)) break;
+        __syncthreads();
     }
     const Carry carry_out = S.kout[nblk - 1];
     if (!full) {
@@ -263,41 +309,53 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
 
     // ---- stage C: count, reserve, write --------------------------------------------------------------
     uint32_t cr = 0, ct = 0, xr = 0, xt = 0;
-    bool emit = false, ext = false;
+    bool need_emit = false, ext = false;
     Carry kin = carry_none(), kout = carry_none();
-    WinGeom xg;
     if (active) {
         kin = S.kin[i];
         kout = S.kout[i];
+        // member of a run whose carry-out came from its descriptor: one pass under the real carry, only if the
+        // window can print at all (records are staged, so usually no write pass follows)
+        if (!S.have_cnt[i]) need_emit = needs_emit(P, d, kin);
+        // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an
+        // unlisted successor: that window may print a continuation / the leftover
+        ext = carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.total_windows;
+    }
+    {
+        const uint32_t nq = block_enqueue(S, need_emit, i, ext, i | 0x10000u);
+        for (uint32_t t = i; t < nq; t += kThreads) {
+            const uint32_t item = S.queue[t], j = item & 0xFFFFu;
+            const bool isx = (item >> 16) != 0;
+            WinGeom wj;
+            if (isx) wj = ext_geom(geo, (long long)S.win[j] + 1, X.pre_bytes);
+            else geo.window((long long)S.win[j], wj);
+            const Carry kj = isx ? S.kout[j] : S.kin[j];
+            WinResult r;
+            WindowEngine<Dec>::run(P, ts, g, wj, kj, MODE_BUFFER, isx ? &S.xstaged[j][0] : &S.staged[j][0], 0, r, nullptr);
+            const uint16_t nr = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
+            if (isx) { S.xcnt_r[j] = nr; S.xcnt_t[j] = r.ntext; }
+            else { S.cnt_r[j] = nr; S.cnt_t[j] = r.ntext; S.have_cnt[j] = 1; }
+        }
+        __syncthreads();
+    }
+    WinGeom xg = wg;
+    if (active) {
         if (S.have_cnt[i]) {
-            if (S.cnt_r[i] != 0xFFFFu) { cr = S.cnt_r[i]; ct = S.cnt_t[i]; }
-            else {
+            cr = S.cnt_r[i]; ct = S.cnt_t[i];
+            if (cr == 0xFFFFu) {  // more records than the 16-bit counter holds: count on the lane
                 WinResult r;
                 WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_COUNT, nullptr, 0, r, nullptr);
                 cr = r.nrec; ct = r.ntext;
             }
-            emit = cr != 0;
-        } else {
-            // member of a run whose carry-out came from its descriptor: one pass under the real carry, only
-            // if the window can print at all (records are staged, so usually no write pass follows)
-            emit = needs_emit(P, d, kin);
-            if (emit) {
-                WinResult r;
-                WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_BUFFER, &S.staged[i][0], 0, r, nullptr);
-                cr = r.nrec; ct = r.ntext;
-                S.have_cnt[i] = 1;
-                S.cnt_r[i] = (uint16_t)(cr > 0xFFFFu ? 0xFFFFu : cr);
-                emit = cr != 0;
-            }
         }
-        // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an
-        // unlisted successor: that window may print a continuation / the leftover
-        ext = carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.total_windows;
         if (ext) {
-            geo.window(w + 1, xg);
-            WinResult r;
-            WindowEngine<Dec>::run(P, ts, g, xg, kout, MODE_COUNT, nullptr, 0, r, nullptr);
-            xr = r.nrec; xt = r.ntext;
+            xg = ext_geom(geo, w + 1, X.pre_bytes);
+            xr = S.xcnt_r[i]; xt = S.xcnt_t[i];
+            if (xr == 0xFFFFu) {
+                WinResult r;
+                WindowEngine<Dec>::run(P, ts, g, xg, kout, MODE_COUNT, nullptr, 0, r, nullptr);
+                xr = r.nrec; xt = r.ntext;
+            }
         }
     }
     const bool is_final = active && (e0 + i == NE - 1);
@@ -318,8 +376,8 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
     const unsigned long long br = S.bases[0], bt = S.bases[1];
     if ((br + tr <= O.rec_cap) && (bt + tt <= O.text_cap)) {
         uint32_t ro = er, to = et;
-        if (emit && cr) {
-            if (S.have_cnt[i] && cr <= kBufRecs) {  // staged by the single pass: patch the text offsets and copy
+        if (cr) {
+            if (cr <= kBufRecs) {  // staged by the counting pass: patch the text offsets and copy
                 for (uint32_t k = 0; k < cr; ++k) {
                     Record r = S.staged[i][k];
                     r.text_off += bt + to;
@@ -331,9 +389,17 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             }
         }
         ro += cr; to += ct;
-        if (ext && xr) {
-            WinResult r;
-            WindowEngine<Dec>::run(P, ts, g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+        if (xr) {
+            if (xr <= kBufRecs) {
+                for (uint32_t k = 0; k < xr; ++k) {
+                    Record r = S.xstaged[i][k];
+                    r.text_off += bt + to;
+                    O.recs[br + ro + k] = r;
+                }
+            } else {
+                WinResult r;
+                WindowEngine<Dec>::run(P, ts, g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+            }
         }
         ro += xr; to += xt;
         if (extra) {

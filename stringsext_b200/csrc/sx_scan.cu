@@ -525,7 +525,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
             if (forced) sure = true;
             else if (tid == 0) sure = lead >= 1;
-            else sure = lead >= 1 && s_trail[tid - 1] + lead >= C.T;
+            else sure = lead >= 1 && s_trail[tid - 1] >= 1 && s_trail[tid - 1] + lead >= C.T;
             if (!sure && longrun) { if (do_refine) cand = true; else sure = true; }
         }
         }

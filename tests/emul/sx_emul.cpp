@@ -115,11 +115,16 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         // extension: a "cut" carry reaches an unlisted successor
         const bool next_adjacent = e + 1 < ne && (int64_t)list[e + 1] == w + 1;
         if (carry_needs_extension(P, kout) && !next_adjacent && w + 1 < total) {
-            WinGeom xg;
-            geo.window(w + 1, xg);
+            WinGeom xf;
+            geo.window(w + 1, xf);
+            WinResult rf;
+            WindowEngine<Dec>::run(P, ts, g, xf, kout, MODE_COUNT, nullptr, 0, rf, nullptr);
+            if (carry_needs_extension(P, rf.out)) stats[3] += 1000;  // must never happen
+            // the product only reads the head of the window (ext_geom): same records as the full window
+            const WinGeom xg = ext_geom(geo, w + 1, pre_bytes);
             WinResult rx;
             emit_window(xg, kout, rx);
-            if (carry_needs_extension(P, rx.out)) stats[3] += 1000;  // must never happen
+            if (rx.nrec != rf.nrec || rx.ntext != rf.ntext) stats[3] += 100000;
         }
     }
     *final_carry = ne ? kprev : P.k0;
