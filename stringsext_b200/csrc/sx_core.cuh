@@ -872,7 +872,9 @@ struct Geometry {
 SX_HD WinGeom preroll_geom(const Geometry& geo, int64_t w, uint32_t pre_bytes) {
     WinGeom pg;
     geo.window(w - 1, pg);
-    if ((int64_t)pre_bytes < pg.we - pg.ws) pg.ws = pg.we - (int64_t)pre_bytes;
+    // at least pre_bytes; rounded down to a 16-byte boundary so the replay can use aligned vector loads
+    const int64_t s = (pg.we - (int64_t)pre_bytes) & ~(int64_t)15;
+    if (s > pg.ws) pg.ws = s;
     pg.final_last = false;
     return pg;
 }
@@ -1121,9 +1123,10 @@ SX_HD bool pref_interesting_ref(const ScanParams& P, const PrefCfg& c, const Geo
     WinGeom gp;
     geo.window(w - 1, gp);
     const PrefWin b = pref_window_ref(P, c, src, gp.ws, gp.we);
-    // a run of >= T good bytes that began in the previous window reaches into this one (a run that only starts at
-    // the window's first byte is an in-window run and subject to the char-count refinement above)
-    return a.lead >= 1 && b.trail >= 1 && b.trail + a.lead >= c.T;
+    // A run of >= T good bytes touches the window's left boundary.  This includes a run that only starts at the
+    // window's first byte (b.trail == 0): whatever its char count, it is the run a "cut" carry would complete,
+    // and listing it keeps the carry-out of every UNLISTED window independent of its carry-in.
+    return a.lead >= 1 && b.trail + a.lead >= c.T;
 }
 
 }  // namespace sx

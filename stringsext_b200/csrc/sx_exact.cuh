@@ -2,8 +2,9 @@
 // code in sx_scan.cu.  One instantiation per decoder lives in its own translation unit
 // (sx_exact_inst.cu compiled with -DSX_INST=n) so that the library builds in parallel.
 #pragma once
-#include "sx_fast_utf8.cuh"
+#include "sx_mask_utf8.cuh"
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace sx {
 
@@ -62,6 +63,11 @@ struct GlobalTile {
     __device__ __forceinline__ uint32_t lut(uint32_t i) const {
         uint32_t v;
         asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(tab_smem + i));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t cls(uint32_t b) const {
+        uint32_t v;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(tab_smem + 2048u + b));
         return v;
     }
     __device__ __forceinline__ uint8_t get(int64_t off) const { return g.get(off); }
@@ -138,6 +144,8 @@ struct ExactSmem {
     uint32_t win[kThreads];       // window index of every entry of the block
     uint32_t win_prev, win_next;  // windows of the entries just outside the block (kNoWin: none)
     uint8_t next_adj[kThreads];
+    uint8_t adj[kThreads];
+    uint8_t declined[kThreads];   // the mask engine declined the entry under its real carry
     WinDesc desc[kThreads];
     Carry kin[kThreads + 1];
     Carry kout[kThreads];
@@ -210,60 +218,135 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
     WinDesc d;
     d.type = WT_CONST; d.nrec = 0; d.ntext = 0; d.a = 0; d.t_out = 0; d.pad = 0; d.null_out = carry_none();
 
+    constexpr bool kIsUtf8 = std::is_same<Dec, DecUtf8>::value;
+    const bool use_mask = kIsUtf8 && !P.general;
+    const int run_mode = full ? MODE_BUFFER : MODE_STATE;
+
     if (active) {
         const long long e = e0 + i;
         w = list_window(X, S.cta_off, e);
         S.win[i] = (uint32_t)w;
         if (i == 0) S.win_prev = e0 > 0 ? (uint32_t)list_window(X, S.cta_off, e0 - 1) : kNoWin;
         if (i == nblk - 1) S.win_next = e + 1 < NE ? (uint32_t)list_window(X, S.cta_off, e + 1) : kNoWin;
+        S.have_cnt[i] = 0;
+        S.out_done[i] = 0;
+        S.in_known[i] = 0;
+        S.declined[i] = 0;
+        S.xcnt_r[i] = 0;
+        S.xcnt_t[i] = 0;
     }
     __syncthreads();
 
-    // ---- stage A: per-entry summary under the null carry ------------------------------------------
+    // An entry resolved under its real carry-in: counts, staged records, carry-out; propagates like a constant window.
+    auto store_resolved = [&](uint32_t j, const Carry& kin_j, const WinResult& r) {
+        S.kin[j] = kin_j;
+        S.in_known[j] = 1;
+        S.cnt_r[j] = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
+        S.cnt_t[j] = r.ntext;
+        S.have_cnt[j] = full ? 1 : 0;
+        S.kout[j] = r.out;
+        S.out_done[j] = 1;
+        WinDesc dj;
+        dj.type = WT_CONST; dj.pad = 0; dj.a = 0; dj.t_out = 0; dj.nrec = 0; dj.ntext = 0; dj.null_out = r.out;
+        S.desc[j] = dj;
+        if (j == nblk - 1) S.last_npend = r.npend_out;
+        if (S.next_adj[j] && j + 1 < nblk) { S.kin[j + 1] = r.out; S.in_known[j + 1] = 1; }
+    };
+
+    // ---- stage A: isolated entries and heads of runs know their carry-in (pre-roll of the unlisted predecessor):
+    //      one pass of the mask engine under the real carry gives carry-out, counts and staged records ------------
     if (active) {
         adj = (i > 0 ? S.win[i - 1] : S.win_prev) + 1u == (uint32_t)w;
         next_adj = (i + 1 < nblk ? S.win[i + 1] : S.win_next) == (uint32_t)w + 1u;
         S.next_adj[i] = next_adj ? 1 : 0;
+        S.adj[i] = adj ? 1 : 0;
         geo.window(w, wg);
-        S.have_cnt[i] = 0;
-        S.out_done[i] = 0;
-        S.xcnt_r[i] = 0;
-        S.xcnt_t[i] = 0;
-        // Isolated entries (and heads of runs) know their carry-in right away (pre-roll of the unlisted
-        // predecessor): ONE pass under the real carry gives carry-out, counts and staged records.  Members of
-        // a run are summarised under the null carry.  Both use the SAME call so the warp stays converged.
-        Carry kin0 = carry_none();
-        if (!adj) {
-            if (w == 0) kin0 = P.k0;
-            else {
-                const WinGeom rg = preroll_geom(geo, w, X.pre_bytes);
-                WinResult rr;
-                WindowEngine<Dec>::run(P, ts, g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
-                kin0 = rr.out;
-            }
-        }
-        WinResult r;
-        WinDesc dsum;
-        const int mode1 = adj ? MODE_COUNT : (full ? MODE_BUFFER : MODE_STATE);
-        WindowEngine<Dec>::run(P, ts, g, wg, kin0, mode1, &S.staged[i][0], 0, r, adj ? &dsum : nullptr);
-        if (i == nblk - 1) S.last_npend = r.npend_out;
-        if (!adj) {
-            S.kin[i] = kin0;
-            S.in_known[i] = 1;
-            S.cnt_r[i] = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
-            S.cnt_t[i] = r.ntext;
-            S.have_cnt[i] = 1;
-            d.type = WT_CONST;  // resolved: propagates like a constant window
-            d.null_out = r.out;
-        } else {
-            d = dsum;
-            if (i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
-            else S.in_known[i] = 0;
-        }
-        S.desc[i] = d;
     }
     __syncthreads();
-    if (active && d.type == WT_CONST) {
+    if constexpr (kIsUtf8) {
+        if (active && use_mask && !adj) {
+            Carry kin0 = P.k0;
+            bool ok = true;
+            if (w != 0) {
+                const WinGeom rg = preroll_geom(geo, w, X.pre_bytes);
+                WinResult rr;
+                ok = utf8_mask_window(P, ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr);
+                kin0 = rr.out;
+            }
+            if (ok) {
+                WinResult r;
+                if (utf8_mask_window(P, ts, wg, kin0, run_mode, &S.staged[i][0], 0, r)) store_resolved(i, kin0, r);
+            }
+        }
+        if (active && adj && i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
+        // Members of short runs: as soon as the predecessor is resolved, the mask engine under the real carry
+        // (queued, so the few members of a block share warps).  Long runs (text) skip this: their members are
+        // summarised under the null carry below, all at once.
+        const uint32_t n_adj = (uint32_t)__syncthreads_count(active && adj);
+        if (use_mask && n_adj <= 48) {
+            for (int round = 0; round < 3; ++round) {
+                const bool rdy = active && adj && !S.out_done[i] && !S.declined[i] && S.in_known[i] && S.kin[i].kind != K_UNKNOWN;
+                const uint32_t nq = block_enqueue(S, rdy, i, false, 0);
+                if (nq == 0) break;
+                if (i < nq) {
+                    const uint32_t j = S.queue[i];
+                    WinGeom wj;
+                    geo.window((long long)S.win[j], wj);
+                    const Carry kj = S.kin[j];
+                    WinResult r;
+                    if (utf8_mask_window(P, ts, wj, kj, run_mode, &S.staged[j][0], 0, r)) store_resolved(j, kj, r);
+                    else S.declined[j] = 1;
+                }
+                __syncthreads();
+            }
+        }
+    } else {
+        if (active && adj && i == 0) { S.kin[0] = carry_in; S.in_known[0] = 1; }
+        __syncthreads();
+    }
+
+    // ---- stage A': everything still open takes the byte-wise engine (queued): heads under their real carry,
+    //      members of runs summarised under the null carry ------------------------------------------------------------
+    const bool need_cls = active && !S.out_done[i];
+    {
+        const uint32_t nq = block_enqueue(S, need_cls, i, false, 0);
+        if (i < nq) {
+            const uint32_t j = S.queue[i];
+            const long long wj_idx = (long long)S.win[j];
+            const bool adj_j = S.adj[j] != 0;
+            WinGeom wj;
+            geo.window(wj_idx, wj);
+            Carry kin0 = carry_none();
+            if (!adj_j) {
+                if (wj_idx == 0) kin0 = P.k0;
+                else {
+                    const WinGeom rg = preroll_geom(geo, wj_idx, X.pre_bytes);
+                    WinResult rr;
+                    WindowEngine<Dec>::run(P, ts, g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
+                    kin0 = rr.out;
+                }
+            }
+            WinResult r;
+            WinDesc dsum;
+            const int mode1 = adj_j ? MODE_COUNT : run_mode;
+            WindowEngine<Dec>::run(P, ts, g, wj, kin0, mode1, &S.staged[j][0], 0, r, adj_j ? &dsum : nullptr);
+            if (j == nblk - 1) S.last_npend = r.npend_out;
+            if (!adj_j) {
+                S.kin[j] = kin0;
+                S.in_known[j] = 1;
+                S.cnt_r[j] = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
+                S.cnt_t[j] = r.ntext;
+                S.have_cnt[j] = 1;
+                dsum.type = WT_CONST;  // resolved: propagates like a constant window
+                dsum.pad = 0; dsum.a = 0; dsum.t_out = 0; dsum.nrec = 0; dsum.ntext = 0;
+                dsum.null_out = r.out;
+            }
+            S.desc[j] = dsum;
+        }
+        __syncthreads();
+    }
+    if (active) d = S.desc[i];
+    if (need_cls && d.type == WT_CONST) {
         S.kout[i] = d.null_out;
         S.out_done[i] = 1;
         if (next_adj && i + 1 < nblk) { S.kin[i + 1] = d.null_out; S.in_known[i + 1] = 1; }
@@ -330,8 +413,11 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             if (isx) wj = ext_geom(geo, (long long)S.win[j] + 1, X.pre_bytes);
             else geo.window((long long)S.win[j], wj);
             const Carry kj = isx ? S.kout[j] : S.kin[j];
+            Record* const dst = isx ? &S.xstaged[j][0] : &S.staged[j][0];
             WinResult r;
-            WindowEngine<Dec>::run(P, ts, g, wj, kj, MODE_BUFFER, isx ? &S.xstaged[j][0] : &S.staged[j][0], 0, r, nullptr);
+            bool done = false;
+            if constexpr (kIsUtf8) done = use_mask && utf8_mask_window(P, ts, wj, kj, MODE_BUFFER, dst, 0, r);
+            if (!done) WindowEngine<Dec>::run(P, ts, g, wj, kj, MODE_BUFFER, dst, 0, r, nullptr);
             const uint16_t nr = (uint16_t)(r.nrec > 0xFFFFu ? 0xFFFFu : r.nrec);
             if (isx) { S.xcnt_r[j] = nr; S.xcnt_t[j] = r.ntext; }
             else { S.cnt_r[j] = nr; S.cnt_t[j] = r.ntext; S.have_cnt[j] = 1; }

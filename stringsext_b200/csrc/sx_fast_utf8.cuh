@@ -20,6 +20,7 @@ namespace sx {
 // 7 Utf8Filter verdict for a char whose UTF-8 lead byte is this byte (mission.rs:333-348).
 struct Utf8Tables {
     uint8_t tt[8 * 256];
+    uint8_t cls[256];  // mask engine (sx_mask_utf8.cuh): bits 0-3 utf8_class(b), bit 4 the filter verdict for lead byte b
 };
 enum : uint32_t { FE_NONE = 0, FE_ASCII = 1, FE_CHAR = 2, FE_MAL = 3 };
 enum : uint32_t { FT_PRE = 0x20, FT_LEAD = 0x40, FT_PASS = 0x80 };
@@ -75,6 +76,7 @@ SX_HD void utf8_tables_fill(const ScanParams& P, Utf8Tables& T, uint32_t i) {  /
     uint32_t t = utf8_trans_entry(st, utf8_class(b));
     if ((b < 0x80 || b >= 0xC0) && pass_filter(P, b)) t |= FT_PASS;
     T.tt[i] = (uint8_t)t;
+    if (st == 0) T.cls[b] = (uint8_t)(utf8_class(b) | ((t & FT_PASS) ? 16u : 0u));
 }
 
 // Cold state: only the out-of-line record writer touches it, so it may live in local memory while the
@@ -339,23 +341,5 @@ SX_HD_NOINLINE void scan_window_fast_utf8(const ScanParams& P, const TileSrc& ts
         else desc->type = WT_CONST;
     }
 }
-
-// Engine dispatch used by the kernels and the test harness: UTF-8 takes the convergent engine.
-template <class Dec> struct WindowEngine {
-    template <class TileSrc>
-    SX_HD static void run(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
-                          int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
-        scan_window<Dec>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
-    }
-};
-template <> struct WindowEngine<DecUtf8> {
-    template <class TileSrc>
-    SX_HD static void run(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
-                          int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
-        // grep_char / same-unicode-block / chars_min_nb > q missions take the general automaton
-        if (tsrc.tables() && !P.general) scan_window_fast_utf8(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
-        else scan_window<DecUtf8>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
-    }
-};
 
 }  // namespace sx

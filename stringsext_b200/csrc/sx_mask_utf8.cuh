@@ -1,0 +1,495 @@
+// sx_mask_utf8.cuh -- bit-parallel window engine for UTF-8 missions (the common case of the exact kernel).
+//
+// Same semantics as scan_window_fast_utf8 / scan_window<DecUtf8> (FindingCollection::from + SplitStr::next,
+// /root/reference/src/finding_collection.rs:84-342, /root/reference/src/helper.rs:210-432, decoder = WHATWG
+// UTF-8 as restated in DecUtf8), but without a byte loop: the window (<= 128 bytes plus 3 bytes of look-back)
+// is turned into bit masks -- one bit per byte -- of the decoder events, and the few runs that can print are
+// located with bit scans.
+//
+//   class planes   every byte -> utf8_class (4 bits) + filter verdict (1 bit) through a 256-entry table, the five
+//                  flag bits of 32 bytes gathered into five mask words (dp4a on the device)
+//   decoder        a lead byte ALWAYS starts a sequence and a non-continuation byte ALWAYS ends one, so whether
+//                  a continuation byte is accepted depends on the <= 3 preceding bytes only:
+//                    ok1 = Cn & (range allowed by the lead one byte back), ok2 = Cn & ok1<<1 & len>=3 two back, ...
+//                  malformed events: X bytes, continuation bytes that are not accepted (`mal`: the next segment
+//                  starts after the byte) and bytes that arrive while a sequence is pending without being accepted
+//                  (`pre`: the next segment starts AT the byte, which is read again)
+//   runs           bytes of passing chars form maximal runs; a run prints iff it holds >= chars_min_nb chars and
+//                  ends inside the window; its position is the last segment start at or before it
+//
+// Everything unusual returns false and the caller takes the byte-wise engine: a carry-in other than a short
+// leftover, a run that could reach output_line_char_nb_max chars, a run covering the whole window, the last
+// window of a flushed stream, a finding whose precision depends on the Precision::Before probe.
+// tests/emul runs this code on the CPU against the oracle (it is tried first by WindowEngine<DecUtf8>).
+#pragma once
+#include "sx_fast_utf8.cuh"
+
+namespace sx {
+
+struct M5 { uint32_t w[5]; };  // bit 32 + p of the 160-bit mask = byte p of the window, p in -32..127
+
+SX_HD uint32_t sx_fsl(uint32_t lo, uint32_t hi, uint32_t k) {  // (hi:lo) << k, upper word; 1 <= k <= 31
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, k);
+#else
+    return (hi << k) | (lo >> (32 - k));
+#endif
+}
+SX_HD uint32_t sx_fsr(uint32_t lo, uint32_t hi, uint32_t k) {  // (hi:lo) >> k, lower word; 1 <= k <= 31
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, k);
+#else
+    return (lo >> k) | (hi << (32 - k));
+#endif
+}
+SX_HD uint32_t sx_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+SX_HD uint32_t sx_clz(uint32_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz(x);
+#else
+    return (uint32_t)__builtin_clz(x);
+#endif
+}
+SX_HD uint32_t sx_ctz(uint32_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(__ffs(x) - 1);
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+
+template <int K> SX_HD M5 m5_shl(const M5& a) {  // towards higher byte positions
+    M5 r;
+    r.w[0] = a.w[0] << K;
+#pragma unroll
+    for (int i = 1; i < 5; ++i) r.w[i] = sx_fsl(a.w[i - 1], a.w[i], K);
+    return r;
+}
+template <int K> SX_HD M5 m5_shr(const M5& a) {
+    M5 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.w[i] = sx_fsr(a.w[i], a.w[i + 1], K);
+    r.w[4] = a.w[4] >> K;
+    return r;
+}
+SX_HD bool m5_bit(const M5& a, uint32_t B) {  // static-index only (no local memory)
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) if ((B >> 5) == (uint32_t)i) v = a.w[i];
+    return ((v >> (B & 31)) & 1u) != 0;
+}
+// highest set bit at index <= B, or -1
+SX_HD int32_t m5_high_le(const M5& a, uint32_t B) {
+    int32_t r = -1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        uint32_t v = a.w[i];
+        const uint32_t lo = (uint32_t)i * 32u;
+        if (B < lo) v = 0;
+        else if (B < lo + 31u) v &= (2u << (B - lo)) - 1u;
+        if (v) r = (int32_t)(lo + 31u - sx_clz(v));
+    }
+    return r;
+}
+// lowest set bit at index >= B, or 160
+SX_HD uint32_t m5_low_ge(const M5& a, uint32_t B) {
+    uint32_t r = 160;
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+        uint32_t v = a.w[i];
+        const uint32_t lo = (uint32_t)i * 32u;
+        if (B >= lo + 32u) v = 0;
+        else if (B > lo) v &= ~((1u << (B - lo)) - 1u);
+        if (v) r = lo + sx_ctz(v);
+    }
+    return r;
+}
+// set bits with index in [A, B] (inclusive)
+SX_HD uint32_t m5_count(const M5& a, uint32_t A, uint32_t B) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        uint32_t v = a.w[i];
+        const uint32_t lo = (uint32_t)i * 32u;
+        if (B < lo || A >= lo + 32u) v = 0;
+        else {
+            if (A > lo) v &= ~((1u << (A - lo)) - 1u);
+            if (B < lo + 31u) v &= (2u << (B - lo)) - 1u;
+        }
+        n += sx_popc(v);
+    }
+    return n;
+}
+
+// The five class planes of a window.  TileSrc: load_chunk(r16, ws, we) (16 bytes, zero outside [ws, we)),
+// cls(b) (table lookup), get(off).
+template <class TileSrc>
+SX_HD void utf8_class_planes(const ScanParams& P, const TileSrc& tsrc, int64_t ws, int64_t we, M5* pl) {
+#pragma unroll
+    for (int t = 0; t < 5; ++t) pl[t].w[0] = 0;
+    // look-back: the three bytes before the window (bytes before the stream start leave the decoder neutral)
+#pragma unroll
+    for (int j = 1; j <= 3; ++j) {
+        const int64_t o = ws - j;
+        if (o >= -(int64_t)P.npend) {
+            const uint32_t c = tsrc.cls(tsrc.get(o));
+#pragma unroll
+            for (int t = 0; t < 5; ++t) pl[t].w[0] |= ((c >> t) & 1u) << (32 - j);
+        }
+    }
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+#if defined(__CUDA_ARCH__)
+        uint32_t acc[5][4];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0; }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t r16 = ws + (int64_t)(grp * 32 + h * 16);
+            if (r16 < we) {
+                const uint4 v = tsrc.load_chunk(r16, ws, we);
+                const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t x = xs[j];
+                    const uint32_t cw = tsrc.cls(x & 0xFFu) | (tsrc.cls((x >> 8) & 0xFFu) << 8) | (tsrc.cls((x >> 16) & 0xFFu) << 16) |
+                                        (tsrc.cls(x >> 24) << 24);
+                    const int k = 4 * h + j;
+                    const uint32_t wt = (k & 1) ? 0x80402010u : 0x08040201u;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) {
+                        uint32_t r;
+                        asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(cw & (0x01010101u << t)), "r"(wt), "r"(acc[t][k >> 1]));
+                        acc[t][k >> 1] = r;  // 8 flags at bits t .. t+7
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+            pl[t].w[grp + 1] = ((acc[t][0] | (acc[t][1] << 8) | (acc[t][2] << 16)) >> t) | (acc[t][3] << (24 - t));
+#else
+#pragma unroll
+        for (int t = 0; t < 5; ++t) pl[t].w[grp + 1] = 0;
+        for (int i = 0; i < 32; ++i) {
+            const int64_t o = ws + grp * 32 + i;
+            if (o >= we) break;
+            const uint32_t c = tsrc.cls(tsrc.get(o));
+            for (int t = 0; t < 5; ++t) pl[t].w[grp + 1] |= ((c >> t) & 1u) << i;
+        }
+#endif
+    }
+}
+
+struct MaskEmit {
+    const ScanParams* P;
+    int64_t base;
+    int mode;
+    Record* wr;
+    uint64_t text_off;
+    uint32_t nrec, ntext;
+};
+SX_HD void mask_emit(MaskEmit& E, int32_t seg_rel, uint32_t prec, int32_t run_s, int32_t run_e, uint32_t flags) {
+    const uint32_t len = (uint32_t)(run_e - run_s);
+    if (E.mode == MODE_WRITE || (E.mode == MODE_BUFFER && E.nrec < kBufRecs)) {
+        Record r;
+        r.position = E.P->base_consumed + (uint64_t)(E.base + seg_rel);  // finding_collection.rs:260
+        r.in_start = E.base + run_s;
+        r.in_len = len;
+        r.text_len = len;  // UTF-8 -> UTF-8: the text is the input range
+        r.text_off = E.text_off;
+        r.flags = flags;
+        r.precision = prec;
+        *E.wr++ = r;
+        E.text_off += len;
+    }
+    E.nrec++;
+    E.ntext += len;
+}
+
+// Returns false when the window needs the byte-wise engine (nothing has been written in that case that the
+// byte-wise engine would not overwrite).
+template <class TileSrc>
+SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode,
+                            Record* wr, uint64_t text_off, WinResult& res) {
+    const int64_t ws = geo.ws, we = geo.we;
+    const int32_t wlen = (int32_t)(we - ws);
+    const uint32_t n = P.n, q = P.q;
+    if (wlen < 4 || wlen > 128 || (ws & 15) != 0 || geo.final_last) return false;
+    if (kin.kind == K_UNKNOWN) return false;
+    const bool kc = kin.kind == K_C;              // the first run completes a cut finding whatever its length
+    const uint32_t k_in = kc ? 0u : kin.k;        // chars of the leftover the first run continues
+
+    M5 pl[5];
+    utf8_class_planes(P, tsrc, ws, we, pl);
+    // positions >= wlen: class 0 (ASCII), verdict 0 (zero fill read through the table may say otherwise)
+    M5 V;  // valid window positions
+    V.w[0] = 0;
+#pragma unroll
+    for (int i = 1; i < 5; ++i) {
+        const int32_t lo = (i - 1) * 32;
+        V.w[i] = wlen >= lo + 32 ? 0xFFFFFFFFu : (wlen > lo ? ((1u << (wlen - lo)) - 1u) : 0u);
+    }
+#pragma unroll
+    for (int t = 0; t < 5; ++t)
+#pragma unroll
+        for (int i = 1; i < 5; ++i) pl[t].w[i] &= V.w[i];
+
+    // ---- class masks (utf8_class: 0 A, 1 80-8F, 2 90-9F, 3 A0-BF, 4 X, 5 L2, 6 E0, 7 E1-EC/EE/EF, 8 ED, 9 F0, 10 F1-F3, 11 F4)
+    M5 Cn, C80, C90, CA0, X, L2, plain, E0, ED, F0, F4, len34, len4, PS;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uint32_t c0 = pl[0].w[i], c1 = pl[1].w[i], c2 = pl[2].w[i], c3 = pl[3].w[i];
+        const uint32_t hi0 = ~c3 & ~c2;  // classes 0..3
+        C80.w[i] = hi0 & ~c1 & c0;
+        C90.w[i] = hi0 & c1 & ~c0;
+        CA0.w[i] = hi0 & c1 & c0;
+        Cn.w[i] = hi0 & (c1 | c0);
+        X.w[i] = ~c3 & c2 & ~c1 & ~c0;                       // 4
+        L2.w[i] = ~c3 & c2 & ~c1 & c0;                       // 5
+        E0.w[i] = ~c3 & c2 & c1 & ~c0;                       // 6
+        const uint32_t l3n = ~c3 & c2 & c1 & c0;             // 7
+        ED.w[i] = c3 & ~c2 & ~c1 & ~c0;                      // 8
+        F0.w[i] = c3 & ~c2 & ~c1 & c0;                       // 9
+        const uint32_t l4n = c3 & ~c2 & c1 & ~c0;            // 10
+        F4.w[i] = c3 & ~c2 & c1 & c0;                        // 11
+        plain.w[i] = L2.w[i] | l3n | l4n;
+        len4.w[i] = F0.w[i] | l4n | F4.w[i];
+        len34.w[i] = E0.w[i] | l3n | ED.w[i] | len4.w[i];
+        PS.w[i] = pl[4].w[i];
+    }
+    // ---- decoder: accepted continuation bytes -----------------------------------------------------------------
+    M5 ok1, ok2, ok3, acc, pendm, pre, mal, seg;
+    {
+        const M5 s_plain = m5_shl<1>(plain), s_e0 = m5_shl<1>(E0), s_ed = m5_shl<1>(ED), s_f0 = m5_shl<1>(F0), s_f4 = m5_shl<1>(F4);
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            ok1.w[i] = Cn.w[i] & (s_plain.w[i] | (s_e0.w[i] & CA0.w[i]) | (s_ed.w[i] & (C80.w[i] | C90.w[i])) |
+                                  (s_f0.w[i] & (C90.w[i] | CA0.w[i])) | (s_f4.w[i] & C80.w[i]));
+        const M5 s1ok1 = m5_shl<1>(ok1), s2l34 = m5_shl<2>(len34);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) ok2.w[i] = Cn.w[i] & s1ok1.w[i] & s2l34.w[i];
+        const M5 s1ok2 = m5_shl<1>(ok2), s3l4 = m5_shl<3>(len4);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) ok3.w[i] = Cn.w[i] & s1ok2.w[i] & s3l4.w[i];
+        const M5 s1l34 = m5_shl<1>(len34), s2l4 = m5_shl<2>(len4);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            acc.w[i] = ok1.w[i] | ok2.w[i] | ok3.w[i];
+            // a sequence is pending AFTER this byte
+            pendm.w[i] = L2.w[i] | len34.w[i] | (ok1.w[i] & s1l34.w[i]) | (ok2.w[i] & s2l4.w[i]);
+            mal.w[i] = X.w[i] | (Cn.w[i] & ~acc.w[i]);
+        }
+        mal.w[0] = 0;  // what happened before the window only matters through the pending sequence
+        const M5 s1pend = m5_shl<1>(pendm), s1mal = m5_shl<1>(mal);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            pre.w[i] = s1pend.w[i] & ~acc.w[i] & V.w[i];
+            seg.w[i] = (pre.w[i] | s1mal.w[i]) & V.w[i];  // a segment starts at this byte
+        }
+    }
+    // ---- char events (at the last byte of the char) and the bytes of passing chars --------------------------------
+    M5 pe, R;  // pe: passing char ends; R: bytes of passing chars
+    {
+        const M5 s1L2 = m5_shl<1>(L2), s2l34 = m5_shl<2>(len34), s2l4 = m5_shl<2>(len4);
+        const M5 s1ps = m5_shl<1>(PS), s2ps = m5_shl<2>(PS), s3ps = m5_shl<3>(PS);
+        M5 p1, p2, p3, p4;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t a = ~(pl[0].w[i] | pl[1].w[i] | pl[2].w[i] | pl[3].w[i]);  // class 0
+            p1.w[i] = a & PS.w[i] & V.w[i];
+            p2.w[i] = ok1.w[i] & s1L2.w[i] & s1ps.w[i] & V.w[i];
+            p3.w[i] = ok2.w[i] & s2l34.w[i] & ~s2l4.w[i] & s2ps.w[i] & V.w[i];
+            p4.w[i] = ok3.w[i] & s3ps.w[i] & V.w[i];
+            pe.w[i] = p1.w[i] | p2.w[i] | p3.w[i] | p4.w[i];
+        }
+        const M5 r2 = m5_shr<1>(p2), r3a = m5_shr<1>(p3), r3b = m5_shr<2>(p3), r4a = m5_shr<1>(p4), r4b = m5_shr<2>(p4), r4c = m5_shr<3>(p4);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) R.w[i] = pe.w[i] | r2.w[i] | r3a.w[i] | r3b.w[i] | r4a.w[i] | r4b.w[i] | r4c.w[i];
+    }
+    // bytes still inside the decoder at the window end
+    const uint32_t Blast = 31u + (uint32_t)wlen;
+    int32_t npend_out = 0;
+    if (m5_bit(pendm, Blast)) {
+        M5 lead;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) lead.w[i] = L2.w[i] | len34.w[i];
+        npend_out = m5_bit(lead, Blast) ? 1 : (m5_bit(lead, Blast - 1) ? 2 : 3);
+        if (npend_out > wlen) return false;
+    }
+
+    MaskEmit E;
+    E.P = &P; E.base = ws; E.mode = mode; E.wr = wr; E.text_off = text_off; E.nrec = 0; E.ntext = 0;
+    const bool at_slice_start = geo.slice_start == ws;
+    // run boundaries
+    M5 RS, RE;  // first / last byte of every run
+    {
+        const M5 up = m5_shl<1>(R), dn = m5_shr<1>(R);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { RS.w[i] = R.w[i] & ~up.w[i]; RE.w[i] = R.w[i] & ~dn.w[i]; }
+    }
+    const uint32_t Bend = 32u + (uint32_t)wlen - (uint32_t)npend_out;  // one past the last complete char
+    int32_t last_seg = -2;  // segment of the last yield (-1: the window's first segment)
+    uint32_t next_B = 32;   // runs starting below this index are done
+
+    // bytes inside the decoder at the window start (the straddling char, if any, starts there)
+    int32_t pend0 = 0;
+    if (m5_bit(pendm, 31)) {
+        M5 lead;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) lead.w[i] = L2.w[i] | len34.w[i];
+        pend0 = m5_bit(lead, 31) ? 1 : (m5_bit(lead, 30) ? 2 : 3);
+    }
+    // The Precision::Before probe (finding_collection.rs:176-207) can only change the precision of a finding of a
+    // segment that starts at the slice start; with no leftover and a neutral decoder it changes nothing.
+    const bool probe_seg1 = at_slice_start && mode != MODE_STATE && k_in == 0 && pend0 > 0;
+    const bool probe_seg0 = at_slice_start && mode != MODE_STATE && k_in > 0;  // second segment at the slice start
+    const uint32_t lo_flags = (k_in > 0 && (kin.flags & CF_HOSTCARRY)) ? (uint32_t)RF_HOSTCARRY : 0u;
+
+    // ---- the run touching the left boundary: continues the leftover / completes the cut finding unless a pending
+    //      sequence breaks first (then the leftover ends at that break, helper.rs:315-322) -----------------------------
+    if (m5_bit(R, 32) && !m5_bit(pre, 32)) {
+        const uint32_t e_last = m5_low_ge(RE, 32);
+        const int32_t s0 = m5_high_le(RS, 32);
+        if (s0 < 29 || e_last >= 160) return false;
+        if (e_last + 1 >= Bend) return false;  // the run covers the whole window: carry-in dependent leftover / cut
+        const uint32_t chars = m5_count(pe, 32, e_last) + k_in;
+        if (chars >= q) return false;
+        if (kc || chars >= n) {
+            if (probe_seg1) return false;
+            mask_emit(E, 0, k_in > 0 ? PREC_BEFORE : PREC_EXACT, k_in > 0 ? -(int32_t)kin.in_bytes : s0 - 32,
+                      (int32_t)e_last + 1 - 32, lo_flags | (kc ? (uint32_t)RF_COMPLETES : 0u));
+            last_seg = -1;
+        }
+        next_B = e_last + 1;
+    } else if (k_in >= n) {
+        // the leftover alone is long enough: printed at the first event of the window
+        mask_emit(E, 0, PREC_BEFORE, -(int32_t)kin.in_bytes, -pend0, lo_flags);
+        last_seg = -1;
+    }
+    // ---- runs of >= n bytes inside the window ------------------------------------------------------------------------
+    {
+        // LR: last bytes of runs holding at least n bytes (n <= 128): AND of R shifted by 0 .. n-1
+        M5 LR = R;
+        uint32_t have = 1;
+        auto and_shl = [&](uint32_t s) {
+            if (s >= 32) {
+                const uint32_t ws_ = s >> 5, bs = s & 31;
+#pragma unroll
+                for (int i = 4; i >= 0; --i) {
+                    uint32_t lo = 0, hi = 0;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        if ((uint32_t)j + ws_ == (uint32_t)i) hi = LR.w[j];
+                        if ((uint32_t)j + ws_ + 1 == (uint32_t)i) lo = LR.w[j];
+                    }
+                    LR.w[i] &= bs ? sx_fsl(lo, hi, bs) : hi;
+                }
+            } else {
+#pragma unroll
+                for (int i = 4; i >= 1; --i) LR.w[i] &= sx_fsl(LR.w[i - 1], LR.w[i], s);
+                LR.w[0] &= LR.w[0] << s;
+            }
+        };
+        if (n >= 2) { and_shl(1); have = 2; }
+        if (n >= 4) { and_shl(2); have = 4; }
+        if (n >= 8) { and_shl(4); have = 8; }
+        if (n >= 16) { and_shl(8); have = 16; }
+        if (n >= 32) { and_shl(16); have = 32; }
+        if (n >= 64) { and_shl(32); have = 64; }
+        if (n > have) and_shl(n - have);
+        M5 cand;  // last bytes of the long runs
+#pragma unroll
+        for (int i = 0; i < 5; ++i) cand.w[i] = LR.w[i] & RE.w[i];
+        int guard = 0;
+        for (; guard < 12; ++guard) {
+            const uint32_t e_last = m5_low_ge(cand, next_B);
+            if (e_last >= 160) break;
+            next_B = e_last + 1;
+            if (e_last + 1 >= Bend) break;  // the run touching the right boundary never prints here (leftover)
+            const int32_t s = m5_high_le(RS, e_last);
+            if (s < 32) return false;
+            const uint32_t chars = m5_count(pe, (uint32_t)s, e_last);
+            if (chars >= q) return false;
+            if (chars < n) continue;
+            const int32_t sg = m5_high_le(seg, (uint32_t)s);  // segment start at or before the run
+            const int32_t seg_id = sg < 32 ? -1 : sg - 32;
+            if ((seg_id == 0 && probe_seg0) || (seg_id < 0 && probe_seg1)) return false;
+            const uint32_t prec = (seg_id == last_seg) ? PREC_AFTER : ((seg_id < 0 && k_in > 0) ? PREC_BEFORE : PREC_EXACT);
+            mask_emit(E, seg_id < 0 ? 0 : seg_id, prec, s - 32, (int32_t)e_last + 1 - 32, 0u);
+            last_seg = seg_id;
+        }
+        if (guard == 12) return false;  // a window crowded with short findings: byte-wise engine
+    }
+    // ---- carry out: the run of complete chars touching the window end (finding_collection.rs:281-284) -------------
+    res.out = carry_none();
+    if (Bend > 32 && m5_bit(R, Bend - 1)) {
+        const int32_t ts = m5_high_le(RS, Bend - 1);
+        if (ts <= 32) return false;
+        const uint32_t chars = m5_count(pe, (uint32_t)ts, Bend - 1);
+        if (chars >= q || chars == 0) return false;
+        Carry c;
+        c.kind = K_L; c.flags = 0; c.k = (uint16_t)chars;
+        c.in_bytes = 32u + (uint32_t)wlen - (uint32_t)ts;
+        c.out_bytes = Bend - (uint32_t)ts;
+        c.aux = 0;
+        res.out = c;
+    }
+    res.nrec = E.nrec;
+    res.ntext = E.ntext;
+    res.npend_out = npend_out;
+    res.m = 1;
+    res.cut1 = 0;
+    return true;
+}
+
+// Engine dispatch used by the kernels and the test harness: UTF-8 tries the mask engine, then the convergent
+// byte-wise engine; grep_char / same-unicode-block / chars_min_nb > q missions take the general automaton.
+template <class Dec> struct WindowEngine {
+    template <class TileSrc>
+    SX_HD static void run(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
+                          int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
+        scan_window<Dec>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
+    }
+};
+template <> struct WindowEngine<DecUtf8> {
+    template <class TileSrc>
+    SX_HD static void run(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
+                          int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
+        if (tsrc.tables() && !P.general) {
+#if !defined(__CUDA_ARCH__)
+            // host harness: the kernels call utf8_mask_window themselves (block_pass) and queue what it declines
+            if (!desc && tsrc.use_mask()) {
+                Record tmp[64];
+                const bool wr_mode = mode == MODE_WRITE || mode == MODE_BUFFER;
+                const bool ok = utf8_mask_window(P, tsrc, geo, kin, mode, wr, text_off, res);
+                tsrc.mask_result(ok);
+                if (ok) {
+                    // self-check of the harness: the byte-wise engine must agree (results and records)
+                    WinResult r2;
+                    scan_window_fast_utf8(P, tsrc, g, geo, kin, mode, tmp, text_off, r2, nullptr);
+                    bool same = r2.nrec == res.nrec && r2.ntext == res.ntext && r2.npend_out == res.npend_out &&
+                                r2.out.kind == res.out.kind && r2.out.k == res.out.k && r2.out.in_bytes == res.out.in_bytes &&
+                                r2.out.out_bytes == res.out.out_bytes && r2.out.flags == res.out.flags;
+                    if (same && wr_mode)
+                        for (uint32_t k = 0; k < res.nrec && (mode == MODE_WRITE || k < kBufRecs); ++k)
+                            same = same && tmp[k].position == wr[k].position && tmp[k].in_start == wr[k].in_start &&
+                                   tmp[k].in_len == wr[k].in_len && tmp[k].flags == wr[k].flags && tmp[k].precision == wr[k].precision &&
+                                   tmp[k].text_off == wr[k].text_off;
+                    if (!same) tsrc.mask_mismatch(geo.ws, geo.we, kin, mode);
+                    return;
+                }
+            }
+#endif
+            scan_window_fast_utf8(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
+        } else scan_window<DecUtf8>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
+    }
+};
+
+}  // namespace sx

@@ -405,8 +405,9 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             if (T >= 16) { and_shl(8); have = 16; }
             if (T >= 32) { and_shl(16); have = 32; }
             if (T > have) and_shl(T - have);
-            // a run that ends inside the first T-1 bytes of the window began in the previous window
-            const uint32_t cross_bits = T > 1 ? (0xFFFFFFFFu >> (33 - T)) : 0u;
+            // a run that ends inside the first T-1 bytes of the window began in the previous window; one that ends at
+            // byte T-1 covers the window's first T bytes: both touch the left boundary (pref_interesting_ref)
+            const uint32_t cross_bits = 0xFFFFFFFFu >> (32 - T);
             const bool crossing = (r[1] & cross_bits) != 0;
             const bool inwin = ((r[1] & ~cross_bits) | r[2] | r[3] | r[4]) != 0;
             if (valid) {
@@ -525,7 +526,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
             if (forced) sure = true;
             else if (tid == 0) sure = lead >= 1;
-            else sure = lead >= 1 && s_trail[tid - 1] >= 1 && s_trail[tid - 1] + lead >= C.T;
+            else sure = lead >= 1 && s_trail[tid - 1] + lead >= C.T;
             if (!sure && longrun) { if (do_refine) cand = true; else sure = true; }
         }
         }

@@ -53,8 +53,9 @@ def lib():
     global _lib
     if _lib is None:
         src = os.path.join(HERE, "sx_emul.cpp")
-        core = os.path.join(HERE, "..", "..", "stringsext_b200", "csrc", "sx_core.cuh")
-        if (not os.path.exists(LIB)) or max(os.path.getmtime(src), os.path.getmtime(core)) > os.path.getmtime(LIB):
+        csrc = os.path.join(HERE, "..", "..", "stringsext_b200", "csrc")
+        deps = [src] + [os.path.join(csrc, f) for f in ("sx_core.cuh", "sx_fast_utf8.cuh", "sx_mask_utf8.cuh")]
+        if (not os.path.exists(LIB)) or max(os.path.getmtime(f) for f in deps) > os.path.getmtime(LIB):
             os.makedirs(os.path.dirname(LIB), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", LIB, src])
         L = C.CDLL(LIB)

@@ -7,7 +7,7 @@
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return s ? (uint32_t)((((uint64_t)hi << 32) | lo) >> s) : lo; }
 #endif
-#include "../../stringsext_b200/csrc/sx_fast_utf8.cuh"
+#include "../../stringsext_b200/csrc/sx_mask_utf8.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,10 +18,21 @@ using namespace sx;
 
 static Utf8Tables g_tables;
 static int g_use_fast = 1;
+static int g_use_mask = 1;
+static uint64_t g_mask_ok = 0, g_mask_declined = 0;
+static uint64_t g_mask_mismatch = 0;
 struct HostTile {
     GlobalSrc g;
     const Utf8Tables* tables() const { return g_use_fast ? &g_tables : nullptr; }
     uint32_t lut(uint32_t i) const { return g_tables.tt[i]; }
+    uint32_t cls(uint32_t b) const { return g_tables.cls[b]; }
+    bool use_mask() const { return g_use_mask != 0; }
+    void mask_result(bool ok) const { if (ok) g_mask_ok++; else g_mask_declined++; }
+    void mask_mismatch(int64_t ws, int64_t we, const Carry& kin, int mode) const {
+        if (g_mask_mismatch++ < 5)
+            fprintf(stderr, "mask engine mismatch: window [%lld,%lld) kin kind=%d k=%d in_bytes=%u flags=%d mode=%d\n", (long long)ws,
+                    (long long)we, kin.kind, kin.k, kin.in_bytes, kin.flags, mode);
+    }
     uint4 load_chunk(int64_t r16, int64_t ws, int64_t we) const {
         uint32_t w[4] = {0, 0, 0, 0};
         for (int i = 0; i < 16; ++i) {
@@ -158,6 +169,9 @@ struct emul_out {
 
 // Returns 0 on success.  `params` is a fully populated ScanParams (in = host pointer).
 void sx_emul_set_fast(int on) { g_use_fast = on; }
+void sx_emul_set_mask(int on) { g_use_mask = on; }
+void sx_emul_mask_counts(uint64_t* ok, uint64_t* declined) { *ok = g_mask_ok; *declined = g_mask_declined; }
+uint64_t sx_emul_mask_mismatches() { return g_mask_mismatch; }
 int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
     for (uint32_t i = 0; i < 2048; ++i) utf8_tables_fill(*P, g_tables, i);
     std::vector<uint32_t> list;
