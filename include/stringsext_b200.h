@@ -134,6 +134,8 @@ typedef struct {
     uint32_t relaunches;         /* pipeline re-runs caused by an output buffer that was too small */
     uint32_t prefilter_used;
     uint32_t tma_used;           /* the prefilter staged its tiles with cp.async.bulk.tensor */
+    uint32_t sparse_used;        /* the exact stage ran as the barrier-free sparse-list pipeline (UTF-8) */
+    uint32_t reserved0;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t n_records, text_bytes;
     uint64_t windows_total, windows_listed;
@@ -147,6 +149,7 @@ void sx_scanner_state_last_stats(const sx_scanner_state*, sx_scan_stats* out);
 /* Tuning / test hooks.  The prefilter never changes results (tests compare both settings). */
 void sx_scanner_state_set_prefilter(sx_scanner_state*, int enabled);
 void sx_scanner_state_set_tma(sx_scanner_state*, int enabled); /* 0: stage tiles with plain vector loads */
+void sx_scanner_state_set_sparse(sx_scanner_state*, int enabled); /* 0: always the block kernel for the exact stage */
 /* Copies the window list the prefilter built in the most recent call (ascending window indices,
  * window = decoder_input_window of finding_collection.rs:120-131) into out[0..cap); returns the
  * list length, 0 when the prefilter did not run. */

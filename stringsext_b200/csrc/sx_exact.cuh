@@ -560,4 +560,12 @@ cudaError_t launch_exact_sb(const ScanParams& P, const ScanOut& O, const ExactCf
 cudaError_t launch_exact_utf32le(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
 cudaError_t launch_exact_utf32be(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
 
+// sparse-list pipeline for UTF-8 (sx_sparse_utf8.cuh, compiled into the UTF-8 translation unit)
+cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
+                               void* queue, long long NE, int num_sms, cudaStream_t st);
+size_t sparse_entry_bytes();
+size_t sparse_tables_bytes();
+uint32_t sparse_threads();
+uint32_t sparse_launches();
+
 }  // namespace sx

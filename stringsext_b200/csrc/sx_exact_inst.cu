@@ -1,5 +1,8 @@
 // sx_exact_inst.cu -- one instantiation of sx_exact_kernel<Dec> per translation unit (-DSX_INST=n).
 #include "sx_exact.cuh"
+#if SX_INST == 1
+#include "sx_sparse_utf8.cuh"
+#endif
 
 namespace sx {
 #if SX_INST == 0
@@ -31,4 +34,21 @@ cudaError_t SX_NAME(const ScanParams& P, const ScanOut& O, const ExactCfg& X, un
     sx_exact_kernel<SX_DEC><<<grid, kThreads, 0, st>>>(P, O, X);
     return cudaGetLastError();
 }
+#if SX_INST == 1
+cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
+                               void* queue, long long NE, int num_sms, cudaStream_t st) {
+    SparseBufs B;
+    B.E = static_cast<EntryState*>(entries);
+    B.btot = static_cast<ulonglong2*>(btot);
+    B.tables = static_cast<Utf8Tables*>(tables);
+    B.queue = static_cast<uint32_t*>(queue);
+    B.qcount = O.counters + 3;  // the block kernel's claim counter, unused on this path (zeroed per attempt)
+    B.NE = NE;
+    return launch_sparse_utf8_impl(P, O, X, B, num_sms, st);
+}
+size_t sparse_entry_bytes() { return sizeof(EntryState); }
+size_t sparse_tables_bytes() { return sizeof(Utf8Tables); }
+uint32_t sparse_threads() { return kSpThreads; }
+uint32_t sparse_launches() { return kSparseLaunches; }
+#endif
 }  // namespace sx

@@ -26,7 +26,8 @@
 
 namespace sx {
 
-struct M5 { uint32_t w[5]; };  // bit 32 + p of the 160-bit mask = byte p of the window, p in -32..127
+template <int NW> struct MK { uint32_t w[NW + 1]; };  // bit 32 + p of the mask = byte p of the window, p in -32 .. 32*NW-1
+// (NW = data words: 4 for a full 128-byte window, 2 for the short pre-roll / extension windows)
 
 SX_HD uint32_t sx_fsl(uint32_t lo, uint32_t hi, uint32_t k) {  // (hi:lo) << k, upper word; 1 <= k <= 31
 #if defined(__CUDA_ARCH__)
@@ -64,31 +65,31 @@ SX_HD uint32_t sx_ctz(uint32_t x) {  // x != 0
 #endif
 }
 
-template <int K> SX_HD M5 m5_shl(const M5& a) {  // towards higher byte positions
-    M5 r;
+template <int K, int NW> SX_HD MK<NW> m5_shl(const MK<NW>& a) {  // towards higher byte positions
+    MK<NW> r;
     r.w[0] = a.w[0] << K;
 #pragma unroll
-    for (int i = 1; i < 5; ++i) r.w[i] = sx_fsl(a.w[i - 1], a.w[i], K);
+    for (int i = 1; i < NW + 1; ++i) r.w[i] = sx_fsl(a.w[i - 1], a.w[i], K);
     return r;
 }
-template <int K> SX_HD M5 m5_shr(const M5& a) {
-    M5 r;
+template <int K, int NW> SX_HD MK<NW> m5_shr(const MK<NW>& a) {
+    MK<NW> r;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r.w[i] = sx_fsr(a.w[i], a.w[i + 1], K);
-    r.w[4] = a.w[4] >> K;
+    for (int i = 0; i < NW; ++i) r.w[i] = sx_fsr(a.w[i], a.w[i + 1], K);
+    r.w[NW] = a.w[NW] >> K;
     return r;
 }
-SX_HD bool m5_bit(const M5& a, uint32_t B) {  // static-index only (no local memory)
+template <int NW> SX_HD bool m5_bit(const MK<NW>& a, uint32_t B) {  // static-index only (no local memory)
     uint32_t v = 0;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) if ((B >> 5) == (uint32_t)i) v = a.w[i];
+    for (int i = 0; i < NW + 1; ++i) if ((B >> 5) == (uint32_t)i) v = a.w[i];
     return ((v >> (B & 31)) & 1u) != 0;
 }
 // highest set bit at index <= B, or -1
-SX_HD int32_t m5_high_le(const M5& a, uint32_t B) {
+template <int NW> SX_HD int32_t m5_high_le(const MK<NW>& a, uint32_t B) {
     int32_t r = -1;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < NW + 1; ++i) {
         uint32_t v = a.w[i];
         const uint32_t lo = (uint32_t)i * 32u;
         if (B < lo) v = 0;
@@ -97,11 +98,11 @@ SX_HD int32_t m5_high_le(const M5& a, uint32_t B) {
     }
     return r;
 }
-// lowest set bit at index >= B, or 160
-SX_HD uint32_t m5_low_ge(const M5& a, uint32_t B) {
-    uint32_t r = 160;
+// lowest set bit at index >= B, or 32 * (NW + 1)
+template <int NW> SX_HD uint32_t m5_low_ge(const MK<NW>& a, uint32_t B) {
+    uint32_t r = 32 * (NW + 1);
 #pragma unroll
-    for (int i = 4; i >= 0; --i) {
+    for (int i = NW; i >= 0; --i) {
         uint32_t v = a.w[i];
         const uint32_t lo = (uint32_t)i * 32u;
         if (B >= lo + 32u) v = 0;
@@ -111,10 +112,10 @@ SX_HD uint32_t m5_low_ge(const M5& a, uint32_t B) {
     return r;
 }
 // set bits with index in [A, B] (inclusive)
-SX_HD uint32_t m5_count(const M5& a, uint32_t A, uint32_t B) {
+template <int NW> SX_HD uint32_t m5_count(const MK<NW>& a, uint32_t A, uint32_t B) {
     uint32_t n = 0;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < NW + 1; ++i) {
         uint32_t v = a.w[i];
         const uint32_t lo = (uint32_t)i * 32u;
         if (B < lo || A >= lo + 32u) v = 0;
@@ -129,8 +130,8 @@ SX_HD uint32_t m5_count(const M5& a, uint32_t A, uint32_t B) {
 
 // The five class planes of a window.  TileSrc: load_chunk(r16, ws, we) (16 bytes, zero outside [ws, we)),
 // cls(b) (table lookup), get(off).
-template <class TileSrc>
-SX_HD void utf8_class_planes(const ScanParams& P, const TileSrc& tsrc, int64_t ws, int64_t we, M5* pl) {
+template <int NW, class TileSrc>
+SX_HD void utf8_class_planes(const ScanParams& P, const TileSrc& tsrc, int64_t ws, int64_t we, MK<NW>* pl) {
 #pragma unroll
     for (int t = 0; t < 5; ++t) pl[t].w[0] = 0;
     // look-back: the three bytes before the window (bytes before the stream start leave the decoder neutral)
@@ -144,7 +145,7 @@ SX_HD void utf8_class_planes(const ScanParams& P, const TileSrc& tsrc, int64_t w
         }
     }
 #pragma unroll
-    for (int grp = 0; grp < 4; ++grp) {
+    for (int grp = 0; grp < NW; ++grp) {
 #if defined(__CUDA_ARCH__)
         uint32_t acc[5][4];
 #pragma unroll
@@ -215,36 +216,37 @@ SX_HD void mask_emit(MaskEmit& E, int32_t seg_rel, uint32_t prec, int32_t run_s,
 
 // Returns false when the window needs the byte-wise engine (nothing has been written in that case that the
 // byte-wise engine would not overwrite).
-template <class TileSrc>
-SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode,
+template <int NW, class TileSrc>
+SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode,
                             Record* wr, uint64_t text_off, WinResult& res) {
     const int64_t ws = geo.ws, we = geo.we;
     const int32_t wlen = (int32_t)(we - ws);
     const uint32_t n = P.n, q = P.q;
-    if (wlen < 4 || wlen > 128 || (ws & 15) != 0 || geo.final_last) return false;
+    if (wlen < 4 || wlen > 32 * NW || (ws & 15) != 0 || geo.final_last) return false;
     if (kin.kind == K_UNKNOWN) return false;
     const bool kc = kin.kind == K_C;              // the first run completes a cut finding whatever its length
     const uint32_t k_in = kc ? 0u : kin.k;        // chars of the leftover the first run continues
 
+    using M5 = MK<NW>;
     M5 pl[5];
-    utf8_class_planes(P, tsrc, ws, we, pl);
+    utf8_class_planes<NW>(P, tsrc, ws, we, pl);
     // positions >= wlen: class 0 (ASCII), verdict 0 (zero fill read through the table may say otherwise)
     M5 V;  // valid window positions
     V.w[0] = 0;
 #pragma unroll
-    for (int i = 1; i < 5; ++i) {
+    for (int i = 1; i < NW + 1; ++i) {
         const int32_t lo = (i - 1) * 32;
         V.w[i] = wlen >= lo + 32 ? 0xFFFFFFFFu : (wlen > lo ? ((1u << (wlen - lo)) - 1u) : 0u);
     }
 #pragma unroll
     for (int t = 0; t < 5; ++t)
 #pragma unroll
-        for (int i = 1; i < 5; ++i) pl[t].w[i] &= V.w[i];
+        for (int i = 1; i < NW + 1; ++i) pl[t].w[i] &= V.w[i];
 
     // ---- class masks (utf8_class: 0 A, 1 80-8F, 2 90-9F, 3 A0-BF, 4 X, 5 L2, 6 E0, 7 E1-EC/EE/EF, 8 ED, 9 F0, 10 F1-F3, 11 F4)
     M5 Cn, C80, C90, CA0, X, L2, plain, E0, ED, F0, F4, len34, len4, PS;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < NW + 1; ++i) {
         const uint32_t c0 = pl[0].w[i], c1 = pl[1].w[i], c2 = pl[2].w[i], c3 = pl[3].w[i];
         const uint32_t hi0 = ~c3 & ~c2;  // classes 0..3
         C80.w[i] = hi0 & ~c1 & c0;
@@ -269,18 +271,18 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
     {
         const M5 s_plain = m5_shl<1>(plain), s_e0 = m5_shl<1>(E0), s_ed = m5_shl<1>(ED), s_f0 = m5_shl<1>(F0), s_f4 = m5_shl<1>(F4);
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
+        for (int i = 0; i < NW + 1; ++i)
             ok1.w[i] = Cn.w[i] & (s_plain.w[i] | (s_e0.w[i] & CA0.w[i]) | (s_ed.w[i] & (C80.w[i] | C90.w[i])) |
                                   (s_f0.w[i] & (C90.w[i] | CA0.w[i])) | (s_f4.w[i] & C80.w[i]));
         const M5 s1ok1 = m5_shl<1>(ok1), s2l34 = m5_shl<2>(len34);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) ok2.w[i] = Cn.w[i] & s1ok1.w[i] & s2l34.w[i];
+        for (int i = 0; i < NW + 1; ++i) ok2.w[i] = Cn.w[i] & s1ok1.w[i] & s2l34.w[i];
         const M5 s1ok2 = m5_shl<1>(ok2), s3l4 = m5_shl<3>(len4);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) ok3.w[i] = Cn.w[i] & s1ok2.w[i] & s3l4.w[i];
+        for (int i = 0; i < NW + 1; ++i) ok3.w[i] = Cn.w[i] & s1ok2.w[i] & s3l4.w[i];
         const M5 s1l34 = m5_shl<1>(len34), s2l4 = m5_shl<2>(len4);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < NW + 1; ++i) {
             acc.w[i] = ok1.w[i] | ok2.w[i] | ok3.w[i];
             // a sequence is pending AFTER this byte
             pendm.w[i] = L2.w[i] | len34.w[i] | (ok1.w[i] & s1l34.w[i]) | (ok2.w[i] & s2l4.w[i]);
@@ -289,7 +291,7 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
         mal.w[0] = 0;  // what happened before the window only matters through the pending sequence
         const M5 s1pend = m5_shl<1>(pendm), s1mal = m5_shl<1>(mal);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < NW + 1; ++i) {
             pre.w[i] = s1pend.w[i] & ~acc.w[i] & V.w[i];
             seg.w[i] = (pre.w[i] | s1mal.w[i]) & V.w[i];  // a segment starts at this byte
         }
@@ -301,7 +303,7 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
         const M5 s1ps = m5_shl<1>(PS), s2ps = m5_shl<2>(PS), s3ps = m5_shl<3>(PS);
         M5 p1, p2, p3, p4;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < NW + 1; ++i) {
             const uint32_t a = ~(pl[0].w[i] | pl[1].w[i] | pl[2].w[i] | pl[3].w[i]);  // class 0
             p1.w[i] = a & PS.w[i] & V.w[i];
             p2.w[i] = ok1.w[i] & s1L2.w[i] & s1ps.w[i] & V.w[i];
@@ -311,7 +313,7 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
         }
         const M5 r2 = m5_shr<1>(p2), r3a = m5_shr<1>(p3), r3b = m5_shr<2>(p3), r4a = m5_shr<1>(p4), r4b = m5_shr<2>(p4), r4c = m5_shr<3>(p4);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) R.w[i] = pe.w[i] | r2.w[i] | r3a.w[i] | r3b.w[i] | r4a.w[i] | r4b.w[i] | r4c.w[i];
+        for (int i = 0; i < NW + 1; ++i) R.w[i] = pe.w[i] | r2.w[i] | r3a.w[i] | r3b.w[i] | r4a.w[i] | r4b.w[i] | r4c.w[i];
     }
     // bytes still inside the decoder at the window end
     const uint32_t Blast = 31u + (uint32_t)wlen;
@@ -319,7 +321,7 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
     if (m5_bit(pendm, Blast)) {
         M5 lead;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) lead.w[i] = L2.w[i] | len34.w[i];
+        for (int i = 0; i < NW + 1; ++i) lead.w[i] = L2.w[i] | len34.w[i];
         npend_out = m5_bit(lead, Blast) ? 1 : (m5_bit(lead, Blast - 1) ? 2 : 3);
         if (npend_out > wlen) return false;
     }
@@ -332,7 +334,7 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
     {
         const M5 up = m5_shl<1>(R), dn = m5_shr<1>(R);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { RS.w[i] = R.w[i] & ~up.w[i]; RE.w[i] = R.w[i] & ~dn.w[i]; }
+        for (int i = 0; i < NW + 1; ++i) { RS.w[i] = R.w[i] & ~up.w[i]; RE.w[i] = R.w[i] & ~dn.w[i]; }
     }
     const uint32_t Bend = 32u + (uint32_t)wlen - (uint32_t)npend_out;  // one past the last complete char
     int32_t last_seg = -2;  // segment of the last yield (-1: the window's first segment)
@@ -343,7 +345,7 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
     if (m5_bit(pendm, 31)) {
         M5 lead;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) lead.w[i] = L2.w[i] | len34.w[i];
+        for (int i = 0; i < NW + 1; ++i) lead.w[i] = L2.w[i] | len34.w[i];
         pend0 = m5_bit(lead, 31) ? 1 : (m5_bit(lead, 30) ? 2 : 3);
     }
     // The Precision::Before probe (finding_collection.rs:176-207) can only change the precision of a finding of a
@@ -357,7 +359,7 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
     if (m5_bit(R, 32) && !m5_bit(pre, 32)) {
         const uint32_t e_last = m5_low_ge(RE, 32);
         const int32_t s0 = m5_high_le(RS, 32);
-        if (s0 < 29 || e_last >= 160) return false;
+        if (s0 < 29 || e_last >= 32 * (NW + 1)) return false;
         if (e_last + 1 >= Bend) return false;  // the run covers the whole window: carry-in dependent leftover / cut
         const uint32_t chars = m5_count(pe, 32, e_last) + k_in;
         if (chars >= q) return false;
@@ -382,10 +384,10 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
             if (s >= 32) {
                 const uint32_t ws_ = s >> 5, bs = s & 31;
 #pragma unroll
-                for (int i = 4; i >= 0; --i) {
+                for (int i = NW; i >= 0; --i) {
                     uint32_t lo = 0, hi = 0;
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) {
+                    for (int j = 0; j < NW + 1; ++j) {
                         if ((uint32_t)j + ws_ == (uint32_t)i) hi = LR.w[j];
                         if ((uint32_t)j + ws_ + 1 == (uint32_t)i) lo = LR.w[j];
                     }
@@ -393,7 +395,7 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
                 }
             } else {
 #pragma unroll
-                for (int i = 4; i >= 1; --i) LR.w[i] &= sx_fsl(LR.w[i - 1], LR.w[i], s);
+                for (int i = NW; i >= 1; --i) LR.w[i] &= sx_fsl(LR.w[i - 1], LR.w[i], s);
                 LR.w[0] &= LR.w[0] << s;
             }
         };
@@ -406,11 +408,11 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
         if (n > have) and_shl(n - have);
         M5 cand;  // last bytes of the long runs
 #pragma unroll
-        for (int i = 0; i < 5; ++i) cand.w[i] = LR.w[i] & RE.w[i];
+        for (int i = 0; i < NW + 1; ++i) cand.w[i] = LR.w[i] & RE.w[i];
         int guard = 0;
         for (; guard < 12; ++guard) {
             const uint32_t e_last = m5_low_ge(cand, next_B);
-            if (e_last >= 160) break;
+            if (e_last >= 32 * (NW + 1)) break;
             next_B = e_last + 1;
             if (e_last + 1 >= Bend) break;  // the run touching the right boundary never prints here (leftover)
             const int32_t s = m5_high_le(RS, e_last);
@@ -447,6 +449,14 @@ SX_HD_NOINLINE bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, c
     res.m = 1;
     res.cut1 = 0;
     return true;
+}
+
+// Short windows (pre-roll, extension) only need two data words.
+template <class TileSrc>
+SX_HD bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode,
+                            Record* wr, uint64_t text_off, WinResult& res) {
+    if (geo.we - geo.ws <= 64) return utf8_mask_window_nw<2>(P, tsrc, geo, kin, mode, wr, text_off, res);
+    return utf8_mask_window_nw<4>(P, tsrc, geo, kin, mode, wr, text_off, res);
 }
 
 // Engine dispatch used by the kernels and the test harness: UTF-8 tries the mask engine, then the convergent

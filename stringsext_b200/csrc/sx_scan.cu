@@ -696,6 +696,11 @@ struct sx_scanner_state {
     uint32_t* d_list = nullptr; size_t list_cap = 0;
     int use_prefilter = 1;
     int use_tma = 1;
+    int use_sparse = 1;
+    uint8_t* d_entries = nullptr; size_t entries_cap = 0;   // sparse pipeline: per-entry state
+    uint8_t* d_btot = nullptr; size_t btot_cap = 0;
+    uint8_t* d_tables = nullptr; size_t tables_cap = 0;
+    uint8_t* d_queue = nullptr; size_t queue_cap = 0;
     uint32_t last_ncta = 0; size_t last_region_stride = 0;
     // pinned host staging for result downloads
     Record* h_recs = nullptr; size_t h_recs_cap = 0;
@@ -782,6 +787,7 @@ void sx_scanner_state_free(sx_scanner_state* ss) {
     cudaSetDevice(ss->device);
     cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_blocks); cudaFree(ss->d_ccount); cudaFree(ss->d_coff); cudaFree(ss->d_list);
     cudaFree(ss->d_counters); cudaFree(ss->d_final);
+    cudaFree(ss->d_entries); cudaFree(ss->d_btot); cudaFree(ss->d_tables); cudaFree(ss->d_queue);
     cudaFreeHost(ss->h_recs); cudaFreeHost(ss->h_text); cudaFreeHost(ss->h_blocks);
     for (auto e : ss->ev) if (e) cudaEventDestroy(e);
     delete ss;
@@ -803,6 +809,7 @@ size_t sx_scanner_state_leftover(const sx_scanner_state* ss, const uint8_t** p) 
 void sx_scanner_state_last_stats(const sx_scanner_state* ss, sx_scan_stats* out) { *out = ss->stats; }
 void sx_scanner_state_set_prefilter(sx_scanner_state* ss, int enabled) { ss->use_prefilter = enabled ? 1 : 0; }
 void sx_scanner_state_set_tma(sx_scanner_state* ss, int enabled) { ss->use_tma = enabled ? 1 : 0; }
+void sx_scanner_state_set_sparse(sx_scanner_state* ss, int enabled) { ss->use_sparse = enabled ? 1 : 0; }
 size_t sx_scanner_state_last_window_list(const sx_scanner_state* ss, uint32_t* out, size_t cap) {
     if (!ss->stats.prefilter_used) return 0;
     const size_t n = (size_t)ss->stats.windows_listed;
@@ -1067,10 +1074,32 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             X.ncta = 0;
             X.region_stride = 0;
         }
-        const unsigned xgrid = (unsigned)std::min<long long>(max_blocks, (long long)ss->num_sms * 4);
-        CK(launch_exact_enc(P, O, X, xgrid, st));
+        // A sparse list of a UTF-8 mission takes the barrier-free pipeline (sx_sparse_utf8.cuh); it needs the entry
+        // count on the host (one small round trip), everything else the block kernel with its run classification.
+        bool sparse = false;
+        if (pc.enabled && ss->use_sparse && P.enc == ENC_UTF8 && !P.general) {
+            unsigned long long ne = 0;
+            CK(cudaMemcpyAsync(&ne, ss->d_counters + 2, sizeof ne, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ss->stats.d2h_bytes += sizeof ne;
+            if (ne > 0 && ne * 8ull <= (unsigned long long)total_windows) {
+                const size_t nb = (size_t)((ne + sparse_threads() - 1) / sparse_threads());
+                if (!grow(&ss->d_entries, &ss->entries_cap, (size_t)ne * sparse_entry_bytes())) return fail;
+                if (!grow(&ss->d_btot, &ss->btot_cap, (nb + 1) * sizeof(ulonglong2))) return fail;
+                if (!grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes())) return fail;
+                if (!grow(&ss->d_queue, &ss->queue_cap, ((size_t)ne + 64) * sizeof(uint32_t))) return fail;
+                CK(launch_sparse_utf8(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st));
+                ss->stats.kernel_launches += sparse_launches();
+                sparse = true;
+            }
+        }
+        ss->stats.sparse_used = sparse ? 1u : 0u;
+        if (!sparse) {
+            const unsigned xgrid = (unsigned)std::min<long long>(max_blocks, (long long)ss->num_sms * 4);
+            CK(launch_exact_enc(P, O, X, xgrid, st));
+            ss->stats.kernel_launches++;
+        }
         CK(cudaEventRecord(ss->ev[1], st));
-        ss->stats.kernel_launches++;
         ss->stats.host_phase_ms[0] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         CK(cudaMemcpyAsync(counters, ss->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&fin, ss->d_final, sizeof fin, cudaMemcpyDeviceToHost, st));
@@ -1109,7 +1138,8 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     ss->stats.text_bytes = ntext;
 
     // ---- text + download ---------------------------------------------------------------------------
-    const size_t nblocks = (size_t)((counters[2] + kThreads - 1) / kThreads);
+    const bool sparse_out = ss->stats.sparse_used != 0;  // records already in stream order: one descriptor
+    const size_t nblocks = sparse_out ? 1 : (size_t)((counters[2] + kThreads - 1) / kThreads);
     if (!grow_pinned(&ss->h_recs, &ss->h_recs_cap, nrec + 1)) return fail;
     if (!grow_pinned(&ss->h_text, &ss->h_text_cap, ntext + 1)) return fail;
     if (!grow_pinned(&ss->h_blocks, &ss->h_blocks_cap, nblocks + 1)) return fail;
@@ -1125,8 +1155,9 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ss->stats.kernel_launches++;
         CK(cudaMemcpyAsync(ss->h_recs, ss->d_recs, nrec * sizeof(Record), cudaMemcpyDeviceToHost, st));
         if (ntext) CK(cudaMemcpyAsync(ss->h_text, ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ss->h_blocks, ss->d_blocks, nblocks * sizeof(uint2), cudaMemcpyDeviceToHost, st));
-        ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + nblocks * sizeof(uint2);
+        if (sparse_out) ss->h_blocks[0] = make_uint2(0u, (unsigned)nrec);
+        else CK(cudaMemcpyAsync(ss->h_blocks, ss->d_blocks, nblocks * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+        ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + (sparse_out ? 0 : nblocks * sizeof(uint2));
     }
     // bytes that stay inside the decoder: the last npend bytes of (old pend ++ buffer)
     uint8_t tail[8] = {0};
@@ -1162,11 +1193,13 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         sx_finding* const out = fc->v.data();
         const int16_t fid = (int16_t)input_file_id;
         const uint8_t mid = ss->m.mission_id;
-        auto fill = [&](size_t t0, size_t t1) {
+        // [t0, t1): descriptors; with a single descriptor (records already in order) [k0, k1) is the record range
+        auto fill = [&](size_t t0, size_t t1, size_t k0 = 0, size_t k1 = ~(size_t)0) {
             for (size_t t = t0; t < t1; ++t) {
-                const Record* r = recs + tiles[t].x;
-                size_t o = out_off[t];
-                for (size_t k = 0; k < tiles[t].y; ++k, ++r, ++o) {
+                const size_t kb = std::min<size_t>(k0, tiles[t].y), ke = std::min<size_t>(k1, tiles[t].y);
+                const Record* r = recs + tiles[t].x + kb;
+                size_t o = out_off[t] + kb;
+                for (size_t k = kb; k < ke; ++k, ++r, ++o) {
                     if (o >= n_out) break;  // the trailing leftover pseudo record
                     sx_finding f;
                     f.position = r->position;
@@ -1192,7 +1225,8 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
                 th.emplace_back([&, k]() {
                     const size_t a0 = ntext * k / nthreads, a1 = ntext * (k + 1) / nthreads;
                     if (a1 > a0) memcpy(tbase + a0, text + a0, a1 - a0);
-                    fill(nblocks * k / nthreads, nblocks * (k + 1) / nthreads);
+                    if (nblocks == 1) fill(0, 1, acc * k / nthreads, acc * (k + 1) / nthreads);
+                    else fill(nblocks * k / nthreads, nblocks * (k + 1) / nthreads);
                 });
             for (auto& t : th) t.join();
         }

@@ -79,6 +79,8 @@ class ScanStats(C.Structure):
         ("relaunches", C.c_uint32),
         ("prefilter_used", C.c_uint32),
         ("tma_used", C.c_uint32),
+        ("sparse_used", C.c_uint32),
+        ("reserved0", C.c_uint32),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
         ("n_records", C.c_uint64),
@@ -116,6 +118,7 @@ def load_library():
     L.sx_scanner_state_last_stats.argtypes = [C.c_void_p, C.POINTER(ScanStats)]
     L.sx_scanner_state_set_prefilter.argtypes = [C.c_void_p, C.c_int]
     L.sx_scanner_state_set_tma.argtypes = [C.c_void_p, C.c_int]
+    L.sx_scanner_state_set_sparse.argtypes = [C.c_void_p, C.c_int]
     L.sx_scanner_state_last_window_list.restype = C.c_size_t
     L.sx_scanner_state_last_window_list.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_size_t]
     L.sx_finding_collection_from.restype = C.c_void_p
@@ -156,7 +159,7 @@ def exported_symbols() -> List[str]:
         "sx_device_count", "sx_scanner_state_new", "sx_scanner_state_free", "sx_scanner_state_reset", "sx_scanner_state_consumed_bytes",
         "sx_scanner_state_maybe_cut", "sx_scanner_state_leftover", "sx_finding_collection_from", "sx_scan_stream",
         "sx_fc_len", "sx_fc_get", "sx_fc_data", "sx_fc_first_byte_position", "sx_fc_str_buf_overflow", "sx_fc_free",
-        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
+        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_set_sparse", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
     ]
 
 
@@ -264,6 +267,10 @@ class ScannerState:
 
     def set_tma(self, enabled: bool) -> None:
         load_library().sx_scanner_state_set_tma(self._h, 1 if enabled else 0)
+
+    def set_sparse(self, enabled: bool) -> None:
+        """False: the exact stage always runs as the block kernel (sx_exact_kernel), never as the sparse-list pipeline."""
+        load_library().sx_scanner_state_set_sparse(self._h, 1 if enabled else 0)
 
     def last_window_list(self) -> List[int]:
         L = load_library()

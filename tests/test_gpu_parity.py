@@ -252,3 +252,41 @@ def test_prefilter_on_off_identical(enc):
         assert ra == rb
         assert a.last_scan_run_leftover == b.last_scan_run_leftover
         assert a.last_run_str_was_printed_and_is_maybe_cut_str == b.last_run_str_was_printed_and_is_maybe_cut_str
+
+
+@pytest.mark.parametrize("n,q,ubf,kind", [(10, 64, None, "rand"), (6, 64, None, "rand"), (4, 64, M.UBF_ALL_VALID, "rand"),
+                                         (10, 64, M.UBF_ALL_VALID, "mixed"), (3, 16, None, "rand"), (8, 8, M.UBF_AFRICAN, "text"),
+                                         (2, 64, None, "rand"), (16, 32, M.UBF_ALL, "runs")])
+def test_sparse_pipeline_matches_block_kernel_and_oracle(n, q, ubf, kind):
+    """UTF-8: the barrier-free sparse-list pipeline (mask engine) == the block kernel == the oracle, incl. chained calls."""
+    m = M.Mission.for_label("utf-8", n, ubf=ubf, output_line_char_nb_max=q)
+    rng = random.Random(4242 + n + q)
+    size = (3 << 20) + 4096 * 3 + 17
+    if kind == "rand":
+        buf = corpus.sx_mix_bytes(11, 0, size)
+        corpus.plant(buf, 11, 1, n, q, density=1 << 13)
+        buf = buf.tobytes()
+    else:
+        # mostly binary with embedded text, so the list stays sparse
+        parts, total = [], 0
+        while total < size:
+            ln = rng.randrange(2000, 60000)
+            parts.append(corpus.sx_mix_bytes(rng.randrange(1 << 30), 0, ln).tobytes())
+            parts.append(corpus.gen(rng, kind, rng.randrange(1, 600), 1))
+            total += ln + len(parts[-1])
+        buf = b"".join(parts)[:size]
+    a, b, os_ = sx.ScannerState(m), sx.ScannerState(m), oracle_state(m)
+    b.set_sparse(False)
+    cuts = [0, 4096 * 100 + 5, 4096 * 300 + 5, len(buf)]
+    used = 0
+    for lo, hi in zip(cuts, cuts[1:]):
+        last = hi == len(buf) and n == 6
+        ra = gpu_findings(a.scan_stream(buf[lo:hi], last, 4096))
+        rb = gpu_findings(b.scan_stream(buf[lo:hi], last, 4096))
+        exp = oracle_findings(os_.scan_stream(buf[lo:hi], last, 4096))
+        used += a.last_stats.sparse_used
+        assert b.last_stats.sparse_used == 0
+        assert ra == exp and rb == exp
+        check_state(a, os_)
+        check_state(b, os_)
+    assert used >= 1 or kind != "rand" or n <= 6  # short minimum lengths list too many windows for the sparse path
