@@ -139,6 +139,7 @@ struct WinDesc {
 };
 
 struct WinResult {
+    Carry in;           // mask engine: the carry-in it worked under (given, or derived from the 32 bytes before the window)
     Carry out;
     uint32_t nrec;
     uint32_t ntext;

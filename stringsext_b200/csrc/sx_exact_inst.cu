@@ -43,6 +43,8 @@ cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const Exac
     B.tables = static_cast<Utf8Tables*>(tables);
     B.queue = static_cast<uint32_t*>(queue);
     B.qcount = O.counters + 3;  // the block kernel's claim counter, unused on this path (zeroed per attempt)
+    B.queue2 = B.queue + NE + 32;
+    B.qcount2 = O.counters + 4;
     B.NE = NE;
     return launch_sparse_utf8_impl(P, O, X, B, num_sms, st);
 }

@@ -128,24 +128,55 @@ template <int NW> SX_HD uint32_t m5_count(const MK<NW>& a, uint32_t A, uint32_t 
     return n;
 }
 
+// index of the j-th (j >= 1) set bit at index >= B; the caller guarantees it exists
+template <int NW> SX_HD uint32_t m5_select(const MK<NW>& a, uint32_t B, uint32_t j) {
+    uint32_t r = 32 * (NW + 1);
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < NW + 1; ++i) {
+        uint32_t v = a.w[i];
+        const uint32_t lo = (uint32_t)i * 32u;
+        if (B >= lo + 32u) v = 0;
+        else if (B > lo) v &= ~((1u << (B - lo)) - 1u);
+        const uint32_t c = sx_popc(v);
+        if (!found) {
+            if (j <= c) {
+#if defined(__CUDA_ARCH__)
+                r = lo + __fns(v, 0, (int)j);
+#else
+                uint32_t t = v;
+                for (uint32_t k = 1; k < j; ++k) t &= t - 1;
+                r = lo + sx_ctz(t);
+#endif
+                found = true;
+            } else j -= c;
+        }
+    }
+    return r;
+}
+
 // The five class planes of a window.  TileSrc: load_chunk(r16, ws, we) (16 bytes, zero outside [ws, we)),
 // cls(b) (table lookup), get(off).
-template <int NW, class TileSrc>
+// LB32: word 0 holds all 32 bytes before the window (requires ws >= 32), otherwise only the last three.
+template <int NW, bool LB32, class TileSrc>
 SX_HD void utf8_class_planes(const ScanParams& P, const TileSrc& tsrc, int64_t ws, int64_t we, MK<NW>* pl) {
 #pragma unroll
     for (int t = 0; t < 5; ++t) pl[t].w[0] = 0;
-    // look-back: the three bytes before the window (bytes before the stream start leave the decoder neutral)
+    if (!LB32) {
+        // look-back: the three bytes before the window (bytes before the stream start leave the decoder neutral)
 #pragma unroll
-    for (int j = 1; j <= 3; ++j) {
-        const int64_t o = ws - j;
-        if (o >= -(int64_t)P.npend) {
-            const uint32_t c = tsrc.cls(tsrc.get(o));
+        for (int j = 1; j <= 3; ++j) {
+            const int64_t o = ws - j;
+            if (o >= -(int64_t)P.npend) {
+                const uint32_t c = tsrc.cls(tsrc.get(o));
 #pragma unroll
-            for (int t = 0; t < 5; ++t) pl[t].w[0] |= ((c >> t) & 1u) << (32 - j);
+                for (int t = 0; t < 5; ++t) pl[t].w[0] |= ((c >> t) & 1u) << (32 - j);
+            }
         }
     }
+    const int64_t lo_bound = LB32 ? ws - 32 : ws;
 #pragma unroll
-    for (int grp = 0; grp < NW; ++grp) {
+    for (int grp = LB32 ? -1 : 0; grp < NW; ++grp) {
 #if defined(__CUDA_ARCH__)
         uint32_t acc[5][4];
 #pragma unroll
@@ -154,7 +185,7 @@ SX_HD void utf8_class_planes(const ScanParams& P, const TileSrc& tsrc, int64_t w
         for (int h = 0; h < 2; ++h) {
             const int64_t r16 = ws + (int64_t)(grp * 32 + h * 16);
             if (r16 < we) {
-                const uint4 v = tsrc.load_chunk(r16, ws, we);
+                const uint4 v = tsrc.load_chunk(r16, lo_bound, we);
                 const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -216,20 +247,25 @@ SX_HD void mask_emit(MaskEmit& E, int32_t seg_rel, uint32_t prec, int32_t run_s,
 
 // Returns false when the window needs the byte-wise engine (nothing has been written in that case that the
 // byte-wise engine would not overwrite).
-template <int NW, class TileSrc>
-SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode,
+// LB32: the carry-in is NOT given but derived from the 32 bytes before the window (the pre-roll of a head folded into
+// the same pass): valid when the caller knows that the run touching the window's left boundary is shorter than 28
+// bytes (the predecessor window is unlisted and pre_bytes <= 28); `kin_arg` is ignored, res.in tells what was derived.
+template <int NW, bool LB32, class TileSrc>
+SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin_arg, int mode,
                             Record* wr, uint64_t text_off, WinResult& res) {
     const int64_t ws = geo.ws, we = geo.we;
     const int32_t wlen = (int32_t)(we - ws);
     const uint32_t n = P.n, q = P.q;
     if (wlen < 4 || wlen > 32 * NW || (ws & 15) != 0 || geo.final_last) return false;
+    if (LB32 && ws < 32) return false;
+    Carry kin = LB32 ? carry_none() : kin_arg;
     if (kin.kind == K_UNKNOWN) return false;
-    const bool kc = kin.kind == K_C;              // the first run completes a cut finding whatever its length
-    const uint32_t k_in = kc ? 0u : kin.k;        // chars of the leftover the first run continues
+    bool kc = kin.kind == K_C;              // the first run completes a cut finding whatever its length
+    uint32_t k_in = kc ? 0u : kin.k;        // chars of the leftover the first run continues
 
     using M5 = MK<NW>;
     M5 pl[5];
-    utf8_class_planes<NW>(P, tsrc, ws, we, pl);
+    utf8_class_planes<NW, LB32>(P, tsrc, ws, we, pl);
     // positions >= wlen: class 0 (ASCII), verdict 0 (zero fill read through the table may say otherwise)
     M5 V;  // valid window positions
     V.w[0] = 0;
@@ -305,16 +341,45 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
 #pragma unroll
         for (int i = 0; i < NW + 1; ++i) {
             const uint32_t a = ~(pl[0].w[i] | pl[1].w[i] | pl[2].w[i] | pl[3].w[i]);  // class 0
-            p1.w[i] = a & PS.w[i] & V.w[i];
-            p2.w[i] = ok1.w[i] & s1L2.w[i] & s1ps.w[i] & V.w[i];
-            p3.w[i] = ok2.w[i] & s2l34.w[i] & ~s2l4.w[i] & s2ps.w[i] & V.w[i];
-            p4.w[i] = ok3.w[i] & s3ps.w[i] & V.w[i];
+            const uint32_t pv = (LB32 && i == 0) ? 0xFFFFFFFFu : V.w[i];  // LB32: the chars before the window count too
+            p1.w[i] = a & PS.w[i] & pv;
+            p2.w[i] = ok1.w[i] & s1L2.w[i] & s1ps.w[i] & pv;
+            p3.w[i] = ok2.w[i] & s2l34.w[i] & ~s2l4.w[i] & s2ps.w[i] & pv;
+            p4.w[i] = ok3.w[i] & s3ps.w[i] & pv;
             pe.w[i] = p1.w[i] | p2.w[i] | p3.w[i] | p4.w[i];
         }
         const M5 r2 = m5_shr<1>(p2), r3a = m5_shr<1>(p3), r3b = m5_shr<2>(p3), r4a = m5_shr<1>(p4), r4b = m5_shr<2>(p4), r4c = m5_shr<3>(p4);
 #pragma unroll
         for (int i = 0; i < NW + 1; ++i) R.w[i] = pe.w[i] | r2.w[i] | r3a.w[i] | r3b.w[i] | r4a.w[i] | r4b.w[i] | r4c.w[i];
     }
+    // bytes inside the decoder at the window start (the straddling char, if any, starts there)
+    int32_t pend0 = 0;
+    if (m5_bit(pendm, 31)) {
+        M5 lead;
+#pragma unroll
+        for (int i = 0; i < NW + 1; ++i) lead.w[i] = L2.w[i] | len34.w[i];
+        pend0 = m5_bit(lead, 31) ? 1 : (m5_bit(lead, 30) ? 2 : 3);
+    }
+    if (LB32) {
+        // the carry-in: the run of complete passing chars that ends where the pending bytes (if any) begin
+        const uint32_t lastB = 31u - (uint32_t)pend0;
+        if ((R.w[0] >> lastB) & 1u) {
+            const uint32_t inv = ~(R.w[0] << (31u - lastB));
+            const uint32_t len = inv ? sx_clz(inv) : 32u;
+            if (len > lastB + 1u - 4u) return false;  // reaches the first bytes of the frame: the pre-roll must decide
+            const uint32_t ls = lastB + 1u - len;
+            const uint32_t k = sx_popc(pe.w[0] & (((1u << len) - 1u) << ls));
+            if (k == 0) return false;
+            kin.kind = K_L; kin.flags = 0; kin.k = (uint16_t)k;
+            kin.in_bytes = 32u - ls;
+            kin.out_bytes = lastB + 1u - ls;
+            kin.aux = 0;
+            k_in = k;
+        }
+        pe.w[0] = 0;
+        R.w[0] &= pend0 ? (0xFFFFFFFFu << (32 - pend0)) : 0u;  // only the straddling char's bytes belong to the window's run
+    }
+    res.in = kin;
     // bytes still inside the decoder at the window end
     const uint32_t Blast = 31u + (uint32_t)wlen;
     int32_t npend_out = 0;
@@ -340,19 +405,82 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
     int32_t last_seg = -2;  // segment of the last yield (-1: the window's first segment)
     uint32_t next_B = 32;   // runs starting below this index are done
 
-    // bytes inside the decoder at the window start (the straddling char, if any, starts there)
-    int32_t pend0 = 0;
-    if (m5_bit(pendm, 31)) {
-        M5 lead;
-#pragma unroll
-        for (int i = 0; i < NW + 1; ++i) lead.w[i] = L2.w[i] | len34.w[i];
-        pend0 = m5_bit(lead, 31) ? 1 : (m5_bit(lead, 30) ? 2 : 3);
-    }
     // The Precision::Before probe (finding_collection.rs:176-207) can only change the precision of a finding of a
     // segment that starts at the slice start; with no leftover and a neutral decoder it changes nothing.
     const bool probe_seg1 = at_slice_start && mode != MODE_STATE && k_in == 0 && pend0 > 0;
     const bool probe_seg0 = at_slice_start && mode != MODE_STATE && k_in > 0;  // second segment at the slice start
     const uint32_t lo_flags = (k_in > 0 && (kin.flags & CF_HOSTCARRY)) ? (uint32_t)RF_HOSTCARRY : 0u;
+
+    // One run of passing chars [sB, eB] (bit indices of its first / last byte).  is_left: it continues whatever touches
+    // the window's left boundary (leftover of k_in chars, or a cut finding).  touches_end: its last char is the last
+    // complete char of the window.  Restates helper.rs:237-431 for the run: forced cut every q chars (the piece after
+    // a cut always "completes"), min-length rule otherwise; at the window end the rest is kept as leftover unless it
+    // completes a cut finding (finding_collection.rs:255-290).  Returns false to decline.
+    res.out = carry_none();
+    res.cut1 = 0;  // here: 1 when the carry-out depends on the carry-in (see below)
+    bool carry_done = false;
+    auto do_run = [&](int32_t sB, uint32_t eB, bool is_left, bool touches_end) -> bool {
+        const uint32_t fromB = sB < 32 ? 32u : (uint32_t)sB;  // chars are counted at their last byte
+        const uint32_t k0 = is_left ? k_in : 0u;
+        const uint32_t inwin = m5_count(pe, fromB, eB);
+        const uint32_t total = inwin + k0;
+        const bool lastcut0 = is_left && kc;
+        int32_t seg_id = -1;
+        if (!is_left) {
+            const int32_t sg = m5_high_le(seg, (uint32_t)sB);  // segment start at or before the run
+            seg_id = sg < 32 ? -1 : sg - 32;
+        }
+        const int32_t start_rel = (k0 > 0) ? -(int32_t)kin.in_bytes : sB - 32;
+        const uint32_t fl0 = (is_left ? lo_flags : 0u) | (lastcut0 ? (uint32_t)RF_COMPLETES : 0u);
+        const bool yields = total >= q || (touches_end ? lastcut0 : (lastcut0 || total >= n));
+        if (yields && ((seg_id == 0 && probe_seg0) || (seg_id < 0 && probe_seg1))) return false;
+        uint32_t prec = (seg_id == last_seg) ? PREC_AFTER : ((seg_id < 0 && k_in > 0) ? PREC_BEFORE : PREC_EXACT);
+        const int32_t seg_rel = seg_id < 0 ? 0 : seg_id;
+        if (yields) last_seg = seg_id;
+        if (total < q) {
+            if (touches_end) {
+                carry_done = true;
+                if (lastcut0) {  // completes the cut finding and may be cut again at the window end
+                    mask_emit(E, seg_rel, prec, start_rel, (int32_t)eB + 1 - 32, fl0);
+                    res.out = carry_cut();
+                } else {         // kept as leftover
+                    Carry c;
+                    c.kind = K_L; c.flags = (uint8_t)((is_left && k0 > 0 && (kin.flags & CF_HOSTCARRY)) ? CF_HOSTCARRY : 0);
+                    c.k = (uint16_t)total;
+                    c.in_bytes = (uint32_t)(wlen - start_rel);
+                    c.out_bytes = (uint32_t)((int32_t)Bend - 32 - start_rel);
+                    c.aux = 0;
+                    res.out = c;
+                }
+            } else if (yields) mask_emit(E, seg_rel, prec, start_rel, (int32_t)eB + 1 - 32, fl0);
+            return true;
+        }
+        // forced cuts every q chars
+        uint32_t need = q - k0, remaining = inwin, posB = fromB, flp = fl0;
+        int32_t piece_s = start_rel;
+        int pieces = 0;
+        while (remaining >= need) {
+            const uint32_t endB = m5_select(pe, posB, need);
+            mask_emit(E, seg_rel, prec, piece_s, (int32_t)endB + 1 - 32, flp);
+            prec = PREC_AFTER;
+            flp = RF_COMPLETES;
+            remaining -= need;
+            need = q;
+            posB = endB + 1;
+            piece_s = (int32_t)endB + 1 - 32;
+            if (++pieces > 24) return false;
+        }
+        if (remaining == 0) {
+            // the run ends exactly at a cut: the "maybe cut" flag outlives it (until the next segment / the window end)
+            if (!touches_end) return false;
+            carry_done = true;
+            res.out = carry_cut();
+        } else {
+            mask_emit(E, seg_rel, prec, piece_s, (int32_t)eB + 1 - 32, RF_COMPLETES);
+            if (touches_end) { carry_done = true; res.out = carry_cut(); }
+        }
+        return true;
+    };
 
     // ---- the run touching the left boundary: continues the leftover / completes the cut finding unless a pending
     //      sequence breaks first (then the leftover ends at that break, helper.rs:315-322) -----------------------------
@@ -360,23 +488,19 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
         const uint32_t e_last = m5_low_ge(RE, 32);
         const int32_t s0 = m5_high_le(RS, 32);
         if (s0 < 29 || e_last >= 32 * (NW + 1)) return false;
-        if (e_last + 1 >= Bend) return false;  // the run covers the whole window: carry-in dependent leftover / cut
-        const uint32_t chars = m5_count(pe, 32, e_last) + k_in;
-        if (chars >= q) return false;
-        if (kc || chars >= n) {
-            if (probe_seg1) return false;
-            mask_emit(E, 0, k_in > 0 ? PREC_BEFORE : PREC_EXACT, k_in > 0 ? -(int32_t)kin.in_bytes : s0 - 32,
-                      (int32_t)e_last + 1 - 32, lo_flags | (kc ? (uint32_t)RF_COMPLETES : 0u));
-            last_seg = -1;
-        }
+        if (!do_run(s0, e_last, true, e_last + 1 >= Bend)) return false;
         next_B = e_last + 1;
+        // The carry-in only acts through this run (its char count decides where the forced cuts fall and whether a
+        // "maybe cut" flag outlives it).  A run that covers the window and holds >= q chars by itself always ends
+        // in a cut at the window end; in every other case the carry-out may depend on the carry-in.
+        res.cut1 = (e_last + 1 >= Bend && m5_count(pe, 32, e_last) >= q) ? 0u : 1u;
     } else if (k_in >= n) {
         // the leftover alone is long enough: printed at the first event of the window
         mask_emit(E, 0, PREC_BEFORE, -(int32_t)kin.in_bytes, -pend0, lo_flags);
         last_seg = -1;
     }
     // ---- runs of >= n bytes inside the window ------------------------------------------------------------------------
-    {
+    if (!carry_done) {
         // LR: last bytes of runs holding at least n bytes (n <= 128): AND of R shifted by 0 .. n-1
         M5 LR = R;
         uint32_t have = 1;
@@ -414,40 +538,23 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
             const uint32_t e_last = m5_low_ge(cand, next_B);
             if (e_last >= 32 * (NW + 1)) break;
             next_B = e_last + 1;
-            if (e_last + 1 >= Bend) break;  // the run touching the right boundary never prints here (leftover)
             const int32_t s = m5_high_le(RS, e_last);
             if (s < 32) return false;
-            const uint32_t chars = m5_count(pe, (uint32_t)s, e_last);
-            if (chars >= q) return false;
-            if (chars < n) continue;
-            const int32_t sg = m5_high_le(seg, (uint32_t)s);  // segment start at or before the run
-            const int32_t seg_id = sg < 32 ? -1 : sg - 32;
-            if ((seg_id == 0 && probe_seg0) || (seg_id < 0 && probe_seg1)) return false;
-            const uint32_t prec = (seg_id == last_seg) ? PREC_AFTER : ((seg_id < 0 && k_in > 0) ? PREC_BEFORE : PREC_EXACT);
-            mask_emit(E, seg_id < 0 ? 0 : seg_id, prec, s - 32, (int32_t)e_last + 1 - 32, 0u);
-            last_seg = seg_id;
+            if (!do_run(s, e_last, false, e_last + 1 >= Bend)) return false;
+            if (carry_done) break;
         }
         if (guard == 12) return false;  // a window crowded with short findings: byte-wise engine
     }
-    // ---- carry out: the run of complete chars touching the window end (finding_collection.rs:281-284) -------------
-    res.out = carry_none();
-    if (Bend > 32 && m5_bit(R, Bend - 1)) {
+    // ---- carry out: a short run of complete chars touching the window end (finding_collection.rs:281-284) ---------
+    if (!carry_done && Bend > 32 && m5_bit(R, Bend - 1)) {
         const int32_t ts = m5_high_le(RS, Bend - 1);
-        if (ts <= 32) return false;
-        const uint32_t chars = m5_count(pe, (uint32_t)ts, Bend - 1);
-        if (chars >= q || chars == 0) return false;
-        Carry c;
-        c.kind = K_L; c.flags = 0; c.k = (uint16_t)chars;
-        c.in_bytes = 32u + (uint32_t)wlen - (uint32_t)ts;
-        c.out_bytes = Bend - (uint32_t)ts;
-        c.aux = 0;
-        res.out = c;
+        if (ts < 32) return false;
+        if (!do_run(ts, Bend - 1, false, true)) return false;
     }
     res.nrec = E.nrec;
     res.ntext = E.ntext;
     res.npend_out = npend_out;
     res.m = 1;
-    res.cut1 = 0;
     return true;
 }
 
@@ -455,8 +562,16 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
 template <class TileSrc>
 SX_HD bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode,
                             Record* wr, uint64_t text_off, WinResult& res) {
-    if (geo.we - geo.ws <= 64) return utf8_mask_window_nw<2>(P, tsrc, geo, kin, mode, wr, text_off, res);
-    return utf8_mask_window_nw<4>(P, tsrc, geo, kin, mode, wr, text_off, res);
+    if (geo.we - geo.ws <= 64) return utf8_mask_window_nw<2, false>(P, tsrc, geo, kin, mode, wr, text_off, res);
+    return utf8_mask_window_nw<4, false>(P, tsrc, geo, kin, mode, wr, text_off, res);
+}
+// A head (predecessor window not listed) in ONE pass: the pre-roll region is the 32 bytes in front of the window.
+constexpr uint32_t kMaskLb32MaxPre = 28;
+template <class TileSrc>
+SX_HD bool utf8_mask_head(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, uint32_t pre_bytes, int mode, Record* wr,
+                          uint64_t text_off, WinResult& res) {
+    if (pre_bytes > kMaskLb32MaxPre || geo.ws < 32 || geo.we - geo.ws <= 64) return false;
+    return utf8_mask_window_nw<4, true>(P, tsrc, geo, carry_none(), mode, wr, text_off, res);
 }
 
 // Engine dispatch used by the kernels and the test harness: UTF-8 tries the mask engine, then the convergent

@@ -775,7 +775,7 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
     cudaDeviceProp prop;
     if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete ss; return fail; }
     ss->num_sms = prop.multiProcessorCount;
-    bool ok = cuda_ok(cudaMalloc(&ss->d_counters, 4 * sizeof(unsigned long long)), "cudaMalloc") &&
+    bool ok = cuda_ok(cudaMalloc(&ss->d_counters, 8 * sizeof(unsigned long long)), "cudaMalloc") &&
               cuda_ok(cudaMalloc(&ss->d_final, sizeof(FinalState)), "cudaMalloc");
     for (int i = 0; ok && i < 6; ++i) ok = cuda_ok(cudaEventCreate(&ss->ev[i]), "cudaEventCreate");
     if (!ok) { sx_scanner_state_free(ss); return fail; }
@@ -1033,7 +1033,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     for (int attempt = 0;; ++attempt) {
         if (!grow(&ss->d_recs, &ss->rec_cap, need_recs)) return fail;
         if (!grow(&ss->d_text, &ss->text_cap, need_text)) return fail;
-        CK(cudaMemsetAsync(ss->d_counters, 0, 4 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ss->d_counters, 0, 8 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(ss->d_final, 0, sizeof(FinalState), st));
         ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final};
         ExactCfg X;
@@ -1087,7 +1087,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
                 if (!grow(&ss->d_entries, &ss->entries_cap, (size_t)ne * sparse_entry_bytes())) return fail;
                 if (!grow(&ss->d_btot, &ss->btot_cap, (nb + 1) * sizeof(ulonglong2))) return fail;
                 if (!grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes())) return fail;
-                if (!grow(&ss->d_queue, &ss->queue_cap, ((size_t)ne + 64) * sizeof(uint32_t))) return fail;
+                if (!grow(&ss->d_queue, &ss->queue_cap, (2 * (size_t)ne + 128) * sizeof(uint32_t))) return fail;
                 CK(launch_sparse_utf8(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st));
                 ss->stats.kernel_launches += sparse_launches();
                 sparse = true;

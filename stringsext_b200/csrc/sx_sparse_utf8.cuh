@@ -6,11 +6,13 @@
 // of single warps (ncu: barrier stalls, profiles/).  Here every stage is its own data-parallel kernel -- one
 // thread per list entry, no barrier on the data path -- and the per-entry results live in a device array:
 //
-//   sx_sp_heads_kernel   entries whose predecessor window is not listed: carry-in from the pre-roll, then ONE pass
-//                        of the mask engine (sx_mask_utf8.cuh) -> carry-out, counts, first records
-//   sx_sp_chains_kernel  runs of adjacent windows, walked in order by the thread of their first member under the
-//                        real carries (mask engine, byte-wise engine when it declines); also heads the mask
-//                        engine declined
+//   sx_sp_queue_kernel   queues the members of runs of adjacent windows (entries whose predecessor window is listed)
+//   sx_sp_heads_kernel   entries whose predecessor window is not listed: carry-in from the pre-roll, then ONE pass of
+//                        the mask engine (sx_mask_utf8.cuh) -> carry-out, counts, first records
+//   sx_sp_members_kernel members, in parallel: carry-in = carry-out of the entry before, taken from a resolved head or
+//                        recomputed from that window alone when it does not depend on ITS carry-in
+//   sx_sp_fix_kernel     the rest, few: heads the mask engine declined (byte-wise engine), members behind a
+//                        carry-dependent window (walked in order)
 //   sx_sp_ext_kernel     extension windows (a "cut" / long leftover carry reaching an unlisted successor),
 //                        per-entry totals -> per-CTA totals
 //   sx_sp_scan_kernel    exclusive scan of the per-CTA totals
@@ -22,10 +24,12 @@
 #pragma once
 #include "sx_exact.cuh"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 namespace sx {
 
-enum : uint8_t { ES_PENDING = 0, ES_DONE = 1, ES_DECLINED = 2 };
+enum : uint8_t { ES_PENDING = 0, ES_DONE = 1, ES_DECLINED = 2 /* head */, ES_DEPENDENT = 3 /* member of a run */ };
 struct EntryState {
     Carry kin, kout;
     uint32_t cnt_r, cnt_t;    // records / text bytes of the window under its real carry
@@ -42,8 +46,10 @@ struct SparseBufs {
     EntryState* E;
     ulonglong2* btot;          // per-CTA {records, text bytes}: totals, then exclusive prefix
     Utf8Tables* tables;        // filled by sx_sp_tables_kernel
-    uint32_t* queue;           // work items of sx_sp_chains_kernel: first members of runs, declined lone heads (| kQueueHead)
+    uint32_t* queue;           // members of runs of adjacent windows (sx_sp_members_kernel)
     unsigned long long* qcount;
+    uint32_t* queue2;          // what is left for sx_sp_fix_kernel: declined heads, members with a carry-dependent predecessor
+    unsigned long long* qcount2;
     long long NE;
 };
 
@@ -75,7 +81,7 @@ __device__ __forceinline__ void sp_store(EntryState* es, const Carry& kin, const
     es->cnt_r = r.nrec;
     es->cnt_t = r.ntext;
     es->npend = (int8_t)r.npend_out;
-    es->status = ES_DONE;
+    if (es->status == ES_PENDING) es->status = ES_DONE;  // sx_sp_fix_kernel leaves DECLINED / DEPENDENT as they are
 }
 // a head (predecessor window not listed) with the byte-wise engine: pre-roll, then one pass under the real carry
 __device__ __noinline__ void sp_head_bytewise(const ScanParams& P, const ExactCfg& X, const SpCtx& c, long long w, EntryState* es) {
@@ -93,95 +99,150 @@ __device__ __noinline__ void sp_head_bytewise(const ScanParams& P, const ExactCf
     sp_store(es, kin0, r);
 }
 
-// warp-aggregated append to the chain queue
-__device__ __forceinline__ void sp_push(const SparseBufs& B, bool pred, uint32_t item) {
+// warp-aggregated append to a work queue
+__device__ __forceinline__ void sp_push(uint32_t* queue, unsigned long long* qcount, bool pred, uint32_t item) {
     const uint32_t m = __ballot_sync(__activemask(), pred);
     if (!pred) return;
     const uint32_t lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
     unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(B.qcount, (unsigned long long)__popc(m));
+    if ((int)lane == leader) base = atomicAdd(qcount, (unsigned long long)__popc(m));
     base = __shfl_sync(m, base, leader);
-    B.queue[base + __popc(m & ((1u << lane) - 1u))] = item;
+    queue[base + __popc(m & ((1u << lane) - 1u))] = item;
 }
 
-__global__ void __launch_bounds__(kSpThreads, 4)
+// Entry roles: a HEAD has no listed predecessor window (its carry-in comes from the pre-roll); a MEMBER continues a
+// run of adjacent windows (its carry-in is the carry-out of the entry before it).
+__global__ void __launch_bounds__(256)
+sx_sp_queue_kernel(const ExactCfg X, const SparseBufs B) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool member = false;
+    if (e < B.NE) {
+        const long long w = list_window(X, X.cta_off, e);
+        EntryState* const es = &B.E[e];
+        es->xcnt_r = 0;
+        es->xcnt_t = 0;
+        es->status = ES_PENDING;
+        member = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
+    }
+    sp_push(B.queue, B.qcount, member, (uint32_t)e);
+}
+
+// a head with the mask engine (pre-roll + one pass under the real carry); false when the engine declines
+__device__ __forceinline__ bool sp_head_mask(const ScanParams& P, const ExactCfg& X, const SpCtx& c, long long w, EntryState* es) {
+    WinGeom wg;
+    c.geo.window(w, wg);
+    WinResult r;
+    // one pass: the pre-roll region is the 32 bytes in front of the window (same class planes, same decoder algebra)
+    if (w != 0 && utf8_mask_head(P, c.ts, wg, X.pre_bytes, MODE_BUFFER, es->staged, 0, r)) {
+        sp_store(es, r.in, r);
+        return true;
+    }
+    Carry kin0 = P.k0;
+    if (w != 0) {
+        const WinGeom rg = preroll_geom(c.geo, w, X.pre_bytes);
+        WinResult rr;
+        if (!utf8_mask_window(P, c.ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr)) return false;
+        kin0 = rr.out;
+    }
+    if (!utf8_mask_window(P, c.ts, wg, kin0, MODE_BUFFER, es->staged, 0, r)) return false;
+    sp_store(es, kin0, r);
+    return true;
+}
+// a member under its real carry: mask engine, byte-wise engine when it declines
+__device__ __forceinline__ Carry sp_member(const ScanParams& P, const SpCtx& c, long long w, const Carry& kin, EntryState* es) {
+    WinGeom wg;
+    c.geo.window(w, wg);
+    WinResult r;
+    if (!utf8_mask_window(P, c.ts, wg, kin, MODE_BUFFER, es->staged, 0, r))
+        WindowEngine<DecUtf8>::run(P, c.ts, c.g, wg, kin, MODE_BUFFER, es->staged, 0, r, nullptr);
+    sp_store(es, kin, r);
+    return r.out;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kSpThreads, MINB)
 sx_sp_heads_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     SpCtx c;
     sp_setup(P, X, B, T, c);
     const long long e = (long long)blockIdx.x * kSpThreads + threadIdx.x;
-    const bool active = e < B.NE;
-    long long w = 0, wp = -2;
-    bool adj = false;
-    EntryState* es = nullptr;
-    if (active) {
-        w = list_window(X, X.cta_off, e);
-        wp = e > 0 ? list_window(X, X.cta_off, e - 1) : -2;
-        adj = wp == w - 1;
-        es = &B.E[e];
-        es->xcnt_r = 0;
-        es->xcnt_t = 0;
-        es->status = ES_PENDING;
-    }
-    // the first member of a run of adjacent windows walks the run in sx_sp_chains_kernel
-    bool chain_start = false;
-    if (active && adj) chain_start = !(e > 1 && list_window(X, X.cta_off, e - 2) == wp - 1);
-    sp_push(B, chain_start, (uint32_t)e);
     bool declined = false;
-    if (active && !adj) {
-        WinGeom wg;
-        c.geo.window(w, wg);
-        Carry kin0 = P.k0;
-        bool ok = true;
-        if (w != 0) {
-            const WinGeom rg = preroll_geom(c.geo, w, X.pre_bytes);
-            WinResult rr;
-            ok = utf8_mask_window(P, c.ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr);
-            kin0 = rr.out;
-        }
-        WinResult r;
-        if (ok) ok = utf8_mask_window(P, c.ts, wg, kin0, MODE_BUFFER, es->staged, 0, r);
-        if (ok) sp_store(es, kin0, r);
-        else {
-            es->status = ES_DECLINED;
-            // with a run behind it the run's walker resolves it, otherwise it is queued on its own
-            declined = !(e + 1 < B.NE && list_window(X, X.cta_off, e + 1) == w + 1);
-        }
+    if (e < B.NE) {
+        const long long w = list_window(X, X.cta_off, e);
+        const bool adj = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
+        if (!adj && !sp_head_mask(P, X, c, w, &B.E[e])) { B.E[e].status = ES_DECLINED; declined = true; }
     }
-    sp_push(B, declined, (uint32_t)e | kQueueHead);
+    sp_push(B.queue2, B.qcount2, declined, (uint32_t)e);
 }
 
-// Persistent over the queue: runs of adjacent windows walked under the real carries, declined heads.
+// Members of runs, all at once: the carry-in of a member is the carry-out of the entry before it -- known when that
+// entry is a resolved head, and computable from the window alone when its carry-out does not depend on its own
+// carry-in (mask engine under the null carry, WinResult.cut1 == 0).  What remains is walked in order by
+// sx_sp_fix_kernel.  Persistent over the queue.
 __global__ void __launch_bounds__(kSpThreads, 4)
-sx_sp_chains_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
+sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     SpCtx c;
     sp_setup(P, X, B, T, c);
     const unsigned long long nq = *B.qcount;
+    const unsigned long long stride = (unsigned long long)gridDim.x * kSpThreads;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * kSpThreads; t0 < nq; t0 += stride) {
+        const unsigned long long t = t0 + threadIdx.x;
+        bool dependent = false;
+        long long e = 0;
+        if (t < nq) {
+            e = (long long)B.queue[t];
+            const long long w = list_window(X, X.cta_off, e);
+            const bool pred_is_member = e > 1 && list_window(X, X.cta_off, e - 2) == w - 2;
+            Carry kin = carry_none();
+            bool known = false;
+            if (!pred_is_member) {
+                known = B.E[e - 1].status == ES_DONE;
+                if (known) kin = B.E[e - 1].kout;
+            } else {
+                WinGeom pg;
+                c.geo.window(w - 1, pg);
+                WinResult rr;
+                known = utf8_mask_window(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr) && rr.cut1 == 0;
+                kin = rr.out;
+            }
+            if (known) sp_member(P, c, w, kin, &B.E[e]);
+            else { B.E[e].status = ES_DEPENDENT; dependent = true; }
+        }
+        sp_push(B.queue2, B.qcount2, dependent, (uint32_t)e);
+    }
+}
+
+// What the parallel stages left: heads the mask engine declined (byte-wise engine) and members whose carry-in needs
+// the entry before them resolved first -- walked in stream order from the first member whose predecessor is resolved.
+// Entry statuses are frozen here (decisions only read what the earlier kernels wrote).  Persistent over queue2.
+__global__ void __launch_bounds__(kSpThreads, 4)
+sx_sp_fix_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
+    __shared__ Utf8Tables T;
+    SpCtx c;
+    sp_setup(P, X, B, T, c);
+    const unsigned long long nq = *B.qcount2;
     for (unsigned long long t = (unsigned long long)blockIdx.x * kSpThreads + threadIdx.x; t < nq;
          t += (unsigned long long)gridDim.x * kSpThreads) {
-        const uint32_t item = B.queue[t];
-        const long long e = (long long)(item & ~kQueueHead);
+        const long long e = (long long)B.queue2[t];
         const long long w = list_window(X, X.cta_off, e);
-        if (item & kQueueHead) {
-            sp_head_bytewise(P, X, c, w, &B.E[e]);
+        const uint8_t st = B.E[e].status;
+        if (st == ES_DECLINED) {
+            // followed by a member: that member is dependent and its walker resolves this head first
+            const bool next_adj = e + 1 < B.NE && list_window(X, X.cta_off, e + 1) == w + 1;
+            if (!next_adj) sp_head_bytewise(P, X, c, w, &B.E[e]);
             continue;
         }
-        if (B.E[e - 1].status != ES_DONE) sp_head_bytewise(P, X, c, w - 1, &B.E[e - 1]);
+        const uint8_t ps = B.E[e - 1].status;
+        if (ps == ES_DEPENDENT) continue;  // the walk that started further left comes through here
+        if (ps == ES_DECLINED) sp_head_bytewise(P, X, c, w - 1, &B.E[e - 1]);
         Carry kin = B.E[e - 1].kout;
         long long m = e, wm = w;
         for (;;) {
-            EntryState* const es = &B.E[m];
-            WinGeom wg;
-            c.geo.window(wm, wg);
-            WinResult r;
-            if (!utf8_mask_window(P, c.ts, wg, kin, MODE_BUFFER, es->staged, 0, r))
-                WindowEngine<DecUtf8>::run(P, c.ts, c.g, wg, kin, MODE_BUFFER, es->staged, 0, r, nullptr);
-            sp_store(es, kin, r);
-            kin = r.out;
+            kin = sp_member(P, c, wm, kin, &B.E[m]);
             ++m;
-            if (m >= B.NE) break;
+            if (m >= B.NE || B.E[m].status != ES_DEPENDENT) break;
             const long long wn = list_window(X, X.cta_off, m);
             if (wn != wm + 1) break;
             wm = wn;
@@ -213,8 +274,8 @@ sx_sp_ext_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
     unsigned long long sum_r = 0, sum_t = 0;
     if (e < B.NE) {
         EntryState* const es = &B.E[e];
-        const Carry kout = es->kout;
         const long long w = list_window(X, X.cta_off, e);
+        const Carry kout = es->kout;
         const bool next_adj = e + 1 < B.NE && list_window(X, X.cta_off, e + 1) == w + 1;
         uint32_t xr = 0, xt = 0;
         // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an unlisted
@@ -361,14 +422,40 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
 inline cudaError_t launch_sparse_utf8_impl(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B, int num_sms,
                                            cudaStream_t st) {
     const unsigned nb = (unsigned)((B.NE + kSpThreads - 1) / kSpThreads);
+    const unsigned pgrid = std::min<unsigned>(nb, (unsigned)num_sms * 4u);
+    static cudaEvent_t dbg[8];
+    static bool dbg_on = getenv("SX_DEBUG_TIMING") != nullptr, dbg_init = false;
+    if (dbg_on && !dbg_init) { for (auto& e : dbg) cudaEventCreate(&e); dbg_init = true; }
+    if (dbg_on) cudaEventRecord(dbg[0], st);
     sx_sp_tables_kernel<<<8, 256, 0, st>>>(P, B.tables);
-    sx_sp_heads_kernel<<<nb, kSpThreads, 0, st>>>(P, X, B);
-    sx_sp_chains_kernel<<<std::min<unsigned>(nb, (unsigned)num_sms * 4u), kSpThreads, 0, st>>>(P, X, B);
+    sx_sp_queue_kernel<<<(unsigned)((B.NE + 255) / 256), 256, 0, st>>>(X, B);
+    if (dbg_on) cudaEventRecord(dbg[1], st);
+    {
+        static const int occ = getenv("SX_HEADS_OCC") ? atoi(getenv("SX_HEADS_OCC")) : 6;
+        if (occ == 5) sx_sp_heads_kernel<5><<<nb, kSpThreads, 0, st>>>(P, X, B);
+        else if (occ == 6) sx_sp_heads_kernel<6><<<nb, kSpThreads, 0, st>>>(P, X, B);
+        else if (occ == 8) sx_sp_heads_kernel<8><<<nb, kSpThreads, 0, st>>>(P, X, B);
+        else sx_sp_heads_kernel<4><<<nb, kSpThreads, 0, st>>>(P, X, B);
+    }
+    if (dbg_on) cudaEventRecord(dbg[2], st);
+    sx_sp_members_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
+    if (dbg_on) cudaEventRecord(dbg[3], st);
+    sx_sp_fix_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
+    if (dbg_on) cudaEventRecord(dbg[4], st);
     sx_sp_ext_kernel<<<nb, kSpThreads, 0, st>>>(P, X, B);
+    if (dbg_on) cudaEventRecord(dbg[5], st);
     sx_sp_scan_kernel<<<1, 1024, 0, st>>>(B.btot, nb, O.counters);
     sx_sp_gather_kernel<<<nb, kSpThreads, 0, st>>>(P, O, X, B);
+    if (dbg_on) {
+        cudaEventRecord(dbg[6], st);
+        cudaEventSynchronize(dbg[6]);
+        float t[6];
+        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], dbg[i], dbg[i + 1]);
+        fprintf(stderr, "[sx sparse] tables+queue %.3f heads %.3f members %.3f fix %.3f ext %.3f scan+gather %.3f ms\n", t[0], t[1], t[2],
+                t[3], t[4], t[5]);
+    }
     return cudaGetLastError();
 }
-constexpr uint32_t kSparseLaunches = 6;
+constexpr uint32_t kSparseLaunches = 8;
 
 }  // namespace sx

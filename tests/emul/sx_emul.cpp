@@ -21,6 +21,7 @@ static int g_use_fast = 1;
 static int g_use_mask = 1;
 static uint64_t g_mask_ok = 0, g_mask_declined = 0;
 static uint64_t g_mask_mismatch = 0;
+static uint64_t g_head_ok = 0;
 struct HostTile {
     GlobalSrc g;
     const Utf8Tables* tables() const { return g_use_fast ? &g_tables : nullptr; }
@@ -119,6 +120,22 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         if (memcmp(&rs.out, &kout, sizeof(Carry)) != 0) { stats[3]++; kout = rs.out; }
         WinResult rc;
         emit_window(wg, kin, rc);
+        if (!adjacent && w != 0 && P.enc == ENC_UTF8 && !P.general && g_use_mask && g_use_fast) {
+            // the product resolves heads in one pass (carry-in derived from the 32 bytes before the window): same
+            // carry-in as the pre-roll, same counts and carry-out as the pass under that carry
+            WinResult rh;
+            if (utf8_mask_head(P, ts, wg, pre_bytes, MODE_COUNT, nullptr, 0, rh)) {
+                g_head_ok++;
+                const bool same = memcmp(&rh.in, &kin, sizeof(Carry)) == 0 && memcmp(&rh.out, &rc.out, sizeof(Carry)) == 0 &&
+                                  rh.nrec == rc.nrec && rh.ntext == rc.ntext && rh.npend_out == rc.npend_out;
+                if (!same) {
+                    stats[3] += 1000000;
+                    if (g_mask_mismatch++ < 5)
+                        fprintf(stderr, "one-pass head mismatch: window [%lld,%lld) kin k=%d/%d in=%u/%u out=%u/%u nrec %u/%u\n", (long long)wg.ws,
+                                (long long)wg.we, rh.in.k, kin.k, rh.in.in_bytes, kin.in_bytes, rh.in.out_bytes, kin.out_bytes, rh.nrec, rc.nrec);
+                }
+            }
+        }
         if (!needs_emit(P, d, kin) && rc.nrec != 0) stats[4]++;
         if (carry_is_null(kin) && d.nrec != 0xFFFF && (rc.nrec != d.nrec || rc.ntext != d.ntext)) stats[5]++;
         last_npend = rs.npend_out;
@@ -172,6 +189,7 @@ void sx_emul_set_fast(int on) { g_use_fast = on; }
 void sx_emul_set_mask(int on) { g_use_mask = on; }
 void sx_emul_mask_counts(uint64_t* ok, uint64_t* declined) { *ok = g_mask_ok; *declined = g_mask_declined; }
 uint64_t sx_emul_mask_mismatches() { return g_mask_mismatch; }
+uint64_t sx_emul_head_ok() { return g_head_ok; }
 int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
     for (uint32_t i = 0; i < 2048; ++i) utf8_tables_fill(*P, g_tables, i);
     std::vector<uint32_t> list;
