@@ -2,7 +2,9 @@
 // code in sx_scan.cu.  One instantiation per decoder lives in its own translation unit
 // (sx_exact_inst.cu compiled with -DSX_INST=n) so that the library builds in parallel.
 #pragma once
+#include "../../include/stringsext_b200.h"
 #include "sx_mask_utf8.cuh"
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <type_traits>
 
@@ -16,6 +18,7 @@ struct FinalState {
     Carry carry;
     int32_t npend;
     uint32_t overflow;
+    uint32_t first_flags, last_flags;  // RF_* of the first / last record in stream order (direct host output only)
 };
 
 struct ScanOut {
@@ -25,7 +28,31 @@ struct ScanOut {
     uint2* block_desc;             // per exact-kernel block {first record, record count}
     unsigned long long* counters;  // [0] records, [1] text bytes, [2] list entries, [3] next block of the exact kernel
     FinalState* final_state;
+    // direct host output (sparse pipeline): findings written by the GPU in their final C-ABI form into pinned host
+    // memory (posted PCIe writes from the gather kernel), so the host neither copies nor converts records
+    sx_finding* host_findings;     // mapped pinned memory, nullptr: off
+    unsigned long long host_cap;
+    const uint8_t* host_text;      // HOST address the finding text will be downloaded to (text arena base)
+    int32_t file_id;
+    uint32_t mission_id;
 };
+
+static_assert(sizeof(sx_finding) == 48 && offsetof(sx_finding, precision) == 8 && offsetof(sx_finding, completes_previous) == 9 &&
+              offsetof(sx_finding, input_file_id) == 10 && offsetof(sx_finding, mission_id) == 12 && offsetof(sx_finding, s) == 16 &&
+              offsetof(sx_finding, s_len) == 24 && offsetof(sx_finding, in_start) == 32 && offsetof(sx_finding, in_len) == 40,
+              "sx_finding layout");
+// One finding in its C-ABI layout, three 16-byte stores (finding.rs:51-74; `s` = host address of its text).
+__device__ __forceinline__ void write_host_finding(const ScanOut& O, unsigned long long idx, const Record& r) {
+    uint4* dst = reinterpret_cast<uint4*>(O.host_findings + idx);
+    const unsigned long long sp = reinterpret_cast<unsigned long long>(O.host_text) + r.text_off;
+    uint4 a, b, c;
+    a.x = (uint32_t)r.position; a.y = (uint32_t)(r.position >> 32);
+    a.z = (r.precision & 0xFFu) | ((r.flags & RF_COMPLETES) ? 0x100u : 0u) | (((uint32_t)O.file_id & 0xFFFFu) << 16);
+    a.w = O.mission_id & 0xFFu;
+    b.x = (uint32_t)sp; b.y = (uint32_t)(sp >> 32); b.z = r.text_len; b.w = 0;
+    c.x = (uint32_t)r.in_start; c.y = (uint32_t)((unsigned long long)r.in_start >> 32); c.z = r.in_len; c.w = 0;
+    dst[0] = a; dst[1] = b; dst[2] = c;
+}
 
 // Work list of the exact kernel: the windows the prefilter kept, in stream order
 // (list == nullptr: every window, entry e is window e).

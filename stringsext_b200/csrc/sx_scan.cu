@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -711,6 +712,7 @@ struct sx_scanner_state {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int num_sms = 0;
     double rec_per_byte = 1.0 / 1024, text_per_byte = 1.0 / 64;
+    size_t host_rec_hint = 1u << 20, host_text_hint = 16u << 20;  // direct host output: first-call sizes of the pinned set
     sx_scan_stats stats;
 };
 
@@ -719,7 +721,9 @@ template <class T>
 struct RawVec {
     T* p = nullptr;
     size_t n = 0, cap = 0;
-    ~RawVec() { free(p); }
+    bool external = false;  // storage owned by someone else (a pinned set)
+    ~RawVec() { if (!external) free(p); }
+    void adopt(T* q, size_t count) { if (!external) free(p); p = q; n = count; cap = count; external = true; }
     void reserve(size_t c) { if (c > cap) { p = (T*)realloc(p, c * sizeof(T)); cap = c; } }
     void resize(size_t c) { reserve(c); n = c; }
     void push_back(const T& x) { if (n == cap) reserve(cap ? cap * 2 : 16); p[n++] = x; }
@@ -731,11 +735,56 @@ struct RawVec {
     const T* begin() const { return p; }
     const T* end() const { return p + n; }
 };
+// Pinned, device-mapped host memory the GPU writes a call's findings into (sx_sp_gather_kernel) and the finding
+// text is downloaded to.  A collection built that way owns its set; sets are recycled through a small pool because
+// pinning memory costs far more than a scan.
+struct PinnedSet {
+    sx_finding* f = nullptr; size_t fcap = 0;  // findings
+    uint8_t* t = nullptr; size_t tcap = 0;     // text bytes
+};
+static std::mutex g_pool_mu;
+static std::vector<PinnedSet> g_pool;
+static void pinned_free(PinnedSet& s) {
+    if (s.f) cudaFreeHost(s.f);
+    if (s.t) cudaFreeHost(s.t);
+    s = PinnedSet();
+}
+static bool pinned_acquire(size_t fcap, size_t tcap, PinnedSet* out) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i].fcap >= fcap && g_pool[i].tcap >= tcap && (best < 0 || g_pool[i].fcap < g_pool[best].fcap)) best = (int)i;
+        if (best >= 0) { *out = g_pool[best]; g_pool.erase(g_pool.begin() + best); return true; }
+    }
+    PinnedSet s;
+    s.fcap = fcap + fcap / 4 + 1024;
+    s.tcap = tcap + tcap / 4 + 65536;
+    if (cudaHostAlloc((void**)&s.f, s.fcap * sizeof(sx_finding), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc((void**)&s.t, s.tcap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        pinned_free(s);
+        return false;
+    }
+    *out = s;
+    return true;
+}
+static void pinned_release(PinnedSet& s) {
+    if (!s.f && !s.t) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < 4) { g_pool.push_back(s); s = PinnedSet(); return; }
+    }
+    pinned_free(s);
+}
+
 struct sx_finding_collection {
     RawVec<sx_finding> v;
     RawVec<uint8_t> text;
+    PinnedSet set;  // direct host output: v and the finding text live here
     uint64_t first_byte_position = 0;
     int str_buf_overflow = 0;
+    ~sx_finding_collection() { pinned_release(set); }
 };
 
 extern "C" {
@@ -1028,6 +1077,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     }
     size_t need_recs = (size_t)(len * ss->rec_per_byte) + 4096;
     size_t need_text = (size_t)(len * ss->text_per_byte) + 65536;
+    size_t need_recs_min = 0, need_text_min = 0;  // after an overflow: what the device counted
     unsigned long long counters[4] = {0, 0, 0, 0};
     FinalState fin;
     for (int attempt = 0;; ++attempt) {
@@ -1035,7 +1085,8 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         if (!grow(&ss->d_text, &ss->text_cap, need_text)) return fail;
         CK(cudaMemsetAsync(ss->d_counters, 0, 8 * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(ss->d_final, 0, sizeof(FinalState), st));
-        ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final};
+        ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, nullptr, 0, nullptr,
+                  input_file_id, ss->m.mission_id};
         ExactCfg X;
         X.total_windows = total_windows;
         X.in_aligned16 = in_aligned16 ? 1u : 0u;
@@ -1088,6 +1139,17 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
                 if (!grow(&ss->d_btot, &ss->btot_cap, (nb + 1) * sizeof(ulonglong2))) return fail;
                 if (!grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes())) return fail;
                 if (!grow(&ss->d_queue, &ss->queue_cap, (2 * (size_t)ne + 128) * sizeof(uint32_t))) return fail;
+                // direct host output: the gather kernel writes the findings in their C-ABI form into a pinned set
+                const size_t want_f = std::min(need_recs, std::max(ss->host_rec_hint, need_recs_min));
+                const size_t want_t = std::min(need_text, std::max(ss->host_text_hint, need_text_min));
+                if (fc->set.fcap < want_f || fc->set.tcap < want_t) {
+                    pinned_release(fc->set);
+                    if (!pinned_acquire(want_f, want_t, &fc->set)) { set_err(SX_ERR_CUDA, "cannot pin host memory for the findings"); return fail; }
+                }
+                O.host_findings = fc->set.f;
+                O.host_cap = fc->set.fcap;
+                O.host_text = fc->set.t;
+                O.text_cap = std::min<unsigned long long>(O.text_cap, fc->set.tcap);
                 CK(launch_sparse_utf8(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st));
                 ss->stats.kernel_launches += sparse_launches();
                 sparse = true;
@@ -1105,10 +1167,13 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         CK(cudaMemcpyAsync(&fin, ss->d_final, sizeof fin, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ss->stats.d2h_bytes += sizeof counters + sizeof fin;
-        if (!fin.overflow && counters[0] <= ss->rec_cap && counters[1] <= ss->text_cap) break;
+        if (!fin.overflow && counters[0] <= ss->rec_cap && counters[1] <= ss->text_cap &&
+            (!fc->set.f || !ss->stats.sparse_used || (counters[0] <= fc->set.fcap && counters[1] <= fc->set.tcap))) break;
         if (attempt >= 2) { set_err(SX_ERR_CUDA, "output buffers still too small after regrowing"); return fail; }
         need_recs = (size_t)counters[0] + 1024;
         need_text = (size_t)counters[1] + 4096;
+        need_recs_min = need_recs;
+        need_text_min = need_text;
         ss->stats.relaunches++;
     }
     if (!pc.enabled) counters[2] = (unsigned long long)total_windows;
@@ -1138,6 +1203,61 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     ss->stats.text_bytes = ntext;
 
     // ---- text + download ---------------------------------------------------------------------------
+    std::vector<uint8_t> new_leftover;
+    bool have_leftover = false;
+    const bool direct_out = ss->stats.sparse_used != 0 && fc->set.f != nullptr;
+    if (direct_out) {
+        // The findings are already in the collection's pinned set, written by the gather kernel in their final form;
+        // only the text (transcoded on the device) is downloaded, straight to the address the findings point to.
+        if (nrec) {
+            const int mgrid = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ss->num_sms * 8);
+            CK(cudaEventRecord(ss->ev[2], st));
+            sx_materialize_kernel<<<mgrid, 256, 0, st>>>(P, ss->d_recs, nrec, ss->d_text, ss->text_cap);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ss->ev[3], st));
+            ss->stats.kernel_launches++;
+            if (ntext) CK(cudaMemcpyAsync(fc->set.t, ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
+            ss->stats.d2h_bytes += nrec * sizeof(sx_finding) + ntext;
+        }
+    }
+    // bytes that stay inside the decoder: the last npend bytes of (old pend ++ buffer)
+    uint8_t tail[8] = {0};
+    const size_t tail_n = std::min<size_t>(8, len);
+    if (direct_out) {
+        if (buf_is_device) CK(cudaMemcpyAsync(tail + 8 - tail_n, d_in + len - tail_n, tail_n, cudaMemcpyDeviceToHost, st));
+        else memcpy(tail + 8 - tail_n, (const uint8_t*)buf + len - tail_n, tail_n);
+        CK(cudaStreamSynchronize(st));
+        if (nrec) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ss->ev[2], ss->ev[3]);
+            ss->stats.materialize_kernel_ms = ms;
+        }
+        const auto t_post = std::chrono::steady_clock::now();
+        ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - t_begin).count();
+        const bool tail_is_leftover = nrec > 0 && (fin.last_flags & RF_LEFTOVER) != 0;
+        const size_t n_out = nrec - (tail_is_leftover ? 1 : 0);
+        fc->v.adopt(fc->set.f, n_out);
+        // host text in front of device text: the first record of a run that began in the previous call, the leftover
+        auto with_host_text = [&](const sx_finding& f, std::vector<uint8_t>& dst) {
+            dst.assign(ss->leftover.begin(), ss->leftover.end());
+            dst.insert(dst.end(), f.s, f.s + f.s_len);
+        };
+        if (tail_is_leftover) {
+            const sx_finding& f = fc->set.f[nrec - 1];
+            if (fin.last_flags & RF_HOSTCARRY) with_host_text(f, new_leftover);
+            else new_leftover.assign(f.s, f.s + f.s_len);
+            have_leftover = true;
+        }
+        if (n_out > 0 && (fin.first_flags & RF_HOSTCARRY)) {
+            std::vector<uint8_t> t;
+            with_host_text(fc->set.f[0], t);
+            fc->text.resize(t.size() + 1);
+            memcpy(fc->text.data(), t.data(), t.size());
+            fc->set.f[0].s = fc->text.data();
+            fc->set.f[0].s_len = (uint32_t)t.size();
+        }
+        ss->stats.host_post_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_post).count();
+    } else {
     const bool sparse_out = ss->stats.sparse_used != 0;  // records already in stream order: one descriptor
     const size_t nblocks = sparse_out ? 1 : (size_t)((counters[2] + kThreads - 1) / kThreads);
     if (!grow_pinned(&ss->h_recs, &ss->h_recs_cap, nrec + 1)) return fail;
@@ -1159,9 +1279,6 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         else CK(cudaMemcpyAsync(ss->h_blocks, ss->d_blocks, nblocks * sizeof(uint2), cudaMemcpyDeviceToHost, st));
         ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + (sparse_out ? 0 : nblocks * sizeof(uint2));
     }
-    // bytes that stay inside the decoder: the last npend bytes of (old pend ++ buffer)
-    uint8_t tail[8] = {0};
-    const size_t tail_n = std::min<size_t>(8, len);
     if (buf_is_device) CK(cudaMemcpyAsync(tail + 8 - tail_n, d_in + len - tail_n, tail_n, cudaMemcpyDeviceToHost, st));
     else memcpy(tail + 8 - tail_n, (const uint8_t*)buf + len - tail_n, tail_n);
     CK(cudaStreamSynchronize(st));
@@ -1178,8 +1295,6 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     // began in the previous call) and the final leftover pseudo record, which is always the last one.
     const size_t extra_text = 2 * (ss->leftover.size() + 8 * (size_t)q + 64);
     fc->text.resize(ntext + extra_text + 1);
-    std::vector<uint8_t> new_leftover;
-    bool have_leftover = false;
     if (nrec) {
         std::vector<size_t> out_off(nblocks + 1);
         size_t acc = 0, last_block = 0;
@@ -1257,6 +1372,8 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         }
     }
 
+    }
+
     // ---- ScannerState update (finding_collection.rs:330-338) -----------------------------------------
     ss->cut = fin.carry.kind == K_C;
     if (fin.carry.kind == K_L && fin.carry.k > 0 && have_leftover) ss->leftover.swap(new_leftover);
@@ -1279,7 +1396,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     {
         const auto t_end = std::chrono::steady_clock::now();
         ss->stats.host_total_ms = std::chrono::duration<float, std::milli>(t_end - t_begin).count();
-        ss->stats.host_post_ms = std::chrono::duration<float, std::milli>(t_end - t_post).count();
+        if (!direct_out) ss->stats.host_post_ms = ss->stats.host_total_ms - ss->stats.host_phase_ms[2];
         ss->stats.host_phase_ms[3] = ss->stats.host_total_ms;
     }
     guard.p = nullptr;

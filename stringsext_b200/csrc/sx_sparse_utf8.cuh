@@ -371,22 +371,32 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     }
     const ulonglong2 base = B.btot[blockIdx.x];
     const unsigned long long br = base.x, bt = base.y;
-    const bool fits = (br + tr <= O.rec_cap) && (bt + tt <= O.text_cap);
+    const bool fits = (br + tr <= O.rec_cap) && (bt + tt <= O.text_cap) && (O.host_findings == nullptr || br + tr <= O.host_cap);
     if (!fits && threadIdx.x == 0) O.final_state->overflow = 1;
     if (active && fits) {
         uint32_t ro = er, to = et;
+        const bool host_out = O.host_findings != nullptr;
+        // the first / last record of the stream: their flags travel in the final state (host-carried text, leftover)
+        auto put = [&](unsigned long long idx, const Record& r) {
+            O.recs[idx] = r;
+            if (host_out) {
+                write_host_finding(O, idx, r);
+                if (idx == 0) O.final_state->first_flags = r.flags;
+            }
+        };
         if (cr) {
             if (cr <= kBufRecs) {
                 for (uint32_t k = 0; k < cr; ++k) {
                     Record r = es->staged[k];
                     r.text_off += bt + to;
-                    O.recs[br + ro + k] = r;
+                    put(br + ro + k, r);
                 }
             } else {
                 WinGeom wg;
                 c.geo.window(list_window(X, X.cta_off, e), wg);
                 WinResult r;
                 WindowEngine<DecUtf8>::run(P, c.ts, c.g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+                if (host_out) for (uint32_t k = 0; k < cr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
         }
         ro += cr; to += ct;
@@ -395,12 +405,13 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
                 for (uint32_t k = 0; k < xr; ++k) {
                     Record r = es->xstaged[k];
                     r.text_off += bt + to;
-                    O.recs[br + ro + k] = r;
+                    put(br + ro + k, r);
                 }
             } else {
                 const WinGeom xg = ext_geom(c.geo, list_window(X, X.cta_off, e) + 1, X.pre_bytes);
                 WinResult r;
                 WindowEngine<DecUtf8>::run(P, c.ts, c.g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+                if (host_out) for (uint32_t k = 0; k < xr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
         }
         ro += xr; to += xt;
@@ -413,7 +424,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
             r.text_off = bt + to;
             r.flags = RF_LEFTOVER | ((kout.flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u);
             r.precision = 0;
-            O.recs[br + ro] = r;
+            put(br + ro, r);
+            O.final_state->last_flags = r.flags;
         }
     }
     if (active && e == B.NE - 1) { O.final_state->carry = kout; O.final_state->npend = es->npend; }
