@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--cpu-sample-mib", type=int, default=256)
     ap.add_argument("--e2e-max-mib", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--as-rank", type=int, default=-1, help="debug: single process scanning rank R's encoding of the --gpus config")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -242,7 +243,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = config_for(args.gpus)
     size = cfg["size"] if not args.size_mib else args.size_mib << 20
-    label, ubf_name = cfg["missions"][rank % len(cfg["missions"])]
+    label, ubf_name = cfg["missions"][(args.as_rank if args.as_rank >= 0 else rank) % len(cfg["missions"])]
     mission = make_mission(sx, label, ubf_name, cfg["n"], rank)
     L = sx.load_library()
 
@@ -274,6 +275,7 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, mat_ms, pre_ms, lst_ms, ex_ms, launches, nfind, d2h = [], [], [], [], [], 0, 0, 0
+    sp_ms, sparse_used = [], 0
     host_ms = []
     e0.record(stream)
     for _ in range(args.steps):
@@ -283,6 +285,8 @@ def main():
         pre_ms.append(st.prefilter_kernel_ms)
         lst_ms.append(st.list_kernels_ms)
         ex_ms.append(st.exact_kernel_ms)
+        sp_ms.append([float(x) for x in st.sparse_stage_ms])
+        sparse_used = int(st.sparse_used)
         win_total, win_listed = st.windows_total, st.windows_listed
         host_ms.append((st.host_total_ms, st.host_post_ms, *[float(x) for x in st.host_phase_ms]))
         launches += st.kernel_launches
@@ -333,9 +337,19 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         avg = lambda v: sum(v) / len(v)
-        kernels = {"sx_prefilter_kernel": avg(pre_ms), "sx_list_scan+expand": avg(lst_ms), "sx_exact_kernel": avg(ex_ms),
-                   "sx_materialize_kernel": avg(mat_ms)}
-        dominant = max(("sx_prefilter_kernel", "sx_exact_kernel"), key=lambda k: kernels[k])
+        kernels = {"sx_prefilter_kernel": avg(pre_ms), "sx_list_offsets_kernel": avg(lst_ms), "sx_materialize_kernel": avg(mat_ms)}
+        if sparse_used:
+            # exact stage = the sparse-list pipeline (sx_sparse_utf8.cuh): one entry per kernel (group), CUDA events between them
+            names = ("sx_sp_tables+queue", "sx_sp_heads_kernel", "sx_sp_members_kernel", "sx_sp_fix_kernel", "sx_sp_ext_kernel",
+                     "sx_sp_scan+gather")
+            for i, nm in enumerate(names):
+                kernels[nm] = avg([v[i] for v in sp_ms])
+            kernels["exact_stage_total(incl. list-length round trip)"] = avg(ex_ms)
+            candidates = ("sx_prefilter_kernel",) + names
+        else:
+            kernels["sx_exact_kernel"] = avg(ex_ms)
+            candidates = ("sx_prefilter_kernel", "sx_exact_kernel")
+        dominant = max(candidates, key=lambda k: kernels[k])
         k_ms = kernels[dominant]
         # algorithmic bytes per launch: the prefilter reads every input byte once; the exact
         # kernel reads the listed windows (128 B each at the default geometry)

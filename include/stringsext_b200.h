@@ -128,7 +128,8 @@ typedef struct {
     float scan_kernel_ms;        /* prefilter + list + exact kernels, first launch to last */
     float prefilter_kernel_ms;   /* sx_prefilter_kernel: the one pass over every input byte (HBM bound) */
     float list_kernels_ms;       /* sx_list_scan_kernel + sx_list_expand_kernel */
-    float exact_kernel_ms;       /* sx_exact_kernel: automaton over the listed windows */
+    float exact_kernel_ms;       /* exact stage over the listed windows: sx_exact_kernel, or the sparse pipeline's kernels
+                                  * incl. the host round trip for the list length */
     float materialize_kernel_ms; /* sx_materialize_kernel (finding text) */
     uint32_t kernel_launches;    /* launches of library kernels in the call */
     uint32_t relaunches;         /* pipeline re-runs caused by an output buffer that was too small */
@@ -141,6 +142,7 @@ typedef struct {
     uint64_t windows_total, windows_listed;
     float host_total_ms; /* wall clock of the whole call */
     float host_post_ms;  /* of which: building the collection after the last device sync */
+    float sparse_stage_ms[6]; /* sparse pipeline (sparse_used): tables+queue, heads, members, fix, ext, scan+gather kernels */
     float host_phase_ms[4]; /* wall clock: [0] call start -> kernels enqueued, [1] -> counters back (first sync),
                              * [2] -> results downloaded (second sync), [3] -> collection built */
 } sx_scan_stats;
@@ -150,6 +152,7 @@ void sx_scanner_state_last_stats(const sx_scanner_state*, sx_scan_stats* out);
 void sx_scanner_state_set_prefilter(sx_scanner_state*, int enabled);
 void sx_scanner_state_set_tma(sx_scanner_state*, int enabled); /* 0: stage tiles with plain vector loads */
 void sx_scanner_state_set_sparse(sx_scanner_state*, int enabled); /* 0: always the block kernel for the exact stage */
+void sx_scanner_state_set_direct_output(sx_scanner_state*, int enabled); /* 0: download records, convert on the host */
 /* Copies the window list the prefilter built in the most recent call (ascending window indices,
  * window = decoder_input_window of finding_collection.rs:120-131) into out[0..cap); returns the
  * list length, 0 when the prefilter did not run. */

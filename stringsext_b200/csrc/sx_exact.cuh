@@ -42,8 +42,7 @@ static_assert(sizeof(sx_finding) == 48 && offsetof(sx_finding, precision) == 8 &
               offsetof(sx_finding, s_len) == 24 && offsetof(sx_finding, in_start) == 32 && offsetof(sx_finding, in_len) == 40,
               "sx_finding layout");
 // One finding in its C-ABI layout, three 16-byte stores (finding.rs:51-74; `s` = host address of its text).
-__device__ __forceinline__ void write_host_finding(const ScanOut& O, unsigned long long idx, const Record& r) {
-    uint4* dst = reinterpret_cast<uint4*>(O.host_findings + idx);
+__device__ __forceinline__ void write_host_finding(const ScanOut& O, uint4* dst, const Record& r) {
     const unsigned long long sp = reinterpret_cast<unsigned long long>(O.host_text) + r.text_off;
     uint4 a, b, c;
     a.x = (uint32_t)r.position; a.y = (uint32_t)(r.position >> 32);
@@ -589,7 +588,7 @@ cudaError_t launch_exact_utf32be(const ScanParams& P, const ScanOut& O, const Ex
 
 // sparse-list pipeline for UTF-8 (sx_sparse_utf8.cuh, compiled into the UTF-8 translation unit)
 cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                               void* queue, long long NE, int num_sms, cudaStream_t st);
+                               void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev);
 size_t sparse_entry_bytes();
 size_t sparse_tables_bytes();
 uint32_t sparse_threads();

@@ -36,7 +36,7 @@ cudaError_t SX_NAME(const ScanParams& P, const ScanOut& O, const ExactCfg& X, un
 }
 #if SX_INST == 1
 cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                               void* queue, long long NE, int num_sms, cudaStream_t st) {
+                               void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev) {
     SparseBufs B;
     B.E = static_cast<EntryState*>(entries);
     B.btot = static_cast<ulonglong2*>(btot);
@@ -46,7 +46,7 @@ cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const Exac
     B.queue2 = B.queue + NE + 32;
     B.qcount2 = O.counters + 4;
     B.NE = NE;
-    return launch_sparse_utf8_impl(P, O, X, B, num_sms, st);
+    return launch_sparse_utf8_impl(P, O, X, B, num_sms, st, ev);
 }
 size_t sparse_entry_bytes() { return sizeof(EntryState); }
 size_t sparse_tables_bytes() { return sizeof(Utf8Tables); }

@@ -615,6 +615,72 @@ __global__ void __launch_bounds__(1024) sx_list_offsets_kernel(const uint32_t* _
     if (tid == 1023) { cta_off[ncta] = base + inc; counters[2] = base + inc; }
 }
 
+// Block-kernel path, direct host output: sx_exact_kernel reserves record ranges block by block in completion order
+// (block_desc[b] = {first record, count}); stream order is the order of the blocks.  sx_order_scan_kernel turns the
+// counts into stream-order positions, sx_order_write_kernel writes every record as a finding (C-ABI layout) to its
+// position in the collection's pinned set -- same result as the sparse pipeline's gather kernel.
+__global__ void __launch_bounds__(1024) sx_order_scan_kernel(const uint2* __restrict__ desc, unsigned long long* __restrict__ pos,
+                                                             unsigned long long nb) {
+    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (unsigned long long base = 0; base < nb; base += 1024) {
+        const unsigned long long k = base + tid;
+        const unsigned long long v = k < nb ? desc[k].y : 0ull;
+        unsigned long long a = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, a, d);
+            if (lane >= (uint32_t)d) a += t;
+        }
+        if (lane == 31) ws[warp] = a;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long x = ws[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += t;
+            }
+            ws[lane] = x;
+        }
+        __syncthreads();
+        const unsigned long long o = carry + (warp ? ws[warp - 1] : 0ull);
+        if (k < nb) pos[k] = o + a - v;
+        __syncthreads();
+        if (tid == 1023) carry = o + a;
+        __syncthreads();
+    }
+}
+// one warp per block descriptor; 32 findings at a time are assembled in shared memory and leave as contiguous
+// 16-byte stores (512 bytes per warp instruction: large PCIe write transactions)
+__global__ void __launch_bounds__(256)
+sx_order_write_kernel(const ScanOut O, const uint2* __restrict__ desc, const unsigned long long* __restrict__ pos, unsigned long long nb,
+                      unsigned long long nrec) {
+    __shared__ uint4 sbuf[8][96];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * 8 + warp; b < nb; b += (unsigned long long)gridDim.x * 8) {
+        const uint2 d = desc[b];
+        const unsigned long long p0 = pos[b];
+        for (uint32_t k0 = 0; k0 < d.y; k0 += 32) {
+            const uint32_t cnt = d.y - k0 < 32u ? d.y - k0 : 32u;
+            if (lane < cnt) {
+                const Record r = O.recs[(unsigned long long)d.x + k0 + lane];
+                const unsigned long long idx = p0 + k0 + lane;
+                write_host_finding(O, &sbuf[warp][lane * 3], r);
+                if (idx == 0) O.final_state->first_flags = r.flags;
+                if (idx == nrec - 1) O.final_state->last_flags = r.flags;
+            }
+            __syncwarp();
+            uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + p0 + k0);
+            for (uint32_t t = lane; t < cnt * 3; t += 32) dst[t] = sbuf[warp][t];
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 sx_materialize_kernel(const __grid_constant__ ScanParams P, const Record* __restrict__ recs, unsigned long long n,
                       uint8_t* __restrict__ text, unsigned long long text_cap) {
@@ -698,10 +764,12 @@ struct sx_scanner_state {
     int use_prefilter = 1;
     int use_tma = 1;
     int use_sparse = 1;
+    int use_direct = 1;  // findings written by the GPU into pinned host memory (0: record download + host conversion)
     uint8_t* d_entries = nullptr; size_t entries_cap = 0;   // sparse pipeline: per-entry state
     uint8_t* d_btot = nullptr; size_t btot_cap = 0;
     uint8_t* d_tables = nullptr; size_t tables_cap = 0;
     uint8_t* d_queue = nullptr; size_t queue_cap = 0;
+    unsigned long long* d_bpos = nullptr; size_t bpos_cap = 0;  // block path, direct output: stream-order position of every block
     uint32_t last_ncta = 0; size_t last_region_stride = 0;
     // pinned host staging for result downloads
     Record* h_recs = nullptr; size_t h_recs_cap = 0;
@@ -710,6 +778,7 @@ struct sx_scanner_state {
     unsigned long long* d_counters = nullptr;
     FinalState* d_final = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t sev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // sparse pipeline stages
     int num_sms = 0;
     double rec_per_byte = 1.0 / 1024, text_per_byte = 1.0 / 64;
     size_t host_rec_hint = 1u << 20, host_text_hint = 16u << 20;  // direct host output: first-call sizes of the pinned set
@@ -827,6 +896,7 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
     bool ok = cuda_ok(cudaMalloc(&ss->d_counters, 8 * sizeof(unsigned long long)), "cudaMalloc") &&
               cuda_ok(cudaMalloc(&ss->d_final, sizeof(FinalState)), "cudaMalloc");
     for (int i = 0; ok && i < 6; ++i) ok = cuda_ok(cudaEventCreate(&ss->ev[i]), "cudaEventCreate");
+    for (int i = 0; ok && i < 7; ++i) ok = cuda_ok(cudaEventCreate(&ss->sev[i]), "cudaEventCreate");
     if (!ok) { sx_scanner_state_free(ss); return fail; }
     return ss;
 }
@@ -836,9 +906,10 @@ void sx_scanner_state_free(sx_scanner_state* ss) {
     cudaSetDevice(ss->device);
     cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_blocks); cudaFree(ss->d_ccount); cudaFree(ss->d_coff); cudaFree(ss->d_list);
     cudaFree(ss->d_counters); cudaFree(ss->d_final);
-    cudaFree(ss->d_entries); cudaFree(ss->d_btot); cudaFree(ss->d_tables); cudaFree(ss->d_queue);
+    cudaFree(ss->d_entries); cudaFree(ss->d_btot); cudaFree(ss->d_tables); cudaFree(ss->d_queue); cudaFree(ss->d_bpos);
     cudaFreeHost(ss->h_recs); cudaFreeHost(ss->h_text); cudaFreeHost(ss->h_blocks);
     for (auto e : ss->ev) if (e) cudaEventDestroy(e);
+    for (auto e : ss->sev) if (e) cudaEventDestroy(e);
     delete ss;
 }
 
@@ -859,6 +930,7 @@ void sx_scanner_state_last_stats(const sx_scanner_state* ss, sx_scan_stats* out)
 void sx_scanner_state_set_prefilter(sx_scanner_state* ss, int enabled) { ss->use_prefilter = enabled ? 1 : 0; }
 void sx_scanner_state_set_tma(sx_scanner_state* ss, int enabled) { ss->use_tma = enabled ? 1 : 0; }
 void sx_scanner_state_set_sparse(sx_scanner_state* ss, int enabled) { ss->use_sparse = enabled ? 1 : 0; }
+void sx_scanner_state_set_direct_output(sx_scanner_state* ss, int enabled) { ss->use_direct = enabled ? 1 : 0; }
 size_t sx_scanner_state_last_window_list(const sx_scanner_state* ss, uint32_t* out, size_t cap) {
     if (!ss->stats.prefilter_used) return 0;
     const size_t n = (size_t)ss->stats.windows_listed;
@@ -1140,17 +1212,19 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
                 if (!grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes())) return fail;
                 if (!grow(&ss->d_queue, &ss->queue_cap, (2 * (size_t)ne + 128) * sizeof(uint32_t))) return fail;
                 // direct host output: the gather kernel writes the findings in their C-ABI form into a pinned set
-                const size_t want_f = std::min(need_recs, std::max(ss->host_rec_hint, need_recs_min));
+                const size_t want_f = !ss->use_direct ? 0 : std::min(need_recs, std::max(ss->host_rec_hint, need_recs_min));
                 const size_t want_t = std::min(need_text, std::max(ss->host_text_hint, need_text_min));
-                if (fc->set.fcap < want_f || fc->set.tcap < want_t) {
-                    pinned_release(fc->set);
-                    if (!pinned_acquire(want_f, want_t, &fc->set)) { set_err(SX_ERR_CUDA, "cannot pin host memory for the findings"); return fail; }
+                if (ss->use_direct) {
+                    if (fc->set.fcap < want_f || fc->set.tcap < want_t) {
+                        pinned_release(fc->set);
+                        if (!pinned_acquire(want_f, want_t, &fc->set)) { set_err(SX_ERR_CUDA, "cannot pin host memory for the findings"); return fail; }
+                    }
+                    O.host_findings = fc->set.f;
+                    O.host_cap = fc->set.fcap;
+                    O.host_text = fc->set.t;
+                    O.text_cap = std::min<unsigned long long>(O.text_cap, fc->set.tcap);
                 }
-                O.host_findings = fc->set.f;
-                O.host_cap = fc->set.fcap;
-                O.host_text = fc->set.t;
-                O.text_cap = std::min<unsigned long long>(O.text_cap, fc->set.tcap);
-                CK(launch_sparse_utf8(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st));
+                CK(launch_sparse_utf8(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st, ss->sev));
                 ss->stats.kernel_launches += sparse_launches();
                 sparse = true;
             }
@@ -1186,6 +1260,10 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ss->stats.list_kernels_ms = pc.enabled ? ms : 0.f;
         cudaEventElapsedTime(&ms, ss->ev[5], ss->ev[1]);
         ss->stats.exact_kernel_ms = ms;
+        for (int i = 0; i < 6; ++i) {
+            ss->stats.sparse_stage_ms[i] = 0.f;
+            if (ss->stats.sparse_used) cudaEventElapsedTime(&ss->stats.sparse_stage_ms[i], ss->sev[i], ss->sev[i + 1]);
+        }
         ss->stats.windows_total = (uint64_t)total_windows;
         ss->stats.windows_listed = counters[2];
         ss->stats.prefilter_used = pc.enabled;
@@ -1205,7 +1283,26 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     // ---- text + download ---------------------------------------------------------------------------
     std::vector<uint8_t> new_leftover;
     bool have_leftover = false;
-    const bool direct_out = ss->stats.sparse_used != 0 && fc->set.f != nullptr;
+    bool direct_out = ss->stats.sparse_used != 0 && fc->set.f != nullptr;
+    if (!direct_out && nrec > 0 && ss->use_direct) {
+        // block-kernel path: order the records on the device and write them as findings into a pinned set
+        const size_t nblocks = (size_t)((counters[2] + kThreads - 1) / kThreads);
+        pinned_release(fc->set);
+        if (pinned_acquire(nrec, ntext, &fc->set) && grow(&ss->d_bpos, &ss->bpos_cap, nblocks + 1)) {
+            ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, fc->set.f, fc->set.fcap, fc->set.t,
+                      input_file_id, ss->m.mission_id};
+            sx_order_scan_kernel<<<1, 1024, 0, st>>>(ss->d_blocks, ss->d_bpos, nblocks);
+            const unsigned wgrid = (unsigned)std::min<size_t>((nblocks + 7) / 8, (size_t)ss->num_sms * 8);
+            sx_order_write_kernel<<<wgrid, 256, 0, st>>>(O, ss->d_blocks, ss->d_bpos, nblocks, nrec);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&fin, ss->d_final, sizeof fin, cudaMemcpyDeviceToHost, st));  // first / last record flags
+            ss->stats.kernel_launches += 2;
+            direct_out = true;
+        } else {
+            cudaGetLastError();
+            pinned_release(fc->set);
+        }
+    }
     if (direct_out) {
         // The findings are already in the collection's pinned set, written by the gather kernel in their final form;
         // only the text (transcoded on the device) is downloaded, straight to the address the findings point to.

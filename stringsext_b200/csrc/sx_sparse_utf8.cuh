@@ -24,8 +24,6 @@
 #pragma once
 #include "sx_exact.cuh"
 #include <algorithm>
-#include <cstdio>
-#include <cstdlib>
 
 namespace sx {
 
@@ -160,8 +158,9 @@ __device__ __forceinline__ Carry sp_member(const ScanParams& P, const SpCtx& c, 
     return r.out;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(kSpThreads, MINB)
+// 6 CTAs of 128 threads per SM (80 registers): measured best for this latency-bound kernel (4: 0.35 ms, 6: 0.29 ms, 8: 0.39 ms
+// before the one-pass heads)
+__global__ void __launch_bounds__(kSpThreads, 6)
 sx_sp_heads_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     SpCtx c;
@@ -338,6 +337,10 @@ __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     __shared__ uint32_t wa[8], wb[8];
+    // direct host output: the CTA's findings are contiguous in the output, so they are assembled in shared memory and
+    // leave as fully coalesced 16-byte stores (large PCIe write transactions instead of one 16-byte store per lane)
+    constexpr uint32_t kStage = 224;
+    __shared__ uint4 sbuf[kStage * 3];
     SpCtx c;
     sp_setup(P, X, B, T, c);
     const long long e = (long long)blockIdx.x * kSpThreads + threadIdx.x;
@@ -373,14 +376,15 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     const unsigned long long br = base.x, bt = base.y;
     const bool fits = (br + tr <= O.rec_cap) && (bt + tt <= O.text_cap) && (O.host_findings == nullptr || br + tr <= O.host_cap);
     if (!fits && threadIdx.x == 0) O.final_state->overflow = 1;
+    const bool host_out = O.host_findings != nullptr;
+    const bool staged_out = host_out && fits && tr <= kStage;
     if (active && fits) {
         uint32_t ro = er, to = et;
-        const bool host_out = O.host_findings != nullptr;
         // the first / last record of the stream: their flags travel in the final state (host-carried text, leftover)
         auto put = [&](unsigned long long idx, const Record& r) {
             O.recs[idx] = r;
             if (host_out) {
-                write_host_finding(O, idx, r);
+                write_host_finding(O, staged_out ? &sbuf[(idx - br) * 3] : reinterpret_cast<uint4*>(O.host_findings + idx), r);
                 if (idx == 0) O.final_state->first_flags = r.flags;
             }
         };
@@ -429,43 +433,33 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
         }
     }
     if (active && e == B.NE - 1) { O.final_state->carry = kout; O.final_state->npend = es->npend; }
+    if (staged_out) {
+        __syncthreads();
+        uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br);
+        for (uint32_t k = threadIdx.x; k < tr * 3; k += kSpThreads) dst[k] = sbuf[k];
+    }
 }
 
+// ev[0..6]: timing events recorded between the stages (the library reports per-stage kernel times in sx_scan_stats)
 inline cudaError_t launch_sparse_utf8_impl(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B, int num_sms,
-                                           cudaStream_t st) {
+                                           cudaStream_t st, cudaEvent_t* ev) {
     const unsigned nb = (unsigned)((B.NE + kSpThreads - 1) / kSpThreads);
     const unsigned pgrid = std::min<unsigned>(nb, (unsigned)num_sms * 4u);
-    static cudaEvent_t dbg[8];
-    static bool dbg_on = getenv("SX_DEBUG_TIMING") != nullptr, dbg_init = false;
-    if (dbg_on && !dbg_init) { for (auto& e : dbg) cudaEventCreate(&e); dbg_init = true; }
-    if (dbg_on) cudaEventRecord(dbg[0], st);
+    cudaEventRecord(ev[0], st);
     sx_sp_tables_kernel<<<8, 256, 0, st>>>(P, B.tables);
     sx_sp_queue_kernel<<<(unsigned)((B.NE + 255) / 256), 256, 0, st>>>(X, B);
-    if (dbg_on) cudaEventRecord(dbg[1], st);
-    {
-        static const int occ = getenv("SX_HEADS_OCC") ? atoi(getenv("SX_HEADS_OCC")) : 6;
-        if (occ == 5) sx_sp_heads_kernel<5><<<nb, kSpThreads, 0, st>>>(P, X, B);
-        else if (occ == 6) sx_sp_heads_kernel<6><<<nb, kSpThreads, 0, st>>>(P, X, B);
-        else if (occ == 8) sx_sp_heads_kernel<8><<<nb, kSpThreads, 0, st>>>(P, X, B);
-        else sx_sp_heads_kernel<4><<<nb, kSpThreads, 0, st>>>(P, X, B);
-    }
-    if (dbg_on) cudaEventRecord(dbg[2], st);
+    cudaEventRecord(ev[1], st);
+    sx_sp_heads_kernel<<<nb, kSpThreads, 0, st>>>(P, X, B);
+    cudaEventRecord(ev[2], st);
     sx_sp_members_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
-    if (dbg_on) cudaEventRecord(dbg[3], st);
+    cudaEventRecord(ev[3], st);
     sx_sp_fix_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
-    if (dbg_on) cudaEventRecord(dbg[4], st);
+    cudaEventRecord(ev[4], st);
     sx_sp_ext_kernel<<<nb, kSpThreads, 0, st>>>(P, X, B);
-    if (dbg_on) cudaEventRecord(dbg[5], st);
+    cudaEventRecord(ev[5], st);
     sx_sp_scan_kernel<<<1, 1024, 0, st>>>(B.btot, nb, O.counters);
     sx_sp_gather_kernel<<<nb, kSpThreads, 0, st>>>(P, O, X, B);
-    if (dbg_on) {
-        cudaEventRecord(dbg[6], st);
-        cudaEventSynchronize(dbg[6]);
-        float t[6];
-        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], dbg[i], dbg[i + 1]);
-        fprintf(stderr, "[sx sparse] tables+queue %.3f heads %.3f members %.3f fix %.3f ext %.3f scan+gather %.3f ms\n", t[0], t[1], t[2],
-                t[3], t[4], t[5]);
-    }
+    cudaEventRecord(ev[6], st);
     return cudaGetLastError();
 }
 constexpr uint32_t kSparseLaunches = 8;

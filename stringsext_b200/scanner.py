@@ -89,6 +89,7 @@ class ScanStats(C.Structure):
         ("windows_listed", C.c_uint64),
         ("host_total_ms", C.c_float),
         ("host_post_ms", C.c_float),
+        ("sparse_stage_ms", C.c_float * 6),
         ("host_phase_ms", C.c_float * 4),
     ]
 
@@ -119,6 +120,7 @@ def load_library():
     L.sx_scanner_state_set_prefilter.argtypes = [C.c_void_p, C.c_int]
     L.sx_scanner_state_set_tma.argtypes = [C.c_void_p, C.c_int]
     L.sx_scanner_state_set_sparse.argtypes = [C.c_void_p, C.c_int]
+    L.sx_scanner_state_set_direct_output.argtypes = [C.c_void_p, C.c_int]
     L.sx_scanner_state_last_window_list.restype = C.c_size_t
     L.sx_scanner_state_last_window_list.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_size_t]
     L.sx_finding_collection_from.restype = C.c_void_p
@@ -159,7 +161,7 @@ def exported_symbols() -> List[str]:
         "sx_device_count", "sx_scanner_state_new", "sx_scanner_state_free", "sx_scanner_state_reset", "sx_scanner_state_consumed_bytes",
         "sx_scanner_state_maybe_cut", "sx_scanner_state_leftover", "sx_finding_collection_from", "sx_scan_stream",
         "sx_fc_len", "sx_fc_get", "sx_fc_data", "sx_fc_first_byte_position", "sx_fc_str_buf_overflow", "sx_fc_free",
-        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_set_sparse", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
+        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_set_sparse", "sx_scanner_state_set_direct_output", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
     ]
 
 
@@ -267,6 +269,10 @@ class ScannerState:
 
     def set_tma(self, enabled: bool) -> None:
         load_library().sx_scanner_state_set_tma(self._h, 1 if enabled else 0)
+
+    def set_direct_output(self, enabled: bool) -> None:
+        """False: records are downloaded and converted on the host instead of being written by the GPU as findings."""
+        load_library().sx_scanner_state_set_direct_output(self._h, 1 if enabled else 0)
 
     def set_sparse(self, enabled: bool) -> None:
         """False: the exact stage always runs as the block kernel (sx_exact_kernel), never as the sparse-list pipeline."""

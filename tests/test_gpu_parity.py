@@ -3,6 +3,7 @@
 Bit-exact bar: identical (position, precision, text, completes) lists in identical order, and an
 identical ScannerState (leftover, cut flag, consumed bytes) after every call.
 """
+import dataclasses
 import os
 import random
 
@@ -290,3 +291,30 @@ def test_sparse_pipeline_matches_block_kernel_and_oracle(n, q, ubf, kind):
         check_state(a, os_)
         check_state(b, os_)
     assert used >= 1 or kind != "rand" or n <= 6  # short minimum lengths list too many windows for the sparse path
+
+
+@pytest.mark.parametrize("enc", [0, 1, 2, 4, 5])
+def test_direct_host_output_matches_record_download(enc):
+    """Findings written by the GPU into the collection's pinned set (both exact-stage variants) == records
+    downloaded and converted on the host == oracle; collections stay valid after later scans (own their set)."""
+    rng = random.Random(900 + enc)
+    kept = []
+    for it in range(6):
+        m = corpus.random_mission(rng, enc, M)
+        m = dataclasses.replace(m, output_line_char_nb_max=64, chars_min_nb=min(m.chars_min_nb, 64))
+        kind = rng.choice(["rand", "mixed", "text"])
+        size = rng.randrange(1, 600000)
+        buf = corpus.gen(rng, kind, size, enc) if kind != "rand" else corpus.sx_mix_bytes(it, 0, size).tobytes()
+        a, b, os_ = sx.ScannerState(m), sx.ScannerState(m), oracle_state(m)
+        b.set_direct_output(False)
+        cut = rng.randrange(0, len(buf) + 1)
+        for part in (buf[:cut], buf[cut:]):
+            fa = a.scan_stream(part, False, 4096)
+            ra, rb = gpu_findings(fa), gpu_findings(b.scan_stream(part, False, 4096))
+            exp = oracle_findings(os_.scan_stream(part, False, 4096)) if len(part) else []
+            assert ra == exp and rb == exp
+            check_state(a, os_)
+            check_state(b, os_)
+            kept.append((fa, exp))
+    for fa, exp in kept:  # earlier collections are untouched by the scans that followed
+        assert gpu_findings(fa) == exp
