@@ -82,9 +82,9 @@ typedef struct sx_finding_collection sx_finding_collection;
 int sx_device_count(void);
 
 /* ScannerState::new (scanner.rs:73-88).  `device`: CUDA ordinal the state's scans run on.
- * Returns NULL (and sets sx_last_error) for missions the kernels do not implement:
- * grep_char != None, require_same_unicode_block, chars_min_nb == 0 or > output_line_char_nb_max,
- * output_line_char_nb_max < 6 (options.rs:33) or > 8192. */
+ * Returns NULL (and sets sx_last_error) for chars_min_nb == 0 and output_line_char_nb_max < 6 (options.rs:33) or
+ * > 8192.  Missions with grep_char, require_same_unicode_block or chars_min_nb > output_line_char_nb_max take the
+ * general automaton on every window (no prefilter). */
 sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device);
 void sx_scanner_state_free(sx_scanner_state*);
 /* Back to the state ScannerState::new leaves (scanner.rs:73-88), keeping the device buffers. */

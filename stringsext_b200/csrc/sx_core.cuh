@@ -176,7 +176,8 @@ struct WinAuto {
     bool grep_ok;    // helper.rs:215: current run holds the grep_char (always true without one)
     bool qfull;      // the run reached q chars; whether it touches the right boundary is known at the next event
     bool dead;       // SplitStr::next returned None (helper.rs:410-415): the rest of the segment is ignored
-    uint32_t last_mb;  // helper.rs:221: lead byte of the run's last multi-byte char (same-unicode-block rule)
+    uint32_t last_mb;  // helper.rs:221: lead byte of the last multi-byte char this SplitStr::next() call saw (may be stale)
+    uint32_t run_mb;   // ... of the current run only: what a re-scan of the run as leftover will see
     uint32_t run_n, run_out;
     int64_t run_in_start, run_in_end;
     // leftover produced by an `again` chunk
@@ -206,7 +207,7 @@ struct WinAuto {
         s1_all_pass = true; s1_later_yield = false; s2_all_pass = true;
         slice_left_present = false; slice_left = carry_none();
         run_n = run_out = 0; run_in_start = run_in_end = 0; run_hostcarry = false;
-        grep_ok = true; qfull = false; dead = false; last_mb = 0;
+        grep_ok = true; qfull = false; dead = false; last_mb = 0; run_mb = 0;
         seg_pos = 0; prec = PREC_EXACT; probe_pending = false; last_cut = false; at_left = true;
     }
     SX_HD bool grep_reset() const { return P->grep_char < 0; }  // helper.rs:215 / :330
@@ -225,7 +226,7 @@ struct WinAuto {
         last_cut = cont;
         at_left = true;
         run_n = 0; run_out = 0; run_hostcarry = false;
-        grep_ok = grep_reset(); last_mb = 0; qfull = false; dead = false;
+        grep_ok = grep_reset(); last_mb = 0; run_mb = 0; qfull = false; dead = false;
         prec = PREC_EXACT;
         probe_pending = probe_possible && (pos == slice_start);
         has_left = false;
@@ -237,6 +238,7 @@ struct WinAuto {
             run_hostcarry = (kin->flags & CF_HOSTCARRY) != 0;
             grep_ok = grep_reset() || (kin->flags & CF_GREP) != 0;
             last_mb = kin->aux;
+            run_mb = kin->aux;
             qfull = run_n >= P->q;  // only possible with a grep_char (helper.rs:389-392)
             prec = PREC_BEFORE;
         }
@@ -268,7 +270,7 @@ struct WinAuto {
         has_left = true;
         left_k = run_n; left_out = run_out; left_in_start = run_in_start; left_hostcarry = run_hostcarry;
         left_grep = grep_ok && P->grep_char >= 0;
-        left_mb = P->same_block ? last_mb : 0u;  // only the same-unicode-block rule reads it
+        left_mb = P->same_block ? run_mb : 0u;  // only the same-unicode-block rule reads it; the leftover is re-scanned from scratch
         cut = false;
         prec = PREC_AFTER;
     }
@@ -276,6 +278,7 @@ struct WinAuto {
         run_n = 0; run_out = 0; run_hostcarry = false;
         grep_ok = grep_reset();
         last_mb = 0;
+        run_mb = 0;
     }
     // The run holds q chars (helper.rs:237 loop exit 2): evaluate the chunk now that `right` is known.
     SX_HD void resolve_qfull(bool right, bool invalid_after) {
@@ -305,7 +308,7 @@ struct WinAuto {
             if (!grep_ok && P->grep_char == (int32_t)lb) grep_ok = true;  // helper.rs:252-254, before the filter
             pass = pass_filter(*P, lb);
         } else if (pass_filter(*P, lb)) {
-            if (!P->same_block || lb == last_mb || last_mb == 0) { last_mb = lb; pass = true; }
+            if (!P->same_block || lb == last_mb || last_mb == 0) { last_mb = lb; run_mb = lb; pass = true; }
             else {
                 // helper.rs:287-292: a passing char of another block ends the run and is scanned again
                 if (m == 1) s1_all_pass = false;
@@ -318,6 +321,7 @@ struct WinAuto {
                 at_left = false;
                 new_run();
                 last_mb = lb;
+                run_mb = lb;
                 pass = true;  // now the first char of a new run
             }
         } else {

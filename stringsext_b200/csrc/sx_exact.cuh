@@ -356,6 +356,12 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             WinDesc dsum;
             const int mode1 = adj_j ? MODE_COUNT : run_mode;
             WindowEngine<Dec>::run(P, ts, g, wj, kin0, mode1, &S.staged[j][0], 0, r, adj_j ? &dsum : nullptr);
+            if (P.general && adj_j && dsum.type == WT_DEP)  // constant iff the flag handed to segment 2 does not matter
+                dsum.type = classify_general(wj, r, [&](const WinGeom& g2) {
+                    WinResult r2;
+                    WindowEngine<Dec>::run(P, ts, g, g2, carry_none(), MODE_STATE, nullptr, 0, r2, nullptr);
+                    return r2.out;
+                });
             if (j == nblk - 1) S.last_npend = r.npend_out;
             if (!adj_j) {
                 S.kin[j] = kin0;

@@ -873,10 +873,9 @@ int sx_device_count(void) {
 sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
     sx_scanner_state* const fail = nullptr;
     if (!m) { set_err(SX_ERR_ARGUMENT, "mission is NULL"); return fail; }
-    if (m->grep_char >= 0) { set_err(SX_ERR_UNSUPPORTED, "grep_char is not implemented by the CUDA scanner yet"); return fail; }
-    if (m->require_same_unicode_block) { set_err(SX_ERR_UNSUPPORTED, "require_same_unicode_block is not implemented by the CUDA scanner yet"); return fail; }
+    if (m->grep_char > 127) { set_err(SX_ERR_ARGUMENT, "grep_char must be an ASCII code (options.rs) or -1"); return fail; }
     if (m->output_line_char_nb_max < 6 || m->output_line_char_nb_max > 8192) { set_err(SX_ERR_UNSUPPORTED, "output_line_char_nb_max must be in 6..8192"); return fail; }
-    if (m->chars_min_nb == 0 || m->chars_min_nb > m->output_line_char_nb_max) { set_err(SX_ERR_UNSUPPORTED, "chars_min_nb must be in 1..output_line_char_nb_max"); return fail; }
+    if (m->chars_min_nb == 0) { set_err(SX_ERR_UNSUPPORTED, "chars_min_nb must be >= 1"); return fail; }
     if (m->encoding_id > SX_ENC_UTF_32BE) { set_err(SX_ERR_ARGUMENT, "unknown encoding_id"); return fail; }
     int n = sx_device_count();
     if (n <= 0) { set_err(SX_ERR_NO_DEVICE, "no CUDA device: the scanner has no CPU fallback"); return fail; }
@@ -1123,9 +1122,22 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     for (size_t i = 0; i < 8 && i < ss->leftover.size(); ++i) P.carry_text8[i] = ss->leftover[i];
     P.carry_text_len = (uint32_t)ss->leftover.size();
     if (ss->cut) P.k0 = carry_cut();
-    else if (!ss->leftover.empty()) P.k0 = Carry{K_L, CF_HOSTCARRY, (uint16_t)utf8_char_count(ss->leftover), (uint32_t)ss->npend, 0};
-    else P.k0 = carry_none();
-    P.grep_char = -1; P.same_block = 0; P.general = 0;  // such missions are rejected by sx_scanner_state_new for now
+    else if (!ss->leftover.empty()) {
+        // the leftover is re-scanned in front of the next buffer (finding_collection.rs:214-221): what that scan would
+        // remember of it -- does it hold the grep char (helper.rs:252-254), its last multi-byte lead byte (helper.rs:221)
+        uint8_t fl = CF_HOSTCARRY;
+        uint32_t last_lead = 0;
+        for (uint8_t b : ss->leftover) {
+            if (ss->m.grep_char >= 0 && b == (uint8_t)ss->m.grep_char) fl |= CF_GREP;
+            if (b >= 0xC0) last_lead = b;
+        }
+        P.k0 = Carry{K_L, fl, (uint16_t)utf8_char_count(ss->leftover), (uint32_t)ss->npend, 0,
+                     ss->m.require_same_unicode_block ? last_lead : 0u};
+    } else P.k0 = carry_none();
+    // --grep-char / --same-unicode-block / chars_min_nb > q: the general automaton (sx_core.cuh WinAuto) on every window
+    P.grep_char = ss->m.grep_char >= 0 ? (int32_t)ss->m.grep_char : -1;
+    P.same_block = ss->m.require_same_unicode_block ? 1u : 0u;
+    P.general = (P.grep_char >= 0 || P.same_block || P.n > P.q) ? 1u : 0u;
     memcpy(P.sb_table, ss->m.sb_table, sizeof P.sb_table);
 
     long long total_windows;
@@ -1137,7 +1149,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     if (total_windows > 0x7FFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
     PrefCfg pc = make_pref_cfg(P, in_aligned16);
-    if (!ss->use_prefilter) pc.enabled = 0;
+    if (!ss->use_prefilter || P.general) pc.enabled = 0;  // the prefilter's proofs are for the plain min-length rule
     const long long ntiles = (total_windows + kPrefTileWin - 1) / kPrefTileWin;
     const long long max_blocks = (total_windows + kThreads - 1) / kThreads;
 

@@ -144,3 +144,14 @@ def random_mission(rng: random.Random, enc: int, M):
     if enc == 0 and rng.random() < 0.5:
         ubf = M.UBF_NONE
     return M.Mission.for_label(label, n, af, ubf, None, q, counter_offset=rng.choice([0, 10000]))
+
+
+def random_general_mission(rng: random.Random, enc: int, M):
+    """Missions with --grep-char and / or --same-unicode-block."""
+    import dataclasses
+
+    m = random_mission(rng, enc, M)
+    kind = rng.choice(["grep", "same", "both"])
+    grep = rng.choice([0x20, ord("a"), ord("e"), ord(":"), ord("?"), 0x00]) if kind in ("grep", "both") else None
+    filt = dataclasses.replace(m.filter, grep_char=grep)
+    return dataclasses.replace(m, filter=filt, require_same_unicode_block=kind in ("same", "both"))

@@ -66,6 +66,14 @@ def lib():
     return _lib
 
 
+def last_multibyte_lead(s: bytes) -> int:
+    """Lead byte of the last multi-byte char of a UTF-8 string, 0 if none (helper.rs:221, same-unicode-block rule)."""
+    for b in reversed(s):
+        if b >= 0xC0:
+            return b
+    return 0
+
+
 def char_count(s: bytes) -> int:
     return sum(1 for b in s if (b & 0xC0) != 0x80)
 
@@ -106,9 +114,10 @@ class EmulState:
         P.af_hi = (m.filter.af >> 64) & 0xFFFFFFFFFFFFFFFF
         P.ubf = m.filter.ubf
         P.base_consumed = self.consumed
-        P.grep_char = -1
-        P.same_block = 0
-        P.general = 0
+        gc = m.filter.grep_char
+        P.grep_char = -1 if gc is None else gc
+        P.same_block = 1 if m.require_same_unicode_block else 0
+        P.general = 1 if (gc is not None or m.require_same_unicode_block or m.chars_min_nb > m.output_line_char_nb_max) else 0
         P.npend = len(self.pend)
         P.is_last = 1 if is_last else 0
         for i, b in enumerate(self.pend):
@@ -119,7 +128,8 @@ class EmulState:
         if self.cut:
             P.k0 = Carry(1, 0, 0, 0, 0, 0)
         elif self.leftover:
-            P.k0 = Carry(0, 1, char_count(self.leftover), len(self.pend), 0, 0)
+            P.k0 = Carry(0, 1 | (2 if (gc is not None and gc in self.leftover) else 0), char_count(self.leftover), len(self.pend), 0,
+                         last_multibyte_lead(self.leftover) if m.require_same_unicode_block else 0)
         else:
             P.k0 = Carry(0, 0, 0, 0, 0, 0)
         if m.sb_table is not None:

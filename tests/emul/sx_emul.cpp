@@ -63,7 +63,7 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
     const int64_t rest = P.len - full * (int64_t)P.slice_len;
     const int64_t total = full * geo.wps + (rest + P.W - 1) / P.W;
     PrefCfg pc = make_pref_cfg(P, true);
-    if (!use_pref) pc.enabled = 0;
+    if (!use_pref || P.general) pc.enabled = 0;  // general missions: every window goes through the exact stage
     stats[7] = pc.enabled;
     list.clear();
     if (pc.enabled) {
@@ -110,6 +110,12 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         WinResult r0;
         WinDesc d;
         WindowEngine<Dec>::run(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, r0, &d);
+        if (P.general && d.type == WT_DEP)  // grep_char / same block / n > q: constant iff the flag handed to segment 2 does not matter
+            d.type = classify_general(wg, r0, [&](const WinGeom& g2) {
+                WinResult r2;
+                WindowEngine<Dec>::run(P, ts, g, g2, carry_none(), MODE_STATE, nullptr, 0, r2, nullptr);
+                return r2.out;
+            });
         WinResult rs;
         WindowEngine<Dec>::run(P, ts, g, wg, kin, MODE_STATE, nullptr, 0, rs, nullptr);
         Carry kout;

@@ -60,6 +60,25 @@ def test_fuzz(enc, seed):
         assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
 
 
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+def test_fuzz_general_missions(enc):
+    """--grep-char / --same-unicode-block: general automaton + dual-simulation classification (classify_general)."""
+    rng = random.Random(31337 + enc)
+    for _ in range(50):
+        m = corpus.random_general_mission(rng, enc, M)
+        slice_len = rng.choice([4096, 4096, 1024, 256, 100, 33, 8192])
+        es, os_ = emul.EmulState(m), oracle_state(m)
+        ncalls = rng.choice([1, 1, 2, 3])
+        for c in range(ncalls):
+            ln = rng.choice([0, 1, 2, 3, 5, 50, 500, 5000]) if rng.random() < 0.5 else rng.randrange(1, 9000)
+            buf = corpus.gen(rng, rng.choice(corpus.KINDS), ln, enc)
+            last = (c == ncalls - 1) and rng.random() < 0.3
+            f, _ = es.scan_stream(buf, last, slice_len)
+            o = os_.scan_stream(buf, last, slice_len).v if ln else []
+            _cmp(es, os_, f, o)
+        assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
+
+
 def test_planted_corpus_utf16():
     """Random bytes + planted UTF-16 strings (random alone yields nothing)."""
     for enc, label in ((2, "utf-16le"), (3, "utf-16be")):

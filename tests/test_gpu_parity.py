@@ -39,7 +39,7 @@ def test_library_is_the_cuda_one():
     assert st.last_stats.kernel_launches >= 1
 
 
-@pytest.mark.parametrize("name,mission_factory,calls", [s for s in RV.SCENARIOS if "grep" not in s[0]],
+@pytest.mark.parametrize("name,mission_factory,calls", RV.SCENARIOS,
                          ids=lambda v: v.split(" ")[0] if isinstance(v, str) else None)
 def test_reference_unit_vectors(name, mission_factory, calls):
     """scanner.rs:193-531, finding_collection.rs:431-502 through FindingCollection::from on the GPU."""
@@ -63,9 +63,52 @@ def test_reference_unit_vectors(name, mission_factory, calls):
 
 
 def test_unsupported_missions_fail_loudly():
+    import dataclasses as dc
+
     with pytest.raises(sx.ScannerError) as e:
-        sx.ScannerState(RV.SCENARIOS[3][1]())  # grep_char = 42
+        sx.ScannerState(dc.replace(RV.SCENARIOS[0][1](), output_line_char_nb_max=5))  # options.rs:33: q >= 6
     assert e.value.code == 3
+
+
+@pytest.mark.parametrize("n,q,grep,files,expected", [
+    (None, 16, 63, ["input1"], "expected_output1"),
+    (10, 32, 58, ["input1", "input2"], "expected_output2"),
+], ids=["golden1", "golden2"])
+def test_cli_golden_1_2(golden_dir, n, q, grep, files, expected):
+    """run-tests:11-30 (--grep-char, three encodings, multi-file): scanned on the GPU, merged and printed like
+    main.rs:103-141 / finding.rs:112-155 -> the reference's golden files byte for byte."""
+    missions = [M.Mission.for_label(lbl, n, M.AF_ALL & ~M.AF_CTRL, M.UBF_COMMON, grep, q, mission_id=i)
+                for i, lbl in enumerate(["UTF-8", "utf-16le", "utf-16be"])]
+    states = [sx.ScannerState(m) for m in missions]
+    out = bytearray(b"\xef\xbb\xbf")
+    for fid, name in enumerate(files, start=1):
+        data = open(os.path.join(golden_dir, name), "rb").read()
+        # the merge is per 4096-byte slice batch in the reference (main.rs:118-136); positions are monotone within a
+        # mission, so merging the whole file's collections gives the same order
+        fcs = [s.scan_stream(data, False, 4096, fid) for s in states]
+        for f in sx.merge(fcs):
+            out += f.print(len(files), 3, "x")
+    out += b"\n"
+    assert bytes(out) == open(os.path.join(golden_dir, expected), "rb").read()
+
+
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+def test_differential_fuzz_general_missions(enc):
+    """--grep-char / --same-unicode-block on the GPU vs the oracle."""
+    rng = random.Random(5150 + enc)
+    for _ in range(25):
+        m = corpus.random_general_mission(rng, enc, M)
+        slice_len = rng.choice([4096, 4096, 1024, 256, 100, 8192])
+        gs, os_ = sx.ScannerState(m), oracle_state(m)
+        ncalls = rng.choice([1, 2, 3])
+        for c in range(ncalls):
+            ln = rng.choice([0, 1, 3, 50, 5000]) if rng.random() < 0.4 else rng.randrange(1, 70000)
+            buf = corpus.gen(rng, rng.choice(corpus.KINDS), ln, enc)
+            last = (c == ncalls - 1) and rng.random() < 0.3
+            got = gpu_findings(gs.scan_stream(buf, last, slice_len))
+            exp = oracle_findings(os_.scan_stream(buf, last, slice_len)) if ln else []
+            assert got == exp, (enc, m, slice_len, ln, last)
+            check_state(gs, os_)
 
 
 def test_field_with_zeros():
