@@ -781,7 +781,10 @@ struct sx_scanner_state {
     cudaEvent_t sev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // sparse pipeline stages
     int num_sms = 0;
     double rec_per_byte = 1.0 / 1024, text_per_byte = 1.0 / 64;
-    size_t host_rec_hint = 1u << 20, host_text_hint = 16u << 20;  // direct host output: first-call sizes of the pinned set
+    // direct host output: cap on the pinned set of a state's FIRST scan (the estimate from rec_per_byte is generous
+    // until a scan has been seen; an overflow simply reruns the exact stage with the counted sizes)
+    size_t host_rec_hint = 1u << 20, host_text_hint = 16u << 20;
+    bool have_history = false;
     sx_scan_stats stats;
 };
 
@@ -1164,6 +1167,10 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     size_t need_recs_min = 0, need_text_min = 0;  // after an overflow: what the device counted
     unsigned long long counters[4] = {0, 0, 0, 0};
     FinalState fin;
+    // bytes that stay inside the decoder: the last npend bytes of (old pend ++ buffer)
+    uint8_t tail[8] = {0};
+    const size_t tail_n = std::min<size_t>(8, len);
+    if (!buf_is_device) memcpy(tail + 8 - tail_n, (const uint8_t*)buf + len - tail_n, tail_n);
     for (int attempt = 0;; ++attempt) {
         if (!grow(&ss->d_recs, &ss->rec_cap, need_recs)) return fail;
         if (!grow(&ss->d_text, &ss->text_cap, need_text)) return fail;
@@ -1224,8 +1231,8 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
                 if (!grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes())) return fail;
                 if (!grow(&ss->d_queue, &ss->queue_cap, (2 * (size_t)ne + 128) * sizeof(uint32_t))) return fail;
                 // direct host output: the gather kernel writes the findings in their C-ABI form into a pinned set
-                const size_t want_f = !ss->use_direct ? 0 : std::min(need_recs, std::max(ss->host_rec_hint, need_recs_min));
-                const size_t want_t = std::min(need_text, std::max(ss->host_text_hint, need_text_min));
+                const size_t want_f = !ss->use_direct ? 0 : (ss->have_history ? need_recs : std::min(need_recs, std::max(ss->host_rec_hint, need_recs_min)));
+                const size_t want_t = ss->have_history ? need_text : std::min(need_text, std::max(ss->host_text_hint, need_text_min));
                 if (ss->use_direct) {
                     if (fc->set.fcap < want_f || fc->set.tcap < want_t) {
                         pinned_release(fc->set);
@@ -1249,6 +1256,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         }
         CK(cudaEventRecord(ss->ev[1], st));
         ss->stats.host_phase_ms[0] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        if (buf_is_device) CK(cudaMemcpyAsync(tail + 8 - tail_n, d_in + len - tail_n, tail_n, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(counters, ss->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&fin, ss->d_final, sizeof fin, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1287,6 +1295,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     }
     const size_t nrec = (size_t)counters[0];
     const size_t ntext = (size_t)counters[1];
+    ss->have_history = true;
     ss->rec_per_byte = std::max(1.0 / 4096, 1.3 * (double)nrec / (double)len);
     ss->text_per_byte = std::max(1.0 / 256, 1.3 * (double)ntext / (double)len);
     ss->stats.n_records = nrec;
@@ -1315,8 +1324,10 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             pinned_release(fc->set);
         }
     }
-    if (direct_out) {
-        // The findings are already in the collection's pinned set, written by the gather kernel in their final form;
+    // sparse pipeline: the gather kernel also wrote the finding text (UTF-8: the input bytes) into the pinned set
+    const bool text_on_host = direct_out && ss->stats.sparse_used != 0;
+    if (direct_out && !text_on_host) {
+        // The findings are already in the collection's pinned set, written by the device in their final form;
         // only the text (transcoded on the device) is downloaded, straight to the address the findings point to.
         if (nrec) {
             const int mgrid = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ss->num_sms * 8);
@@ -1329,18 +1340,14 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             ss->stats.d2h_bytes += nrec * sizeof(sx_finding) + ntext;
         }
     }
-    // bytes that stay inside the decoder: the last npend bytes of (old pend ++ buffer)
-    uint8_t tail[8] = {0};
-    const size_t tail_n = std::min<size_t>(8, len);
     if (direct_out) {
-        if (buf_is_device) CK(cudaMemcpyAsync(tail + 8 - tail_n, d_in + len - tail_n, tail_n, cudaMemcpyDeviceToHost, st));
-        else memcpy(tail + 8 - tail_n, (const uint8_t*)buf + len - tail_n, tail_n);
-        CK(cudaStreamSynchronize(st));
-        if (nrec) {
+        if (!text_on_host) CK(cudaStreamSynchronize(st));
+        if (nrec && !text_on_host) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ss->ev[2], ss->ev[3]);
             ss->stats.materialize_kernel_ms = ms;
         }
+        if (text_on_host) ss->stats.d2h_bytes += nrec * sizeof(sx_finding) + ntext;
         const auto t_post = std::chrono::steady_clock::now();
         ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - t_begin).count();
         const bool tail_is_leftover = nrec > 0 && (fin.last_flags & RF_LEFTOVER) != 0;
@@ -1388,8 +1395,6 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         else CK(cudaMemcpyAsync(ss->h_blocks, ss->d_blocks, nblocks * sizeof(uint2), cudaMemcpyDeviceToHost, st));
         ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + (sparse_out ? 0 : nblocks * sizeof(uint2));
     }
-    if (buf_is_device) CK(cudaMemcpyAsync(tail + 8 - tail_n, d_in + len - tail_n, tail_n, cudaMemcpyDeviceToHost, st));
-    else memcpy(tail + 8 - tail_n, (const uint8_t*)buf + len - tail_n, tail_n);
     CK(cudaStreamSynchronize(st));
     if (nrec) {
         float ms = 0;

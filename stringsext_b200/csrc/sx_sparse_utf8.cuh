@@ -341,6 +341,9 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     // leave as fully coalesced 16-byte stores (large PCIe write transactions instead of one 16-byte store per lane)
     constexpr uint32_t kStage = 224;
     __shared__ uint4 sbuf[kStage * 3];
+    // ... and so is their text (UTF-8 -> UTF-8: the bytes of the input range), written to the host the same way
+    constexpr uint32_t kTextStage = 4096;
+    __shared__ __align__(16) uint8_t tbuf[kTextStage];
     SpCtx c;
     sp_setup(P, X, B, T, c);
     const long long e = (long long)blockIdx.x * kSpThreads + threadIdx.x;
@@ -378,6 +381,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     if (!fits && threadIdx.x == 0) O.final_state->overflow = 1;
     const bool host_out = O.host_findings != nullptr;
     const bool staged_out = host_out && fits && tr <= kStage;
+    const bool text_staged = host_out && fits && tt <= kTextStage;
+    uint8_t* const host_text = const_cast<uint8_t*>(O.host_text);
     if (active && fits) {
         uint32_t ro = er, to = et;
         // the first / last record of the stream: their flags travel in the final state (host-carried text, leftover)
@@ -386,6 +391,7 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
             if (host_out) {
                 write_host_finding(O, staged_out ? &sbuf[(idx - br) * 3] : reinterpret_cast<uint4*>(O.host_findings + idx), r);
                 if (idx == 0) O.final_state->first_flags = r.flags;
+                transcode_range(P, c.g, r.in_start, r.in_len, text_staged ? tbuf + (r.text_off - bt) : host_text + r.text_off);
             }
         };
         if (cr) {
@@ -433,10 +439,28 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
         }
     }
     if (active && e == B.NE - 1) { O.final_state->carry = kout; O.final_state->npend = es->npend; }
+    if (staged_out || text_staged) __syncthreads();
     if (staged_out) {
-        __syncthreads();
         uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br);
         for (uint32_t k = threadIdx.x; k < tr * 3; k += kSpThreads) dst[k] = sbuf[k];
+    }
+    if (text_staged && tt) {
+        // [bt, bt + tt) of the text arena: bytes up to the first 16-byte boundary, aligned 16-byte body, tail bytes
+        uint8_t* const dst = host_text + bt;
+        const uint32_t head = (uint32_t)((16u - (uint32_t)(reinterpret_cast<unsigned long long>(dst) & 15u)) & 15u);
+        const uint32_t h = head < tt ? head : tt;
+        const uint32_t body = (tt - h) >> 4;
+        for (uint32_t k = threadIdx.x; k < h; k += kSpThreads) dst[k] = tbuf[k];
+        for (uint32_t k = threadIdx.x; k < body; k += kSpThreads) {
+            const uint8_t* sp = tbuf + h + 16u * k;  // shared memory is byte addressable: assemble the 16 bytes
+            uint4 v;
+            v.x = sp[0] | (sp[1] << 8) | (sp[2] << 16) | ((uint32_t)sp[3] << 24);
+            v.y = sp[4] | (sp[5] << 8) | (sp[6] << 16) | ((uint32_t)sp[7] << 24);
+            v.z = sp[8] | (sp[9] << 8) | (sp[10] << 16) | ((uint32_t)sp[11] << 24);
+            v.w = sp[12] | (sp[13] << 8) | (sp[14] << 16) | ((uint32_t)sp[15] << 24);
+            *reinterpret_cast<uint4*>(dst + h + 16u * k) = v;
+        }
+        for (uint32_t k = h + 16u * body + threadIdx.x; k < tt; k += kSpThreads) dst[k] = tbuf[k];
     }
 }
 
