@@ -146,6 +146,9 @@ struct WinResult {
     int32_t npend_out;  // bytes still inside the decoder at the window end
     uint32_t m;         // segments in the window
     uint32_t cut1;      // carry flag handed from segment 1 to segment 2
+    // mask engine: caseb != 0: the window is ONE run of `a` (< q) passing chars with `t_out` text bytes covering it
+    // completely, so its carry-out follows eval_caseb() from any carry-in (WinDesc WT_CASEB without a pass)
+    uint16_t caseb, a, t_out;
 };
 
 // MODE_BUFFER: count, and also write the first kBufRecs records (text_off relative to the window's first

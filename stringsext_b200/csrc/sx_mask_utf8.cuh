@@ -407,7 +407,20 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
 
     // The Precision::Before probe (finding_collection.rs:176-207) can only change the precision of a finding of a
     // segment that starts at the slice start; with no leftover and a neutral decoder it changes nothing.
-    const bool probe_seg1 = at_slice_start && mode != MODE_STATE && k_in == 0 && pend0 > 0;
+    // First segment of a slice with bytes pending from the previous slice and no leftover: the probe fires at the
+    // segment's first char if that char is multi-byte -- i.e. iff the pending sequence completes (a broken one starts
+    // a second segment at offset 0 instead) -- and then says Before (finding_collection.rs:183-207: the fresh decoder
+    // of the probe starts on a continuation byte and writes nothing).
+    bool straddle_completes = false;
+    if (pend0 > 0) {
+#pragma unroll
+        for (uint32_t p = 0; p < 3; ++p) {
+            if (!m5_bit(acc, 32 + p) || (int32_t)p >= wlen) break;
+            if (!m5_bit(pendm, 32 + p)) { straddle_completes = true; break; }
+        }
+    }
+    const bool seg1_before = k_in > 0 || (at_slice_start && pend0 > 0 && straddle_completes);
+    const bool probe_seg1 = false;
     const bool probe_seg0 = at_slice_start && mode != MODE_STATE && k_in > 0;  // second segment at the slice start
     const uint32_t lo_flags = (k_in > 0 && (kin.flags & CF_HOSTCARRY)) ? (uint32_t)RF_HOSTCARRY : 0u;
 
@@ -418,6 +431,7 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
     // completes a cut finding (finding_collection.rs:255-290).  Returns false to decline.
     res.out = carry_none();
     res.cut1 = 0;  // here: 1 when the carry-out depends on the carry-in (see below)
+    res.caseb = 0; res.a = 0; res.t_out = 0;
     bool carry_done = false;
     auto do_run = [&](int32_t sB, uint32_t eB, bool is_left, bool touches_end) -> bool {
         const uint32_t fromB = sB < 32 ? 32u : (uint32_t)sB;  // chars are counted at their last byte
@@ -434,7 +448,7 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
         const uint32_t fl0 = (is_left ? lo_flags : 0u) | (lastcut0 ? (uint32_t)RF_COMPLETES : 0u);
         const bool yields = total >= q || (touches_end ? lastcut0 : (lastcut0 || total >= n));
         if (yields && ((seg_id == 0 && probe_seg0) || (seg_id < 0 && probe_seg1))) return false;
-        uint32_t prec = (seg_id == last_seg) ? PREC_AFTER : ((seg_id < 0 && k_in > 0) ? PREC_BEFORE : PREC_EXACT);
+        uint32_t prec = (seg_id == last_seg) ? PREC_AFTER : ((seg_id < 0 && seg1_before) ? PREC_BEFORE : PREC_EXACT);
         const int32_t seg_rel = seg_id < 0 ? 0 : seg_id;
         if (yields) last_seg = seg_id;
         if (total < q) {
@@ -493,7 +507,13 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
         // The carry-in only acts through this run (its char count decides where the forced cuts fall and whether a
         // "maybe cut" flag outlives it).  A run that covers the window and holds >= q chars by itself always ends
         // in a cut at the window end; in every other case the carry-out may depend on the carry-in.
-        res.cut1 = (e_last + 1 >= Bend && m5_count(pe, 32, e_last) >= q) ? 0u : 1u;
+        const uint32_t inwin = m5_count(pe, 32, e_last);
+        res.cut1 = (e_last + 1 >= Bend && inwin >= q) ? 0u : 1u;
+        if (e_last + 1 >= Bend && inwin < q) {  // one run covering the window: closed-form transfer function
+            res.caseb = 1;
+            res.a = (uint16_t)inwin;
+            res.t_out = (uint16_t)(Bend - 32u + (uint32_t)pend0);
+        }
     } else if (k_in >= n) {
         // the leftover alone is long enough: printed at the first event of the window
         mask_emit(E, 0, PREC_BEFORE, -(int32_t)kin.in_bytes, -pend0, lo_flags);

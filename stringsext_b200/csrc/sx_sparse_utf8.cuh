@@ -12,7 +12,8 @@
 //   sx_sp_members_kernel members, in parallel: carry-in = carry-out of the entry before, taken from a resolved head or
 //                        recomputed from that window alone when it does not depend on ITS carry-in
 //   sx_sp_fix_kernel     the rest, few: heads the mask engine declined (byte-wise engine), members behind a
-//                        carry-dependent window (walked in order)
+//                        carry-dependent window (walked in order; a window that is one short run is passed in closed
+//                        form, eval_caseb, and resolved afterwards by sx_sp_late_kernel, in parallel)
 //   sx_sp_ext_kernel     extension windows (a "cut" / long leftover carry reaching an unlisted successor),
 //                        per-entry totals -> per-CTA totals
 //   sx_sp_scan_kernel    exclusive scan of the per-CTA totals
@@ -34,8 +35,14 @@ struct EntryState {
     uint32_t xcnt_r, xcnt_t;  // ... of the extension window
     uint8_t status;
     int8_t npend;             // bytes inside the decoder at the window end
-    uint16_t pad0;
+    uint8_t resolved;         // kin / kout / counts / staged records are final
+    uint8_t kin_known;        // sx_sp_fix_kernel: kin is final, the window itself is resolved by sx_sp_late_kernel
+    // closed-form transfer function of the window (written by the thread of the NEXT entry, sx_sp_members_kernel):
+    // one run of d_a (< q) passing chars with d_t text bytes covering the window, eval_caseb()
+    uint16_t d_a, d_t;
+    uint32_t d_caseb;
     uint32_t pad1;
+    Carry d_null;
     Record staged[kBufRecs];
     Record xstaged[kBufRecs];
 };
@@ -79,6 +86,7 @@ __device__ __forceinline__ void sp_store(EntryState* es, const Carry& kin, const
     es->cnt_r = r.nrec;
     es->cnt_t = r.ntext;
     es->npend = (int8_t)r.npend_out;
+    es->resolved = 1;
     if (es->status == ES_PENDING) es->status = ES_DONE;  // sx_sp_fix_kernel leaves DECLINED / DEPENDENT as they are
 }
 // a head (predecessor window not listed) with the byte-wise engine: pre-roll, then one pass under the real carry
@@ -121,6 +129,9 @@ sx_sp_queue_kernel(const ExactCfg X, const SparseBufs B) {
         es->xcnt_r = 0;
         es->xcnt_t = 0;
         es->status = ES_PENDING;
+        es->resolved = 0;
+        es->kin_known = 0;
+        es->d_caseb = 0;
         member = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
     }
     sp_push(B.queue, B.qcount, member, (uint32_t)e);
@@ -203,8 +214,13 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
                 WinGeom pg;
                 c.geo.window(w - 1, pg);
                 WinResult rr;
-                known = utf8_mask_window(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr) && rr.cut1 == 0;
+                const bool ok = utf8_mask_window(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr);
+                known = ok && rr.cut1 == 0;
                 kin = rr.out;
+                if (ok && rr.caseb) {  // the walk of sx_sp_fix_kernel gets through that window without a pass
+                    EntryState* const pe = &B.E[e - 1];
+                    pe->d_a = rr.a; pe->d_t = rr.t_out; pe->d_null = rr.out; pe->d_caseb = 1;
+                }
             }
             if (known) sp_member(P, c, w, kin, &B.E[e]);
             else { B.E[e].status = ES_DEPENDENT; dependent = true; }
@@ -239,13 +255,39 @@ sx_sp_fix_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
         Carry kin = B.E[e - 1].kout;
         long long m = e, wm = w;
         for (;;) {
-            kin = sp_member(P, c, wm, kin, &B.E[m]);
+            EntryState* const es = &B.E[m];
+            if (es->d_caseb) {
+                // one short run covering the window: its carry-out follows in closed form, the window itself (its
+                // findings under this carry-in) is left to sx_sp_late_kernel, in parallel with the others
+                es->kin = kin;
+                es->kin_known = 1;
+                WinDesc d;
+                d.type = WT_CASEB; d.pad = 0; d.a = es->d_a; d.t_out = es->d_t; d.nrec = 0; d.ntext = 0; d.null_out = es->d_null;
+                WinGeom wg;
+                c.geo.window(wm, wg);
+                kin = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws));
+            } else kin = sp_member(P, c, wm, kin, es);
             ++m;
             if (m >= B.NE || B.E[m].status != ES_DEPENDENT) break;
             const long long wn = list_window(X, X.cta_off, m);
             if (wn != wm + 1) break;
             wm = wn;
         }
+    }
+}
+
+// members whose carry-in sx_sp_fix_kernel settled in closed form: resolved here, all at once
+__global__ void __launch_bounds__(kSpThreads, 4)
+sx_sp_late_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
+    __shared__ Utf8Tables T;
+    SpCtx c;
+    sp_setup(P, X, B, T, c);
+    const unsigned long long nq = *B.qcount2;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * kSpThreads + threadIdx.x; t < nq;
+         t += (unsigned long long)gridDim.x * kSpThreads) {
+        const long long e = (long long)B.queue2[t];
+        EntryState* const es = &B.E[e];
+        if (es->kin_known && !es->resolved) sp_member(P, c, list_window(X, X.cta_off, e), es->kin, es);
     }
 }
 
@@ -478,6 +520,7 @@ inline cudaError_t launch_sparse_utf8_impl(const ScanParams& P, const ScanOut& O
     sx_sp_members_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[3], st);
     sx_sp_fix_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
+    sx_sp_late_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[4], st);
     sx_sp_ext_kernel<<<nb, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[5], st);
@@ -486,6 +529,6 @@ inline cudaError_t launch_sparse_utf8_impl(const ScanParams& P, const ScanOut& O
     cudaEventRecord(ev[6], st);
     return cudaGetLastError();
 }
-constexpr uint32_t kSparseLaunches = 8;
+constexpr uint32_t kSparseLaunches = 9;
 
 }  // namespace sx

@@ -142,6 +142,23 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
                 }
             }
         }
+        if (P.enc == ENC_UTF8 && !P.general && g_use_mask && g_use_fast) {
+            // the sparse pipeline's closed form for windows that are one short run (WinResult.caseb of a pass under the
+            // null carry): eval_caseb from the real carry-in must give the real carry-out
+            WinResult rn;
+            if (utf8_mask_window(P, ts, wg, carry_none(), MODE_STATE, nullptr, 0, rn) && rn.caseb) {
+                WinDesc dc;
+                dc.type = WT_CASEB; dc.pad = 0; dc.a = rn.a; dc.t_out = rn.t_out; dc.nrec = 0; dc.ntext = 0; dc.null_out = rn.out;
+                const Carry ke = eval_caseb(P, dc, kin, (uint32_t)(wg.we - wg.ws));
+                if (memcmp(&ke, &rs.out, sizeof(Carry)) != 0) {
+                    stats[3] += 10000000;
+                    if (g_mask_mismatch++ < 5)
+                        fprintf(stderr, "caseb closed form mismatch: window [%lld,%lld) kin kind=%d k=%d -> kind %d/%d k %d/%d in %u/%u out %u/%u\n",
+                                (long long)wg.ws, (long long)wg.we, kin.kind, kin.k, ke.kind, rs.out.kind, ke.k, rs.out.k, ke.in_bytes,
+                                rs.out.in_bytes, ke.out_bytes, rs.out.out_bytes);
+                }
+            }
+        }
         if (!needs_emit(P, d, kin) && rc.nrec != 0) stats[4]++;
         if (carry_is_null(kin) && d.nrec != 0xFFFF && (rc.nrec != d.nrec || rc.ntext != d.ntext)) stats[5]++;
         last_npend = rs.npend_out;
