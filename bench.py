@@ -227,6 +227,8 @@ def main():
     ap.add_argument("--e2e-max-mib", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--as-rank", type=int, default=-1, help="debug: single process scanning rank R's encoding of the --gpus config")
+    ap.add_argument("--sparse-mode", type=int, default=1, help="debug: 0 block kernel only, 1 default, 2 sparse pipeline whenever possible")
+    ap.add_argument("--corpus", default="random", help="debug: 'text' = UTF-8 text (repeated 4 MiB block) instead of random bytes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -260,7 +262,19 @@ def main():
         dbuf[off : off + len(s)] = torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda()
     torch.cuda.synchronize()
 
+    if args.corpus == "text":
+        import random as _r
+
+        import corpus as _c
+
+        blk = _c.gen(_r.Random(7), "text", 4 << 20, mission.encoding_id)
+        tblk = torch.frombuffer(bytearray(blk), dtype=torch.uint8).cuda()
+        for off in range(0, size, len(blk)):
+            n = min(len(blk), size - off)
+            dbuf[off : off + n] = tblk[:n]
+        torch.cuda.synchronize()
     ss_dev = sx.ScannerState(mission, local)
+    ss_dev.set_sparse(args.sparse_mode)
 
     def step_device():
         ss_dev.reset()  # ScannerState::new semantics per pass (same work every step), device buffers are reused

@@ -151,7 +151,9 @@ void sx_scanner_state_last_stats(const sx_scanner_state*, sx_scan_stats* out);
 /* Tuning / test hooks.  The prefilter never changes results (tests compare both settings). */
 void sx_scanner_state_set_prefilter(sx_scanner_state*, int enabled);
 void sx_scanner_state_set_tma(sx_scanner_state*, int enabled); /* 0: stage tiles with plain vector loads */
-void sx_scanner_state_set_sparse(sx_scanner_state*, int enabled); /* 0: always the block kernel for the exact stage */
+void sx_scanner_state_set_sparse(sx_scanner_state*, int mode); /* 0: always the block kernel for the exact stage; 1 (default):
+                                                                 * UTF-8 missions take the per-stage pipeline whenever its
+                                                                 * per-entry state fits in memory */
 void sx_scanner_state_set_direct_output(sx_scanner_state*, int enabled); /* 0: download records, convert on the host */
 /* Copies the window list the prefilter built in the most recent call (ascending window indices,
  * window = decoder_input_window of finding_collection.rs:120-131) into out[0..cap); returns the

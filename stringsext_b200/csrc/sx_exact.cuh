@@ -19,6 +19,7 @@ struct FinalState {
     int32_t npend;
     uint32_t overflow;
     uint32_t first_flags, last_flags;  // RF_* of the first / last record in stream order (direct host output only)
+    uint32_t text_fallback;            // sparse pipeline: some CTA left its text to the device arena (materialize + download)
 };
 
 struct ScanOut {

@@ -433,6 +433,9 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
     res.cut1 = 0;  // here: 1 when the carry-out depends on the carry-in (see below)
     res.caseb = 0; res.a = 0; res.t_out = 0;
     bool carry_done = false;
+    bool has_left = false;       // a run continues what touches the left boundary and ends inside the window at left_end
+    uint32_t left_end = 0;
+    bool seg1_cleared = false;   // ... and a later event of the first segment resets the "maybe cut" flag it may leave behind
     auto do_run = [&](int32_t sB, uint32_t eB, bool is_left, bool touches_end) -> bool {
         const uint32_t fromB = sB < 32 ? 32u : (uint32_t)sB;  // chars are counted at their last byte
         const uint32_t k0 = is_left ? k_in : 0u;
@@ -451,6 +454,8 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
         uint32_t prec = (seg_id == last_seg) ? PREC_AFTER : ((seg_id < 0 && seg1_before) ? PREC_BEFORE : PREC_EXACT);
         const int32_t seg_rel = seg_id < 0 ? 0 : seg_id;
         if (yields) last_seg = seg_id;
+        // a finding, or the leftover at the window end, of the first segment after the left run (cut := false / kept)
+        if (!is_left && seg_id < 0 && (touches_end || total >= n)) seg1_cleared = true;
         if (total < q) {
             if (touches_end) {
                 carry_done = true;
@@ -504,15 +509,19 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
         if (s0 < 29 || e_last >= 32 * (NW + 1)) return false;
         if (!do_run(s0, e_last, true, e_last + 1 >= Bend)) return false;
         next_B = e_last + 1;
-        // The carry-in only acts through this run (its char count decides where the forced cuts fall and whether a
-        // "maybe cut" flag outlives it).  A run that covers the window and holds >= q chars by itself always ends
-        // in a cut at the window end; in every other case the carry-out may depend on the carry-in.
         const uint32_t inwin = m5_count(pe, 32, e_last);
-        res.cut1 = (e_last + 1 >= Bend && inwin >= q) ? 0u : 1u;
-        if (e_last + 1 >= Bend && inwin < q) {  // one run covering the window: closed-form transfer function
-            res.caseb = 1;
-            res.a = (uint16_t)inwin;
-            res.t_out = (uint16_t)(Bend - 32u + (uint32_t)pend0);
+        if (e_last + 1 >= Bend) {
+            // a run covering the window: >= q chars by itself always end in a cut at the window end; fewer follow the
+            // closed-form transfer function eval_caseb (leftover accumulates, or is cut once it reaches q)
+            res.cut1 = inwin >= q ? 0u : 1u;
+            if (inwin < q) {
+                res.caseb = 1;
+                res.a = (uint16_t)inwin;
+                res.t_out = (uint16_t)(Bend - 32u + (uint32_t)pend0);
+            }
+        } else {
+            has_left = true;
+            left_end = e_last;
         }
     } else if (k_in >= n) {
         // the leftover alone is long enough: printed at the first event of the window
@@ -570,6 +579,24 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
         const int32_t ts = m5_high_le(RS, Bend - 1);
         if (ts < 32) return false;
         if (!do_run(ts, Bend - 1, false, true)) return false;
+    }
+    if (has_left) {
+        // Does the carry-out depend on the carry-in?  The carry-in decides whether the left run is printed (no trace in
+        // the carry) and, when leftover + run is an exact multiple of q, leaves the "maybe cut" flag set behind the run
+        // (helper.rs:353, finding_collection.rs:268).  The flag dies at the next finding or leftover of the same segment;
+        // at the next segment start it becomes that segment's "last was cut" (finding_collection.rs:240), which only
+        // matters if the segment begins with a run of passing chars -- and only shows in the carry if that run (< q
+        // chars) reaches the window end (cut again vs kept as leftover).
+        bool dep = false;
+        if (!seg1_cleared) {
+            const uint32_t s1 = m5_low_ge(seg, left_end + 1);
+            if (s1 >= 32u + (uint32_t)wlen) dep = true;  // the first segment runs to the window end: the flag is the carry
+            else if (m5_bit(R, s1)) {
+                const uint32_t e2 = m5_low_ge(RE, s1);
+                dep = e2 + 1 >= Bend && m5_count(pe, s1, e2) < q;
+            }
+        }
+        res.cut1 = dep ? 1u : 0u;
     }
     res.nrec = E.nrec;
     res.ntext = E.ntext;

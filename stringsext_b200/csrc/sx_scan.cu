@@ -931,7 +931,7 @@ size_t sx_scanner_state_leftover(const sx_scanner_state* ss, const uint8_t** p) 
 void sx_scanner_state_last_stats(const sx_scanner_state* ss, sx_scan_stats* out) { *out = ss->stats; }
 void sx_scanner_state_set_prefilter(sx_scanner_state* ss, int enabled) { ss->use_prefilter = enabled ? 1 : 0; }
 void sx_scanner_state_set_tma(sx_scanner_state* ss, int enabled) { ss->use_tma = enabled ? 1 : 0; }
-void sx_scanner_state_set_sparse(sx_scanner_state* ss, int enabled) { ss->use_sparse = enabled ? 1 : 0; }
+void sx_scanner_state_set_sparse(sx_scanner_state* ss, int mode) { ss->use_sparse = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 void sx_scanner_state_set_direct_output(sx_scanner_state* ss, int enabled) { ss->use_direct = enabled ? 1 : 0; }
 size_t sx_scanner_state_last_window_list(const sx_scanner_state* ss, uint32_t* out, size_t cap) {
     if (!ss->stats.prefilter_used) return 0;
@@ -1224,7 +1224,10 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             CK(cudaMemcpyAsync(&ne, ss->d_counters + 2, sizeof ne, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             ss->stats.d2h_bytes += sizeof ne;
-            if (ne > 0 && ne * 8ull <= (unsigned long long)total_windows) {
+            // whenever the per-entry state (240 B per listed window) fits a 16 GiB budget; beyond that (more than ~8 GiB
+            // of text-like input in one call) the block kernel
+            const bool fits_mem = ne * (unsigned long long)sparse_entry_bytes() <= (16ull << 30);
+            if (ne > 0 && fits_mem) {
                 const size_t nb = (size_t)((ne + sparse_threads() - 1) / sparse_threads());
                 if (!grow(&ss->d_entries, &ss->entries_cap, (size_t)ne * sparse_entry_bytes())) return fail;
                 if (!grow(&ss->d_btot, &ss->btot_cap, (nb + 1) * sizeof(ulonglong2))) return fail;
@@ -1325,7 +1328,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         }
     }
     // sparse pipeline: the gather kernel also wrote the finding text (UTF-8: the input bytes) into the pinned set
-    const bool text_on_host = direct_out && ss->stats.sparse_used != 0;
+    const bool text_on_host = direct_out && ss->stats.sparse_used != 0 && !fin.text_fallback;
     if (direct_out && !text_on_host) {
         // The findings are already in the collection's pinned set, written by the device in their final form;
         // only the text (transcoded on the device) is downloaded, straight to the address the findings point to.

@@ -1,27 +1,30 @@
-// sx_sparse_utf8.cuh -- the exact stage for UTF-8 missions over a SPARSE window list (binary input: the
-// prefilter keeps a few per cent of the windows, most of them isolated).
+// sx_sparse_utf8.cuh -- the exact stage for UTF-8 missions as a pipeline of data-parallel kernels, one thread per
+// listed window ("entry"), no barrier on the data path.
 //
-// sx_exact_kernel (sx_exact.cuh) resolves the carries of a block of entries with block barriers between its
-// stages; on a sparse list almost every stage has a handful of busy lanes, so the kernel is bound by the latency
-// of single warps (ncu: barrier stalls, profiles/).  Here every stage is its own data-parallel kernel -- one
-// thread per list entry, no barrier on the data path -- and the per-entry results live in a device array:
+// sx_exact_kernel (sx_exact.cuh) resolves the carries of a block of entries with block barriers between its stages;
+// on the sparse lists of binary input almost every stage has a handful of busy lanes, so the kernel is bound by the
+// latency of single warps (ncu: barrier stalls, profiles/).  Here every stage is its own kernel and the per-entry
+// results live in a device array (EntryState):
 //
 //   sx_sp_queue_kernel   queues the members of runs of adjacent windows (entries whose predecessor window is listed)
-//   sx_sp_heads_kernel   entries whose predecessor window is not listed: carry-in from the pre-roll, then ONE pass of
-//                        the mask engine (sx_mask_utf8.cuh) -> carry-out, counts, first records
+//   sx_sp_heads_kernel   entries whose predecessor window is not listed: carry-in from the 32 bytes in front of the
+//                        window (the pre-roll folded into the mask frame), ONE pass of the mask engine
+//                        (sx_mask_utf8.cuh) -> carry-out, counts, first records
 //   sx_sp_members_kernel members, in parallel: carry-in = carry-out of the entry before, taken from a resolved head or
-//                        recomputed from that window alone when it does not depend on ITS carry-in
+//                        recomputed from that window alone when it does not depend on ITS carry-in (WinResult.cut1)
 //   sx_sp_fix_kernel     the rest, few: heads the mask engine declined (byte-wise engine), members behind a
 //                        carry-dependent window (walked in order; a window that is one short run is passed in closed
 //                        form, eval_caseb, and resolved afterwards by sx_sp_late_kernel, in parallel)
 //   sx_sp_ext_kernel     extension windows (a "cut" / long leftover carry reaching an unlisted successor),
 //                        per-entry totals -> per-CTA totals
 //   sx_sp_scan_kernel    exclusive scan of the per-CTA totals
-//   sx_sp_gather_kernel  records and text offsets in stream order (exactly the order FindingCollection::from
-//                        pushes them, finding_collection.rs:255-285), final carry for the ScannerState
+//   sx_sp_gather_kernel  records and text offsets in stream order (exactly the order FindingCollection::from pushes
+//                        them, finding_collection.rs:255-285); findings (C-ABI layout) and their text straight into
+//                        the collection's pinned host memory; final carry for the ScannerState
 //
-// The host picks this path when the list is sparse (sx_scan.cu); dense lists (text) keep sx_exact_kernel, whose
-// transfer-function classification resolves long runs of adjacent windows in parallel.
+// Text-like input (every window listed, several findings per window) takes the same path: most windows' carry-out is
+// independent of their carry-in, so the members resolve in parallel too.  The block kernel remains for the other
+// encodings, for general missions and when the per-entry state would not fit (sx_scan.cu).
 #pragma once
 #include "sx_exact.cuh"
 #include <algorithm>
@@ -214,12 +217,24 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
                 WinGeom pg;
                 c.geo.window(w - 1, pg);
                 WinResult rr;
-                const bool ok = utf8_mask_window(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr);
-                known = ok && rr.cut1 == 0;
-                kin = rr.out;
-                if (ok && rr.caseb) {  // the walk of sx_sp_fix_kernel gets through that window without a pass
-                    EntryState* const pe = &B.E[e - 1];
-                    pe->d_a = rr.a; pe->d_t = rr.t_out; pe->d_null = rr.out; pe->d_caseb = 1;
+                if (utf8_mask_window(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr)) {
+                    known = rr.cut1 == 0;
+                    kin = rr.out;
+                    if (rr.caseb) {  // the walk of sx_sp_fix_kernel gets through that window without a pass
+                        EntryState* const pe = &B.E[e - 1];
+                        pe->d_a = rr.a; pe->d_t = rr.t_out; pe->d_null = rr.out; pe->d_caseb = 1;
+                    }
+                } else {
+                    // the mask engine declines (e.g. a window crowded with findings): the byte-wise engine's
+                    // transfer-function summary decides, so that such windows do not chain up in sx_sp_fix_kernel
+                    WinDesc d;
+                    WindowEngine<DecUtf8>::run(P, c.ts, c.g, pg, carry_none(), MODE_COUNT, nullptr, 0, rr, &d);
+                    known = d.type == WT_CONST;
+                    kin = d.null_out;
+                    if (d.type == WT_CASEB) {
+                        EntryState* const pe = &B.E[e - 1];
+                        pe->d_a = d.a; pe->d_t = d.t_out; pe->d_null = d.null_out; pe->d_caseb = 1;
+                    }
                 }
             }
             if (known) sp_member(P, c, w, kin, &B.E[e]);
@@ -423,7 +438,11 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     if (!fits && threadIdx.x == 0) O.final_state->overflow = 1;
     const bool host_out = O.host_findings != nullptr;
     const bool staged_out = host_out && fits && tr <= kStage;
+    // CTAs with more findings than the staging buffer holds (text-like input) write their records to device memory first
+    // and convert them kRound at a time below; their text goes through the device arena (materialize kernel + download)
+    const bool round_out = host_out && fits && !staged_out;
     const bool text_staged = host_out && fits && tt <= kTextStage;
+    if (host_out && fits && !text_staged && threadIdx.x == 0) O.final_state->text_fallback = 1;
     uint8_t* const host_text = const_cast<uint8_t*>(O.host_text);
     if (active && fits) {
         uint32_t ro = er, to = et;
@@ -431,9 +450,9 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
         auto put = [&](unsigned long long idx, const Record& r) {
             O.recs[idx] = r;
             if (host_out) {
-                write_host_finding(O, staged_out ? &sbuf[(idx - br) * 3] : reinterpret_cast<uint4*>(O.host_findings + idx), r);
+                if (staged_out) write_host_finding(O, &sbuf[(idx - br) * 3], r);
                 if (idx == 0) O.final_state->first_flags = r.flags;
-                transcode_range(P, c.g, r.in_start, r.in_len, text_staged ? tbuf + (r.text_off - bt) : host_text + r.text_off);
+                if (text_staged) transcode_range(P, c.g, r.in_start, r.in_len, tbuf + (r.text_off - bt));
             }
         };
         if (cr) {
@@ -444,10 +463,12 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
                     put(br + ro + k, r);
                 }
             } else {
+                // more findings than the entry's staging slots: written straight to their place by one more pass
                 WinGeom wg;
                 c.geo.window(list_window(X, X.cta_off, e), wg);
                 WinResult r;
-                WindowEngine<DecUtf8>::run(P, c.ts, c.g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+                if (!utf8_mask_window(P, c.ts, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r))
+                    WindowEngine<DecUtf8>::run(P, c.ts, c.g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
                 if (host_out) for (uint32_t k = 0; k < cr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
         }
@@ -462,7 +483,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
             } else {
                 const WinGeom xg = ext_geom(c.geo, list_window(X, X.cta_off, e) + 1, X.pre_bytes);
                 WinResult r;
-                WindowEngine<DecUtf8>::run(P, c.ts, c.g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+                if (!utf8_mask_window(P, c.ts, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r))
+                    WindowEngine<DecUtf8>::run(P, c.ts, c.g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
                 if (host_out) for (uint32_t k = 0; k < xr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
         }
@@ -481,10 +503,21 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
         }
     }
     if (active && e == B.NE - 1) { O.final_state->carry = kout; O.final_state->npend = es->npend; }
-    if (staged_out || text_staged) __syncthreads();
+    if (host_out) __syncthreads();
     if (staged_out) {
         uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br);
         for (uint32_t k = threadIdx.x; k < tr * 3; k += kSpThreads) dst[k] = sbuf[k];
+    }
+    if (round_out) {
+        constexpr uint32_t kRound = kSpThreads;
+        for (uint32_t base = 0; base < tr; base += kRound) {
+            const uint32_t cnt = tr - base < kRound ? tr - base : kRound;
+            if (threadIdx.x < cnt) write_host_finding(O, &sbuf[threadIdx.x * 3], O.recs[br + base + threadIdx.x]);
+            __syncthreads();
+            uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br + base);
+            for (uint32_t k = threadIdx.x; k < cnt * 3; k += kSpThreads) dst[k] = sbuf[k];
+            __syncthreads();
+        }
     }
     if (text_staged && tt) {
         // [bt, bt + tt) of the text arena: bytes up to the first 16-byte boundary, aligned 16-byte body, tail bytes

@@ -276,7 +276,7 @@ class ScannerState:
 
     def set_sparse(self, enabled: bool) -> None:
         """False: the exact stage always runs as the block kernel (sx_exact_kernel), never as the sparse-list pipeline."""
-        load_library().sx_scanner_state_set_sparse(self._h, 1 if enabled else 0)
+        load_library().sx_scanner_state_set_sparse(self._h, int(enabled))  # 0 off, 1 default, 2 whenever possible
 
     def last_window_list(self) -> List[int]:
         L = load_library()

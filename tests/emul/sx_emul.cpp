@@ -22,6 +22,7 @@ static int g_use_mask = 1;
 static uint64_t g_mask_ok = 0, g_mask_declined = 0;
 static uint64_t g_mask_mismatch = 0;
 static uint64_t g_head_ok = 0;
+static uint64_t g_indep = 0, g_dep = 0;
 struct HostTile {
     GlobalSrc g;
     const Utf8Tables* tables() const { return g_use_fast ? &g_tables : nullptr; }
@@ -146,7 +147,19 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
             // the sparse pipeline's closed form for windows that are one short run (WinResult.caseb of a pass under the
             // null carry): eval_caseb from the real carry-in must give the real carry-out
             WinResult rn;
-            if (utf8_mask_window(P, ts, wg, carry_none(), MODE_STATE, nullptr, 0, rn) && rn.caseb) {
+            const bool rn_ok = utf8_mask_window(P, ts, wg, carry_none(), MODE_STATE, nullptr, 0, rn);
+            if (rn_ok && rn.cut1 == 0) {
+                // "the carry-out does not depend on the carry-in" (sx_sp_members_kernel takes the null-carry result as the
+                // next entry's carry-in): must equal the carry-out under the real carry-in
+                g_indep++;
+                if (memcmp(&rn.out, &rs.out, sizeof(Carry)) != 0) {
+                    stats[3] += 100000000;
+                    if (g_mask_mismatch++ < 5)
+                        fprintf(stderr, "independence mismatch: window [%lld,%lld) kin kind=%d k=%d: null-carry out kind=%d k=%d vs real kind=%d k=%d\n",
+                                (long long)wg.ws, (long long)wg.we, kin.kind, kin.k, rn.out.kind, rn.out.k, rs.out.kind, rs.out.k);
+                }
+            } else if (rn_ok) g_dep++;
+            if (rn_ok && rn.caseb) {
                 WinDesc dc;
                 dc.type = WT_CASEB; dc.pad = 0; dc.a = rn.a; dc.t_out = rn.t_out; dc.nrec = 0; dc.ntext = 0; dc.null_out = rn.out;
                 const Carry ke = eval_caseb(P, dc, kin, (uint32_t)(wg.we - wg.ws));
@@ -213,6 +226,7 @@ void sx_emul_set_mask(int on) { g_use_mask = on; }
 void sx_emul_mask_counts(uint64_t* ok, uint64_t* declined) { *ok = g_mask_ok; *declined = g_mask_declined; }
 uint64_t sx_emul_mask_mismatches() { return g_mask_mismatch; }
 uint64_t sx_emul_head_ok() { return g_head_ok; }
+void sx_emul_indep_counts(uint64_t* indep, uint64_t* dep) { *indep = g_indep; *dep = g_dep; }
 int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
     for (uint32_t i = 0; i < 2048; ++i) utf8_tables_fill(*P, g_tables, i);
     std::vector<uint32_t> list;

@@ -361,3 +361,27 @@ def test_direct_host_output_matches_record_download(enc):
             kept.append((fa, exp))
     for fa, exp in kept:  # earlier collections are untouched by the scans that followed
         assert gpu_findings(fa) == exp
+
+
+@pytest.mark.parametrize("n,q,ubf,kind", [(10, 64, None, "text"), (4, 64, M.UBF_ALL_VALID, "text"), (6, 64, M.UBF_ALL, "mixed"),
+                                         (3, 64, None, "runs"), (8, 64, M.UBF_ALL_VALID, "lowent"), (10, 64, M.UBF_AFRICAN, "text"),
+                                         (6, 32, M.UBF_ALL_VALID, "text"), (2, 64, None, "mixed")])
+def test_sparse_pipeline_forced_on_dense_input(n, q, ubf, kind):
+    """UTF-8 text-like input (every window listed, long runs of adjacent windows): the sparse-list pipeline forced on
+    (carry-independence rule, closed-form walks) == the block kernel == the oracle, incl. chained calls and is_last."""
+    m = M.Mission.for_label("utf-8", n, ubf=ubf, output_line_char_nb_max=q)
+    rng = random.Random(777 + n + q)
+    buf = corpus.gen(rng, kind, 700000 + rng.randrange(5000), 1)
+    a, b, os_ = sx.ScannerState(m), sx.ScannerState(m), oracle_state(m)
+    a.set_sparse(2)
+    b.set_sparse(0)
+    cuts = [0, 4096 * 50 + 3, 4096 * 120, len(buf)]
+    for lo, hi in zip(cuts, cuts[1:]):
+        last = hi == len(buf)
+        ra = gpu_findings(a.scan_stream(buf[lo:hi], last, 4096))
+        rb = gpu_findings(b.scan_stream(buf[lo:hi], last, 4096))
+        exp = oracle_findings(os_.scan_stream(buf[lo:hi], last, 4096))
+        assert a.last_stats.sparse_used == 1 and b.last_stats.sparse_used == 0
+        assert ra == exp and rb == exp
+        check_state(a, os_)
+        check_state(b, os_)
