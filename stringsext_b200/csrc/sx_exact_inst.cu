@@ -1,7 +1,8 @@
 // sx_exact_inst.cu -- one instantiation of sx_exact_kernel<Dec> per translation unit (-DSX_INST=n).
 #include "sx_exact.cuh"
-#if SX_INST == 1
+#if SX_INST == 0 || SX_INST == 1 || SX_INST == 4
 #include "sx_sparse_utf8.cuh"
+#define SX_HAS_SPARSE 1
 #endif
 
 namespace sx {
@@ -34,9 +35,16 @@ cudaError_t SX_NAME(const ScanParams& P, const ScanOut& O, const ExactCfg& X, un
     sx_exact_kernel<SX_DEC><<<grid, kThreads, 0, st>>>(P, O, X);
     return cudaGetLastError();
 }
-#if SX_INST == 1
-cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                               void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev) {
+#if defined(SX_HAS_SPARSE)
+#if SX_INST == 0
+#define SX_SPARSE_NAME launch_sparse_xud
+#elif SX_INST == 1
+#define SX_SPARSE_NAME launch_sparse_utf8
+#else
+#define SX_SPARSE_NAME launch_sparse_sb
+#endif
+cudaError_t SX_SPARSE_NAME(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
+                           void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev) {
     SparseBufs B;
     B.E = static_cast<EntryState*>(entries);
     B.btot = static_cast<ulonglong2*>(btot);
@@ -46,8 +54,10 @@ cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const Exac
     B.queue2 = B.queue + NE + 32;
     B.qcount2 = O.counters + 4;
     B.NE = NE;
-    return launch_sparse_utf8_impl(P, O, X, B, num_sms, st, ev);
+    return launch_sparse_impl<SX_DEC>(P, O, X, B, num_sms, st, ev);
 }
+#endif
+#if SX_INST == 1
 size_t sparse_entry_bytes() { return sizeof(EntryState); }
 size_t sparse_tables_bytes() { return sizeof(Utf8Tables); }
 uint32_t sparse_threads() { return kSpThreads; }

@@ -227,22 +227,22 @@ struct MaskEmit {
     uint64_t text_off;
     uint32_t nrec, ntext;
 };
-SX_HD void mask_emit(MaskEmit& E, int32_t seg_rel, uint32_t prec, int32_t run_s, int32_t run_e, uint32_t flags) {
+SX_HD void mask_emit(MaskEmit& E, int32_t seg_rel, uint32_t prec, int32_t run_s, int32_t run_e, uint32_t text_len, uint32_t flags) {
     const uint32_t len = (uint32_t)(run_e - run_s);
     if (E.mode == MODE_WRITE || (E.mode == MODE_BUFFER && E.nrec < kBufRecs)) {
         Record r;
         r.position = E.P->base_consumed + (uint64_t)(E.base + seg_rel);  // finding_collection.rs:260
         r.in_start = E.base + run_s;
         r.in_len = len;
-        r.text_len = len;  // UTF-8 -> UTF-8: the text is the input range
+        r.text_len = text_len;
         r.text_off = E.text_off;
         r.flags = flags;
         r.precision = prec;
         *E.wr++ = r;
-        E.text_off += len;
+        E.text_off += text_len;
     }
     E.nrec++;
-    E.ntext += len;
+    E.ntext += text_len;
 }
 
 // Returns false when the window needs the byte-wise engine (nothing has been written in that case that the
@@ -250,8 +250,10 @@ SX_HD void mask_emit(MaskEmit& E, int32_t seg_rel, uint32_t prec, int32_t run_s,
 // LB32: the carry-in is NOT given but derived from the 32 bytes before the window (the pre-roll of a head folded into
 // the same pass): valid when the caller knows that the run touching the window's left boundary is shorter than 28
 // bytes (the predecessor window is unlisted and pre_bytes <= 28); `kin_arg` is ignored, res.in tells what was derived.
-template <int NW, bool LB32, class TileSrc>
-SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin_arg, int mode,
+// SBYTE: single-byte family (x-user-defined, table driven): no decoder state, a char is a byte, the class table gives
+// verdict / unmapped / UTF-8 length of the mapped char; everything after the event masks is shared with UTF-8.
+template <int NW, bool LB32, bool SBYTE, class TileSrc>
+SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin_arg, int mode,
                             Record* wr, uint64_t text_off, WinResult& res) {
     const int64_t ws = geo.ws, we = geo.we;
     const int32_t wlen = (int32_t)(we - ws);
@@ -279,87 +281,108 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
 #pragma unroll
         for (int i = 1; i < NW + 1; ++i) pl[t].w[i] &= V.w[i];
 
-    // ---- class masks (utf8_class: 0 A, 1 80-8F, 2 90-9F, 3 A0-BF, 4 X, 5 L2, 6 E0, 7 E1-EC/EE/EF, 8 ED, 9 F0, 10 F1-F3, 11 F4)
-    M5 Cn, C80, C90, CA0, X, L2, plain, E0, ED, F0, F4, len34, len4, PS;
-#pragma unroll
-    for (int i = 0; i < NW + 1; ++i) {
-        const uint32_t c0 = pl[0].w[i], c1 = pl[1].w[i], c2 = pl[2].w[i], c3 = pl[3].w[i];
-        const uint32_t hi0 = ~c3 & ~c2;  // classes 0..3
-        C80.w[i] = hi0 & ~c1 & c0;
-        C90.w[i] = hi0 & c1 & ~c0;
-        CA0.w[i] = hi0 & c1 & c0;
-        Cn.w[i] = hi0 & (c1 | c0);
-        X.w[i] = ~c3 & c2 & ~c1 & ~c0;                       // 4
-        L2.w[i] = ~c3 & c2 & ~c1 & c0;                       // 5
-        E0.w[i] = ~c3 & c2 & c1 & ~c0;                       // 6
-        const uint32_t l3n = ~c3 & c2 & c1 & c0;             // 7
-        ED.w[i] = c3 & ~c2 & ~c1 & ~c0;                      // 8
-        F0.w[i] = c3 & ~c2 & ~c1 & c0;                       // 9
-        const uint32_t l4n = c3 & ~c2 & c1 & ~c0;            // 10
-        F4.w[i] = c3 & ~c2 & c1 & c0;                        // 11
-        plain.w[i] = L2.w[i] | l3n | l4n;
-        len4.w[i] = F0.w[i] | l4n | F4.w[i];
-        len34.w[i] = E0.w[i] | l3n | ED.w[i] | len4.w[i];
-        PS.w[i] = pl[4].w[i];
-    }
-    // ---- decoder: accepted continuation bytes -----------------------------------------------------------------
-    M5 ok1, ok2, ok3, acc, pendm, pre, mal, seg;
-    {
-        const M5 s_plain = m5_shl<1>(plain), s_e0 = m5_shl<1>(E0), s_ed = m5_shl<1>(ED), s_f0 = m5_shl<1>(F0), s_f4 = m5_shl<1>(F4);
-#pragma unroll
-        for (int i = 0; i < NW + 1; ++i)
-            ok1.w[i] = Cn.w[i] & (s_plain.w[i] | (s_e0.w[i] & CA0.w[i]) | (s_ed.w[i] & (C80.w[i] | C90.w[i])) |
-                                  (s_f0.w[i] & (C90.w[i] | CA0.w[i])) | (s_f4.w[i] & C80.w[i]));
-        const M5 s1ok1 = m5_shl<1>(ok1), s2l34 = m5_shl<2>(len34);
-#pragma unroll
-        for (int i = 0; i < NW + 1; ++i) ok2.w[i] = Cn.w[i] & s1ok1.w[i] & s2l34.w[i];
-        const M5 s1ok2 = m5_shl<1>(ok2), s3l4 = m5_shl<3>(len4);
-#pragma unroll
-        for (int i = 0; i < NW + 1; ++i) ok3.w[i] = Cn.w[i] & s1ok2.w[i] & s3l4.w[i];
-        const M5 s1l34 = m5_shl<1>(len34), s2l4 = m5_shl<2>(len4);
+    // event masks shared by both families: acc / pendm (UTF-8 decoder), pre / seg (segment starts), pe (passing char
+    // ends), R (bytes of passing chars), lead (UTF-8 lead bytes), TL0 / TL1 (single-byte: UTF-8 length - 1 of the char)
+    M5 acc, pendm, pre, seg, pe, R, lead, TL0, TL1;
+    if (SBYTE) {
+        // class table bits: 0 verdict, 1 unmapped (malformed, DecSb), 2-3 UTF-8 length - 1 of the mapped char
+        M5 mal;
 #pragma unroll
         for (int i = 0; i < NW + 1; ++i) {
-            acc.w[i] = ok1.w[i] | ok2.w[i] | ok3.w[i];
-            // a sequence is pending AFTER this byte
-            pendm.w[i] = L2.w[i] | len34.w[i] | (ok1.w[i] & s1l34.w[i]) | (ok2.w[i] & s2l4.w[i]);
-            mal.w[i] = X.w[i] | (Cn.w[i] & ~acc.w[i]);
+            const uint32_t pv = (LB32 && i == 0) ? 0xFFFFFFFFu : V.w[i];
+            R.w[i] = pl[0].w[i] & pv;
+            pe.w[i] = R.w[i];
+            mal.w[i] = i == 0 ? 0u : pl[1].w[i];
+            TL0.w[i] = pl[2].w[i];
+            TL1.w[i] = pl[3].w[i];
+            acc.w[i] = 0; pendm.w[i] = 0; pre.w[i] = 0; lead.w[i] = 0;
         }
-        mal.w[0] = 0;  // what happened before the window only matters through the pending sequence
-        const M5 s1pend = m5_shl<1>(pendm), s1mal = m5_shl<1>(mal);
+        const M5 s1mal = m5_shl<1>(mal);
 #pragma unroll
+        for (int i = 0; i < NW + 1; ++i) seg.w[i] = s1mal.w[i] & V.w[i];
+    } else {
+        // ---- class masks (utf8_class: 0 A, 1 80-8F, 2 90-9F, 3 A0-BF, 4 X, 5 L2, 6 E0, 7 E1-EC/EE/EF, 8 ED, 9 F0, 10 F1-F3, 11 F4)
+        M5 Cn, C80, C90, CA0, X, L2, plain, E0, ED, F0, F4, len34, len4, PS;
+    #pragma unroll
         for (int i = 0; i < NW + 1; ++i) {
-            pre.w[i] = s1pend.w[i] & ~acc.w[i] & V.w[i];
-            seg.w[i] = (pre.w[i] | s1mal.w[i]) & V.w[i];  // a segment starts at this byte
+            const uint32_t c0 = pl[0].w[i], c1 = pl[1].w[i], c2 = pl[2].w[i], c3 = pl[3].w[i];
+            const uint32_t hi0 = ~c3 & ~c2;  // classes 0..3
+            C80.w[i] = hi0 & ~c1 & c0;
+            C90.w[i] = hi0 & c1 & ~c0;
+            CA0.w[i] = hi0 & c1 & c0;
+            Cn.w[i] = hi0 & (c1 | c0);
+            X.w[i] = ~c3 & c2 & ~c1 & ~c0;                       // 4
+            L2.w[i] = ~c3 & c2 & ~c1 & c0;                       // 5
+            E0.w[i] = ~c3 & c2 & c1 & ~c0;                       // 6
+            const uint32_t l3n = ~c3 & c2 & c1 & c0;             // 7
+            ED.w[i] = c3 & ~c2 & ~c1 & ~c0;                      // 8
+            F0.w[i] = c3 & ~c2 & ~c1 & c0;                       // 9
+            const uint32_t l4n = c3 & ~c2 & c1 & ~c0;            // 10
+            F4.w[i] = c3 & ~c2 & c1 & c0;                        // 11
+            plain.w[i] = L2.w[i] | l3n | l4n;
+            len4.w[i] = F0.w[i] | l4n | F4.w[i];
+            len34.w[i] = E0.w[i] | l3n | ED.w[i] | len4.w[i];
+            PS.w[i] = pl[4].w[i];
         }
-    }
-    // ---- char events (at the last byte of the char) and the bytes of passing chars --------------------------------
-    M5 pe, R;  // pe: passing char ends; R: bytes of passing chars
-    {
-        const M5 s1L2 = m5_shl<1>(L2), s2l34 = m5_shl<2>(len34), s2l4 = m5_shl<2>(len4);
-        const M5 s1ps = m5_shl<1>(PS), s2ps = m5_shl<2>(PS), s3ps = m5_shl<3>(PS);
-        M5 p1, p2, p3, p4;
-#pragma unroll
-        for (int i = 0; i < NW + 1; ++i) {
-            const uint32_t a = ~(pl[0].w[i] | pl[1].w[i] | pl[2].w[i] | pl[3].w[i]);  // class 0
-            const uint32_t pv = (LB32 && i == 0) ? 0xFFFFFFFFu : V.w[i];  // LB32: the chars before the window count too
-            p1.w[i] = a & PS.w[i] & pv;
-            p2.w[i] = ok1.w[i] & s1L2.w[i] & s1ps.w[i] & pv;
-            p3.w[i] = ok2.w[i] & s2l34.w[i] & ~s2l4.w[i] & s2ps.w[i] & pv;
-            p4.w[i] = ok3.w[i] & s3ps.w[i] & pv;
-            pe.w[i] = p1.w[i] | p2.w[i] | p3.w[i] | p4.w[i];
+        // ---- decoder: accepted continuation bytes -----------------------------------------------------------------
+        M5 ok1, ok2, ok3, mal;
+        {
+            const M5 s_plain = m5_shl<1>(plain), s_e0 = m5_shl<1>(E0), s_ed = m5_shl<1>(ED), s_f0 = m5_shl<1>(F0), s_f4 = m5_shl<1>(F4);
+    #pragma unroll
+            for (int i = 0; i < NW + 1; ++i)
+                ok1.w[i] = Cn.w[i] & (s_plain.w[i] | (s_e0.w[i] & CA0.w[i]) | (s_ed.w[i] & (C80.w[i] | C90.w[i])) |
+                                      (s_f0.w[i] & (C90.w[i] | CA0.w[i])) | (s_f4.w[i] & C80.w[i]));
+            const M5 s1ok1 = m5_shl<1>(ok1), s2l34 = m5_shl<2>(len34);
+    #pragma unroll
+            for (int i = 0; i < NW + 1; ++i) ok2.w[i] = Cn.w[i] & s1ok1.w[i] & s2l34.w[i];
+            const M5 s1ok2 = m5_shl<1>(ok2), s3l4 = m5_shl<3>(len4);
+    #pragma unroll
+            for (int i = 0; i < NW + 1; ++i) ok3.w[i] = Cn.w[i] & s1ok2.w[i] & s3l4.w[i];
+            const M5 s1l34 = m5_shl<1>(len34), s2l4 = m5_shl<2>(len4);
+    #pragma unroll
+            for (int i = 0; i < NW + 1; ++i) {
+                acc.w[i] = ok1.w[i] | ok2.w[i] | ok3.w[i];
+                // a sequence is pending AFTER this byte
+                pendm.w[i] = L2.w[i] | len34.w[i] | (ok1.w[i] & s1l34.w[i]) | (ok2.w[i] & s2l4.w[i]);
+                mal.w[i] = X.w[i] | (Cn.w[i] & ~acc.w[i]);
+            }
+            mal.w[0] = 0;  // what happened before the window only matters through the pending sequence
+            const M5 s1pend = m5_shl<1>(pendm), s1mal = m5_shl<1>(mal);
+    #pragma unroll
+            for (int i = 0; i < NW + 1; ++i) {
+                pre.w[i] = s1pend.w[i] & ~acc.w[i] & V.w[i];
+                seg.w[i] = (pre.w[i] | s1mal.w[i]) & V.w[i];  // a segment starts at this byte
+            }
         }
-        const M5 r2 = m5_shr<1>(p2), r3a = m5_shr<1>(p3), r3b = m5_shr<2>(p3), r4a = m5_shr<1>(p4), r4b = m5_shr<2>(p4), r4c = m5_shr<3>(p4);
+        // ---- char events (at the last byte of the char) and the bytes of passing chars --------------------------------
+        {
+            const M5 s1L2 = m5_shl<1>(L2), s2l34 = m5_shl<2>(len34), s2l4 = m5_shl<2>(len4);
+            const M5 s1ps = m5_shl<1>(PS), s2ps = m5_shl<2>(PS), s3ps = m5_shl<3>(PS);
+            M5 p1, p2, p3, p4;
+    #pragma unroll
+            for (int i = 0; i < NW + 1; ++i) {
+                const uint32_t a = ~(pl[0].w[i] | pl[1].w[i] | pl[2].w[i] | pl[3].w[i]);  // class 0
+                const uint32_t pv = (LB32 && i == 0) ? 0xFFFFFFFFu : V.w[i];  // LB32: the chars before the window count too
+                p1.w[i] = a & PS.w[i] & pv;
+                p2.w[i] = ok1.w[i] & s1L2.w[i] & s1ps.w[i] & pv;
+                p3.w[i] = ok2.w[i] & s2l34.w[i] & ~s2l4.w[i] & s2ps.w[i] & pv;
+                p4.w[i] = ok3.w[i] & s3ps.w[i] & pv;
+                pe.w[i] = p1.w[i] | p2.w[i] | p3.w[i] | p4.w[i];
+            }
+            const M5 r2 = m5_shr<1>(p2), r3a = m5_shr<1>(p3), r3b = m5_shr<2>(p3), r4a = m5_shr<1>(p4), r4b = m5_shr<2>(p4), r4c = m5_shr<3>(p4);
+    #pragma unroll
+            for (int i = 0; i < NW + 1; ++i) R.w[i] = pe.w[i] | r2.w[i] | r3a.w[i] | r3b.w[i] | r4a.w[i] | r4b.w[i] | r4c.w[i];
+        }
 #pragma unroll
-        for (int i = 0; i < NW + 1; ++i) R.w[i] = pe.w[i] | r2.w[i] | r3a.w[i] | r3b.w[i] | r4a.w[i] | r4b.w[i] | r4c.w[i];
+        for (int i = 0; i < NW + 1; ++i) { lead.w[i] = L2.w[i] | len34.w[i]; TL0.w[i] = 0; TL1.w[i] = 0; }
     }
+    // text bytes (UTF-8) of the chars whose bytes are the mask bits [a, b]
+    auto T = [&](uint32_t a, uint32_t b) -> uint32_t {
+        return SBYTE ? (b + 1u - a) + m5_count(TL0, a, b) + 2u * m5_count(TL1, a, b) : (b + 1u - a);
+    };
     // bytes inside the decoder at the window start (the straddling char, if any, starts there)
     int32_t pend0 = 0;
-    if (m5_bit(pendm, 31)) {
-        M5 lead;
-#pragma unroll
-        for (int i = 0; i < NW + 1; ++i) lead.w[i] = L2.w[i] | len34.w[i];
-        pend0 = m5_bit(lead, 31) ? 1 : (m5_bit(lead, 30) ? 2 : 3);
-    }
+    if (!SBYTE && m5_bit(pendm, 31)) pend0 = m5_bit(lead, 31) ? 1 : (m5_bit(lead, 30) ? 2 : 3);
     if (LB32) {
         // the carry-in: the run of complete passing chars that ends where the pending bytes (if any) begin
         const uint32_t lastB = 31u - (uint32_t)pend0;
@@ -372,7 +395,7 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
             if (k == 0) return false;
             kin.kind = K_L; kin.flags = 0; kin.k = (uint16_t)k;
             kin.in_bytes = 32u - ls;
-            kin.out_bytes = lastB + 1u - ls;
+            kin.out_bytes = T(ls, lastB);
             kin.aux = 0;
             k_in = k;
         }
@@ -383,10 +406,7 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
     // bytes still inside the decoder at the window end
     const uint32_t Blast = 31u + (uint32_t)wlen;
     int32_t npend_out = 0;
-    if (m5_bit(pendm, Blast)) {
-        M5 lead;
-#pragma unroll
-        for (int i = 0; i < NW + 1; ++i) lead.w[i] = L2.w[i] | len34.w[i];
+    if (!SBYTE && m5_bit(pendm, Blast)) {
         npend_out = m5_bit(lead, Blast) ? 1 : (m5_bit(lead, Blast - 1) ? 2 : 3);
         if (npend_out > wlen) return false;
     }
@@ -419,9 +439,9 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
             if (!m5_bit(pendm, 32 + p)) { straddle_completes = true; break; }
         }
     }
-    const bool seg1_before = k_in > 0 || (at_slice_start && pend0 > 0 && straddle_completes);
+    const bool seg1_before = k_in > 0 || (!SBYTE && at_slice_start && pend0 > 0 && straddle_completes);
     const bool probe_seg1 = false;
-    const bool probe_seg0 = at_slice_start && mode != MODE_STATE && k_in > 0;  // second segment at the slice start
+    const bool probe_seg0 = !SBYTE && at_slice_start && mode != MODE_STATE && k_in > 0;  // second segment at the slice start
     const uint32_t lo_flags = (k_in > 0 && (kin.flags & CF_HOSTCARRY)) ? (uint32_t)RF_HOSTCARRY : 0u;
 
     // One run of passing chars [sB, eB] (bit indices of its first / last byte).  is_left: it continues whatever touches
@@ -448,6 +468,9 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
             seg_id = sg < 32 ? -1 : sg - 32;
         }
         const int32_t start_rel = (k0 > 0) ? -(int32_t)kin.in_bytes : sB - 32;
+        // text of the run: the leftover's (decoded earlier) + the chars from the straddling char / the run start on
+        const uint32_t text0 = k0 > 0 ? kin.out_bytes : 0u;
+        const uint32_t tfrom = k0 > 0 ? 32u - (uint32_t)pend0 : (uint32_t)sB;
         const uint32_t fl0 = (is_left ? lo_flags : 0u) | (lastcut0 ? (uint32_t)RF_COMPLETES : 0u);
         const bool yields = total >= q || (touches_end ? lastcut0 : (lastcut0 || total >= n));
         if (yields && ((seg_id == 0 && probe_seg0) || (seg_id < 0 && probe_seg1))) return false;
@@ -460,27 +483,30 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
             if (touches_end) {
                 carry_done = true;
                 if (lastcut0) {  // completes the cut finding and may be cut again at the window end
-                    mask_emit(E, seg_rel, prec, start_rel, (int32_t)eB + 1 - 32, fl0);
+                    mask_emit(E, seg_rel, prec, start_rel, (int32_t)eB + 1 - 32, text0 + T(tfrom, eB), fl0);
                     res.out = carry_cut();
                 } else {         // kept as leftover
                     Carry c;
                     c.kind = K_L; c.flags = (uint8_t)((is_left && k0 > 0 && (kin.flags & CF_HOSTCARRY)) ? CF_HOSTCARRY : 0);
                     c.k = (uint16_t)total;
                     c.in_bytes = (uint32_t)(wlen - start_rel);
-                    c.out_bytes = (uint32_t)((int32_t)Bend - 32 - start_rel);
+                    c.out_bytes = text0 + T(tfrom, Bend - 1);
                     c.aux = 0;
                     res.out = c;
                 }
-            } else if (yields) mask_emit(E, seg_rel, prec, start_rel, (int32_t)eB + 1 - 32, fl0);
+            } else if (yields) mask_emit(E, seg_rel, prec, start_rel, (int32_t)eB + 1 - 32, text0 + T(tfrom, eB), fl0);
             return true;
         }
         // forced cuts every q chars
         uint32_t need = q - k0, remaining = inwin, posB = fromB, flp = fl0;
         int32_t piece_s = start_rel;
+        uint32_t piece_t0 = text0, piece_from = tfrom;
         int pieces = 0;
         while (remaining >= need) {
             const uint32_t endB = m5_select(pe, posB, need);
-            mask_emit(E, seg_rel, prec, piece_s, (int32_t)endB + 1 - 32, flp);
+            mask_emit(E, seg_rel, prec, piece_s, (int32_t)endB + 1 - 32, piece_t0 + T(piece_from, endB), flp);
+            piece_t0 = 0;
+            piece_from = endB + 1;
             prec = PREC_AFTER;
             flp = RF_COMPLETES;
             remaining -= need;
@@ -495,7 +521,7 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
             carry_done = true;
             res.out = carry_cut();
         } else {
-            mask_emit(E, seg_rel, prec, piece_s, (int32_t)eB + 1 - 32, RF_COMPLETES);
+            mask_emit(E, seg_rel, prec, piece_s, (int32_t)eB + 1 - 32, piece_t0 + T(piece_from, eB), RF_COMPLETES);
             if (touches_end) { carry_done = true; res.out = carry_cut(); }
         }
         return true;
@@ -517,7 +543,7 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
             if (inwin < q) {
                 res.caseb = 1;
                 res.a = (uint16_t)inwin;
-                res.t_out = (uint16_t)(Bend - 32u + (uint32_t)pend0);
+                res.t_out = (uint16_t)T(32u - (uint32_t)pend0, Bend - 1);
             }
         } else {
             has_left = true;
@@ -525,7 +551,7 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
         }
     } else if (k_in >= n) {
         // the leftover alone is long enough: printed at the first event of the window
-        mask_emit(E, 0, PREC_BEFORE, -(int32_t)kin.in_bytes, -pend0, lo_flags);
+        mask_emit(E, 0, PREC_BEFORE, -(int32_t)kin.in_bytes, -pend0, kin.out_bytes, lo_flags);
         last_seg = -1;
     }
     // ---- runs of >= n bytes inside the window ------------------------------------------------------------------------
@@ -606,27 +632,94 @@ SX_HD_NOINLINE bool utf8_mask_window_nw(const ScanParams& P, const TileSrc& tsrc
 }
 
 // Short windows (pre-roll, extension) only need two data words.
-template <class TileSrc>
-SX_HD bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode,
-                            Record* wr, uint64_t text_off, WinResult& res) {
-    if (geo.we - geo.ws <= 64) return utf8_mask_window_nw<2, false>(P, tsrc, geo, kin, mode, wr, text_off, res);
-    return utf8_mask_window_nw<4, false>(P, tsrc, geo, kin, mode, wr, text_off, res);
+template <bool SBYTE, class TileSrc>
+SX_HD bool mask_window(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode, Record* wr,
+                       uint64_t text_off, WinResult& res) {
+    if (geo.we - geo.ws <= 64) return mask_window_nw<2, false, SBYTE>(P, tsrc, geo, kin, mode, wr, text_off, res);
+    return mask_window_nw<4, false, SBYTE>(P, tsrc, geo, kin, mode, wr, text_off, res);
 }
 // A head (predecessor window not listed) in ONE pass: the pre-roll region is the 32 bytes in front of the window.
 constexpr uint32_t kMaskLb32MaxPre = 28;
+template <bool SBYTE, class TileSrc>
+SX_HD bool mask_head(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, uint32_t pre_bytes, int mode, Record* wr,
+                     uint64_t text_off, WinResult& res) {
+    if (pre_bytes > kMaskLb32MaxPre || geo.ws < 32 || geo.we - geo.ws <= 64) return false;
+    return mask_window_nw<4, true, SBYTE>(P, tsrc, geo, carry_none(), mode, wr, text_off, res);
+}
+template <class TileSrc>
+SX_HD bool utf8_mask_window(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode, Record* wr,
+                            uint64_t text_off, WinResult& res) {
+    return mask_window<false>(P, tsrc, geo, kin, mode, wr, text_off, res);
+}
 template <class TileSrc>
 SX_HD bool utf8_mask_head(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, uint32_t pre_bytes, int mode, Record* wr,
                           uint64_t text_off, WinResult& res) {
-    if (pre_bytes > kMaskLb32MaxPre || geo.ws < 32 || geo.we - geo.ws <= 64) return false;
-    return utf8_mask_window_nw<4, true>(P, tsrc, geo, carry_none(), mode, wr, text_off, res);
+    return mask_head<false>(P, tsrc, geo, pre_bytes, mode, wr, text_off, res);
+}
+// which decoders the mask engine covers
+template <class Dec> struct MaskFamily { static constexpr bool kHas = false, kSByte = false; };
+template <> struct MaskFamily<DecUtf8> { static constexpr bool kHas = true, kSByte = false; };
+template <> struct MaskFamily<DecXud> { static constexpr bool kHas = true, kSByte = true; };
+template <> struct MaskFamily<DecSb> { static constexpr bool kHas = true, kSByte = true; };
+
+// Class table of the single-byte family (Utf8Tables.cls): bit 0 filter verdict of the mapped char, bit 1 unmapped byte
+// (malformed, DecSb), bits 2-3 UTF-8 length - 1 of the mapped char.
+SX_HD void sbyte_cls_fill(const ScanParams& P, Utf8Tables& T, uint32_t b) {
+    uint32_t pass, mal = 0, len = 1;
+    if (b < 0x80) pass = pass_filter(P, b) ? 1u : 0u;
+    else if (P.enc == ENC_XUD) { pass = pass_filter(P, 0xEF) ? 1u : 0u; len = 3; }  // U+F780 + (b - 0x80)
+    else {
+        const uint32_t cp = P.sb_table[b - 0x80];
+        if (cp == 0) { mal = 1; pass = 0; }
+        else { pass = pass_filter(P, utf8_lead_of_cp(cp)) ? 1u : 0u; len = utf8_len_of_cp(cp); }
+    }
+    T.cls[b] = (uint8_t)(pass | (mal << 1) | ((len - 1u) << 2));
+}
+// i in 0..2047: the tables the engines of the mission's encoding read
+SX_HD void mask_tables_fill(const ScanParams& P, Utf8Tables& T, uint32_t i) {
+    if (P.enc == ENC_UTF8) utf8_tables_fill(P, T, i);
+    else if (i < 256) sbyte_cls_fill(P, T, i);
 }
 
-// Engine dispatch used by the kernels and the test harness: UTF-8 tries the mask engine, then the convergent
-// byte-wise engine; grep_char / same-unicode-block / chars_min_nb > q missions take the general automaton.
+#if !defined(__CUDA_ARCH__)
+// Host harness only: try the mask engine and cross-check it against the byte-wise engine `fallback` (results and records).
+template <bool SBYTE, class TileSrc, class Fallback>
+inline bool host_mask_try(const ScanParams& P, const TileSrc& tsrc, const WinGeom& geo, const Carry& kin, int mode, Record* wr,
+                          uint64_t text_off, WinResult& res, Fallback&& fallback) {
+    Record tmp[80];
+    const bool wr_mode = mode == MODE_WRITE || mode == MODE_BUFFER;
+    const bool ok = mask_window<SBYTE>(P, tsrc, geo, kin, mode, wr, text_off, res);
+    tsrc.mask_result(ok);
+    if (!ok) return false;
+    WinResult r2;
+    fallback(tmp, r2);
+    bool same = r2.nrec == res.nrec && r2.ntext == res.ntext && r2.npend_out == res.npend_out && r2.out.kind == res.out.kind &&
+                r2.out.k == res.out.k && r2.out.in_bytes == res.out.in_bytes && r2.out.out_bytes == res.out.out_bytes &&
+                r2.out.flags == res.out.flags;
+    if (same && wr_mode)
+        for (uint32_t k = 0; k < res.nrec && (mode == MODE_WRITE || k < kBufRecs); ++k)
+            same = same && tmp[k].position == wr[k].position && tmp[k].in_start == wr[k].in_start && tmp[k].in_len == wr[k].in_len &&
+                   tmp[k].flags == wr[k].flags && tmp[k].precision == wr[k].precision && tmp[k].text_off == wr[k].text_off &&
+                   tmp[k].text_len == wr[k].text_len;
+    if (!same) tsrc.mask_mismatch(geo.ws, geo.we, kin, mode);
+    return true;
+}
+#endif
+
+// Engine dispatch used by the kernels and the test harness: the mask engine first where it exists (host harness; the
+// kernels call it themselves and queue what it declines), then the byte-wise engines; grep_char / same-unicode-block /
+// chars_min_nb > q missions take the general automaton.
 template <class Dec> struct WindowEngine {
     template <class TileSrc>
     SX_HD static void run(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo, const Carry& kin,
                           int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
+#if !defined(__CUDA_ARCH__)
+        if (MaskFamily<Dec>::kSByte && tsrc.tables() && !P.general && !desc && tsrc.use_mask() &&
+            host_mask_try<true>(P, tsrc, geo, kin, mode, wr, text_off, res, [&](Record* tmp, WinResult& r2) {
+                scan_window<Dec>(P, tsrc, g, geo, kin, mode, tmp, text_off, r2, nullptr);
+            }))
+            return;
+#endif
         scan_window<Dec>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
     }
 };
@@ -636,28 +729,11 @@ template <> struct WindowEngine<DecUtf8> {
                           int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
         if (tsrc.tables() && !P.general) {
 #if !defined(__CUDA_ARCH__)
-            // host harness: the kernels call utf8_mask_window themselves (block_pass) and queue what it declines
-            if (!desc && tsrc.use_mask()) {
-                Record tmp[64];
-                const bool wr_mode = mode == MODE_WRITE || mode == MODE_BUFFER;
-                const bool ok = utf8_mask_window(P, tsrc, geo, kin, mode, wr, text_off, res);
-                tsrc.mask_result(ok);
-                if (ok) {
-                    // self-check of the harness: the byte-wise engine must agree (results and records)
-                    WinResult r2;
+            if (!desc && tsrc.use_mask() &&
+                host_mask_try<false>(P, tsrc, geo, kin, mode, wr, text_off, res, [&](Record* tmp, WinResult& r2) {
                     scan_window_fast_utf8(P, tsrc, g, geo, kin, mode, tmp, text_off, r2, nullptr);
-                    bool same = r2.nrec == res.nrec && r2.ntext == res.ntext && r2.npend_out == res.npend_out &&
-                                r2.out.kind == res.out.kind && r2.out.k == res.out.k && r2.out.in_bytes == res.out.in_bytes &&
-                                r2.out.out_bytes == res.out.out_bytes && r2.out.flags == res.out.flags;
-                    if (same && wr_mode)
-                        for (uint32_t k = 0; k < res.nrec && (mode == MODE_WRITE || k < kBufRecs); ++k)
-                            same = same && tmp[k].position == wr[k].position && tmp[k].in_start == wr[k].in_start &&
-                                   tmp[k].in_len == wr[k].in_len && tmp[k].flags == wr[k].flags && tmp[k].precision == wr[k].precision &&
-                                   tmp[k].text_off == wr[k].text_off;
-                    if (!same) tsrc.mask_mismatch(geo.ws, geo.we, kin, mode);
-                    return;
-                }
-            }
+                }))
+                return;
 #endif
             scan_window_fast_utf8(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
         } else scan_window<DecUtf8>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);

@@ -1219,7 +1219,8 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         // A sparse list of a UTF-8 mission takes the barrier-free pipeline (sx_sparse_utf8.cuh); it needs the entry
         // count on the host (one small round trip), everything else the block kernel with its run classification.
         bool sparse = false;
-        if (pc.enabled && ss->use_sparse && P.enc == ENC_UTF8 && !P.general) {
+        const bool has_mask_engine = P.enc == ENC_UTF8 || P.enc == ENC_XUD || P.enc == ENC_SB;
+        if (pc.enabled && ss->use_sparse && has_mask_engine && !P.general) {
             unsigned long long ne = 0;
             CK(cudaMemcpyAsync(&ne, ss->d_counters + 2, sizeof ne, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -1246,7 +1247,8 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
                     O.host_text = fc->set.t;
                     O.text_cap = std::min<unsigned long long>(O.text_cap, fc->set.tcap);
                 }
-                CK(launch_sparse_utf8(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st, ss->sev));
+                const auto launch = P.enc == ENC_UTF8 ? launch_sparse_utf8 : P.enc == ENC_XUD ? launch_sparse_xud : launch_sparse_sb;
+                CK(launch(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st, ss->sev));
                 ss->stats.kernel_launches += sparse_launches();
                 sparse = true;
             }

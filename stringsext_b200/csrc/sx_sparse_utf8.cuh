@@ -64,9 +64,9 @@ struct SparseBufs {
 constexpr int kSpThreads = 128;
 constexpr uint32_t kQueueHead = 0x80000000u;
 
-__global__ void __launch_bounds__(256) sx_sp_tables_kernel(const __grid_constant__ ScanParams P, Utf8Tables* T) {
+static __global__ void __launch_bounds__(256) sx_sp_tables_kernel(const __grid_constant__ ScanParams P, Utf8Tables* T) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < 2048) utf8_tables_fill(P, *T, k);
+    if (k < 2048) mask_tables_fill(P, *T, k);
 }
 
 struct SpCtx {
@@ -93,6 +93,7 @@ __device__ __forceinline__ void sp_store(EntryState* es, const Carry& kin, const
     if (es->status == ES_PENDING) es->status = ES_DONE;  // sx_sp_fix_kernel leaves DECLINED / DEPENDENT as they are
 }
 // a head (predecessor window not listed) with the byte-wise engine: pre-roll, then one pass under the real carry
+template <class Dec>
 __device__ __noinline__ void sp_head_bytewise(const ScanParams& P, const ExactCfg& X, const SpCtx& c, long long w, EntryState* es) {
     WinGeom wg;
     c.geo.window(w, wg);
@@ -100,11 +101,11 @@ __device__ __noinline__ void sp_head_bytewise(const ScanParams& P, const ExactCf
     if (w != 0) {
         const WinGeom rg = preroll_geom(c.geo, w, X.pre_bytes);
         WinResult rr;
-        WindowEngine<DecUtf8>::run(P, c.ts, c.g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
+        WindowEngine<Dec>::run(P, c.ts, c.g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
         kin0 = rr.out;
     }
     WinResult r;
-    WindowEngine<DecUtf8>::run(P, c.ts, c.g, wg, kin0, MODE_BUFFER, es->staged, 0, r, nullptr);
+    WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin0, MODE_BUFFER, es->staged, 0, r, nullptr);
     sp_store(es, kin0, r);
 }
 
@@ -122,7 +123,7 @@ __device__ __forceinline__ void sp_push(uint32_t* queue, unsigned long long* qco
 
 // Entry roles: a HEAD has no listed predecessor window (its carry-in comes from the pre-roll); a MEMBER continues a
 // run of adjacent windows (its carry-in is the carry-out of the entry before it).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 sx_sp_queue_kernel(const ExactCfg X, const SparseBufs B) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool member = false;
@@ -141,12 +142,13 @@ sx_sp_queue_kernel(const ExactCfg X, const SparseBufs B) {
 }
 
 // a head with the mask engine (pre-roll + one pass under the real carry); false when the engine declines
+template <class Dec>
 __device__ __forceinline__ bool sp_head_mask(const ScanParams& P, const ExactCfg& X, const SpCtx& c, long long w, EntryState* es) {
     WinGeom wg;
     c.geo.window(w, wg);
     WinResult r;
     // one pass: the pre-roll region is the 32 bytes in front of the window (same class planes, same decoder algebra)
-    if (w != 0 && utf8_mask_head(P, c.ts, wg, X.pre_bytes, MODE_BUFFER, es->staged, 0, r)) {
+    if (w != 0 && mask_head<MaskFamily<Dec>::kSByte>(P, c.ts, wg, X.pre_bytes, MODE_BUFFER, es->staged, 0, r)) {
         sp_store(es, r.in, r);
         return true;
     }
@@ -154,26 +156,28 @@ __device__ __forceinline__ bool sp_head_mask(const ScanParams& P, const ExactCfg
     if (w != 0) {
         const WinGeom rg = preroll_geom(c.geo, w, X.pre_bytes);
         WinResult rr;
-        if (!utf8_mask_window(P, c.ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr)) return false;
+        if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr)) return false;
         kin0 = rr.out;
     }
-    if (!utf8_mask_window(P, c.ts, wg, kin0, MODE_BUFFER, es->staged, 0, r)) return false;
+    if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin0, MODE_BUFFER, es->staged, 0, r)) return false;
     sp_store(es, kin0, r);
     return true;
 }
 // a member under its real carry: mask engine, byte-wise engine when it declines
+template <class Dec>
 __device__ __forceinline__ Carry sp_member(const ScanParams& P, const SpCtx& c, long long w, const Carry& kin, EntryState* es) {
     WinGeom wg;
     c.geo.window(w, wg);
     WinResult r;
-    if (!utf8_mask_window(P, c.ts, wg, kin, MODE_BUFFER, es->staged, 0, r))
-        WindowEngine<DecUtf8>::run(P, c.ts, c.g, wg, kin, MODE_BUFFER, es->staged, 0, r, nullptr);
+    if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin, MODE_BUFFER, es->staged, 0, r))
+        WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin, MODE_BUFFER, es->staged, 0, r, nullptr);
     sp_store(es, kin, r);
     return r.out;
 }
 
 // 6 CTAs of 128 threads per SM (80 registers): measured best for this latency-bound kernel (4: 0.35 ms, 6: 0.29 ms, 8: 0.39 ms
 // before the one-pass heads)
+template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 6)
 sx_sp_heads_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
@@ -184,7 +188,7 @@ sx_sp_heads_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const
     if (e < B.NE) {
         const long long w = list_window(X, X.cta_off, e);
         const bool adj = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
-        if (!adj && !sp_head_mask(P, X, c, w, &B.E[e])) { B.E[e].status = ES_DECLINED; declined = true; }
+        if (!adj && !sp_head_mask<Dec>(P, X, c, w, &B.E[e])) { B.E[e].status = ES_DECLINED; declined = true; }
     }
     sp_push(B.queue2, B.qcount2, declined, (uint32_t)e);
 }
@@ -193,6 +197,7 @@ sx_sp_heads_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const
 // entry is a resolved head, and computable from the window alone when its carry-out does not depend on its own
 // carry-in (mask engine under the null carry, WinResult.cut1 == 0).  What remains is walked in order by
 // sx_sp_fix_kernel.  Persistent over the queue.
+template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
@@ -217,7 +222,7 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
                 WinGeom pg;
                 c.geo.window(w - 1, pg);
                 WinResult rr;
-                if (utf8_mask_window(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr)) {
+                if (mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr)) {
                     known = rr.cut1 == 0;
                     kin = rr.out;
                     if (rr.caseb) {  // the walk of sx_sp_fix_kernel gets through that window without a pass
@@ -228,7 +233,7 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
                     // the mask engine declines (e.g. a window crowded with findings): the byte-wise engine's
                     // transfer-function summary decides, so that such windows do not chain up in sx_sp_fix_kernel
                     WinDesc d;
-                    WindowEngine<DecUtf8>::run(P, c.ts, c.g, pg, carry_none(), MODE_COUNT, nullptr, 0, rr, &d);
+                    WindowEngine<Dec>::run(P, c.ts, c.g, pg, carry_none(), MODE_COUNT, nullptr, 0, rr, &d);
                     known = d.type == WT_CONST;
                     kin = d.null_out;
                     if (d.type == WT_CASEB) {
@@ -237,7 +242,7 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
                     }
                 }
             }
-            if (known) sp_member(P, c, w, kin, &B.E[e]);
+            if (known) sp_member<Dec>(P, c, w, kin, &B.E[e]);
             else { B.E[e].status = ES_DEPENDENT; dependent = true; }
         }
         sp_push(B.queue2, B.qcount2, dependent, (uint32_t)e);
@@ -247,6 +252,7 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
 // What the parallel stages left: heads the mask engine declined (byte-wise engine) and members whose carry-in needs
 // the entry before them resolved first -- walked in stream order from the first member whose predecessor is resolved.
 // Entry statuses are frozen here (decisions only read what the earlier kernels wrote).  Persistent over queue2.
+template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_fix_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
@@ -261,12 +267,12 @@ sx_sp_fix_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
         if (st == ES_DECLINED) {
             // followed by a member: that member is dependent and its walker resolves this head first
             const bool next_adj = e + 1 < B.NE && list_window(X, X.cta_off, e + 1) == w + 1;
-            if (!next_adj) sp_head_bytewise(P, X, c, w, &B.E[e]);
+            if (!next_adj) sp_head_bytewise<Dec>(P, X, c, w, &B.E[e]);
             continue;
         }
         const uint8_t ps = B.E[e - 1].status;
         if (ps == ES_DEPENDENT) continue;  // the walk that started further left comes through here
-        if (ps == ES_DECLINED) sp_head_bytewise(P, X, c, w - 1, &B.E[e - 1]);
+        if (ps == ES_DECLINED) sp_head_bytewise<Dec>(P, X, c, w - 1, &B.E[e - 1]);
         Carry kin = B.E[e - 1].kout;
         long long m = e, wm = w;
         for (;;) {
@@ -281,7 +287,7 @@ sx_sp_fix_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
                 WinGeom wg;
                 c.geo.window(wm, wg);
                 kin = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws));
-            } else kin = sp_member(P, c, wm, kin, es);
+            } else kin = sp_member<Dec>(P, c, wm, kin, es);
             ++m;
             if (m >= B.NE || B.E[m].status != ES_DEPENDENT) break;
             const long long wn = list_window(X, X.cta_off, m);
@@ -292,6 +298,7 @@ sx_sp_fix_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
 }
 
 // members whose carry-in sx_sp_fix_kernel settled in closed form: resolved here, all at once
+template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_late_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
@@ -302,7 +309,7 @@ sx_sp_late_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const 
          t += (unsigned long long)gridDim.x * kSpThreads) {
         const long long e = (long long)B.queue2[t];
         EntryState* const es = &B.E[e];
-        if (es->kin_known && !es->resolved) sp_member(P, c, list_window(X, X.cta_off, e), es->kin, es);
+        if (es->kin_known && !es->resolved) sp_member<Dec>(P, c, list_window(X, X.cta_off, e), es->kin, es);
     }
 }
 
@@ -320,6 +327,7 @@ __device__ __forceinline__ void sp_block_sum2(unsigned long long& a, unsigned lo
     __syncthreads();
 }
 
+template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_ext_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
@@ -339,8 +347,8 @@ sx_sp_ext_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
         if (carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.total_windows) {
             const WinGeom xg = ext_geom(c.geo, w + 1, X.pre_bytes);
             WinResult r;
-            if (!utf8_mask_window(P, c.ts, xg, kout, MODE_BUFFER, es->xstaged, 0, r))
-                WindowEngine<DecUtf8>::run(P, c.ts, c.g, xg, kout, MODE_BUFFER, es->xstaged, 0, r, nullptr);
+            if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, xg, kout, MODE_BUFFER, es->xstaged, 0, r))
+                WindowEngine<Dec>::run(P, c.ts, c.g, xg, kout, MODE_BUFFER, es->xstaged, 0, r, nullptr);
             xr = r.nrec; xt = r.ntext;
             es->xcnt_r = xr;
             es->xcnt_t = xt;
@@ -354,7 +362,7 @@ sx_sp_ext_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
 }
 
 // exclusive scan of the per-CTA totals, in place; grand totals -> counters[0], counters[1]
-__global__ void __launch_bounds__(1024) sx_sp_scan_kernel(ulonglong2* btot, uint32_t nb, unsigned long long* counters) {
+static __global__ void __launch_bounds__(1024) sx_sp_scan_kernel(ulonglong2* btot, uint32_t nb, unsigned long long* counters) {
     __shared__ unsigned long long wa[32], wb[32];
     __shared__ unsigned long long carry_a, carry_b;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -390,6 +398,7 @@ __global__ void __launch_bounds__(1024) sx_sp_scan_kernel(ulonglong2* btot, uint
     if (tid == 0) { counters[0] = carry_a; counters[1] = carry_b; }
 }
 
+template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
@@ -467,8 +476,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
                 WinGeom wg;
                 c.geo.window(list_window(X, X.cta_off, e), wg);
                 WinResult r;
-                if (!utf8_mask_window(P, c.ts, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r))
-                    WindowEngine<DecUtf8>::run(P, c.ts, c.g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+                if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r))
+                    WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
                 if (host_out) for (uint32_t k = 0; k < cr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
         }
@@ -483,8 +492,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
             } else {
                 const WinGeom xg = ext_geom(c.geo, list_window(X, X.cta_off, e) + 1, X.pre_bytes);
                 WinResult r;
-                if (!utf8_mask_window(P, c.ts, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r))
-                    WindowEngine<DecUtf8>::run(P, c.ts, c.g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
+                if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r))
+                    WindowEngine<Dec>::run(P, c.ts, c.g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
                 if (host_out) for (uint32_t k = 0; k < xr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
         }
@@ -540,7 +549,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
 }
 
 // ev[0..6]: timing events recorded between the stages (the library reports per-stage kernel times in sx_scan_stats)
-inline cudaError_t launch_sparse_utf8_impl(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B, int num_sms,
+template <class Dec>
+inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B, int num_sms,
                                            cudaStream_t st, cudaEvent_t* ev) {
     const unsigned nb = (unsigned)((B.NE + kSpThreads - 1) / kSpThreads);
     const unsigned pgrid = std::min<unsigned>(nb, (unsigned)num_sms * 4u);
@@ -548,17 +558,17 @@ inline cudaError_t launch_sparse_utf8_impl(const ScanParams& P, const ScanOut& O
     sx_sp_tables_kernel<<<8, 256, 0, st>>>(P, B.tables);
     sx_sp_queue_kernel<<<(unsigned)((B.NE + 255) / 256), 256, 0, st>>>(X, B);
     cudaEventRecord(ev[1], st);
-    sx_sp_heads_kernel<<<nb, kSpThreads, 0, st>>>(P, X, B);
+    sx_sp_heads_kernel<Dec><<<nb, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[2], st);
-    sx_sp_members_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
+    sx_sp_members_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[3], st);
-    sx_sp_fix_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
-    sx_sp_late_kernel<<<pgrid, kSpThreads, 0, st>>>(P, X, B);
+    sx_sp_fix_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
+    sx_sp_late_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[4], st);
-    sx_sp_ext_kernel<<<nb, kSpThreads, 0, st>>>(P, X, B);
+    sx_sp_ext_kernel<Dec><<<nb, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[5], st);
     sx_sp_scan_kernel<<<1, 1024, 0, st>>>(B.btot, nb, O.counters);
-    sx_sp_gather_kernel<<<nb, kSpThreads, 0, st>>>(P, O, X, B);
+    sx_sp_gather_kernel<Dec><<<nb, kSpThreads, 0, st>>>(P, O, X, B);
     cudaEventRecord(ev[6], st);
     return cudaGetLastError();
 }

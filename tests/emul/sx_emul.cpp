@@ -127,11 +127,11 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         if (memcmp(&rs.out, &kout, sizeof(Carry)) != 0) { stats[3]++; kout = rs.out; }
         WinResult rc;
         emit_window(wg, kin, rc);
-        if (!adjacent && w != 0 && P.enc == ENC_UTF8 && !P.general && g_use_mask && g_use_fast) {
+        if (!adjacent && w != 0 && MaskFamily<Dec>::kHas && !P.general && g_use_mask && g_use_fast) {
             // the product resolves heads in one pass (carry-in derived from the 32 bytes before the window): same
             // carry-in as the pre-roll, same counts and carry-out as the pass under that carry
             WinResult rh;
-            if (utf8_mask_head(P, ts, wg, pre_bytes, MODE_COUNT, nullptr, 0, rh)) {
+            if (mask_head<MaskFamily<Dec>::kSByte>(P, ts, wg, pre_bytes, MODE_COUNT, nullptr, 0, rh)) {
                 g_head_ok++;
                 const bool same = memcmp(&rh.in, &kin, sizeof(Carry)) == 0 && memcmp(&rh.out, &rc.out, sizeof(Carry)) == 0 &&
                                   rh.nrec == rc.nrec && rh.ntext == rc.ntext && rh.npend_out == rc.npend_out;
@@ -143,11 +143,11 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
                 }
             }
         }
-        if (P.enc == ENC_UTF8 && !P.general && g_use_mask && g_use_fast) {
+        if (MaskFamily<Dec>::kHas && !P.general && g_use_mask && g_use_fast) {
             // the sparse pipeline's closed form for windows that are one short run (WinResult.caseb of a pass under the
             // null carry): eval_caseb from the real carry-in must give the real carry-out
             WinResult rn;
-            const bool rn_ok = utf8_mask_window(P, ts, wg, carry_none(), MODE_STATE, nullptr, 0, rn);
+            const bool rn_ok = mask_window<MaskFamily<Dec>::kSByte>(P, ts, wg, carry_none(), MODE_STATE, nullptr, 0, rn);
             if (rn_ok && rn.cut1 == 0) {
                 // "the carry-out does not depend on the carry-in" (sx_sp_members_kernel takes the null-carry result as the
                 // next entry's carry-in): must equal the carry-out under the real carry-in
@@ -228,7 +228,7 @@ uint64_t sx_emul_mask_mismatches() { return g_mask_mismatch; }
 uint64_t sx_emul_head_ok() { return g_head_ok; }
 void sx_emul_indep_counts(uint64_t* indep, uint64_t* dep) { *indep = g_indep; *dep = g_dep; }
 int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
-    for (uint32_t i = 0; i < 2048; ++i) utf8_tables_fill(*P, g_tables, i);
+    for (uint32_t i = 0; i < 2048; ++i) mask_tables_fill(*P, g_tables, i);
     std::vector<uint32_t> list;
     std::vector<Record> recs;
     std::vector<uint8_t> text;

@@ -385,3 +385,35 @@ def test_sparse_pipeline_forced_on_dense_input(n, q, ubf, kind):
         assert ra == exp and rb == exp
         check_state(a, os_)
         check_state(b, os_)
+
+
+@pytest.mark.parametrize("label,n,q,kind", [("ascii", 4, 64, "rand"), ("ascii", 6, 64, "mixed"), ("koi8-r", 6, 64, "rand"),
+                                           ("windows-1252", 8, 64, "text"), ("koi8-r", 3, 32, "runs"), ("ascii", 10, 64, "text"),
+                                           ("ibm866", 2, 64, "lowent"), ("iso-8859-5", 16, 16, "mixed")])
+def test_sparse_pipeline_single_byte_encodings(label, n, q, kind):
+    """x-user-defined / table-driven single-byte missions: the per-stage pipeline with the single-byte mask engine
+    == the block kernel == the oracle, incl. chained calls and is_last."""
+    m = M.Mission.for_label(label, n, output_line_char_nb_max=q)
+    rng = random.Random(1234 + n + q)
+    size = 900000 + rng.randrange(5000)
+    if kind == "rand":
+        buf = corpus.sx_mix_bytes(21, 0, size)
+        corpus.plant(buf, 21, m.encoding_id, n, q, density=1 << 13)
+        buf = buf.tobytes()
+    else:
+        buf = corpus.gen(rng, kind, size, m.encoding_id)
+    a, b, os_ = sx.ScannerState(m), sx.ScannerState(m), oracle_state(m)
+    b.set_sparse(0)
+    cuts = [0, 4096 * 60 + 1, 4096 * 130, len(buf)]
+    used = 0
+    for lo, hi in zip(cuts, cuts[1:]):
+        last = hi == len(buf)
+        ra = gpu_findings(a.scan_stream(buf[lo:hi], last, 4096))
+        rb = gpu_findings(b.scan_stream(buf[lo:hi], last, 4096))
+        exp = oracle_findings(os_.scan_stream(buf[lo:hi], last, 4096))
+        used += a.last_stats.sparse_used
+        assert b.last_stats.sparse_used == 0
+        assert ra == exp and rb == exp
+        check_state(a, os_)
+        check_state(b, os_)
+    assert used >= 1 or q != 64
