@@ -1225,15 +1225,18 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             CK(cudaMemcpyAsync(&ne, ss->d_counters + 2, sizeof ne, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             ss->stats.d2h_bytes += sizeof ne;
-            // whenever the per-entry state (240 B per listed window) fits a 16 GiB budget; beyond that (more than ~8 GiB
-            // of text-like input in one call) the block kernel
-            const bool fits_mem = ne * (unsigned long long)sparse_entry_bytes() <= (16ull << 30);
+            // whenever the per-entry state (240 B per listed window) fits a 24 GiB budget and can be allocated; beyond
+            // that (more than ~12 GiB of text-like input in one call) the block kernel
+            const size_t nb = (size_t)((ne + sparse_threads() - 1) / sparse_threads());
+            bool fits_mem = ne * (unsigned long long)sparse_entry_bytes() <= (24ull << 30);
             if (ne > 0 && fits_mem) {
-                const size_t nb = (size_t)((ne + sparse_threads() - 1) / sparse_threads());
-                if (!grow(&ss->d_entries, &ss->entries_cap, (size_t)ne * sparse_entry_bytes())) return fail;
-                if (!grow(&ss->d_btot, &ss->btot_cap, (nb + 1) * sizeof(ulonglong2))) return fail;
-                if (!grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes())) return fail;
-                if (!grow(&ss->d_queue, &ss->queue_cap, (2 * (size_t)ne + 128) * sizeof(uint32_t))) return fail;
+                fits_mem = grow(&ss->d_entries, &ss->entries_cap, (size_t)ne * sparse_entry_bytes()) &&
+                           grow(&ss->d_btot, &ss->btot_cap, (nb + 1) * sizeof(ulonglong2)) &&
+                           grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes()) &&
+                           grow(&ss->d_queue, &ss->queue_cap, (2 * (size_t)ne + 128) * sizeof(uint32_t));
+                if (!fits_mem) { cudaGetLastError(); set_err(SX_OK, ""); }  // out of device memory: the block kernel needs far less
+            }
+            if (ne > 0 && fits_mem) {
                 // direct host output: the gather kernel writes the findings in their C-ABI form into a pinned set
                 const size_t want_f = !ss->use_direct ? 0 : (ss->have_history ? need_recs : std::min(need_recs, std::max(ss->host_rec_hint, need_recs_min)));
                 const size_t want_t = ss->have_history ? need_text : std::min(need_text, std::max(ss->host_text_hint, need_text_min));
