@@ -397,6 +397,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "peak_note": "the measured peak is a device copy (read + write); a read-only pass can slightly exceed it",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "kernels_ms": kernels,
                          "pipeline_ms": avg(scan_ms), "pipeline_gbs": size / 1e9 / (avg(scan_ms) / 1e3),
                          "windows_total": int(win_total), "windows_listed": int(win_listed),
