@@ -441,7 +441,20 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
     }
     const bool seg1_before = k_in > 0 || (!SBYTE && at_slice_start && pend0 > 0 && straddle_completes);
     const bool probe_seg1 = false;
-    const bool probe_seg0 = !SBYTE && at_slice_start && mode != MODE_STATE && k_in > 0;  // second segment at the slice start
+    // Second segment at the slice start (the pending sequence broke at byte 0, which is read again) with a leftover in
+    // front: the probe fires if that segment begins with a complete multi-byte char, and compares the fresh decode
+    // with what sits at the start of the output buffer (probe_utf8, the literal emulation).
+    bool seg0_before = false;
+    if (!SBYTE && at_slice_start && mode != MODE_STATE && k_in > 0 && m5_bit(pre, 32) && m5_bit(lead, 32)) {
+        bool completes = false;
+#pragma unroll
+        for (uint32_t p = 1; p < 4; ++p) {
+            if ((int32_t)p >= wlen || !m5_bit(acc, 32 + p)) break;
+            if (!m5_bit(pendm, 32 + p)) { completes = true; break; }
+        }
+        if (completes) seg0_before = probe_utf8(P, tsrc.g, geo.slice_start, geo.slice_end, false, pend0, kin);
+    }
+    const bool probe_seg0 = false;
     const uint32_t lo_flags = (k_in > 0 && (kin.flags & CF_HOSTCARRY)) ? (uint32_t)RF_HOSTCARRY : 0u;
 
     // One run of passing chars [sB, eB] (bit indices of its first / last byte).  is_left: it continues whatever touches
@@ -474,7 +487,8 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
         const uint32_t fl0 = (is_left ? lo_flags : 0u) | (lastcut0 ? (uint32_t)RF_COMPLETES : 0u);
         const bool yields = total >= q || (touches_end ? lastcut0 : (lastcut0 || total >= n));
         if (yields && ((seg_id == 0 && probe_seg0) || (seg_id < 0 && probe_seg1))) return false;
-        uint32_t prec = (seg_id == last_seg) ? PREC_AFTER : ((seg_id < 0 && seg1_before) ? PREC_BEFORE : PREC_EXACT);
+        uint32_t prec = (seg_id == last_seg) ? PREC_AFTER
+                        : ((seg_id < 0 && seg1_before) || (seg_id == 0 && seg0_before)) ? PREC_BEFORE : PREC_EXACT;
         const int32_t seg_rel = seg_id < 0 ? 0 : seg_id;
         if (yields) last_seg = seg_id;
         // a finding, or the leftover at the window end, of the first segment after the left run (cut := false / kept)
