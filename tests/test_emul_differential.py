@@ -90,3 +90,50 @@ def test_planted_corpus_utf16():
         o = os_.scan_stream(buf, False, 4096).v
         assert len(o) > 5
         _cmp(es, os_, f, o)
+
+
+@pytest.mark.parametrize("enc", [1, 0, 4])
+def test_mask_engine_cross_checks(enc):
+    """The bit-parallel window engines (sx_mask_utf8.cuh: UTF-8 and the single-byte family) run on the CPU by the
+    harness: every call is cross-checked against the byte-wise engine (results and records), the one-pass head against
+    pre-roll + pass, the carry-independence claim and the closed form (eval_caseb) against a replay under the real
+    carry; the findings against the oracle."""
+    import ctypes as C
+    import dataclasses
+
+    L = emul.lib()
+    L.sx_emul_mask_mismatches.restype = C.c_uint64
+    L.sx_emul_head_ok.restype = C.c_uint64
+    ok0, dec0 = C.c_uint64(), C.c_uint64()
+    L.sx_emul_mask_counts(C.byref(ok0), C.byref(dec0))
+    heads0, mism0 = L.sx_emul_head_ok(), L.sx_emul_mask_mismatches()
+    rng = random.Random(2024 + enc)
+    for it in range(24):
+        m = corpus.random_mission(rng, enc, M)
+        q = rng.choice([64, 64, 64, 32, 16, 8])
+        m = dataclasses.replace(m, output_line_char_nb_max=q, chars_min_nb=min(rng.choice([1, 2, 3, 4, 6, 10, 16]), q))
+        kind = rng.choice(["rand", "rand", "mixed", "lowent", "runs", "text"])
+        size = rng.choice([1 << 16, (1 << 17) + 77, 200000])
+        if kind == "rand":
+            buf = corpus.sx_mix_bytes(it + 500, 0, size)
+            corpus.plant(buf, it, enc, m.chars_min_nb, q, density=1 << 12)
+            buf = buf.tobytes()
+        else:
+            buf = corpus.gen(rng, kind, size, enc)
+        es, os_ = emul.EmulState(m), oracle_state(m)
+        cuts = [0] + sorted(rng.sample(range(1, len(buf)), rng.choice([0, 1, 2]))) + [len(buf)]
+        for a, b in zip(cuts, cuts[1:]):
+            f, _ = es.scan_stream(buf[a:b], False, rng.choice([4096, 4096, 512]))
+            # (the oracle must see the same slicing)
+        es2, os2 = emul.EmulState(m), oracle_state(m)
+        for a, b in zip(cuts, cuts[1:]):
+            f, _ = es2.scan_stream(buf[a:b], False, 4096)
+            o = os2.scan_stream(buf[a:b], False, 4096).v
+            _cmp(es2, os2, f, o)
+        assert es.stats[3] == 0 and es2.stats[3] == 0 and es2.stats[4] == 0 and es2.stats[5] == 0 and es2.stats[6] == 0
+    ok1, dec1 = C.c_uint64(), C.c_uint64()
+    L.sx_emul_mask_counts(C.byref(ok1), C.byref(dec1))
+    assert L.sx_emul_mask_mismatches() == mism0          # mask engine == byte-wise engine on every call it accepted
+    assert ok1.value - ok0.value > 10000                 # ... and it accepted most of them
+    assert ok1.value - ok0.value > 3 * (dec1.value - dec0.value)
+    assert L.sx_emul_head_ok() > heads0                  # the one-pass head path was exercised
