@@ -283,10 +283,9 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
 
     // event masks shared by both families: acc / pendm (UTF-8 decoder), pre / seg (segment starts), pe (passing char
     // ends), R (bytes of passing chars), lead (UTF-8 lead bytes), TL0 / TL1 (single-byte: UTF-8 length - 1 of the char)
-    M5 acc, pendm, pre, seg, pe, R, lead, TL0, TL1;
+    M5 acc, pendm, pre, seg, pe, R, lead, TL0, TL1, mal;
     if (SBYTE) {
         // class table bits: 0 verdict, 1 unmapped (malformed, DecSb), 2-3 UTF-8 length - 1 of the mapped char
-        M5 mal;
 #pragma unroll
         for (int i = 0; i < NW + 1; ++i) {
             const uint32_t pv = (LB32 && i == 0) ? 0xFFFFFFFFu : V.w[i];
@@ -325,7 +324,7 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
             PS.w[i] = pl[4].w[i];
         }
         // ---- decoder: accepted continuation bytes -----------------------------------------------------------------
-        M5 ok1, ok2, ok3, mal;
+        M5 ok1, ok2, ok3;
         {
             const M5 s_plain = m5_shl<1>(plain), s_e0 = m5_shl<1>(E0), s_ed = m5_shl<1>(ED), s_f0 = m5_shl<1>(F0), s_f4 = m5_shl<1>(F4);
     #pragma unroll
@@ -469,12 +468,19 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
     bool has_left = false;       // a run continues what touches the left boundary and ends inside the window at left_end
     uint32_t left_end = 0;
     bool seg1_cleared = false;   // ... and a later event of the first segment resets the "maybe cut" flag it may leave behind
-    auto do_run = [&](int32_t sB, uint32_t eB, bool is_left, bool touches_end) -> bool {
+    // A run that ends exactly at a forced cut inside the window leaves the "maybe cut" flag set (helper.rs:353,
+    // finding_collection.rs:268).  It is reset by the next finding or leftover of the same segment; at the next
+    // segment start it becomes that segment's "last was cut" (finding_collection.rs:240-241): a run beginning right
+    // there completes the cut finding whatever its length; with no segment start left it is the window's carry-out.
+    bool cutp = false, cutp_used = false;
+    int32_t cutp_seg = 0;
+    uint32_t cutp_pos = 0;
+    auto do_run = [&](int32_t sB, uint32_t eB, bool is_left, bool touches_end, bool lastcut_in = false) -> bool {
         const uint32_t fromB = sB < 32 ? 32u : (uint32_t)sB;  // chars are counted at their last byte
         const uint32_t k0 = is_left ? k_in : 0u;
         const uint32_t inwin = m5_count(pe, fromB, eB);
         const uint32_t total = inwin + k0;
-        const bool lastcut0 = is_left && kc;
+        const bool lastcut0 = (is_left && kc) || lastcut_in;
         int32_t seg_id = -1;
         if (!is_left) {
             const int32_t sg = m5_high_le(seg, (uint32_t)sB);  // segment start at or before the run
@@ -491,6 +497,7 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
                         : ((seg_id < 0 && seg1_before) || (seg_id == 0 && seg0_before)) ? PREC_BEFORE : PREC_EXACT;
         const int32_t seg_rel = seg_id < 0 ? 0 : seg_id;
         if (yields) last_seg = seg_id;
+        if (cutp && seg_id == cutp_seg && (yields || touches_end)) cutp = false;  // reset by this finding / leftover
         // a finding, or the leftover at the window end, of the first segment after the left run (cut := false / kept)
         if (!is_left && seg_id < 0 && (touches_end || total >= n)) seg1_cleared = true;
         if (total < q) {
@@ -531,12 +538,30 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
         }
         if (remaining == 0) {
             // the run ends exactly at a cut: the "maybe cut" flag outlives it (until the next segment / the window end)
-            if (!touches_end) return false;
-            carry_done = true;
-            res.out = carry_cut();
+            if (touches_end) { carry_done = true; res.out = carry_cut(); }
+            else {
+                if (cutp_used) return false;  // twice in one window: byte-wise engine
+                cutp = true; cutp_used = true; cutp_seg = seg_id; cutp_pos = eB;
+            }
         } else {
             mask_emit(E, seg_rel, prec, piece_s, (int32_t)eB + 1 - 32, piece_t0 + T(piece_from, eB), RF_COMPLETES);
             if (touches_end) { carry_done = true; res.out = carry_cut(); }
+        }
+        return true;
+    };
+
+    // hands a pending "maybe cut" flag to the segment that starts before bit index `upto`; *ran_to: last byte of the run
+    // it processed (a run beginning at that segment start), 0 if none
+    auto flush_cut = [&](uint32_t upto, uint32_t* ran_to) -> bool {
+        *ran_to = 0;
+        if (!cutp) return true;
+        const uint32_t s1 = m5_low_ge(seg, cutp_pos + 1);
+        if (s1 >= 32u + (uint32_t)wlen || s1 > upto) return true;
+        cutp = false;
+        if (m5_bit(R, s1)) {
+            const uint32_t e2 = m5_low_ge(RE, s1);
+            if (!do_run((int32_t)s1, e2, false, e2 + 1 >= Bend, true)) return false;
+            *ran_to = e2;
         }
         return true;
     };
@@ -609,10 +634,16 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
             next_B = e_last + 1;
             const int32_t s = m5_high_le(RS, e_last);
             if (s < 32) return false;
-            if (!do_run(s, e_last, false, e_last + 1 >= Bend)) return false;
+            uint32_t ran_to;
+            if (!flush_cut((uint32_t)s, &ran_to)) return false;
+            if (ran_to != e_last && !do_run(s, e_last, false, e_last + 1 >= Bend)) return false;
             if (carry_done) break;
         }
         if (guard == 12) return false;  // a window crowded with short findings: byte-wise engine
+    }
+    if (!carry_done) {
+        uint32_t ran_to;
+        if (!flush_cut(0xFFFFFFFFu, &ran_to)) return false;
     }
     // ---- carry out: a short run of complete chars touching the window end (finding_collection.rs:281-284) ---------
     if (!carry_done && Bend > 32 && m5_bit(R, Bend - 1)) {
@@ -620,6 +651,9 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
         if (ts < 32) return false;
         if (!do_run(ts, Bend - 1, false, true)) return false;
     }
+    // a malformed last byte starts an (empty) segment at the window end, which swallows the flag (finding_collection.rs:134-143)
+    const bool seg_at_end = m5_bit(mal, 31u + (uint32_t)wlen);
+    if (cutp && !carry_done && !seg_at_end) res.out = carry_cut();  // no segment start behind the run: the flag is the carry (Q4)
     if (has_left) {
         // Does the carry-out depend on the carry-in?  The carry-in decides whether the left run is printed (no trace in
         // the carry) and, when leftover + run is an exact multiple of q, leaves the "maybe cut" flag set behind the run
@@ -630,7 +664,7 @@ SX_HD_NOINLINE bool mask_window_nw(const ScanParams& P, const TileSrc& tsrc, con
         bool dep = false;
         if (!seg1_cleared) {
             const uint32_t s1 = m5_low_ge(seg, left_end + 1);
-            if (s1 >= 32u + (uint32_t)wlen) dep = true;  // the first segment runs to the window end: the flag is the carry
+            if (s1 >= 32u + (uint32_t)wlen) dep = !seg_at_end;  // the first segment runs to the window end: the flag is the carry
             else if (m5_bit(R, s1)) {
                 const uint32_t e2 = m5_low_ge(RE, s1);
                 dep = e2 + 1 >= Bend && m5_count(pe, s1, e2) < q;
