@@ -142,7 +142,7 @@ typedef struct {
     uint64_t windows_total, windows_listed;
     float host_total_ms; /* wall clock of the whole call */
     float host_post_ms;  /* of which: building the collection after the last device sync */
-    float sparse_stage_ms[6]; /* sparse pipeline (sparse_used): tables+queue, heads, members, fix, ext, scan+gather kernels */
+    float sparse_stage_ms[6]; /* sparse pipeline (sparse_used): tables, heads, members, fix+late, ext, scan+gather kernels */
     float host_phase_ms[4]; /* wall clock: [0] call start -> kernels enqueued, [1] -> counters back (first sync),
                              * [2] -> results downloaded (second sync), [3] -> collection built */
 } sx_scan_stats;

@@ -595,11 +595,14 @@ cudaError_t launch_exact_utf32be(const ScanParams& P, const ScanOut& O, const Ex
 
 // sparse-list pipeline for UTF-8 (sx_sparse_utf8.cuh, compiled into the UTF-8 translation unit)
 cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                               void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev);
+                               void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side,
+        cudaEvent_t* evs);
 cudaError_t launch_sparse_xud(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                              void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev);
+                              void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side,
+        cudaEvent_t* evs);
 cudaError_t launch_sparse_sb(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                             void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev);
+                             void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side,
+        cudaEvent_t* evs);
 size_t sparse_entry_bytes();
 size_t sparse_tables_bytes();
 uint32_t sparse_threads();

@@ -44,7 +44,7 @@ cudaError_t SX_NAME(const ScanParams& P, const ScanOut& O, const ExactCfg& X, un
 #define SX_SPARSE_NAME launch_sparse_sb
 #endif
 cudaError_t SX_SPARSE_NAME(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                           void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev) {
+                           void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side, cudaEvent_t* evs) {
     SparseBufs B;
     B.E = static_cast<EntryState*>(entries);
     B.btot = static_cast<ulonglong2*>(btot);
@@ -52,9 +52,9 @@ cudaError_t SX_SPARSE_NAME(const ScanParams& P, const ScanOut& O, const ExactCfg
     B.queue = static_cast<uint32_t*>(queue);
     B.qcount = O.counters + 3;  // the block kernel's claim counter, unused on this path (zeroed per attempt)
     B.queue2 = B.queue + NE + 32;
-    B.qcount2 = O.counters + 4;
+    B.qcount2 = O.counters + 4;  // [5]: snapshot of [4] for sx_sp_declined_kernel
     B.NE = NE;
-    return launch_sparse_impl<SX_DEC>(P, O, X, B, num_sms, st, ev);
+    return launch_sparse_impl<SX_DEC>(P, O, X, B, num_sms, st, ev, side, evs);
 }
 #endif
 #if SX_INST == 1

@@ -779,6 +779,8 @@ struct sx_scanner_state {
     FinalState* d_final = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t sev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // sparse pipeline stages
+    cudaEvent_t sord[2] = {nullptr, nullptr};  // ... ordering with the side stream (declined heads beside the members)
+    cudaStream_t side = nullptr;
     int num_sms = 0;
     double rec_per_byte = 1.0 / 1024, text_per_byte = 1.0 / 64;
     // direct host output: cap on the pinned set of a state's FIRST scan (the estimate from rec_per_byte is generous
@@ -899,6 +901,8 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
               cuda_ok(cudaMalloc(&ss->d_final, sizeof(FinalState)), "cudaMalloc");
     for (int i = 0; ok && i < 6; ++i) ok = cuda_ok(cudaEventCreate(&ss->ev[i]), "cudaEventCreate");
     for (int i = 0; ok && i < 7; ++i) ok = cuda_ok(cudaEventCreate(&ss->sev[i]), "cudaEventCreate");
+    for (int i = 0; ok && i < 2; ++i) ok = cuda_ok(cudaEventCreateWithFlags(&ss->sord[i], cudaEventDisableTiming), "cudaEventCreate");
+    ok = ok && cuda_ok(cudaStreamCreateWithFlags(&ss->side, cudaStreamNonBlocking), "cudaStreamCreate");
     if (!ok) { sx_scanner_state_free(ss); return fail; }
     return ss;
 }
@@ -912,6 +916,8 @@ void sx_scanner_state_free(sx_scanner_state* ss) {
     cudaFreeHost(ss->h_recs); cudaFreeHost(ss->h_text); cudaFreeHost(ss->h_blocks);
     for (auto e : ss->ev) if (e) cudaEventDestroy(e);
     for (auto e : ss->sev) if (e) cudaEventDestroy(e);
+    for (auto e : ss->sord) if (e) cudaEventDestroy(e);
+    if (ss->side) cudaStreamDestroy(ss->side);
     delete ss;
 }
 
@@ -1251,7 +1257,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
                     O.text_cap = std::min<unsigned long long>(O.text_cap, fc->set.tcap);
                 }
                 const auto launch = P.enc == ENC_UTF8 ? launch_sparse_utf8 : P.enc == ENC_XUD ? launch_sparse_xud : launch_sparse_sb;
-                CK(launch(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st, ss->sev));
+                CK(launch(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st, ss->sev, ss->side, ss->sord));
                 ss->stats.kernel_launches += sparse_launches();
                 sparse = true;
             }

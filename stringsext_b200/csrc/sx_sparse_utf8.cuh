@@ -6,14 +6,14 @@
 // latency of single warps (ncu: barrier stalls, profiles/).  Here every stage is its own kernel and the per-entry
 // results live in a device array (EntryState):
 //
-//   sx_sp_queue_kernel   queues the members of runs of adjacent windows (entries whose predecessor window is listed)
-//   sx_sp_heads_kernel   entries whose predecessor window is not listed: carry-in from the 32 bytes in front of the
+//   sx_sp_heads_kernel   queues the members of runs of adjacent windows (entries whose predecessor window is listed);
+//                        entries whose predecessor window is not listed: carry-in from the 32 bytes in front of the
 //                        window (the pre-roll folded into the mask frame), ONE pass of the mask engine
 //                        (sx_mask_utf8.cuh) -> carry-out, counts, first records
 //   sx_sp_members_kernel members, in parallel: carry-in = carry-out of the entry before, taken from a resolved head or
 //                        recomputed from that window alone when it does not depend on ITS carry-in (WinResult.cut1)
-//   sx_sp_fix_kernel     the rest, few: heads the mask engine declined (byte-wise engine), members behind a
-//                        carry-dependent window (walked in order; a window that is one short run is passed in closed
+//   sx_sp_declined_kernel heads the mask engine declined (byte-wise engine), on a side stream beside the members
+//   sx_sp_fix_kernel     the rest, few: members behind a carry-dependent window (walked in order; a window that is one short run is passed in closed
 //                        form, eval_caseb, and resolved afterwards by sx_sp_late_kernel, in parallel)
 //   sx_sp_ext_kernel     extension windows (a "cut" / long leftover carry reaching an unlisted successor),
 //                        per-entry totals -> per-CTA totals
@@ -123,24 +123,6 @@ __device__ __forceinline__ void sp_push(uint32_t* queue, unsigned long long* qco
 
 // Entry roles: a HEAD has no listed predecessor window (its carry-in comes from the pre-roll); a MEMBER continues a
 // run of adjacent windows (its carry-in is the carry-out of the entry before it).
-static __global__ void __launch_bounds__(256)
-sx_sp_queue_kernel(const ExactCfg X, const SparseBufs B) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool member = false;
-    if (e < B.NE) {
-        const long long w = list_window(X, X.cta_off, e);
-        EntryState* const es = &B.E[e];
-        es->xcnt_r = 0;
-        es->xcnt_t = 0;
-        es->status = ES_PENDING;
-        es->resolved = 0;
-        es->kin_known = 0;
-        es->d_caseb = 0;
-        member = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
-    }
-    sp_push(B.queue, B.qcount, member, (uint32_t)e);
-}
-
 // a head with the mask engine (pre-roll + one pass under the real carry); false when the engine declines
 template <class Dec>
 __device__ __forceinline__ bool sp_head_mask(const ScanParams& P, const ExactCfg& X, const SpCtx& c, long long w, EntryState* es) {
@@ -184,12 +166,20 @@ sx_sp_heads_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const
     SpCtx c;
     sp_setup(P, X, B, T, c);
     const long long e = (long long)blockIdx.x * kSpThreads + threadIdx.x;
-    bool declined = false;
+    bool declined = false, member = false;
     if (e < B.NE) {
         const long long w = list_window(X, X.cta_off, e);
-        const bool adj = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
-        if (!adj && !sp_head_mask<Dec>(P, X, c, w, &B.E[e])) { B.E[e].status = ES_DECLINED; declined = true; }
+        EntryState* const es = &B.E[e];
+        es->xcnt_r = 0;
+        es->xcnt_t = 0;
+        es->status = ES_PENDING;
+        es->resolved = 0;
+        es->kin_known = 0;
+        es->d_caseb = 0;
+        member = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
+        if (!member && !sp_head_mask<Dec>(P, X, c, w, es)) { es->status = ES_DECLINED; declined = true; }
     }
+    sp_push(B.queue, B.qcount, member, (uint32_t)e);  // resolved by sx_sp_members_kernel
     sp_push(B.queue2, B.qcount2, declined, (uint32_t)e);
 }
 
@@ -249,6 +239,24 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
     }
 }
 
+// Heads the mask engine declined (rare: 0.04 % of the entries on binary input), byte-wise.  The byte-wise engine takes
+// ~0.1 ms for one window on a lone warp, so this kernel runs on a side stream beside sx_sp_members_kernel instead of
+// sitting in front of the walks of sx_sp_fix_kernel.  Persistent over queue2 (which only holds declined heads when it
+// is launched).
+template <class Dec>
+__global__ void __launch_bounds__(kSpThreads, 4)
+sx_sp_declined_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B, const unsigned long long* nq_ptr) {
+    __shared__ Utf8Tables T;
+    SpCtx c;
+    sp_setup(P, X, B, T, c);
+    const unsigned long long nq = *nq_ptr;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * kSpThreads + threadIdx.x; t < nq;
+         t += (unsigned long long)gridDim.x * kSpThreads) {
+        const long long e = (long long)B.queue2[t];
+        sp_head_bytewise<Dec>(P, X, c, list_window(X, X.cta_off, e), &B.E[e]);
+    }
+}
+
 // What the parallel stages left: heads the mask engine declined (byte-wise engine) and members whose carry-in needs
 // the entry before them resolved first -- walked in stream order from the first member whose predecessor is resolved.
 // Entry statuses are frozen here (decisions only read what the earlier kernels wrote).  Persistent over queue2.
@@ -263,16 +271,9 @@ sx_sp_fix_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
          t += (unsigned long long)gridDim.x * kSpThreads) {
         const long long e = (long long)B.queue2[t];
         const long long w = list_window(X, X.cta_off, e);
-        const uint8_t st = B.E[e].status;
-        if (st == ES_DECLINED) {
-            // followed by a member: that member is dependent and its walker resolves this head first
-            const bool next_adj = e + 1 < B.NE && list_window(X, X.cta_off, e + 1) == w + 1;
-            if (!next_adj) sp_head_bytewise<Dec>(P, X, c, w, &B.E[e]);
-            continue;
-        }
+        if (B.E[e].status == ES_DECLINED) continue;  // a head: resolved by sx_sp_declined_kernel
         const uint8_t ps = B.E[e - 1].status;
         if (ps == ES_DEPENDENT) continue;  // the walk that started further left comes through here
-        if (ps == ES_DECLINED) sp_head_bytewise<Dec>(P, X, c, w - 1, &B.E[e - 1]);
         Carry kin = B.E[e - 1].kout;
         long long m = e, wm = w;
         for (;;) {
@@ -551,17 +552,24 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
 // ev[0..6]: timing events recorded between the stages (the library reports per-stage kernel times in sx_scan_stats)
 template <class Dec>
 inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B, int num_sms,
-                                           cudaStream_t st, cudaEvent_t* ev) {
+                                      cudaStream_t st, cudaEvent_t* ev, cudaStream_t side, cudaEvent_t* evs) {
     const unsigned nb = (unsigned)((B.NE + kSpThreads - 1) / kSpThreads);
     const unsigned pgrid = std::min<unsigned>(nb, (unsigned)num_sms * 4u);
     cudaEventRecord(ev[0], st);
     sx_sp_tables_kernel<<<8, 256, 0, st>>>(P, B.tables);
-    sx_sp_queue_kernel<<<(unsigned)((B.NE + 255) / 256), 256, 0, st>>>(X, B);
     cudaEventRecord(ev[1], st);
     sx_sp_heads_kernel<Dec><<<nb, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[2], st);
+    // queue2 holds the declined heads now (the members kernel appends its dependent members behind them): snapshot its
+    // length, then resolve those heads on the side stream while the members run
+    cudaMemcpyAsync(B.qcount2 + 1, B.qcount2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st);
+    cudaEventRecord(evs[0], st);
+    cudaStreamWaitEvent(side, evs[0], 0);
+    sx_sp_declined_kernel<Dec><<<std::min<unsigned>(pgrid, (unsigned)num_sms), kSpThreads, 0, side>>>(P, X, B, B.qcount2 + 1);
+    cudaEventRecord(evs[1], side);
     sx_sp_members_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[3], st);
+    cudaStreamWaitEvent(st, evs[1], 0);
     sx_sp_fix_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
     sx_sp_late_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
     cudaEventRecord(ev[4], st);
