@@ -787,6 +787,7 @@ struct sx_scanner_state {
     // until a scan has been seen; an overflow simply reruns the exact stage with the counted sizes)
     size_t host_rec_hint = 1u << 20, host_text_hint = 16u << 20;
     bool have_history = false;
+    size_t last_nrec = 0, last_ntext = 0, last_len = 0;  // previous scan: sizes the next pinned set (+ 1/16)
     sx_scan_stats stats;
 };
 
@@ -823,6 +824,11 @@ static void pinned_free(PinnedSet& s) {
     if (s.t) cudaFreeHost(s.t);
     s = PinnedSet();
 }
+static size_t pinned_bytes(const PinnedSet& s) { return s.fcap * sizeof(sx_finding) + s.tcap; }
+// Pool policy: page-locked memory is not swappable and output-heavy scans need tens of GB of it, so the pool never
+// holds more than one large set (the most recently released one, so that a loop of equal scans reuses it) plus up to
+// 1 GiB of small ones; a request is served by the smallest pooled set that fits.
+constexpr size_t kPoolSmallBytes = 64ull << 20, kPoolSmallTotal = 1ull << 30;
 static bool pinned_acquire(size_t fcap, size_t tcap, PinnedSet* out) {
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -830,10 +836,15 @@ static bool pinned_acquire(size_t fcap, size_t tcap, PinnedSet* out) {
         for (size_t i = 0; i < g_pool.size(); ++i)
             if (g_pool[i].fcap >= fcap && g_pool[i].tcap >= tcap && (best < 0 || g_pool[i].fcap < g_pool[best].fcap)) best = (int)i;
         if (best >= 0) { *out = g_pool[best]; g_pool.erase(g_pool.begin() + best); return true; }
+        // nothing fits: pooled large sets would only sit beside the new allocation
+        for (size_t i = 0; i < g_pool.size();) {
+            if (pinned_bytes(g_pool[i]) > kPoolSmallBytes) { pinned_free(g_pool[i]); g_pool.erase(g_pool.begin() + i); }
+            else ++i;
+        }
     }
     PinnedSet s;
-    s.fcap = fcap + fcap / 4 + 1024;
-    s.tcap = tcap + tcap / 4 + 65536;
+    s.fcap = fcap + fcap / 16 + 1024;
+    s.tcap = tcap + tcap / 16 + 65536;
     if (cudaHostAlloc((void**)&s.f, s.fcap * sizeof(sx_finding), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void**)&s.t, s.tcap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
@@ -847,7 +858,14 @@ static void pinned_release(PinnedSet& s) {
     if (!s.f && !s.t) return;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        if (g_pool.size() < 4) { g_pool.push_back(s); s = PinnedSet(); return; }
+        const bool large = pinned_bytes(s) > kPoolSmallBytes;
+        size_t small_total = 0;
+        for (size_t i = 0; i < g_pool.size();) {
+            if (large && pinned_bytes(g_pool[i]) > kPoolSmallBytes) { pinned_free(g_pool[i]); g_pool.erase(g_pool.begin() + i); continue; }
+            if (pinned_bytes(g_pool[i]) <= kPoolSmallBytes) small_total += pinned_bytes(g_pool[i]);
+            ++i;
+        }
+        if (large || (small_total + pinned_bytes(s) <= kPoolSmallTotal && g_pool.size() < 16)) { g_pool.push_back(s); s = PinnedSet(); return; }
     }
     pinned_free(s);
 }
@@ -1244,8 +1262,13 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             }
             if (ne > 0 && fits_mem) {
                 // direct host output: the gather kernel writes the findings in their C-ABI form into a pinned set
-                const size_t want_f = !ss->use_direct ? 0 : (ss->have_history ? need_recs : std::min(need_recs, std::max(ss->host_rec_hint, need_recs_min)));
-                const size_t want_t = ss->have_history ? need_text : std::min(need_text, std::max(ss->host_text_hint, need_text_min));
+                // pinned set: sized from the previous scan of this state scaled to this call's length (+ 1/16, an overflow
+                // reruns the exact stage with the counted sizes); a first scan starts from a modest guess
+                const double scale = ss->have_history && ss->last_len ? (double)len / (double)ss->last_len : 1.0;
+                const size_t guess_f = ss->have_history ? (size_t)(ss->last_nrec * scale) + ss->last_nrec / 16 + 4096 : ss->host_rec_hint;
+                const size_t guess_t = ss->have_history ? (size_t)(ss->last_ntext * scale) + ss->last_ntext / 16 + 65536 : ss->host_text_hint;
+                const size_t want_f = !ss->use_direct ? 0 : std::min(need_recs, std::max(guess_f, need_recs_min));
+                const size_t want_t = std::min(need_text, std::max(guess_t, need_text_min));
                 if (ss->use_direct) {
                     if (fc->set.fcap < want_f || fc->set.tcap < want_t) {
                         pinned_release(fc->set);
@@ -1310,6 +1333,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     const size_t nrec = (size_t)counters[0];
     const size_t ntext = (size_t)counters[1];
     ss->have_history = true;
+    ss->last_nrec = nrec; ss->last_ntext = ntext; ss->last_len = len;
     ss->rec_per_byte = std::max(1.0 / 4096, 1.3 * (double)nrec / (double)len);
     ss->text_per_byte = std::max(1.0 / 256, 1.3 * (double)ntext / (double)len);
     ss->stats.n_records = nrec;
