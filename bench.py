@@ -326,6 +326,10 @@ def main():
     hbuf.copy_(dbuf[:e2e_size])
     torch.cuda.synchronize()
     harr = hbuf.numpy()
+    # the device-timed state and its buffer go first: at the 32 GiB configs they hold most of the HBM
+    ss_dev.close()
+    del dbuf
+    torch.cuda.empty_cache()
 
     ss_host = sx.ScannerState(mission, local)
 

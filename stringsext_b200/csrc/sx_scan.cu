@@ -997,12 +997,12 @@ static bool grow_pinned(T** p, size_t* cap, size_t need) {
 }
 
 template <class T>
-static bool grow(T** p, size_t* cap, size_t need) {
+static bool grow(T** p, size_t* cap, size_t need, bool slack = true) {
     if (need <= *cap) return true;
     if (*p) cudaFree(*p);
     *p = nullptr;
     *cap = 0;
-    const size_t want = need + need / 4 + 256;
+    const size_t want = need + (slack ? std::min<size_t>(need / 4, (1ull << 30) / sizeof(T)) : 0) + 256;  // slack capped at 1 GiB
     if (!cuda_ok(cudaMalloc(p, want * sizeof(T)), "cudaMalloc")) return false;
     *cap = want;
     return true;
@@ -1249,12 +1249,23 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
             CK(cudaMemcpyAsync(&ne, ss->d_counters + 2, sizeof ne, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             ss->stats.d2h_bytes += sizeof ne;
-            // whenever the per-entry state (240 B per listed window) fits a 24 GiB budget and can be allocated; beyond
-            // that (more than ~12 GiB of text-like input in one call) the block kernel
+            // whenever the per-entry state (240 B per listed window) can be allocated: up to 24 GiB without asking, beyond
+            // that (more than ~12 GiB of text-like input in one call) only while 16 GiB of the device stay free for the
+            // other buffers; else the block kernel
             const size_t nb = (size_t)((ne + sparse_threads() - 1) / sparse_threads());
-            bool fits_mem = ne * (unsigned long long)sparse_entry_bytes() <= (24ull << 30);
+            const unsigned long long state_bytes = ne * (unsigned long long)sparse_entry_bytes();
+            bool fits_mem = state_bytes <= (24ull << 30);
+            if (!fits_mem) {
+                size_t free_b = 0, total_b = 0;
+                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                    const unsigned long long avail = (unsigned long long)free_b + ss->entries_cap;
+                    fits_mem = avail > (16ull << 30) && state_bytes <= avail - (16ull << 30);
+                } else {
+                    cudaGetLastError();
+                }
+            }
             if (ne > 0 && fits_mem) {
-                fits_mem = grow(&ss->d_entries, &ss->entries_cap, (size_t)ne * sparse_entry_bytes()) &&
+                fits_mem = grow(&ss->d_entries, &ss->entries_cap, (size_t)state_bytes, state_bytes <= (24ull << 30)) &&
                            grow(&ss->d_btot, &ss->btot_cap, (nb + 1) * sizeof(ulonglong2)) &&
                            grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes()) &&
                            grow(&ss->d_queue, &ss->queue_cap, (2 * (size_t)ne + 128) * sizeof(uint32_t));
