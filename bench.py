@@ -396,7 +396,9 @@ def main():
                        "size_overridden": bool(args.size_mib)},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "GiB/s", "h2d_bytes_per_step": int(st_e.h2d_bytes),
-                    "d2h_bytes_per_step": int(st_e.d2h_bytes), "bytes_scanned_per_gpu": e2e_size, "findings_rank0": n_e2e},
+                    "d2h_bytes_per_step": int(st_e.d2h_bytes), "bytes_scanned_per_gpu": e2e_size, "findings_rank0": n_e2e,
+                    "ms_per_step_rank0": dt * 1e3, "host_phase_ms_rank0": [float(x) for x in st_e.host_phase_ms],
+                    "exact_stage_ms_rank0": float(st_e.exact_kernel_ms), "sparse_used": int(st_e.sparse_used)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
