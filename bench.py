@@ -410,6 +410,12 @@ def main():
                          "host_call_ms": avg([h[0] for h in host_ms]), "host_post_ms": avg([h[1] for h in host_ms]),
                          "host_phase_ms": [avg([h[2 + k] for h in host_ms]) for k in range(4)]},
         }
+        if dominant == "sx_sp_scan+gather":
+            # output-heavy workloads: the dominant kernel stores the findings (48 B each) and their text into pinned host
+            # memory, so its ceiling is the PCIe link (measured D2H copy on this pool: ~55 GB/s, tools/ubench/d2h.py)
+            line["roofline"]["note"] = "dominant kernel writes the findings to host memory: PCIe-bound, the HBM fraction is not its ceiling"
+            line["roofline"]["pcie"] = {"bytes_per_launch": int(d2h), "achieved_gbs": d2h / 1e9 / (k_ms / 1e3), "peak_gbs": 55.0,
+                                        "frac": d2h / 1e9 / (k_ms / 1e3) / 55.0}
         if not args.no_cpu:
             from helpers import to_oracle
 

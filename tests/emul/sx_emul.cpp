@@ -64,7 +64,10 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
     const int64_t rest = P.len - full * (int64_t)P.slice_len;
     const int64_t total = full * geo.wps + (rest + P.W - 1) / P.W;
     PrefCfg pc = make_pref_cfg(P, true);
-    if (!use_pref || P.general) pc.enabled = 0;  // general missions: every window goes through the exact stage
+    // general missions (grep_char / same block / n > q) keep the prefilter: a finding still needs a run of >= T good
+    // bytes (or completes a cut, which the extension window handles), and the pre-roll of a head recomputes the
+    // leftover with its grep / lead-byte attributes from the look-back bytes
+    if (!use_pref) pc.enabled = 0;
     stats[7] = pc.enabled;
     list.clear();
     if (pc.enabled) {

@@ -298,6 +298,41 @@ def test_prefilter_on_off_identical(enc):
         assert a.last_run_str_was_printed_and_is_maybe_cut_str == b.last_run_str_was_printed_and_is_maybe_cut_str
 
 
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+def test_general_missions_prefilter_on_off_and_oracle(enc):
+    """--grep-char / --same-unicode-block / n > q keep the prefilter (a finding still needs a run of >= T good bytes;
+    a head's pre-roll recomputes the leftover with its grep / lead-byte attributes): same findings with and without
+    it, and the oracle's, on sparse lists (random bytes + planted strings) and dense ones."""
+    import dataclasses
+
+    rng = random.Random(4242 + enc)
+    for it in range(8):
+        m = corpus.random_general_mission(rng, enc, M)
+        q = rng.choice([8, 16, 32, 64, 64])
+        n = min(m.chars_min_nb, q) if rng.random() < 0.8 else q + rng.choice([1, 3, 10])
+        m = dataclasses.replace(m, output_line_char_nb_max=q, chars_min_nb=n)
+        if it < 3:
+            arr = corpus.sx_mix_bytes(900 + it, 0, (1 << 20) + 4096 * it)
+            corpus.plant(arr, it, enc, max(1, min(n, q)), q, density=1 << 11)
+            buf = arr.tobytes()
+        else:
+            buf = corpus.gen(rng, rng.choice(corpus.KINDS), rng.randrange(1, 300000), enc)
+        a, b, os_ = sx.ScannerState(m), sx.ScannerState(m), oracle_state(m)
+        b.set_prefilter(False)
+        cut = rng.randrange(1, len(buf)) if len(buf) > 1 and rng.random() < 0.5 else len(buf)
+        for part in (buf[:cut], buf[cut:]):
+            if not part:
+                continue
+            ra = gpu_findings(a.scan_stream(part, False, 4096))
+            rb = gpu_findings(b.scan_stream(part, False, 4096))
+            assert b.last_stats.prefilter_used == 0
+            exp = oracle_findings(os_.scan_stream(part, False, 4096))
+            assert ra == exp, (enc, m, len(part))
+            assert rb == exp, (enc, m, len(part))
+            check_state(a, os_)
+            check_state(b, os_)
+
+
 @pytest.mark.parametrize("n,q,ubf,kind", [(10, 64, None, "rand"), (6, 64, None, "rand"), (4, 64, M.UBF_ALL_VALID, "rand"),
                                          (10, 64, M.UBF_ALL_VALID, "mixed"), (3, 16, None, "rand"), (8, 8, M.UBF_AFRICAN, "text"),
                                          (2, 64, None, "rand"), (16, 32, M.UBF_ALL, "runs")])
