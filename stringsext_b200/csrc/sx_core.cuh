@@ -127,7 +127,7 @@ SX_HD uint32_t put_utf8(uint8_t* d, uint32_t c) {
 // ------------------------------------------------------------------------------------------
 // Window summary (stage A) -> transfer-function descriptor used by the tile-level resolve.
 // ------------------------------------------------------------------------------------------
-enum : uint8_t { WT_CONST = 0, WT_CASEB = 1, WT_DEP = 2 };
+enum : uint8_t { WT_CONST = 0, WT_CASEB = 1, WT_DEP = 2, WT_GUARD = 3 };
 struct WinDesc {
     uint8_t type;        // WT_*
     uint8_t pad;
@@ -201,13 +201,15 @@ struct WinAuto {
     bool in_first_run;      // still inside the first run of segment 1
     bool s1_all_pass, s1_later_yield, s2_all_pass;
     bool cut1;              // carry flag handed from segment 1 to segment 2 (classification)
+    bool first_ended;       // the first run of segment 1 ended inside the segment ...
+    bool first_clean;       // ... in a way that leaves no stale lead byte behind (general missions, WT_GUARD)
 
     SX_HD void init(const ScanParams* p, int md, int64_t slice_st, bool probe_ok) {
         P = p; mode = md; wr = nullptr; text_off = 0; slice_start = slice_st; probe_possible = probe_ok;
         force_s2_cont = -1; cut1 = false;
         cut = false; has_left = false; left_hostcarry = false; left_grep = false; left_k = left_out = left_mb = 0; left_in_start = 0;
         nrec = ntext = 0; m = 0; a = 0; s1_out = 0; in_first_run = false;
-        s1_all_pass = true; s1_later_yield = false; s2_all_pass = true;
+        s1_all_pass = true; s1_later_yield = false; s2_all_pass = true; first_ended = false; first_clean = false;
         slice_left_present = false; slice_left = carry_none();
         run_n = run_out = 0; run_in_start = run_in_end = 0; run_hostcarry = false;
         grep_ok = true; qfull = false; dead = false; last_mb = 0; run_mb = 0;
@@ -320,6 +322,7 @@ struct WinAuto {
                     yield(at_left && last_cut, false);
                     last_cut = false;
                 }
+                if (m == 1 && in_first_run) { first_ended = true; first_clean = true; }
                 if (m == 1) in_first_run = false;
                 at_left = false;
                 new_run();
@@ -350,6 +353,7 @@ struct WinAuto {
                     broke = true;
                 }
             }
+            if (m == 1 && in_first_run) { first_ended = true; first_clean = !P->same_block || lb >= 0x80; }
             if (m == 1) in_first_run = false;
             at_left = false;
             // helper.rs:327-330: without a `break` the same next() call goes on and keeps its (possibly stale)
@@ -825,7 +829,18 @@ SX_HD_NOINLINE void scan_window(const ScanParams& P, const TileSrc& tsrc, const 
         desc->pad = 0;
         const bool single_all_pass = (A.m == 1 && A.s1_all_pass);
         if (geo.final_last) desc->type = WT_CONST;
-        else if (P.general) desc->type = WT_DEP;  // refined by classify_general() with a second pass
+        else if (P.general) {
+            // >= 2 segments: refined by classify_general() with a second pass.  One segment whose first run ends inside
+            // the window under the null carry with a < q chars: past that point the automaton holds nothing of the
+            // carry-in (run state reset, cut == false, no leftover; `first_clean`: no stale lead byte either) unless
+            // the carried leftover drives the first run to q chars (k + a >= q: forced cut, possibly a dead segment,
+            // helper.rs:389-415).  k <= q - 1 without a grep_char, <= q with one.
+            desc->type = WT_DEP;
+            if (A.m == 1 && A.first_ended && A.first_clean && A.a < P.q) {
+                const uint32_t kmax = P.grep_char >= 0 ? P.q : P.q - 1;
+                desc->type = (A.a + kmax < P.q) ? WT_CONST : WT_GUARD;
+            }
+        }
         else if (single_all_pass) {
             if (A.a < P.q) { desc->type = WT_CASEB; desc->t_out = (uint16_t)A.s1_out; }
             else desc->type = WT_CONST;
@@ -915,6 +930,19 @@ SX_HD uint8_t classify_general(const WinGeom& geo, const WinResult& r1, RunFn&& 
     const bool same = o1.kind == o2.kind && o1.flags == o2.flags && o1.k == o2.k && o1.in_bytes == o2.in_bytes &&
                       o1.out_bytes == o2.out_bytes && o1.aux == o2.aux;
     return same ? WT_CONST : WT_DEP;
+}
+
+// WT_GUARD: the carry-out is the one seen under the null carry unless the carried leftover fills the first run up.
+SX_HD bool guard_benign(const ScanParams& P, const WinDesc& d, const Carry& kin) {
+    return kin.kind != K_L || (uint32_t)kin.k + d.a < P.q;
+}
+
+// A WT_GUARD window behind an adjacent WT_GUARD / WT_CONST window `dp` of the same general mission, carry-in unknown:
+// whatever reached `dp`, its carry-out is its null_out, "none" (the leftover killed its segment, helper.rs:410-415) or
+// "cut" (the forced cut was the last event, helper.rs:353) -- so if dp.null_out is benign for `d`, every possible
+// carry-in is, and d's carry-out is d.null_out.  This is what lets a block find a known carry a few windows back.
+SX_HD bool guard_known_behind(const ScanParams& P, const WinDesc& d, const WinDesc& dp) {
+    return d.type == WT_GUARD && (dp.type == WT_GUARD || dp.type == WT_CONST) && guard_benign(P, d, dp.null_out);
 }
 
 SX_HD bool carry_needs_extension(const ScanParams& P, const Carry& k) {

@@ -388,6 +388,30 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
 
     // ---- stage B: resolve the carries along runs of adjacent windows (compacted replays) ---------------
     for (;;) {
+        if (P.general) {
+            // General missions: most windows are WT_GUARD (carry-out = the one seen under the null carry unless the
+            // carried leftover fills the first run up); chains of them resolve without a pass, so one lane walks the
+            // block in order.  With an unknown carry-in (warm-up of a block that starts inside a run) a guard window
+            // behind a guard / constant one is still decided (guard_known_behind), which is what ends the warm-up.
+            if (threadIdx.x == 0) {
+                for (uint32_t j = 0; j < nblk; ++j) {
+                    if (S.out_done[j] || !S.in_known[j]) continue;
+                    const WinDesc dj = S.desc[j];
+                    if (dj.type != WT_GUARD) continue;
+                    const Carry kj = S.kin[j];
+                    Carry out;
+                    if (kj.kind == K_UNKNOWN) {
+                        if (j > 0 && S.adj[j] && guard_known_behind(P, dj, S.desc[j - 1])) out = dj.null_out;
+                        else out = kj;
+                    } else if (guard_benign(P, dj, kj)) out = dj.null_out;
+                    else continue;  // a leftover that fills the first run up: replay below
+                    S.kout[j] = out;
+                    S.out_done[j] = 1;
+                    if (S.next_adj[j] && j + 1 < nblk) { S.kin[j + 1] = out; S.in_known[j + 1] = 1; }
+                }
+            }
+            __syncthreads();
+        }
         const bool rdy = active && !S.out_done[i] && S.in_known[i];
         const uint32_t nq = block_enqueue(S, rdy, i, false, 0);
         if (nq == 0) break;

@@ -1176,9 +1176,10 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     if (total_windows > 0x7FFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
     PrefCfg pc = make_pref_cfg(P, in_aligned16);
-    // General missions keep the prefilter: a finding still needs a run of >= T good bytes (or completes a cut: extension
-    // window), and a head's pre-roll recomputes the leftover with its grep / lead-byte attributes from the look-back.
-    if (!ss->use_prefilter) pc.enabled = 0;
+    // General missions run without the prefilter: an unlisted window's carry-out must not depend on its carry-in, and
+    // there it does -- a leftover of q chars without the grep char kills the next window's segment (helper.rs:410-415:
+    // its trailing run is then no leftover), a stale lead byte survives ASCII junk (helper.rs:327-330).  DESIGN.md 7.
+    if (!ss->use_prefilter || P.general) pc.enabled = 0;
     const long long ntiles = (total_windows + kPrefTileWin - 1) / kPrefTileWin;
     const long long max_blocks = (total_windows + kThreads - 1) / kThreads;
 

@@ -22,6 +22,8 @@ static int g_use_mask = 1;
 static uint64_t g_mask_ok = 0, g_mask_declined = 0;
 static uint64_t g_mask_mismatch = 0;
 static uint64_t g_head_ok = 0;
+static uint64_t g_guard_behind = 0, g_guard_behind_hard = 0;
+static uint64_t g_guard_ok = 0, g_guard_killer = 0;  // WT_GUARD windows: carry-in benign / a leftover that fills the first run
 static uint64_t g_indep = 0, g_dep = 0;
 struct HostTile {
     GlobalSrc g;
@@ -64,10 +66,9 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
     const int64_t rest = P.len - full * (int64_t)P.slice_len;
     const int64_t total = full * geo.wps + (rest + P.W - 1) / P.W;
     PrefCfg pc = make_pref_cfg(P, true);
-    // general missions (grep_char / same block / n > q) keep the prefilter: a finding still needs a run of >= T good
-    // bytes (or completes a cut, which the extension window handles), and the pre-roll of a head recomputes the
-    // leftover with its grep / lead-byte attributes from the look-back bytes
-    if (!use_pref) pc.enabled = 0;
+    // general missions: every window goes through the exact stage (an unlisted window's carry-out would depend on its
+    // carry-in: killed segments, stale lead bytes -- sx_scan.cu)
+    if (!use_pref || P.general) pc.enabled = 0;
     stats[7] = pc.enabled;
     list.clear();
     if (pc.enabled) {
@@ -97,6 +98,8 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         }
         text.resize(tb + rc.ntext);
     };
+    WinDesc prev_d;
+    bool prev_valid = false, prev_off_null = false;
     for (size_t e = 0; e < ne; ++e) {
         const int64_t w = list[e];
         WinGeom wg;
@@ -125,9 +128,19 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         Carry kout;
         if (d.type == WT_CONST) kout = d.null_out;
         else if (d.type == WT_CASEB) { kout = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws)); stats[2]++; }
-        else { kout = rs.out; stats[1]++; }
+        else if (d.type == WT_GUARD && guard_benign(P, d, kin)) { kout = d.null_out; g_guard_ok++; }
+        else { kout = rs.out; stats[1]++; if (d.type == WT_GUARD) g_guard_killer++; }
         stats[0]++;
         if (memcmp(&rs.out, &kout, sizeof(Carry)) != 0) { stats[3]++; kout = rs.out; }
+        // the block kernel's warm-up rule (carry-in unknown): checked against the replay under the real carry
+        if (P.general && adjacent && prev_valid && guard_known_behind(P, d, prev_d)) {
+            g_guard_behind++;
+            if (prev_off_null) g_guard_behind_hard++;  // the predecessor's carry-out was not its null_out (killed / cut)
+            if (memcmp(&rs.out, &d.null_out, sizeof(Carry)) != 0) stats[3]++;
+        }
+        prev_d = d;
+        prev_valid = true;
+        prev_off_null = memcmp(&kout, &d.null_out, sizeof(Carry)) != 0;
         WinResult rc;
         emit_window(wg, kin, rc);
         if (!adjacent && w != 0 && MaskFamily<Dec>::kHas && !P.general && g_use_mask && g_use_fast) {
@@ -230,6 +243,10 @@ void sx_emul_mask_counts(uint64_t* ok, uint64_t* declined) { *ok = g_mask_ok; *d
 uint64_t sx_emul_mask_mismatches() { return g_mask_mismatch; }
 uint64_t sx_emul_head_ok() { return g_head_ok; }
 void sx_emul_indep_counts(uint64_t* indep, uint64_t* dep) { *indep = g_indep; *dep = g_dep; }
+void sx_emul_guard_counts(uint64_t* ok, uint64_t* killer) { *ok = g_guard_ok; *killer = g_guard_killer; }
+uint64_t sx_emul_guard_behind() { return g_guard_behind; }
+uint64_t sx_emul_guard_behind_hard() { return g_guard_behind_hard; }
+
 int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
     for (uint32_t i = 0; i < 2048; ++i) mask_tables_fill(*P, g_tables, i);
     std::vector<uint32_t> list;

@@ -299,10 +299,11 @@ def test_prefilter_on_off_identical(enc):
 
 
 @pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
-def test_general_missions_prefilter_on_off_and_oracle(enc):
-    """--grep-char / --same-unicode-block / n > q keep the prefilter (a finding still needs a run of >= T good bytes;
-    a head's pre-roll recomputes the leftover with its grep / lead-byte attributes): same findings with and without
-    it, and the oracle's, on sparse lists (random bytes + planted strings) and dense ones."""
+def test_general_missions_large_buffers_vs_oracle(enc):
+    """--grep-char / --same-unicode-block / n > q on buffers of many 128-entry blocks (the block kernel's warm-up finds
+    a known carry through the WT_GUARD rules, sx_core.cuh guard_benign / guard_known_behind): the oracle's findings,
+    on sparse input (random bytes + planted strings) and dense input.  These missions never use the prefilter (an
+    unlisted window's carry-out would depend on its carry-in)."""
     import dataclasses
 
     rng = random.Random(4242 + enc)
@@ -325,7 +326,7 @@ def test_general_missions_prefilter_on_off_and_oracle(enc):
                 continue
             ra = gpu_findings(a.scan_stream(part, False, 4096))
             rb = gpu_findings(b.scan_stream(part, False, 4096))
-            assert b.last_stats.prefilter_used == 0
+            assert a.last_stats.prefilter_used == 0 and b.last_stats.prefilter_used == 0
             exp = oracle_findings(os_.scan_stream(part, False, 4096))
             assert ra == exp, (enc, m, len(part))
             assert rb == exp, (enc, m, len(part))

@@ -14,12 +14,12 @@ size = (int(sys.argv[1]) if len(sys.argv) > 1 else 1024) << 20
 g = torch.Generator(device="cuda").manual_seed(1)
 buf = torch.randint(0, 256, (size,), dtype=torch.uint8, device="cuda", generator=g)
 stream = torch.cuda.current_stream()
-# (label, grep, same block, prefilter, bytes scanned): without the prefilter every window goes through the block kernel,
-# and single-segment windows of general missions are all carry-dependent, so those cases are small
+# (label, grep, same block, prefilter, bytes scanned).  General missions never use the prefilter, so the
+# flag only matters for the plain mission at the end (reference point).
 small = min(size, 32 << 20)
-CASES = (("utf-8", ord("e"), False, True, size), ("utf-8", ord("e"), False, False, size), ("utf-8", None, True, True, size),
-         ("ascii", ord("e"), False, True, size), ("utf-16le", ord("e"), True, True, size), ("ascii", ord("e"), False, False, small),
-         ("koi8-r", ord("e"), False, True, small))
+CASES = (("ascii", ord("e"), False, True, small), ("koi8-r", ord("e"), False, True, small), ("utf-8", ord("e"), False, True, size),
+         ("utf-8", None, True, True, size), ("ascii", ord("e"), False, True, size), ("koi8-r", None, True, True, size),
+         ("utf-16le", ord("e"), True, True, size), ("utf-8", None, False, True, size))
 for label, grep, same, pref, nbytes in CASES:
     m = sx.Mission.for_label(label, 10)
     m = dataclasses.replace(m, filter=dataclasses.replace(m.filter, grep_char=grep), require_same_unicode_block=same)
@@ -28,7 +28,7 @@ for label, grep, same, pref, nbytes in CASES:
         ss = sx.ScannerState(m, 0)
         ss.set_prefilter(pref)
         ms, n = [], 0
-        for it in range(4 if pref else 2):
+        for it in range(3):
             ss.reset()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -38,5 +38,5 @@ for label, grep, same, pref, nbytes in CASES:
             ms.append(e0.elapsed_time(e1))
             n = len(fc)
             del fc
-        print(f"{label} -n 10 grep={grep} same_block={same} prefilter={pref}: {min(ms):.2f} ms = {size / 2**30 / (min(ms) / 1e3):.1f} GiB/s, "
+        print(f"{nbytes >> 20} MiB {label} -n 10 grep={grep} same_block={same} prefilter={pref}: {min(ms):.2f} ms = {size / 2**30 / (min(ms) / 1e3):.1f} GiB/s, "
               f"{n} findings, listed {ss.last_stats.windows_listed} of {ss.last_stats.windows_total}")
