@@ -79,6 +79,41 @@ def test_fuzz_general_missions(enc):
         assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
 
 
+def test_general_missions_guard_rules():
+    """WT_GUARD (sx_core.cuh): a general-mission window whose first run ends inside it keeps the carry-out seen under
+    the null carry unless the carried leftover fills that run up to q chars (guard_benign), and behind an adjacent
+    guard / constant window that holds for every possible carry-in (guard_known_behind, what ends the block kernel's
+    warm-up).  The harness checks both claims against the replay under the real carry on every window (stats[3]);
+    small q and n make the "killer" leftovers frequent.  General missions never use the prefilter: the fuzz found an
+    unlisted window killed by its predecessor's leftover."""
+    import ctypes as C
+    import dataclasses
+
+    L = emul.lib()
+    L.sx_emul_guard_behind.restype = C.c_uint64
+    L.sx_emul_guard_behind_hard.restype = C.c_uint64
+    ok0, k0 = C.c_uint64(), C.c_uint64()
+    L.sx_emul_guard_counts(C.byref(ok0), C.byref(k0))
+    b0, h0 = L.sx_emul_guard_behind(), L.sx_emul_guard_behind_hard()
+    for enc in (0, 1, 4, 2):
+        rng = random.Random(31000 + enc)
+        for _ in range(40):
+            m = corpus.random_general_mission(rng, enc, M)
+            q = rng.choice([8, 8, 16, 32, 64])
+            m = dataclasses.replace(m, output_line_char_nb_max=q, chars_min_nb=rng.choice([1, 2, 3, 4, 6, 8, 10, 12, 20]))
+            es, os_ = emul.EmulState(m), oracle_state(m)
+            for c in range(rng.choice([1, 2])):
+                buf = corpus.gen(rng, rng.choice(corpus.KINDS), rng.randrange(1, 30000), enc)
+                f, _ = es.scan_stream(buf, False, 4096)
+                _cmp(es, os_, f, os_.scan_stream(buf, False, 4096).v)
+                assert es.stats[7] == 0  # no prefilter
+            assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
+    ok1, k1 = C.c_uint64(), C.c_uint64()
+    L.sx_emul_guard_counts(C.byref(ok1), C.byref(k1))
+    assert ok1.value - ok0.value > 5000 and k1.value - k0.value > 100
+    assert L.sx_emul_guard_behind() - b0 > 5000 and L.sx_emul_guard_behind_hard() - h0 > 20
+
+
 def test_planted_corpus_utf16():
     """Random bytes + planted UTF-16 strings (random alone yields nothing)."""
     for enc, label in ((2, "utf-16le"), (3, "utf-16be")):
