@@ -20,11 +20,12 @@ t0 = time.time()
 nf = 0
 for it in range(iters):
     enc = rng.choice([0, 1, 1, 1, 2, 3, 4, 4, 5, 6])
-    general = rng.random() < 0.15
+    general = rng.random() < float(os.environ.get("SX_STRESS_GENERAL", "0.15"))  # --grep-char / --same-unicode-block share
     m = corpus.random_general_mission(rng, enc, M) if general else corpus.random_mission(rng, enc, M)
     if rng.random() < 0.7:
         q = rng.choice([64, 64, 64, 32, 16, 8])
-        m = dataclasses.replace(m, output_line_char_nb_max=q, chars_min_nb=min(m.chars_min_nb, q))
+        n = min(m.chars_min_nb, q) if not general or rng.random() < 0.8 else q + rng.choice([1, 4, 20])  # n > q: general too
+        m = dataclasses.replace(m, output_line_char_nb_max=q, chars_min_nb=n)
     size = rng.choice([0, 1, 777, 4096, 70000, 300000, 1 << 20, (2 << 20) + 13])
     kind = rng.choice(["rand", "rand", "mixed", "lowent", "runs", "text", "planted"])
     if kind == "planted":
