@@ -155,3 +155,26 @@ def random_general_mission(rng: random.Random, enc: int, M):
     grep = rng.choice([0x20, ord("a"), ord("e"), ord(":"), ord("?"), 0x00]) if kind in ("grep", "both") else None
     filt = dataclasses.replace(m.filter, grep_char=grep)
     return dataclasses.replace(m, filter=filt, require_same_unicode_block=kind in ("same", "both"))
+
+
+# A window killed by its predecessor's leftover (helper.rs:389-415), found by the general-mission fuzz: ISO-8859-5,
+# -n 3, q = 8 (16-byte windows), --grep-char ':', every ASCII char but NUL passes, no multi-byte block does.
+# Window 1 ends in the 8 = q chars `s2W\x02i}|k` without the grep char: kept as a leftover ("again").  Window 2 starts
+# with a failing byte: the leftover is evaluated there, holds q chars and no grep char, and the whole segment is dropped
+# -- including its trailing `3:`, which is therefore NOT a leftover, so `3:O` across the boundary to window 3 does not
+# print.  With a ':' in window 1's run both strings print.  (This is why such missions cannot use the prefilter as it is:
+# window 2 has no run of >= n good bytes, yet its carry-out depends on its carry-in.)
+KILLED_WINDOW_CASE = (
+    b"!n\xb0\xbe&\x8c\\\x8aR\x07QB\xc0\x12\xcb\xd7"
+    b"\xf3\xb8\xba\x94=\xa1\xd3\xfas2W\x02i}|k"
+    b"\xd1\xc9\xe4}/\xe2\xd0\xb6\xed\xe0\xe5\x8c\xb8\xa63:"
+    b"O\xd6T\xfd\x02\xb4\xaa{\x8e\x87\xfe\n\xd3O\x02\xb1"
+)
+
+
+def killed_window_inputs():
+    """(mission arguments for Mission.for_label, [(input, expected (position, text) list)])"""
+    pad = lambda c: c + b"\x00" * (4096 + 64 - len(c))
+    return (("iso-8859-5", 3, (1 << 128) - 2, 0, ord(":"), 8),
+            [(pad(KILLED_WINDOW_CASE), []),
+             (pad(KILLED_WINDOW_CASE.replace(b"s2W", b"s2:")), [(16, b"s2:\x02i}|k"), (48, b"3:O")])])

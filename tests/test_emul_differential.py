@@ -114,6 +114,20 @@ def test_general_missions_guard_rules():
     assert L.sx_emul_guard_behind() - b0 > 5000 and L.sx_emul_guard_behind_hard() - h0 > 20
 
 
+def test_killed_window_case():
+    """corpus.KILLED_WINDOW_CASE: the oracle drops the segment behind a q-char leftover without the grep char
+    (helper.rs:389-415), the harness follows."""
+    args, cases = corpus.killed_window_inputs()
+    m = M.Mission.for_label(*args)
+    for data, expected in cases:
+        es, os_ = emul.EmulState(m), oracle_state(m)
+        o = os_.scan_stream(data, False, 4096).v
+        assert [(x.position, x.s) for x in o] == expected
+        f, _ = es.scan_stream(data, False, 4096)
+        _cmp(es, os_, f, o)
+        assert es.stats[7] == 0  # general mission: no prefilter
+
+
 def test_planted_corpus_utf16():
     """Random bytes + planted UTF-16 strings (random alone yields nothing)."""
     for enc, label in ((2, "utf-16le"), (3, "utf-16be")):

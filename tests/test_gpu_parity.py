@@ -111,6 +111,21 @@ def test_differential_fuzz_general_missions(enc):
             check_state(gs, os_)
 
 
+def test_killed_window_case():
+    """corpus.KILLED_WINDOW_CASE (a window dropped because of its predecessor's leftover) on the GPU, also embedded in
+    a larger stream so that the windows sit in the middle of a block."""
+    args, cases = corpus.killed_window_inputs()
+    m = M.Mission.for_label(*args)
+    for data, expected in cases:
+        got = sx.ScannerState(m).scan_stream(data, False, 4096)
+        assert [(f.position, f.s) for f in got.v] == expected
+        big = b"\x00" * 8192 + data + b"\x00" * 8192
+        gs, os_ = sx.ScannerState(m), oracle_state(m)
+        assert gpu_findings(gs.scan_stream(big, False, 4096)) == oracle_findings(os_.scan_stream(big, False, 4096))
+        assert [(f[0], f[2]) for f in gpu_findings(sx.ScannerState(m).scan_stream(big, False, 4096))] == [(p + 8192, t) for p, t in expected]
+        check_state(gs, os_)
+
+
 def test_field_with_zeros():
     factory, inp = RV.FIELD_WITH_ZEROS
     assert len(sx.ScannerState(factory()).scan(inp, False, 0).v) != 1

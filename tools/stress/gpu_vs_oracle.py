@@ -19,6 +19,8 @@ rng = random.Random(seed)
 t0 = time.time()
 nf = 0
 for it in range(iters):
+    if it and it % 200 == 0:
+        print("...", it, "iterations ok", flush=True)
     enc = rng.choice([0, 1, 1, 1, 2, 3, 4, 4, 5, 6])
     general = rng.random() < float(os.environ.get("SX_STRESS_GENERAL", "0.15"))  # --grep-char / --same-unicode-block share
     m = corpus.random_general_mission(rng, enc, M) if general else corpus.random_mission(rng, enc, M)
