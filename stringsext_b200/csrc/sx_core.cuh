@@ -1026,6 +1026,7 @@ struct PrefCfg {
     uint32_t n_chars; // chars_min_nb
     uint32_t refine;  // PF_UTF8: a long good-byte run only counts if it holds >= n_chars non-continuation bytes
     uint32_t pre_bytes;  // pre-roll length: longest possible trailing good run of an uninteresting window + slack
+    uint32_t kill_trail; // --grep-char missions: a window behind >= this many trailing good bytes is listed (0: rule off)
 };
 
 // Reference (byte-wise) definition of G; the SWAR kernel must produce exactly these flags.
@@ -1055,10 +1056,14 @@ SX_HD bool pref_good(const ScanParams& P, const PrefCfg& c, const S& src, int64_
     return ((c.blkH >> (src.get(t) >> 5)) & 1u) != 0;
 }
 
-struct PrefWin { uint32_t lead, trail, maxrun, maxchars; };  // maxchars: most non-continuation bytes in a run of >= T bytes
+struct PrefWin { uint32_t lead, trail, maxrun, maxchars, kill; };  // kill: see PrefCfg::kill_trail  // maxchars: most non-continuation bytes in a run of >= T bytes
+// General missions that may use the prefilter (see make_pref_cfg: kill_trail); the others need every window scanned:
+// a stale lead byte survives ASCII junk under --same-unicode-block (helper.rs:327-330), n > q drops whole segments.
+SX_HD bool pref_general_ok(const ScanParams& P) { return P.grep_char >= 0 && !P.same_block && P.n <= P.q; }
+
 template <class S>
 SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& src, int64_t ws, int64_t we) {
-    PrefWin r{0, 0, 0, 0};
+    PrefWin r{0, 0, 0, 0, 0};
     uint32_t run = 0, chars = 0;
     bool seen_bad = false;
     auto close_run = [&]() { if (run >= c.T && chars > r.maxchars) r.maxchars = chars; };
@@ -1068,6 +1073,9 @@ SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& sr
             const uint32_t b = src.get(i);
             if (!(b >= 0x80 && b < 0xC0)) chars++;
             if (run > r.maxrun) r.maxrun = run;
+            // a good run of >= kill_trail bytes, or one that began at (before) the window's first byte, reaching one of
+            // the last 4 bytes: the decoded text may end in >= q passing chars (up to 3 bytes stay pending in the decoder)
+            if (c.kill_trail != 0 && i + 4 >= we && (run >= c.kill_trail || !seen_bad)) r.kill = 1;
         } else {
             close_run();
             if (!seen_bad) { r.lead = run; seen_bad = true; }
@@ -1086,7 +1094,7 @@ SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& sr
 inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned) {
     PrefCfg c;
     c.enabled = 0; c.family = PF_BYTE; c.blkA = 0; c.blkH = 0; c.multi = 0; c.T = P.n; c.unit = 1; c.hi_pos = 0;
-    c.n_chars = P.n; c.refine = 0; c.pre_bytes = 0;
+    c.n_chars = P.n; c.refine = 0; c.pre_bytes = 0; c.kill_trail = 0;
     for (uint32_t k = 0; k < 4; ++k) {
         const uint64_t word = k < 2 ? P.af_lo : P.af_hi;
         if ((word >> ((k & 1) * 32)) & 0xFFFFFFFFull) c.blkA |= 1u << k;
@@ -1139,6 +1147,13 @@ inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned) {
         c.pre_bytes = (c.refine ? P.n * maxlen : c.T) + 3 + c.unit;
     }
     c.enabled = (P.W % 16 == 0 && P.W <= 128 && P.slice_len % P.W == 0 && input_16b_aligned) ? 1u : 0u;
+    // --grep-char (without --same-unicode-block, chars_min_nb <= q): a leftover of q chars is possible (helper.rs:389-392)
+    // and is evaluated at the next window's first char -- dropped together with the rest of that segment if it lacks the
+    // grep char (helper.rs:410-415), printed as a "maybe cut" string otherwise -- so the window behind >= q good chars
+    // (>= q * unit bytes) has to be scanned exactly even if it holds no run itself.  With that window listed, no unlisted
+    // window ever sees its first run filled up to q chars (trail + lead >= q * unit >= T lists it), and past its first
+    // run an unlisted window holds nothing of its carry-in.  Other general missions: no prefilter (pref_general_ok).
+    if (P.grep_char >= 0 && !P.same_block && P.n <= P.q) c.kill_trail = P.q * c.unit;
     return c;
 }
 
@@ -1155,10 +1170,11 @@ SX_HD bool pref_interesting_ref(const ScanParams& P, const PrefCfg& c, const Geo
     if (w == 0 || w == total_windows - 1 || (uint32_t)(g.we - g.ws) < P.W || g.final_last) return true;
     const PrefWin a = pref_window_ref(P, c, src, g.ws, g.we);
     if (c.refine ? (a.maxrun >= c.T && a.maxchars >= c.n_chars) : (a.maxrun >= c.T)) return true;
-    if ((w % kPrefTileWin) == 0) return a.lead >= 1;
+    if ((w % kPrefTileWin) == 0) return a.lead >= 1 || c.kill_trail != 0;  // previous window unknown to the tile
     WinGeom gp;
     geo.window(w - 1, gp);
     const PrefWin b = pref_window_ref(P, c, src, gp.ws, gp.we);
+    if (b.kill) return true;
     // A run of >= T good bytes touches the window's left boundary.  This includes a run that only starts at the
     // window's first byte (b.trail == 0): whatever its char count, it is the run a "cut" carry would complete,
     // and listing it keeps the carry-out of every UNLISTED window independent of its carry-in.

@@ -518,6 +518,22 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             else { lead = ctz128(nm); trail = wlen - 128u + clz128(nm); }
             uint32_t rs[4];
             longrun = has_run128(m, C.T, rs);
+            if (C.kill_trail != 0) {
+                // PrefWin::kill: a good run of >= kill_trail bytes, or one that covers the window from its first byte,
+                // reaches one of the last 4 bytes
+                for (uint32_t j = 0; j < 4 && j < wlen; ++j) {
+                    const uint32_t p = wlen - 1u - j;                       // run must cover byte p
+                    if ((m[p >> 5] >> (p & 31u)) & 1u) {
+                        int hb = -1;                                        // highest bad byte below p
+                        for (int q4 = (int)(p >> 5); q4 >= 0 && hb < 0; --q4) {
+                            uint32_t bad = nm[q4];
+                            if (q4 == (int)(p >> 5)) bad &= (p & 31u) == 31u ? 0xFFFFFFFFu : ((1u << ((p & 31u) + 1u)) - 1u);
+                            if (bad) hb = q4 * 32 + 31 - __clz(bad);
+                        }
+                        if (hb < 0 || p - (uint32_t)hb >= C.kill_trail) trail |= 0x80000000u;
+                    }
+                }
+            }
 
         }
         s_trail[tid] = trail;
@@ -526,8 +542,11 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         if (valid) {
             const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
             if (forced) sure = true;
-            else if (tid == 0) sure = lead >= 1;
-            else sure = lead >= 1 && s_trail[tid - 1] + lead >= C.T;
+            else if (tid == 0) sure = lead >= 1 || C.kill_trail != 0;
+            else {
+                const uint32_t pt = s_trail[tid - 1];  // bit 31: the previous window's kill flag
+                sure = (lead >= 1 && (pt & 0x7FFFFFFFu) + lead >= C.T) || (pt >> 31) != 0;
+            }
             if (!sure && longrun) { if (do_refine) cand = true; else sure = true; }
         }
         }
@@ -1085,7 +1104,7 @@ static cudaError_t launch_prefilter_t(const ScanParams& P, const PrefCfg& c, con
 static cudaError_t launch_prefilter(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
                                     long long ntiles, int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
     const bool defshape = c.family == PF_UTF8 && c.blkA == 0xEu && c.blkH == (1u << 6) && !c.multi;
-    const bool fast = P.W == 128 && c.T <= 32;
+    const bool fast = P.W == 128 && c.T <= 32 && c.kill_trail == 0;  // the bit-plane path keeps only T - 1 flags of the previous window
 #define SX_PREF(F, D) (fast ? launch_prefilter_t<F, D, true>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma) \
                             : launch_prefilter_t<F, D, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma))
     switch (c.family) {
@@ -1176,10 +1195,10 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     if (total_windows > 0x7FFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
     PrefCfg pc = make_pref_cfg(P, in_aligned16);
-    // General missions run without the prefilter: an unlisted window's carry-out must not depend on its carry-in, and
-    // there it does -- a leftover of q chars without the grep char kills the next window's segment (helper.rs:410-415:
-    // its trailing run is then no leftover), a stale lead byte survives ASCII junk (helper.rs:327-330).  DESIGN.md 7.
-    if (!ss->use_prefilter || P.general) pc.enabled = 0;
+    // General missions: an unlisted window's carry-out must not depend on its carry-in.  --grep-char alone gets there with
+    // one more listing rule (PrefCfg::kill_trail, sx_core.cuh); under --same-unicode-block a stale lead byte survives
+    // ASCII junk (helper.rs:327-330) and n > q drops whole segments: those run without the prefilter.  DESIGN.md 7.
+    if (!ss->use_prefilter || (P.general && !pref_general_ok(P))) pc.enabled = 0;
     const long long ntiles = (total_windows + kPrefTileWin - 1) / kPrefTileWin;
     const long long max_blocks = (total_windows + kThreads - 1) / kThreads;
 

@@ -67,8 +67,8 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
     const int64_t total = full * geo.wps + (rest + P.W - 1) / P.W;
     PrefCfg pc = make_pref_cfg(P, true);
     // general missions: every window goes through the exact stage (an unlisted window's carry-out would depend on its
-    // carry-in: killed segments, stale lead bytes -- sx_scan.cu)
-    if (!use_pref || P.general) pc.enabled = 0;
+    // carry-in: killed segments, stale lead bytes -- sx_scan.cu), except --grep-char alone (PrefCfg::kill_trail)
+    if (!use_pref || (P.general && !pref_general_ok(P))) pc.enabled = 0;
     stats[7] = pc.enabled;
     list.clear();
     if (pc.enabled) {

@@ -84,8 +84,8 @@ def test_general_missions_guard_rules():
     the null carry unless the carried leftover fills that run up to q chars (guard_benign), and behind an adjacent
     guard / constant window that holds for every possible carry-in (guard_known_behind, what ends the block kernel's
     warm-up).  The harness checks both claims against the replay under the real carry on every window (stats[3]);
-    small q and n make the "killer" leftovers frequent.  General missions never use the prefilter: the fuzz found an
-    unlisted window killed by its predecessor's leftover."""
+    small q and n make the "killer" leftovers frequent.  Of the general missions only --grep-char alone uses the
+    prefilter, with the extra listing rule the fuzz's counterexample asked for."""
     import ctypes as C
     import dataclasses
 
@@ -106,7 +106,8 @@ def test_general_missions_guard_rules():
                 buf = corpus.gen(rng, rng.choice(corpus.KINDS), rng.randrange(1, 30000), enc)
                 f, _ = es.scan_stream(buf, False, 4096)
                 _cmp(es, os_, f, os_.scan_stream(buf, False, 4096).v)
-                assert es.stats[7] == 0  # no prefilter
+                grep_only = m.filter.grep_char is not None and not m.require_same_unicode_block and m.chars_min_nb <= q
+                assert es.stats[7] == (1 if grep_only else 0)  # prefilter only for --grep-char alone (PrefCfg::kill_trail)
             assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
     ok1, k1 = C.c_uint64(), C.c_uint64()
     L.sx_emul_guard_counts(C.byref(ok1), C.byref(k1))
@@ -125,7 +126,7 @@ def test_killed_window_case():
         assert [(x.position, x.s) for x in o] == expected
         f, _ = es.scan_stream(data, False, 4096)
         _cmp(es, os_, f, o)
-        assert es.stats[7] == 0  # general mission: no prefilter
+        assert es.stats[7] == 1 and 2 in es.last_list  # --grep-char alone: prefilter on, the killed window is listed
 
 
 def test_planted_corpus_utf16():

@@ -111,6 +111,34 @@ def test_differential_fuzz_general_missions(enc):
             check_state(gs, os_)
 
 
+@pytest.mark.parametrize("label,n,q,grep,kind", [
+    ("utf-8", 6, 64, ":", "rand"), ("utf-8", 10, 64, "e", "rand"), ("ascii", 4, 8, "e", "rand"), ("koi8-r", 3, 8, ":", "runs"),
+    ("iso-8859-5", 3, 8, ":", "rand"), ("utf-16le", 4, 16, "e", "rand"), ("utf-8", 3, 8, "a", "mixed"), ("ascii", 8, 16, " ", "text"),
+])
+def test_prefilter_window_list_matches_spec_grep(label, n, q, grep, kind):
+    """--grep-char alone keeps the prefilter with one more rule (a window behind >= q good chars is listed,
+    PrefCfg::kill_trail): the kernel lists exactly the windows of the byte-wise specification and the findings are the
+    oracle's."""
+    import emul
+
+    m = M.Mission.for_label(label, n, (1 << 128) - 2 if q == 8 else None, None, ord(grep), q)
+    rng = random.Random(123)
+    size = (1 << 20) + 4096
+    if kind == "rand":
+        buf = corpus.sx_mix_bytes(17, 0, size)
+        corpus.plant(buf, 17, m.encoding_id, n, q, density=1 << 12)
+        buf = buf.tobytes()
+    else:
+        buf = corpus.gen(rng, kind, size, m.encoding_id)
+    gs, es, os_ = sx.ScannerState(m), emul.EmulState(m, True), oracle_state(m)
+    got = gpu_findings(gs.scan_stream(buf, False, 4096))
+    exp, _ = es.scan_stream(buf, False, 4096)
+    assert gs.last_stats.prefilter_used == 1 and es.stats[7] == 1
+    assert gs.last_window_list() == es.last_list
+    assert got == exp == oracle_findings(os_.scan_stream(buf, False, 4096))
+    check_state(gs, os_)
+
+
 def test_killed_window_case():
     """corpus.KILLED_WINDOW_CASE (a window dropped because of its predecessor's leftover) on the GPU, also embedded in
     a larger stream so that the windows sit in the middle of a block."""
@@ -317,8 +345,8 @@ def test_prefilter_on_off_identical(enc):
 def test_general_missions_large_buffers_vs_oracle(enc):
     """--grep-char / --same-unicode-block / n > q on buffers of many 128-entry blocks (the block kernel's warm-up finds
     a known carry through the WT_GUARD rules, sx_core.cuh guard_benign / guard_known_behind): the oracle's findings,
-    on sparse input (random bytes + planted strings) and dense input.  These missions never use the prefilter (an
-    unlisted window's carry-out would depend on its carry-in)."""
+    on sparse input (random bytes + planted strings) and dense input, with and without the prefilter (which only
+    --grep-char alone may use, PrefCfg::kill_trail; DESIGN.md section 7)."""
     import dataclasses
 
     rng = random.Random(4242 + enc)
@@ -341,7 +369,8 @@ def test_general_missions_large_buffers_vs_oracle(enc):
                 continue
             ra = gpu_findings(a.scan_stream(part, False, 4096))
             rb = gpu_findings(b.scan_stream(part, False, 4096))
-            assert a.last_stats.prefilter_used == 0 and b.last_stats.prefilter_used == 0
+            grep_only = m.filter.grep_char is not None and not m.require_same_unicode_block and n <= q
+            assert a.last_stats.prefilter_used == (1 if grep_only else 0) and b.last_stats.prefilter_used == 0
             exp = oracle_findings(os_.scan_stream(part, False, 4096))
             assert ra == exp, (enc, m, len(part))
             assert rb == exp, (enc, m, len(part))
