@@ -84,7 +84,7 @@ int sx_device_count(void);
 /* ScannerState::new (scanner.rs:73-88).  `device`: CUDA ordinal the state's scans run on.
  * Returns NULL (and sets sx_last_error) for chars_min_nb == 0 and output_line_char_nb_max < 6 (options.rs:33) or
  * > 8192.  Missions with grep_char, require_same_unicode_block or chars_min_nb > output_line_char_nb_max take the
- * general automaton on every window (no prefilter: DESIGN.md section 7 has the counterexample). */
+ * general automaton; of these only grep_char alone keeps the prefilter. */
 sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device);
 void sx_scanner_state_free(sx_scanner_state*);
 /* Back to the state ScannerState::new leaves (scanner.rs:73-88), keeping the device buffers. */
