@@ -115,6 +115,32 @@ def test_general_missions_guard_rules():
     assert L.sx_emul_guard_behind() - b0 > 5000 and L.sx_emul_guard_behind_hard() - h0 > 20
 
 
+@pytest.mark.parametrize("enc", [0, 1, 2, 4, 5])
+def test_fuzz_grep_missions_with_prefilter(enc):
+    """--grep-char alone keeps the prefilter (PrefCfg::kill_trail: the window behind >= q good chars is listed).  Small
+    q makes q-char leftovers -- the ones that kill or "maybe cut" the next window -- frequent; the first version of the
+    rule (without the pending-bytes clause) failed 6 of 12 000 such missions, UTF-8 and UTF-16."""
+    import dataclasses
+
+    rng = random.Random(7100 + enc)
+    used = 0
+    for _ in range(60):
+        m = corpus.random_mission(rng, enc, M)
+        grep = rng.choice([0x20, ord("a"), ord("e"), ord(":"), ord("?"), 0x00])
+        q = rng.choice([64, 32, 16, 8, 8, 8])
+        m = dataclasses.replace(m, filter=dataclasses.replace(m.filter, grep_char=grep), require_same_unicode_block=False,
+                                output_line_char_nb_max=q, chars_min_nb=min(rng.choice([1, 2, 3, 3, 4, 6, 8, 10]), q))
+        es, os_ = emul.EmulState(m), oracle_state(m)
+        for c in range(rng.choice([1, 1, 2, 3])):
+            buf = corpus.gen(rng, rng.choice(corpus.KINDS), rng.randrange(1, 40000), enc)
+            sl = rng.choice([4096, 4096, 1024, 8192])
+            f, _ = es.scan_stream(buf, False, sl)
+            _cmp(es, os_, f, os_.scan_stream(buf, False, sl).v)
+            used += es.stats[7]
+        assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
+    assert used > 60  # the prefilter was on for most calls
+
+
 def test_killed_window_case():
     """corpus.KILLED_WINDOW_CASE: the oracle drops the segment behind a q-char leftover without the grep char
     (helper.rs:389-415), the harness follows."""
