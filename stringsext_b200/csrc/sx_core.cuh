@@ -1,22 +1,25 @@
-// sx_core.cuh -- per-window scanner automaton shared by the CUDA kernels (sx_kernels.cu).
+// sx_core.cuh -- per-window scanner automaton shared by the CUDA kernels (sx_scan.cu, sx_exact.cuh,
+// sx_sparse_utf8.cuh) and by the CPU test harness (tests/emul).
 //
 // One "window" is one decoder_input_window of the reference (2 * output_line_char_nb_max input
 // bytes, /root/reference/src/finding_collection.rs:120-131).  The reference walks windows
 // strictly sequentially; here every window is processed independently by one GPU lane:
 //
-//   * the decoder state at the window start is re-derived from the <= 5 preceding bytes
-//     (UTF-8 / UTF-16 are self-synchronising under the WHATWG decoders, see Dec*::init),
+//   * the decoder state at the window start is re-derived from the preceding bytes
+//     (UTF-8 / UTF-16 are self-synchronising under the WHATWG decoders, see Dec*::init; the
+//     lead/trail encodings Big5 / EUC-JP walk back to the last byte that cannot be a trail),
 //   * the scanner carry between windows (`Carry`: leftover run or "cut" flag, i.e.
 //     ScannerState.last_scan_run_leftover / last_run_str_was_printed_and_is_maybe_cut_str,
-//     /root/reference/src/scanner.rs:45-68) is resolved by the tile-level transfer-function
-//     pass in sx_kernels.cu,
+//     /root/reference/src/scanner.rs:45-68) is resolved along runs of adjacent listed windows by
+//     the exact stage (sx_exact.cuh block kernel / sx_sparse_utf8.cuh per-stage pipeline),
 //   * the SplitStr iterator (/root/reference/src/helper.rs:210-432) and the chunk loop of
 //     FindingCollection::from (finding_collection.rs:246-290) are restated as ONE streaming
 //     automaton over decoder events (`WinAuto`), so no decoded text is ever materialised.
 //
-// The automaton supports missions with grep_char == None, require_same_unicode_block == false
-// and 1 <= chars_min_nb <= output_line_char_nb_max (everything else is rejected loudly by
-// the C ABI; see DESIGN.md "Scope").
+// WinAuto is the GENERAL automaton: it also implements grep_char (helper.rs:215-331 incl. the
+// early-termination quirk), require_same_unicode_block (helper.rs:287-292) and
+// chars_min_nb > output_line_char_nb_max; the C ABI only rejects chars_min_nb == 0 and
+// output_line_char_nb_max outside 6..8192.
 //
 // Everything is SX_HD so the host-side *test* harness (tests/emul/) can run the same code on
 // the CPU to debug the decomposition without a GPU.  The product never does that.

@@ -1089,13 +1089,19 @@ static bool make_tensor_map(CUtensorMap* tm, const uint8_t* d_in, size_t len, ui
 template <int FAMILY, bool DEF, bool FAST>
 static cudaError_t launch_prefilter_t(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
                                       long long ntiles, int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
-    static thread_local bool attr_done[16] = {false};
+    // the attribute is per device and per instantiation; set once per device (any ordinal), process wide
+    static std::mutex mu;
+    static std::vector<char> attr_done;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 16 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(sx_prefilter_kernel<FAMILY, DEF, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrefSmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_done[dev] = true;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if ((size_t)dev >= attr_done.size()) attr_done.resize((size_t)dev + 1, 0);
+        if (!attr_done[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(sx_prefilter_kernel<FAMILY, DEF, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrefSmemBytes);
+            if (e != cudaSuccess) return e;
+            attr_done[dev] = 1;
+        }
     }
     sx_prefilter_kernel<FAMILY, DEF, FAST><<<grid, kPrefThreads, kPrefSmemBytes, st>>>(P, c, k, o, total_windows, ntiles, tm, use_tma);
     return cudaGetLastError();
@@ -1232,6 +1238,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         if (pc.enabled) {
             const PrefK pk = make_pref_k(P, pc);
             int pgrid = (int)std::min<long long>(ntiles, std::min<long long>(1024, (long long)ss->num_sms * 3));
+            if (const char* ev = getenv("SX_PREF_GRID")) { const int g = atoi(ev); if (g > 0) pgrid = (int)std::min<long long>(ntiles, std::min(1024, g)); }
             const long long tiles_per_cta = (ntiles + pgrid - 1) / pgrid;
             pgrid = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
             const PrefOut po{ss->d_list, ss->d_ccount, tiles_per_cta};
