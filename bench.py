@@ -362,7 +362,7 @@ def main():
         kernels = {"sx_prefilter_kernel": avg(pre_ms), "sx_list_offsets_kernel": avg(lst_ms), "sx_materialize_kernel": avg(mat_ms)}
         if sparse_used:
             # exact stage = the sparse-list pipeline (sx_sparse_utf8.cuh): one entry per kernel (group), CUDA events between them
-            names = ("sx_sp_tables_kernel", "sx_sp_heads_kernel", "sx_sp_members_kernel", "sx_sp_fix_kernel", "sx_sp_ext_kernel",
+            names = ("sx_list_compact_kernel", "sx_sp_heads_kernel", "sx_sp_members_kernel", "sx_sp_fix_kernel", "sx_sp_ext_kernel",
                      "sx_sp_scan+gather")
             for i, nm in enumerate(names):
                 kernels[nm] = avg([v[i] for v in sp_ms])

@@ -109,6 +109,20 @@ sx_finding_collection* sx_finding_collection_from(sx_scanner_state*, int input_f
 sx_finding_collection* sx_scan_stream(sx_scanner_state*, int input_file_id, const void* buf, size_t len,
                                       size_t slice_len, int buf_is_device, int is_last, void* cuda_stream);
 
+/* One RANGE of a resident stream: the findings sx_scan_stream would emit while it processes the bytes [lo, hi) of buf
+ * (lo, hi multiples of slice_len, or hi == len), in the same order -- so the collections of consecutive ranges
+ * concatenate to the collection of the whole call.  This is how one mission is spread over several GPUs / streams
+ * (SURVEY.md 8(e)(2)): the reference gives a mission one thread (main.rs:151-167), here every device scans its own
+ * range.  The carry into the range's first window is derived on the device by walking back to the nearest window
+ * whose carry-out does not depend on its carry-in (on binary input: the window before the range).
+ * flags & SX_RANGE_PREFIX_UNKNOWN: buf does not start where the state stands but somewhere earlier in the stream
+ * (a halo in front of the range, lo > 0; the state's counter_offset / consumed bytes must equal the stream offset
+ * of buf[0]); the call fails (SX_ERR_UNSUPPORTED) if the walk back would have to leave the halo.
+ * The ScannerState only moves on when hi == len (then exactly as sx_scan_stream would leave it). */
+enum { SX_RANGE_PREFIX_UNKNOWN = 1 };
+sx_finding_collection* sx_scan_range(sx_scanner_state*, int input_file_id, const void* buf, size_t len, size_t slice_len,
+                                     int buf_is_device, int is_last, size_t lo, size_t hi, int flags, void* cuda_stream);
+
 /* FindingCollection accessors (finding_collection.rs:31-50, :371-415). */
 size_t sx_fc_len(const sx_finding_collection*);
 const sx_finding* sx_fc_get(const sx_finding_collection*, size_t i);
@@ -135,14 +149,15 @@ typedef struct {
     uint32_t relaunches;         /* pipeline re-runs caused by an output buffer that was too small */
     uint32_t prefilter_used;
     uint32_t tma_used;           /* the prefilter staged its tiles with cp.async.bulk.tensor */
-    uint32_t sparse_used;        /* the exact stage ran as the barrier-free sparse-list pipeline (UTF-8) */
-    uint32_t reserved0;
+    uint32_t sparse_used;        /* the exact stage ran as the barrier-free sparse-list pipeline (UTF-8, single-byte) */
+    uint32_t pieces;             /* pieces the call was cut into (prefilter of piece k+1 overlaps exact stage + download of piece k) */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t n_records, text_bytes;
     uint64_t windows_total, windows_listed;
     float host_total_ms; /* wall clock of the whole call */
     float host_post_ms;  /* of which: building the collection after the last device sync */
-    float sparse_stage_ms[6]; /* sparse pipeline (sparse_used): tables, heads, members, fix+late, ext, scan+gather kernels */
+    float sparse_stage_ms[6]; /* sparse pipeline (sparse_used), summed over the pieces: list compaction, heads, members,
+                               * fix+late, ext, scan+gather kernels */
     float host_phase_ms[4]; /* wall clock: [0] call start -> kernels enqueued, [1] -> counters back (first sync),
                              * [2] -> results downloaded (second sync), [3] -> collection built */
 } sx_scan_stats;
@@ -155,6 +170,8 @@ void sx_scanner_state_set_sparse(sx_scanner_state*, int mode); /* 0: always the 
                                                                  * UTF-8 missions take the per-stage pipeline whenever its
                                                                  * per-entry state fits in memory */
 void sx_scanner_state_set_direct_output(sx_scanner_state*, int enabled); /* 0: download records, convert on the host */
+void sx_scanner_state_set_pieces(sx_scanner_state*, int pieces); /* sparse pipeline: cut every call into this many pieces
+                                                                  * (0: automatic, by size); results never depend on it */
 /* Copies the window list the prefilter built in the most recent call (ascending window indices,
  * window = decoder_input_window of finding_collection.rs:120-131) into out[0..cap); returns the
  * list length, 0 when the prefilter did not run. */

@@ -63,10 +63,20 @@ struct ExactCfg {
     long long total_windows;
     uint32_t in_aligned16;
     uint32_t pre_bytes;                // pre-roll length for entries whose predecessor window is not listed
-    const uint32_t* cta_off;           // list != nullptr: entry offsets of the prefilter CTAs' list regions (ncta + 1)
-    uint32_t ncta;
+    const uint32_t* cta_off;           // list != nullptr: entry offsets of the prefilter CTAs' list regions (ncta + 1);
+    uint32_t ncta;                     // ncta == 0: `list` is compact (entry e is list[e])
     unsigned long long region_stride;  // list region of prefilter CTA b starts at b * region_stride
+    // Window range of this pass, [w_first, w_end) of the stream's windows (a whole call: 0 .. total_windows).  The first
+    // window of a range is always listed; its carry-in is *k0_ptr (device; written by sx_range_carry_kernel, which walks
+    // back to the nearest window whose carry-out does not depend on its carry-in) or P.k0 when k0_ptr == nullptr.  A
+    // range that ends before the stream does leaves what its last carry prints in the next window to the next range
+    // (whose first window is listed by construction) and produces no final leftover.
+    long long w_first, w_end;
+    const Carry* k0_ptr;
+    unsigned long long ne_cap;         // capacity of the per-entry arrays (pipelined pieces: ne beyond it is an overflow)
 };
+__device__ __forceinline__ Carry range_carry_in(const ScanParams& P, const ExactCfg& X) { return X.k0_ptr ? *X.k0_ptr : P.k0; }
+__device__ __forceinline__ bool range_is_tail(const ExactCfg& X) { return X.w_end >= X.total_windows; }
 
 __device__ __forceinline__ uint32_t swz(uint32_t r) { return r ^ (((r >> 7) & 7u) << 4); }
 
@@ -197,7 +207,8 @@ constexpr uint32_t kNoWin = 0xFFFFFFFEu;
 
 // entry index -> window index: binary search of the owning prefilter CTA's region (offsets staged in smem)
 __device__ __forceinline__ long long list_window(const ExactCfg& X, const uint32_t* soff, long long e) {
-    if (!X.list) return e;
+    if (!X.list) return X.w_first + e;
+    if (X.ncta == 0) return (long long)X.list[e];
     uint32_t lo = 0, hi = X.ncta;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
@@ -292,9 +303,9 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
     __syncthreads();
     if constexpr (kIsUtf8) {
         if (active && use_mask && !adj) {
-            Carry kin0 = P.k0;
+            Carry kin0 = range_carry_in(P, X);
             bool ok = true;
-            if (w != 0) {
+            if (w != X.w_first) {
                 const WinGeom rg = preroll_geom(geo, w, X.pre_bytes);
                 WinResult rr;
                 ok = utf8_mask_window(P, ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr);
@@ -345,7 +356,7 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             geo.window(wj_idx, wj);
             Carry kin0 = carry_none();
             if (!adj_j) {
-                if (wj_idx == 0) kin0 = P.k0;
+                if (wj_idx == X.w_first) kin0 = range_carry_in(P, X);
                 else {
                     const WinGeom rg = preroll_geom(geo, wj_idx, X.pre_bytes);
                     WinResult rr;
@@ -459,7 +470,7 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
         if (!S.have_cnt[i]) need_emit = needs_emit(P, d, kin);
         // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an
         // unlisted successor: that window may print a continuation / the leftover
-        ext = carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.total_windows;
+        ext = carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.w_end;
     }
     {
         const uint32_t nq = block_enqueue(S, need_emit, i, ext, i | 0x10000u);
@@ -502,7 +513,7 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
         }
     }
     const bool is_final = active && (e0 + i == NE - 1);
-    const bool extra = is_final && kout.kind == K_L && kout.k > 0;  // the scanner's final leftover as a pseudo record
+    const bool extra = is_final && range_is_tail(X) && kout.kind == K_L && kout.k > 0;  // the scanner's final leftover as a pseudo record
     uint32_t sum_r = cr + xr + (extra ? 1u : 0u), sum_t = ct + xt + (extra ? kout.out_bytes : 0u);
     uint32_t er, et, tr, tt;
     block_excl_scan2(sum_r, sum_t, S.warp_a, S.warp_b, er, et, tr, tt);
@@ -608,28 +619,101 @@ sx_exact_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const Exa
 }
 
 
-// launchers, one per decoder (defined in sx_exact_inst.cu)
-cudaError_t launch_exact_xud(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
-cudaError_t launch_exact_utf8(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
-cudaError_t launch_exact_utf16le(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
-cudaError_t launch_exact_utf16be(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
-cudaError_t launch_exact_sb(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
-cudaError_t launch_exact_utf32le(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
-cudaError_t launch_exact_utf32be(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);
+// Carry into the first window of a range that does not start at the stream start (pieces of a pipelined call, ranges
+// of a stream sharded over several GPUs): walk back from the window before it to the nearest window whose carry-out
+// does not depend on its carry-in -- the rule the exact stage already relies on (mask engine: WinResult.cut1 == 0;
+// byte-wise engine: WinDesc WT_CONST) -- then replay forward under the real carries.  On binary input the window right
+// before the range almost always qualifies; on text about 85 % of the windows do.  One warp per range, lane 0 works.
+//   out[r]: the carry; fail[r] != 0: no such window within `max_back` windows, or the walk reached window 0 while the
+//   carry at the stream start is not known (prefix_known == 0)
+struct RangeCarryOut { Carry k0; uint32_t fail; uint32_t back; };
+constexpr int kMaxRanges = 32;
+struct RangeCarryArgs {
+    long long w_first[kMaxRanges];
+    uint32_t nranges, in_aligned16, prefix_known, max_back;
+    RangeCarryOut* out;        // device; element r at byte offset r * out_stride
+    size_t out_stride;
+};
+template <class Dec>
+__global__ void __launch_bounds__(32)
+sx_range_carry_kernel(const __grid_constant__ ScanParams P, const __grid_constant__ RangeCarryArgs A) {
+    const uint32_t nranges = A.nranges, in_aligned16 = A.in_aligned16, prefix_known = A.prefix_known, max_back = A.max_back;
+    RangeCarryOut* const out = A.out;
+    const size_t out_stride = A.out_stride;
+    __shared__ Utf8Tables T;
+    constexpr bool kMask = MaskFamily<Dec>::kHas;
+    if (kMask)
+        for (uint32_t k = threadIdx.x; k < 2048; k += 32) mask_tables_fill(P, T, k);
+    __syncthreads();
+    if (threadIdx.x != 0 || blockIdx.x >= nranges) return;
+    RangeCarryOut* const o = reinterpret_cast<RangeCarryOut*>(reinterpret_cast<uint8_t*>(out) + (size_t)blockIdx.x * out_stride);
+    const long long wb = A.w_first[blockIdx.x];
+    Geometry geo;
+    geo.init(P);
+    const GlobalSrc g{P.in, P.pend};
+    const GlobalTile ts{g, P.len, in_aligned16 != 0, kMask ? &T : nullptr, (uint32_t)__cvta_generic_to_shared(&T.tt[0])};
+    Carry c = P.k0;
+    uint32_t fail = 0, back = 0;
+    long long start = 0;
+    if (wb > 0) {
+        long long j = wb - 1;
+        for (;;) {
+            if (j < 0) { fail = prefix_known ? 0u : 1u; c = P.k0; start = 0; break; }
+            if (back >= max_back) { fail = 1; break; }
+            WinGeom wg;
+            geo.window(j, wg);
+            WinResult rr;
+            bool indep;
+            Carry co;
+            bool done = false;
+            if constexpr (kMask) {
+                if (!P.general && mask_window<MaskFamily<Dec>::kSByte>(P, ts, wg, carry_none(), MODE_STATE, nullptr, 0, rr)) {
+                    indep = rr.cut1 == 0; co = rr.out; done = true;
+                }
+            }
+            if (!done) {
+                WinDesc d;
+                WindowEngine<Dec>::run(P, ts, g, wg, carry_none(), MODE_COUNT, nullptr, 0, rr, &d);
+                if (P.general && d.type == WT_DEP)
+                    d.type = classify_general(wg, rr, [&](const WinGeom& g2) {
+                        WinResult r2;
+                        WindowEngine<Dec>::run(P, ts, g, g2, carry_none(), MODE_STATE, nullptr, 0, r2, nullptr);
+                        return r2.out;
+                    });
+                indep = d.type == WT_CONST; co = d.null_out;
+            }
+            ++back;
+            if (indep) { c = co; start = j + 1; break; }
+            --j;
+        }
+        if (!fail) {
+            for (long long w = start; w < wb; ++w) {
+                WinGeom wg;
+                geo.window(w, wg);
+                WinResult rr;
+                bool done = false;
+                if constexpr (kMask) done = !P.general && mask_window<MaskFamily<Dec>::kSByte>(P, ts, wg, c, MODE_STATE, nullptr, 0, rr);
+                if (!done) WindowEngine<Dec>::run(P, ts, g, wg, c, MODE_STATE, nullptr, 0, rr, nullptr);
+                c = rr.out;
+            }
+        }
+    }
+    o->k0 = c;
+    o->fail = fail;
+    o->back = back;
+}
 
-// sparse-list pipeline for UTF-8 (sx_sparse_utf8.cuh, compiled into the UTF-8 translation unit)
-cudaError_t launch_sparse_utf8(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                               void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side,
-        cudaEvent_t* evs);
-cudaError_t launch_sparse_xud(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                              void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side,
-        cudaEvent_t* evs);
-cudaError_t launch_sparse_sb(const ScanParams& P, const ScanOut& O, const ExactCfg& X, void* entries, void* btot, void* tables,
-                             void* queue, long long NE, int num_sms, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side,
-        cudaEvent_t* evs);
-size_t sparse_entry_bytes();
-size_t sparse_tables_bytes();
-uint32_t sparse_threads();
-uint32_t sparse_launches();
+// Launchers, one set per decoder, each in its own translation unit (sx_exact_inst.cu compiled with -DSX_INST=<ENC_*>).
+struct SparseBufs;
+struct SparseLaunchCfg;
+#define SX_DECLARE_INST(N)                                                                                                          \
+    cudaError_t launch_exact_##N(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st);         \
+    cudaError_t launch_range_carry_##N(const ScanParams& P, const RangeCarryArgs& A, cudaStream_t st);                              \
+    cudaError_t launch_sparse_##N(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B,                    \
+                                  const SparseLaunchCfg& L, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side, cudaEvent_t* evs); \
+    bool has_sparse_##N();
+SX_DECLARE_INST(0) SX_DECLARE_INST(1) SX_DECLARE_INST(2) SX_DECLARE_INST(3) SX_DECLARE_INST(4) SX_DECLARE_INST(5) SX_DECLARE_INST(6)
+#undef SX_DECLARE_INST
+constexpr int kNumInst = 7;
 
 }  // namespace sx

@@ -13,6 +13,7 @@
 // There is no CPU scanning path in this file: without a CUDA device every call fails.
 #include "../../include/stringsext_b200.h"
 #include "sx_exact.cuh"
+#include "sx_sparse_utf8.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -38,9 +39,12 @@ namespace sx {
 // Every prefilter CTA owns a contiguous range of tiles and compacts the windows it keeps into its own
 // region of `list` (region of CTA b starts at b * region_stride); cta_count[b] = how many it kept.
 struct PrefOut {
-    uint32_t* list;
-    uint32_t* cta_count;
+    uint32_t* list;        // indexed by tile: the region of a CTA starts at its first tile * 256
+    uint32_t* cta_count;   // of this launch (piece)
     long long tiles_per_cta;
+    long long tile0, tile_end;  // tiles of this launch: one piece of the call's window range
+    long long w_first;          // first window of the piece: always listed (its carry-in is given, sx_range_carry_kernel)
+    long long w_lo, w_hi;       // the call's window range: windows of the boundary tiles outside it are not this call's
 };
 
 struct PrefK {
@@ -243,7 +247,7 @@ constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64 + 32 + kP
 template <int FAMILY, bool DEFSHAPE, bool FAST>
 __global__ void __launch_bounds__(kPrefThreads, 3)
 sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const __grid_constant__ PrefK K, const PrefOut O,
-                    long long total_windows, long long ntiles, const __grid_constant__ CUtensorMap tmap, uint32_t use_tma) {
+                    long long total_windows, const __grid_constant__ CUtensorMap tmap, uint32_t use_tma) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // two 32 KiB stages (TMA SWIZZLE_128B layout == swz()), then the per-tile exchange arrays and the mbarriers
     uint32_t* s_trail = reinterpret_cast<uint32_t*>(smem_raw + 2 * kPrefStageBytes);  // 256
@@ -256,8 +260,8 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = P.W, nchunk = W >> 4;
     const uint32_t tile_bytes = kPrefTileWin * W;
-    const long long t_begin = (long long)blockIdx.x * O.tiles_per_cta;
-    const long long t_end = (t_begin + O.tiles_per_cta) < ntiles ? (t_begin + O.tiles_per_cta) : ntiles;
+    const long long t_begin = O.tile0 + (long long)blockIdx.x * O.tiles_per_cta;
+    const long long t_end = (t_begin + O.tiles_per_cta) < O.tile_end ? (t_begin + O.tiles_per_cta) : O.tile_end;
     uint32_t* const my_list = O.list + (size_t)t_begin * kPrefTileWin;
     uint32_t kept = 0;  // windows this CTA has listed so far (uniform across the block)
     const int64_t full_rows_bytes = (P.len >> 7) << 7;  // the tensor map covers whole 128-byte rows only
@@ -309,7 +313,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         // ---- per-window classification -----------------------------------------------------------------
         const long long w = tile * kPrefTileWin + tid;
         const int64_t ws = lo + (int64_t)tid * W;
-        bool valid = w < total_windows;
+        bool valid = w < total_windows && w >= O.w_lo && w < O.w_hi;
         uint32_t wlen = 0;
         if (valid) wlen = (uint32_t)(((ws + W) < P.len ? (ws + W) : P.len) - ws);
         uint32_t m[4] = {0, 0, 0, 0};
@@ -412,7 +416,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             const bool crossing = (r[1] & cross_bits) != 0;
             const bool inwin = ((r[1] & ~cross_bits) | r[2] | r[3] | r[4]) != 0;
             if (valid) {
-                const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
+                const bool forced = (w == O.w_first) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
                 sure = forced || crossing;
                 if (!sure && inwin) { if (do_refine) cand = true; else sure = true; }
             }
@@ -540,7 +544,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         __syncthreads();
         // sure: listed whatever the refinement says; cand: listed only if a long run holds enough chars
         if (valid) {
-            const bool forced = (w == 0) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
+            const bool forced = (w == O.w_first) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
             if (forced) sure = true;
             else if (tid == 0) sure = lead >= 1 || C.kill_trail != 0;
             else {
@@ -762,6 +766,23 @@ static bool cuda_ok(cudaError_t e, const char* what) {
         if (!cuda_ok((call), #call)) return fail; \
     } while (0)
 
+constexpr int kMaxPieces = 32;
+// Host-visible control block of a state (pinned, device-mapped): what the kernels of the sparse pipeline report per piece
+// and the final state of the scan; the host reads it after an event, no small device-to-host copies.
+struct HostCtl {
+    PieceSummary piece[kMaxPieces];
+    FinalState fin;
+    uint8_t tail[8];  // the last bytes of a device-resident buffer (pending decoder bytes of the ScannerState)
+};
+struct PieceEvents {
+    cudaEvent_t p0 = nullptr, p1 = nullptr;  // around the piece's prefilter launch
+    cudaEvent_t b0 = nullptr, b1 = nullptr;  // around its exact stage
+    cudaEvent_t sev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t sord[2] = {nullptr, nullptr};
+    cudaEvent_t sc = nullptr;                // after the piece's sx_sp_scan_kernel (the next piece's scan builds on its totals)
+    cudaEvent_t gp[kGatherParts] = {nullptr, nullptr, nullptr, nullptr};  // after every part of its gather
+};
+
 struct sx_scanner_state {
     sx_mission m;
     int device;
@@ -783,13 +804,23 @@ struct sx_scanner_state {
     int use_prefilter = 1;
     int use_tma = 1;
     int use_sparse = 1;
-    int use_direct = 1;  // findings written by the GPU into pinned host memory (0: record download + host conversion)
-    uint8_t* d_entries = nullptr; size_t entries_cap = 0;   // sparse pipeline: per-entry state
+    int use_direct = 1;  // findings written by the GPU in their C-ABI form (0: record download + host conversion)
+    int pieces = 0;      // test / tuning hook: number of pieces of the sparse pipeline (0: automatic)
+    // sparse pipeline: per-entry arrays (EntryHot, null carries, staged records), per-chunk totals, tables, queues,
+    // compact list, per-piece control blocks, staging of the findings in their C-ABI form
+    uint8_t* d_entries = nullptr; size_t entries_cap = 0;
     uint8_t* d_btot = nullptr; size_t btot_cap = 0;
     uint8_t* d_tables = nullptr; size_t tables_cap = 0;
-    uint8_t* d_queue = nullptr; size_t queue_cap = 0;
+    uint32_t* d_queue = nullptr; size_t queue_cap = 0;
+    uint32_t* d_clist = nullptr; size_t clist_cap = 0;
+    sx_finding* d_findings = nullptr; size_t findings_cap = 0;
+    PieceCtl* d_ctl = nullptr;
+    HostCtl* h_ctl = nullptr;
     unsigned long long* d_bpos = nullptr; size_t bpos_cap = 0;  // block path, direct output: stream-order position of every block
     uint32_t last_ncta = 0; size_t last_region_stride = 0;
+    bool last_list_compact = false; size_t last_list_len = 0;
+    const uint32_t* last_list_base = nullptr;
+    std::vector<std::pair<size_t, size_t>> last_piece_lists;  // (offset into d_clist, entries) per piece
     // pinned host staging for result downloads
     Record* h_recs = nullptr; size_t h_recs_cap = 0;
     uint8_t* h_text = nullptr; size_t h_text_cap = 0;
@@ -797,11 +828,17 @@ struct sx_scanner_state {
     unsigned long long* d_counters = nullptr;
     FinalState* d_final = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t sev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // sparse pipeline stages
-    cudaEvent_t sord[2] = {nullptr, nullptr};  // ... ordering with the side stream (declined heads beside the members)
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    std::vector<PieceEvents> pev;
     cudaStream_t side = nullptr;
+    cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr;  // prefilter / set-up of the exact stage / copies to the host
+    static constexpr int kLanes = 4;                        // exact stages of consecutive pieces run side by side: their kernels are
+    cudaStream_t sBk[kLanes] = {nullptr, nullptr, nullptr, nullptr};    // latency bound, a piece's chain takes longer than its prefilter
+    cudaStream_t sidek[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_setup = nullptr;
     int num_sms = 0;
     double rec_per_byte = 1.0 / 1024, text_per_byte = 1.0 / 64;
+    double listed_frac = 1.0 / 16;  // windows the prefilter kept in the previous scan (sizes the entry arrays of large calls)
     // direct host output: cap on the pinned set of a state's FIRST scan (the estimate from rec_per_byte is generous
     // until a scan has been seen; an overflow simply reruns the exact stage with the counted sizes)
     size_t host_rec_hint = 1u << 20, host_text_hint = 16u << 20;
@@ -935,27 +972,52 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
     if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete ss; return fail; }
     ss->num_sms = prop.multiProcessorCount;
     bool ok = cuda_ok(cudaMalloc(&ss->d_counters, 8 * sizeof(unsigned long long)), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&ss->d_final, sizeof(FinalState)), "cudaMalloc");
+              cuda_ok(cudaMalloc(&ss->d_final, sizeof(FinalState)), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&ss->d_ctl, sizeof(PieceCtl) * kMaxPieces), "cudaMalloc") &&
+              cuda_ok(cudaHostAlloc((void**)&ss->h_ctl, sizeof(HostCtl), cudaHostAllocPortable | cudaHostAllocMapped), "cudaHostAlloc");
     for (int i = 0; ok && i < 6; ++i) ok = cuda_ok(cudaEventCreate(&ss->ev[i]), "cudaEventCreate");
-    for (int i = 0; ok && i < 7; ++i) ok = cuda_ok(cudaEventCreate(&ss->sev[i]), "cudaEventCreate");
-    for (int i = 0; ok && i < 2; ++i) ok = cuda_ok(cudaEventCreateWithFlags(&ss->sord[i], cudaEventDisableTiming), "cudaEventCreate");
-    ok = ok && cuda_ok(cudaStreamCreateWithFlags(&ss->side, cudaStreamNonBlocking), "cudaStreamCreate");
+    ok = ok && cuda_ok(cudaEventCreateWithFlags(&ss->ev_in, cudaEventDisableTiming), "cudaEventCreate") &&
+         cuda_ok(cudaEventCreateWithFlags(&ss->ev_done, cudaEventDisableTiming), "cudaEventCreate");
+    // the exact stage and the copies outrank the streaming prefilter: their small kernels must not queue behind it
+    int prio_lo = 0, prio_hi = 0;
+    if (ok) ok = cuda_ok(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi), "cudaDeviceGetStreamPriorityRange");
+    ok = ok && cuda_ok(cudaStreamCreateWithPriority(&ss->side, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate") &&
+         cuda_ok(cudaStreamCreateWithPriority(&ss->sA, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate") &&
+         cuda_ok(cudaStreamCreateWithPriority(&ss->sB, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate") &&
+         cuda_ok(cudaStreamCreateWithPriority(&ss->sC, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate") &&
+         cuda_ok(cudaEventCreateWithFlags(&ss->ev_setup, cudaEventDisableTiming), "cudaEventCreate");
+    for (int i = 0; ok && i < sx_scanner_state::kLanes; ++i)
+        ok = cuda_ok(cudaStreamCreateWithPriority(&ss->sBk[i], cudaStreamNonBlocking, prio_hi), "cudaStreamCreate") &&
+             cuda_ok(cudaStreamCreateWithPriority(&ss->sidek[i], cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
     if (!ok) { sx_scanner_state_free(ss); return fail; }
     return ss;
 }
 
 void sx_scanner_state_free(sx_scanner_state* ss) {
     if (!ss) return;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     cudaSetDevice(ss->device);
     cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_blocks); cudaFree(ss->d_ccount); cudaFree(ss->d_coff); cudaFree(ss->d_list);
-    cudaFree(ss->d_counters); cudaFree(ss->d_final);
+    cudaFree(ss->d_counters); cudaFree(ss->d_final); cudaFree(ss->d_ctl);
     cudaFree(ss->d_entries); cudaFree(ss->d_btot); cudaFree(ss->d_tables); cudaFree(ss->d_queue); cudaFree(ss->d_bpos);
-    cudaFreeHost(ss->h_recs); cudaFreeHost(ss->h_text); cudaFreeHost(ss->h_blocks);
+    cudaFree(ss->d_clist); cudaFree(ss->d_findings);
+    cudaFreeHost(ss->h_recs); cudaFreeHost(ss->h_text); cudaFreeHost(ss->h_blocks); cudaFreeHost(ss->h_ctl);
     for (auto e : ss->ev) if (e) cudaEventDestroy(e);
-    for (auto e : ss->sev) if (e) cudaEventDestroy(e);
-    for (auto e : ss->sord) if (e) cudaEventDestroy(e);
-    if (ss->side) cudaStreamDestroy(ss->side);
+    if (ss->ev_in) cudaEventDestroy(ss->ev_in);
+    if (ss->ev_done) cudaEventDestroy(ss->ev_done);
+    for (auto& pe : ss->pev) {
+        for (cudaEvent_t e : {pe.p0, pe.p1, pe.b0, pe.b1, pe.sc}) if (e) cudaEventDestroy(e);
+        for (auto e : pe.sev) if (e) cudaEventDestroy(e);
+        for (auto e : pe.sord) if (e) cudaEventDestroy(e);
+        for (auto e : pe.gp) if (e) cudaEventDestroy(e);
+    }
+    for (cudaStream_t q : {ss->side, ss->sA, ss->sB, ss->sC}) if (q) cudaStreamDestroy(q);
+    for (cudaStream_t q : ss->sBk) if (q) cudaStreamDestroy(q);
+    for (cudaStream_t q : ss->sidek) if (q) cudaStreamDestroy(q);
+    if (ss->ev_setup) cudaEventDestroy(ss->ev_setup);
     delete ss;
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
 }
 
 void sx_scanner_state_reset(sx_scanner_state* ss) {
@@ -982,17 +1044,26 @@ size_t sx_scanner_state_last_window_list(const sx_scanner_state* ss, uint32_t* o
     const size_t k = n < cap ? n : cap;
     if (k && out) {
         cudaSetDevice(ss->device);
+        size_t done = 0;
+        if (ss->last_list_compact) {  // sparse pipeline: the pieces' compact lists
+            for (const auto& pl : ss->last_piece_lists) {
+                const size_t c = std::min<size_t>(pl.second, k - done);
+                if (c && cudaMemcpy(out + done, ss->d_clist + pl.first, c * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+                done += c;
+            }
+            return n;
+        }
         std::vector<uint32_t> off(ss->last_ncta + 1);
         if (cudaMemcpy(off.data(), ss->d_coff, off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-        size_t done = 0;
         for (uint32_t b = 0; b < ss->last_ncta && done < k; ++b) {
             const size_t c = std::min<size_t>(off[b + 1] - off[b], k - done);
-            if (c && cudaMemcpy(out + done, ss->d_list + (size_t)b * ss->last_region_stride, c * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+            if (c && cudaMemcpy(out + done, ss->last_list_base + (size_t)b * ss->last_region_stride, c * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
             done += c;
         }
     }
     return n;
 }
+void sx_scanner_state_set_pieces(sx_scanner_state* ss, int pieces) { ss->pieces = pieces < 0 ? 0 : (pieces > kMaxPieces ? kMaxPieces : pieces); }
 
 size_t sx_fc_len(const sx_finding_collection* fc) { return fc->v.size(); }
 const sx_finding* sx_fc_get(const sx_finding_collection* fc, size_t i) { return &fc->v[i]; }
@@ -1025,19 +1096,6 @@ static bool grow(T** p, size_t* cap, size_t need, bool slack = true) {
     if (!cuda_ok(cudaMalloc(p, want * sizeof(T)), "cudaMalloc")) return false;
     *cap = want;
     return true;
-}
-
-static cudaError_t launch_exact_enc(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st) {
-    switch (P.enc) {
-    case ENC_XUD: return launch_exact_xud(P, O, X, grid, st);
-    case ENC_UTF8: return launch_exact_utf8(P, O, X, grid, st);
-    case ENC_UTF16LE: return launch_exact_utf16le(P, O, X, grid, st);
-    case ENC_UTF16BE: return launch_exact_utf16be(P, O, X, grid, st);
-    case ENC_SB: return launch_exact_sb(P, O, X, grid, st);
-    case ENC_UTF32LE: return launch_exact_utf32le(P, O, X, grid, st);
-    case ENC_UTF32BE: return launch_exact_utf32be(P, O, X, grid, st);
-    }
-    return cudaErrorInvalidValue;
 }
 
 static PrefK make_pref_k(const ScanParams& P, const PrefCfg& c) {
@@ -1088,7 +1146,7 @@ static bool make_tensor_map(CUtensorMap* tm, const uint8_t* d_in, size_t len, ui
 
 template <int FAMILY, bool DEF, bool FAST>
 static cudaError_t launch_prefilter_t(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
-                                      long long ntiles, int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
+                                      int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
     // the attribute is per device and per instantiation; set once per device (any ordinal), process wide
     static std::mutex mu;
     static std::vector<char> attr_done;
@@ -1103,16 +1161,16 @@ static cudaError_t launch_prefilter_t(const ScanParams& P, const PrefCfg& c, con
             attr_done[dev] = 1;
         }
     }
-    sx_prefilter_kernel<FAMILY, DEF, FAST><<<grid, kPrefThreads, kPrefSmemBytes, st>>>(P, c, k, o, total_windows, ntiles, tm, use_tma);
+    sx_prefilter_kernel<FAMILY, DEF, FAST><<<grid, kPrefThreads, kPrefSmemBytes, st>>>(P, c, k, o, total_windows, tm, use_tma);
     return cudaGetLastError();
 }
 
 static cudaError_t launch_prefilter(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
-                                    long long ntiles, int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
+                                    int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
     const bool defshape = c.family == PF_UTF8 && c.blkA == 0xEu && c.blkH == (1u << 6) && !c.multi;
     const bool fast = P.W == 128 && c.T <= 32 && c.kill_trail == 0;  // the bit-plane path keeps only T - 1 flags of the previous window
-#define SX_PREF(F, D) (fast ? launch_prefilter_t<F, D, true>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma) \
-                            : launch_prefilter_t<F, D, false>(P, c, k, o, total_windows, ntiles, grid, st, tm, use_tma))
+#define SX_PREF(F, D) (fast ? launch_prefilter_t<F, D, true>(P, c, k, o, total_windows, grid, st, tm, use_tma) \
+                            : launch_prefilter_t<F, D, false>(P, c, k, o, total_windows, grid, st, tm, use_tma))
     switch (c.family) {
     case PF_BYTE: return SX_PREF(PF_BYTE, false);
     case PF_UTF8: return defshape ? SX_PREF(PF_UTF8, true) : SX_PREF(PF_UTF8, false);
@@ -1127,22 +1185,549 @@ static size_t utf8_char_count(const std::vector<uint8_t>& s) {
     return n;
 }
 
-extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input_file_id, const void* buf, size_t len,
-                                                 size_t slice_len, int buf_is_device, int is_last, void* cuda_stream) {
+// =============================================================================================
+// sx_scan_stream / sx_scan_range
+// =============================================================================================
+struct CallCtx {
+    sx_scanner_state* ss;
+    sx_finding_collection* fc;
+    int input_file_id;
+    const uint8_t* d_in;
+    size_t len;
+    cudaStream_t st;
+    ScanParams P;
+    PrefCfg pc;
+    long long total_windows, w_lo, w_hi;  // the call's window range
+    bool in_aligned16, prefix_known, buf_is_device;
+    std::chrono::steady_clock::time_point t_begin;
+    // results of the device part
+    size_t nrec = 0, ntext = 0;
+    unsigned long long windows_listed = 0;
+    FinalState fin;
+    bool direct_out = false;   // findings and text are complete in fc->set
+    bool records_in_order = false;  // (legacy download) d_recs is in stream order: one descriptor
+    uint8_t tail[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t tail_n = 0;
+};
+static float ms_since(const std::chrono::steady_clock::time_point& t0) {
+    return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+static cudaError_t launch_exact_enc(const ScanParams& P, const ScanOut& O, const ExactCfg& X, unsigned grid, cudaStream_t st) {
+    switch (P.enc) {
+    case 0: return launch_exact_0(P, O, X, grid, st);
+    case 1: return launch_exact_1(P, O, X, grid, st);
+    case 2: return launch_exact_2(P, O, X, grid, st);
+    case 3: return launch_exact_3(P, O, X, grid, st);
+    case 4: return launch_exact_4(P, O, X, grid, st);
+    case 5: return launch_exact_5(P, O, X, grid, st);
+    case 6: return launch_exact_6(P, O, X, grid, st);
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t launch_range_carry_enc(const ScanParams& P, const RangeCarryArgs& A, cudaStream_t st) {
+    switch (P.enc) {
+    case 0: return launch_range_carry_0(P, A, st);
+    case 1: return launch_range_carry_1(P, A, st);
+    case 2: return launch_range_carry_2(P, A, st);
+    case 3: return launch_range_carry_3(P, A, st);
+    case 4: return launch_range_carry_4(P, A, st);
+    case 5: return launch_range_carry_5(P, A, st);
+    case 6: return launch_range_carry_6(P, A, st);
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t launch_sparse_enc(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B, const SparseLaunchCfg& L,
+                                     cudaStream_t st, cudaEvent_t* ev, cudaStream_t side, cudaEvent_t* evs) {
+    switch (P.enc) {
+    case 0: return launch_sparse_0(P, O, X, B, L, st, ev, side, evs);
+    case 1: return launch_sparse_1(P, O, X, B, L, st, ev, side, evs);
+    case 4: return launch_sparse_4(P, O, X, B, L, st, ev, side, evs);
+    }
+    return cudaErrorNotSupported;
+}
+static bool has_sparse_enc(uint32_t enc) { return enc == ENC_XUD || enc == ENC_UTF8 || enc == ENC_SB; }
+
+static bool ensure_piece_events(sx_scanner_state* ss, size_t n) {
+    while (ss->pev.size() < n) {
+        PieceEvents e;
+        bool ok = cuda_ok(cudaEventCreate(&e.p0), "cudaEventCreate") && cuda_ok(cudaEventCreate(&e.p1), "cudaEventCreate") &&
+                  cuda_ok(cudaEventCreate(&e.b0), "cudaEventCreate") && cuda_ok(cudaEventCreate(&e.b1), "cudaEventCreate");
+        for (int i = 0; ok && i < 7; ++i) ok = cuda_ok(cudaEventCreate(&e.sev[i]), "cudaEventCreate");
+        for (int i = 0; ok && i < 2; ++i) ok = cuda_ok(cudaEventCreateWithFlags(&e.sord[i], cudaEventDisableTiming), "cudaEventCreate");
+        ok = ok && cuda_ok(cudaEventCreateWithFlags(&e.sc, cudaEventDisableTiming), "cudaEventCreate");
+        for (int i = 0; ok && i < kGatherParts; ++i) ok = cuda_ok(cudaEventCreateWithFlags(&e.gp[i], cudaEventDisableTiming), "cudaEventCreate");
+        ss->pev.push_back(e);
+        if (!ok) return false;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sparse pipeline over the call's window range, cut into pieces: the prefilter of piece k + 1 streams (stream sA) while
+// the exact stage of piece k resolves (sB) and the findings of piece k - 1 travel to the host (copy engine, sC).
+// Returns 1 on success, 0 on error (sx_last_error set).
+// ---------------------------------------------------------------------------------------------
+static int run_sparse(CallCtx& c) {
+    const int fail = 0;
+    sx_scanner_state* const ss = c.ss;
+    sx_finding_collection* const fc = c.fc;
+    const ScanParams& P = c.P;
+    const long long nwin = c.w_hi - c.w_lo;
+    const long long tile_lo = c.w_lo / kPrefTileWin, tile_hi = (c.w_hi + kPrefTileWin - 1) / kPrefTileWin;
+    const long long ntiles = tile_hi - tile_lo;
+    // ---- piece plan -------------------------------------------------------------------------------
+    int K = ss->pieces;
+    if (const char* ev = getenv("SX_PIECES")) K = atoi(ev);
+    // Measured on B200 (profiles/r02_pieces.txt): the exact stage of a piece is a chain of latency-bound kernels (~0.25 ms
+    // whatever the piece size) and slows the prefilter down by 40 % while it runs beside it, so one piece -- prefilter,
+    // then the exact stage on the whole machine, the download overlapped part by part with the gather -- is fastest.
+    if (K <= 0) K = 1;
+    if (K > kMaxPieces) K = kMaxPieces;
+    if ((long long)K > ntiles) K = (int)std::max<long long>(1, ntiles);
+    std::vector<long long> pt(K + 1);  // tile boundaries of the pieces
+    {
+        // equal pieces except the last two, which shrink (1/2, 1/4 of a regular piece): what cannot be overlapped with
+        // the next piece's prefilter is the exact stage and the download of the LAST piece
+        std::vector<double> wgt(K, 1.0);
+        if (K >= 4 && !getenv("SX_PIECES_EQUAL")) { wgt[K - 2] = 0.5; wgt[K - 1] = 0.25; }
+        double tot = 0;
+        for (double x : wgt) tot += x;
+        double acc = 0;
+        pt[0] = tile_lo;
+        for (int k = 0; k < K; ++k) {
+            acc += wgt[k];
+            pt[k + 1] = k + 1 == K ? tile_hi : tile_lo + (long long)((double)ntiles * acc / tot);
+        }
+        // every piece holds at least one tile (K <= ntiles)
+        for (int k = 1; k < K; ++k) pt[k] = std::max(pt[k], pt[k - 1] + 1);
+        for (int k = K - 1; k >= 1; --k) pt[k] = std::min(pt[k], pt[k + 1] - 1);
+    }
+    struct Piece { long long w0, w1, t0, t1; unsigned long long cap, ebase, cbase; int pgrid; long long tpc; };
+    std::vector<Piece> pcs(K);
+    std::vector<unsigned long long> want_cap(K, 0);  // after an overflow: the counted entries
+    std::vector<uint32_t> gparts(K, 1);
+    if (!ensure_piece_events(ss, (size_t)K)) return fail;
+    {   // same shared-memory carve-out as the prefilter, so that these kernels can share SMs with it (sx_sparse_utf8.cuh)
+        static thread_local int done_dev = -1;
+        if (done_dev != ss->device) {
+            cudaFuncSetAttribute(sx_list_compact_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(sx_sp_tables_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(sx_materialize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            done_dev = ss->device;
+        }
+    }
+    if (!grow(&ss->d_ccount, &ss->ccount_cap, (size_t)kMaxPieces * kMaxPrefCtas)) return fail;
+    if (!grow(&ss->d_list, &ss->list_cap, (size_t)(c.total_windows + 2 * kPrefTileWin))) return fail;
+    if (!grow(&ss->d_tables, &ss->tables_cap, sizeof(Utf8Tables))) return fail;
+
+    size_t need_recs = (size_t)((double)(nwin * P.W) * ss->rec_per_byte) + 4096;
+    size_t need_text = (size_t)((double)(nwin * P.W) * ss->text_per_byte) + 65536;
+    size_t need_recs_min = 0, need_text_min = 0;
+    HostCtl* const hc = ss->h_ctl;
+    int pgrid_max = ss->num_sms * 3;
+    if (const char* ev = getenv("SX_PREF_GRID")) { const int g = atoi(ev); if (g > 0) pgrid_max = g; }
+    pgrid_max = std::min(pgrid_max, kMaxPrefCtas);
+
+    for (int attempt = 0;; ++attempt) {
+        // ---- capacities -----------------------------------------------------------------------------
+        unsigned long long etot = 0, ctot = 0;
+        for (int k = 0; k < K; ++k) {
+            Piece& p = pcs[k];
+            p.t0 = pt[k]; p.t1 = pt[k + 1];
+            p.w0 = std::max<long long>(c.w_lo, p.t0 * kPrefTileWin);
+            p.w1 = std::min<long long>(c.w_hi, p.t1 * kPrefTileWin);
+            const unsigned long long wins = (unsigned long long)(p.w1 - p.w0);
+            unsigned long long cap = wins;
+            if (nwin > (256ll << 10)) cap = std::min<unsigned long long>(wins, (unsigned long long)((double)wins * ss->listed_frac * 1.5) + 16384);
+            if (want_cap[k]) cap = std::min<unsigned long long>(wins, want_cap[k] + 1024);
+            p.cap = cap; p.ebase = etot; p.cbase = ctot;
+            etot += cap;
+            ctot += (cap + kSpThreads - 1) / kSpThreads + 1;
+            const long long nt = p.t1 - p.t0;
+            int g = (int)std::min<long long>(nt, pgrid_max);
+            p.tpc = (nt + g - 1) / g;
+            p.pgrid = (int)((nt + p.tpc - 1) / p.tpc);
+        }
+        const size_t entry_bytes = sizeof(EntryHot) + sizeof(Carry) + 2 * kBufRecs * sizeof(Record);
+        if (!grow(&ss->d_entries, &ss->entries_cap, (size_t)etot * entry_bytes + 256, etot * entry_bytes <= (24ull << 30))) return fail;
+        if (!grow(&ss->d_btot, &ss->btot_cap, (size_t)(ctot + 1) * sizeof(ulonglong2))) return fail;
+        if (!grow(&ss->d_queue, &ss->queue_cap, (size_t)(2 * etot + 64 * K + 128))) return fail;
+        if (!grow(&ss->d_clist, &ss->clist_cap, (size_t)etot + 64)) return fail;
+        if (!grow(&ss->d_recs, &ss->rec_cap, need_recs)) return fail;
+        if (!grow(&ss->d_text, &ss->text_cap, need_text)) return fail;
+        EntryHot* const d_hot = reinterpret_cast<EntryHot*>(ss->d_entries);
+        Carry* const d_dnull = reinterpret_cast<Carry*>(ss->d_entries + (size_t)etot * sizeof(EntryHot));
+        Record* const d_staged = reinterpret_cast<Record*>(ss->d_entries + (size_t)etot * (sizeof(EntryHot) + sizeof(Carry)));
+        Record* const d_xstaged = d_staged + (size_t)etot * kBufRecs;
+        // ---- output set -----------------------------------------------------------------------------
+        unsigned long long out_cap = ~0ull, text_cap = ss->text_cap;
+        if (ss->use_direct) {
+            const double scale = ss->have_history && ss->last_len ? (double)(nwin * P.W) / (double)ss->last_len : 1.0;
+            const size_t guess_f = ss->have_history ? (size_t)(ss->last_nrec * scale) + ss->last_nrec / 16 + 4096 : ss->host_rec_hint;
+            const size_t guess_t = ss->have_history ? (size_t)(ss->last_ntext * scale) + ss->last_ntext / 16 + 65536 : ss->host_text_hint;
+            const size_t want_f = std::min(need_recs, std::max(guess_f, need_recs_min));
+            const size_t want_t = std::min(need_text, std::max(guess_t, need_text_min));
+            if (fc->set.fcap < want_f || fc->set.tcap < want_t) {
+                pinned_release(fc->set);
+                if (!pinned_acquire(want_f, want_t, &fc->set)) { set_err(SX_ERR_CUDA, "cannot pin host memory for the findings"); return fail; }
+            }
+            if (!grow(&ss->d_findings, &ss->findings_cap, fc->set.fcap)) return fail;
+            out_cap = fc->set.fcap;
+            text_cap = std::min<unsigned long long>(text_cap, fc->set.tcap);
+        }
+        // ---- enqueue --------------------------------------------------------------------------------
+        CK(cudaEventRecord(ss->ev_in, c.st));
+        CK(cudaStreamWaitEvent(ss->sA, ss->ev_in, 0));
+        CK(cudaStreamWaitEvent(ss->sB, ss->ev_in, 0));
+        CK(cudaStreamWaitEvent(ss->sC, ss->ev_in, 0));
+        CK(cudaMemsetAsync(ss->d_ctl, 0, sizeof(PieceCtl) * kMaxPieces, ss->sB));
+        memset(hc, 0, sizeof(HostCtl));
+        {
+            RangeCarryArgs ra;
+            memset(&ra, 0, sizeof ra);
+            for (int k = 0; k < K; ++k) ra.w_first[k] = pcs[k].w0;
+            ra.nranges = (uint32_t)K; ra.in_aligned16 = c.in_aligned16 ? 1u : 0u;
+            ra.prefix_known = c.prefix_known ? 1u : 0u; ra.max_back = 1u << 16;
+            ra.out = reinterpret_cast<RangeCarryOut*>(reinterpret_cast<uint8_t*>(ss->d_ctl) + offsetof(PieceCtl, rc));
+            ra.out_stride = sizeof(PieceCtl);
+            CK(launch_range_carry_enc(P, ra, ss->sB));
+            sx_sp_tables_kernel<<<8, 256, 0, ss->sB>>>(P, reinterpret_cast<Utf8Tables*>(ss->d_tables));
+            CK(cudaGetLastError());
+            ss->stats.kernel_launches += 2;
+            CK(cudaEventRecord(ss->ev_setup, ss->sB));
+            for (int i = 0; i < sx_scanner_state::kLanes; ++i) CK(cudaStreamWaitEvent(ss->sBk[i], ss->ev_setup, 0));
+        }
+        const PrefK pk = make_pref_k(P, c.pc);
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof tmap);
+        const uint32_t use_tma = (ss->use_tma && make_tensor_map(&tmap, c.d_in, c.len, kPrefTileWin * P.W)) ? 1u : 0u;
+        ss->stats.tma_used = use_tma;
+        for (int k = 0; k < K; ++k) {
+            const Piece& p = pcs[k];
+            PrefOut po;
+            po.list = ss->d_list; po.cta_count = ss->d_ccount + (size_t)k * kMaxPrefCtas; po.tiles_per_cta = p.tpc;
+            po.tile0 = p.t0; po.tile_end = p.t1; po.w_first = p.w0; po.w_lo = c.w_lo; po.w_hi = c.w_hi;
+            CK(cudaEventRecord(ss->pev[k].p0, ss->sA));
+            CK(launch_prefilter(P, c.pc, pk, po, c.total_windows, p.pgrid, ss->sA, tmap, use_tma));
+            CK(cudaEventRecord(ss->pev[k].p1, ss->sA));
+            ss->stats.kernel_launches++;
+        }
+        const unsigned chunk_grid_max = (unsigned)ss->num_sms * 6u, queue_grid_max = (unsigned)ss->num_sms * 4u;
+        for (int k = 0; k < K; ++k) {
+            const Piece& p = pcs[k];
+            PieceCtl* const ctl = ss->d_ctl + k;
+            cudaStream_t sb = ss->sBk[k % sx_scanner_state::kLanes], sd = ss->sidek[k % sx_scanner_state::kLanes];
+            CK(cudaStreamWaitEvent(sb, ss->pev[k].p1, 0));
+            CK(cudaEventRecord(ss->pev[k].b0, sb));
+            uint32_t* const clist = ss->d_clist + p.ebase;
+            sx_list_compact_kernel<<<p.pgrid, 256, 0, sb>>>(ss->d_ccount + (size_t)k * kMaxPrefCtas, (uint32_t)p.pgrid, ss->d_list, p.t0, p.tpc,
+                                                               clist, ctl, p.cap);
+            CK(cudaGetLastError());
+            ScanOut O{ss->d_recs, ss->rec_cap, text_cap, ss->d_blocks, ss->d_counters, &hc->fin, ss->use_direct ? ss->d_findings : nullptr,
+                      out_cap, ss->use_direct ? fc->set.t : nullptr, c.input_file_id, ss->m.mission_id};
+            ExactCfg X;
+            X.list = clist; X.ne_ptr = &ctl->ne; X.ne_static = 0; X.total_windows = c.total_windows;
+            X.in_aligned16 = c.in_aligned16 ? 1u : 0u; X.pre_bytes = c.pc.pre_bytes; X.cta_off = nullptr; X.ncta = 0; X.region_stride = 0;
+            X.w_first = p.w0; X.w_end = p.w1; X.k0_ptr = &ctl->rc.k0; X.ne_cap = p.cap;
+            SparseBufs B;
+            B.H = d_hot + p.ebase; B.dnull = d_dnull + p.ebase; B.staged = d_staged + p.ebase * kBufRecs; B.xstaged = d_xstaged + p.ebase * kBufRecs;
+            B.btot = reinterpret_cast<ulonglong2*>(ss->d_btot) + p.cbase;
+            B.tables = reinterpret_cast<Utf8Tables*>(ss->d_tables);
+            B.queue = ss->d_queue + 2 * p.ebase + 64 * (size_t)k; B.queue2 = B.queue + p.cap + 32;
+            B.ctl = ctl; B.prev = k ? ctl - 1 : nullptr; B.summary = &hc->piece[k]; B.text_out = ss->d_text;
+            SparseLaunchCfg L;
+            L.grid_chunks = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((p.cap + kSpThreads - 1) / kSpThreads, chunk_grid_max));
+            L.grid_queue = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((p.cap + kSpThreads - 1) / kSpThreads, queue_grid_max));
+            L.rec_cap = ss->rec_cap; L.text_cap = text_cap; L.out_cap = out_cap;
+            L.ev_scan_prev = k ? ss->pev[k - 1].sc : nullptr; L.ev_scan_done = ss->pev[k].sc;
+            // large pieces: the gather runs in parts, the download of a part beside the gathering of the next
+            L.gather_parts = p.cap >= (64u << 10) ? (uint32_t)kGatherParts : 1u;
+            if (const char* evp = getenv("SX_GATHER_PARTS")) L.gather_parts = (uint32_t)std::min(kGatherParts, std::max(1, atoi(evp)));
+            L.ev_part = ss->pev[k].gp;
+            gparts[k] = L.gather_parts;
+            CK(launch_sparse_enc(P, O, X, B, L, sb, ss->pev[k].sev, sd, ss->pev[k].sord));
+            CK(cudaEventRecord(ss->pev[k].b1, sb));
+            ss->stats.kernel_launches += 1 + kSparseLaunches;
+        }
+        if (c.tail_n && c.buf_is_device)
+            CK(cudaMemcpyAsync(hc->tail + 8 - c.tail_n, c.d_in + c.len - c.tail_n, c.tail_n, cudaMemcpyDeviceToHost, ss->sC));
+        ss->stats.host_phase_ms[0] = ms_since(c.t_begin);
+        // ---- per piece: wait for its exact stage, copy its findings and text to the pinned set ---------------
+        bool overflow = false;
+        unsigned long long tot_rec = 0, tot_text = 0, tot_listed = 0;
+        for (int k = 0; k < K; ++k) {
+            CK(cudaEventSynchronize(ss->pev[k].sc));  // the piece's totals are known (its gather may still be running)
+            const PieceSummary s = hc->piece[k];
+            tot_listed += s.ne_raw;
+            if (s.overflow & 0x100u) { set_err(SX_ERR_UNSUPPORTED, "range start: no carry-independent window found (halo too short?)"); cudaDeviceSynchronize(); return fail; }
+            if (s.overflow) overflow = true;
+            if (overflow) { CK(cudaEventSynchronize(ss->pev[k].b1)); continue; }
+            tot_rec = s.rec_base + s.nrec; tot_text = s.text_base + s.ntext;
+            unsigned long long r0 = s.rec_base, t0 = s.text_base;
+            for (uint32_t part = 0; part < gparts[k]; ++part) {
+                CK(cudaEventSynchronize(ss->pev[k].gp[part]));
+                const unsigned long long r1 = part + 1 == gparts[k] ? s.rec_base + s.nrec : s.part_rec_end[part];
+                const unsigned long long t1 = part + 1 == gparts[k] ? s.text_base + s.ntext : s.part_text_end[part];
+                if (hc->piece[k].text_fallback && r1 > r0) {
+                    const int mgrid = (int)std::min<size_t>((size_t)(r1 - r0 + 255) / 256, (size_t)ss->num_sms * 8);
+                    sx_materialize_kernel<<<mgrid, 256, 0, ss->sC>>>(P, ss->d_recs + r0, r1 - r0, ss->d_text, ss->text_cap);
+                    CK(cudaGetLastError());
+                    ss->stats.kernel_launches++;
+                }
+                if (ss->use_direct) {
+                    if (r1 > r0) CK(cudaMemcpyAsync(fc->set.f + r0, ss->d_findings + r0, (size_t)(r1 - r0) * sizeof(sx_finding), cudaMemcpyDeviceToHost, ss->sC));
+                    if (t1 > t0) CK(cudaMemcpyAsync(fc->set.t + t0, ss->d_text + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ss->sC));
+                    ss->stats.d2h_bytes += (r1 - r0) * sizeof(sx_finding) + (t1 - t0);
+                }
+                r0 = r1; t0 = t1;
+            }
+        }
+        ss->stats.host_phase_ms[1] = ms_since(c.t_begin);
+        CK(cudaStreamSynchronize(ss->sC));
+        CK(cudaStreamSynchronize(ss->sA));
+        for (int i = 0; i < sx_scanner_state::kLanes; ++i) { CK(cudaStreamSynchronize(ss->sBk[i])); CK(cudaStreamSynchronize(ss->sidek[i])); }
+        if (!overflow) {
+            c.nrec = (size_t)tot_rec; c.ntext = (size_t)tot_text; c.windows_listed = tot_listed;
+            break;
+        }
+        if (attempt >= 3) { set_err(SX_ERR_CUDA, "output buffers still too small after regrowing"); return fail; }
+        // what the device counted: entries per piece, records / text of the pieces that got that far
+        unsigned long long cr = 0, ctx = 0;
+        bool entries_ok = true;
+        for (int k = 0; k < K; ++k) {
+            const PieceSummary s = hc->piece[k];
+            want_cap[k] = s.ne_raw;
+            if (s.overflow & 1u) entries_ok = false;
+            cr = std::max(cr, s.rec_base + s.nrec); ctx = std::max(ctx, s.text_base + s.ntext);
+        }
+        if (entries_ok) { need_recs = (size_t)cr + 1024; need_text = (size_t)ctx + 4096; }
+        else { need_recs = std::max(need_recs, (size_t)cr * 2 + 1024); need_text = std::max(need_text, (size_t)ctx * 2 + 4096); }
+        need_recs_min = need_recs; need_text_min = need_text;
+        ss->stats.relaunches++;
+    }
+    // ---- stats ---------------------------------------------------------------------------------------
+    {
+        float pre = 0, ex = 0, stage[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < K; ++k) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ss->pev[k].p0, ss->pev[k].p1) == cudaSuccess) pre += ms;
+            if (cudaEventElapsedTime(&ms, ss->pev[k].b0, ss->pev[k].b1) == cudaSuccess) ex += ms;
+            if (cudaEventElapsedTime(&ms, ss->pev[k].b0, ss->pev[k].sev[1]) == cudaSuccess) stage[0] += ms;  // compact
+            for (int i = 1; i < 6; ++i)
+                if (cudaEventElapsedTime(&ms, ss->pev[k].sev[i], ss->pev[k].sev[i + 1]) == cudaSuccess) stage[i] += ms;
+        }
+        cudaGetLastError();
+        ss->stats.prefilter_kernel_ms = pre;
+        ss->stats.exact_kernel_ms = ex;
+        for (int i = 0; i < 6; ++i) ss->stats.sparse_stage_ms[i] = stage[i];
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ss->pev[0].p0, ss->pev[K - 1].b1) == cudaSuccess) ss->stats.scan_kernel_ms = ms;
+        cudaGetLastError();
+        ss->stats.pieces = (uint32_t)K;
+    }
+    ss->stats.sparse_used = 1;
+    ss->stats.prefilter_used = 1;
+    ss->listed_frac = std::max(1.0 / 4096, (double)c.windows_listed / (double)std::max<long long>(1, nwin));
+    ss->last_list_compact = true; ss->last_list_len = (size_t)c.windows_listed;
+    ss->last_piece_lists.clear();
+    for (int k = 0; k < K; ++k) ss->last_piece_lists.emplace_back((size_t)pcs[k].ebase, (size_t)hc->piece[k].ne_raw);
+    c.fin = hc->fin;
+    if (c.tail_n && c.buf_is_device) memcpy(c.tail + 8 - c.tail_n, hc->tail + 8 - c.tail_n, c.tail_n);
+    c.direct_out = ss->use_direct != 0;
+    c.records_in_order = true;
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-kernel path (UTF-16 / UTF-32, general missions, prefilter off): one prefilter launch over the range, the
+// persistent block kernel over its list, records ordered on the device afterwards.  Everything on the caller's stream.
+// ---------------------------------------------------------------------------------------------
+static int run_block(CallCtx& c) {
+    const int fail = 0;
+    sx_scanner_state* const ss = c.ss;
+    sx_finding_collection* const fc = c.fc;
+    const ScanParams& P = c.P;
+    const PrefCfg& pc = c.pc;
+    cudaStream_t st = c.st;
+    const long long nwin = c.w_hi - c.w_lo;
+    const long long tile_lo = c.w_lo / kPrefTileWin, tile_hi = (c.w_hi + kPrefTileWin - 1) / kPrefTileWin;
+    const long long ntiles = tile_hi - tile_lo;
+    const long long max_blocks = (nwin + kThreads - 1) / kThreads;
+    if (!grow(&ss->d_blocks, &ss->blocks_cap, (size_t)max_blocks + 1)) return fail;
+    if (pc.enabled) {
+        if (!grow(&ss->d_ccount, &ss->ccount_cap, (size_t)kMaxPieces * kMaxPrefCtas)) return fail;
+        if (!grow(&ss->d_coff, &ss->coff_cap, (size_t)kMaxPrefCtas + 8)) return fail;
+        if (!grow(&ss->d_list, &ss->list_cap, (size_t)(c.total_windows + 2 * kPrefTileWin))) return fail;
+    }
+    size_t need_recs = (size_t)((double)(nwin * P.W) * ss->rec_per_byte) + 4096;
+    size_t need_text = (size_t)((double)(nwin * P.W) * ss->text_per_byte) + 65536;
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    FinalState fin;
+    HostCtl* const hc = ss->h_ctl;
+    for (int attempt = 0;; ++attempt) {
+        if (!grow(&ss->d_recs, &ss->rec_cap, need_recs)) return fail;
+        if (!grow(&ss->d_text, &ss->text_cap, need_text)) return fail;
+        CK(cudaMemsetAsync(ss->d_counters, 0, 8 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ss->d_final, 0, sizeof(FinalState), st));
+        ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, nullptr, 0, nullptr,
+                  c.input_file_id, ss->m.mission_id};
+        ExactCfg X;
+        X.total_windows = c.total_windows;
+        X.in_aligned16 = c.in_aligned16 ? 1u : 0u;
+        X.pre_bytes = pc.pre_bytes;
+        X.w_first = c.w_lo; X.w_end = c.w_hi; X.k0_ptr = nullptr; X.ne_cap = 0;
+        if (c.w_lo > 0) {
+            // the carry into the range's first window
+            CK(cudaMemsetAsync(ss->d_ctl, 0, sizeof(PieceCtl), st));
+            RangeCarryArgs ra;
+            memset(&ra, 0, sizeof ra);
+            ra.w_first[0] = c.w_lo;
+            ra.nranges = 1; ra.in_aligned16 = X.in_aligned16; ra.prefix_known = c.prefix_known ? 1u : 0u;
+            ra.max_back = 1u << 16;
+            ra.out = reinterpret_cast<RangeCarryOut*>(reinterpret_cast<uint8_t*>(ss->d_ctl) + offsetof(PieceCtl, rc));
+            ra.out_stride = sizeof(PieceCtl);
+            CK(launch_range_carry_enc(P, ra, st));
+            ss->stats.kernel_launches++;
+            X.k0_ptr = &ss->d_ctl->rc.k0;
+        }
+        CK(cudaEventRecord(ss->ev[0], st));
+        if (pc.enabled) {
+            const PrefK pk = make_pref_k(P, pc);
+            int pgrid = (int)std::min<long long>(ntiles, std::min<long long>(kMaxPrefCtas, (long long)ss->num_sms * 3));
+            const long long tiles_per_cta = (ntiles + pgrid - 1) / pgrid;
+            pgrid = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
+            PrefOut po;
+            po.list = ss->d_list; po.cta_count = ss->d_ccount; po.tiles_per_cta = tiles_per_cta;
+            po.tile0 = tile_lo; po.tile_end = tile_hi; po.w_first = c.w_lo; po.w_lo = c.w_lo; po.w_hi = c.w_hi;
+            CUtensorMap tmap;
+            memset(&tmap, 0, sizeof tmap);
+            const uint32_t use_tma = (ss->use_tma && make_tensor_map(&tmap, c.d_in, c.len, kPrefTileWin * P.W)) ? 1u : 0u;
+            ss->stats.tma_used = use_tma;
+            CK(launch_prefilter(P, pc, pk, po, c.total_windows, pgrid, st, tmap, use_tma));
+            CK(cudaEventRecord(ss->ev[4], st));
+            sx_list_offsets_kernel<<<1, 1024, 0, st>>>(ss->d_ccount, ss->d_coff, (uint32_t)pgrid, ss->d_counters);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ss->ev[5], st));
+            ss->stats.kernel_launches += 2;
+            X.list = ss->d_list + (size_t)tile_lo * kPrefTileWin;
+            X.ne_ptr = ss->d_counters + 2;
+            X.ne_static = 0;
+            X.cta_off = ss->d_coff;
+            X.ncta = (uint32_t)pgrid;
+            X.region_stride = (unsigned long long)tiles_per_cta * kPrefTileWin;
+            ss->last_ncta = (uint32_t)pgrid; ss->last_region_stride = (size_t)X.region_stride;
+            ss->last_list_compact = false; ss->last_list_base = X.list;
+        } else {
+            CK(cudaEventRecord(ss->ev[4], st));
+            CK(cudaEventRecord(ss->ev[5], st));
+            X.list = nullptr;
+            X.ne_ptr = nullptr;
+            X.ne_static = nwin;
+            X.cta_off = nullptr;
+            X.ncta = 0;
+            X.region_stride = 0;
+        }
+        const unsigned xgrid = (unsigned)std::max<long long>(1, std::min<long long>(max_blocks, (long long)ss->num_sms * 4));
+        CK(launch_exact_enc(P, O, X, xgrid, st));
+        ss->stats.kernel_launches++;
+        CK(cudaEventRecord(ss->ev[1], st));
+        ss->stats.host_phase_ms[0] = ms_since(c.t_begin);
+        if (c.tail_n && c.buf_is_device) CK(cudaMemcpyAsync(c.tail + 8 - c.tail_n, c.d_in + c.len - c.tail_n, c.tail_n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(counters, ss->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&fin, ss->d_final, sizeof fin, cudaMemcpyDeviceToHost, st));
+        if (c.w_lo > 0) CK(cudaMemcpyAsync(&hc->piece[0].overflow, &ss->d_ctl->rc.fail, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ss->stats.d2h_bytes += sizeof counters + sizeof fin;
+        if (c.w_lo > 0 && hc->piece[0].overflow) { set_err(SX_ERR_UNSUPPORTED, "range start: no carry-independent window found (halo too short?)"); return fail; }
+        if (!fin.overflow && counters[0] <= ss->rec_cap && counters[1] <= ss->text_cap) break;
+        if (attempt >= 2) { set_err(SX_ERR_CUDA, "output buffers still too small after regrowing"); return fail; }
+        need_recs = (size_t)counters[0] + 1024;
+        need_text = (size_t)counters[1] + 4096;
+        ss->stats.relaunches++;
+    }
+    if (!pc.enabled) counters[2] = (unsigned long long)nwin;
+    ss->stats.host_phase_ms[1] = ms_since(c.t_begin);
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ss->ev[0], ss->ev[4]);
+        ss->stats.prefilter_kernel_ms = pc.enabled ? ms : 0.f;
+        cudaEventElapsedTime(&ms, ss->ev[4], ss->ev[5]);
+        ss->stats.list_kernels_ms = pc.enabled ? ms : 0.f;
+        cudaEventElapsedTime(&ms, ss->ev[5], ss->ev[1]);
+        ss->stats.exact_kernel_ms = ms;
+        cudaEventElapsedTime(&ms, ss->ev[0], ss->ev[1]);
+        ss->stats.scan_kernel_ms = ms;
+        ss->stats.prefilter_used = pc.enabled;
+        ss->stats.pieces = 1;
+    }
+    c.nrec = (size_t)counters[0];
+    c.ntext = (size_t)counters[1];
+    c.windows_listed = counters[2];
+    ss->last_list_len = (size_t)counters[2];
+    c.fin = fin;
+    c.direct_out = false;
+    c.records_in_order = false;
+    const size_t nrec = c.nrec, ntext = c.ntext;
+    if (nrec > 0 && ss->use_direct) {
+        // order the records on the device and write them as findings into a pinned set; the text follows (transcoded on
+        // the device, one copy to the address the findings already point to)
+        const size_t nblocks = (size_t)((counters[2] + kThreads - 1) / kThreads);
+        pinned_release(fc->set);
+        if (pinned_acquire(nrec, ntext, &fc->set) && grow(&ss->d_bpos, &ss->bpos_cap, nblocks + 1)) {
+            ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, fc->set.f, fc->set.fcap, fc->set.t,
+                      c.input_file_id, ss->m.mission_id};
+            sx_order_scan_kernel<<<1, 1024, 0, st>>>(ss->d_blocks, ss->d_bpos, nblocks);
+            const unsigned wgrid = (unsigned)std::min<size_t>((nblocks + 7) / 8, (size_t)ss->num_sms * 8);
+            sx_order_write_kernel<<<wgrid, 256, 0, st>>>(O, ss->d_blocks, ss->d_bpos, nblocks, nrec);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&c.fin, ss->d_final, sizeof c.fin, cudaMemcpyDeviceToHost, st));  // first / last record flags
+            const int mgrid = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ss->num_sms * 8);
+            CK(cudaEventRecord(ss->ev[2], st));
+            sx_materialize_kernel<<<mgrid, 256, 0, st>>>(P, ss->d_recs, nrec, ss->d_text, ss->text_cap);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ss->ev[3], st));
+            ss->stats.kernel_launches += 3;
+            if (ntext) CK(cudaMemcpyAsync(fc->set.t, ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
+            ss->stats.d2h_bytes += nrec * sizeof(sx_finding) + ntext;
+            CK(cudaStreamSynchronize(st));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ss->ev[2], ss->ev[3]);
+            ss->stats.materialize_kernel_ms = ms;
+            c.direct_out = true;
+        } else {
+            cudaGetLastError();
+            pinned_release(fc->set);
+        }
+    }
+    return 1;
+}
+
+static sx_finding_collection* scan_impl(sx_scanner_state* ss, int input_file_id, const void* buf, size_t len, size_t slice_len,
+                                        int buf_is_device, int is_last, size_t lo, size_t hi, int prefix_unknown, void* cuda_stream) {
     sx_finding_collection* const fail = nullptr;
     if (!ss) { set_err(SX_ERR_ARGUMENT, "state is NULL"); return fail; }
     if (len > 0 && !buf) { set_err(SX_ERR_ARGUMENT, "buf is NULL"); return fail; }
     const uint32_t q = ss->m.output_line_char_nb_max;
     const uint32_t W = 2 * q;
     if (slice_len == 0 || slice_len > 0x7FFFFFFFull) { set_err(SX_ERR_ARGUMENT, "slice_len must be in 1..2^31-1"); return fail; }
+    if (lo > hi || hi > len || (lo % slice_len) != 0 || (hi != len && (hi % slice_len) != 0)) {
+        set_err(SX_ERR_ARGUMENT, "range must satisfy lo <= hi <= len with lo and hi multiples of slice_len (or hi == len)");
+        return fail;
+    }
+    if (prefix_unknown && lo == 0 && len > 0) { set_err(SX_ERR_ARGUMENT, "SX_RANGE_PREFIX_UNKNOWN needs a halo in front of the range (lo > 0)"); return fail; }
     const uint32_t wps = (uint32_t)((slice_len + W - 1) / W);
     memset(&ss->stats, 0, sizeof ss->stats);
-    const auto t_begin = std::chrono::steady_clock::now();
+    CallCtx c;
+    c.t_begin = std::chrono::steady_clock::now();
     sx_finding_collection* fc = new sx_finding_collection();
-    fc->first_byte_position = ss->consumed;
-    if (len == 0) return fc;  // finding_collection.rs:124: the window loop does not run, state untouched
+    fc->first_byte_position = ss->consumed + lo;
+    if (len == 0 || lo == hi) return fc;  // finding_collection.rs:124: the window loop does not run, state untouched
     struct Guard { sx_finding_collection* p; ~Guard() { delete p; } } guard{fc};
 
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } dev_restore{prev_dev};  // the caller's current device is left as it was
     CK(cudaSetDevice(ss->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
 
@@ -1157,7 +1742,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     }
 
     // ---- parameters ------------------------------------------------------------------------------
-    ScanParams P;
+    ScanParams& P = c.P;
     memset(&P, 0, sizeof P);
     P.in = d_in;
     P.len = (int64_t)len;
@@ -1200,234 +1785,45 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     }
     if (total_windows > 0x7FFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
-    PrefCfg pc = make_pref_cfg(P, in_aligned16);
+    c.pc = make_pref_cfg(P, in_aligned16);
     // General missions: an unlisted window's carry-out must not depend on its carry-in.  --grep-char alone gets there with
     // one more listing rule (PrefCfg::kill_trail, sx_core.cuh); under --same-unicode-block a stale lead byte survives
     // ASCII junk (helper.rs:327-330) and n > q drops whole segments: those run without the prefilter.  DESIGN.md 7.
-    if (!ss->use_prefilter || (P.general && !pref_general_ok(P))) pc.enabled = 0;
-    const long long ntiles = (total_windows + kPrefTileWin - 1) / kPrefTileWin;
-    const long long max_blocks = (total_windows + kThreads - 1) / kThreads;
-
-    if (!grow(&ss->d_blocks, &ss->blocks_cap, (size_t)max_blocks)) return fail;
-    if (pc.enabled) {
-        if (!grow(&ss->d_ccount, &ss->ccount_cap, (size_t)1024)) return fail;
-        if (!grow(&ss->d_coff, &ss->coff_cap, (size_t)1032)) return fail;
-        if (!grow(&ss->d_list, &ss->list_cap, (size_t)ntiles * kPrefTileWin)) return fail;
-    }
-    size_t need_recs = (size_t)(len * ss->rec_per_byte) + 4096;
-    size_t need_text = (size_t)(len * ss->text_per_byte) + 65536;
-    size_t need_recs_min = 0, need_text_min = 0;  // after an overflow: what the device counted
-    unsigned long long counters[4] = {0, 0, 0, 0};
-    FinalState fin;
+    if (!ss->use_prefilter || (P.general && !pref_general_ok(P))) c.pc.enabled = 0;
+    c.ss = ss; c.fc = fc; c.input_file_id = input_file_id; c.d_in = d_in; c.len = len; c.st = st;
+    c.total_windows = total_windows;
+    c.w_lo = (long long)(lo / slice_len) * wps;
+    c.w_hi = hi == len ? total_windows : (long long)(hi / slice_len) * wps;
+    c.in_aligned16 = in_aligned16;
+    c.prefix_known = !prefix_unknown;
+    c.buf_is_device = buf_is_device != 0;
+    const bool tail = hi == len;  // the range reaches the end of the buffer: the ScannerState moves on
     // bytes that stay inside the decoder: the last npend bytes of (old pend ++ buffer)
-    uint8_t tail[8] = {0};
-    const size_t tail_n = std::min<size_t>(8, len);
-    if (!buf_is_device) memcpy(tail + 8 - tail_n, (const uint8_t*)buf + len - tail_n, tail_n);
-    for (int attempt = 0;; ++attempt) {
-        if (!grow(&ss->d_recs, &ss->rec_cap, need_recs)) return fail;
-        if (!grow(&ss->d_text, &ss->text_cap, need_text)) return fail;
-        CK(cudaMemsetAsync(ss->d_counters, 0, 8 * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(ss->d_final, 0, sizeof(FinalState), st));
-        ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, nullptr, 0, nullptr,
-                  input_file_id, ss->m.mission_id};
-        ExactCfg X;
-        X.total_windows = total_windows;
-        X.in_aligned16 = in_aligned16 ? 1u : 0u;
-        X.pre_bytes = pc.pre_bytes;
-        CK(cudaEventRecord(ss->ev[0], st));
-        if (pc.enabled) {
-            const PrefK pk = make_pref_k(P, pc);
-            int pgrid = (int)std::min<long long>(ntiles, std::min<long long>(1024, (long long)ss->num_sms * 3));
-            if (const char* ev = getenv("SX_PREF_GRID")) { const int g = atoi(ev); if (g > 0) pgrid = (int)std::min<long long>(ntiles, std::min(1024, g)); }
-            const long long tiles_per_cta = (ntiles + pgrid - 1) / pgrid;
-            pgrid = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
-            const PrefOut po{ss->d_list, ss->d_ccount, tiles_per_cta};
-            CUtensorMap tmap;
-            memset(&tmap, 0, sizeof tmap);
-            const uint32_t use_tma = (ss->use_tma && make_tensor_map(&tmap, d_in, len, kPrefTileWin * W)) ? 1u : 0u;
-            ss->stats.tma_used = use_tma;
-            CK(launch_prefilter(P, pc, pk, po, total_windows, ntiles, pgrid, st, tmap, use_tma));
-            CK(cudaEventRecord(ss->ev[4], st));
-            sx_list_offsets_kernel<<<1, 1024, 0, st>>>(ss->d_ccount, ss->d_coff, (uint32_t)pgrid, ss->d_counters);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(ss->ev[5], st));
-            ss->stats.kernel_launches += 2;
-            X.list = ss->d_list;
-            X.ne_ptr = ss->d_counters + 2;
-            X.ne_static = 0;
-            X.cta_off = ss->d_coff;
-            X.ncta = (uint32_t)pgrid;
-            X.region_stride = (unsigned long long)tiles_per_cta * kPrefTileWin;
-            ss->last_ncta = (uint32_t)pgrid; ss->last_region_stride = (size_t)X.region_stride;
-        } else {
-            CK(cudaEventRecord(ss->ev[4], st));
-            CK(cudaEventRecord(ss->ev[5], st));
-            X.list = nullptr;
-            X.ne_ptr = nullptr;
-            X.ne_static = total_windows;
-            X.cta_off = nullptr;
-            X.ncta = 0;
-            X.region_stride = 0;
-        }
-        // A sparse list of a UTF-8 mission takes the barrier-free pipeline (sx_sparse_utf8.cuh); it needs the entry
-        // count on the host (one small round trip), everything else the block kernel with its run classification.
-        bool sparse = false;
-        const bool has_mask_engine = P.enc == ENC_UTF8 || P.enc == ENC_XUD || P.enc == ENC_SB;
-        if (pc.enabled && ss->use_sparse && has_mask_engine && !P.general) {
-            unsigned long long ne = 0;
-            CK(cudaMemcpyAsync(&ne, ss->d_counters + 2, sizeof ne, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            ss->stats.d2h_bytes += sizeof ne;
-            // whenever the per-entry state (240 B per listed window) can be allocated: up to 24 GiB without asking, beyond
-            // that (more than ~12 GiB of text-like input in one call) only while 16 GiB of the device stay free for the
-            // other buffers; else the block kernel
-            const size_t nb = (size_t)((ne + sparse_threads() - 1) / sparse_threads());
-            const unsigned long long state_bytes = ne * (unsigned long long)sparse_entry_bytes();
-            bool fits_mem = state_bytes <= (24ull << 30);
-            if (!fits_mem) {
-                size_t free_b = 0, total_b = 0;
-                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-                    const unsigned long long avail = (unsigned long long)free_b + ss->entries_cap;
-                    fits_mem = avail > (16ull << 30) && state_bytes <= avail - (16ull << 30);
-                } else {
-                    cudaGetLastError();
-                }
-            }
-            if (ne > 0 && fits_mem) {
-                fits_mem = grow(&ss->d_entries, &ss->entries_cap, (size_t)state_bytes, state_bytes <= (24ull << 30)) &&
-                           grow(&ss->d_btot, &ss->btot_cap, (nb + 1) * sizeof(ulonglong2)) &&
-                           grow(&ss->d_tables, &ss->tables_cap, sparse_tables_bytes()) &&
-                           grow(&ss->d_queue, &ss->queue_cap, (2 * (size_t)ne + 128) * sizeof(uint32_t));
-                if (!fits_mem) { cudaGetLastError(); set_err(SX_OK, ""); }  // out of device memory: the block kernel needs far less
-            }
-            if (ne > 0 && fits_mem) {
-                // direct host output: the gather kernel writes the findings in their C-ABI form into a pinned set
-                // pinned set: sized from the previous scan of this state scaled to this call's length (+ 1/16, an overflow
-                // reruns the exact stage with the counted sizes); a first scan starts from a modest guess
-                const double scale = ss->have_history && ss->last_len ? (double)len / (double)ss->last_len : 1.0;
-                const size_t guess_f = ss->have_history ? (size_t)(ss->last_nrec * scale) + ss->last_nrec / 16 + 4096 : ss->host_rec_hint;
-                const size_t guess_t = ss->have_history ? (size_t)(ss->last_ntext * scale) + ss->last_ntext / 16 + 65536 : ss->host_text_hint;
-                const size_t want_f = !ss->use_direct ? 0 : std::min(need_recs, std::max(guess_f, need_recs_min));
-                const size_t want_t = std::min(need_text, std::max(guess_t, need_text_min));
-                if (ss->use_direct) {
-                    if (fc->set.fcap < want_f || fc->set.tcap < want_t) {
-                        pinned_release(fc->set);
-                        if (!pinned_acquire(want_f, want_t, &fc->set)) { set_err(SX_ERR_CUDA, "cannot pin host memory for the findings"); return fail; }
-                    }
-                    O.host_findings = fc->set.f;
-                    O.host_cap = fc->set.fcap;
-                    O.host_text = fc->set.t;
-                    O.text_cap = std::min<unsigned long long>(O.text_cap, fc->set.tcap);
-                }
-                const auto launch = P.enc == ENC_UTF8 ? launch_sparse_utf8 : P.enc == ENC_XUD ? launch_sparse_xud : launch_sparse_sb;
-                CK(launch(P, O, X, ss->d_entries, ss->d_btot, ss->d_tables, ss->d_queue, (long long)ne, ss->num_sms, st, ss->sev, ss->side, ss->sord));
-                ss->stats.kernel_launches += sparse_launches();
-                sparse = true;
-            }
-        }
-        ss->stats.sparse_used = sparse ? 1u : 0u;
-        if (!sparse) {
-            const unsigned xgrid = (unsigned)std::min<long long>(max_blocks, (long long)ss->num_sms * 4);
-            CK(launch_exact_enc(P, O, X, xgrid, st));
-            ss->stats.kernel_launches++;
-        }
-        CK(cudaEventRecord(ss->ev[1], st));
-        ss->stats.host_phase_ms[0] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-        if (buf_is_device) CK(cudaMemcpyAsync(tail + 8 - tail_n, d_in + len - tail_n, tail_n, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(counters, ss->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&fin, ss->d_final, sizeof fin, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        ss->stats.d2h_bytes += sizeof counters + sizeof fin;
-        if (!fin.overflow && counters[0] <= ss->rec_cap && counters[1] <= ss->text_cap &&
-            (!fc->set.f || !ss->stats.sparse_used || (counters[0] <= fc->set.fcap && counters[1] <= fc->set.tcap))) break;
-        if (attempt >= 2) { set_err(SX_ERR_CUDA, "output buffers still too small after regrowing"); return fail; }
-        need_recs = (size_t)counters[0] + 1024;
-        need_text = (size_t)counters[1] + 4096;
-        need_recs_min = need_recs;
-        need_text_min = need_text;
-        ss->stats.relaunches++;
-    }
-    if (!pc.enabled) counters[2] = (unsigned long long)total_windows;
-    ss->stats.host_phase_ms[1] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ss->ev[0], ss->ev[4]);
-        ss->stats.prefilter_kernel_ms = pc.enabled ? ms : 0.f;
-        cudaEventElapsedTime(&ms, ss->ev[4], ss->ev[5]);
-        ss->stats.list_kernels_ms = pc.enabled ? ms : 0.f;
-        cudaEventElapsedTime(&ms, ss->ev[5], ss->ev[1]);
-        ss->stats.exact_kernel_ms = ms;
-        for (int i = 0; i < 6; ++i) {
-            ss->stats.sparse_stage_ms[i] = 0.f;
-            if (ss->stats.sparse_used) cudaEventElapsedTime(&ss->stats.sparse_stage_ms[i], ss->sev[i], ss->sev[i + 1]);
-        }
-        ss->stats.windows_total = (uint64_t)total_windows;
-        ss->stats.windows_listed = counters[2];
-        ss->stats.prefilter_used = pc.enabled;
-    }
-    {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ss->ev[0], ss->ev[1]);
-        ss->stats.scan_kernel_ms = ms;
-    }
-    const size_t nrec = (size_t)counters[0];
-    const size_t ntext = (size_t)counters[1];
+    c.tail_n = tail ? std::min<size_t>(8, len) : 0;
+    if (!buf_is_device && c.tail_n) memcpy(c.tail + 8 - c.tail_n, (const uint8_t*)buf + len - c.tail_n, c.tail_n);
+
+    const bool sparse = c.pc.enabled && ss->use_sparse && has_sparse_enc(P.enc) && !P.general;
+    if (!(sparse ? run_sparse(c) : run_block(c))) return fail;
+
+    const size_t nrec = c.nrec, ntext = c.ntext;
+    const FinalState& fin = c.fin;
+    ss->stats.windows_total = (uint64_t)(c.w_hi - c.w_lo);
+    ss->stats.windows_listed = c.windows_listed;
     ss->have_history = true;
-    ss->last_nrec = nrec; ss->last_ntext = ntext; ss->last_len = len;
-    ss->rec_per_byte = std::max(1.0 / 4096, 1.3 * (double)nrec / (double)len);
-    ss->text_per_byte = std::max(1.0 / 256, 1.3 * (double)ntext / (double)len);
+    ss->last_nrec = nrec; ss->last_ntext = ntext; ss->last_len = hi - lo;
+    ss->rec_per_byte = std::max(1.0 / 4096, 1.3 * (double)nrec / (double)(hi - lo));
+    ss->text_per_byte = std::max(1.0 / 256, 1.3 * (double)ntext / (double)(hi - lo));
     ss->stats.n_records = nrec;
     ss->stats.text_bytes = ntext;
 
-    // ---- text + download ---------------------------------------------------------------------------
+    // ---- the collection ----------------------------------------------------------------------------
     std::vector<uint8_t> new_leftover;
     bool have_leftover = false;
-    bool direct_out = ss->stats.sparse_used != 0 && fc->set.f != nullptr;
-    if (!direct_out && nrec > 0 && ss->use_direct) {
-        // block-kernel path: order the records on the device and write them as findings into a pinned set
-        const size_t nblocks = (size_t)((counters[2] + kThreads - 1) / kThreads);
-        pinned_release(fc->set);
-        if (pinned_acquire(nrec, ntext, &fc->set) && grow(&ss->d_bpos, &ss->bpos_cap, nblocks + 1)) {
-            ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, fc->set.f, fc->set.fcap, fc->set.t,
-                      input_file_id, ss->m.mission_id};
-            sx_order_scan_kernel<<<1, 1024, 0, st>>>(ss->d_blocks, ss->d_bpos, nblocks);
-            const unsigned wgrid = (unsigned)std::min<size_t>((nblocks + 7) / 8, (size_t)ss->num_sms * 8);
-            sx_order_write_kernel<<<wgrid, 256, 0, st>>>(O, ss->d_blocks, ss->d_bpos, nblocks, nrec);
-            CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(&fin, ss->d_final, sizeof fin, cudaMemcpyDeviceToHost, st));  // first / last record flags
-            ss->stats.kernel_launches += 2;
-            direct_out = true;
-        } else {
-            cudaGetLastError();
-            pinned_release(fc->set);
-        }
-    }
-    // sparse pipeline: the gather kernel also wrote the finding text (UTF-8: the input bytes) into the pinned set
-    const bool text_on_host = direct_out && ss->stats.sparse_used != 0 && !fin.text_fallback;
-    if (direct_out && !text_on_host) {
-        // The findings are already in the collection's pinned set, written by the device in their final form;
-        // only the text (transcoded on the device) is downloaded, straight to the address the findings point to.
-        if (nrec) {
-            const int mgrid = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ss->num_sms * 8);
-            CK(cudaEventRecord(ss->ev[2], st));
-            sx_materialize_kernel<<<mgrid, 256, 0, st>>>(P, ss->d_recs, nrec, ss->d_text, ss->text_cap);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(ss->ev[3], st));
-            ss->stats.kernel_launches++;
-            if (ntext) CK(cudaMemcpyAsync(fc->set.t, ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
-            ss->stats.d2h_bytes += nrec * sizeof(sx_finding) + ntext;
-        }
-    }
-    if (direct_out) {
-        if (!text_on_host) CK(cudaStreamSynchronize(st));
-        if (nrec && !text_on_host) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ss->ev[2], ss->ev[3]);
-            ss->stats.materialize_kernel_ms = ms;
-        }
-        if (text_on_host) ss->stats.d2h_bytes += nrec * sizeof(sx_finding) + ntext;
+    if (c.direct_out) {
+        // The findings are already in the collection's pinned set in their final form, their text at the address they
+        // point to; the host neither copies nor converts records.
         const auto t_post = std::chrono::steady_clock::now();
-        ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - t_begin).count();
+        ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - c.t_begin).count();
         const bool tail_is_leftover = nrec > 0 && (fin.last_flags & RF_LEFTOVER) != 0;
         const size_t n_out = nrec - (tail_is_leftover ? 1 : 0);
         fc->v.adopt(fc->set.f, n_out);
@@ -1452,8 +1848,10 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         }
         ss->stats.host_post_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_post).count();
     } else {
-    const bool sparse_out = ss->stats.sparse_used != 0;  // records already in stream order: one descriptor
-    const size_t nblocks = sparse_out ? 1 : (size_t)((counters[2] + kThreads - 1) / kThreads);
+    // legacy download (test hook sx_scanner_state_set_direct_output(0), or no pinned memory): records and text are copied
+    // from the device and converted on the host
+    const bool in_order = c.records_in_order;  // one descriptor
+    const size_t nblocks = in_order ? 1 : (size_t)((c.windows_listed + kThreads - 1) / kThreads);
     if (!grow_pinned(&ss->h_recs, &ss->h_recs_cap, nrec + 1)) return fail;
     if (!grow_pinned(&ss->h_text, &ss->h_text_cap, ntext + 1)) return fail;
     if (!grow_pinned(&ss->h_blocks, &ss->h_blocks_cap, nblocks + 1)) return fail;
@@ -1469,9 +1867,9 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
         ss->stats.kernel_launches++;
         CK(cudaMemcpyAsync(ss->h_recs, ss->d_recs, nrec * sizeof(Record), cudaMemcpyDeviceToHost, st));
         if (ntext) CK(cudaMemcpyAsync(ss->h_text, ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
-        if (sparse_out) ss->h_blocks[0] = make_uint2(0u, (unsigned)nrec);
+        if (in_order) ss->h_blocks[0] = make_uint2(0u, (unsigned)nrec);
         else CK(cudaMemcpyAsync(ss->h_blocks, ss->d_blocks, nblocks * sizeof(uint2), cudaMemcpyDeviceToHost, st));
-        ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + (sparse_out ? 0 : nblocks * sizeof(uint2));
+        ss->stats.d2h_bytes += nrec * sizeof(Record) + ntext + (in_order ? 0 : nblocks * sizeof(uint2));
     }
     CK(cudaStreamSynchronize(st));
     if (nrec) {
@@ -1481,7 +1879,7 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
     }
 
     const auto t_post = std::chrono::steady_clock::now();
-    ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - t_begin).count();
+    ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - c.t_begin).count();
     // ---- build the collection in stream order (blocks own contiguous record ranges) -------------------
     // At most two records carry host text in front of their device text: the very first record (a run that
     // began in the previous call) and the final leftover pseudo record, which is always the last one.
@@ -1566,33 +1964,42 @@ extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input
 
     }
 
-    // ---- ScannerState update (finding_collection.rs:330-338) -----------------------------------------
-    ss->cut = fin.carry.kind == K_C;
-    if (fin.carry.kind == K_L && fin.carry.k > 0 && have_leftover) ss->leftover.swap(new_leftover);
-    else ss->leftover.clear();
-    {
+    // ---- ScannerState update (finding_collection.rs:330-338): only when the range reaches the end of the buffer ----
+    if (tail) {
+        ss->cut = fin.carry.kind == K_C;
+        if (fin.carry.kind == K_L && fin.carry.k > 0 && have_leftover) ss->leftover.swap(new_leftover);
+        else ss->leftover.clear();
         uint8_t all[16];
         memcpy(all, ss->pend, 8);  // old pend occupies all[8-npend..8)
-        memcpy(all + 8, tail, 8);  // tail occupies all[16-tail_n..16)
         // concatenation old_pend ++ tail, right aligned: when len < 8 the old pend bytes must follow on directly
         uint8_t cat[16];
         size_t cn = 0;
         for (int i = 8 - ss->npend; i < 8; ++i) cat[cn++] = all[i];
-        for (size_t i = 8 - tail_n; i < 8; ++i) cat[cn++] = tail[i];
+        for (size_t i = 8 - c.tail_n; i < 8; ++i) cat[cn++] = c.tail[i];
         const int np = fin.npend;
         memset(ss->pend, 0, 8);
         if (np > 0 && (size_t)np <= cn) memcpy(ss->pend + 8 - np, cat + cn - np, (size_t)np);
         ss->npend = (np > 0 && (size_t)np <= cn) ? np : 0;
+        ss->consumed += len;
     }
-    ss->consumed += len;
     {
-        const auto t_end = std::chrono::steady_clock::now();
-        ss->stats.host_total_ms = std::chrono::duration<float, std::milli>(t_end - t_begin).count();
-        if (!direct_out) ss->stats.host_post_ms = ss->stats.host_total_ms - ss->stats.host_phase_ms[2];
+        ss->stats.host_total_ms = ms_since(c.t_begin);
+        if (!c.direct_out) ss->stats.host_post_ms = ss->stats.host_total_ms - ss->stats.host_phase_ms[2];
         ss->stats.host_phase_ms[3] = ss->stats.host_total_ms;
     }
     guard.p = nullptr;
     return fc;
+}
+
+extern "C" sx_finding_collection* sx_scan_stream(sx_scanner_state* ss, int input_file_id, const void* buf, size_t len,
+                                                 size_t slice_len, int buf_is_device, int is_last, void* cuda_stream) {
+    return scan_impl(ss, input_file_id, buf, len, slice_len, buf_is_device, is_last, 0, len, 0, cuda_stream);
+}
+
+extern "C" sx_finding_collection* sx_scan_range(sx_scanner_state* ss, int input_file_id, const void* buf, size_t len, size_t slice_len,
+                                                int buf_is_device, int is_last, size_t lo, size_t hi, int flags, void* cuda_stream) {
+    return scan_impl(ss, input_file_id, buf, len, slice_len, buf_is_device, is_last, lo, hi, (flags & SX_RANGE_PREFIX_UNKNOWN) ? 1 : 0,
+                     cuda_stream);
 }
 
 extern "C" sx_finding_collection* sx_finding_collection_from(sx_scanner_state* ss, int input_file_id, const uint8_t* buf,

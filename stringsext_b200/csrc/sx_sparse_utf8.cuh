@@ -1,11 +1,12 @@
-// sx_sparse_utf8.cuh -- the exact stage for UTF-8 missions as a pipeline of data-parallel kernels, one thread per
-// listed window ("entry"), no barrier on the data path.
+// sx_sparse_utf8.cuh -- the exact stage for missions with a bit-parallel window engine (UTF-8 and the single-byte
+// family) as a pipeline of data-parallel kernels, one thread per listed window ("entry"), no barrier on the data path.
 //
 // sx_exact_kernel (sx_exact.cuh) resolves the carries of a block of entries with block barriers between its stages;
 // on the sparse lists of binary input almost every stage has a handful of busy lanes, so the kernel is bound by the
 // latency of single warps (ncu: barrier stalls, profiles/).  Here every stage is its own kernel and the per-entry
-// results live in a device array (EntryState):
+// results live in device arrays (EntryHot + staged records):
 //
+//   sx_list_compact_kernel  the prefilter CTAs' list regions -> one contiguous list of the piece; entry count
 //   sx_sp_heads_kernel   queues the members of runs of adjacent windows (entries whose predecessor window is listed);
 //                        entries whose predecessor window is not listed: carry-in from the 32 bytes in front of the
 //                        window (the pre-roll folded into the mask frame), ONE pass of the mask engine
@@ -16,15 +17,20 @@
 //   sx_sp_fix_kernel     the rest, few: members behind a carry-dependent window (walked in order; a window that is one short run is passed in closed
 //                        form, eval_caseb, and resolved afterwards by sx_sp_late_kernel, in parallel)
 //   sx_sp_ext_kernel     extension windows (a "cut" / long leftover carry reaching an unlisted successor),
-//                        per-entry totals -> per-CTA totals
-//   sx_sp_scan_kernel    exclusive scan of the per-CTA totals
+//                        per-entry totals -> per-chunk totals
+//   sx_sp_scan_kernel    exclusive scan of the per-chunk totals on top of the totals of the pieces before this one
 //   sx_sp_gather_kernel  records and text offsets in stream order (exactly the order FindingCollection::from pushes
-//                        them, finding_collection.rs:255-285); findings (C-ABI layout) and their text straight into
-//                        the collection's pinned host memory; final carry for the ScannerState
+//                        them, finding_collection.rs:255-285); findings (C-ABI layout) and their text into device staging
+//                        buffers that the host copies to the collection's pinned memory piece by piece (copy engine,
+//                        overlapping the scan of the next piece); final carry for the ScannerState
+//
+// A call is cut into PIECES (window ranges, sx_scan.cu): each piece runs this pipeline on its own slices of the arrays
+// below while the prefilter already streams the next piece; the carry into a piece's first window comes from
+// sx_range_carry_kernel (sx_exact.cuh), so pieces do not wait for each other except for the record offsets.
 //
 // Text-like input (every window listed, several findings per window) takes the same path: most windows' carry-out is
 // independent of their carry-in, so the members resolve in parallel too.  The block kernel remains for the other
-// encodings, for general missions and when the per-entry state would not fit (sx_scan.cu).
+// encodings and for general missions (sx_scan.cu).
 #pragma once
 #include "sx_exact.cuh"
 #include <algorithm>
@@ -32,7 +38,10 @@
 namespace sx {
 
 enum : uint8_t { ES_PENDING = 0, ES_DONE = 1, ES_DECLINED = 2 /* head */, ES_DEPENDENT = 3 /* member of a run */ };
-struct EntryState {
+// Per-entry state every stage reads and writes: one 64-byte line.  The records a window stages (kBufRecs of its own,
+// kBufRecs of its extension window) and the closed-form descriptor's null carry live in separate arrays that are only
+// touched when there is something to store -- most listed windows of binary input print nothing.
+struct EntryHot {
     Carry kin, kout;
     uint32_t cnt_r, cnt_t;    // records / text bytes of the window under its real carry
     uint32_t xcnt_r, xcnt_t;  // ... of the extension window
@@ -41,24 +50,47 @@ struct EntryState {
     uint8_t resolved;         // kin / kout / counts / staged records are final
     uint8_t kin_known;        // sx_sp_fix_kernel: kin is final, the window itself is resolved by sx_sp_late_kernel
     // closed-form transfer function of the window (written by the thread of the NEXT entry, sx_sp_members_kernel):
-    // one run of d_a (< q) passing chars with d_t text bytes covering the window, eval_caseb()
-    uint16_t d_a, d_t;
-    uint32_t d_caseb;
-    uint32_t pad1;
-    Carry d_null;
-    Record staged[kBufRecs];
-    Record xstaged[kBufRecs];
+    // one run of d_a (< q) passing chars with d_t text bytes covering the window, eval_caseb(); null carry in dnull[]
+    uint8_t d_caseb, pad0;
+    uint16_t d_a, d_t, pad1;
+    uint32_t pad2;
+};
+static_assert(sizeof(EntryHot) == 64, "EntryHot is one 64-byte line");
+
+// Device-resident control block of one piece.
+struct PieceCtl {
+    unsigned long long ne;        // list entries of the piece (0 when they do not fit the entry arrays: overflow)
+    unsigned long long ne_raw;    // windows the prefilter kept
+    unsigned long long qcount, qcount2, qcount2_snap;
+    unsigned long long nrec, ntext;          // findings / text bytes of this piece
+    unsigned long long rec_base, text_base;  // ... of all pieces before it
+    uint32_t overflow;            // 1: entries > capacity, 2: records / text beyond the output buffers
+    uint32_t text_fallback;       // some CTA left its text to sx_materialize_kernel
+    RangeCarryOut rc;             // carry into the piece's first window (sx_range_carry_kernel); rc.fail: none found
+};
+// What the host reads per piece (pinned, device-mapped; written by sx_sp_scan_kernel / sx_sp_gather_kernel).
+constexpr int kGatherParts = 4;
+struct PieceSummary {
+    unsigned long long nrec, ntext, rec_base, text_base, ne_raw;
+    uint32_t overflow, text_fallback;
+    // the gather kernel is launched in parts (chunk ranges) so that the download of a part overlaps the gathering of the
+    // next one: cumulative record / text offsets at the END of every part
+    unsigned long long part_rec_end[kGatherParts], part_text_end[kGatherParts];
 };
 
 struct SparseBufs {
-    EntryState* E;
-    ulonglong2* btot;          // per-CTA {records, text bytes}: totals, then exclusive prefix
+    EntryHot* H;
+    Carry* dnull;              // per entry: null carry of its closed-form descriptor (d_caseb)
+    Record* staged;            // per entry kBufRecs records
+    Record* xstaged;           // per entry kBufRecs records of the extension window
+    ulonglong2* btot;          // per chunk of kSpThreads entries {records, text bytes}: totals, then exclusive prefix
     Utf8Tables* tables;        // filled by sx_sp_tables_kernel
     uint32_t* queue;           // members of runs of adjacent windows (sx_sp_members_kernel)
-    unsigned long long* qcount;
     uint32_t* queue2;          // what is left for sx_sp_fix_kernel: declined heads, members with a carry-dependent predecessor
-    unsigned long long* qcount2;
-    long long NE;
+    PieceCtl* ctl;             // this piece
+    const PieceCtl* prev;      // the piece before it (nullptr: first piece of the call)
+    PieceSummary* summary;     // host-visible
+    uint8_t* text_out;         // device text arena (staging of the finding text)
 };
 
 constexpr int kSpThreads = 128;
@@ -67,6 +99,40 @@ constexpr uint32_t kQueueHead = 0x80000000u;
 static __global__ void __launch_bounds__(256) sx_sp_tables_kernel(const __grid_constant__ ScanParams P, Utf8Tables* T) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < 2048) mask_tables_fill(P, *T, k);
+}
+
+// The list regions of the prefilter CTAs of one piece -> a contiguous list; entry count and queue counters of the piece.
+static __global__ void __launch_bounds__(256)
+sx_list_compact_kernel(const uint32_t* __restrict__ cta_count, uint32_t ncta, const uint32_t* __restrict__ list, long long tile0,
+                       long long tiles_per_cta, uint32_t* __restrict__ out, PieceCtl* ctl, unsigned long long cap) {
+    __shared__ unsigned long long s_pre[8], s_tot[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    unsigned long long pre = 0, tot = 0;
+    for (uint32_t k = tid; k < ncta; k += 256) {
+        const uint32_t c = cta_count[k];
+        tot += c;
+        if (k < b) pre += c;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        pre += __shfl_down_sync(0xffffffffu, pre, d);
+        tot += __shfl_down_sync(0xffffffffu, tot, d);
+    }
+    if (lane == 0) { s_pre[warp] = pre; s_tot[warp] = tot; }
+    __syncthreads();
+    pre = 0; tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { pre += s_pre[k]; tot += s_tot[k]; }
+    if (b == 0 && tid == 0) {
+        ctl->ne_raw = tot;
+        ctl->ne = tot <= cap ? tot : 0ull;
+        if (tot > cap) ctl->overflow |= 1u;
+        ctl->qcount = 0; ctl->qcount2 = 0; ctl->qcount2_snap = 0;
+    }
+    if (tot > cap) return;
+    const uint32_t n = cta_count[b];
+    const uint32_t* src = list + (size_t)(tile0 + (long long)b * tiles_per_cta) * kPrefTileWin;
+    for (uint32_t i = tid; i < n; i += 256) out[pre + i] = src[i];
 }
 
 struct SpCtx {
@@ -83,7 +149,9 @@ __device__ __forceinline__ void sp_setup(const ScanParams& P, const ExactCfg& X,
     c.g = GlobalSrc{P.in, P.pend};
     c.ts = GlobalTile{c.g, P.len, X.in_aligned16 != 0, &S, (uint32_t)__cvta_generic_to_shared(&S.tt[0])};
 }
-__device__ __forceinline__ void sp_store(EntryState* es, const Carry& kin, const WinResult& r) {
+__device__ __forceinline__ Record* sp_staged(const SparseBufs& B, long long e) { return B.staged + (size_t)e * kBufRecs; }
+__device__ __forceinline__ Record* sp_xstaged(const SparseBufs& B, long long e) { return B.xstaged + (size_t)e * kBufRecs; }
+__device__ __forceinline__ void sp_store(EntryHot* es, const Carry& kin, const WinResult& r) {
     es->kin = kin;
     es->kout = r.out;
     es->cnt_r = r.nrec;
@@ -94,19 +162,20 @@ __device__ __forceinline__ void sp_store(EntryState* es, const Carry& kin, const
 }
 // a head (predecessor window not listed) with the byte-wise engine: pre-roll, then one pass under the real carry
 template <class Dec>
-__device__ __noinline__ void sp_head_bytewise(const ScanParams& P, const ExactCfg& X, const SpCtx& c, long long w, EntryState* es) {
+__device__ __noinline__ void sp_head_bytewise(const ScanParams& P, const ExactCfg& X, const SparseBufs& B, const SpCtx& c, long long w,
+                                              long long e) {
     WinGeom wg;
     c.geo.window(w, wg);
-    Carry kin0 = P.k0;
-    if (w != 0) {
+    Carry kin0 = range_carry_in(P, X);
+    if (w != X.w_first) {
         const WinGeom rg = preroll_geom(c.geo, w, X.pre_bytes);
         WinResult rr;
         WindowEngine<Dec>::run(P, c.ts, c.g, rg, carry_none(), MODE_STATE, nullptr, 0, rr, nullptr);
         kin0 = rr.out;
     }
     WinResult r;
-    WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin0, MODE_BUFFER, es->staged, 0, r, nullptr);
-    sp_store(es, kin0, r);
+    WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin0, MODE_BUFFER, sp_staged(B, e), 0, r, nullptr);
+    sp_store(&B.H[e], kin0, r);
 }
 
 // warp-aggregated append to a work queue
@@ -125,63 +194,74 @@ __device__ __forceinline__ void sp_push(uint32_t* queue, unsigned long long* qco
 // run of adjacent windows (its carry-in is the carry-out of the entry before it).
 // a head with the mask engine (pre-roll + one pass under the real carry); false when the engine declines
 template <class Dec>
-__device__ __forceinline__ bool sp_head_mask(const ScanParams& P, const ExactCfg& X, const SpCtx& c, long long w, EntryState* es) {
+__device__ __forceinline__ bool sp_head_mask(const ScanParams& P, const ExactCfg& X, const SparseBufs& B, const SpCtx& c, long long w,
+                                             long long e) {
     WinGeom wg;
     c.geo.window(w, wg);
     WinResult r;
+    EntryHot* const es = &B.H[e];
     // one pass: the pre-roll region is the 32 bytes in front of the window (same class planes, same decoder algebra)
-    if (w != 0 && mask_head<MaskFamily<Dec>::kSByte>(P, c.ts, wg, X.pre_bytes, MODE_BUFFER, es->staged, 0, r)) {
+    if (w != X.w_first && mask_head<MaskFamily<Dec>::kSByte>(P, c.ts, wg, X.pre_bytes, MODE_BUFFER, sp_staged(B, e), 0, r)) {
         sp_store(es, r.in, r);
         return true;
     }
-    Carry kin0 = P.k0;
-    if (w != 0) {
+    Carry kin0 = range_carry_in(P, X);
+    if (w != X.w_first) {
         const WinGeom rg = preroll_geom(c.geo, w, X.pre_bytes);
         WinResult rr;
         if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr)) return false;
         kin0 = rr.out;
     }
-    if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin0, MODE_BUFFER, es->staged, 0, r)) return false;
+    if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin0, MODE_BUFFER, sp_staged(B, e), 0, r)) return false;
     sp_store(es, kin0, r);
     return true;
 }
 // a member under its real carry: mask engine, byte-wise engine when it declines
 template <class Dec>
-__device__ __forceinline__ Carry sp_member(const ScanParams& P, const SpCtx& c, long long w, const Carry& kin, EntryState* es) {
+__device__ __forceinline__ Carry sp_member(const ScanParams& P, const SparseBufs& B, const SpCtx& c, long long w, const Carry& kin,
+                                           long long e) {
     WinGeom wg;
     c.geo.window(w, wg);
     WinResult r;
-    if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin, MODE_BUFFER, es->staged, 0, r))
-        WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin, MODE_BUFFER, es->staged, 0, r, nullptr);
-    sp_store(es, kin, r);
+    if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin, MODE_BUFFER, sp_staged(B, e), 0, r))
+        WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin, MODE_BUFFER, sp_staged(B, e), 0, r, nullptr);
+    sp_store(&B.H[e], kin, r);
     return r.out;
 }
 
+// The kernels are persistent over the piece's entries (the entry count only exists on the device): chunk = kSpThreads
+// consecutive entries, CTA b takes chunks b, b + gridDim.x, ...
 // 6 CTAs of 128 threads per SM (80 registers): measured best for this latency-bound kernel (4: 0.35 ms, 6: 0.29 ms, 8: 0.39 ms
 // before the one-pass heads)
 template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 6)
 sx_sp_heads_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
+    const long long NE = (long long)B.ctl->ne;
+    if ((long long)blockIdx.x * kSpThreads >= NE) return;
     SpCtx c;
     sp_setup(P, X, B, T, c);
-    const long long e = (long long)blockIdx.x * kSpThreads + threadIdx.x;
-    bool declined = false, member = false;
-    if (e < B.NE) {
-        const long long w = list_window(X, X.cta_off, e);
-        EntryState* const es = &B.E[e];
-        es->xcnt_r = 0;
-        es->xcnt_t = 0;
-        es->status = ES_PENDING;
-        es->resolved = 0;
-        es->kin_known = 0;
-        es->d_caseb = 0;
-        member = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
-        if (!member && !sp_head_mask<Dec>(P, X, c, w, es)) { es->status = ES_DECLINED; declined = true; }
+    for (long long e0 = (long long)blockIdx.x * kSpThreads; e0 < NE; e0 += (long long)gridDim.x * kSpThreads) {
+        const long long e = e0 + threadIdx.x;
+        bool declined = false, member = false;
+        if (e < NE) {
+            const long long w = list_window(X, X.cta_off, e);
+            EntryHot* const es = &B.H[e];
+            es->xcnt_r = 0;
+            es->xcnt_t = 0;
+            es->status = ES_PENDING;
+            es->resolved = 0;
+            es->kin_known = 0;
+            es->d_caseb = 0;
+            member = e > 0 && list_window(X, X.cta_off, e - 1) == w - 1;
+            if (!member && !sp_head_mask<Dec>(P, X, B, c, w, e)) { es->status = ES_DECLINED; declined = true; }
+        }
+        sp_push(B.queue, &B.ctl->qcount, member, (uint32_t)e);  // resolved by sx_sp_members_kernel
+        sp_push(B.queue2, &B.ctl->qcount2, declined, (uint32_t)e);
     }
-    sp_push(B.queue, B.qcount, member, (uint32_t)e);  // resolved by sx_sp_members_kernel
-    sp_push(B.queue2, B.qcount2, declined, (uint32_t)e);
 }
+// queue2 holds the declined heads now (the members kernel appends its dependent members behind them): snapshot its length
+static __global__ void sx_sp_snapshot_kernel(PieceCtl* ctl) { ctl->qcount2_snap = ctl->qcount2; }
 
 // Members of runs, all at once: the carry-in of a member is the carry-out of the entry before it -- known when that
 // entry is a resolved head, and computable from the window alone when its carry-out does not depend on its own
@@ -191,9 +271,10 @@ template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
+    const unsigned long long nq = B.ctl->qcount;
+    if ((unsigned long long)blockIdx.x * kSpThreads >= nq) return;
     SpCtx c;
     sp_setup(P, X, B, T, c);
-    const unsigned long long nq = *B.qcount;
     const unsigned long long stride = (unsigned long long)gridDim.x * kSpThreads;
     for (unsigned long long t0 = (unsigned long long)blockIdx.x * kSpThreads; t0 < nq; t0 += stride) {
         const unsigned long long t = t0 + threadIdx.x;
@@ -206,8 +287,8 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
             Carry kin = carry_none();
             bool known = false;
             if (!pred_is_member) {
-                known = B.E[e - 1].status == ES_DONE;
-                if (known) kin = B.E[e - 1].kout;
+                known = B.H[e - 1].status == ES_DONE;
+                if (known) kin = B.H[e - 1].kout;
             } else {
                 WinGeom pg;
                 c.geo.window(w - 1, pg);
@@ -216,8 +297,8 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
                     known = rr.cut1 == 0;
                     kin = rr.out;
                     if (rr.caseb) {  // the walk of sx_sp_fix_kernel gets through that window without a pass
-                        EntryState* const pe = &B.E[e - 1];
-                        pe->d_a = rr.a; pe->d_t = rr.t_out; pe->d_null = rr.out; pe->d_caseb = 1;
+                        EntryHot* const pe = &B.H[e - 1];
+                        pe->d_a = rr.a; pe->d_t = rr.t_out; B.dnull[e - 1] = rr.out; pe->d_caseb = 1;
                     }
                 } else {
                     // the mask engine declines (e.g. a window crowded with findings): the byte-wise engine's
@@ -227,33 +308,34 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
                     known = d.type == WT_CONST;
                     kin = d.null_out;
                     if (d.type == WT_CASEB) {
-                        EntryState* const pe = &B.E[e - 1];
-                        pe->d_a = d.a; pe->d_t = d.t_out; pe->d_null = d.null_out; pe->d_caseb = 1;
+                        EntryHot* const pe = &B.H[e - 1];
+                        pe->d_a = d.a; pe->d_t = d.t_out; B.dnull[e - 1] = d.null_out; pe->d_caseb = 1;
                     }
                 }
             }
-            if (known) sp_member<Dec>(P, c, w, kin, &B.E[e]);
-            else { B.E[e].status = ES_DEPENDENT; dependent = true; }
+            if (known) sp_member<Dec>(P, B, c, w, kin, e);
+            else { B.H[e].status = ES_DEPENDENT; dependent = true; }
         }
-        sp_push(B.queue2, B.qcount2, dependent, (uint32_t)e);
+        sp_push(B.queue2, &B.ctl->qcount2, dependent, (uint32_t)e);
     }
 }
 
 // Heads the mask engine declined (rare: 0.04 % of the entries on binary input), byte-wise.  The byte-wise engine takes
 // ~0.1 ms for one window on a lone warp, so this kernel runs on a side stream beside sx_sp_members_kernel instead of
-// sitting in front of the walks of sx_sp_fix_kernel.  Persistent over queue2 (which only holds declined heads when it
-// is launched).
+// sitting in front of the walks of sx_sp_fix_kernel.  Persistent over the first qcount2_snap items of queue2 (the
+// declined heads).
 template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
-sx_sp_declined_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B, const unsigned long long* nq_ptr) {
+sx_sp_declined_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
+    const unsigned long long nq = B.ctl->qcount2_snap;
+    if ((unsigned long long)blockIdx.x * kSpThreads >= nq) return;
     SpCtx c;
     sp_setup(P, X, B, T, c);
-    const unsigned long long nq = *nq_ptr;
     for (unsigned long long t = (unsigned long long)blockIdx.x * kSpThreads + threadIdx.x; t < nq;
          t += (unsigned long long)gridDim.x * kSpThreads) {
         const long long e = (long long)B.queue2[t];
-        sp_head_bytewise<Dec>(P, X, c, list_window(X, X.cta_off, e), &B.E[e]);
+        sp_head_bytewise<Dec>(P, X, B, c, list_window(X, X.cta_off, e), e);
     }
 }
 
@@ -264,33 +346,35 @@ template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_fix_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
+    const unsigned long long nq = B.ctl->qcount2;
+    if ((unsigned long long)blockIdx.x * kSpThreads >= nq) return;
+    const long long NE = (long long)B.ctl->ne;
     SpCtx c;
     sp_setup(P, X, B, T, c);
-    const unsigned long long nq = *B.qcount2;
     for (unsigned long long t = (unsigned long long)blockIdx.x * kSpThreads + threadIdx.x; t < nq;
          t += (unsigned long long)gridDim.x * kSpThreads) {
         const long long e = (long long)B.queue2[t];
         const long long w = list_window(X, X.cta_off, e);
-        if (B.E[e].status == ES_DECLINED) continue;  // a head: resolved by sx_sp_declined_kernel
-        const uint8_t ps = B.E[e - 1].status;
+        if (B.H[e].status == ES_DECLINED) continue;  // a head: resolved by sx_sp_declined_kernel
+        const uint8_t ps = B.H[e - 1].status;
         if (ps == ES_DEPENDENT) continue;  // the walk that started further left comes through here
-        Carry kin = B.E[e - 1].kout;
+        Carry kin = B.H[e - 1].kout;
         long long m = e, wm = w;
         for (;;) {
-            EntryState* const es = &B.E[m];
+            EntryHot* const es = &B.H[m];
             if (es->d_caseb) {
                 // one short run covering the window: its carry-out follows in closed form, the window itself (its
                 // findings under this carry-in) is left to sx_sp_late_kernel, in parallel with the others
                 es->kin = kin;
                 es->kin_known = 1;
                 WinDesc d;
-                d.type = WT_CASEB; d.pad = 0; d.a = es->d_a; d.t_out = es->d_t; d.nrec = 0; d.ntext = 0; d.null_out = es->d_null;
+                d.type = WT_CASEB; d.pad = 0; d.a = es->d_a; d.t_out = es->d_t; d.nrec = 0; d.ntext = 0; d.null_out = B.dnull[m];
                 WinGeom wg;
                 c.geo.window(wm, wg);
                 kin = eval_caseb(P, d, kin, (uint32_t)(wg.we - wg.ws));
-            } else kin = sp_member<Dec>(P, c, wm, kin, es);
+            } else kin = sp_member<Dec>(P, B, c, wm, kin, m);
             ++m;
-            if (m >= B.NE || B.E[m].status != ES_DEPENDENT) break;
+            if (m >= NE || B.H[m].status != ES_DEPENDENT) break;
             const long long wn = list_window(X, X.cta_off, m);
             if (wn != wm + 1) break;
             wm = wn;
@@ -303,14 +387,15 @@ template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_late_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
+    const unsigned long long nq = B.ctl->qcount2;
+    if ((unsigned long long)blockIdx.x * kSpThreads >= nq) return;
     SpCtx c;
     sp_setup(P, X, B, T, c);
-    const unsigned long long nq = *B.qcount2;
     for (unsigned long long t = (unsigned long long)blockIdx.x * kSpThreads + threadIdx.x; t < nq;
          t += (unsigned long long)gridDim.x * kSpThreads) {
         const long long e = (long long)B.queue2[t];
-        EntryState* const es = &B.E[e];
-        if (es->kin_known && !es->resolved) sp_member<Dec>(P, c, list_window(X, X.cta_off, e), es->kin, es);
+        EntryHot* const es = &B.H[e];
+        if (es->kin_known && !es->resolved) sp_member<Dec>(P, B, c, list_window(X, X.cta_off, e), es->kin, e);
     }
 }
 
@@ -328,46 +413,64 @@ __device__ __forceinline__ void sp_block_sum2(unsigned long long& a, unsigned lo
     __syncthreads();
 }
 
+// is the window behind entry e (window w) listed?  The first window of the NEXT range is, by construction.
+__device__ __forceinline__ bool sp_next_adjacent(const ExactCfg& X, long long NE, long long e, long long w) {
+    if (e + 1 < NE) return list_window(X, X.cta_off, e + 1) == w + 1;
+    return w + 1 == X.w_end && !range_is_tail(X);
+}
+
 template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
 sx_sp_ext_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     __shared__ unsigned long long sa[kSpThreads / 32], sb[kSpThreads / 32];
+    const long long NE = (long long)B.ctl->ne;
+    if ((long long)blockIdx.x * kSpThreads >= NE) return;
     SpCtx c;
     sp_setup(P, X, B, T, c);
-    const long long e = (long long)blockIdx.x * kSpThreads + threadIdx.x;
-    unsigned long long sum_r = 0, sum_t = 0;
-    if (e < B.NE) {
-        EntryState* const es = &B.E[e];
-        const long long w = list_window(X, X.cta_off, e);
-        const Carry kout = es->kout;
-        const bool next_adj = e + 1 < B.NE && list_window(X, X.cta_off, e + 1) == w + 1;
-        uint32_t xr = 0, xt = 0;
-        // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an unlisted
-        // successor: that window may print a continuation / the leftover
-        if (carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.total_windows) {
-            const WinGeom xg = ext_geom(c.geo, w + 1, X.pre_bytes);
-            WinResult r;
-            if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, xg, kout, MODE_BUFFER, es->xstaged, 0, r))
-                WindowEngine<Dec>::run(P, c.ts, c.g, xg, kout, MODE_BUFFER, es->xstaged, 0, r, nullptr);
-            xr = r.nrec; xt = r.ntext;
-            es->xcnt_r = xr;
-            es->xcnt_t = xt;
+    for (long long e0 = (long long)blockIdx.x * kSpThreads; e0 < NE; e0 += (long long)gridDim.x * kSpThreads) {
+        const long long e = e0 + threadIdx.x;
+        unsigned long long sum_r = 0, sum_t = 0;
+        if (e < NE) {
+            EntryHot* const es = &B.H[e];
+            const long long w = list_window(X, X.cta_off, e);
+            const Carry kout = es->kout;
+            const bool next_adj = sp_next_adjacent(X, NE, e, w);
+            uint32_t xr = 0, xt = 0;
+            // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an unlisted
+            // successor: that window may print a continuation / the leftover
+            if (carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.w_end) {
+                const WinGeom xg = ext_geom(c.geo, w + 1, X.pre_bytes);
+                WinResult r;
+                if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, xg, kout, MODE_BUFFER, sp_xstaged(B, e), 0, r))
+                    WindowEngine<Dec>::run(P, c.ts, c.g, xg, kout, MODE_BUFFER, sp_xstaged(B, e), 0, r, nullptr);
+                xr = r.nrec; xt = r.ntext;
+                es->xcnt_r = xr;
+                es->xcnt_t = xt;
+            }
+            // the scanner's final leftover (pseudo record)
+            const bool extra = (e == NE - 1) && range_is_tail(X) && kout.kind == K_L && kout.k > 0;
+            sum_r = (unsigned long long)es->cnt_r + xr + (extra ? 1u : 0u);
+            sum_t = (unsigned long long)es->cnt_t + xt + (extra ? kout.out_bytes : 0u);
         }
-        const bool extra = (e == B.NE - 1) && kout.kind == K_L && kout.k > 0;  // the scanner's final leftover (pseudo record)
-        sum_r = (unsigned long long)es->cnt_r + xr + (extra ? 1u : 0u);
-        sum_t = (unsigned long long)es->cnt_t + xt + (extra ? kout.out_bytes : 0u);
+        sp_block_sum2(sum_r, sum_t, sa, sb);
+        if (threadIdx.x == 0) B.btot[e0 / kSpThreads] = make_ulonglong2(sum_r, sum_t);
     }
-    sp_block_sum2(sum_r, sum_t, sa, sb);
-    if (threadIdx.x == 0) B.btot[blockIdx.x] = make_ulonglong2(sum_r, sum_t);
 }
 
-// exclusive scan of the per-CTA totals, in place; grand totals -> counters[0], counters[1]
-static __global__ void __launch_bounds__(1024) sx_sp_scan_kernel(ulonglong2* btot, uint32_t nb, unsigned long long* counters) {
+// exclusive scan of the per-chunk totals, in place, starting from the totals of the pieces before this one; the piece's
+// totals -> its control block and the host-visible summary
+static __global__ void __launch_bounds__(1024) sx_sp_scan_kernel(const SparseBufs B, unsigned long long rec_cap, unsigned long long text_cap,
+                                                                 unsigned long long out_cap, uint32_t nparts) {
     __shared__ unsigned long long wa[32], wb[32];
     __shared__ unsigned long long carry_a, carry_b;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry_a = 0; carry_b = 0; }
+    ulonglong2* const btot = B.btot;
+    const unsigned long long ne = B.ctl->ne;
+    const uint32_t nb = (uint32_t)((ne + kSpThreads - 1) / kSpThreads);
+    const unsigned long long base_a = B.prev ? B.prev->rec_base + B.prev->nrec : 0ull;
+    const unsigned long long base_b = B.prev ? B.prev->text_base + B.prev->ntext : 0ull;
+    if (tid == 0) { carry_a = base_a; carry_b = base_b; }
     __syncthreads();
     for (uint32_t base = 0; base < nb; base += 1024) {
         const uint32_t k = base + tid;
@@ -396,34 +499,58 @@ static __global__ void __launch_bounds__(1024) sx_sp_scan_kernel(ulonglong2* bto
         if (tid == 1023) { carry_a = oa + a; carry_b = ob + b; }
         __syncthreads();
     }
-    if (tid == 0) { counters[0] = carry_a; counters[1] = carry_b; }
+    if (tid == 0) {
+        PieceCtl* const ctl = B.ctl;
+        ctl->rec_base = base_a; ctl->text_base = base_b;
+        ctl->nrec = carry_a - base_a; ctl->ntext = carry_b - base_b;
+        if (B.prev && (B.prev->overflow != 0)) ctl->overflow |= 4u;  // an earlier piece already failed
+        if (carry_a > rec_cap || carry_a > out_cap || carry_b > text_cap) ctl->overflow |= 2u;
+        if (ctl->rc.fail) ctl->overflow |= 0x100u;
+        PieceSummary s;
+        s.nrec = ctl->nrec; s.ntext = ctl->ntext; s.rec_base = base_a; s.text_base = base_b; s.ne_raw = ctl->ne_raw;
+        s.overflow = ctl->overflow; s.text_fallback = 0;
+        for (int i = 0; i < kGatherParts; ++i) {
+            const uint32_t cb = (uint32_t)(((unsigned long long)nb * (unsigned)(i + 1)) / (unsigned)nparts);
+            const bool last = i + 1 >= (int)nparts || cb >= nb;
+            s.part_rec_end[i] = last ? carry_a : btot[cb].x;
+            s.part_text_end[i] = last ? carry_b : btot[cb].y;
+        }
+        *B.summary = s;
+    }
 }
 
 template <class Dec>
 __global__ void __launch_bounds__(kSpThreads, 4)
-sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X, const SparseBufs B) {
+sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X, const SparseBufs B, uint32_t part, uint32_t nparts) {
     __shared__ Utf8Tables T;
     __shared__ uint32_t wa[8], wb[8];
-    // direct host output: the CTA's findings are contiguous in the output, so they are assembled in shared memory and
-    // leave as fully coalesced 16-byte stores (large PCIe write transactions instead of one 16-byte store per lane)
+    // the chunk's findings are contiguous in the output, so they are assembled in shared memory and leave as fully
+    // coalesced 16-byte stores
     constexpr uint32_t kStage = 224;
     __shared__ uint4 sbuf[kStage * 3];
-    // ... and so is their text (UTF-8 -> UTF-8: the bytes of the input range), written to the host the same way
+    // ... and so is their text (UTF-8 -> UTF-8: the bytes of the input range)
     constexpr uint32_t kTextStage = 4096;
     __shared__ __align__(16) uint8_t tbuf[kTextStage];
+    const long long NE = (long long)B.ctl->ne;
+    // this launch: chunks [c_lo, c_hi) of the piece
+    const unsigned long long nb = (unsigned long long)((NE + kSpThreads - 1) / kSpThreads);
+    const long long c_lo = (long long)((nb * part) / nparts), c_hi = part + 1 >= nparts ? (long long)nb : (long long)((nb * (part + 1)) / nparts);
+    if (c_lo + (long long)blockIdx.x >= c_hi) return;
+    if (B.ctl->overflow & 2u) return;  // the outputs do not fit: the host reruns with the counted sizes
     SpCtx c;
     sp_setup(P, X, B, T, c);
-    const long long e = (long long)blockIdx.x * kSpThreads + threadIdx.x;
-    const bool active = e < B.NE;
+    for (long long e0 = (c_lo + (long long)blockIdx.x) * kSpThreads; e0 < c_hi * kSpThreads; e0 += (long long)gridDim.x * kSpThreads) {
+    const long long e = e0 + threadIdx.x;
+    const bool active = e < NE;
     uint32_t cr = 0, ct = 0, xr = 0, xt = 0;
     bool extra = false;
     Carry kin = carry_none(), kout = carry_none();
-    const EntryState* es = nullptr;
+    const EntryHot* es = nullptr;
     if (active) {
-        es = &B.E[e];
+        es = &B.H[e];
         cr = es->cnt_r; ct = es->cnt_t; xr = es->xcnt_r; xt = es->xcnt_t;
         kin = es->kin; kout = es->kout;
-        extra = (e == B.NE - 1) && kout.kind == K_L && kout.k > 0;
+        extra = (e == NE - 1) && range_is_tail(X) && kout.kind == K_L && kout.k > 0;
     }
     const uint32_t sum_r = cr + xr + (extra ? 1u : 0u), sum_t = ct + xt + (extra ? kout.out_bytes : 0u);
     uint32_t er, et, tr, tt;
@@ -442,33 +569,29 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
         er = oa + ia - sum_r;
         et = ob + ib - sum_t;
     }
-    const ulonglong2 base = B.btot[blockIdx.x];
+    const ulonglong2 base = B.btot[e0 / kSpThreads];
     const unsigned long long br = base.x, bt = base.y;
-    const bool fits = (br + tr <= O.rec_cap) && (bt + tt <= O.text_cap) && (O.host_findings == nullptr || br + tr <= O.host_cap);
-    if (!fits && threadIdx.x == 0) O.final_state->overflow = 1;
     const bool host_out = O.host_findings != nullptr;
-    const bool staged_out = host_out && fits && tr <= kStage;
-    // CTAs with more findings than the staging buffer holds (text-like input) write their records to device memory first
-    // and convert them kRound at a time below; their text goes through the device arena (materialize kernel + download)
-    const bool round_out = host_out && fits && !staged_out;
-    const bool text_staged = host_out && fits && tt <= kTextStage;
-    if (host_out && fits && !text_staged && threadIdx.x == 0) O.final_state->text_fallback = 1;
-    uint8_t* const host_text = const_cast<uint8_t*>(O.host_text);
-    if (active && fits) {
+    const bool staged_out = host_out && tr <= kStage;
+    // chunks with more findings than the staging buffer holds (text-like input) write their records to device memory first
+    // and convert them kRound at a time below; their text goes through sx_materialize_kernel
+    const bool round_out = host_out && !staged_out;
+    const bool text_staged = tt <= kTextStage;
+    if (!text_staged && threadIdx.x == 0) { B.ctl->text_fallback = 1; B.summary->text_fallback = 1; }
+    if (active) {
         uint32_t ro = er, to = et;
         // the first / last record of the stream: their flags travel in the final state (host-carried text, leftover)
         auto put = [&](unsigned long long idx, const Record& r) {
             O.recs[idx] = r;
-            if (host_out) {
-                if (staged_out) write_host_finding(O, &sbuf[(idx - br) * 3], r);
-                if (idx == 0) O.final_state->first_flags = r.flags;
-                if (text_staged) transcode_range(P, c.g, r.in_start, r.in_len, tbuf + (r.text_off - bt));
-            }
+            if (staged_out) write_host_finding(O, &sbuf[(idx - br) * 3], r);
+            if (idx == 0) O.final_state->first_flags = r.flags;
+            if (text_staged) transcode_range(P, c.g, r.in_start, r.in_len, tbuf + (r.text_off - bt));
         };
         if (cr) {
             if (cr <= kBufRecs) {
+                const Record* st = sp_staged(B, e);
                 for (uint32_t k = 0; k < cr; ++k) {
-                    Record r = es->staged[k];
+                    Record r = st[k];
                     r.text_off += bt + to;
                     put(br + ro + k, r);
                 }
@@ -479,14 +602,15 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
                 WinResult r;
                 if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r))
                     WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
-                if (host_out) for (uint32_t k = 0; k < cr; ++k) put(br + ro + k, O.recs[br + ro + k]);
+                for (uint32_t k = 0; k < cr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
         }
         ro += cr; to += ct;
         if (xr) {
             if (xr <= kBufRecs) {
+                const Record* st = sp_xstaged(B, e);
                 for (uint32_t k = 0; k < xr; ++k) {
-                    Record r = es->xstaged[k];
+                    Record r = st[k];
                     r.text_off += bt + to;
                     put(br + ro + k, r);
                 }
@@ -495,7 +619,7 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
                 WinResult r;
                 if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r))
                     WindowEngine<Dec>::run(P, c.ts, c.g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
-                if (host_out) for (uint32_t k = 0; k < xr; ++k) put(br + ro + k, O.recs[br + ro + k]);
+                for (uint32_t k = 0; k < xr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
         }
         ro += xr; to += xt;
@@ -512,26 +636,26 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
             O.final_state->last_flags = r.flags;
         }
     }
-    if (active && e == B.NE - 1) { O.final_state->carry = kout; O.final_state->npend = es->npend; }
-    if (host_out) __syncthreads();
+    if (active && e == NE - 1 && range_is_tail(X)) { O.final_state->carry = kout; O.final_state->npend = es->npend; }
+    __syncthreads();
     if (staged_out) {
         uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br);
         for (uint32_t k = threadIdx.x; k < tr * 3; k += kSpThreads) dst[k] = sbuf[k];
     }
     if (round_out) {
         constexpr uint32_t kRound = kSpThreads;
-        for (uint32_t base = 0; base < tr; base += kRound) {
-            const uint32_t cnt = tr - base < kRound ? tr - base : kRound;
-            if (threadIdx.x < cnt) write_host_finding(O, &sbuf[threadIdx.x * 3], O.recs[br + base + threadIdx.x]);
+        for (uint32_t rb = 0; rb < tr; rb += kRound) {
+            const uint32_t cnt = tr - rb < kRound ? tr - rb : kRound;
+            if (threadIdx.x < cnt) write_host_finding(O, &sbuf[threadIdx.x * 3], O.recs[br + rb + threadIdx.x]);
             __syncthreads();
-            uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br + base);
+            uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br + rb);
             for (uint32_t k = threadIdx.x; k < cnt * 3; k += kSpThreads) dst[k] = sbuf[k];
             __syncthreads();
         }
     }
     if (text_staged && tt) {
         // [bt, bt + tt) of the text arena: bytes up to the first 16-byte boundary, aligned 16-byte body, tail bytes
-        uint8_t* const dst = host_text + bt;
+        uint8_t* const dst = B.text_out + bt;
         const uint32_t head = (uint32_t)((16u - (uint32_t)(reinterpret_cast<unsigned long long>(dst) & 15u)) & 15u);
         const uint32_t h = head < tt ? head : tt;
         const uint32_t body = (tt - h) >> 4;
@@ -547,39 +671,71 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
         }
         for (uint32_t k = h + 16u * body + threadIdx.x; k < tt; k += kSpThreads) dst[k] = tbuf[k];
     }
+    __syncthreads();  // sbuf / tbuf are reused by the next chunk
+    }
 }
 
-// ev[0..6]: timing events recorded between the stages (the library reports per-stage kernel times in sx_scan_stats)
+// One piece through the pipeline.  st: the stream of the exact stage; side: declined heads beside the members.
+// ev (optional, 7 timing events) is recorded between the stages; evs[0..1] order the side stream.
+struct SparseLaunchCfg {
+    unsigned grid_chunks;   // persistent grids of the per-chunk kernels (heads, ext, gather)
+    unsigned grid_queue;    // ... of the queue kernels (members, declined, fix, late)
+    unsigned long long rec_cap, text_cap, out_cap;
+    cudaEvent_t ev_scan_prev = nullptr;  // the scan kernel of the piece before this one (another stream)
+    cudaEvent_t ev_scan_done = nullptr;
+    uint32_t gather_parts = 1;           // <= kGatherParts
+    cudaEvent_t* ev_part = nullptr;      // recorded after every part of the gather
+};
 template <class Dec>
-inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B, int num_sms,
+inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B, const SparseLaunchCfg& L,
                                       cudaStream_t st, cudaEvent_t* ev, cudaStream_t side, cudaEvent_t* evs) {
-    const unsigned nb = (unsigned)((B.NE + kSpThreads - 1) / kSpThreads);
-    const unsigned pgrid = std::min<unsigned>(nb, (unsigned)num_sms * 4u);
-    cudaEventRecord(ev[0], st);
-    sx_sp_tables_kernel<<<8, 256, 0, st>>>(P, B.tables);
-    cudaEventRecord(ev[1], st);
-    sx_sp_heads_kernel<Dec><<<nb, kSpThreads, 0, st>>>(P, X, B);
-    cudaEventRecord(ev[2], st);
-    // queue2 holds the declined heads now (the members kernel appends its dependent members behind them): snapshot its
-    // length, then resolve those heads on the side stream while the members run
-    cudaMemcpyAsync(B.qcount2 + 1, B.qcount2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st);
+    {
+        // Same shared-memory carve-out as the prefilter (which needs the maximum): kernels that prefer different L1 /
+        // shared splits cannot share an SM, and these have to run beside the prefilter CTAs of the next piece.
+        static thread_local int done_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (done_dev != dev) {
+            const int co = cudaSharedmemCarveoutMaxShared;
+            cudaFuncSetAttribute(sx_sp_heads_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_members_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_declined_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_fix_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_late_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_ext_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_gather_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_snapshot_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_list_compact_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            done_dev = dev;
+        }
+    }
+    if (ev) cudaEventRecord(ev[1], st);
+    sx_sp_heads_kernel<Dec><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+    if (ev) cudaEventRecord(ev[2], st);
+    sx_sp_snapshot_kernel<<<1, 1, 0, st>>>(B.ctl);
     cudaEventRecord(evs[0], st);
     cudaStreamWaitEvent(side, evs[0], 0);
-    sx_sp_declined_kernel<Dec><<<std::min<unsigned>(pgrid, (unsigned)num_sms), kSpThreads, 0, side>>>(P, X, B, B.qcount2 + 1);
+    sx_sp_declined_kernel<Dec><<<std::min<unsigned>(L.grid_queue, 148u), kSpThreads, 0, side>>>(P, X, B);
     cudaEventRecord(evs[1], side);
-    sx_sp_members_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
-    cudaEventRecord(ev[3], st);
+    sx_sp_members_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
+    if (ev) cudaEventRecord(ev[3], st);
     cudaStreamWaitEvent(st, evs[1], 0);
-    sx_sp_fix_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
-    sx_sp_late_kernel<Dec><<<pgrid, kSpThreads, 0, st>>>(P, X, B);
-    cudaEventRecord(ev[4], st);
-    sx_sp_ext_kernel<Dec><<<nb, kSpThreads, 0, st>>>(P, X, B);
-    cudaEventRecord(ev[5], st);
-    sx_sp_scan_kernel<<<1, 1024, 0, st>>>(B.btot, nb, O.counters);
-    sx_sp_gather_kernel<Dec><<<nb, kSpThreads, 0, st>>>(P, O, X, B);
-    cudaEventRecord(ev[6], st);
+    sx_sp_fix_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
+    sx_sp_late_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
+    if (ev) cudaEventRecord(ev[4], st);
+    sx_sp_ext_kernel<Dec><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+    if (ev) cudaEventRecord(ev[5], st);
+    if (L.ev_scan_prev) cudaStreamWaitEvent(st, L.ev_scan_prev, 0);
+    sx_sp_scan_kernel<<<1, 1024, 0, st>>>(B, L.rec_cap, L.text_cap, L.out_cap, L.gather_parts);
+    if (L.ev_scan_done) cudaEventRecord(L.ev_scan_done, st);
+    for (uint32_t part = 0; part < L.gather_parts; ++part) {
+        sx_sp_gather_kernel<Dec><<<L.grid_chunks, kSpThreads, 0, st>>>(P, O, X, B, part, L.gather_parts);
+        if (L.ev_part) cudaEventRecord(L.ev_part[part], st);
+    }
+    if (ev) cudaEventRecord(ev[6], st);
     return cudaGetLastError();
 }
-constexpr uint32_t kSparseLaunches = 9;
+constexpr uint32_t kSparseLaunches = 9;  // heads, snapshot, declined, members, fix, late, ext, scan, gather
 
 }  // namespace sx

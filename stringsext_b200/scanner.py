@@ -68,6 +68,9 @@ class _CFinding(C.Structure):
     ]
 
 
+RANGE_PREFIX_UNKNOWN = 1  # SX_RANGE_PREFIX_UNKNOWN
+
+
 class ScanStats(C.Structure):
     _fields_ = [
         ("scan_kernel_ms", C.c_float),
@@ -80,7 +83,7 @@ class ScanStats(C.Structure):
         ("prefilter_used", C.c_uint32),
         ("tma_used", C.c_uint32),
         ("sparse_used", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("pieces", C.c_uint32),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
         ("n_records", C.c_uint64),
@@ -121,6 +124,10 @@ def load_library():
     L.sx_scanner_state_set_tma.argtypes = [C.c_void_p, C.c_int]
     L.sx_scanner_state_set_sparse.argtypes = [C.c_void_p, C.c_int]
     L.sx_scanner_state_set_direct_output.argtypes = [C.c_void_p, C.c_int]
+    L.sx_scanner_state_set_pieces.argtypes = [C.c_void_p, C.c_int]
+    L.sx_scan_range.restype = C.c_void_p
+    L.sx_scan_range.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                C.c_int, C.c_void_p]
     L.sx_scanner_state_last_window_list.restype = C.c_size_t
     L.sx_scanner_state_last_window_list.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_size_t]
     L.sx_finding_collection_from.restype = C.c_void_p
@@ -161,7 +168,7 @@ def exported_symbols() -> List[str]:
         "sx_device_count", "sx_scanner_state_new", "sx_scanner_state_free", "sx_scanner_state_reset", "sx_scanner_state_consumed_bytes",
         "sx_scanner_state_maybe_cut", "sx_scanner_state_leftover", "sx_finding_collection_from", "sx_scan_stream",
         "sx_fc_len", "sx_fc_get", "sx_fc_data", "sx_fc_first_byte_position", "sx_fc_str_buf_overflow", "sx_fc_free",
-        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_set_sparse", "sx_scanner_state_set_direct_output", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
+        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_set_sparse", "sx_scanner_state_set_direct_output", "sx_scanner_state_set_pieces", "sx_scan_range", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
     ]
 
 
@@ -274,6 +281,10 @@ class ScannerState:
         """False: records are downloaded and converted on the host instead of being written by the GPU as findings."""
         load_library().sx_scanner_state_set_direct_output(self._h, 1 if enabled else 0)
 
+    def set_pieces(self, pieces: int) -> None:
+        """Cut every call of the sparse pipeline into this many pieces (0: automatic); results never depend on it."""
+        load_library().sx_scanner_state_set_pieces(self._h, int(pieces))
+
     def set_sparse(self, enabled: bool) -> None:
         """False: the exact stage always runs as the block kernel (sx_exact_kernel), never as the sparse-list pipeline."""
         load_library().sx_scanner_state_set_sparse(self._h, int(enabled))  # 0 off, 1 default, 2 whenever possible
@@ -319,7 +330,7 @@ class ScannerState:
 
     def scan_stream(self, buf, is_last: bool = False, slice_len: int = 4096, input_file_id: Optional[int] = None,
                     device_ptr: Optional[int] = None, length: Optional[int] = None, cuda_stream: int = 0,
-                    raw: bool = False):
+                    raw: bool = False, lo: Optional[int] = None, hi: Optional[int] = None, prefix_unknown: bool = False):
         """The fold of `scan` over slice_len pieces.  `buf`: bytes / numpy uint8 array (host) or, with
         `device_ptr`+`length`, a device pointer on this state's device.  raw=True returns the C
         collection handle wrapped in RawCollection (no per-finding Python objects)."""
@@ -333,7 +344,11 @@ class ScannerState:
             p, n, isdev = C.cast(C.c_char_p(keep), C.c_void_p), len(keep), 0
         else:  # numpy array or anything with ctypes.data / nbytes
             p, n, isdev = C.c_void_p(buf.ctypes.data), int(buf.nbytes if length is None else length), 0
-        fc = L.sx_scan_stream(self._h, fid, p, n, slice_len, isdev, 1 if is_last else 0, C.c_void_p(cuda_stream))
+        if lo is None and hi is None:
+            fc = L.sx_scan_stream(self._h, fid, p, n, slice_len, isdev, 1 if is_last else 0, C.c_void_p(cuda_stream))
+        else:  # sx_scan_range: only the findings emitted while the bytes [lo, hi) are processed
+            fc = L.sx_scan_range(self._h, fid, p, n, slice_len, isdev, 1 if is_last else 0, int(lo or 0), n if hi is None else int(hi),
+                                 RANGE_PREFIX_UNKNOWN if prefix_unknown else 0, C.c_void_p(cuda_stream))
         del keep
         if raw:
             if not fc:

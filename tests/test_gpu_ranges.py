@@ -1,0 +1,123 @@
+"""GPU tests of the pieces / ranges machinery: a call cut into pipelined pieces, and one mission's
+stream scanned range by range (sx_scan_range), must give exactly the findings of the plain fold -- checked against the
+CPU oracle -- whatever the cut points are."""
+import dataclasses
+import random
+
+import pytest
+
+import corpus
+import stringsext_b200 as sx
+from helpers import M, oracle_state
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_findings(fc):
+    return [(f.position, int(f.position_precision), f.s, f.s_completes_previous_s) for f in fc.v]
+
+
+def oracle_findings(oc):
+    return [(f.position, f.precision, f.s, f.completes) for f in oc.v]
+
+
+def check_state(gs, os_):
+    assert gs.last_scan_run_leftover == os_.leftover
+    assert gs.last_run_str_was_printed_and_is_maybe_cut_str == os_.cut
+    assert gs.consumed_bytes == os_.consumed_bytes
+
+
+def make_buf(kind, size, enc, n, q, seed):
+    rng = random.Random(seed)
+    if kind == "rand":
+        buf = corpus.sx_mix_bytes(seed, 0, size)
+        corpus.plant(buf, seed, enc, n, q, density=1 << 12)
+        return buf.tobytes()
+    return corpus.gen(rng, kind, size, enc)
+
+
+CASES = [("utf-8", 10, 64, None, "rand"), ("utf-8", 4, 64, M.UBF_ALL_VALID, "text"), ("utf-8", 6, 32, M.UBF_ALL, "mixed"),
+         ("ascii", 4, 64, None, "rand"), ("koi8-r", 6, 64, None, "rand"), ("koi8-r", 3, 64, None, "text"),
+         ("windows-1252", 8, 16, None, "runs"), ("utf-8", 2, 64, None, "lowent")]
+
+
+@pytest.mark.parametrize("label,n,q,ubf,kind", CASES)
+def test_pieces_equal_the_fold(label, n, q, ubf, kind):
+    """The sparse pipeline cut into K pieces (prefilter of piece k+1 beside the exact stage of piece k, carry into each
+    piece from sx_range_carry_kernel): identical findings and ScannerState for every K, chained calls included."""
+    m = M.Mission.for_label(label, n, ubf=ubf, output_line_char_nb_max=q)
+    size = (3 << 20) + 4096 * 5 + 321
+    buf = make_buf(kind, size, m.encoding_id, n, q, 31 + n + q)
+    cuts = [0, 4096 * 311 + 7, len(buf)]
+    for pieces in (1, 3, 7, 32):
+        gs, os_ = sx.ScannerState(m), oracle_state(m)
+        gs.set_pieces(pieces)
+        for lo, hi in zip(cuts, cuts[1:]):
+            last = hi == len(buf) and pieces == 3
+            got = gpu_findings(gs.scan_stream(buf[lo:hi], last, 4096))
+            exp = oracle_findings(os_.scan_stream(buf[lo:hi], last, 4096))
+            assert gs.last_stats.sparse_used == 1
+            assert gs.last_stats.pieces == min(pieces, gs.last_stats.pieces)
+            assert got == exp, (label, pieces, lo, hi)
+            check_state(gs, os_)
+
+
+RANGE_CASES = CASES + [("utf-16le", 4, 64, M.UBF_ALL_VALID, "mixed"), ("utf-16be", 6, 32, None, "text"), ("utf-32le", 6, 64, None, "rand"),
+                       ("utf-16le", 10, 64, M.UBF_AFRICAN, "rand")]
+
+
+@pytest.mark.parametrize("label,n,q,ubf,kind", RANGE_CASES)
+def test_ranges_concatenate_to_the_whole_scan(label, n, q, ubf, kind):
+    """concat(sx_scan_range pieces) == sx_scan_stream == oracle, cut at random slice multiples; the ScannerState moves on
+    only with the range that reaches the end of the buffer, and then exactly like the fold."""
+    m = M.Mission.for_label(label, n, ubf=ubf, output_line_char_nb_max=q)
+    size = (2 << 20) + 4096 * 3 + 1234
+    buf = make_buf(kind, size, m.encoding_id, n, q, 77 + n + q)
+    os_ = oracle_state(m)
+    exp = oracle_findings(os_.scan_stream(buf, False, 4096))
+    rng = random.Random(5 + n)
+    for trial in range(3):
+        nslices = len(buf) // 4096
+        cuts = sorted({0, len(buf)} | {4096 * rng.randrange(1, nslices) for _ in range(rng.choice([1, 2, 5]))})
+        if trial == 0:
+            cuts = sorted(set(cuts) | {4096, 8192})  # tiny first ranges
+        gs = sx.ScannerState(m)
+        got = []
+        for lo, hi in zip(cuts, cuts[1:]):
+            before = gs.consumed_bytes
+            fc = gs.scan_stream(buf, False, 4096, lo=lo, hi=hi)
+            assert fc.first_byte_position == lo
+            got += gpu_findings(fc)
+            assert gs.consumed_bytes == (before if hi != len(buf) else before + len(buf))
+        assert got == exp, (label, cuts)
+        check_state(gs, os_)
+
+
+@pytest.mark.parametrize("label,n,q,ubf,kind", RANGE_CASES[:6] + RANGE_CASES[8:10])
+def test_range_with_unknown_prefix(label, n, q, ubf, kind):
+    """A rank of a range-sharded job only holds [range start - halo, range end): the carry into the range is found by the
+    walk back inside the halo (SX_RANGE_PREFIX_UNKNOWN), positions come from the state's counter_offset."""
+    m = M.Mission.for_label(label, n, ubf=ubf, output_line_char_nb_max=q)
+    size = (2 << 20) + 4096
+    buf = make_buf(kind, size, m.encoding_id, n, q, 99 + n + q)
+    lo, hi = 4096 * 200, 4096 * 390
+    whole = sx.ScannerState(m)
+    exp = gpu_findings(whole.scan_stream(buf, False, 4096, lo=lo, hi=hi))
+    for halo in (4096 * 64, 4096 * 8):
+        m2 = dataclasses.replace(m, counter_offset=lo - halo)
+        gs = sx.ScannerState(m2)
+        part = buf[lo - halo:hi]
+        got = gpu_findings(gs.scan_stream(part, False, 4096, lo=halo, hi=len(part), prefix_unknown=True))
+        assert got == exp, (label, halo)
+
+
+def test_range_argument_checks():
+    m = M.Mission.for_label("utf-8", 6)
+    gs = sx.ScannerState(m)
+    buf = bytes(20000)
+    for lo, hi in ((100, 4096), (0, 5000), (8192, 4096)):
+        with pytest.raises(sx.ScannerError):
+            gs.scan_stream(buf, False, 4096, lo=lo, hi=hi)
+    with pytest.raises(sx.ScannerError):
+        gs.scan_stream(buf, False, 4096, lo=0, hi=4096, prefix_unknown=True)
+    assert len(gs.scan_stream(buf, False, 4096, lo=4096, hi=4096).v) == 0
