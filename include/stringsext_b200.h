@@ -32,7 +32,10 @@ enum {
     SX_ENC_UTF_16BE = 3,
     SX_ENC_SINGLE_BYTE = 4, /* sb_table gives the upper half (koi8-r, ibm866, windows-125x, ...) */
     SX_ENC_UTF_32LE = 5,    /* extension: the reference rejects utf-32 (mission.rs:681-688) */
-    SX_ENC_UTF_32BE = 6
+    SX_ENC_UTF_32BE = 6,
+    SX_ENC_BIG5 = 7,   /* WHATWG Big5; index table generated from CPython's big5hkscs (tools/gen_multibyte_tables.py):
+                        * self-consistent with the oracle, not reference-pinned (no WHATWG index offline) */
+    SX_ENC_EUC_JP = 8  /* WHATWG EUC-JP; jis0208 / jis0212 from CPython's euc_jp, same caveat */
 };
 
 /* finding.rs:34-46 Precision */

@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libsx_oracle.so")
 
-ENC_X_USER_DEFINED, ENC_UTF_8, ENC_UTF_16LE, ENC_UTF_16BE, ENC_SINGLE_BYTE, ENC_UTF_32LE, ENC_UTF_32BE = range(7)
+ENC_X_USER_DEFINED, ENC_UTF_8, ENC_UTF_16LE, ENC_UTF_16BE, ENC_SINGLE_BYTE, ENC_UTF_32LE, ENC_UTF_32BE, ENC_BIG5, ENC_EUC_JP = range(9)
 BEFORE, EXACT, AFTER = 0, 1, 2
 
 

@@ -36,6 +36,9 @@ struct sxo_decoder {
     /* UTF-32 (extension) */
     uint8_t u32buf[4];
     int u32n;
+    /* Big5 / EUC-JP (WHATWG decoders): pending lead byte, EUC-JP jis0212 flag */
+    uint8_t mb_lead;
+    uint8_t mb_j0212;
 };
 
 static void dec_reset(sxo_decoder *d) {
@@ -48,6 +51,8 @@ static void dec_reset(sxo_decoder *d) {
     d->lead_byte = -1;
     d->pending_bmp = 0;
     d->u32n = 0;
+    d->mb_lead = 0;
+    d->mb_j0212 = 0;
 }
 
 static void dec_init(sxo_decoder *d, uint32_t enc, const uint16_t *tab) {
@@ -404,9 +409,138 @@ static int dec_utf32(sxo_decoder *d, int be, const uint8_t *src, size_t slen, ui
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Big5 and EUC-JP: the WHATWG Encoding Standard decoders (https://encoding.spec.whatwg.org/#big5-decoder,
+ * #euc-jp-decoder) in the calling convention of encoding_rs 0.8.34 (big5.rs / euc_jp.rs): `read` ends after the bytes
+ * the decoder consumed for a malformed sequence -- an ASCII byte that fails as a trail is NOT consumed (it is
+ * "prepended to the stream", i.e. re-read by the next call) --, an incomplete sequence at the end of the input stays
+ * pending, destination space is checked before every byte read (check_space_astral: 4 free bytes for Big5, whose
+ * pointers 1133 / 1135 / 1164 / 1166 decode to TWO code points; check_space_bmp: 3 for EUC-JP).
+ * The index tables are the library's (stringsext_b200/csrc/sx_mb_tables.inc, generated from CPython's codecs because
+ * the WHATWG index files are not available offline): PARITY UNPINNED w.r.t. encoding_rs' tables and `written`
+ * details -- the tests check "oracle == kernels on the same table" (SURVEY.md 8(c)).
+ * ---------------------------------------------------------------------------------------- */
+#include "../stringsext_b200/csrc/sx_mb_tables.inc"
+
+static int dec_big5(sxo_decoder *d, const uint8_t *src, size_t slen, uint8_t *dst, size_t dlen, int last, size_t *rd,
+                    size_t *wr) {
+    size_t sp = 0, dp = 0;
+    for (;;) {
+        if (sp >= slen) {
+            *rd = sp;
+            *wr = dp;
+            if (last && d->mb_lead) {
+                d->mb_lead = 0;
+                return R_MALFORMED;
+            }
+            return R_INPUT_EMPTY;
+        }
+        if (!(dp + 3 < dlen)) {
+            *rd = sp;
+            *wr = dp;
+            return R_OUTPUT_FULL;
+        }
+        uint8_t b = src[sp++];
+        if (d->mb_lead) {
+            uint32_t l = d->mb_lead;
+            d->mb_lead = 0;
+            if ((b >= 0x40 && b <= 0x7E) || (b >= 0xA1 && b <= 0xFE)) {
+                uint32_t ptr = (l - 0x81u) * 157u + (uint32_t)(b - (b < 0x7F ? 0x40 : 0x62));
+                if (ptr == 1133 || ptr == 1135 || ptr == 1164 || ptr == 1166) {
+                    dp += put_utf8(dst + dp, ptr < 1150 ? 0xCA : 0xEA);
+                    dp += put_utf8(dst + dp, (ptr == 1133 || ptr == 1164) ? 0x304 : 0x30C);
+                    continue;
+                }
+                uint32_t cp = kSxBig5Index[ptr];
+                if (cp) {
+                    dp += put_utf8(dst + dp, cp);
+                    continue;
+                }
+            }
+            if (b < 0x80) sp--; /* prepend the ASCII byte to the stream */
+            *rd = sp;
+            *wr = dp;
+            return R_MALFORMED;
+        }
+        if (b < 0x80) {
+            dst[dp++] = b;
+            continue;
+        }
+        if (b >= 0x81 && b <= 0xFE) {
+            d->mb_lead = b;
+            continue;
+        }
+        *rd = sp;
+        *wr = dp;
+        return R_MALFORMED;
+    }
+}
+
+static int dec_eucjp(sxo_decoder *d, const uint8_t *src, size_t slen, uint8_t *dst, size_t dlen, int last, size_t *rd,
+                     size_t *wr) {
+    size_t sp = 0, dp = 0;
+    for (;;) {
+        if (sp >= slen) {
+            *rd = sp;
+            *wr = dp;
+            if (last && d->mb_lead) {
+                d->mb_lead = 0;
+                d->mb_j0212 = 0;
+                return R_MALFORMED;
+            }
+            return R_INPUT_EMPTY;
+        }
+        if (!(dp + 2 < dlen)) {
+            *rd = sp;
+            *wr = dp;
+            return R_OUTPUT_FULL;
+        }
+        uint8_t b = src[sp++];
+        if (d->mb_lead == 0x8E && b >= 0xA1 && b <= 0xDF) {
+            d->mb_lead = 0;
+            dp += put_utf8(dst + dp, 0xFF61u - 0xA1u + b);
+            continue;
+        }
+        if (d->mb_lead == 0x8F && b >= 0xA1 && b <= 0xFE) {
+            d->mb_j0212 = 1;
+            d->mb_lead = b;
+            continue;
+        }
+        if (d->mb_lead) {
+            uint32_t l = d->mb_lead, cp = 0;
+            int three = d->mb_j0212;
+            d->mb_lead = 0;
+            d->mb_j0212 = 0;
+            if (l >= 0xA1 && l <= 0xFE && b >= 0xA1 && b <= 0xFE)
+                cp = (three ? kSxJis0212Index : kSxJis0208Index)[(l - 0xA1u) * 94u + (uint32_t)(b - 0xA1)];
+            if (cp) {
+                dp += put_utf8(dst + dp, cp);
+                continue;
+            }
+            if (b < 0x80) sp--;
+            *rd = sp;
+            *wr = dp;
+            return R_MALFORMED;
+        }
+        if (b < 0x80) {
+            dst[dp++] = b;
+            continue;
+        }
+        if (b == 0x8E || b == 0x8F || (b >= 0xA1 && b <= 0xFE)) {
+            d->mb_lead = b;
+            continue;
+        }
+        *rd = sp;
+        *wr = dp;
+        return R_MALFORMED;
+    }
+}
+
 static int dec_decode(sxo_decoder *d, const uint8_t *src, size_t slen, uint8_t *dst, size_t dlen, int last, size_t *rd,
                       size_t *wr) {
     switch (d->enc) {
+    case SXO_ENC_BIG5: return dec_big5(d, src, slen, dst, dlen, last, rd, wr);
+    case SXO_ENC_EUC_JP: return dec_eucjp(d, src, slen, dst, dlen, last, rd, wr);
     case SXO_ENC_X_USER_DEFINED: return dec_xud(src, slen, dst, dlen, rd, wr);
     case SXO_ENC_UTF_8: return dec_utf8(d, src, slen, dst, dlen, last, rd, wr);
     case SXO_ENC_UTF_16LE: return dec_utf16(d, 0, src, slen, dst, dlen, last, rd, wr);

@@ -38,7 +38,9 @@ enum {
     SXO_ENC_UTF_16BE = 3,
     SXO_ENC_SINGLE_BYTE = 4, /* table driven (koi8-r, ibm866, ...); table passed at state creation */
     SXO_ENC_UTF_32LE = 5,    /* EXTENSION: not in encoding_rs / the reference */
-    SXO_ENC_UTF_32BE = 6     /* EXTENSION */
+    SXO_ENC_UTF_32BE = 6,    /* EXTENSION */
+    SXO_ENC_BIG5 = 7,        /* WHATWG Big5 decoder over the library's generated index (parity unpinned, see sx_oracle.c) */
+    SXO_ENC_EUC_JP = 8       /* WHATWG EUC-JP decoder, same caveat */
 };
 
 enum { SXO_BEFORE = 0, SXO_EXACT = 1, SXO_AFTER = 2 }; /* finding.rs:34-46 */

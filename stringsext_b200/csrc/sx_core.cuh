@@ -43,7 +43,9 @@ enum : uint32_t {
     ENC_UTF16BE = 3,
     ENC_SB = 4,       // single-byte, table driven
     ENC_UTF32LE = 5,  // extension (no reference semantics)
-    ENC_UTF32BE = 6
+    ENC_UTF32BE = 6,
+    ENC_BIG5 = 7,     // WHATWG Big5 (lead 81-FE, trail 40-7E | A1-FE), table: sx_mb_tables.inc
+    ENC_EUCJP = 8     // WHATWG EUC-JP (jis0208, 8E kana, 8F + jis0212)
 };
 
 enum : uint8_t { PREC_BEFORE = 0, PREC_EXACT = 1, PREC_AFTER = 2 };  // finding.rs:34-46
@@ -52,7 +54,9 @@ enum : uint8_t { PREC_BEFORE = 0, PREC_EXACT = 1, PREC_AFTER = 2 };  // finding.
 enum : uint8_t { K_L = 0, K_C = 1, K_UNKNOWN = 2 };
 enum : uint8_t {
     CF_HOSTCARRY = 1,  // leftover starts with text carried in the host ScannerState
-    CF_GREP = 2        // leftover contains the mission's grep_char (helper.rs:252-254)
+    CF_GREP = 2,       // leftover contains the mission's grep_char (helper.rs:252-254)
+    CF_HALF = 4        // leftover starts with the SECOND code point of a Big5 two-code-point pair (its first input bytes
+                       // are the pair; the pair's first code point is not part of the text)
 };
 struct Carry {
     uint8_t kind;        // K_L: leftover of k chars (k may be 0) and cut == false; K_C: cut == true
@@ -68,7 +72,8 @@ SX_HD Carry carry_unknown() { return Carry{K_UNKNOWN, 0, 0, 0, 0, 0}; }
 SX_HD bool carry_is_null(const Carry& c) { return c.kind == K_L && c.k == 0; }
 
 // One finding as it leaves the GPU (before text materialisation).
-enum : uint32_t { RF_COMPLETES = 1, RF_HOSTCARRY = 2, RF_LEFTOVER = 4 };
+enum : uint32_t { RF_COMPLETES = 1, RF_HOSTCARRY = 2, RF_LEFTOVER = 4,
+                  RF_HALFSTART = 8 /* the text starts with the second code point of the pair at in_start (Big5) */ };
 struct Record {
     uint64_t position;  // Finding.position (absolute, includes counter_offset)   finding.rs:61
     int64_t in_start;   // first input byte of the text, buffer-relative (may reach into the virtual prefix)
@@ -97,6 +102,11 @@ struct ScanParams {
     uint32_t same_block;     // Mission.require_same_unicode_block
     uint32_t general;        // grep_char / same_block / chars_min_nb > q: general automaton + dual-simulation classification
     uint16_t sb_table[128];
+    // Big5 / EUC-JP index tables (device memory in the kernels, host memory in the test harness): mb_a = Big5 index
+    // or jis0208, mb_b = jis0212
+    const uint32_t* mb_a;
+    const uint32_t* mb_b;
+    uint32_t* mb_fail;  // set to 1 when a decoder-state walk ran into its bound (the call then fails loudly)
 };
 
 // Byte source over the whole stream incl. the virtual prefix.  Used on the rare paths
@@ -182,6 +192,9 @@ struct WinAuto {
     bool grep_ok;    // helper.rs:215: current run holds the grep_char (always true without one)
     bool qfull;      // the run reached q chars; whether it touches the right boundary is known at the next event
     bool dead;       // SplitStr::next returned None (helper.rs:410-415): the rest of the segment is ignored
+    bool next_half2;   // the char about to be reported is the second code point of a two-code-point pair (Big5)
+    bool run_half;     // the current run starts with such a char
+    bool left_half;
     uint32_t last_mb;  // helper.rs:221: lead byte of the last multi-byte char this SplitStr::next() call saw (may be stale)
     uint32_t run_mb;   // ... of the current run only: what a re-scan of the run as leftover will see
     uint32_t run_n, run_out;
@@ -217,6 +230,7 @@ struct WinAuto {
         run_n = run_out = 0; run_in_start = run_in_end = 0; run_hostcarry = false;
         grep_ok = true; qfull = false; dead = false; last_mb = 0; run_mb = 0;
         seg_pos = 0; prec = PREC_EXACT; probe_pending = false; last_cut = false; at_left = true;
+        next_half2 = false; run_half = false; left_half = false;
     }
     SX_HD bool grep_reset() const { return P->grep_char < 0; }  // helper.rs:215 / :330
 
@@ -233,7 +247,7 @@ struct WinAuto {
         cut = false;
         last_cut = cont;
         at_left = true;
-        run_n = 0; run_out = 0; run_hostcarry = false;
+        run_n = 0; run_out = 0; run_hostcarry = false; run_half = false;
         grep_ok = grep_reset(); last_mb = 0; run_mb = 0; qfull = false; dead = false;
         prec = PREC_EXACT;
         probe_pending = probe_possible && (pos == slice_start);
@@ -244,6 +258,7 @@ struct WinAuto {
             run_in_start = pos - (int64_t)kin->in_bytes;
             run_in_end = pos - pend_len;
             run_hostcarry = (kin->flags & CF_HOSTCARRY) != 0;
+            run_half = (kin->flags & CF_HALF) != 0;
             grep_ok = grep_reset() || (kin->flags & CF_GREP) != 0;
             last_mb = kin->aux;
             run_mb = kin->aux;
@@ -262,7 +277,7 @@ struct WinAuto {
             r.in_len = (uint32_t)(run_in_end - run_in_start);
             r.text_len = run_out;
             r.text_off = text_off;
-            r.flags = (completes ? RF_COMPLETES : 0u) | (run_hostcarry ? RF_HOSTCARRY : 0u);
+            r.flags = (completes ? RF_COMPLETES : 0u) | (run_hostcarry ? RF_HOSTCARRY : 0u) | (run_half ? (uint32_t)RF_HALFSTART : 0u);
             r.precision = prec;
             *wr++ = r;
             text_off += run_out;
@@ -276,14 +291,14 @@ struct WinAuto {
     SX_HD void keep_leftover() {  // an `again` chunk, finding_collection.rs:281-284
         if (m == 1 && !in_first_run) s1_later_yield = true;
         has_left = true;
-        left_k = run_n; left_out = run_out; left_in_start = run_in_start; left_hostcarry = run_hostcarry;
+        left_k = run_n; left_out = run_out; left_in_start = run_in_start; left_hostcarry = run_hostcarry; left_half = run_half;
         left_grep = grep_ok && P->grep_char >= 0;
         left_mb = P->same_block ? run_mb : 0u;  // only the same-unicode-block rule reads it; the leftover is re-scanned from scratch
         cut = false;
         prec = PREC_AFTER;
     }
     SX_HD void new_run() {  // a fresh SplitStr::next() call
-        run_n = 0; run_out = 0; run_hostcarry = false;
+        run_n = 0; run_out = 0; run_hostcarry = false; run_half = false;
         grep_ok = grep_reset();
         last_mb = 0;
         run_mb = 0;
@@ -338,7 +353,7 @@ struct WinAuto {
             pass = false;
         }
         if (pass) {
-            if (run_n == 0) { run_in_start = cstart; }
+            if (run_n == 0) { run_in_start = cstart; run_half = next_half2; }
             run_n++;
             run_out += ul;
             run_in_end = cend;
@@ -392,7 +407,7 @@ struct WinAuto {
         if (has_left) {
             Carry c;
             c.kind = K_L;
-            c.flags = (uint8_t)((left_hostcarry ? CF_HOSTCARRY : 0) | (left_grep ? CF_GREP : 0));
+            c.flags = (uint8_t)((left_hostcarry ? CF_HOSTCARRY : 0) | (left_grep ? CF_GREP : 0) | (left_half ? CF_HALF : 0));
             c.k = (uint16_t)left_k;
             c.in_bytes = (uint32_t)(boundary - left_in_start);
             c.out_bytes = left_out;
@@ -558,6 +573,113 @@ struct DecUtf32 {  // EXTENSION: no reference semantics (mission.rs:681-688 reje
     }
     template <class E> SX_HD void eof(E&) { nb = 0; acc = 0; }
 };
+
+// ------------------------------------------------------------------------------------------
+// Big5 and EUC-JP (WHATWG Encoding Standard decoders, as encoding_rs implements them; tables from
+// tools/gen_multibyte_tables.py -- parity "self-consistent").
+// Lead / trail roles depend on the parse history, so the state at a window start is found by walking back to the last
+// byte that leaves the decoder neutral whatever came before it (Big5: a byte outside 81-FE; EUC-JP: a byte outside
+// {8E, 8F, A1-FE}) and parsing forward from there.  The walk is bounded: kMbMaxBack bytes without
+// such a byte (never seen outside adversarial input) raise SX_ERR_UNSUPPORTED through mb_walk_failed.
+// ------------------------------------------------------------------------------------------
+constexpr int64_t kMbMaxBack = 256 << 10;
+SX_HD bool big5_is_run_byte(uint32_t b) { return b >= 0x81 && b <= 0xFE; }
+SX_HD bool big5_is_trail(uint32_t b) { return (b >= 0x40 && b <= 0x7E) || (b >= 0xA1 && b <= 0xFE); }
+SX_HD uint32_t big5_pointer(uint32_t lead, uint32_t trail) { return (lead - 0x81u) * 157u + (trail - (trail < 0x7Fu ? 0x40u : 0x62u)); }
+// the four pointers that decode to TWO code points (U+00CA / U+00EA followed by U+0304 / U+030C)
+SX_HD bool big5_is_double(uint32_t ptr) { return ptr == 1133u || ptr == 1135u || ptr == 1164u || ptr == 1166u; }
+SX_HD uint32_t big5_double_first(uint32_t ptr) { return ptr < 1150u ? 0xCAu : 0xEAu; }
+SX_HD uint32_t big5_double_second(uint32_t ptr) { return (ptr == 1133u || ptr == 1164u) ? 0x304u : 0x30Cu; }
+SX_HD bool eucjp_is_run_byte(uint32_t b) { return b == 0x8E || b == 0x8F || (b >= 0xA1 && b <= 0xFE); }
+
+struct DecBig5 {
+    uint32_t lead;  // pending lead byte, 0: neutral
+    static constexpr bool kStateful = true;
+    SX_HD int32_t pending_len() const { return lead ? 1 : 0; }
+    template <class S> SX_HD void init(const ScanParams& P, const S& src, int64_t ws) {
+        lead = 0;
+        const int64_t lo_off = -(int64_t)P.npend;
+        int64_t o = ws - 1;
+        while (o >= lo_off && big5_is_run_byte(src.get(o))) {
+            if (ws - o > kMbMaxBack) { if (P.mb_fail) *P.mb_fail = 1u; break; }
+            --o;
+        }
+        // bytes (o, ws) are all 81-FE and pair up, mapped or not (an unmapped pair with a non-ASCII trail is consumed whole)
+        if (((ws - 1 - o) & 1) != 0) lead = src.get(ws - 1);
+    }
+    template <class E> SX_HD void step(const ScanParams& P, uint32_t b, int64_t pos, E& e) {
+        if (lead) {
+            const uint32_t l = lead;
+            lead = 0;
+            if (big5_is_trail(b)) {
+                const uint32_t ptr = big5_pointer(l, b);
+                if (big5_is_double(ptr)) {
+                    e.cp(big5_double_first(ptr));
+                    e.ch(0xC3, 2, pos - 1, pos + 1);   // U+00CA / U+00EA
+                    e.cp(big5_double_second(ptr));
+                    e.ch2(0xCC, 2, pos - 1, pos + 1);  // U+0304 / U+030C
+                    return;
+                }
+                const uint32_t cp = P.mb_a[ptr];
+                if (cp) { e.cp(cp); e.ch(utf8_lead_of_cp(cp), utf8_len_of_cp(cp), pos - 1, pos + 1); return; }
+            }
+            if (b >= 0x80) { e.mal(pos + 1); return; }
+            e.mal(pos);  // an ASCII byte is not consumed: it starts the next segment
+        }
+        if (b < 0x80) { e.cp(b); e.ch(b, 1, pos, pos + 1); return; }
+        if (b == 0x80 || b == 0xFF) { e.mal(pos + 1); return; }
+        lead = b;
+    }
+    template <class E> SX_HD void eof(E&) { lead = 0; }
+};
+
+struct DecEucJp {
+    uint32_t lead;   // pending byte: 8E, 8F or A1-FE (with j0212: the byte after 8F), 0: neutral
+    uint32_t j0212;
+    static constexpr bool kStateful = true;
+    SX_HD int32_t pending_len() const { return lead ? (j0212 ? 2 : 1) : 0; }
+    // state transition without events (used by init to parse forward from the last neutral point)
+    SX_HD void advance(uint32_t b) {
+        if (lead == 0x8F && !j0212 && b >= 0xA1 && b <= 0xFE) { j0212 = 1; lead = b; return; }
+        if (lead) { lead = 0; j0212 = 0; return; }  // whatever run byte follows a lead is consumed with it
+        lead = b;
+    }
+    template <class S> SX_HD void init(const ScanParams& P, const S& src, int64_t ws) {
+        lead = 0; j0212 = 0;
+        const int64_t lo_off = -(int64_t)P.npend;
+        int64_t o = ws - 1;
+        while (o >= lo_off && eucjp_is_run_byte(src.get(o))) {
+            if (ws - o > kMbMaxBack) { if (P.mb_fail) *P.mb_fail = 1u; break; }
+            --o;
+        }
+        for (int64_t p = o + 1; p < ws; ++p) advance(src.get(p));
+    }
+    template <class E> SX_HD void step(const ScanParams& P, uint32_t b, int64_t pos, E& e) {
+        if (lead == 0x8E && !j0212 && b >= 0xA1 && b <= 0xDF) {  // U+FF61..U+FF9F
+            lead = 0;
+            e.cp(0xFF61u - 0xA1u + b);
+            e.ch(0xEF, 3, pos - 1, pos + 1);
+            return;
+        }
+        if (lead == 0x8F && !j0212 && b >= 0xA1 && b <= 0xFE) { j0212 = 1; lead = b; return; }
+        if (lead) {
+            const uint32_t l = lead, three = j0212;
+            lead = 0; j0212 = 0;
+            if (l >= 0xA1 && l <= 0xFE && b >= 0xA1 && b <= 0xFE) {
+                const uint32_t cp = (three ? P.mb_b : P.mb_a)[(l - 0xA1u) * 94u + (b - 0xA1u)];
+                if (cp) { e.cp(cp); e.ch(utf8_lead_of_cp(cp), utf8_len_of_cp(cp), pos - (three ? 2 : 1), pos + 1); return; }
+            }
+            if (b >= 0x80) { e.mal(pos + 1); return; }
+            e.mal(pos);  // an ASCII byte is not consumed: it starts the next segment
+        }
+        if (b < 0x80) { e.cp(b); e.ch(b, 1, pos, pos + 1); return; }
+        if (eucjp_is_run_byte(b)) { lead = b; return; }
+        e.mal(pos + 1);
+    }
+    template <class E> SX_HD void eof(E&) { lead = 0; j0212 = 0; }
+};
+SX_HD void mb_set_state(DecBig5& d, uint32_t lead, uint32_t) { d.lead = lead; }
+SX_HD void mb_set_state(DecEucJp& d, uint32_t lead, uint32_t j) { d.lead = lead; d.j0212 = j; }
 
 // ------------------------------------------------------------------------------------------
 // Precision::Before probe (finding_collection.rs:176-207), literal emulation of the 8-byte
@@ -726,6 +848,58 @@ SX_HD_NOINLINE bool probe_utf32(const GlobalSrc& g, int64_t slice_start, int64_t
     return false;
 }
 
+// Text of decoded chars (Big5 / EUC-JP): the decoders report every code point through cp() before ch().
+struct MbTextEmit {
+    uint8_t* dst;
+    uint32_t dp, cap;
+    uint32_t skip;   // code points to drop at the front (a text that starts with the second half of a Big5 pair)
+    uint32_t last;
+    bool stop;
+    SX_HD void cp(uint32_t c) { last = c; }
+    SX_HD void ch(uint32_t, uint32_t ul, int64_t, int64_t) {
+        if (stop) return;
+        if (skip) { --skip; return; }
+        if (dp + ul > cap) { stop = true; return; }
+        dp += put_utf8(dst + dp, last);
+    }
+    SX_HD void ch2(uint32_t lb, uint32_t ul, int64_t a, int64_t b) { ch(lb, ul, a, b); }
+    SX_HD void mal(int64_t) { stop = true; }
+};
+// Decode from `pos` with decoder state `d` into at most `cap` bytes, stopping at the first malformed sequence or `end`.
+// need_free != 0: like encoding_rs, require that many free bytes before every byte read (check_space_bmp: 3,
+// check_space_astral: 4); otherwise stop when a char no longer fits.  Returns the bytes written.
+template <class Dec>
+SX_HD uint32_t mb_decode_some(const ScanParams& P, const GlobalSrc& g, Dec d, int64_t pos, int64_t end, uint8_t* dst, uint32_t cap,
+                              uint32_t need_free) {
+    MbTextEmit te{dst, 0, cap, 0, 0, false};
+    for (; pos < end && !te.stop; ++pos) {
+        if (need_free ? (te.dp + need_free > cap) : (te.dp + 4 > cap)) break;
+        d.step(P, g.get(pos), pos, te);
+    }
+    return te.dp;
+}
+template <class Dec> struct MbTraits { static constexpr uint32_t kNeedFree = 3; };
+template <> struct MbTraits<DecBig5> { static constexpr uint32_t kNeedFree = 4; };  // astral / two code points
+// Precision::Before probe for the lead / trail encodings (finding_collection.rs:176-207), literal: a fresh decoder over
+// the slice into 8 bytes vs what the real first decoder call of the slice (the first window, real pending state) wrote.
+template <class Dec>
+SX_HD_NOINLINE bool probe_mb(const ScanParams& P, const GlobalSrc& g, int64_t slice_start, int64_t slice_end, int64_t win_end,
+                             uint32_t lead0, uint32_t j0, const Carry& slice_left) {
+    if (slice_left.kind == K_L && slice_left.k > 0) return true;  // leftover prepended: Before anyway
+    if (lead0 == 0 && win_end - slice_start >= 24) return false;  // same state, same bytes, and the window covers the probe
+    uint8_t fb[16], ob[16];
+    for (int i = 0; i < 16; ++i) { fb[i] = 0; ob[i] = 0; }
+    Dec fresh, real;
+    mb_set_state(fresh, 0, 0);
+    mb_set_state(real, lead0, j0);
+    const uint32_t w2 = mb_decode_some<Dec>(P, g, fresh, slice_start, slice_end, fb, 8, MbTraits<Dec>::kNeedFree);
+    if (w2 == 0) return true;
+    (void)mb_decode_some<Dec>(P, g, real, slice_start, win_end, ob, 12, 0);
+    for (uint32_t i = 0; i < w2; ++i)
+        if (ob[i] != fb[i]) return true;
+    return false;
+}
+
 // ------------------------------------------------------------------------------------------
 // Window driver.
 // ------------------------------------------------------------------------------------------
@@ -767,7 +941,20 @@ template <bool BE> struct ProbeImpl<DecUtf32<BE>> {
     }
 };
 
+template <> struct ProbeImpl<DecBig5> {
+    SX_HD static bool run(const ProbeCtx<DecBig5>& c, bool, const Carry& slice_left) {
+        return probe_mb<DecBig5>(*c.P, *c.g, c.geo->slice_start, c.geo->slice_end, c.geo->we, c.s0, c.s1, slice_left);
+    }
+};
+template <> struct ProbeImpl<DecEucJp> {
+    SX_HD static bool run(const ProbeCtx<DecEucJp>& c, bool, const Carry& slice_left) {
+        return probe_mb<DecEucJp>(*c.P, *c.g, c.geo->slice_start, c.geo->slice_end, c.geo->we, c.s0, c.s1, slice_left);
+    }
+};
+
 template <class Dec> SX_HD void probe_capture(ProbeCtx<Dec>& c, const Dec& d) { (void)c; (void)d; }
+SX_HD void probe_capture(ProbeCtx<DecBig5>& c, const DecBig5& d) { c.s0 = d.lead; c.s1 = 0; }
+SX_HD void probe_capture(ProbeCtx<DecEucJp>& c, const DecEucJp& d) { c.s0 = d.lead; c.s1 = d.j0212; }
 SX_HD void probe_capture(ProbeCtx<DecUtf8>& c, const DecUtf8& d) { c.pend0 = d.pending_len(); }
 template <bool BE> SX_HD void probe_capture(ProbeCtx<DecUtf16<BE>>& c, const DecUtf16<BE>& d) {
     c.s0 = d.has_lead; c.s1 = d.lead_byte; c.s2 = d.lead_sur;
@@ -781,6 +968,13 @@ struct Emit {
     SX_HD void ch(uint32_t lb, uint32_t ul, int64_t cs, int64_t ce) {
         const ProbeCtx<Dec>* c = pc;
         A->on_char(lb, ul, cs, ce, [c](bool first_segment, Carry slice_left) { return ProbeImpl<Dec>::run(*c, first_segment, slice_left); });
+    }
+    SX_HD void cp(uint32_t) {}  // the scanner only needs the UTF-8 lead byte and length of a char
+    // second code point of a two-code-point pair (Big5): same input bytes as the first one
+    SX_HD void ch2(uint32_t lb, uint32_t ul, int64_t cs, int64_t ce) {
+        A->next_half2 = true;
+        ch(lb, ul, cs, ce);
+        A->next_half2 = false;
     }
     SX_HD void mal(int64_t next) { A->on_malformed(next); }
 };
@@ -989,6 +1183,22 @@ SX_HD uint32_t transcode_range(const ScanParams& P, const GlobalSrc& g, int64_t 
         }
         break;
     }
+    case ENC_BIG5: {
+        DecBig5 d;
+        d.lead = 0;
+        MbTextEmit te{dst, 0, 0xFFFFFFFFu, 0, 0, false};
+        for (int64_t p = s; p < e && !te.stop; ++p) d.step(P, g.get(p), p, te);
+        dp = te.dp;
+        break;
+    }
+    case ENC_EUCJP: {
+        DecEucJp d;
+        d.lead = 0; d.j0212 = 0;
+        MbTextEmit te{dst, 0, 0xFFFFFFFFu, 0, 0, false};
+        for (int64_t p = s; p < e && !te.stop; ++p) d.step(P, g.get(p), p, te);
+        dp = te.dp;
+        break;
+    }
     case ENC_UTF32LE:
     case ENC_UTF32BE: {
         const bool be = P.enc == ENC_UTF32BE;
@@ -1005,6 +1215,18 @@ SX_HD uint32_t transcode_range(const ScanParams& P, const GlobalSrc& g, int64_t 
 
 
 
+// The text of one record.  Big5: a text may start with the second code point of a two-code-point pair (RF_HALFSTART) or
+// end with the first one (then text_len stops the output early); every other text is exactly its input range.
+SX_HD uint32_t transcode_record(const ScanParams& P, const GlobalSrc& g, const Record& r, uint8_t* dst) {
+    if (P.enc != ENC_BIG5) return transcode_range(P, g, r.in_start, r.in_len, dst);
+    DecBig5 d;
+    d.lead = 0;
+    MbTextEmit te{dst, 0, r.text_len, (r.flags & RF_HALFSTART) ? 1u : 0u, 0, false};
+    const int64_t e = r.in_start + r.in_len;
+    for (int64_t p = r.in_start; p < e && !te.stop; ++p) d.step(P, g.get(p), p, te);
+    return te.dp;
+}
+
 // ------------------------------------------------------------------------------------------
 // Prefilter (kernel sx_prefilter_kernel): a conservative per-byte "could belong to a passing
 // char" flag G at 32-byte-block granularity of the byte value (top 3 bits), cheap enough for
@@ -1014,7 +1236,7 @@ SX_HD uint32_t transcode_range(const ScanParams& P, const GlobalSrc& g, int64_t 
 // DESIGN.md "Prefilter" for the proof that every other window emits nothing and does not
 // influence any carry.
 // ------------------------------------------------------------------------------------------
-enum : uint32_t { PF_BYTE = 0, PF_UTF8 = 1, PF_UNIT = 2 };
+enum : uint32_t { PF_BYTE = 0, PF_UTF8 = 1, PF_UNIT = 2, PF_PAIR = 3 };
 constexpr uint32_t kPrefTileWin = 256;
 struct PrefCfg {
     uint32_t enabled;
@@ -1030,6 +1252,11 @@ struct PrefCfg {
     uint32_t refine;  // PF_UTF8: a long good-byte run only counts if it holds >= n_chars non-continuation bytes
     uint32_t pre_bytes;  // pre-roll length: longest possible trailing good run of an uninteresting window + slack
     uint32_t kill_trail; // --grep-char missions: a window behind >= this many trailing good bytes is listed (0: rule off)
+    // PF_PAIR (Big5, EUC-JP): per byte value, bit 0: a passing single-byte char, bit 1: may be the lead (or, EUC-JP, the
+    // middle byte) of a passing multi-byte char, bit 2: may be a trail byte.  A byte is good when it is a passing
+    // single-byte char, a lead candidate followed by a trail candidate, or a trail candidate behind a lead candidate --
+    // whatever the real parse is, every byte of a passing char is good.
+    uint8_t pair_cls[256];
 };
 
 // Reference (byte-wise) definition of G; the SWAR kernel must produce exactly these flags.
@@ -1050,6 +1277,13 @@ SX_HD bool pref_good(const ScanParams& P, const PrefCfg& c, const S& src, int64_
         const uint32_t pb = src.get(i - 1);
         if (pb >= 0xC0) return ((c.blkH >> (pb >> 5)) & 1u) != 0;
         return c.multi && pb >= 0x80;
+    }
+    if (c.family == PF_PAIR) {
+        const uint32_t k = c.pair_cls[b];
+        if (k & 1u) return true;
+        if ((k & 2u) && (i + 1 >= we || (c.pair_cls[src.get(i + 1)] & 4u))) return true;
+        if ((k & 4u) && (i - 1 < ws || (c.pair_cls[src.get(i - 1)] & 2u))) return true;
+        return false;
     }
     // PF_UNIT
     int64_t rel = i - (int64_t)P.align;
@@ -1094,10 +1328,12 @@ SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& sr
 
 // Host-side: derive the prefilter configuration of a mission (used by the C ABI and by the
 // test harness, so both classify identically).
-inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned) {
+// mb_a / mb_b: HOST copies of the Big5 / EUC-JP index tables (P.mb_a / P.mb_b are device pointers in the product).
+inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned, const uint32_t* mb_a = nullptr, const uint32_t* mb_b = nullptr) {
     PrefCfg c;
     c.enabled = 0; c.family = PF_BYTE; c.blkA = 0; c.blkH = 0; c.multi = 0; c.T = P.n; c.unit = 1; c.hi_pos = 0;
     c.n_chars = P.n; c.refine = 0; c.pre_bytes = 0; c.kill_trail = 0;
+    for (uint32_t k = 0; k < 256; ++k) c.pair_cls[k] = 0;
     for (uint32_t k = 0; k < 4; ++k) {
         const uint64_t word = k < 2 ? P.af_lo : P.af_hi;
         if ((word >> ((k & 1) * 32)) & 0xFFFFFFFFull) c.blkA |= 1u << k;
@@ -1137,6 +1373,34 @@ inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned) {
     case ENC_UTF32BE:
         c.family = PF_UNIT; c.unit = 4; c.hi_pos = P.enc == ENC_UTF32LE ? 3 : 0;
         c.blkH = (P.af_lo | P.af_hi | P.ubf) ? 1u : 0u;
+        break;
+    case ENC_BIG5:
+        c.family = PF_PAIR;
+        for (uint32_t b = 0; b < 0x80; ++b) c.pair_cls[b] = pass_filter(P, b) ? 1u : 0u;
+        for (uint32_t b = 0x40; b <= 0xFE; ++b) if (big5_is_trail(b)) c.pair_cls[b] |= 4u;
+        for (uint32_t lead = 0x81; lead <= 0xFE && mb_a; ++lead)
+            for (uint32_t t = 0x40; t <= 0xFE; ++t) {
+                if (!big5_is_trail(t)) continue;
+                const uint32_t ptr = big5_pointer(lead, t);
+                const bool ok = big5_is_double(ptr) ? (pass_lead(0xC3) || pass_lead(0xCC)) : (mb_a[ptr] != 0 && pass_cp(mb_a[ptr]));
+                if (ok) { c.pair_cls[lead] |= 2u; break; }
+            }
+        break;
+    case ENC_EUCJP:
+        c.family = PF_PAIR;
+        for (uint32_t b = 0; b < 0x80; ++b) c.pair_cls[b] = pass_filter(P, b) ? 1u : 0u;
+        for (uint32_t b = 0xA1; b <= 0xFE; ++b) c.pair_cls[b] |= 4u;
+        if (pass_lead(0xEF)) c.pair_cls[0x8E] |= 2u;  // half-width katakana U+FF61..U+FF9F
+        for (uint32_t lead = 0xA1; lead <= 0xFE && mb_a && mb_b; ++lead) {
+            bool ok8 = false, ok12 = false;
+            for (uint32_t t = 0; t < 94; ++t) {
+                const uint32_t c8 = mb_a[(lead - 0xA1u) * 94u + t], c12 = mb_b[(lead - 0xA1u) * 94u + t];
+                ok8 = ok8 || (c8 != 0 && pass_cp(c8));
+                ok12 = ok12 || (c12 != 0 && pass_cp(c12));
+            }
+            if (ok8 || ok12) c.pair_cls[lead] |= 2u;      // lead of a jis0208 char / middle byte of a jis0212 char
+            if (ok12) c.pair_cls[0x8F] |= 2u;
+        }
         break;
     }
     c.T = P.n * c.unit;

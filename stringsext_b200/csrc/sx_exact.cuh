@@ -563,7 +563,8 @@ __device__ Carry block_pass(const ScanParams& P, const ScanOut& O, const ExactCf
             r.in_len = kout.in_bytes - (uint32_t)S.last_npend;
             r.text_len = kout.out_bytes;
             r.text_off = bt + to;
-            r.flags = RF_LEFTOVER | ((kout.flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u);
+            r.flags = RF_LEFTOVER | ((kout.flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u) |
+                      ((kout.flags & CF_HALF) ? (uint32_t)RF_HALFSTART : 0u);
             r.precision = 0;
             O.recs[br + ro] = r;
         }
@@ -713,7 +714,8 @@ struct SparseLaunchCfg;
                                   const SparseLaunchCfg& L, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side, cudaEvent_t* evs); \
     bool has_sparse_##N();
 SX_DECLARE_INST(0) SX_DECLARE_INST(1) SX_DECLARE_INST(2) SX_DECLARE_INST(3) SX_DECLARE_INST(4) SX_DECLARE_INST(5) SX_DECLARE_INST(6)
+SX_DECLARE_INST(7) SX_DECLARE_INST(8)
 #undef SX_DECLARE_INST
-constexpr int kNumInst = 7;
+constexpr int kNumInst = 9;
 
 }  // namespace sx

@@ -19,8 +19,12 @@ namespace sx {
 #define SX_DEC DecUtf32<false>
 #elif SX_INST == 6
 #define SX_DEC DecUtf32<true>
+#elif SX_INST == 7
+#define SX_DEC DecBig5
+#elif SX_INST == 8
+#define SX_DEC DecEucJp
 #else
-#error "SX_INST must be 0..6"
+#error "SX_INST must be 0..8"
 #endif
 #define SX_CAT2(a, b) a##b
 #define SX_CAT(a, b) SX_CAT2(a, b)

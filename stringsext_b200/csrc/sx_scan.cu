@@ -235,7 +235,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 
 constexpr uint32_t kPrefStageBytes = 32768;
 constexpr uint32_t kPrefQueueCap = 448;  // flushed as soon as fewer than one tile's worth of slots is free
-constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64 + 32 + kPrefQueueCap * 20;
+constexpr size_t kPrefSmemBytes = 2 * kPrefStageBytes + 1024 + 64 + 64 + 32 + kPrefQueueCap * 20 + 256;
 
 // DEFSHAPE (PF_UTF8 only): the default filter shape -- ASCII blocks 1..3 may pass, only 2-byte leads
 // (block 6) may pass -- with the block functions folded into single LOP3s.
@@ -255,6 +255,11 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_iw + 16);                         // 2 mbarriers
     uint32_t* s_qw = s_iw + 24;                                                       // queue: window index | candidate flag
     uint32_t* s_qm = s_qw + kPrefQueueCap;                                            // queue: good-byte masks of candidates
+    uint8_t* s_lut = reinterpret_cast<uint8_t*>(s_qm + 4 * kPrefQueueCap);             // PF_PAIR: class of every byte value
+    if (FAMILY == PF_PAIR) {
+        s_lut[threadIdx.x] = C.pair_cls[threadIdx.x];  // kPrefThreads == 256
+        __syncthreads();
+    }
     const bool do_refine = (FAMILY == PF_UTF8) && C.refine != 0;
     uint32_t qn = 0;  // queued windows (uniform across the block)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -444,11 +449,18 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t x = xs[j];
                         const uint32_t x1 = x << 1, x2 = x << 2;
-                        if (FAMILY == PF_UTF8) {
-                            const uint32_t cn = x & ~x1;  // 10xxxxxx
-                            // 11xxxxxx in a passing lead block / ASCII in a passing block
-                            const uint32_t lp = DEFSHAPE ? (x & x1 & ~x2) : (x & x1 & lop3_sel(x2, K.kh[3], K.kh[2]));
-                            const uint32_t ap = DEFSHAPE ? (~x & (x1 | x2)) : (~x & blk2(x1, x2, K.ka));
+                        if (FAMILY == PF_UTF8 || FAMILY == PF_PAIR) {
+                            uint32_t cn, lp, ap;  // flags at bit 7 of every byte: trail candidate, lead candidate, passing single byte
+                            if (FAMILY == PF_PAIR) {
+                                const uint32_t cw = (uint32_t)s_lut[x & 0xFFu] | ((uint32_t)s_lut[(x >> 8) & 0xFFu] << 8) |
+                                                    ((uint32_t)s_lut[(x >> 16) & 0xFFu] << 16) | ((uint32_t)s_lut[x >> 24] << 24);
+                                ap = cw << 7; lp = cw << 6; cn = cw << 5;
+                            } else {
+                                cn = x & ~x1;  // 10xxxxxx
+                                // 11xxxxxx in a passing lead block / ASCII in a passing block
+                                lp = DEFSHAPE ? (x & x1 & ~x2) : (x & x1 & lop3_sel(x2, K.kh[3], K.kh[2]));
+                                ap = DEFSHAPE ? (~x & (x1 | x2)) : (~x & blk2(x1, x2, K.ka));
+                            }
                             if (c > 0 || j > 0) {
                                 const uint32_t ncn = __funnelshift_r(pC, cn, 8);    // byte i: Cn(i + 1)
                                 const uint32_t lcp = DEFSHAPE ? pL : (pL | (pC & K.multi));
@@ -461,7 +473,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                             put(4 * c + j, lop3_sel(x, blk2(x1, x2, K.kh), blk2(x1, x2, K.ka)));
                         }
                     }
-                    if (FAMILY == PF_UTF8 && (uint32_t)c == nchunk - 1) {  // flush the last word: right edge favourable
+                    if ((FAMILY == PF_UTF8 || FAMILY == PF_PAIR) && (uint32_t)c == nchunk - 1) {  // flush the last word: right edge favourable
                         const uint32_t ncn = __funnelshift_r(pC, 0xFFFFFFFFu, 8);
                         const uint32_t pl = __funnelshift_l(ppLC, DEFSHAPE ? pL : (pL | (pC & K.multi)), 8);
                         put(4 * c + 3, pA | (pL & ncn) | (pC & pl));
@@ -711,7 +723,7 @@ sx_materialize_kernel(const __grid_constant__ ScanParams P, const Record* __rest
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const Record r = recs[i];
-        if (r.text_off + r.text_len <= text_cap) transcode_range(P, g, r.in_start, r.in_len, text + r.text_off);
+        if (r.text_off + r.text_len <= text_cap) transcode_record(P, g, r, text + r.text_off);
     }
 }
 
@@ -747,6 +759,8 @@ __global__ void __launch_bounds__(256) sx_fill_kernel(uint8_t* dst, unsigned lon
 // Host side: C ABI
 // =============================================================================================
 using namespace sx;
+
+#include "sx_mb_tables.inc"  // kSxBig5Index, kSxJis0208Index, kSxJis0212Index (generated, tools/gen_multibyte_tables.py)
 
 static thread_local int g_err_code = SX_OK;
 static thread_local std::string g_err_msg;
@@ -926,6 +940,29 @@ static void pinned_release(PinnedSet& s) {
     pinned_free(s);
 }
 
+// Device copies of the Big5 / EUC-JP index tables, one set per device, made on first use.
+struct MbDeviceTables { uint32_t* big5 = nullptr; uint32_t* jis0208 = nullptr; uint32_t* jis0212 = nullptr; };
+static std::mutex g_mb_mu;
+static std::vector<MbDeviceTables> g_mb_tables;
+static bool mb_tables_for(int device, MbDeviceTables* out) {
+    std::lock_guard<std::mutex> lk(g_mb_mu);
+    if ((size_t)device >= g_mb_tables.size()) g_mb_tables.resize((size_t)device + 1);
+    MbDeviceTables& t = g_mb_tables[device];
+    if (!t.big5) {
+        auto up = [](uint32_t** d, const uint32_t* h, size_t n) {
+            return cudaMalloc(d, n * sizeof(uint32_t)) == cudaSuccess && cudaMemcpy(*d, h, n * sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess;
+        };
+        if (!up(&t.big5, kSxBig5Index, sizeof kSxBig5Index / 4) || !up(&t.jis0208, kSxJis0208Index, sizeof kSxJis0208Index / 4) ||
+            !up(&t.jis0212, kSxJis0212Index, sizeof kSxJis0212Index / 4)) {
+            cudaGetLastError();
+            t = MbDeviceTables();
+            return false;
+        }
+    }
+    *out = t;
+    return true;
+}
+
 struct sx_finding_collection {
     RawVec<sx_finding> v;
     RawVec<uint8_t> text;
@@ -955,7 +992,7 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
     if (m->grep_char > 127) { set_err(SX_ERR_ARGUMENT, "grep_char must be an ASCII code (options.rs) or -1"); return fail; }
     if (m->output_line_char_nb_max < 6 || m->output_line_char_nb_max > 8192) { set_err(SX_ERR_UNSUPPORTED, "output_line_char_nb_max must be in 6..8192"); return fail; }
     if (m->chars_min_nb == 0) { set_err(SX_ERR_UNSUPPORTED, "chars_min_nb must be >= 1"); return fail; }
-    if (m->encoding_id > SX_ENC_UTF_32BE) { set_err(SX_ERR_ARGUMENT, "unknown encoding_id"); return fail; }
+    if (m->encoding_id > SX_ENC_EUC_JP) { set_err(SX_ERR_ARGUMENT, "unknown encoding_id"); return fail; }
     int n = sx_device_count();
     if (n <= 0) { set_err(SX_ERR_NO_DEVICE, "no CUDA device: the scanner has no CPU fallback"); return fail; }
     if (device < 0 || device >= n) { set_err(SX_ERR_ARGUMENT, "device ordinal out of range"); return fail; }
@@ -1174,6 +1211,7 @@ static cudaError_t launch_prefilter(const ScanParams& P, const PrefCfg& c, const
     switch (c.family) {
     case PF_BYTE: return SX_PREF(PF_BYTE, false);
     case PF_UTF8: return defshape ? SX_PREF(PF_UTF8, true) : SX_PREF(PF_UTF8, false);
+    case PF_PAIR: return launch_prefilter_t<PF_PAIR, false, false>(P, c, k, o, total_windows, grid, st, tm, use_tma);
     default: return SX_PREF(PF_UNIT, false);
     }
 #undef SX_PREF
@@ -1222,6 +1260,8 @@ static cudaError_t launch_exact_enc(const ScanParams& P, const ScanOut& O, const
     case 4: return launch_exact_4(P, O, X, grid, st);
     case 5: return launch_exact_5(P, O, X, grid, st);
     case 6: return launch_exact_6(P, O, X, grid, st);
+    case 7: return launch_exact_7(P, O, X, grid, st);
+    case 8: return launch_exact_8(P, O, X, grid, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -1234,6 +1274,8 @@ static cudaError_t launch_range_carry_enc(const ScanParams& P, const RangeCarryA
     case 4: return launch_range_carry_4(P, A, st);
     case 5: return launch_range_carry_5(P, A, st);
     case 6: return launch_range_carry_6(P, A, st);
+    case 7: return launch_range_carry_7(P, A, st);
+    case 8: return launch_range_carry_8(P, A, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -1562,7 +1604,7 @@ static int run_block(CallCtx& c) {
     }
     size_t need_recs = (size_t)((double)(nwin * P.W) * ss->rec_per_byte) + 4096;
     size_t need_text = (size_t)((double)(nwin * P.W) * ss->text_per_byte) + 65536;
-    unsigned long long counters[4] = {0, 0, 0, 0};
+    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     FinalState fin;
     HostCtl* const hc = ss->h_ctl;
     for (int attempt = 0;; ++attempt) {
@@ -1640,6 +1682,10 @@ static int run_block(CallCtx& c) {
         CK(cudaStreamSynchronize(st));
         ss->stats.d2h_bytes += sizeof counters + sizeof fin;
         if (c.w_lo > 0 && hc->piece[0].overflow) { set_err(SX_ERR_UNSUPPORTED, "range start: no carry-independent window found (halo too short?)"); return fail; }
+        if (counters[7]) {
+            set_err(SX_ERR_UNSUPPORTED, "Big5 / EUC-JP: more than 256 KiB of lead / trail bytes without a byte that resynchronises the decoder");
+            return fail;
+        }
         if (!fin.overflow && counters[0] <= ss->rec_cap && counters[1] <= ss->text_cap) break;
         if (attempt >= 2) { set_err(SX_ERR_CUDA, "output buffers still too small after regrowing"); return fail; }
         need_recs = (size_t)counters[0] + 1024;
@@ -1776,6 +1822,16 @@ static sx_finding_collection* scan_impl(sx_scanner_state* ss, int input_file_id,
     P.same_block = ss->m.require_same_unicode_block ? 1u : 0u;
     P.general = (P.grep_char >= 0 || P.same_block || P.n > P.q) ? 1u : 0u;
     memcpy(P.sb_table, ss->m.sb_table, sizeof P.sb_table);
+    const uint32_t *host_mb_a = nullptr, *host_mb_b = nullptr;
+    if (P.enc == ENC_BIG5 || P.enc == ENC_EUCJP) {
+        MbDeviceTables t;
+        if (!mb_tables_for(ss->device, &t)) { set_err(SX_ERR_CUDA, "cannot upload the Big5 / EUC-JP index tables"); return fail; }
+        P.mb_a = P.enc == ENC_BIG5 ? t.big5 : t.jis0208;
+        P.mb_b = P.enc == ENC_BIG5 ? nullptr : t.jis0212;
+        host_mb_a = P.enc == ENC_BIG5 ? kSxBig5Index : kSxJis0208Index;
+        host_mb_b = P.enc == ENC_BIG5 ? nullptr : kSxJis0212Index;
+        P.mb_fail = reinterpret_cast<uint32_t*>(ss->d_counters + 7);
+    }
 
     long long total_windows;
     {
@@ -1785,7 +1841,7 @@ static sx_finding_collection* scan_impl(sx_scanner_state* ss, int input_file_id,
     }
     if (total_windows > 0x7FFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
-    c.pc = make_pref_cfg(P, in_aligned16);
+    c.pc = make_pref_cfg(P, in_aligned16, host_mb_a, host_mb_b);
     // General missions: an unlisted window's carry-out must not depend on its carry-in.  --grep-char alone gets there with
     // one more listing rule (PrefCfg::kill_trail, sx_core.cuh); under --same-unicode-block a stale lead byte survives
     // ASCII junk (helper.rs:327-330) and n > q drops whole segments: those run without the prefilter.  DESIGN.md 7.

@@ -62,6 +62,8 @@ ENC_UTF_16BE = 3
 ENC_SINGLE_BYTE = 4
 ENC_UTF_32LE = 5  # extension: the reference has no UTF-32 (mission.rs:681-688)
 ENC_UTF_32BE = 6  # extension
+ENC_BIG5 = 7      # WHATWG Big5, index table generated from CPython's big5hkscs (tools/gen_multibyte_tables.py)
+ENC_EUC_JP = 8    # WHATWG EUC-JP, jis0208 / jis0212 generated from CPython's euc_jp
 
 # label -> (encoding id, canonical name as printed by Encoding::name(), single-byte table key)
 _LABELS = {
@@ -79,6 +81,9 @@ _LABELS = {
     "iso-8859-5": (ENC_SINGLE_BYTE, "ISO-8859-5", "iso-8859-5"),
     "windows-1251": (ENC_SINGLE_BYTE, "windows-1251", "windows-1251"),
     "windows-1252": (ENC_SINGLE_BYTE, "windows-1252", "windows-1252"),
+    "big5": (ENC_BIG5, "Big5", None),
+    "big5-hkscs": (ENC_BIG5, "Big5", None),
+    "euc-jp": (ENC_EUC_JP, "EUC-JP", None),
 }
 
 

@@ -30,6 +30,7 @@ def sx_mix_bytes(seed: int, offset: int, length: int) -> np.ndarray:
     return b[s : s + length].copy()
 
 
+_WORDS_MB = ["\u00ca\u0304", "\u00ea\u030cx", "中文", "ｱｲｳ", "Āā"]
 _WORDS = ["hello", "world", "straße", "naïve", "€uro", "日本語", "😀", "a", "xy", "longer-word-here", "ΑΒΓ", "привет",
           "Հայերեն", "עברית", "العربية"]
 
@@ -47,6 +48,10 @@ def encode_for(enc_id: int, s: str) -> bytes:
         return s.encode("koi8-r", errors="replace")
     if enc_id == 0:
         return s.encode("ascii", errors="replace")
+    if enc_id == 7:
+        return s.encode("big5hkscs", errors="replace")
+    if enc_id == 8:
+        return s.encode("euc_jp", errors="replace")
     return s.encode("utf-8")
 
 
@@ -64,6 +69,10 @@ def planted_strings(rng: random.Random, enc_id: int, n: int, q: int):
                 alpha = alphabets[0]
             if enc_id == 4:
                 alpha = alphabets[0] + "абвгдежзийклмноп"
+            if enc_id == 7:  # Big5: CJK, Greek, Cyrillic, and the pairs that decode to two code points
+                alpha = alphabets[0] + rng.choice(["日本語中文字", "ΑΒΓΔαβγδ", "абвгдеж", "\u00ca\u0304\u00ea\u030c", "äöü"])
+            if enc_id == 8:  # EUC-JP: jis0208 kanji / kana / Greek / Cyrillic, half-width katakana (8E), jis0212 Latin (8F)
+                alpha = alphabets[0] + rng.choice(["日本語漢字かなカナ", "ΑΒΓΔαβγδ", "абвгдеж", "ｱｲｳｴｵ", "ÀÁÂãäåĀāĂ"])
             s = "".join(rng.choice(alpha) for _ in range(ln))
             out.append(encode_for(enc_id, s))
     return out
@@ -105,22 +114,31 @@ def gen(rng: random.Random, kind: str, n: int, enc: int) -> bytes:
         return b""
     if kind == "rand":
         return bytes(rng.getrandbits(8) for _ in range(n))
+    if kind == "lowent" and enc in (7, 8) and rng.random() < 0.5:
+        alpha = (b"ab \x00\xa4\x40\xa3\x44\x88\x62\x80" if enc == 7 else b"ab \x00\xc6\xfc\x8e\xb1\x8f\xaa\xa1\x80")
+        return bytes(rng.choice(alpha) for _ in range(n))
     if kind == "lowent":
         alpha = rng.choice([b"ab\x00", b"abc \x00\xc3\xa9\xe2\x82\xac", b"a\x00", bytes(range(0x20, 0x7F)) + b"\x00\x01\xff",
                             b"\xc3\xa9\xc3a\x80", b"a\x00b\x00\xd8\x00\xdc\x3d\xd8", b"\xe2\x82\xac\xf0\x9f\x98\x80a\x00"])
         return bytes(rng.choice(alpha) for _ in range(n))
     if kind == "text":
         s = ""
+        words = _WORDS + _WORDS_MB if enc in (7, 8) else _WORDS
         while len(s) < n:
-            s += rng.choice(_WORDS) + rng.choice([" ", " ", "\n", "\x00", "", "\t"])
+            s += rng.choice(words) + rng.choice([" ", " ", "\n", "\x00", "", "\t"])
         b = encode_for(enc, s)
         off = rng.randrange(0, 4)
         return (bytes(rng.getrandbits(8) for _ in range(off)) + b)[:n]
     if kind == "runs":
         out = bytearray()
+        choices = [b"a", b"\xc3\xa9", b"\xe2\x82\xac", b"\xf0\x9f\x98\x80", b"a\x00", b"\x00a", b"\x00", b"\xff",
+                   b"\xc0", b" ", b"\xe9"]
+        if enc == 7:  # Big5 pairs: CJK, Greek, a two-code-point pair, an unmapped pair with an ASCII trail, a lone lead
+            choices = choices + [b"\xa4\x40", b"\xa3\x44", b"\x88\x62", b"\x88\xa5a", b"\x81\x41", b"\xa1", b"\xfe\xfe"]
+        if enc == 8:  # EUC-JP: kanji, half-width katakana, jis0212, broken three-byte sequences
+            choices = choices + [b"\xc6\xfc", b"\x8e\xb1", b"\x8f\xaa\xa1", b"\x8f\xa1", b"\x8e", b"\xa1\x41", b"\x8f\x8f\xb0\xa1"]
         while len(out) < n:
-            c = rng.choice([b"a", b"\xc3\xa9", b"\xe2\x82\xac", b"\xf0\x9f\x98\x80", b"a\x00", b"\x00a", b"\x00", b"\xff",
-                            b"\xc0", b" ", b"\xe9"])
+            c = rng.choice(choices)
             out += c * rng.randrange(1, 300)
         return bytes(out[:n])
     out = bytearray()  # mixed
@@ -130,7 +148,7 @@ def gen(rng: random.Random, kind: str, n: int, enc: int) -> bytes:
 
 
 KINDS = ["rand", "lowent", "text", "mixed", "runs"]
-LABELS = {0: "ascii", 1: "utf-8", 2: "utf-16le", 3: "utf-16be", 4: "koi8-r", 5: "utf-32le", 6: "utf-32be"}
+LABELS = {0: "ascii", 1: "utf-8", 2: "utf-16le", 3: "utf-16be", 4: "koi8-r", 5: "utf-32le", 6: "utf-32be", 7: "big5", 8: "euc-jp"}
 
 
 def random_mission(rng: random.Random, enc: int, M):

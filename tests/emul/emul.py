@@ -32,6 +32,7 @@ class ScanParams(C.Structure):
         ("k0", Carry),
         ("grep_char", C.c_int32), ("same_block", C.c_uint32), ("general", C.c_uint32),
         ("sb_table", C.c_uint16 * 128),
+        ("mb_a", C.c_void_p), ("mb_b", C.c_void_p), ("mb_fail", C.c_void_p),  # set by the harness itself
     ]
 
 
@@ -54,7 +55,7 @@ def lib():
     if _lib is None:
         src = os.path.join(HERE, "sx_emul.cpp")
         csrc = os.path.join(HERE, "..", "..", "stringsext_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("sx_core.cuh", "sx_fast_utf8.cuh", "sx_mask_utf8.cuh")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("sx_core.cuh", "sx_fast_utf8.cuh", "sx_mask_utf8.cuh", "sx_mb_tables.inc")]
         if (not os.path.exists(LIB)) or max(os.path.getmtime(f) for f in deps) > os.path.getmtime(LIB):
             os.makedirs(os.path.dirname(LIB), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", LIB, src])

@@ -8,6 +8,7 @@ struct uint4 { uint32_t x, y, z, w; };
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return s ? (uint32_t)((((uint64_t)hi << 32) | lo) >> s) : lo; }
 #endif
 #include "../../stringsext_b200/csrc/sx_mask_utf8.cuh"
+#include "../../stringsext_b200/csrc/sx_mb_tables.inc"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -65,7 +66,7 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
     const int64_t full = P.len / P.slice_len;
     const int64_t rest = P.len - full * (int64_t)P.slice_len;
     const int64_t total = full * geo.wps + (rest + P.W - 1) / P.W;
-    PrefCfg pc = make_pref_cfg(P, true);
+    PrefCfg pc = make_pref_cfg(P, true, P.mb_a, P.mb_b);
     // general missions: every window goes through the exact stage (an unlisted window's carry-out would depend on its
     // carry-in: killed segments, stale lead bytes -- sx_scan.cu), except --grep-char alone (PrefCfg::kill_trail)
     if (!use_pref || (P.general && !pref_general_ok(P))) pc.enabled = 0;
@@ -93,7 +94,7 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         text.resize(tb + rc.ntext + 8);
         for (size_t k = base; k < recs.size(); ++k) {
             Record& r = recs[k];
-            const uint32_t n = transcode_range(P, g, r.in_start, r.in_len, text.data() + r.text_off);
+            const uint32_t n = transcode_record(P, g, r, text.data() + r.text_off);
             if (n != r.text_len) stats[6]++;
         }
         text.resize(tb + rc.ntext);
@@ -215,9 +216,10 @@ static void run(const ScanParams& P, int use_pref, std::vector<Record>& recs, st
         r.in_len = final_carry->in_bytes - (uint32_t)*final_npend;
         r.text_len = final_carry->out_bytes;
         r.text_off = text.size();
-        r.flags = RF_LEFTOVER | ((final_carry->flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u);
+        r.flags = RF_LEFTOVER | ((final_carry->flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u) |
+                  ((final_carry->flags & CF_HALF) ? (uint32_t)RF_HALFSTART : 0u);
         text.resize(text.size() + r.text_len + 8);
-        transcode_range(P, g, r.in_start, r.in_len, text.data() + r.text_off);
+        transcode_record(P, g, r, text.data() + r.text_off);
         text.resize(text.size() - 8);
         recs.push_back(r);
     }
@@ -247,7 +249,14 @@ void sx_emul_guard_counts(uint64_t* ok, uint64_t* killer) { *ok = g_guard_ok; *k
 uint64_t sx_emul_guard_behind() { return g_guard_behind; }
 uint64_t sx_emul_guard_behind_hard() { return g_guard_behind_hard; }
 
-int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
+int sx_emul_scan(const ScanParams* P_in, int use_pref, emul_out* out) {
+    ScanParams Pl = *P_in;
+    static uint32_t mb_fail;
+    mb_fail = 0;
+    if (Pl.enc == ENC_BIG5) { Pl.mb_a = kSxBig5Index; Pl.mb_b = nullptr; }
+    if (Pl.enc == ENC_EUCJP) { Pl.mb_a = kSxJis0208Index; Pl.mb_b = kSxJis0212Index; }
+    Pl.mb_fail = &mb_fail;
+    const ScanParams* P = &Pl;
     for (uint32_t i = 0; i < 2048; ++i) mask_tables_fill(*P, g_tables, i);
     std::vector<uint32_t> list;
     std::vector<Record> recs;
@@ -261,8 +270,11 @@ int sx_emul_scan(const ScanParams* P, int use_pref, emul_out* out) {
     case ENC_SB: run<DecSb>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
     case ENC_UTF32LE: run<DecUtf32<false>>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
     case ENC_UTF32BE: run<DecUtf32<true>>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
+    case ENC_BIG5: run<DecBig5>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
+    case ENC_EUCJP: run<DecEucJp>(*P, use_pref, recs, text, &out->final_carry, &out->final_npend, out->stats, list); break;
     default: return 1;
     }
+    if (mb_fail) return 2;
     out->nrecs = recs.size();
     out->recs = (Record*)malloc(sizeof(Record) * (recs.size() + 1));
     memcpy(out->recs, recs.data(), sizeof(Record) * recs.size());

@@ -40,7 +40,7 @@ def test_reference_vectors(name, mission_factory, calls):
     assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
 
 
-@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_fuzz(enc, seed):
     rng = random.Random(seed * 100 + enc)
@@ -60,7 +60,7 @@ def test_fuzz(enc, seed):
         assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
 
 
-@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_fuzz_general_missions(enc):
     """--grep-char / --same-unicode-block: general automaton + dual-simulation classification (classify_general)."""
     rng = random.Random(31337 + enc)

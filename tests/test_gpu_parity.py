@@ -92,7 +92,7 @@ def test_cli_golden_1_2(golden_dir, n, q, grep, files, expected):
     assert bytes(out) == open(os.path.join(golden_dir, expected), "rb").read()
 
 
-@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_differential_fuzz_general_missions(enc):
     """--grep-char / --same-unicode-block on the GPU vs the oracle."""
     rng = random.Random(5150 + enc)
@@ -191,7 +191,7 @@ def test_reference_fixture_files(golden_dir, label, n, q, ubf):
         check_state(gs, os_)
 
 
-@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_differential_fuzz(enc):
     rng = random.Random(4242 + enc)
     for _ in range(40):
@@ -216,6 +216,8 @@ def test_differential_fuzz(enc):
     ("utf-16be", 10, 16, 3),
     ("koi8-r", 6, 16, 5),     # config 5 member with heavy output
     ("utf-32le", 6, 16, 5),   # extension
+    ("big5", 8, 16, 4),       # config 4 member (table provenance: DESIGN.md section 2)
+    ("euc-jp", 6, 16, 5),     # config 5 member
 ])
 def test_baseline_configs_vs_oracle(label, n, size_mib, seed):
     ubf = M.UBF_AFRICAN if label.startswith("utf-16") else None
@@ -285,6 +287,7 @@ _sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "em
     ("ascii", 6, 64, None, "rand"), ("utf-16le", 10, 64, M.UBF_AFRICAN, "rand"), ("utf-16be", 6, 32, None, "text"),
     ("utf-16le", 4, 64, M.UBF_ALL_VALID, "mixed"), ("utf-32le", 6, 64, None, "rand"), ("utf-32be", 4, 16, None, "text"),
     ("koi8-r", 10, 64, M.UBF_NONE, "rand"), ("windows-1252", 8, 64, None, "mixed"), ("utf-8", 4, 8, None, "mixed"),
+    ("big5", 8, 64, None, "rand"), ("big5", 4, 64, M.UBF_ALL_VALID, "text"), ("euc-jp", 6, 64, None, "rand"), ("euc-jp", 4, 32, M.UBF_ALL, "mixed"),
 ])
 def test_prefilter_window_list_matches_spec(label, n, q, ubf, kind):
     """The SWAR prefilter must list exactly the windows its byte-wise specification
@@ -300,7 +303,7 @@ def test_prefilter_window_list_matches_spec(label, n, q, ubf, kind):
         buf = buf.tobytes()
     else:
         buf = corpus.gen(rng, kind, size, m.encoding_id)
-    for pend_prefix in (b"", b"\xe2" if label == "utf-8" else b"\x41"):
+    for pend_prefix in (b"", b"\xe2" if label == "utf-8" else b"\xa4" if label in ("big5", "euc-jp") else b"\x41"):
         gs = sx.ScannerState(m)
         es = emul.EmulState(m, True)
         if pend_prefix:  # shift the unit grid / leave a pending sequence from a previous call
@@ -321,7 +324,7 @@ def test_prefilter_window_list_matches_spec(label, n, q, ubf, kind):
         assert g2.last_stats.tma_used == 0 and g2.last_window_list() == es.last_list and got2 == exp
 
 
-@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_prefilter_on_off_identical(enc):
     rng = random.Random(777 + enc)
     for _ in range(12):
@@ -341,7 +344,7 @@ def test_prefilter_on_off_identical(enc):
         assert a.last_run_str_was_printed_and_is_maybe_cut_str == b.last_run_str_was_printed_and_is_maybe_cut_str
 
 
-@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_general_missions_large_buffers_vs_oracle(enc):
     """--grep-char / --same-unicode-block / n > q on buffers of many 128-entry blocks (the block kernel's warm-up finds
     a known carry through the WT_GUARD rules, sx_core.cuh guard_benign / guard_known_behind): the oracle's findings,

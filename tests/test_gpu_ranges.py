@@ -63,7 +63,8 @@ def test_pieces_equal_the_fold(label, n, q, ubf, kind):
 
 
 RANGE_CASES = CASES + [("utf-16le", 4, 64, M.UBF_ALL_VALID, "mixed"), ("utf-16be", 6, 32, None, "text"), ("utf-32le", 6, 64, None, "rand"),
-                       ("utf-16le", 10, 64, M.UBF_AFRICAN, "rand")]
+                       ("utf-16le", 10, 64, M.UBF_AFRICAN, "rand"), ("big5", 8, 64, None, "rand"), ("big5", 4, 64, M.UBF_ALL_VALID, "text"),
+                       ("euc-jp", 6, 64, None, "rand"), ("euc-jp", 3, 32, M.UBF_ALL, "mixed")]
 
 
 @pytest.mark.parametrize("label,n,q,ubf,kind", RANGE_CASES)
@@ -93,7 +94,7 @@ def test_ranges_concatenate_to_the_whole_scan(label, n, q, ubf, kind):
         check_state(gs, os_)
 
 
-@pytest.mark.parametrize("label,n,q,ubf,kind", RANGE_CASES[:6] + RANGE_CASES[8:10])
+@pytest.mark.parametrize("label,n,q,ubf,kind", RANGE_CASES[:6] + RANGE_CASES[8:10] + RANGE_CASES[12:])
 def test_range_with_unknown_prefix(label, n, q, ubf, kind):
     """A rank of a range-sharded job only holds [range start - halo, range end): the carry into the range is found by the
     walk back inside the halo (SX_RANGE_PREFIX_UNKNOWN), positions come from the state's counter_offset."""
