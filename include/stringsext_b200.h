@@ -74,8 +74,8 @@ typedef struct {
     uint8_t mission_id;
     const uint8_t* s; /* UTF-8, not NUL terminated */
     uint32_t s_len;
-    int64_t in_start; /* extension: contiguous input range of the text, relative to the call's buffer */
-    uint32_t in_len;
+    int64_t in_start; /* reserved, 0 (an earlier revision reported the input range of the text here; it is no longer */
+    uint32_t in_len;  /* shipped from the device: a finding crosses PCIe as 16 bytes + its text)                      */
 } sx_finding;
 
 typedef struct sx_scanner_state sx_scanner_state;

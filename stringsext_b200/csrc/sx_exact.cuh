@@ -29,29 +29,31 @@ struct ScanOut {
     uint2* block_desc;             // per exact-kernel block {first record, record count}
     unsigned long long* counters;  // [0] records, [1] text bytes, [2] list entries, [3] next block of the exact kernel
     FinalState* final_state;
-    // direct host output (sparse pipeline): findings written by the GPU in their final C-ABI form into pinned host
-    // memory (posted PCIe writes from the gather kernel), so the host neither copies nor converts records
-    sx_finding* host_findings;     // mapped pinned memory, nullptr: off
+    // direct output: the GPU writes every finding as a 16-byte wire record (WireFinding) -- into a device staging array
+    // that the copy engine moves to the collection's pinned memory (sparse pipeline), or straight into that memory
+    // (block path); the host expands them to sx_finding on demand, page by page (sx_fc_get / sx_fc_data)
+    uint4* host_findings;          // nullptr: off (records are downloaded and converted on the host)
     unsigned long long host_cap;
-    const uint8_t* host_text;      // HOST address the finding text will be downloaded to (text arena base)
+    const uint8_t* host_text;      // unused by the kernels (kept so that both paths share the struct)
     int32_t file_id;
     uint32_t mission_id;
 };
 
-static_assert(sizeof(sx_finding) == 48 && offsetof(sx_finding, precision) == 8 && offsetof(sx_finding, completes_previous) == 9 &&
-              offsetof(sx_finding, input_file_id) == 10 && offsetof(sx_finding, mission_id) == 12 && offsetof(sx_finding, s) == 16 &&
-              offsetof(sx_finding, s_len) == 24 && offsetof(sx_finding, in_start) == 32 && offsetof(sx_finding, in_len) == 40,
-              "sx_finding layout");
-// One finding in its C-ABI layout, three 16-byte stores (finding.rs:51-74; `s` = host address of its text).
-__device__ __forceinline__ void write_host_finding(const ScanOut& O, uint4* dst, const Record& r) {
-    const unsigned long long sp = reinterpret_cast<unsigned long long>(O.host_text) + r.text_off;
-    uint4 a, b, c;
-    a.x = (uint32_t)r.position; a.y = (uint32_t)(r.position >> 32);
-    a.z = (r.precision & 0xFFu) | ((r.flags & RF_COMPLETES) ? 0x100u : 0u) | (((uint32_t)O.file_id & 0xFFFFu) << 16);
-    a.w = O.mission_id & 0xFFu;
-    b.x = (uint32_t)sp; b.y = (uint32_t)(sp >> 32); b.z = r.text_len; b.w = 0;
-    c.x = (uint32_t)r.in_start; c.y = (uint32_t)((unsigned long long)r.in_start >> 32); c.z = r.in_len; c.w = 0;
-    dst[0] = a; dst[1] = b; dst[2] = c;
+// One finding on the wire (finding.rs:51-74 minus what the host knows: mission, file, text base address):
+//   x, y: position relative to the call's first byte (40 bits) | text length (22 bits) << 40 | precision (2 bits) << 62
+//   z, w: text offset in the collection's text arena (40 bits) | completes-previous flag << 40
+struct WireFinding { unsigned long long a, b; };
+static_assert(sizeof(WireFinding) == 16, "wire record");
+__host__ __device__ __forceinline__ WireFinding wire_pack(unsigned long long pos_rel, uint32_t text_len, uint32_t precision,
+                                                          unsigned long long text_off, bool completes) {
+    WireFinding w;
+    w.a = (pos_rel & 0xFFFFFFFFFFull) | ((unsigned long long)(text_len & 0x3FFFFFu) << 40) | ((unsigned long long)(precision & 3u) << 62);
+    w.b = (text_off & 0xFFFFFFFFFFull) | ((unsigned long long)(completes ? 1u : 0u) << 40);
+    return w;
+}
+__device__ __forceinline__ void write_host_finding(const ScanParams& P, uint4* dst, const Record& r) {
+    const WireFinding w = wire_pack(r.position - P.base_consumed, r.text_len, r.precision, r.text_off, (r.flags & RF_COMPLETES) != 0);
+    *dst = make_uint4((uint32_t)w.a, (uint32_t)(w.a >> 32), (uint32_t)w.b, (uint32_t)(w.b >> 32));
 }
 
 // Work list of the exact kernel: the windows the prefilter kept, in stream order

@@ -692,9 +692,8 @@ __global__ void __launch_bounds__(1024) sx_order_scan_kernel(const uint2* __rest
 // one warp per block descriptor; 32 findings at a time are assembled in shared memory and leave as contiguous
 // 16-byte stores (512 bytes per warp instruction: large PCIe write transactions)
 __global__ void __launch_bounds__(256)
-sx_order_write_kernel(const ScanOut O, const uint2* __restrict__ desc, const unsigned long long* __restrict__ pos, unsigned long long nb,
-                      unsigned long long nrec) {
-    __shared__ uint4 sbuf[8][96];
+sx_order_write_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const uint2* __restrict__ desc,
+                      const unsigned long long* __restrict__ pos, unsigned long long nb, unsigned long long nrec) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (unsigned long long b = (unsigned long long)blockIdx.x * 8 + warp; b < nb; b += (unsigned long long)gridDim.x * 8) {
         const uint2 d = desc[b];
@@ -704,14 +703,10 @@ sx_order_write_kernel(const ScanOut O, const uint2* __restrict__ desc, const uns
             if (lane < cnt) {
                 const Record r = O.recs[(unsigned long long)d.x + k0 + lane];
                 const unsigned long long idx = p0 + k0 + lane;
-                write_host_finding(O, &sbuf[warp][lane * 3], r);
+                write_host_finding(P, O.host_findings + idx, r);  // consecutive lanes, consecutive 16-byte records
                 if (idx == 0) O.final_state->first_flags = r.flags;
                 if (idx == nrec - 1) O.final_state->last_flags = r.flags;
             }
-            __syncwarp();
-            uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + p0 + k0);
-            for (uint32_t t = lane; t < cnt * 3; t += 32) dst[t] = sbuf[warp][t];
-            __syncwarp();
         }
     }
 }
@@ -827,7 +822,7 @@ struct sx_scanner_state {
     uint8_t* d_tables = nullptr; size_t tables_cap = 0;
     uint32_t* d_queue = nullptr; size_t queue_cap = 0;
     uint32_t* d_clist = nullptr; size_t clist_cap = 0;
-    sx_finding* d_findings = nullptr; size_t findings_cap = 0;
+    WireFinding* d_findings = nullptr; size_t findings_cap = 0;
     PieceCtl* d_ctl = nullptr;
     HostCtl* h_ctl = nullptr;
     unsigned long long* d_bpos = nullptr; size_t bpos_cap = 0;  // block path, direct output: stream-order position of every block
@@ -884,8 +879,8 @@ struct RawVec {
 // text is downloaded to.  A collection built that way owns its set; sets are recycled through a small pool because
 // pinning memory costs far more than a scan.
 struct PinnedSet {
-    sx_finding* f = nullptr; size_t fcap = 0;  // findings
-    uint8_t* t = nullptr; size_t tcap = 0;     // text bytes
+    WireFinding* f = nullptr; size_t fcap = 0;  // findings as they come off the wire (16 bytes each)
+    uint8_t* t = nullptr; size_t tcap = 0;      // text bytes
 };
 static std::mutex g_pool_mu;
 static std::vector<PinnedSet> g_pool;
@@ -894,50 +889,74 @@ static void pinned_free(PinnedSet& s) {
     if (s.t) cudaFreeHost(s.t);
     s = PinnedSet();
 }
-static size_t pinned_bytes(const PinnedSet& s) { return s.fcap * sizeof(sx_finding) + s.tcap; }
-// Pool policy: page-locked memory is not swappable and output-heavy scans need tens of GB of it, so the pool never
-// holds more than one large set (the most recently released one, so that a loop of equal scans reuses it) plus up to
-// 1 GiB of small ones; a request is served by the smallest pooled set that fits.
-constexpr size_t kPoolSmallBytes = 64ull << 20, kPoolSmallTotal = 1ull << 30;
+static size_t pinned_bytes(const PinnedSet& s) { return s.fcap * sizeof(WireFinding) + s.tcap; }
+// Pool policy: pinning memory costs far more than a scan (seconds per GB), so released sets are kept for reuse -- up
+// to kPoolTotal bytes per process (SX_PINNED_POOL_MIB overrides; page-locked memory is not swappable).  A process
+// typically runs several missions side by side, each returning a collection per call, so several large sets are live
+// at once; a request is served by the smallest pooled set that fits, and when the pool is full the least recently
+// released sets go first.
+static size_t pool_total_cap() {
+    static size_t cap = 0;
+    if (!cap) {
+        cap = 24ull << 30;
+        if (const char* ev = getenv("SX_PINNED_POOL_MIB")) { const long long v = atoll(ev); if (v >= 0) cap = (size_t)v << 20; }
+    }
+    return cap;
+}
 static bool pinned_acquire(size_t fcap, size_t tcap, PinnedSet* out) {
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         int best = -1;
         for (size_t i = 0; i < g_pool.size(); ++i)
-            if (g_pool[i].fcap >= fcap && g_pool[i].tcap >= tcap && (best < 0 || g_pool[i].fcap < g_pool[best].fcap)) best = (int)i;
-        if (best >= 0) { *out = g_pool[best]; g_pool.erase(g_pool.begin() + best); return true; }
-        // nothing fits: pooled large sets would only sit beside the new allocation
-        for (size_t i = 0; i < g_pool.size();) {
-            if (pinned_bytes(g_pool[i]) > kPoolSmallBytes) { pinned_free(g_pool[i]); g_pool.erase(g_pool.begin() + i); }
-            else ++i;
+            if (g_pool[i].fcap >= fcap && g_pool[i].tcap >= tcap && (best < 0 || pinned_bytes(g_pool[i]) < pinned_bytes(g_pool[best]))) best = (int)i;
+        // a pooled set several times larger than needed stays for the caller that needs it
+        if (best >= 0 && pinned_bytes(g_pool[best]) <= 4 * (fcap * sizeof(WireFinding) + tcap) + (64ull << 20)) {
+            *out = g_pool[best];
+            g_pool.erase(g_pool.begin() + best);
+            return true;
         }
     }
     PinnedSet s;
     s.fcap = fcap + fcap / 16 + 1024;
     s.tcap = tcap + tcap / 16 + 65536;
-    if (cudaHostAlloc((void**)&s.f, s.fcap * sizeof(sx_finding), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc((void**)&s.f, s.fcap * sizeof(WireFinding), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void**)&s.t, s.tcap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         pinned_free(s);
-        return false;
+        // out of pinnable memory: drop the pool and try once more
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            for (auto& q : g_pool) pinned_free(q);
+            g_pool.clear();
+        }
+        s.fcap = fcap + 1024;
+        s.tcap = tcap + 65536;
+        if (cudaHostAlloc((void**)&s.f, s.fcap * sizeof(WireFinding), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostAlloc((void**)&s.t, s.tcap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            pinned_free(s);
+            return false;
+        }
     }
     *out = s;
     return true;
 }
 static void pinned_release(PinnedSet& s) {
     if (!s.f && !s.t) return;
+    std::vector<PinnedSet> drop;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        const bool large = pinned_bytes(s) > kPoolSmallBytes;
-        size_t small_total = 0;
-        for (size_t i = 0; i < g_pool.size();) {
-            if (large && pinned_bytes(g_pool[i]) > kPoolSmallBytes) { pinned_free(g_pool[i]); g_pool.erase(g_pool.begin() + i); continue; }
-            if (pinned_bytes(g_pool[i]) <= kPoolSmallBytes) small_total += pinned_bytes(g_pool[i]);
-            ++i;
+        g_pool.push_back(s);  // most recently released last
+        s = PinnedSet();
+        size_t total = 0;
+        for (const auto& q : g_pool) total += pinned_bytes(q);
+        while (!g_pool.empty() && (total > pool_total_cap() || g_pool.size() > 64)) {
+            total -= pinned_bytes(g_pool.front());
+            drop.push_back(g_pool.front());
+            g_pool.erase(g_pool.begin());
         }
-        if (large || (small_total + pinned_bytes(s) <= kPoolSmallTotal && g_pool.size() < 16)) { g_pool.push_back(s); s = PinnedSet(); return; }
     }
-    pinned_free(s);
+    for (auto& q : drop) pinned_free(q);
 }
 
 // Device copies of the Big5 / EUC-JP index tables, one set per device, made on first use.
@@ -963,13 +982,72 @@ static bool mb_tables_for(int device, MbDeviceTables* out) {
     return true;
 }
 
+// A collection either holds its findings expanded (v, the record-download path) or as they came off the wire: 16-byte
+// records + text in a pinned set, expanded to sx_finding on demand in pages of kPage findings (a consumer that walks a
+// 100-million-finding collection pays for what it touches, the scan does not pay for any of it).
 struct sx_finding_collection {
+    static constexpr size_t kPage = 4096;
     RawVec<sx_finding> v;
     RawVec<uint8_t> text;
-    PinnedSet set;  // direct host output: v and the finding text live here
+    PinnedSet set;  // direct output: wire records and the finding text live here
+    bool wire = false;
+    size_t n = 0;                 // findings
+    uint64_t base = 0;            // stream position of the call's first byte (wire positions are relative to it)
+    int16_t file_id = -1;
+    uint8_t mission_id = 0;
+    bool have_first = false;      // the first finding's text is in `text` (host-carried leftover in front of it)
+    std::vector<uint8_t> page_done;
+    bool all_done = false;
+    std::mutex mu;
     uint64_t first_byte_position = 0;
     int str_buf_overflow = 0;
     ~sx_finding_collection() { pinned_release(set); }
+    void expand(size_t i0, size_t i1) {
+        sx_finding* const out = v.data();
+        const WireFinding* const w = set.f;
+        for (size_t i = i0; i < i1; ++i) {
+            sx_finding f;
+            f.position = base + (w[i].a & 0xFFFFFFFFFFull);
+            f.precision = (uint8_t)(w[i].a >> 62);
+            f.completes_previous = (uint8_t)((w[i].b >> 40) & 1u);
+            f.input_file_id = file_id;
+            f.mission_id = mission_id;
+            f.s = set.t + (w[i].b & 0xFFFFFFFFFFull);
+            f.s_len = (uint32_t)((w[i].a >> 40) & 0x3FFFFFu);
+            f.in_start = 0;
+            f.in_len = 0;
+            out[i] = f;
+        }
+        if (have_first && i0 == 0 && i1 > 0) { out[0].s = text.data(); out[0].s_len = (uint32_t)(text.size() - 1); }
+    }
+    void ensure_page(size_t i) {
+        if (!wire || all_done) return;
+        const size_t pg = i / kPage;
+        std::lock_guard<std::mutex> lk(mu);
+        if (v.cap < n) v.resize(n);
+        if (page_done.empty()) page_done.assign((n + kPage - 1) / kPage, 0);
+        if (!page_done[pg]) { expand(pg * kPage, std::min(n, (pg + 1) * kPage)); page_done[pg] = 1; }
+    }
+    void ensure_all() {
+        if (!wire || all_done) return;
+        std::lock_guard<std::mutex> lk(mu);
+        if (all_done) return;
+        if (v.cap < n) v.resize(n);
+        if (page_done.empty()) page_done.assign((n + kPage - 1) / kPage, 0);
+        const size_t npages = page_done.size();
+        const unsigned nth = n > (1u << 20) ? std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        auto job = [&](size_t p0, size_t p1) {
+            for (size_t pg = p0; pg < p1; ++pg)
+                if (!page_done[pg]) { expand(pg * kPage, std::min(n, (pg + 1) * kPage)); page_done[pg] = 1; }
+        };
+        if (nth <= 1) job(0, npages);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned k = 0; k < nth; ++k) th.emplace_back(job, npages * k / nth, npages * (k + 1) / nth);
+            for (auto& t : th) t.join();
+        }
+        all_done = true;
+    }
 };
 
 extern "C" {
@@ -1102,9 +1180,15 @@ size_t sx_scanner_state_last_window_list(const sx_scanner_state* ss, uint32_t* o
 }
 void sx_scanner_state_set_pieces(sx_scanner_state* ss, int pieces) { ss->pieces = pieces < 0 ? 0 : (pieces > kMaxPieces ? kMaxPieces : pieces); }
 
-size_t sx_fc_len(const sx_finding_collection* fc) { return fc->v.size(); }
-const sx_finding* sx_fc_get(const sx_finding_collection* fc, size_t i) { return &fc->v[i]; }
-const sx_finding* sx_fc_data(const sx_finding_collection* fc) { return fc->v.data(); }
+size_t sx_fc_len(const sx_finding_collection* fc) { return fc->wire ? fc->n : fc->v.size(); }
+const sx_finding* sx_fc_get(const sx_finding_collection* fc, size_t i) {
+    const_cast<sx_finding_collection*>(fc)->ensure_page(i);
+    return &fc->v[i];
+}
+const sx_finding* sx_fc_data(const sx_finding_collection* fc) {
+    const_cast<sx_finding_collection*>(fc)->ensure_all();
+    return fc->v.data();
+}
 uint64_t sx_fc_first_byte_position(const sx_finding_collection* fc) { return fc->first_byte_position; }
 int sx_fc_str_buf_overflow(const sx_finding_collection* fc) { return fc->str_buf_overflow; }
 void sx_fc_free(sx_finding_collection* fc) { delete fc; }
@@ -1466,8 +1550,8 @@ static int run_sparse(CallCtx& c) {
             sx_list_compact_kernel<<<p.pgrid, 256, 0, sb>>>(ss->d_ccount + (size_t)k * kMaxPrefCtas, (uint32_t)p.pgrid, ss->d_list, p.t0, p.tpc,
                                                                clist, ctl, p.cap);
             CK(cudaGetLastError());
-            ScanOut O{ss->d_recs, ss->rec_cap, text_cap, ss->d_blocks, ss->d_counters, &hc->fin, ss->use_direct ? ss->d_findings : nullptr,
-                      out_cap, ss->use_direct ? fc->set.t : nullptr, c.input_file_id, ss->m.mission_id};
+            ScanOut O{ss->d_recs, ss->rec_cap, text_cap, ss->d_blocks, ss->d_counters, &hc->fin, ss->use_direct ? reinterpret_cast<uint4*>(ss->d_findings) : nullptr,
+                      out_cap, nullptr, c.input_file_id, ss->m.mission_id};
             ExactCfg X;
             X.list = clist; X.ne_ptr = &ctl->ne; X.ne_static = 0; X.total_windows = c.total_windows;
             X.in_aligned16 = c.in_aligned16 ? 1u : 0u; X.pre_bytes = c.pc.pre_bytes; X.cta_off = nullptr; X.ncta = 0; X.region_stride = 0;
@@ -1518,9 +1602,9 @@ static int run_sparse(CallCtx& c) {
                     ss->stats.kernel_launches++;
                 }
                 if (ss->use_direct) {
-                    if (r1 > r0) CK(cudaMemcpyAsync(fc->set.f + r0, ss->d_findings + r0, (size_t)(r1 - r0) * sizeof(sx_finding), cudaMemcpyDeviceToHost, ss->sC));
+                    if (r1 > r0) CK(cudaMemcpyAsync(fc->set.f + r0, ss->d_findings + r0, (size_t)(r1 - r0) * sizeof(WireFinding), cudaMemcpyDeviceToHost, ss->sC));
                     if (t1 > t0) CK(cudaMemcpyAsync(fc->set.t + t0, ss->d_text + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ss->sC));
-                    ss->stats.d2h_bytes += (r1 - r0) * sizeof(sx_finding) + (t1 - t0);
+                    ss->stats.d2h_bytes += (r1 - r0) * sizeof(WireFinding) + (t1 - t0);
                 }
                 r0 = r1; t0 = t1;
             }
@@ -1721,11 +1805,11 @@ static int run_block(CallCtx& c) {
         const size_t nblocks = (size_t)((counters[2] + kThreads - 1) / kThreads);
         pinned_release(fc->set);
         if (pinned_acquire(nrec, ntext, &fc->set) && grow(&ss->d_bpos, &ss->bpos_cap, nblocks + 1)) {
-            ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, fc->set.f, fc->set.fcap, fc->set.t,
-                      c.input_file_id, ss->m.mission_id};
+            ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, reinterpret_cast<uint4*>(fc->set.f),
+                      fc->set.fcap, nullptr, c.input_file_id, ss->m.mission_id};
             sx_order_scan_kernel<<<1, 1024, 0, st>>>(ss->d_blocks, ss->d_bpos, nblocks);
             const unsigned wgrid = (unsigned)std::min<size_t>((nblocks + 7) / 8, (size_t)ss->num_sms * 8);
-            sx_order_write_kernel<<<wgrid, 256, 0, st>>>(O, ss->d_blocks, ss->d_bpos, nblocks, nrec);
+            sx_order_write_kernel<<<wgrid, 256, 0, st>>>(P, O, ss->d_blocks, ss->d_bpos, nblocks, nrec);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(&c.fin, ss->d_final, sizeof c.fin, cudaMemcpyDeviceToHost, st));  // first / last record flags
             const int mgrid = (int)std::min<size_t>((nrec + 255) / 256, (size_t)ss->num_sms * 8);
@@ -1735,7 +1819,7 @@ static int run_block(CallCtx& c) {
             CK(cudaEventRecord(ss->ev[3], st));
             ss->stats.kernel_launches += 3;
             if (ntext) CK(cudaMemcpyAsync(fc->set.t, ss->d_text, ntext, cudaMemcpyDeviceToHost, st));
-            ss->stats.d2h_bytes += nrec * sizeof(sx_finding) + ntext;
+            ss->stats.d2h_bytes += nrec * sizeof(WireFinding) + ntext;
             CK(cudaStreamSynchronize(st));
             float ms = 0;
             cudaEventElapsedTime(&ms, ss->ev[2], ss->ev[3]);
@@ -1882,25 +1966,37 @@ static sx_finding_collection* scan_impl(sx_scanner_state* ss, int input_file_id,
         ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - c.t_begin).count();
         const bool tail_is_leftover = nrec > 0 && (fin.last_flags & RF_LEFTOVER) != 0;
         const size_t n_out = nrec - (tail_is_leftover ? 1 : 0);
-        fc->v.adopt(fc->set.f, n_out);
+        fc->wire = true;
+        fc->n = n_out;
+        fc->base = P.base_consumed;
+        fc->file_id = (int16_t)input_file_id;
+        fc->mission_id = ss->m.mission_id;
+        auto wire_text = [&](size_t i, const uint8_t** p, size_t* len) {
+            *p = fc->set.t + (fc->set.f[i].b & 0xFFFFFFFFFFull);
+            *len = (size_t)((fc->set.f[i].a >> 40) & 0x3FFFFFu);
+        };
         // host text in front of device text: the first record of a run that began in the previous call, the leftover
-        auto with_host_text = [&](const sx_finding& f, std::vector<uint8_t>& dst) {
+        auto with_host_text = [&](size_t i, std::vector<uint8_t>& dst) {
+            const uint8_t* p; size_t len;
+            wire_text(i, &p, &len);
             dst.assign(ss->leftover.begin(), ss->leftover.end());
-            dst.insert(dst.end(), f.s, f.s + f.s_len);
+            dst.insert(dst.end(), p, p + len);
         };
         if (tail_is_leftover) {
-            const sx_finding& f = fc->set.f[nrec - 1];
-            if (fin.last_flags & RF_HOSTCARRY) with_host_text(f, new_leftover);
-            else new_leftover.assign(f.s, f.s + f.s_len);
+            if (fin.last_flags & RF_HOSTCARRY) with_host_text(nrec - 1, new_leftover);
+            else {
+                const uint8_t* p; size_t len;
+                wire_text(nrec - 1, &p, &len);
+                new_leftover.assign(p, p + len);
+            }
             have_leftover = true;
         }
         if (n_out > 0 && (fin.first_flags & RF_HOSTCARRY)) {
             std::vector<uint8_t> t;
-            with_host_text(fc->set.f[0], t);
+            with_host_text(0, t);
             fc->text.resize(t.size() + 1);
             memcpy(fc->text.data(), t.data(), t.size());
-            fc->set.f[0].s = fc->text.data();
-            fc->set.f[0].s_len = (uint32_t)t.size();
+            fc->have_first = true;
         }
         ss->stats.host_post_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_post).count();
     } else {
@@ -2067,8 +2163,10 @@ extern "C" size_t sx_merge(const sx_finding_collection* const* fcs, size_t n, co
     // finding.rs:92-109 via itertools::kmerge (main.rs:133): position, then mission_id; every
     // collection is position-monotone, so a stable sort of the concatenation is the k-way merge.
     size_t k = 0;
-    for (size_t i = 0; i < n; ++i)
-        for (const sx_finding& f : fcs[i]->v) out[k++] = &f;
+    for (size_t i = 0; i < n; ++i) {
+        const sx_finding* f = sx_fc_data(fcs[i]);
+        for (size_t j = 0, m = sx_fc_len(fcs[i]); j < m; ++j) out[k++] = f + j;
+    }
     std::stable_sort(out, out + k, [](const sx_finding* a, const sx_finding* b) {
         if (a->position != b->position) return a->position < b->position;
         return a->mission_id < b->mission_id;

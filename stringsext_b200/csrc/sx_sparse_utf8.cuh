@@ -526,8 +526,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     __shared__ uint32_t wa[8], wb[8];
     // the chunk's findings are contiguous in the output, so they are assembled in shared memory and leave as fully
     // coalesced 16-byte stores
-    constexpr uint32_t kStage = 224;
-    __shared__ uint4 sbuf[kStage * 3];
+    constexpr uint32_t kStage = 512;
+    __shared__ uint4 sbuf[kStage];
     // ... and so is their text (UTF-8 -> UTF-8: the bytes of the input range)
     constexpr uint32_t kTextStage = 4096;
     __shared__ __align__(16) uint8_t tbuf[kTextStage];
@@ -583,7 +583,7 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
         // the first / last record of the stream: their flags travel in the final state (host-carried text, leftover)
         auto put = [&](unsigned long long idx, const Record& r) {
             O.recs[idx] = r;
-            if (staged_out) write_host_finding(O, &sbuf[(idx - br) * 3], r);
+            if (staged_out) write_host_finding(P, &sbuf[idx - br], r);
             if (idx == 0) O.final_state->first_flags = r.flags;
             if (text_staged) transcode_range(P, c.g, r.in_start, r.in_len, tbuf + (r.text_off - bt));
         };
@@ -639,19 +639,11 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     if (active && e == NE - 1 && range_is_tail(X)) { O.final_state->carry = kout; O.final_state->npend = es->npend; }
     __syncthreads();
     if (staged_out) {
-        uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br);
-        for (uint32_t k = threadIdx.x; k < tr * 3; k += kSpThreads) dst[k] = sbuf[k];
+        uint4* const dst = O.host_findings + br;
+        for (uint32_t k = threadIdx.x; k < tr; k += kSpThreads) dst[k] = sbuf[k];
     }
     if (round_out) {
-        constexpr uint32_t kRound = kSpThreads;
-        for (uint32_t rb = 0; rb < tr; rb += kRound) {
-            const uint32_t cnt = tr - rb < kRound ? tr - rb : kRound;
-            if (threadIdx.x < cnt) write_host_finding(O, &sbuf[threadIdx.x * 3], O.recs[br + rb + threadIdx.x]);
-            __syncthreads();
-            uint4* const dst = reinterpret_cast<uint4*>(O.host_findings + br + rb);
-            for (uint32_t k = threadIdx.x; k < cnt * 3; k += kSpThreads) dst[k] = sbuf[k];
-            __syncthreads();
-        }
+        for (uint32_t k = threadIdx.x; k < tr; k += kSpThreads) write_host_finding(P, O.host_findings + br + k, O.recs[br + k]);
     }
     if (text_staged && tt) {
         // [bt, bt + tt) of the text arena: bytes up to the first 16-byte boundary, aligned 16-byte body, tail bytes

@@ -377,6 +377,30 @@ class RawCollection:
         return [(arr[i].position, arr[i].precision, C.string_at(arr[i].s, arr[i].s_len), bool(arr[i].completes_previous))
                 for i in range(n)]
 
+    def as_numpy(self):
+        """The findings as a structured numpy array over the collection's own memory (valid until close())."""
+        import numpy as np
+
+        dt = np.dtype({"names": ["position", "precision", "completes", "file_id", "mission_id", "s", "s_len", "in_start", "in_len"],
+                       "formats": ["<u8", "u1", "u1", "<i2", "u1", "<u8", "<u4", "<i8", "<u4"],
+                       "offsets": [0, 8, 9, 10, 12, 16, 24, 32, 40], "itemsize": 48})
+        L = load_library()
+        n = L.sx_fc_len(self._h)
+        if n == 0:
+            return np.zeros(0, dtype=dt)
+        addr = C.cast(L.sx_fc_data(self._h), C.c_void_p).value
+        buf = (C.c_uint8 * (48 * n)).from_address(addr)
+        return np.frombuffer(buf, dtype=dt, count=n)
+
+    def select(self, lo: int, hi: int):
+        """(position, precision, text, completes) of the findings with lo <= position < hi (positions are monotone)."""
+        import numpy as np
+
+        a = self.as_numpy()
+        i0, i1 = np.searchsorted(a["position"], [lo, hi], side="left")
+        return [(int(r["position"]), int(r["precision"]), C.string_at(int(r["s"]), int(r["s_len"])), bool(r["completes"]))
+                for r in a[i0:i1]]
+
     def close(self):
         if self._h:
             load_library().sx_fc_free(self._h)
