@@ -427,19 +427,26 @@ sx_sp_ext_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
     const long long NE = (long long)B.ctl->ne;
     if ((long long)blockIdx.x * kSpThreads >= NE) return;
     SpCtx c;
-    sp_setup(P, X, B, T, c);
+    bool ready = false;  // the tables are only needed by the few chunks that hold an extension window
     for (long long e0 = (long long)blockIdx.x * kSpThreads; e0 < NE; e0 += (long long)gridDim.x * kSpThreads) {
         const long long e = e0 + threadIdx.x;
         unsigned long long sum_r = 0, sum_t = 0;
+        bool need_x = false;
+        long long w = 0;
+        Carry kout = carry_none();
+        EntryHot* es = nullptr;
         if (e < NE) {
-            EntryHot* const es = &B.H[e];
-            const long long w = list_window(X, X.cta_off, e);
-            const Carry kout = es->kout;
-            const bool next_adj = sp_next_adjacent(X, NE, e, w);
-            uint32_t xr = 0, xt = 0;
+            es = &B.H[e];
+            w = list_window(X, X.cta_off, e);
+            kout = es->kout;
             // a "cut" carry (or a leftover already long enough to print) out of a listed window reaches an unlisted
             // successor: that window may print a continuation / the leftover
-            if (carry_needs_extension(P, kout) && !next_adj && (w + 1) < X.w_end) {
+            need_x = carry_needs_extension(P, kout) && (w + 1) < X.w_end && !sp_next_adjacent(X, NE, e, w);
+        }
+        if (__syncthreads_or(need_x) && !ready) { sp_setup(P, X, B, T, c); ready = true; }
+        if (e < NE) {
+            uint32_t xr = 0, xt = 0;
+            if (need_x) {
                 const WinGeom xg = ext_geom(c.geo, w + 1, X.pre_bytes);
                 WinResult r;
                 if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, xg, kout, MODE_BUFFER, sp_xstaged(B, e), 0, r))
@@ -722,7 +729,7 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
     sx_sp_scan_kernel<<<1, 1024, 0, st>>>(B, L.rec_cap, L.text_cap, L.out_cap, L.gather_parts);
     if (L.ev_scan_done) cudaEventRecord(L.ev_scan_done, st);
     for (uint32_t part = 0; part < L.gather_parts; ++part) {
-        sx_sp_gather_kernel<Dec><<<L.grid_chunks, kSpThreads, 0, st>>>(P, O, X, B, part, L.gather_parts);
+        sx_sp_gather_kernel<Dec><<<L.grid_chunks / L.gather_parts + 1, kSpThreads, 0, st>>>(P, O, X, B, part, L.gather_parts);
         if (L.ev_part) cudaEventRecord(L.ev_part[part], st);
     }
     if (ev) cudaEventRecord(ev[6], st);
