@@ -126,6 +126,39 @@ enum { SX_RANGE_PREFIX_UNKNOWN = 1 };
 sx_finding_collection* sx_scan_range(sx_scanner_state*, int input_file_id, const void* buf, size_t len, size_t slice_len,
                                      int buf_is_device, int is_last, size_t lo, size_t hi, int flags, void* cuda_stream);
 
+/* Asynchronous forms.  The reference overlaps scanning with merging / printing: every mission has a scanner thread
+ * that sends its collections through a bounded channel to the merger thread (main.rs:98 sync_channel, :161 tx.send,
+ * :103-141 merger).  Here every state owns a worker thread: the *_async calls return a handle at once, the scans of
+ * one state run in call order (so chained calls see the ScannerState the previous call left), scans of different
+ * states -- on the same or on different GPUs -- run side by side.  sx_fc_wait blocks until the collection is complete,
+ * returns it (NULL on error: sx_last_error* of the WAITING thread is set) and consumes the handle.  buf must stay
+ * valid until the wait returns. */
+typedef struct sx_pending sx_pending;
+sx_pending* sx_scan_stream_async(sx_scanner_state*, int input_file_id, const void* buf, size_t len, size_t slice_len,
+                                 int buf_is_device, int is_last, void* cuda_stream);
+sx_pending* sx_scan_range_async(sx_scanner_state*, int input_file_id, const void* buf, size_t len, size_t slice_len,
+                                int buf_is_device, int is_last, size_t lo, size_t hi, int flags, void* cuda_stream);
+int sx_pending_ready(const sx_pending*); /* 1: sx_fc_wait will not block */
+sx_finding_collection* sx_fc_wait(sx_pending*);
+
+/* Streaming driver: the loop of main.rs:143-167 over the input iterator of input.rs:104-168, for the GPU.  One input is
+ * pulled through `read` (returns the bytes it stored, 0 at the end of the input; short reads are fine) in pieces of
+ * chunk_bytes (a positive multiple of 4096: the slice grid inside the library is then the reference's, and restarts
+ * with every input like input.rs), each piece is uploaded once per device (double buffered: the read and the upload of
+ * piece k + 1 overlap the scans of piece k) and scanned by every state side by side; `batch` gets the piece's
+ * collections in state order and owns them (sx_fc_free) -- sx_merge over them gives the order of main.rs:118-136;
+ * a non-zero return of `batch` stops the run and is returned.  Carry, pending decoder bytes and byte counters stay in
+ * the states: call once per input with the reference's 1-based file label (-1: none).  The "last input buffer" flag is
+ * never set, like the reference's CLI (input.rs:130-137).  Returns 0, batch's non-zero value, or -1 on error. */
+typedef size_t (*sx_read_fn)(void* user, uint8_t* dst, size_t cap);
+typedef int (*sx_batch_fn)(void* user, int input_file_id, sx_finding_collection* const* fcs, size_t n_states);
+int sx_scan_reader(sx_scanner_state* const* states, size_t n_states, int input_file_id, sx_read_fn read, void* read_user,
+                   size_t chunk_bytes, sx_batch_fn batch, void* batch_user);
+/* The same with a file (path == NULL: stdin); an unreadable file is reported on stderr and scanned as an empty input
+ * (input.rs:78-84). */
+int sx_scan_file(sx_scanner_state* const* states, size_t n_states, int input_file_id, const char* path, size_t chunk_bytes,
+                 sx_batch_fn batch, void* batch_user);
+
 /* FindingCollection accessors (finding_collection.rs:31-50, :371-415). */
 size_t sx_fc_len(const sx_finding_collection*);
 const sx_finding* sx_fc_get(const sx_finding_collection*, size_t i);

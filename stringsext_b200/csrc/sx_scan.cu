@@ -23,6 +23,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -792,6 +795,38 @@ struct PieceEvents {
     cudaEvent_t gp[kGatherParts] = {nullptr, nullptr, nullptr, nullptr};  // after every part of its gather
 };
 
+// Asynchronous boundary: the reference's scanner threads hand their collections to the merger through a channel
+// (main.rs:98, :161); here every state owns one worker thread that runs its scans in call order and a handle per call
+// that the consumer waits on (sx_fc_wait).
+struct sx_pending {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool done = false;
+    sx_finding_collection* fc = nullptr;
+    int err = SX_OK;
+    std::string msg;
+};
+struct ScanWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false;
+    void run() {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                job = std::move(q.front());
+                q.pop_front();
+            }
+            job();
+        }
+    }
+};
+
 struct sx_scanner_state {
     sx_mission m;
     int device;
@@ -854,6 +889,8 @@ struct sx_scanner_state {
     bool have_history = false;
     size_t last_nrec = 0, last_ntext = 0, last_len = 0;  // previous scan: sizes the next pinned set (+ 1/16)
     sx_scan_stats stats;
+    struct ScanWorker* worker = nullptr;  // asynchronous calls (sx_scan_*_async): one thread per state, calls run in call order
+    cudaStream_t own = nullptr;           // the streaming driver's scans of this state (sx_scan_reader)
 };
 
 // uninitialised storage: value-initialising tens of MB per call showed up in the whole-job time
@@ -1101,6 +1138,7 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
          cuda_ok(cudaStreamCreateWithPriority(&ss->sB, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate") &&
          cuda_ok(cudaStreamCreateWithPriority(&ss->sC, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate") &&
          cuda_ok(cudaEventCreateWithFlags(&ss->ev_setup, cudaEventDisableTiming), "cudaEventCreate");
+    ok = ok && cuda_ok(cudaStreamCreateWithFlags(&ss->own, cudaStreamNonBlocking), "cudaStreamCreate");
     for (int i = 0; ok && i < sx_scanner_state::kLanes; ++i)
         ok = cuda_ok(cudaStreamCreateWithPriority(&ss->sBk[i], cudaStreamNonBlocking, prio_hi), "cudaStreamCreate") &&
              cuda_ok(cudaStreamCreateWithPriority(&ss->sidek[i], cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
@@ -1110,6 +1148,16 @@ sx_scanner_state* sx_scanner_state_new(const sx_mission* m, int device) {
 
 void sx_scanner_state_free(sx_scanner_state* ss) {
     if (!ss) return;
+    if (ss->worker) {  // pending asynchronous scans finish first
+        {
+            std::lock_guard<std::mutex> lk(ss->worker->mu);
+            ss->worker->stop = true;
+        }
+        ss->worker->cv.notify_all();
+        if (ss->worker->th.joinable()) ss->worker->th.join();
+        delete ss->worker;
+        ss->worker = nullptr;
+    }
     int prev_dev = -1;
     cudaGetDevice(&prev_dev);
     cudaSetDevice(ss->device);
@@ -1127,7 +1175,7 @@ void sx_scanner_state_free(sx_scanner_state* ss) {
         for (auto e : pe.sord) if (e) cudaEventDestroy(e);
         for (auto e : pe.gp) if (e) cudaEventDestroy(e);
     }
-    for (cudaStream_t q : {ss->side, ss->sA, ss->sB, ss->sC}) if (q) cudaStreamDestroy(q);
+    for (cudaStream_t q : {ss->side, ss->sA, ss->sB, ss->sC, ss->own}) if (q) cudaStreamDestroy(q);
     for (cudaStream_t q : ss->sBk) if (q) cudaStreamDestroy(q);
     for (cudaStream_t q : ss->sidek) if (q) cudaStreamDestroy(q);
     if (ss->ev_setup) cudaEventDestroy(ss->ev_setup);
@@ -2175,6 +2223,173 @@ extern "C" size_t sx_merge(const sx_finding_collection* const* fcs, size_t n, co
         return a->mission_id < b->mission_id;
     });
     return k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Asynchronous calls and the streaming driver
+// ---------------------------------------------------------------------------------------------
+static sx_pending* submit_scan(sx_scanner_state* ss, std::function<sx_finding_collection*()> fn) {
+    if (!ss) { set_err(SX_ERR_ARGUMENT, "state is NULL"); return nullptr; }
+    if (!ss->worker) {
+        ss->worker = new ScanWorker();
+        ss->worker->th = std::thread([w = ss->worker] { w->run(); });
+    }
+    sx_pending* p = new sx_pending();
+    {
+        std::lock_guard<std::mutex> lk(ss->worker->mu);
+        ss->worker->q.emplace_back([p, fn = std::move(fn)] {
+            sx_finding_collection* fc = fn();
+            std::lock_guard<std::mutex> lk2(p->mu);
+            p->fc = fc;
+            if (!fc) { p->err = g_err_code; p->msg = g_err_msg; }  // the worker thread's error travels with the handle
+            p->done = true;
+            p->cv.notify_all();
+        });
+    }
+    ss->worker->cv.notify_one();
+    return p;
+}
+
+extern "C" sx_pending* sx_scan_stream_async(sx_scanner_state* ss, int input_file_id, const void* buf, size_t len, size_t slice_len,
+                                            int buf_is_device, int is_last, void* cuda_stream) {
+    return submit_scan(ss, [=] { return scan_impl(ss, input_file_id, buf, len, slice_len, buf_is_device, is_last, 0, len, 0, cuda_stream); });
+}
+extern "C" sx_pending* sx_scan_range_async(sx_scanner_state* ss, int input_file_id, const void* buf, size_t len, size_t slice_len,
+                                           int buf_is_device, int is_last, size_t lo, size_t hi, int flags, void* cuda_stream) {
+    return submit_scan(ss, [=] {
+        return scan_impl(ss, input_file_id, buf, len, slice_len, buf_is_device, is_last, lo, hi, (flags & SX_RANGE_PREFIX_UNKNOWN) ? 1 : 0, cuda_stream);
+    });
+}
+extern "C" int sx_pending_ready(const sx_pending* p) {
+    if (!p) return 1;
+    std::lock_guard<std::mutex> lk(const_cast<sx_pending*>(p)->mu);
+    return p->done ? 1 : 0;
+}
+extern "C" sx_finding_collection* sx_fc_wait(sx_pending* p) {
+    if (!p) { set_err(SX_ERR_ARGUMENT, "handle is NULL"); return nullptr; }
+    sx_finding_collection* fc;
+    {
+        std::unique_lock<std::mutex> lk(p->mu);
+        p->cv.wait(lk, [&] { return p->done; });
+        fc = p->fc;
+        if (!fc) set_err(p->err, p->msg);
+    }
+    delete p;
+    return fc;
+}
+
+// Streaming driver: main.rs:143-167 over input.rs:104-168 for the GPU.  One input (file, pipe, anything behind `read`) is
+// read in pieces of chunk_bytes (a multiple of 4096, so the slice grid inside the library is the reference's: every
+// input starts a new grid, input.rs:104-168), every piece is uploaded once per device and scanned by every state -- the
+// states' scans run side by side on their worker threads, the read and the upload of piece k + 1 overlap the scan of
+// piece k (two pinned staging buffers, two device buffers per device).  `batch` receives the piece's collections in
+// state order (they are the caller's: sx_fc_free); merging them with sx_merge gives the order of main.rs:118-136.
+// Carry, pending decoder bytes and byte counters stay in the states, so the caller simply calls this once per input
+// with the reference's 1-based file label (or -1).  The "last buffer" flag is never set (input.rs:130-137).
+extern "C" int sx_scan_reader(sx_scanner_state* const* states, size_t n_states, int input_file_id, sx_read_fn read, void* read_user,
+                              size_t chunk_bytes, sx_batch_fn batch, void* batch_user) {
+    const int fail = -1;
+    if (!states || n_states == 0 || !read || !batch) { set_err(SX_ERR_ARGUMENT, "states, read and batch must be given"); return fail; }
+    if (chunk_bytes == 0 || (chunk_bytes % 4096) != 0) { set_err(SX_ERR_ARGUMENT, "chunk_bytes must be a positive multiple of 4096"); return fail; }
+    std::vector<int> devices;
+    for (size_t i = 0; i < n_states; ++i) {
+        if (!states[i]) { set_err(SX_ERR_ARGUMENT, "state is NULL"); return fail; }
+        if (std::find(devices.begin(), devices.end(), states[i]->device) == devices.end()) devices.push_back(states[i]->device);
+    }
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    struct Dev { int id; uint8_t* buf[2] = {nullptr, nullptr}; cudaStream_t cs = nullptr; cudaEvent_t up[2] = {nullptr, nullptr}; };
+    std::vector<Dev> devs(devices.size());
+    uint8_t* host[2] = {nullptr, nullptr};
+    int rc = 0;
+    auto cleanup = [&] {
+        for (auto& d : devs) {
+            cudaSetDevice(d.id);
+            for (int k = 0; k < 2; ++k) { if (d.buf[k]) cudaFree(d.buf[k]); if (d.up[k]) cudaEventDestroy(d.up[k]); }
+            if (d.cs) cudaStreamDestroy(d.cs);
+        }
+        for (int k = 0; k < 2; ++k) if (host[k]) cudaFreeHost(host[k]);
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    };
+    bool ok = true;
+    for (int k = 0; ok && k < 2; ++k) ok = cuda_ok(cudaHostAlloc((void**)&host[k], chunk_bytes, cudaHostAllocPortable), "cudaHostAlloc");
+    for (size_t i = 0; ok && i < devs.size(); ++i) {
+        devs[i].id = devices[i];
+        ok = cuda_ok(cudaSetDevice(devs[i].id), "cudaSetDevice") && cuda_ok(cudaStreamCreateWithFlags(&devs[i].cs, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int k = 0; ok && k < 2; ++k)
+            ok = cuda_ok(cudaMalloc(&devs[i].buf[k], chunk_bytes), "cudaMalloc") && cuda_ok(cudaEventCreateWithFlags(&devs[i].up[k], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    if (!ok) { cleanup(); return fail; }
+    auto fill = [&](int k) {  // short reads are retried: only the end of the input ends a piece early
+        size_t n = 0;
+        while (n < chunk_bytes) {
+            const size_t got = read(read_user, host[k] + n, chunk_bytes - n);
+            if (got == 0) break;
+            n += got;
+        }
+        return n;
+    };
+    auto upload = [&](int k, size_t n) {
+        for (auto& d : devs) {
+            if (!cuda_ok(cudaSetDevice(d.id), "cudaSetDevice") ||
+                !cuda_ok(cudaMemcpyAsync(d.buf[k], host[k], n, cudaMemcpyHostToDevice, d.cs), "cudaMemcpyAsync") ||
+                !cuda_ok(cudaEventRecord(d.up[k], d.cs), "cudaEventRecord")) return false;
+        }
+        return true;
+    };
+    int k = 0;
+    size_t n = fill(k);
+    if (n && !upload(k, n)) { cleanup(); return fail; }
+    std::vector<sx_pending*> pend(n_states);
+    std::vector<sx_finding_collection*> fcs(n_states);
+    while (n && rc == 0) {
+        // piece k is on its way to every device: scans wait for the upload on their own streams
+        for (size_t i = 0; i < n_states; ++i) {
+            sx_scanner_state* ss = states[i];
+            const Dev& d = devs[std::find(devices.begin(), devices.end(), ss->device) - devices.begin()];
+            cudaSetDevice(d.id);
+            cudaStreamWaitEvent(ss->own, d.up[k], 0);
+            pend[i] = sx_scan_stream_async(ss, input_file_id, d.buf[k], n, 4096, 1, 0, ss->own);
+        }
+        // meanwhile: read and upload the next piece (its buffers were released when the scans of piece k - 1 returned)
+        const int k2 = k ^ 1;
+        size_t n2 = 0;
+        bool up_ok = true;
+        if (n == chunk_bytes) {
+            for (auto& d : devs) { cudaSetDevice(d.id); cudaEventSynchronize(d.up[k]); }  // host[k2] was read by the copy of piece k - 1: long done; host[k] must be free before the NEXT fill
+            n2 = fill(k2);
+            if (n2) up_ok = upload(k2, n2);
+        }
+        bool scan_ok = true;
+        for (size_t i = 0; i < n_states; ++i) {
+            fcs[i] = pend[i] ? sx_fc_wait(pend[i]) : nullptr;
+            if (!fcs[i]) scan_ok = false;
+        }
+        if (!scan_ok || !up_ok) {
+            for (auto* fc : fcs) if (fc) sx_fc_free(fc);
+            cleanup();
+            return fail;
+        }
+        rc = batch(batch_user, input_file_id, fcs.data(), n_states);
+        k = k2;
+        n = n2;
+    }
+    for (auto& d : devs) { cudaSetDevice(d.id); cudaStreamSynchronize(d.cs); }
+    cleanup();
+    return rc;
+}
+
+static size_t file_read_fn(void* user, uint8_t* dst, size_t cap) { return fread(dst, 1, cap, (FILE*)user); }
+extern "C" int sx_scan_file(sx_scanner_state* const* states, size_t n_states, int input_file_id, const char* path, size_t chunk_bytes,
+                            sx_batch_fn batch, void* batch_user) {
+    FILE* f = path ? fopen(path, "rb") : stdin;
+    if (!f) {  // input.rs:78-84: reported, then treated as an empty input
+        fprintf(stderr, "Error: can not read file `%s`\n", path);
+        return 0;
+    }
+    const int rc = sx_scan_reader(states, n_states, input_file_id, file_read_fn, f, chunk_bytes, batch, batch_user);
+    if (path) fclose(f);
+    return rc;
 }
 
 extern "C" int sx_fill_random(void* device_buf, size_t len, uint64_t seed, uint64_t stream_offset, int device, void* cuda_stream) {

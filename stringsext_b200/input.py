@@ -6,15 +6,16 @@ an empty piece marks the switch to the next file, the file label is 1-based (Non
 scanner's results depend on -- the "this is the very last piece" flag never reaches the consumer as true
 (input.rs:130-137 returns None in exactly that case).
 
-`scan_files` is the driver of main.rs:143-167 for the GPU: instead of one `FindingCollection::from` per 4096-byte
-slice it hands the library large pieces (`sx_scan_stream` folds over the slices inside the call) and keeps the GPU
-fed: two pinned staging buffers and two device buffers per GPU, piece k+1 is read from disk and copied to the device
-on a copy stream while piece k is being scanned.  torch is used for the pinned / device memory and the streams only.
+`scan_inputs` / `scan_files` drive main.rs:143-167 for the GPU through the library's C streaming driver
+(`sx_scan_file` / `sx_scan_reader`, include/stringsext_b200.h): instead of one `FindingCollection::from` per 4096-byte
+slice the library gets large pieces (`sx_scan_stream` folds over the slices inside the call) and keeps the GPUs fed:
+two pinned staging buffers and two device buffers per GPU, piece k+1 is read and copied to the devices while piece k
+is being scanned, and the missions' scans run side by side (one worker thread per ScannerState).  No torch involved.
 """
 from __future__ import annotations
 
 import sys
-from typing import BinaryIO, Iterator, List, Optional, Sequence, Tuple
+from typing import BinaryIO, Callable, Iterator, List, Optional, Sequence, Tuple
 
 from .scanner import FindingCollection, ScannerState
 
@@ -55,85 +56,70 @@ class Slicer:
             yield b, idx, False
 
 
-def scan_files(states: Sequence[ScannerState], inputs: Sequence[str], chunk_bytes: int = 256 << 20,
-               stdin: Optional[BinaryIO] = None) -> Iterator[Tuple[Optional[int], List[FindingCollection]]]:
-    """Scan the concatenated inputs with every state (one per mission; they may sit on different GPUs).
+def scan_inputs(states: Sequence[ScannerState], inputs: Sequence[str], on_batch: Callable[[Optional[int], List[FindingCollection]], None],
+                chunk_bytes: int = 256 << 20, stdin: Optional[BinaryIO] = None) -> None:
+    """Stream the concatenated inputs through every state (one per mission; they may sit on different GPUs) with the
+    library's streaming driver `sx_scan_file` / `sx_scan_reader` (C: pinned double buffering, one upload per device,
+    the states' scans side by side on their worker threads, read + upload of piece k + 1 beside the scan of piece k).
 
-    Yields (input_file_id, [one FindingCollection per state]) per piece of at most chunk_bytes (a multiple of 4096, so
-    the slice grid inside the library is the reference's); merging a piece's collections with `merge` gives the order
-    of main.rs:118-136.  Equivalent to feeding `Slicer`'s slices one by one to `ScannerState.scan` (tests compare)."""
-    import torch
+    `on_batch(input_file_id, [one FindingCollection per state])` is called per piece of at most chunk_bytes (a multiple of
+    4096, so the slice grid inside the library is the reference's); merging a piece's collections with `merge` gives the
+    order of main.rs:118-136.  Equivalent to feeding `Slicer`'s slices one by one to `ScannerState.scan` (tests compare).
+    Inputs read from `stdin` (or a Python file object) go through the reader-callback form; note that the library
+    normalises the grid to full 4096-byte slices, while the reference's `Read::read` (input.rs:118) turns every short
+    read of a pipe into its own slice -- only regular files are reproducible in the reference."""
+    import ctypes as C
+
+    from .scanner import BATCH_FN, READ_FN, load_library
 
     assert chunk_bytes % INPUT_BUF_LEN == 0 and chunk_bytes > 0
+    L = load_library()
+    harr = (C.c_void_p * len(states))(*[s._h for s in states])
+    err: list = []
+
+    def batch(_user, fid, fcs, n):
+        try:
+            file_id = None if fid < 0 else fid
+            on_batch(file_id, [states[i]._collect(fcs[i], fid) for i in range(n)])
+            return 0
+        except BaseException as e:  # noqa: BLE001 -- must not unwind through C
+            err.append(e)
+            return 1
+
+    cb = BATCH_FN(batch)
     from_stdin = len(inputs) == 0 or (len(inputs) == 1 and inputs[0] == "-")
-    devices = sorted({s.device for s in states})
-    host = [torch.empty(chunk_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    hview = [memoryview(h.numpy()) for h in host]
-    dev = {d: [torch.empty(chunk_bytes, dtype=torch.uint8, device=f"cuda:{d}") for _ in range(2)] for d in devices}
-    copy_stream = {d: torch.cuda.Stream(device=d) for d in devices}
-    copied = {d: [None, None] for d in devices}   # event: piece in dev[d][k] is complete
-    scanned = {d: [None, None] for d in devices}  # event: dev[d][k] may be overwritten
-    host_free = [None, None]                      # events: host[k] has been copied to every device
+    if from_stdin:
+        rd = stdin if stdin is not None else sys.stdin.buffer
 
-    def pieces():
-        """(file id, reader) pairs in input order; an unreadable file is an empty input."""
-        if from_stdin:
-            yield None, (stdin if stdin is not None else sys.stdin.buffer)
-            return
-        for i, p in enumerate(inputs, start=1):
-            yield i, Slicer._open(p)
+        def read(_user, dst, cap):
+            b = rd.read(cap)
+            if b:
+                C.memmove(dst, b, len(b))
+            return len(b)
 
-    def fill(reader, k) -> int:
-        """Read up to chunk_bytes into host[k] (short reads are retried: only EOF ends a piece early)."""
-        if host_free[k] is not None:
-            for ev in host_free[k]:
-                ev.synchronize()
-            host_free[k] = None
-        n = 0
-        while reader is not None and n < chunk_bytes:
-            got = reader.readinto(hview[k][n:])
-            if not got:
-                break
-            n += got
-        return n
+        rc = L.sx_scan_reader(harr, len(states), -1, READ_FN(read), None, chunk_bytes, cb, None)
+        if err:
+            raise err[0]
+        if rc < 0:
+            from .scanner import _raise_last
 
-    def upload(k, n):
-        evs = []
-        for d in devices:
-            with torch.cuda.device(d), torch.cuda.stream(copy_stream[d]):
-                if scanned[d][k] is not None:
-                    copy_stream[d].wait_event(scanned[d][k])
-                dev[d][k][:n].copy_(host[k][:n], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream[d])
-                copied[d][k] = ev
-                evs.append(ev)
-        host_free[k] = evs
+            _raise_last()
+        return
+    for i, p in enumerate(inputs, start=1):
+        rc = L.sx_scan_file(harr, len(states), i, p.encode(), chunk_bytes, cb, None)
+        if err:
+            raise err[0]
+        if rc < 0:
+            from .scanner import _raise_last
 
-    for fid, reader in pieces():
-        k = 0
-        n = fill(reader, k)
-        if n:
-            upload(k, n)
-        while n:
-            # next piece of the same file: disk read + H2D overlap the scan of the current one
-            k2 = k ^ 1
-            n2 = fill(reader, k2) if n == chunk_bytes else 0
-            if n2:
-                upload(k2, n2)
-            out = []
-            for s in states:
-                d = s.device
-                with torch.cuda.device(d):
-                    torch.cuda.current_stream(d).wait_event(copied[d][k])
-                    out.append(s.scan_stream(None, False, INPUT_BUF_LEN, fid, device_ptr=dev[d][k].data_ptr(), length=n,
-                                             cuda_stream=torch.cuda.current_stream(d).cuda_stream))
-            for d in devices:
-                with torch.cuda.device(d):
-                    ev = torch.cuda.Event()
-                    ev.record(torch.cuda.current_stream(d))
-                    scanned[d][k] = ev
-            yield fid, out
-            k, n = k2, n2
-        if reader is not None and not from_stdin:
-            reader.close()
+            _raise_last()
+
+
+def scan_files(states: Sequence[ScannerState], inputs: Sequence[str], chunk_bytes: int = 256 << 20,
+               stdin: Optional[BinaryIO] = None) -> Iterator[Tuple[Optional[int], List[FindingCollection]]]:
+    """Generator form of `scan_inputs`: yields (input_file_id, [one FindingCollection per state]) per piece.  The C driver
+    calls back and cannot be suspended, so the pieces are collected first; use `scan_inputs` with a callback for inputs
+    whose findings do not fit in memory."""
+    out: list = []
+    scan_inputs(states, inputs, lambda fid, fcs: out.append((fid, fcs)), chunk_bytes, stdin)
+    yield from out

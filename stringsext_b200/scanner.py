@@ -97,6 +97,9 @@ class ScanStats(C.Structure):
     ]
 
 
+READ_FN = C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)          # sx_read_fn
+BATCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_size_t)  # sx_batch_fn
+
 _lib = None
 
 
@@ -134,6 +137,15 @@ def load_library():
     L.sx_finding_collection_from.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_int]
     L.sx_scan_stream.restype = C.c_void_p
     L.sx_scan_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    L.sx_scan_stream_async.restype = C.c_void_p
+    L.sx_scan_stream_async.argtypes = L.sx_scan_stream.argtypes
+    L.sx_scan_range_async.restype = C.c_void_p
+    L.sx_scan_range_async.argtypes = L.sx_scan_range.argtypes
+    L.sx_pending_ready.argtypes = [C.c_void_p]
+    L.sx_fc_wait.restype = C.c_void_p
+    L.sx_fc_wait.argtypes = [C.c_void_p]
+    L.sx_scan_reader.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, READ_FN, C.c_void_p, C.c_size_t, BATCH_FN, C.c_void_p]
+    L.sx_scan_file.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_char_p, C.c_size_t, BATCH_FN, C.c_void_p]
     L.sx_fc_len.restype = C.c_size_t
     L.sx_fc_len.argtypes = [C.c_void_p]
     L.sx_fc_get.restype = C.POINTER(_CFinding)
@@ -168,7 +180,8 @@ def exported_symbols() -> List[str]:
         "sx_device_count", "sx_scanner_state_new", "sx_scanner_state_free", "sx_scanner_state_reset", "sx_scanner_state_consumed_bytes",
         "sx_scanner_state_maybe_cut", "sx_scanner_state_leftover", "sx_finding_collection_from", "sx_scan_stream",
         "sx_fc_len", "sx_fc_get", "sx_fc_data", "sx_fc_first_byte_position", "sx_fc_str_buf_overflow", "sx_fc_free",
-        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_set_sparse", "sx_scanner_state_set_direct_output", "sx_scanner_state_set_pieces", "sx_scan_range", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
+        "sx_merge", "sx_scanner_state_last_stats", "sx_scanner_state_set_prefilter", "sx_scanner_state_set_tma", "sx_scanner_state_set_sparse", "sx_scanner_state_set_direct_output", "sx_scanner_state_set_pieces", "sx_scan_range", "sx_scan_stream_async", "sx_scan_range_async", "sx_pending_ready", "sx_fc_wait",
+        "sx_scan_reader", "sx_scan_file", "sx_scanner_state_last_window_list", "sx_fill_random", "sx_last_error_code", "sx_last_error",
     ]
 
 
@@ -355,6 +368,52 @@ class ScannerState:
                 _raise_last()
             return RawCollection(fc)
         return self._collect(fc, fid)
+
+
+    def scan_stream_async(self, buf=None, is_last: bool = False, slice_len: int = 4096, input_file_id: Optional[int] = None,
+                          device_ptr: Optional[int] = None, length: Optional[int] = None, cuda_stream: int = 0,
+                          lo: Optional[int] = None, hi: Optional[int] = None, prefix_unknown: bool = False) -> "PendingScan":
+        """sx_scan_stream_async / sx_scan_range_async: returns at once; `.wait()` gives the collection.  Scans of one state
+        run in call order, scans of different states side by side (main.rs:98-167: scanner threads + channel)."""
+        L = load_library()
+        fid = -1 if input_file_id is None else input_file_id
+        keep = None
+        if device_ptr is not None:
+            p, n, isdev = C.c_void_p(device_ptr), int(length), 1
+        elif isinstance(buf, (bytes, bytearray)):
+            keep = bytes(buf)
+            p, n, isdev = C.cast(C.c_char_p(keep), C.c_void_p), len(keep), 0
+        else:
+            keep = buf
+            p, n, isdev = C.c_void_p(buf.ctypes.data), int(buf.nbytes if length is None else length), 0
+        if lo is None and hi is None:
+            h = L.sx_scan_stream_async(self._h, fid, p, n, slice_len, isdev, 1 if is_last else 0, C.c_void_p(cuda_stream))
+        else:
+            h = L.sx_scan_range_async(self._h, fid, p, n, slice_len, isdev, 1 if is_last else 0, int(lo or 0), n if hi is None else int(hi),
+                                      RANGE_PREFIX_UNKNOWN if prefix_unknown else 0, C.c_void_p(cuda_stream))
+        if not h:
+            _raise_last()
+        return PendingScan(self, h, fid, keep)
+
+
+class PendingScan:
+    """Handle of an asynchronous scan (sx_pending)."""
+
+    def __init__(self, state, h, fid, keep):
+        self._state, self._h, self._fid, self._keep = state, h, fid, keep
+
+    def ready(self) -> bool:
+        return self._h is None or bool(load_library().sx_pending_ready(self._h))
+
+    def wait(self, raw: bool = False):
+        h, self._h = self._h, None
+        fc = load_library().sx_fc_wait(h)
+        self._keep = None
+        if raw:
+            if not fc:
+                _raise_last()
+            return RawCollection(fc)
+        return self._state._collect(fc, self._fid)
 
 
 class RawCollection:

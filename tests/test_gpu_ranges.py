@@ -122,3 +122,43 @@ def test_range_argument_checks():
     with pytest.raises(sx.ScannerError):
         gs.scan_stream(buf, False, 4096, lo=0, hi=4096, prefix_unknown=True)
     assert len(gs.scan_stream(buf, False, 4096, lo=4096, hi=4096).v) == 0
+
+
+def test_offsets_beyond_4gib_vs_oracle():
+    """One device-resident call of 5 GiB + 12 KiB: stream offsets, window indices and text offsets beyond 2^32
+    (finding_collection.rs:260: `position` is u64).  Ranges below, across and above the 4 GiB line are regenerated on
+    the host and compared with the oracle finding by finding; the ScannerState counts every byte."""
+    import numpy as np
+    import torch
+
+    size = (5 << 30) + 4096 * 3
+    if torch.cuda.mem_get_info(0)[0] < size + (4 << 30):
+        pytest.skip("needs ~10 GB of free device memory")
+    seed, n = 12, 8
+    m = M.Mission.for_label("utf-8", n)
+    t = torch.empty(size, dtype=torch.uint8, device="cuda:0")
+    L = sx.load_library()
+    assert L.sx_fill_random(t.data_ptr(), size, seed, 0, 0, None) == 0
+    planted = {}
+    for off in ((1 << 32) - 20, (1 << 32) + 4096 * 7 - 3, (9 << 29) + 5, size - 60):  # straddling 2^32, a slice boundary, the tail
+        s = b"\x00planted across the line: \xc3\xa4\xc3\xb6\xc3\xbc 0123456789\x00"
+        planted[off] = s
+        t[off:off + len(s)] = torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda()
+    torch.cuda.synchronize()
+    gs = sx.ScannerState(m)
+    raw = gs.scan_stream(None, False, 4096, device_ptr=t.data_ptr(), length=size, raw=True)
+    assert gs.consumed_bytes == size and gs.last_stats.windows_total == (size + 127) // 128
+    halo = 1 << 20
+    for a, b in ((0, 8 << 20), ((1 << 32) - (8 << 20), (1 << 32) + (8 << 20)), (9 << 29, (9 << 29) + (8 << 20)), (size - (8 << 20) - 4096 * 3, size)):
+        data = corpus.sx_mix_bytes(seed, a - min(a, halo), b - a + min(a, halo))
+        for off, s in planted.items():
+            lo, hi = max(off, a - min(a, halo)), min(off + len(s), b)
+            if lo < hi:
+                data[lo - (a - min(a, halo)):hi - (a - min(a, halo))] = np.frombuffer(s[lo - off:hi - off], dtype=np.uint8)
+        mo = dataclasses.replace(m, counter_offset=a - min(a, halo))
+        exp = [f for f in oracle_findings(oracle_state(mo).scan_stream(data, False, 4096)) if a <= f[0] < b]
+        got = raw.select(a, b)
+        assert got == exp, (a, b)
+        assert len(exp) > 1000
+    assert any(p >= (1 << 32) and b"planted across" in s for p, _, s, _ in raw.select(1 << 32, (1 << 32) + (1 << 20)))
+    raw.close()
