@@ -233,8 +233,8 @@ __device__ __forceinline__ Carry sp_member(const ScanParams& P, const SparseBufs
 // consecutive entries, CTA b takes chunks b, b + gridDim.x, ...
 // 6 CTAs of 128 threads per SM (80 registers): measured best for this latency-bound kernel (4: 0.35 ms, 6: 0.29 ms, 8: 0.39 ms
 // before the one-pass heads)
-template <class Dec>
-__global__ void __launch_bounds__(kSpThreads, 6)
+template <class Dec, int MINB>
+__global__ void __launch_bounds__(kSpThreads, MINB)
 sx_sp_heads_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     const long long NE = (long long)B.ctl->ne;
@@ -419,8 +419,8 @@ __device__ __forceinline__ bool sp_next_adjacent(const ExactCfg& X, long long NE
     return w + 1 == X.w_end && !range_is_tail(X);
 }
 
-template <class Dec>
-__global__ void __launch_bounds__(kSpThreads, 4)
+template <class Dec, int MINB>
+__global__ void __launch_bounds__(kSpThreads, MINB)
 sx_sp_ext_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     __shared__ unsigned long long sa[kSpThreads / 32], sb[kSpThreads / 32];
@@ -526,8 +526,8 @@ static __global__ void __launch_bounds__(1024) sx_sp_scan_kernel(const SparseBuf
     }
 }
 
-template <class Dec>
-__global__ void __launch_bounds__(kSpThreads, 4)
+template <class Dec, int MINB>
+__global__ void __launch_bounds__(kSpThreads, MINB)
 sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const ExactCfg X, const SparseBufs B, uint32_t part, uint32_t nparts) {
     __shared__ Utf8Tables T;
     __shared__ uint32_t wa[8], wb[8];
@@ -696,13 +696,13 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
         cudaGetDevice(&dev);
         if (done_dev != dev) {
             const int co = cudaSharedmemCarveoutMaxShared;
-            cudaFuncSetAttribute(sx_sp_heads_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_heads_kernel<Dec, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_members_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_declined_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_fix_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_late_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(sx_sp_ext_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(sx_sp_gather_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_ext_kernel<Dec, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_gather_kernel<Dec, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_snapshot_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_list_compact_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
@@ -710,7 +710,15 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
         }
     }
     if (ev) cudaEventRecord(ev[1], st);
-    sx_sp_heads_kernel<Dec><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+    {
+        static int minb = -1;
+        // CTAs per SM of the heads kernel, measured (profiles/r02_tuning.txt): 4: 0.214 ms, 5: 0.201, 6: 0.237, 8: 0.231
+        if (minb < 0) { const char* hv = getenv("SX_HEADS_MINB"); minb = hv ? atoi(hv) : 5; }
+        if (minb == 4) sx_sp_heads_kernel<Dec, 4><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+        else if (minb == 5) sx_sp_heads_kernel<Dec, 5><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+        else if (minb == 8) sx_sp_heads_kernel<Dec, 8><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+        else sx_sp_heads_kernel<Dec, 6><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+    }
     if (ev) cudaEventRecord(ev[2], st);
     sx_sp_snapshot_kernel<<<1, 1, 0, st>>>(B.ctl);
     cudaEventRecord(evs[0], st);
@@ -723,13 +731,21 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
     sx_sp_fix_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
     sx_sp_late_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
     if (ev) cudaEventRecord(ev[4], st);
-    sx_sp_ext_kernel<Dec><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+    static int xminb = -1, gminb = -1;
+    // CTAs per SM, measured (profiles/r02_tuning.txt): ext 4: 0.044 ms, 6: 0.037, 8: 0.037; gather 4: 0.184 ms, 6: 0.163, 8: 0.155
+    if (xminb < 0) { const char* e1 = getenv("SX_EXT_MINB"); xminb = e1 ? atoi(e1) : 6; const char* e2 = getenv("SX_GATHER_MINB"); gminb = e2 ? atoi(e2) : 8; }
+    if (xminb == 8) sx_sp_ext_kernel<Dec, 8><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+    else if (xminb == 6) sx_sp_ext_kernel<Dec, 6><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
+    else sx_sp_ext_kernel<Dec, 4><<<L.grid_chunks, kSpThreads, 0, st>>>(P, X, B);
     if (ev) cudaEventRecord(ev[5], st);
     if (L.ev_scan_prev) cudaStreamWaitEvent(st, L.ev_scan_prev, 0);
     sx_sp_scan_kernel<<<1, 1024, 0, st>>>(B, L.rec_cap, L.text_cap, L.out_cap, L.gather_parts);
     if (L.ev_scan_done) cudaEventRecord(L.ev_scan_done, st);
     for (uint32_t part = 0; part < L.gather_parts; ++part) {
-        sx_sp_gather_kernel<Dec><<<L.grid_chunks / L.gather_parts + 1, kSpThreads, 0, st>>>(P, O, X, B, part, L.gather_parts);
+        const unsigned gg = L.grid_chunks / L.gather_parts + 1;
+        if (gminb == 8) sx_sp_gather_kernel<Dec, 8><<<gg, kSpThreads, 0, st>>>(P, O, X, B, part, L.gather_parts);
+        else if (gminb == 6) sx_sp_gather_kernel<Dec, 6><<<gg, kSpThreads, 0, st>>>(P, O, X, B, part, L.gather_parts);
+        else sx_sp_gather_kernel<Dec, 4><<<gg, kSpThreads, 0, st>>>(P, O, X, B, part, L.gather_parts);
         if (L.ev_part) cudaEventRecord(L.ev_part[part], st);
     }
     if (ev) cudaEventRecord(ev[6], st);
