@@ -330,6 +330,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sparse-mode", type=int, default=1, help="debug: 0 block kernel only, 1 default")
     ap.add_argument("--as-rank", type=int, default=-1, help="debug: a single process doing the work of rank R of a --gpus N job")
+    ap.add_argument("--only", default="", help="debug: comma-separated mission indices of the config to run (others are skipped)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -369,6 +370,8 @@ def main():
     else:
         lo, hi = 0, size
         my_missions = [lay_rank]
+    if args.only:
+        my_missions = [i for i in my_missions if i in {int(x) for x in args.only.split(",")}]
     base = max(0, lo - HALO)  # stream offset of the first byte this rank holds
     blen = hi - base
     missions = [make_mission(sx, cfg["missions"][i][0], cfg["missions"][i][1], cfg["n"], i, counter_offset=base) for i in my_missions]

@@ -37,7 +37,7 @@ cudaError_t SX_CAT(launch_range_carry_, SX_INST)(const ScanParams& P, const Rang
     sx_range_carry_kernel<SX_DEC><<<A.nranges, 32, 0, st>>>(P, A);
     return cudaGetLastError();
 }
-bool SX_CAT(has_sparse_, SX_INST)() { return MaskFamily<SX_DEC>::kHas; }
+bool SX_CAT(has_sparse_, SX_INST)() { return true; }
 template <class Dec, bool kHas> struct SparseLauncher {
     static cudaError_t go(const ScanParams&, const ScanOut&, const ExactCfg&, const SparseBufs&, const SparseLaunchCfg&, cudaStream_t,
                           cudaEvent_t*, cudaStream_t, cudaEvent_t*) { return cudaErrorNotSupported; }
@@ -50,6 +50,6 @@ template <class Dec> struct SparseLauncher<Dec, true> {
 };
 cudaError_t SX_CAT(launch_sparse_, SX_INST)(const ScanParams& P, const ScanOut& O, const ExactCfg& X, const SparseBufs& B,
                                             const SparseLaunchCfg& L, cudaStream_t st, cudaEvent_t* ev, cudaStream_t side, cudaEvent_t* evs) {
-    return SparseLauncher<SX_DEC, MaskFamily<SX_DEC>::kHas>::go(P, O, X, B, L, st, ev, side, evs);
+    return SparseLauncher<SX_DEC, true>::go(P, O, X, B, L, st, ev, side, evs);
 }
 }  // namespace sx

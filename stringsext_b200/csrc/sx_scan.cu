@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1416,11 +1417,23 @@ static cudaError_t launch_sparse_enc(const ScanParams& P, const ScanOut& O, cons
     switch (P.enc) {
     case 0: return launch_sparse_0(P, O, X, B, L, st, ev, side, evs);
     case 1: return launch_sparse_1(P, O, X, B, L, st, ev, side, evs);
+    case 2: return launch_sparse_2(P, O, X, B, L, st, ev, side, evs);
+    case 3: return launch_sparse_3(P, O, X, B, L, st, ev, side, evs);
     case 4: return launch_sparse_4(P, O, X, B, L, st, ev, side, evs);
+    case 5: return launch_sparse_5(P, O, X, B, L, st, ev, side, evs);
+    case 6: return launch_sparse_6(P, O, X, B, L, st, ev, side, evs);
+    case 7: return launch_sparse_7(P, O, X, B, L, st, ev, side, evs);
+    case 8: return launch_sparse_8(P, O, X, B, L, st, ev, side, evs);
     }
     return cudaErrorNotSupported;
 }
-static bool has_sparse_enc(uint32_t enc) { return enc == ENC_XUD || enc == ENC_UTF8 || enc == ENC_SB; }
+// Every decoder can take the per-stage pipeline (those without a mask engine run the byte-wise engine in it);
+// SX_SPARSE_ALL=0 restricts it to the mask-engine families again (the others then take the block kernel).
+static bool has_sparse_enc(uint32_t enc) {
+    static int all = -1;
+    if (all < 0) { const char* ev = getenv("SX_SPARSE_ALL"); all = ev ? atoi(ev) : 1; }
+    return all || enc == ENC_XUD || enc == ENC_UTF8 || enc == ENC_SB;
+}
 
 static bool ensure_piece_events(sx_scanner_state* ss, size_t n) {
     while (ss->pev.size() < n) {
@@ -1456,7 +1469,19 @@ static int run_sparse(CallCtx& c) {
     // Measured on B200 (profiles/r02_pieces.txt): the exact stage of a piece is a chain of latency-bound kernels (~0.25 ms
     // whatever the piece size) and slows the prefilter down by 40 % while it runs beside it, so one piece -- prefilter,
     // then the exact stage on the whole machine, the download overlapped part by part with the gather -- is fastest.
-    if (K <= 0) K = 1;
+    // Output-heavy calls are different (koi8-r on random bytes: 115 M findings per 4 GiB, 3.2 GB over PCIe = 65 ms behind
+    // 83 ms of exact stage): there the download of piece k hides behind the exact stage of piece k + 1 (copy engine vs SMs).
+    int lanes = sx_scanner_state::kLanes;  // exact stages of that many pieces side by side
+    if (K <= 0) {
+        K = 1;
+        if (ss->have_history && ss->last_len) {
+            const double scale = (double)(nwin * P.W) / (double)ss->last_len;
+            const double pcie_ms = ((double)ss->last_nrec * sizeof(WireFinding) + (double)ss->last_ntext) * scale / 50e6;  // ~50 GB/s
+            // one lane: the pieces' exact stages run one after the other, so piece k is on its way to the host while
+            // piece k + 1 resolves (side by side they would all finish -- and start downloading -- at the end)
+            if (pcie_ms > 8.0) { K = (int)std::min(8.0, std::ceil(pcie_ms / 8.0) + 1.0); lanes = 1; }
+        }
+    }
     if (K > kMaxPieces) K = kMaxPieces;
     if ((long long)K > ntiles) K = (int)std::max<long long>(1, ntiles);
     std::vector<long long> pt(K + 1);  // tile boundaries of the pieces
@@ -1556,6 +1581,7 @@ static int run_sparse(CallCtx& c) {
         CK(cudaStreamWaitEvent(ss->sB, ss->ev_in, 0));
         CK(cudaStreamWaitEvent(ss->sC, ss->ev_in, 0));
         CK(cudaMemsetAsync(ss->d_ctl, 0, sizeof(PieceCtl) * kMaxPieces, ss->sB));
+        CK(cudaMemsetAsync(ss->d_counters, 0, 8 * sizeof(unsigned long long), ss->sB));  // [7]: Big5 / EUC-JP walk bound flag
         memset(hc, 0, sizeof(HostCtl));
         {
             RangeCarryArgs ra;
@@ -1591,7 +1617,7 @@ static int run_sparse(CallCtx& c) {
         for (int k = 0; k < K; ++k) {
             const Piece& p = pcs[k];
             PieceCtl* const ctl = ss->d_ctl + k;
-            cudaStream_t sb = ss->sBk[k % sx_scanner_state::kLanes], sd = ss->sidek[k % sx_scanner_state::kLanes];
+            cudaStream_t sb = ss->sBk[k % lanes], sd = ss->sidek[k % lanes];
             CK(cudaStreamWaitEvent(sb, ss->pev[k].p1, 0));
             CK(cudaEventRecord(ss->pev[k].b0, sb));
             uint32_t* const clist = ss->d_clist + p.ebase;
@@ -1664,6 +1690,14 @@ static int run_sparse(CallCtx& c) {
         CK(cudaStreamSynchronize(ss->sC));
         CK(cudaStreamSynchronize(ss->sA));
         for (int i = 0; i < sx_scanner_state::kLanes; ++i) { CK(cudaStreamSynchronize(ss->sBk[i])); CK(cudaStreamSynchronize(ss->sidek[i])); }
+        if (P.mb_fail) {
+            unsigned long long flag = 0;
+            CK(cudaMemcpy(&flag, ss->d_counters + 7, sizeof flag, cudaMemcpyDeviceToHost));
+            if (flag) {
+                set_err(SX_ERR_UNSUPPORTED, "Big5 / EUC-JP: more than 256 KiB of lead / trail bytes without a byte that resynchronises the decoder");
+                return fail;
+            }
+        }
         if (!overflow) {
             c.nrec = (size_t)tot_rec; c.ntext = (size_t)tot_text; c.windows_listed = tot_listed;
             break;

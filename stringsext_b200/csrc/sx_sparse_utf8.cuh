@@ -135,6 +135,22 @@ sx_list_compact_kernel(const uint32_t* __restrict__ cta_count, uint32_t ncta, co
     for (uint32_t i = tid; i < n; i += 256) out[pre + i] = src[i];
 }
 
+// The bit-parallel engine where the decoder has one (UTF-8, single-byte family); every other decoder "declines", i.e. all
+// its windows take the byte-wise engine through the fallbacks every stage has anyway -- still one thread per entry and
+// no block barrier, which is what makes this pipeline faster than the block kernel on long lists.
+template <class Dec, class TileSrc>
+__device__ __forceinline__ bool sp_mask_window(const ScanParams& P, const TileSrc& ts, const WinGeom& geo, const Carry& kin, int mode,
+                                               Record* wr, uint64_t text_off, WinResult& res) {
+    if constexpr (MaskFamily<Dec>::kHas) return mask_window<MaskFamily<Dec>::kSByte>(P, ts, geo, kin, mode, wr, text_off, res);
+    else return false;
+}
+template <class Dec, class TileSrc>
+__device__ __forceinline__ bool sp_mask_head(const ScanParams& P, const TileSrc& ts, const WinGeom& geo, uint32_t pre_bytes, int mode,
+                                             Record* wr, uint64_t text_off, WinResult& res) {
+    if constexpr (MaskFamily<Dec>::kHas) return mask_head<MaskFamily<Dec>::kSByte>(P, ts, geo, pre_bytes, mode, wr, text_off, res);
+    else return false;
+}
+
 struct SpCtx {
     Geometry geo;
     GlobalSrc g;
@@ -147,7 +163,9 @@ __device__ __forceinline__ void sp_setup(const ScanParams& P, const ExactCfg& X,
     __syncthreads();
     c.geo.init(P);
     c.g = GlobalSrc{P.in, P.pend};
-    c.ts = GlobalTile{c.g, P.len, X.in_aligned16 != 0, &S, (uint32_t)__cvta_generic_to_shared(&S.tt[0])};
+    // decoders without tables (UTF-16 / UTF-32 / Big5 / EUC-JP) get none: WindowEngine<Dec> then takes the generic automaton
+    c.ts = GlobalTile{c.g, P.len, X.in_aligned16 != 0, (P.enc == ENC_UTF8 || P.enc == ENC_XUD || P.enc == ENC_SB) ? &S : nullptr,
+                      (uint32_t)__cvta_generic_to_shared(&S.tt[0])};
 }
 __device__ __forceinline__ Record* sp_staged(const SparseBufs& B, long long e) { return B.staged + (size_t)e * kBufRecs; }
 __device__ __forceinline__ Record* sp_xstaged(const SparseBufs& B, long long e) { return B.xstaged + (size_t)e * kBufRecs; }
@@ -201,7 +219,7 @@ __device__ __forceinline__ bool sp_head_mask(const ScanParams& P, const ExactCfg
     WinResult r;
     EntryHot* const es = &B.H[e];
     // one pass: the pre-roll region is the 32 bytes in front of the window (same class planes, same decoder algebra)
-    if (w != X.w_first && mask_head<MaskFamily<Dec>::kSByte>(P, c.ts, wg, X.pre_bytes, MODE_BUFFER, sp_staged(B, e), 0, r)) {
+    if (w != X.w_first && sp_mask_head<Dec>(P, c.ts, wg, X.pre_bytes, MODE_BUFFER, sp_staged(B, e), 0, r)) {
         sp_store(es, r.in, r);
         return true;
     }
@@ -209,10 +227,10 @@ __device__ __forceinline__ bool sp_head_mask(const ScanParams& P, const ExactCfg
     if (w != X.w_first) {
         const WinGeom rg = preroll_geom(c.geo, w, X.pre_bytes);
         WinResult rr;
-        if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr)) return false;
+        if (!sp_mask_window<Dec>(P, c.ts, rg, carry_none(), MODE_STATE, nullptr, 0, rr)) return false;
         kin0 = rr.out;
     }
-    if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin0, MODE_BUFFER, sp_staged(B, e), 0, r)) return false;
+    if (!sp_mask_window<Dec>(P, c.ts, wg, kin0, MODE_BUFFER, sp_staged(B, e), 0, r)) return false;
     sp_store(es, kin0, r);
     return true;
 }
@@ -223,7 +241,7 @@ __device__ __forceinline__ Carry sp_member(const ScanParams& P, const SparseBufs
     WinGeom wg;
     c.geo.window(w, wg);
     WinResult r;
-    if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin, MODE_BUFFER, sp_staged(B, e), 0, r))
+    if (!sp_mask_window<Dec>(P, c.ts, wg, kin, MODE_BUFFER, sp_staged(B, e), 0, r))
         WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin, MODE_BUFFER, sp_staged(B, e), 0, r, nullptr);
     sp_store(&B.H[e], kin, r);
     return r.out;
@@ -293,7 +311,7 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
                 WinGeom pg;
                 c.geo.window(w - 1, pg);
                 WinResult rr;
-                if (mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr)) {
+                if (sp_mask_window<Dec>(P, c.ts, pg, carry_none(), MODE_STATE, nullptr, 0, rr)) {
                     known = rr.cut1 == 0;
                     kin = rr.out;
                     if (rr.caseb) {  // the walk of sx_sp_fix_kernel gets through that window without a pass
@@ -449,7 +467,7 @@ sx_sp_ext_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const S
             if (need_x) {
                 const WinGeom xg = ext_geom(c.geo, w + 1, X.pre_bytes);
                 WinResult r;
-                if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, xg, kout, MODE_BUFFER, sp_xstaged(B, e), 0, r))
+                if (!sp_mask_window<Dec>(P, c.ts, xg, kout, MODE_BUFFER, sp_xstaged(B, e), 0, r))
                     WindowEngine<Dec>::run(P, c.ts, c.g, xg, kout, MODE_BUFFER, sp_xstaged(B, e), 0, r, nullptr);
                 xr = r.nrec; xt = r.ntext;
                 es->xcnt_r = xr;
@@ -592,7 +610,7 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
             O.recs[idx] = r;
             if (staged_out) write_host_finding(P, &sbuf[idx - br], r);
             if (idx == 0) O.final_state->first_flags = r.flags;
-            if (text_staged) transcode_range(P, c.g, r.in_start, r.in_len, tbuf + (r.text_off - bt));
+            if (text_staged) transcode_record(P, c.g, r, tbuf + (r.text_off - bt));
         };
         if (cr) {
             if (cr <= kBufRecs) {
@@ -607,7 +625,7 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
                 WinGeom wg;
                 c.geo.window(list_window(X, X.cta_off, e), wg);
                 WinResult r;
-                if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r))
+                if (!sp_mask_window<Dec>(P, c.ts, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r))
                     WindowEngine<Dec>::run(P, c.ts, c.g, wg, kin, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
                 for (uint32_t k = 0; k < cr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
@@ -624,7 +642,7 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
             } else {
                 const WinGeom xg = ext_geom(c.geo, list_window(X, X.cta_off, e) + 1, X.pre_bytes);
                 WinResult r;
-                if (!mask_window<MaskFamily<Dec>::kSByte>(P, c.ts, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r))
+                if (!sp_mask_window<Dec>(P, c.ts, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r))
                     WindowEngine<Dec>::run(P, c.ts, c.g, xg, kout, MODE_WRITE, O.recs + br + ro, bt + to, r, nullptr);
                 for (uint32_t k = 0; k < xr; ++k) put(br + ro + k, O.recs[br + ro + k]);
             }
@@ -637,7 +655,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
             r.in_len = kout.in_bytes - (uint32_t)es->npend;
             r.text_len = kout.out_bytes;
             r.text_off = bt + to;
-            r.flags = RF_LEFTOVER | ((kout.flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u);
+            r.flags = RF_LEFTOVER | ((kout.flags & CF_HOSTCARRY) ? (uint32_t)RF_HOSTCARRY : 0u) |
+                      ((kout.flags & CF_HALF) ? (uint32_t)RF_HALFSTART : 0u);
             r.precision = 0;
             put(br + ro, r);
             O.final_state->last_flags = r.flags;
@@ -723,7 +742,7 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
     sx_sp_snapshot_kernel<<<1, 1, 0, st>>>(B.ctl);
     cudaEventRecord(evs[0], st);
     cudaStreamWaitEvent(side, evs[0], 0);
-    sx_sp_declined_kernel<Dec><<<std::min<unsigned>(L.grid_queue, 148u), kSpThreads, 0, side>>>(P, X, B);
+    sx_sp_declined_kernel<Dec><<<L.grid_queue, kSpThreads, 0, side>>>(P, X, B);
     cudaEventRecord(evs[1], side);
     sx_sp_members_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
     if (ev) cudaEventRecord(ev[3], st);
