@@ -1624,7 +1624,13 @@ static int run_sparse(CallCtx& c) {
             sx_list_compact_kernel<<<p.pgrid, 256, 0, sb>>>(ss->d_ccount + (size_t)k * kMaxPrefCtas, (uint32_t)p.pgrid, ss->d_list, p.t0, p.tpc,
                                                                clist, ctl, p.cap);
             CK(cudaGetLastError());
-            ScanOut O{ss->d_recs, ss->rec_cap, text_cap, ss->d_blocks, ss->d_counters, &hc->fin, ss->use_direct ? reinterpret_cast<uint4*>(ss->d_findings) : nullptr,
+            // Where the gather writes: one piece (little output) -> straight into the collection's pinned, device-mapped set
+            // (posted PCIe writes, staged in shared memory so they leave as large transactions: nothing is left to download
+            // when the kernel ends); several pieces (output-heavy) -> device staging, moved by the copy engine while the next
+            // piece resolves.
+            const bool zero_copy = ss->use_direct && K == 1 && !getenv("SX_NO_ZERO_COPY");
+            ScanOut O{ss->d_recs, ss->rec_cap, text_cap, ss->d_blocks, ss->d_counters, &hc->fin,
+                      !ss->use_direct ? nullptr : zero_copy ? reinterpret_cast<uint4*>(fc->set.f) : reinterpret_cast<uint4*>(ss->d_findings),
                       out_cap, nullptr, c.input_file_id, ss->m.mission_id};
             ExactCfg X;
             X.list = clist; X.ne_ptr = &ctl->ne; X.ne_static = 0; X.total_windows = c.total_windows;
@@ -1635,7 +1641,8 @@ static int run_sparse(CallCtx& c) {
             B.btot = reinterpret_cast<ulonglong2*>(ss->d_btot) + p.cbase;
             B.tables = reinterpret_cast<Utf8Tables*>(ss->d_tables);
             B.queue = ss->d_queue + 2 * p.ebase + 64 * (size_t)k; B.queue2 = B.queue + p.cap + 32;
-            B.ctl = ctl; B.prev = k ? ctl - 1 : nullptr; B.summary = &hc->piece[k]; B.text_out = ss->d_text;
+            B.ctl = ctl; B.prev = k ? ctl - 1 : nullptr; B.summary = &hc->piece[k];
+            B.text_out = zero_copy ? fc->set.t : ss->d_text;
             SparseLaunchCfg L;
             // one chunk per CTA (CTAs beyond the entry count, which only the device knows, leave at once): measured faster
             // than a persistent grid for these latency-bound kernels
@@ -1645,7 +1652,7 @@ static int run_sparse(CallCtx& c) {
             L.rec_cap = ss->rec_cap; L.text_cap = text_cap; L.out_cap = out_cap;
             L.ev_scan_prev = k ? ss->pev[k - 1].sc : nullptr; L.ev_scan_done = ss->pev[k].sc;
             // large pieces: the gather runs in parts, the download of a part beside the gathering of the next
-            L.gather_parts = p.cap >= (64u << 10) ? 2u : 1u;  // measured: 2 parts 1.43 ms, 4 parts 1.44, 1 part 1.47 per 4 GiB
+            L.gather_parts = (p.cap >= (64u << 10) && !zero_copy) ? 2u : 1u;  // staging: 2 parts 1.43 ms, 4 parts 1.44, 1 part 1.47 per 4 GiB
             if (const char* evp = getenv("SX_GATHER_PARTS")) L.gather_parts = (uint32_t)std::min(kGatherParts, std::max(1, atoi(evp)));
             L.ev_part = ss->pev[k].gp;
             gparts[k] = L.gather_parts;
@@ -1672,15 +1679,18 @@ static int run_sparse(CallCtx& c) {
                 CK(cudaEventSynchronize(ss->pev[k].gp[part]));
                 const unsigned long long r1 = part + 1 == gparts[k] ? s.rec_base + s.nrec : s.part_rec_end[part];
                 const unsigned long long t1 = part + 1 == gparts[k] ? s.text_base + s.ntext : s.part_text_end[part];
-                if (hc->piece[k].text_fallback && r1 > r0) {
+                const bool zc = ss->use_direct && K == 1 && !getenv("SX_NO_ZERO_COPY");
+                const bool fb = hc->piece[k].text_fallback != 0;
+                if (fb && r1 > r0) {
                     const int mgrid = (int)std::min<size_t>((size_t)(r1 - r0 + 255) / 256, (size_t)ss->num_sms * 8);
                     sx_materialize_kernel<<<mgrid, 256, 0, ss->sC>>>(P, ss->d_recs + r0, r1 - r0, ss->d_text, ss->text_cap);
                     CK(cudaGetLastError());
                     ss->stats.kernel_launches++;
                 }
                 if (ss->use_direct) {
-                    if (r1 > r0) CK(cudaMemcpyAsync(fc->set.f + r0, ss->d_findings + r0, (size_t)(r1 - r0) * sizeof(WireFinding), cudaMemcpyDeviceToHost, ss->sC));
-                    if (t1 > t0) CK(cudaMemcpyAsync(fc->set.t + t0, ss->d_text + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ss->sC));
+                    if (!zc && r1 > r0) CK(cudaMemcpyAsync(fc->set.f + r0, ss->d_findings + r0, (size_t)(r1 - r0) * sizeof(WireFinding), cudaMemcpyDeviceToHost, ss->sC));
+                    // zero copy: the text is already there, unless some chunk left it to the materialize kernel
+                    if ((!zc || fb) && t1 > t0) CK(cudaMemcpyAsync(fc->set.t + t0, ss->d_text + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ss->sC));
                     ss->stats.d2h_bytes += (r1 - r0) * sizeof(WireFinding) + (t1 - t0);
                 }
                 r0 = r1; t0 = t1;
