@@ -645,7 +645,7 @@ sx_range_carry_kernel(const __grid_constant__ ScanParams P, const __grid_constan
     const size_t out_stride = A.out_stride;
     __shared__ Utf8Tables T;
     constexpr bool kMask = MaskFamily<Dec>::kHas;
-    if (kMask)
+    if (kMask && blockIdx.x < A.nranges && A.w_first[blockIdx.x] > 0)  // a range at the stream start just takes P.k0
         for (uint32_t k = threadIdx.x; k < 2048; k += 32) mask_tables_fill(P, T, k);
     __syncthreads();
     if (threadIdx.x != 0 || blockIdx.x >= nranges) return;
