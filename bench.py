@@ -50,7 +50,7 @@ CONFIGS = {
     1: dict(name="-e utf-8 -n 10 over 4 GiB random buffer, 1xB200", size=4 << 30, n=10, seed=2,
             missions=[("utf-8", None)]),
     2: dict(name="-e utf-16le -e utf-16be -n 10 -u African over 4 GiB, 2xB200 (one encoding per GPU)", size=4 << 30,
-            n=10, seed=3, missions=[("utf-16le", "African"), ("utf-16be", "African")]),
+            n=10, seed=3, missions=[("utf-16le", "African"), ("utf-16be", "African")], balanced=True),
     4: dict(name="-e utf-8 -e utf-16le -e utf-16be -e big5 -n 8 over 16 GiB, 4xB200", size=16 << 30, n=8, seed=4,
             missions=[("utf-8", None), ("utf-16le", None), ("utf-16be", None), ("big5", None)]),
     8: dict(name="8 encodings (ascii, utf-8, utf-16le, utf-16be, utf-32le, utf-32be, euc-jp, koi8-r) -n 6 over 32 GiB, 8xB200",
@@ -319,7 +319,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--shard", default="range", choices=["range", "mission"])
+    ap.add_argument("--shard", default="auto", choices=["auto", "range", "mission"],
+                    help="auto: by range, except for a config whose missions cost the same (configs[2]: utf-16le / utf-16be), where one "
+                         "encoding per GPU avoids paying the exact stage's fixed latency twice per GPU")
     ap.add_argument("--config", type=int, default=0, help="BASELINE config to run (1, 2, 4, 8) instead of the one --gpus names; "
                                                           "e.g. --config 1 --gpus 8 = one mission range-sharded over 8 GPUs")
     ap.add_argument("--size-mib", type=int, default=0, help="override the stream size (debug only; invalidates the number)")
@@ -360,19 +362,20 @@ def main():
 
     # ---- this rank's part of the job -------------------------------------------------------------------
     shard = args.shard if lay_world > 1 else "range"
+    if shard == "auto":
+        shard = "mission" if (cfg.get("balanced") and lay_world == n_miss) else "range"
     if shard == "mission" and lay_world != n_miss:
         shard = "range"
     if shard == "range":
-        per = -(-size // lay_world)
-        per = -(-per // SLICE) * SLICE
-        lo, hi = min(size, lay_rank * per), min(size, (lay_rank + 1) * per)
+        from stringsext_b200.multi import range_plan
+
+        base, lo, hi = range_plan(size, lay_world, SLICE, HALO)[lay_rank]  # base: stream offset of the first byte this rank holds
         my_missions = list(range(n_miss))
     else:
-        lo, hi = 0, size
+        base, lo, hi = 0, 0, size
         my_missions = [lay_rank]
     if args.only:
         my_missions = [i for i in my_missions if i in {int(x) for x in args.only.split(",")}]
-    base = max(0, lo - HALO)  # stream offset of the first byte this rank holds
     blen = hi - base
     missions = [make_mission(sx, cfg["missions"][i][0], cfg["missions"][i][1], cfg["n"], i, counter_offset=base) for i in my_missions]
     labels = [cfg["missions"][i][0] for i in my_missions]

@@ -1,4 +1,4 @@
-"""One mission per GPU, one process per GPU.
+"""Sharding a scan job over several GPUs, one process per GPU: by mission or by stream range.
 
 The reference runs one scanner thread per `--encoding` mission and merges the per-slice results in a
 separate thread (/root/reference/src/main.rs:97-167).  Missions are independent, so here rank r of a
@@ -8,7 +8,7 @@ the order of `impl PartialOrd for Finding` (finding.rs:92-109).
 """
 from __future__ import annotations
 
-from typing import Callable, List, Sequence
+from typing import Callable, List, Sequence, Tuple
 
 from .mission import Mission
 
@@ -40,3 +40,37 @@ def scan_sharded(missions: Sequence[Mission], data, scan_fn: Callable[[Mission, 
     if rank != 0:
         return None
     return merge_findings([lst for per_rank in gathered for lst in per_rank])
+
+
+# ---- range sharding (SURVEY.md 8(e)(2)) ----------------------------------------------------------------------------
+# A mission's stream is cut at slice boundaries; rank r holds bytes [base_r, hi_r) = its range plus a halo in front and
+# scans [lo_r, hi_r) with `sx_scan_range(..., SX_RANGE_PREFIX_UNKNOWN)`: the carry into the range is derived on the
+# device inside the halo.  No data flows between ranks; the per-range collections concatenate in rank order.
+def range_plan(size: int, world_size: int, slice_len: int = 4096, halo: int = 1 << 20) -> List[Tuple[int, int, int]]:
+    """[(base, lo, hi)] per rank: slice-aligned ranges [lo, hi) covering [0, size), base = start of the halo in front."""
+    per = -(-size // world_size)
+    per = -(-per // slice_len) * slice_len
+    out = []
+    for r in range(world_size):
+        lo, hi = min(size, r * per), min(size, (r + 1) * per)
+        out.append((max(0, lo - (halo // slice_len) * slice_len), lo, hi))
+    return out
+
+
+def scan_range_sharded(missions: Sequence[Mission], size: int, scan_fn: Callable[[Mission, int, int, int], List[tuple]], dist=None,
+                       slice_len: int = 4096, halo: int = 1 << 20):
+    """Every rank runs `scan_fn(mission, base, lo, hi)` -- the findings emitted for stream bytes [lo, hi), scanned from a
+    buffer that starts at `base` -- for EVERY mission over its own range; rank 0 concatenates each mission's lists in
+    rank order (they are position-monotone and disjoint) and merges the missions.  Returns the merged list on rank 0."""
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    base, lo, hi = range_plan(size, world, slice_len, halo)[rank]
+    mine = [scan_fn(m, base, lo, hi) if hi > lo else [] for m in missions]
+    if dist is None or world == 1:
+        return merge_findings(mine)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    if rank != 0:
+        return None
+    per_mission = [[f for per_rank in gathered for f in per_rank[i]] for i in range(len(missions))]
+    return merge_findings(per_mission)
