@@ -34,10 +34,14 @@ struct ScanOut {
     // (block path); the host expands them to sx_finding on demand, page by page (sx_fc_get / sx_fc_data)
     uint4* host_findings;          // nullptr: off (records are downloaded and converted on the host)
     unsigned long long host_cap;
-    const uint8_t* host_text;      // unused by the kernels (kept so that both paths share the struct)
+    // per-stage pipeline: 8-byte wire records (Wire8, written through `host_findings` as unsigned long long) whose text
+    // offsets are implicit -- the text arena is gap free in record order -- except for one explicit offset per page of
+    // kWirePage records, written here
+    unsigned long long* page_base;
     int32_t file_id;
     uint32_t mission_id;
 };
+constexpr uint32_t kWirePage = 4096;
 
 // One finding on the wire (finding.rs:51-74 minus what the host knows: mission, file, text base address):
 //   x, y: position relative to the call's first byte (40 bits) | text length (22 bits) << 40 | precision (2 bits) << 62
@@ -50,6 +54,17 @@ __host__ __device__ __forceinline__ WireFinding wire_pack(unsigned long long pos
     w.a = (pos_rel & 0xFFFFFFFFFFull) | ((unsigned long long)(text_len & 0x3FFFFFu) << 40) | ((unsigned long long)(precision & 3u) << 62);
     w.b = (text_off & 0xFFFFFFFFFFull) | ((unsigned long long)(completes ? 1u : 0u) << 40);
     return w;
+}
+// The per-stage pipeline's wire record, 8 bytes: position relative to the call's first byte (40 bits) | text length
+// (21 bits) << 40 | precision (2 bits) << 61 | completes-previous flag << 63.  The text of record i starts where the text
+// of record i - 1 ends; page_base[i / kWirePage] holds the offset of every kWirePage-th record.
+__host__ __device__ __forceinline__ unsigned long long wire8_pack(unsigned long long pos_rel, uint32_t text_len, uint32_t precision,
+                                                                  bool completes) {
+    return (pos_rel & 0xFFFFFFFFFFull) | ((unsigned long long)(text_len & 0x1FFFFFu) << 40) | ((unsigned long long)(precision & 3u) << 61) |
+           ((unsigned long long)(completes ? 1u : 0u) << 63);
+}
+__device__ __forceinline__ unsigned long long wire8_of(const ScanParams& P, const Record& r) {
+    return wire8_pack(r.position - P.base_consumed, r.text_len, r.precision, (r.flags & RF_COMPLETES) != 0);
 }
 __device__ __forceinline__ void write_host_finding(const ScanParams& P, uint4* dst, const Record& r) {
     const WireFinding w = wire_pack(r.position - P.base_consumed, r.text_len, r.precision, r.text_off, (r.flags & RF_COMPLETES) != 0);

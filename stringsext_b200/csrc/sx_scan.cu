@@ -49,6 +49,7 @@ struct PrefOut {
     long long tile0, tile_end;  // tiles of this launch: one piece of the call's window range
     long long w_first;          // first window of the piece: always listed (its carry-in is given, sx_range_carry_kernel)
     long long w_lo, w_hi;       // the call's window range: windows of the boundary tiles outside it are not this call's
+    uint32_t piece_ctas;        // > 0: every piece_ctas-th CTA starts a piece of the exact stage; its first window is listed too
 };
 
 struct PrefK {
@@ -272,6 +273,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
     const long long t_begin = O.tile0 + (long long)blockIdx.x * O.tiles_per_cta;
     const long long t_end = (t_begin + O.tiles_per_cta) < O.tile_end ? (t_begin + O.tiles_per_cta) : O.tile_end;
     uint32_t* const my_list = O.list + (size_t)t_begin * kPrefTileWin;
+    const bool piece_start = O.piece_ctas != 0 && (blockIdx.x % O.piece_ctas) == 0;
     uint32_t kept = 0;  // windows this CTA has listed so far (uniform across the block)
     const int64_t full_rows_bytes = (P.len >> 7) << 7;  // the tensor map covers whole 128-byte rows only
 
@@ -425,7 +427,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             const bool crossing = (r[1] & cross_bits) != 0;
             const bool inwin = ((r[1] & ~cross_bits) | r[2] | r[3] | r[4]) != 0;
             if (valid) {
-                const bool forced = (w == O.w_first) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
+                const bool forced = (w == O.w_first) || (piece_start && w == t_begin * (long long)kPrefTileWin) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
                 sure = forced || crossing;
                 if (!sure && inwin) { if (do_refine) cand = true; else sure = true; }
             }
@@ -560,7 +562,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         __syncthreads();
         // sure: listed whatever the refinement says; cand: listed only if a long run holds enough chars
         if (valid) {
-            const bool forced = (w == O.w_first) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
+            const bool forced = (w == O.w_first) || (piece_start && w == t_begin * (long long)kPrefTileWin) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
             if (forced) sure = true;
             else if (tid == 0) sure = lead >= 1 || C.kill_trail != 0;
             else {
@@ -858,7 +860,8 @@ struct sx_scanner_state {
     uint8_t* d_tables = nullptr; size_t tables_cap = 0;
     uint32_t* d_queue = nullptr; size_t queue_cap = 0;
     uint32_t* d_clist = nullptr; size_t clist_cap = 0;
-    WireFinding* d_findings = nullptr; size_t findings_cap = 0;
+    unsigned long long* d_findings = nullptr; size_t findings_cap = 0;  // staging: 8-byte wire records
+    unsigned long long* d_pagebase = nullptr; size_t pagebase_cap = 0;
     PieceCtl* d_ctl = nullptr;
     HostCtl* h_ctl = nullptr;
     unsigned long long* d_bpos = nullptr; size_t bpos_cap = 0;  // block path, direct output: stream-order position of every block
@@ -917,9 +920,13 @@ struct RawVec {
 // text is downloaded to.  A collection built that way owns its set; sets are recycled through a small pool because
 // pinning memory costs far more than a scan.
 struct PinnedSet {
-    WireFinding* f = nullptr; size_t fcap = 0;  // findings as they come off the wire (16 bytes each)
-    uint8_t* t = nullptr; size_t tcap = 0;      // text bytes
+    uint8_t* f = nullptr; size_t fcap = 0;  // findings as they come off the wire: fcap BYTES (8-byte records + page bases of the
+                                            // per-stage pipeline, 16-byte records of the block path)
+    uint8_t* t = nullptr; size_t tcap = 0;  // text bytes
 };
+// 8-byte records + one text offset per page of kWirePage records
+static size_t wire8_bytes(size_t cap) { return cap * 8 + (cap / kWirePage + 2) * 8; }
+static size_t wire8_cap(size_t bytes) { return bytes < 64 ? 0 : (size_t)((double)(bytes - 32) * kWirePage / (8.0 * (kWirePage + 1))); }
 static std::mutex g_pool_mu;
 static std::vector<PinnedSet> g_pool;
 static void pinned_free(PinnedSet& s) {
@@ -927,7 +934,7 @@ static void pinned_free(PinnedSet& s) {
     if (s.t) cudaFreeHost(s.t);
     s = PinnedSet();
 }
-static size_t pinned_bytes(const PinnedSet& s) { return s.fcap * sizeof(WireFinding) + s.tcap; }
+static size_t pinned_bytes(const PinnedSet& s) { return s.fcap + s.tcap; }
 // Pool policy: pinning memory costs far more than a scan (seconds per GB), so released sets are kept for reuse -- up
 // to kPoolTotal bytes per process (SX_PINNED_POOL_MIB overrides; page-locked memory is not swappable).  A process
 // typically runs several missions side by side, each returning a collection per call, so several large sets are live
@@ -948,16 +955,16 @@ static bool pinned_acquire(size_t fcap, size_t tcap, PinnedSet* out) {
         for (size_t i = 0; i < g_pool.size(); ++i)
             if (g_pool[i].fcap >= fcap && g_pool[i].tcap >= tcap && (best < 0 || pinned_bytes(g_pool[i]) < pinned_bytes(g_pool[best]))) best = (int)i;
         // a pooled set several times larger than needed stays for the caller that needs it
-        if (best >= 0 && pinned_bytes(g_pool[best]) <= 4 * (fcap * sizeof(WireFinding) + tcap) + (64ull << 20)) {
+        if (best >= 0 && pinned_bytes(g_pool[best]) <= 4 * (fcap + tcap) + (64ull << 20)) {
             *out = g_pool[best];
             g_pool.erase(g_pool.begin() + best);
             return true;
         }
     }
     PinnedSet s;
-    s.fcap = fcap + fcap / 16 + 1024;
+    s.fcap = fcap + fcap / 16 + 16384;
     s.tcap = tcap + tcap / 16 + 65536;
-    if (cudaHostAlloc((void**)&s.f, s.fcap * sizeof(WireFinding), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc((void**)&s.f, s.fcap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void**)&s.t, s.tcap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         pinned_free(s);
@@ -967,9 +974,9 @@ static bool pinned_acquire(size_t fcap, size_t tcap, PinnedSet* out) {
             for (auto& q : g_pool) pinned_free(q);
             g_pool.clear();
         }
-        s.fcap = fcap + 1024;
+        s.fcap = fcap + 16384;
         s.tcap = tcap + 65536;
-        if (cudaHostAlloc((void**)&s.f, s.fcap * sizeof(WireFinding), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
+        if (cudaHostAlloc((void**)&s.f, s.fcap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess ||
             cudaHostAlloc((void**)&s.t, s.tcap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
             cudaGetLastError();
             pinned_free(s);
@@ -1024,11 +1031,12 @@ static bool mb_tables_for(int device, MbDeviceTables* out) {
 // records + text in a pinned set, expanded to sx_finding on demand in pages of kPage findings (a consumer that walks a
 // 100-million-finding collection pays for what it touches, the scan does not pay for any of it).
 struct sx_finding_collection {
-    static constexpr size_t kPage = 4096;
+    static constexpr size_t kPage = kWirePage;  // expansion granularity = the wire format's page
     RawVec<sx_finding> v;
     RawVec<uint8_t> text;
     PinnedSet set;  // direct output: wire records and the finding text live here
-    bool wire = false;
+    int wire = 0;                 // 0: expanded (v), 8: per-stage pipeline's records + page bases, 16: block path's records
+    size_t wcap = 0;              // wire == 8: record capacity of the set (the page bases follow the records)
     size_t n = 0;                 // findings
     uint64_t base = 0;            // stream position of the call's first byte (wire positions are relative to it)
     int16_t file_id = -1;
@@ -1040,21 +1048,51 @@ struct sx_finding_collection {
     uint64_t first_byte_position = 0;
     int str_buf_overflow = 0;
     ~sx_finding_collection() { pinned_release(set); }
-    void expand(size_t i0, size_t i1) {
+    const unsigned long long* page_bases() const { return reinterpret_cast<const unsigned long long*>(set.f + wcap * 8); }
+    // text of wire record i (without a host-carried prefix)
+    void wire_text(size_t i, const uint8_t** p, size_t* len) const {
+        if (wire == 16) {
+            const WireFinding* w = reinterpret_cast<const WireFinding*>(set.f);
+            *p = set.t + (w[i].b & 0xFFFFFFFFFFull);
+            *len = (size_t)((w[i].a >> 40) & 0x3FFFFFu);
+            return;
+        }
+        const unsigned long long* w = reinterpret_cast<const unsigned long long*>(set.f);
+        unsigned long long off = page_bases()[i / kWirePage];
+        for (size_t j = (i / kWirePage) * kWirePage; j < i; ++j) off += (w[j] >> 40) & 0x1FFFFFu;
+        *p = set.t + off;
+        *len = (size_t)((w[i] >> 40) & 0x1FFFFFu);
+    }
+    void expand(size_t i0, size_t i1) {  // [i0, i1) lies inside one page
         sx_finding* const out = v.data();
-        const WireFinding* const w = set.f;
-        for (size_t i = i0; i < i1; ++i) {
-            sx_finding f;
-            f.position = base + (w[i].a & 0xFFFFFFFFFFull);
-            f.precision = (uint8_t)(w[i].a >> 62);
-            f.completes_previous = (uint8_t)((w[i].b >> 40) & 1u);
-            f.input_file_id = file_id;
-            f.mission_id = mission_id;
-            f.s = set.t + (w[i].b & 0xFFFFFFFFFFull);
-            f.s_len = (uint32_t)((w[i].a >> 40) & 0x3FFFFFu);
-            f.in_start = 0;
-            f.in_len = 0;
-            out[i] = f;
+        sx_finding f;
+        f.input_file_id = file_id;
+        f.mission_id = mission_id;
+        f.in_start = 0;
+        f.in_len = 0;
+        if (wire == 16) {
+            const WireFinding* const w = reinterpret_cast<const WireFinding*>(set.f);
+            for (size_t i = i0; i < i1; ++i) {
+                f.position = base + (w[i].a & 0xFFFFFFFFFFull);
+                f.precision = (uint8_t)(w[i].a >> 62);
+                f.completes_previous = (uint8_t)((w[i].b >> 40) & 1u);
+                f.s = set.t + (w[i].b & 0xFFFFFFFFFFull);
+                f.s_len = (uint32_t)((w[i].a >> 40) & 0x3FFFFFu);
+                out[i] = f;
+            }
+        } else {
+            const unsigned long long* const w = reinterpret_cast<const unsigned long long*>(set.f);
+            unsigned long long off = i0 < i1 ? page_bases()[i0 / kWirePage] : 0ull;
+            for (size_t i = i0; i < i1; ++i) {
+                const unsigned long long a = w[i];
+                f.position = base + (a & 0xFFFFFFFFFFull);
+                f.precision = (uint8_t)((a >> 61) & 3u);
+                f.completes_previous = (uint8_t)(a >> 63);
+                f.s_len = (uint32_t)((a >> 40) & 0x1FFFFFu);
+                f.s = set.t + off;
+                off += f.s_len;
+                out[i] = f;
+            }
         }
         if (have_first && i0 == 0 && i1 > 0) { out[0].s = text.data(); out[0].s_len = (uint32_t)(text.size() - 1); }
     }
@@ -1165,7 +1203,7 @@ void sx_scanner_state_free(sx_scanner_state* ss) {
     cudaFree(ss->d_in); cudaFree(ss->d_recs); cudaFree(ss->d_text); cudaFree(ss->d_blocks); cudaFree(ss->d_ccount); cudaFree(ss->d_coff); cudaFree(ss->d_list);
     cudaFree(ss->d_counters); cudaFree(ss->d_final); cudaFree(ss->d_ctl);
     cudaFree(ss->d_entries); cudaFree(ss->d_btot); cudaFree(ss->d_tables); cudaFree(ss->d_queue); cudaFree(ss->d_bpos);
-    cudaFree(ss->d_clist); cudaFree(ss->d_findings);
+    cudaFree(ss->d_clist); cudaFree(ss->d_findings); cudaFree(ss->d_pagebase);
     cudaFreeHost(ss->h_recs); cudaFreeHost(ss->h_text); cudaFreeHost(ss->h_blocks); cudaFreeHost(ss->h_ctl);
     for (auto e : ss->ev) if (e) cudaEventDestroy(e);
     if (ss->ev_in) cudaEventDestroy(ss->ev_in);
@@ -1376,6 +1414,7 @@ struct CallCtx {
     unsigned long long windows_listed = 0;
     FinalState fin;
     bool direct_out = false;   // findings and text are complete in fc->set
+    int wire = 0;              // ... as 8-byte (per-stage pipeline) or 16-byte (block path) wire records
     bool records_in_order = false;  // (legacy download) d_recs is in stream order: one descriptor
     uint8_t tail[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t tail_n = 0;
@@ -1464,44 +1503,40 @@ static int run_sparse(CallCtx& c) {
     const long long tile_lo = c.w_lo / kPrefTileWin, tile_hi = (c.w_hi + kPrefTileWin - 1) / kPrefTileWin;
     const long long ntiles = tile_hi - tile_lo;
     // ---- piece plan -------------------------------------------------------------------------------
+    // ONE prefilter launch streams the whole range (alone on the machine: anything that shares its SMs costs it 25-45 %,
+    // profiles/r02_pieces.txt); the exact stage is cut into K pieces = groups of consecutive prefilter CTAs, i.e. window
+    // ranges whose first window is force-listed and whose carry-in comes from sx_range_carry_kernel.  The pieces' exact
+    // stages run on `lanes` streams: the SM-bound heads of piece k + 1 beside the latency-bound members / walks of piece k
+    // and the PCIe-bound gather of piece k - 1.  Output-heavy calls (koi8-r on random bytes: 115 M findings per 4 GiB):
+    // more pieces on ONE lane, so that piece k travels to the host (copy engine) while piece k + 1 resolves.
     int K = ss->pieces;
     if (const char* ev = getenv("SX_PIECES")) K = atoi(ev);
-    // Measured on B200 (profiles/r02_pieces.txt): the exact stage of a piece is a chain of latency-bound kernels (~0.25 ms
-    // whatever the piece size) and slows the prefilter down by 40 % while it runs beside it, so one piece -- prefilter,
-    // then the exact stage on the whole machine, the download overlapped part by part with the gather -- is fastest.
-    // Output-heavy calls are different (koi8-r on random bytes: 115 M findings per 4 GiB, 3.2 GB over PCIe = 65 ms behind
-    // 83 ms of exact stage): there the download of piece k hides behind the exact stage of piece k + 1 (copy engine vs SMs).
-    int lanes = sx_scanner_state::kLanes;  // exact stages of that many pieces side by side
-    if (K <= 0) {
-        K = 1;
-        if (ss->have_history && ss->last_len) {
-            const double scale = (double)(nwin * P.W) / (double)ss->last_len;
-            const double pcie_ms = ((double)ss->last_nrec * sizeof(WireFinding) + (double)ss->last_ntext) * scale / 50e6;  // ~50 GB/s
-            // one lane: the pieces' exact stages run one after the other, so piece k is on its way to the host while
-            // piece k + 1 resolves (side by side they would all finish -- and start downloading -- at the end)
-            if (pcie_ms > 8.0) { K = (int)std::min(8.0, std::ceil(pcie_ms / 8.0) + 1.0); lanes = 1; }
-        }
+    int lanes = 2;
+    bool heavy = false;
+    if (ss->have_history && ss->last_len) {
+        const double scale = (double)(nwin * P.W) / (double)ss->last_len;
+        const double pcie_ms = ((double)ss->last_nrec * 8 + (double)ss->last_ntext) * scale / 50e6;  // ~50 GB/s
+        heavy = pcie_ms > 8.0;
+        if (heavy && K <= 0) K = (int)std::min(8.0, std::ceil(pcie_ms / 8.0) + 1.0);
     }
+    if (heavy) lanes = 1;
+    // Light output: ONE piece.  Measured (profiles/r02_pieces.txt): exact-stage pieces side by side on 2-4 lanes run in lockstep
+    // and share the SMs (K = 2: 1.32 ms, 4: 1.41, 8: 1.67 vs 1.29 for K = 1): the latency-bound stages of one piece slow down
+    // 3x beside the SM-bound heads of another, which eats what the overlap would give.
+    if (K <= 0) K = 1;
+    if (const char* ev = getenv("SX_LANES")) lanes = std::max(1, std::min((int)sx_scanner_state::kLanes, atoi(ev)));
     if (K > kMaxPieces) K = kMaxPieces;
+    int pgrid_max = ss->num_sms * 3;
+    if (const char* ev = getenv("SX_PREF_GRID")) { const int g = atoi(ev); if (g > 0) pgrid_max = g; }
+    pgrid_max = std::min(pgrid_max, kMaxPrefCtas);
     if ((long long)K > ntiles) K = (int)std::max<long long>(1, ntiles);
-    std::vector<long long> pt(K + 1);  // tile boundaries of the pieces
-    {
-        // equal pieces except the last two, which shrink (1/2, 1/4 of a regular piece): what cannot be overlapped with
-        // the next piece's prefilter is the exact stage and the download of the LAST piece
-        std::vector<double> wgt(K, 1.0);
-        if (K >= 4 && !getenv("SX_PIECES_EQUAL")) { wgt[K - 2] = 0.5; wgt[K - 1] = 0.25; }
-        double tot = 0;
-        for (double x : wgt) tot += x;
-        double acc = 0;
-        pt[0] = tile_lo;
-        for (int k = 0; k < K; ++k) {
-            acc += wgt[k];
-            pt[k + 1] = k + 1 == K ? tile_hi : tile_lo + (long long)((double)ntiles * acc / tot);
-        }
-        // every piece holds at least one tile (K <= ntiles)
-        for (int k = 1; k < K; ++k) pt[k] = std::max(pt[k], pt[k - 1] + 1);
-        for (int k = K - 1; k >= 1; --k) pt[k] = std::min(pt[k], pt[k + 1] - 1);
-    }
+    if (K > pgrid_max) K = pgrid_max;
+    // prefilter CTAs: cpp per piece, tpc tiles each
+    int cpp = std::max(1, pgrid_max / K);
+    if ((long long)cpp * K > ntiles) cpp = (int)std::max<long long>(1, ntiles / K);
+    const long long tpc = (ntiles + (long long)cpp * K - 1) / ((long long)cpp * K);
+    const int pgrid_all = (int)((ntiles + tpc - 1) / tpc);  // <= cpp * K
+    K = (pgrid_all + cpp - 1) / cpp;
     struct Piece { long long w0, w1, t0, t1; unsigned long long cap, ebase, cbase; int pgrid; long long tpc; };
     std::vector<Piece> pcs(K);
     std::vector<unsigned long long> want_cap(K, 0);  // after an overflow: the counted entries
@@ -1524,16 +1559,14 @@ static int run_sparse(CallCtx& c) {
     size_t need_text = (size_t)((double)(nwin * P.W) * ss->text_per_byte) + 65536;
     size_t need_recs_min = 0, need_text_min = 0;
     HostCtl* const hc = ss->h_ctl;
-    int pgrid_max = ss->num_sms * 3;
-    if (const char* ev = getenv("SX_PREF_GRID")) { const int g = atoi(ev); if (g > 0) pgrid_max = g; }
-    pgrid_max = std::min(pgrid_max, kMaxPrefCtas);
 
     for (int attempt = 0;; ++attempt) {
         // ---- capacities -----------------------------------------------------------------------------
         unsigned long long etot = 0, ctot = 0;
         for (int k = 0; k < K; ++k) {
             Piece& p = pcs[k];
-            p.t0 = pt[k]; p.t1 = pt[k + 1];
+            p.t0 = tile_lo + (long long)k * cpp * tpc;
+            p.t1 = std::min<long long>(tile_hi, p.t0 + (long long)cpp * tpc);
             p.w0 = std::max<long long>(c.w_lo, p.t0 * kPrefTileWin);
             p.w1 = std::min<long long>(c.w_hi, p.t1 * kPrefTileWin);
             const unsigned long long wins = (unsigned long long)(p.w1 - p.w0);
@@ -1543,10 +1576,8 @@ static int run_sparse(CallCtx& c) {
             p.cap = cap; p.ebase = etot; p.cbase = ctot;
             etot += cap;
             ctot += (cap + kSpThreads - 1) / kSpThreads + 1;
-            const long long nt = p.t1 - p.t0;
-            int g = (int)std::min<long long>(nt, pgrid_max);
-            p.tpc = (nt + g - 1) / g;
-            p.pgrid = (int)((nt + p.tpc - 1) / p.tpc);
+            p.tpc = tpc;
+            p.pgrid = std::min(cpp, pgrid_all - k * cpp);  // prefilter CTAs (list regions) of this piece
         }
         const size_t entry_bytes = sizeof(EntryHot) + sizeof(Carry) + 2 * kBufRecs * sizeof(Record);
         if (!grow(&ss->d_entries, &ss->entries_cap, (size_t)etot * entry_bytes + 256, etot * entry_bytes <= (24ull << 30))) return fail;
@@ -1567,12 +1598,16 @@ static int run_sparse(CallCtx& c) {
             const size_t guess_t = ss->have_history ? (size_t)(ss->last_ntext * scale) + ss->last_ntext / 16 + 65536 : ss->host_text_hint;
             const size_t want_f = std::min(need_recs, std::max(guess_f, need_recs_min));
             const size_t want_t = std::min(need_text, std::max(guess_t, need_text_min));
-            if (fc->set.fcap < want_f || fc->set.tcap < want_t) {
+            if (fc->set.fcap < wire8_bytes(want_f) || fc->set.tcap < want_t) {
                 pinned_release(fc->set);
-                if (!pinned_acquire(want_f, want_t, &fc->set)) { set_err(SX_ERR_CUDA, "cannot pin host memory for the findings"); return fail; }
+                if (!pinned_acquire(wire8_bytes(want_f), want_t, &fc->set)) { set_err(SX_ERR_CUDA, "cannot pin host memory for the findings"); return fail; }
             }
-            if (!grow(&ss->d_findings, &ss->findings_cap, fc->set.fcap)) return fail;
-            out_cap = fc->set.fcap;
+            out_cap = wire8_cap(fc->set.fcap);
+            fc->wcap = (size_t)out_cap;
+            if (heavy || getenv("SX_NO_ZERO_COPY")) {
+                if (!grow(&ss->d_findings, &ss->findings_cap, (size_t)out_cap)) return fail;
+                if (!grow(&ss->d_pagebase, &ss->pagebase_cap, (size_t)out_cap / kWirePage + 2)) return fail;
+            }
             text_cap = std::min<unsigned long long>(text_cap, fc->set.tcap);
         }
         // ---- enqueue --------------------------------------------------------------------------------
@@ -1603,14 +1638,14 @@ static int run_sparse(CallCtx& c) {
         memset(&tmap, 0, sizeof tmap);
         const uint32_t use_tma = (ss->use_tma && make_tensor_map(&tmap, c.d_in, c.len, kPrefTileWin * P.W)) ? 1u : 0u;
         ss->stats.tma_used = use_tma;
-        for (int k = 0; k < K; ++k) {
-            const Piece& p = pcs[k];
+        {
             PrefOut po;
-            po.list = ss->d_list; po.cta_count = ss->d_ccount + (size_t)k * kMaxPrefCtas; po.tiles_per_cta = p.tpc;
-            po.tile0 = p.t0; po.tile_end = p.t1; po.w_first = p.w0; po.w_lo = c.w_lo; po.w_hi = c.w_hi;
-            CK(cudaEventRecord(ss->pev[k].p0, ss->sA));
-            CK(launch_prefilter(P, c.pc, pk, po, c.total_windows, p.pgrid, ss->sA, tmap, use_tma));
-            CK(cudaEventRecord(ss->pev[k].p1, ss->sA));
+            po.list = ss->d_list; po.cta_count = ss->d_ccount; po.tiles_per_cta = tpc;
+            po.tile0 = tile_lo; po.tile_end = tile_hi; po.w_first = c.w_lo; po.w_lo = c.w_lo; po.w_hi = c.w_hi;
+            po.piece_ctas = K > 1 ? (uint32_t)cpp : 0u;
+            CK(cudaEventRecord(ss->pev[0].p0, ss->sA));
+            CK(launch_prefilter(P, c.pc, pk, po, c.total_windows, pgrid_all, ss->sA, tmap, use_tma));
+            CK(cudaEventRecord(ss->pev[0].p1, ss->sA));
             ss->stats.kernel_launches++;
         }
         const unsigned chunk_grid_max = (unsigned)ss->num_sms * 6u, queue_grid_max = (unsigned)ss->num_sms * 4u;
@@ -1618,20 +1653,22 @@ static int run_sparse(CallCtx& c) {
             const Piece& p = pcs[k];
             PieceCtl* const ctl = ss->d_ctl + k;
             cudaStream_t sb = ss->sBk[k % lanes], sd = ss->sidek[k % lanes];
-            CK(cudaStreamWaitEvent(sb, ss->pev[k].p1, 0));
+            CK(cudaStreamWaitEvent(sb, ss->pev[0].p1, 0));
             CK(cudaEventRecord(ss->pev[k].b0, sb));
             uint32_t* const clist = ss->d_clist + p.ebase;
-            sx_list_compact_kernel<<<p.pgrid, 256, 0, sb>>>(ss->d_ccount + (size_t)k * kMaxPrefCtas, (uint32_t)p.pgrid, ss->d_list, p.t0, p.tpc,
+            sx_list_compact_kernel<<<p.pgrid, 256, 0, sb>>>(ss->d_ccount + (size_t)k * cpp, (uint32_t)p.pgrid, ss->d_list, p.t0, p.tpc,
                                                                clist, ctl, p.cap);
             CK(cudaGetLastError());
             // Where the gather writes: one piece (little output) -> straight into the collection's pinned, device-mapped set
             // (posted PCIe writes, staged in shared memory so they leave as large transactions: nothing is left to download
             // when the kernel ends); several pieces (output-heavy) -> device staging, moved by the copy engine while the next
             // piece resolves.
-            const bool zero_copy = ss->use_direct && K == 1 && !getenv("SX_NO_ZERO_COPY");
+            const bool zero_copy = ss->use_direct && !heavy && !getenv("SX_NO_ZERO_COPY");
             ScanOut O{ss->d_recs, ss->rec_cap, text_cap, ss->d_blocks, ss->d_counters, &hc->fin,
                       !ss->use_direct ? nullptr : zero_copy ? reinterpret_cast<uint4*>(fc->set.f) : reinterpret_cast<uint4*>(ss->d_findings),
-                      out_cap, nullptr, c.input_file_id, ss->m.mission_id};
+                      out_cap,
+                      !ss->use_direct ? nullptr : zero_copy ? reinterpret_cast<unsigned long long*>(fc->set.f + fc->wcap * 8) : ss->d_pagebase,
+                      c.input_file_id, ss->m.mission_id};
             ExactCfg X;
             X.list = clist; X.ne_ptr = &ctl->ne; X.ne_static = 0; X.total_windows = c.total_windows;
             X.in_aligned16 = c.in_aligned16 ? 1u : 0u; X.pre_bytes = c.pc.pre_bytes; X.cta_off = nullptr; X.ncta = 0; X.region_stride = 0;
@@ -1679,7 +1716,7 @@ static int run_sparse(CallCtx& c) {
                 CK(cudaEventSynchronize(ss->pev[k].gp[part]));
                 const unsigned long long r1 = part + 1 == gparts[k] ? s.rec_base + s.nrec : s.part_rec_end[part];
                 const unsigned long long t1 = part + 1 == gparts[k] ? s.text_base + s.ntext : s.part_text_end[part];
-                const bool zc = ss->use_direct && K == 1 && !getenv("SX_NO_ZERO_COPY");
+                const bool zc = ss->use_direct && !heavy && !getenv("SX_NO_ZERO_COPY");
                 const bool fb = hc->piece[k].text_fallback != 0;
                 if (fb && r1 > r0) {
                     const int mgrid = (int)std::min<size_t>((size_t)(r1 - r0 + 255) / 256, (size_t)ss->num_sms * 8);
@@ -1688,10 +1725,14 @@ static int run_sparse(CallCtx& c) {
                     ss->stats.kernel_launches++;
                 }
                 if (ss->use_direct) {
-                    if (!zc && r1 > r0) CK(cudaMemcpyAsync(fc->set.f + r0, ss->d_findings + r0, (size_t)(r1 - r0) * sizeof(WireFinding), cudaMemcpyDeviceToHost, ss->sC));
+                    if (!zc && r1 > r0) {
+                        CK(cudaMemcpyAsync(fc->set.f + r0 * 8, ss->d_findings + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, ss->sC));
+                        const unsigned long long p0 = (r0 + kWirePage - 1) / kWirePage, p1 = (r1 + kWirePage - 1) / kWirePage;  // pages that start here
+                        if (p1 > p0) CK(cudaMemcpyAsync(fc->set.f + fc->wcap * 8 + p0 * 8, ss->d_pagebase + p0, (size_t)(p1 - p0) * 8, cudaMemcpyDeviceToHost, ss->sC));
+                    }
                     // zero copy: the text is already there, unless some chunk left it to the materialize kernel
                     if ((!zc || fb) && t1 > t0) CK(cudaMemcpyAsync(fc->set.t + t0, ss->d_text + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ss->sC));
-                    ss->stats.d2h_bytes += (r1 - r0) * sizeof(WireFinding) + (t1 - t0);
+                    ss->stats.d2h_bytes += (r1 - r0) * 8 + (t1 - t0);
                 }
                 r0 = r1; t0 = t1;
             }
@@ -1732,7 +1773,7 @@ static int run_sparse(CallCtx& c) {
         float pre = 0, ex = 0, stage[6] = {0, 0, 0, 0, 0, 0};
         for (int k = 0; k < K; ++k) {
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, ss->pev[k].p0, ss->pev[k].p1) == cudaSuccess) pre += ms;
+            if (k == 0 && cudaEventElapsedTime(&ms, ss->pev[0].p0, ss->pev[0].p1) == cudaSuccess) pre += ms;
             if (cudaEventElapsedTime(&ms, ss->pev[k].b0, ss->pev[k].b1) == cudaSuccess) ex += ms;
             if (cudaEventElapsedTime(&ms, ss->pev[k].b0, ss->pev[k].sev[1]) == cudaSuccess) stage[0] += ms;  // compact
             for (int i = 1; i < 6; ++i)
@@ -1743,7 +1784,8 @@ static int run_sparse(CallCtx& c) {
         ss->stats.exact_kernel_ms = ex;
         for (int i = 0; i < 6; ++i) ss->stats.sparse_stage_ms[i] = stage[i];
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, ss->pev[0].p0, ss->pev[K - 1].b1) == cudaSuccess) ss->stats.scan_kernel_ms = ms;
+        for (int k = 0; k < K; ++k)
+            if (cudaEventElapsedTime(&ms, ss->pev[0].p0, ss->pev[k].b1) == cudaSuccess) ss->stats.scan_kernel_ms = std::max(ss->stats.scan_kernel_ms, ms);
         cudaGetLastError();
         ss->stats.pieces = (uint32_t)K;
     }
@@ -1756,6 +1798,7 @@ static int run_sparse(CallCtx& c) {
     c.fin = hc->fin;
     if (c.tail_n && c.buf_is_device) memcpy(c.tail + 8 - c.tail_n, hc->tail + 8 - c.tail_n, c.tail_n);
     c.direct_out = ss->use_direct != 0;
+    c.wire = 8;
     c.records_in_order = true;
     return 1;
 }
@@ -1899,9 +1942,9 @@ static int run_block(CallCtx& c) {
         // the device, one copy to the address the findings already point to)
         const size_t nblocks = (size_t)((counters[2] + kThreads - 1) / kThreads);
         pinned_release(fc->set);
-        if (pinned_acquire(nrec, ntext, &fc->set) && grow(&ss->d_bpos, &ss->bpos_cap, nblocks + 1)) {
+        if (pinned_acquire(nrec * sizeof(WireFinding), ntext, &fc->set) && grow(&ss->d_bpos, &ss->bpos_cap, nblocks + 1)) {
             ScanOut O{ss->d_recs, ss->rec_cap, ss->text_cap, ss->d_blocks, ss->d_counters, ss->d_final, reinterpret_cast<uint4*>(fc->set.f),
-                      fc->set.fcap, nullptr, c.input_file_id, ss->m.mission_id};
+                      fc->set.fcap / sizeof(WireFinding), nullptr, c.input_file_id, ss->m.mission_id};
             sx_order_scan_kernel<<<1, 1024, 0, st>>>(ss->d_blocks, ss->d_bpos, nblocks);
             const unsigned wgrid = (unsigned)std::min<size_t>((nblocks + 7) / 8, (size_t)ss->num_sms * 8);
             sx_order_write_kernel<<<wgrid, 256, 0, st>>>(P, O, ss->d_blocks, ss->d_bpos, nblocks, nrec);
@@ -1920,6 +1963,7 @@ static int run_block(CallCtx& c) {
             cudaEventElapsedTime(&ms, ss->ev[2], ss->ev[3]);
             ss->stats.materialize_kernel_ms = ms;
             c.direct_out = true;
+            c.wire = 16;
         } else {
             cudaGetLastError();
             pinned_release(fc->set);
@@ -2061,15 +2105,12 @@ static sx_finding_collection* scan_impl(sx_scanner_state* ss, int input_file_id,
         ss->stats.host_phase_ms[2] = std::chrono::duration<float, std::milli>(t_post - c.t_begin).count();
         const bool tail_is_leftover = nrec > 0 && (fin.last_flags & RF_LEFTOVER) != 0;
         const size_t n_out = nrec - (tail_is_leftover ? 1 : 0);
-        fc->wire = true;
+        fc->wire = c.wire;
         fc->n = n_out;
         fc->base = P.base_consumed;
         fc->file_id = (int16_t)input_file_id;
         fc->mission_id = ss->m.mission_id;
-        auto wire_text = [&](size_t i, const uint8_t** p, size_t* len) {
-            *p = fc->set.t + (fc->set.f[i].b & 0xFFFFFFFFFFull);
-            *len = (size_t)((fc->set.f[i].a >> 40) & 0x3FFFFFu);
-        };
+        auto wire_text = [&](size_t i, const uint8_t** p, size_t* len) { fc->wire_text(i, p, len); };
         // host text in front of device text: the first record of a run that began in the previous call, the leftover
         auto with_host_text = [&](size_t i, std::vector<uint8_t>& dst) {
             const uint8_t* p; size_t len;

@@ -285,8 +285,8 @@ static __global__ void sx_sp_snapshot_kernel(PieceCtl* ctl) { ctl->qcount2_snap 
 // entry is a resolved head, and computable from the window alone when its carry-out does not depend on its own
 // carry-in (mask engine under the null carry, WinResult.cut1 == 0).  What remains is walked in order by
 // sx_sp_fix_kernel.  Persistent over the queue.
-template <class Dec>
-__global__ void __launch_bounds__(kSpThreads, 4)
+template <class Dec, int MINB>
+__global__ void __launch_bounds__(kSpThreads, MINB)
 sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     const unsigned long long nq = B.ctl->qcount;
@@ -342,8 +342,8 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
 // ~0.1 ms for one window on a lone warp, so this kernel runs on a side stream beside sx_sp_members_kernel instead of
 // sitting in front of the walks of sx_sp_fix_kernel.  Persistent over the first qcount2_snap items of queue2 (the
 // declined heads).
-template <class Dec>
-__global__ void __launch_bounds__(kSpThreads, 4)
+template <class Dec, int MINB>
+__global__ void __launch_bounds__(kSpThreads, MINB)
 sx_sp_declined_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, const SparseBufs B) {
     __shared__ Utf8Tables T;
     const unsigned long long nq = B.ctl->qcount2_snap;
@@ -551,8 +551,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     __shared__ uint32_t wa[8], wb[8];
     // the chunk's findings are contiguous in the output, so they are assembled in shared memory and leave as fully
     // coalesced 16-byte stores
-    constexpr uint32_t kStage = 512;
-    __shared__ uint4 sbuf[kStage];
+    constexpr uint32_t kStage = 1024;
+    __shared__ unsigned long long sbuf[kStage];
     // ... and so is their text (UTF-8 -> UTF-8: the bytes of the input range)
     constexpr uint32_t kTextStage = 4096;
     __shared__ __align__(16) uint8_t tbuf[kTextStage];
@@ -608,7 +608,8 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
         // the first / last record of the stream: their flags travel in the final state (host-carried text, leftover)
         auto put = [&](unsigned long long idx, const Record& r) {
             O.recs[idx] = r;
-            if (staged_out) write_host_finding(P, &sbuf[idx - br], r);
+            if (staged_out) sbuf[idx - br] = wire8_of(P, r);
+            if (host_out && (idx % kWirePage) == 0) O.page_base[idx / kWirePage] = r.text_off;
             if (idx == 0) O.final_state->first_flags = r.flags;
             if (text_staged) transcode_record(P, c.g, r, tbuf + (r.text_off - bt));
         };
@@ -665,11 +666,12 @@ sx_sp_gather_kernel(const __grid_constant__ ScanParams P, const ScanOut O, const
     if (active && e == NE - 1 && range_is_tail(X)) { O.final_state->carry = kout; O.final_state->npend = es->npend; }
     __syncthreads();
     if (staged_out) {
-        uint4* const dst = O.host_findings + br;
+        unsigned long long* const dst = reinterpret_cast<unsigned long long*>(O.host_findings) + br;
         for (uint32_t k = threadIdx.x; k < tr; k += kSpThreads) dst[k] = sbuf[k];
     }
     if (round_out) {
-        for (uint32_t k = threadIdx.x; k < tr; k += kSpThreads) write_host_finding(P, O.host_findings + br + k, O.recs[br + k]);
+        unsigned long long* const dst = reinterpret_cast<unsigned long long*>(O.host_findings) + br;
+        for (uint32_t k = threadIdx.x; k < tr; k += kSpThreads) dst[k] = wire8_of(P, O.recs[br + k]);
     }
     if (text_staged && tt) {
         // [bt, bt + tt) of the text arena: bytes up to the first 16-byte boundary, aligned 16-byte body, tail bytes
@@ -716,8 +718,8 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
         if (done_dev != dev) {
             const int co = cudaSharedmemCarveoutMaxShared;
             cudaFuncSetAttribute(sx_sp_heads_kernel<Dec, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(sx_sp_members_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(sx_sp_declined_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_members_kernel<Dec, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(sx_sp_declined_kernel<Dec, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_fix_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_late_kernel<Dec>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_ext_kernel<Dec, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
@@ -742,9 +744,23 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
     sx_sp_snapshot_kernel<<<1, 1, 0, st>>>(B.ctl);
     cudaEventRecord(evs[0], st);
     cudaStreamWaitEvent(side, evs[0], 0);
-    sx_sp_declined_kernel<Dec><<<L.grid_queue, kSpThreads, 0, side>>>(P, X, B);
+    static int mminb = -1, dminb = -1;
+    // CTAs per SM, measured on 4 GiB ranges (profiles/r02_tuning.txt): koi8-r (mask engine) members 4 / 6 / 8: 56.5 / 49.2 / 46.8 ms;
+    // euc-jp (byte-wise engine) members 14.8 / 14.3 / 21.3 ms, declined heads 35.1 / 30.2 / 28.1 ms
+    if (mminb < 0) {
+        const char* e1 = getenv("SX_MEMBERS_MINB");
+        mminb = e1 ? atoi(e1) : (MaskFamily<Dec>::kHas ? 8 : 6);
+        const char* e2 = getenv("SX_DECLINED_MINB");
+        dminb = e2 ? atoi(e2) : 8;
+    }
+    const unsigned gq = L.grid_queue;
+    if (dminb == 8) sx_sp_declined_kernel<Dec, 8><<<gq * 2, kSpThreads, 0, side>>>(P, X, B);
+    else if (dminb == 6) sx_sp_declined_kernel<Dec, 6><<<gq * 3 / 2, kSpThreads, 0, side>>>(P, X, B);
+    else sx_sp_declined_kernel<Dec, 4><<<gq, kSpThreads, 0, side>>>(P, X, B);
     cudaEventRecord(evs[1], side);
-    sx_sp_members_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
+    if (mminb == 8) sx_sp_members_kernel<Dec, 8><<<gq * 2, kSpThreads, 0, st>>>(P, X, B);
+    else if (mminb == 6) sx_sp_members_kernel<Dec, 6><<<gq * 3 / 2, kSpThreads, 0, st>>>(P, X, B);
+    else sx_sp_members_kernel<Dec, 4><<<gq, kSpThreads, 0, st>>>(P, X, B);
     if (ev) cudaEventRecord(ev[3], st);
     cudaStreamWaitEvent(st, evs[1], 0);
     sx_sp_fix_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);

@@ -162,3 +162,25 @@ def test_offsets_beyond_4gib_vs_oracle():
         assert len(exp) > 1000
     assert any(p >= (1 << 32) and b"planted across" in s for p, _, s, _ in raw.select(1 << 32, (1 << 32) + (1 << 20)))
     raw.close()
+
+
+def test_capacity_overflow_reruns_with_counted_sizes():
+    """A first call of a state has no history: entry arrays sized for 1/16 of the windows and a pinned set for one million
+    findings.  koi8-r over 40 MiB of random bytes lists every window (327 680) and prints 1.1 million findings: both
+    capacities overflow, the device reports the counted sizes, the call reruns -- same findings as the oracle; the second
+    call of the state is sized from the first and needs no rerun."""
+    m = M.Mission.for_label("koi8-r", 6)
+    buf = corpus.sx_mix_bytes(44, 0, 40 << 20)
+    gs, os_ = sx.ScannerState(m), oracle_state(m)
+    raw = gs.scan_stream(buf, False, 4096, raw=True)
+    assert gs.last_stats.relaunches >= 1 and gs.last_stats.windows_listed > 300000
+    exp = oracle_findings(os_.scan_stream(buf, False, 4096))
+    assert len(raw) == len(exp) > 1000000
+    assert raw.all() == exp
+    check_state(gs, os_)
+    raw.close()
+    raw = gs.scan_stream(buf, False, 4096, raw=True)
+    assert gs.last_stats.relaunches == 0
+    exp2 = oracle_findings(os_.scan_stream(buf, False, 4096))
+    assert raw.all() == exp2
+    check_state(gs, os_)
