@@ -454,7 +454,18 @@ def main():
             d2h_step += st.d2h_bytes
     e1.record(stream)
     barrier()
+    clock_note = None
+    if len(sampler.lines) < 3:
+        # the timed region is shorter than a few of nvidia-smi's 20 ms sampling periods: keep the same load up (untimed)
+        # until the sampler has seen it
+        t_probe = time.perf_counter()
+        while len(sampler.lines) < 4 and time.perf_counter() - t_probe < 0.5:
+            scan_all(dbuf.data_ptr())
+        torch.cuda.synchronize()
+        clock_note = "timed region shorter than nvidia-smi's 20 ms sampling period: sampled over identical untimed steps run right after it"
     clocks = sampler.stop()
+    if clock_note:
+        clocks["note"] = clock_note
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:

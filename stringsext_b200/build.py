@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libstringsext_b200.so")
-DEPS = ["sx_mb_tables.inc", "sx_core.cuh", "sx_fast_utf8.cuh", "sx_mask_utf8.cuh", "sx_sparse_utf8.cuh", "sx_exact.cuh", "sx_scan.cu", "sx_exact_inst.cu", os.path.join("..", "..", "include", "stringsext_b200.h")]
+DEPS = ["sx_mb_tables.inc", "sx_core.cuh", "sx_fast_utf8.cuh", "sx_fast_generic.cuh", "sx_mask_utf8.cuh", "sx_sparse_utf8.cuh", "sx_exact.cuh", "sx_scan.cu", "sx_exact_inst.cu", os.path.join("..", "..", "include", "stringsext_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 N_INST = 9
 

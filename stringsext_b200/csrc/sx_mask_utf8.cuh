@@ -23,6 +23,7 @@
 // tests/emul runs this code on the CPU against the oracle (it is tried first by WindowEngine<DecUtf8>).
 #pragma once
 #include "sx_fast_utf8.cuh"
+#include "sx_fast_generic.cuh"
 
 namespace sx {
 
@@ -768,7 +769,8 @@ template <class Dec> struct WindowEngine {
             }))
             return;
 #endif
-        scan_window<Dec>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
+        if (Dec::kStateful && !P.general) scan_window_fast_generic<Dec>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
+        else scan_window<Dec>(P, tsrc, g, geo, kin, mode, wr, text_off, res, desc);
     }
 };
 template <> struct WindowEngine<DecUtf8> {

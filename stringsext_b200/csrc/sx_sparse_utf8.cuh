@@ -305,7 +305,8 @@ sx_sp_members_kernel(const __grid_constant__ ScanParams P, const ExactCfg X, con
             Carry kin = carry_none();
             bool known = false;
             if (!pred_is_member) {
-                known = B.H[e - 1].status == ES_DONE;
+                // byte-wise decoders: sx_sp_declined_kernel has run (stream order), the head keeps its ES_DECLINED status
+                known = B.H[e - 1].status == ES_DONE || (!MaskFamily<Dec>::kHas && B.H[e - 1].resolved);
                 if (known) kin = B.H[e - 1].kout;
             } else {
                 WinGeom pg;
@@ -716,7 +717,9 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
         int dev = 0;
         cudaGetDevice(&dev);
         if (done_dev != dev) {
-            const int co = cudaSharedmemCarveoutMaxShared;
+            static int co_env = -2;
+            if (co_env == -2) { const char* cv = getenv("SX_CARVEOUT"); co_env = cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared; }
+            const int co = co_env;
             cudaFuncSetAttribute(sx_sp_heads_kernel<Dec, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_members_kernel<Dec, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
             cudaFuncSetAttribute(sx_sp_declined_kernel<Dec, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
@@ -742,8 +745,14 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
     }
     if (ev) cudaEventRecord(ev[2], st);
     sx_sp_snapshot_kernel<<<1, 1, 0, st>>>(B.ctl);
-    cudaEventRecord(evs[0], st);
-    cudaStreamWaitEvent(side, evs[0], 0);
+    // Mask-engine decoders: the few declined heads run on the side stream beside the members.  Byte-wise decoders: every
+    // head is "declined", so they run first, in stream order, and the members find their heads resolved.
+    constexpr bool kSide = MaskFamily<Dec>::kHas;
+    cudaStream_t dst = kSide ? side : st;
+    if (kSide) {
+        cudaEventRecord(evs[0], st);
+        cudaStreamWaitEvent(side, evs[0], 0);
+    }
     static int mminb = -1, dminb = -1;
     // CTAs per SM, measured on 4 GiB ranges (profiles/r02_tuning.txt): koi8-r (mask engine) members 4 / 6 / 8: 56.5 / 49.2 / 46.8 ms;
     // euc-jp (byte-wise engine) members 14.8 / 14.3 / 21.3 ms, declined heads 35.1 / 30.2 / 28.1 ms
@@ -754,15 +763,15 @@ inline cudaError_t launch_sparse_impl(const ScanParams& P, const ScanOut& O, con
         dminb = e2 ? atoi(e2) : 8;
     }
     const unsigned gq = L.grid_queue;
-    if (dminb == 8) sx_sp_declined_kernel<Dec, 8><<<gq * 2, kSpThreads, 0, side>>>(P, X, B);
-    else if (dminb == 6) sx_sp_declined_kernel<Dec, 6><<<gq * 3 / 2, kSpThreads, 0, side>>>(P, X, B);
-    else sx_sp_declined_kernel<Dec, 4><<<gq, kSpThreads, 0, side>>>(P, X, B);
-    cudaEventRecord(evs[1], side);
+    if (dminb == 8) sx_sp_declined_kernel<Dec, 8><<<gq * 2, kSpThreads, 0, dst>>>(P, X, B);
+    else if (dminb == 6) sx_sp_declined_kernel<Dec, 6><<<gq * 3 / 2, kSpThreads, 0, dst>>>(P, X, B);
+    else sx_sp_declined_kernel<Dec, 4><<<gq, kSpThreads, 0, dst>>>(P, X, B);
+    if (kSide) cudaEventRecord(evs[1], side);
     if (mminb == 8) sx_sp_members_kernel<Dec, 8><<<gq * 2, kSpThreads, 0, st>>>(P, X, B);
     else if (mminb == 6) sx_sp_members_kernel<Dec, 6><<<gq * 3 / 2, kSpThreads, 0, st>>>(P, X, B);
     else sx_sp_members_kernel<Dec, 4><<<gq, kSpThreads, 0, st>>>(P, X, B);
     if (ev) cudaEventRecord(ev[3], st);
-    cudaStreamWaitEvent(st, evs[1], 0);
+    if (kSide) cudaStreamWaitEvent(st, evs[1], 0);
     sx_sp_fix_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
     sx_sp_late_kernel<Dec><<<L.grid_queue, kSpThreads, 0, st>>>(P, X, B);
     if (ev) cudaEventRecord(ev[4], st);

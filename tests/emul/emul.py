@@ -55,7 +55,7 @@ def lib():
     if _lib is None:
         src = os.path.join(HERE, "sx_emul.cpp")
         csrc = os.path.join(HERE, "..", "..", "stringsext_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("sx_core.cuh", "sx_fast_utf8.cuh", "sx_mask_utf8.cuh", "sx_mb_tables.inc")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("sx_core.cuh", "sx_fast_utf8.cuh", "sx_fast_generic.cuh", "sx_mask_utf8.cuh", "sx_mb_tables.inc")]
         if (not os.path.exists(LIB)) or max(os.path.getmtime(f) for f in deps) > os.path.getmtime(LIB):
             os.makedirs(os.path.dirname(LIB), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", LIB, src])
