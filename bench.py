@@ -376,6 +376,8 @@ def main():
         my_missions = [lay_rank]
     if args.only:
         my_missions = [i for i in my_missions if i in {int(x) for x in args.only.split(",")}]
+        if not my_missions:
+            sys.exit("--only selects none of this rank's missions (mission sharding gives rank r mission r)")
     blen = hi - base
     missions = [make_mission(sx, cfg["missions"][i][0], cfg["missions"][i][1], cfg["n"], i, counter_offset=base) for i in my_missions]
     labels = [cfg["missions"][i][0] for i in my_missions]

@@ -177,7 +177,10 @@ template <class Dec, class TileSrc>
 SX_HD_NOINLINE void scan_window_fast_generic(const ScanParams& P, const TileSrc& tsrc, const GlobalSrc& g, const WinGeom& geo,
                                              const Carry& kin, int mode, Record* wr, uint64_t text_off, WinResult& res, WinDesc* desc) {
     const uint32_t n = P.n, q = P.q;
-    const uint64_t af_lo = P.af_lo, af_hi = P.af_hi, ubf = P.ubf;
+    // pass_filter (sx_core.cuh; Utf8Filter::pass_af_filter / pass_ubf_filter, mission.rs:333-348) as one indexed word:
+    // lead bytes 00-7F index the 128-bit ASCII filter, 80-FF the 64-bit unicode-block filter with (lb & 0x3f)
+    const uint32_t ftab[8] = {(uint32_t)P.af_lo, (uint32_t)(P.af_lo >> 32), (uint32_t)P.af_hi, (uint32_t)(P.af_hi >> 32),
+                              (uint32_t)P.ubf,   (uint32_t)(P.ubf >> 32),   (uint32_t)P.ubf,   (uint32_t)(P.ubf >> 32)};
     Dec dec;
     dec.init(P, tsrc, geo.ws);
     ProbeCtx<Dec> pc;
@@ -227,9 +230,7 @@ SX_HD_NOINLINE void scan_window_fast_generic(const ScanParams& P, const TileSrc&
 #define SXG_MASK(cond) (0u - (uint32_t)(cond))
     auto feed = [&](const GenEvent& ev) {
         uint32_t k_char = SXG_MASK(ev.kind == GE_CHAR), k_mal = SXG_MASK(ev.kind == GE_MAL);
-        const uint64_t w_lo = 0ull - (uint64_t)(ev.lb < 64u), w_ub = 0ull - (uint64_t)(ev.lb >= 128u);
-        const uint64_t word = (af_lo & w_lo) | (af_hi & ~(w_lo | w_ub)) | (ubf & w_ub);  // pass_filter, mission.rs:333-348
-        const uint32_t k_pf = 0u - ((uint32_t)(word >> (ev.lb & 63u)) & 1u);
+        const uint32_t k_pf = 0u - ((ftab[(ev.lb >> 5) & 7u] >> (ev.lb & 31u)) & 1u);
         uint32_t k_pass = k_char & k_pf, k_fail = k_char & ~k_pf;
         const uint32_t k_ends = k_mal | k_fail;
         const uint32_t k_print = SXG_MASK(run_n >= n) | SXG_MASK((fl & (FF_ATLEFT | FF_LASTCUT)) == (FF_ATLEFT | FF_LASTCUT));
@@ -304,7 +305,23 @@ SX_HD_NOINLINE void scan_window_fast_generic(const ScanParams& P, const TileSrc&
         SX_OPAQUE(e0.kind); SX_OPAQUE(e0.lb); SX_OPAQUE(e0.ul); SX_OPAQUE(e0.cs); SX_OPAQUE(e0.ce); SX_OPAQUE(e0.half2);
         SX_OPAQUE(e1.kind); SX_OPAQUE(e1.lb); SX_OPAQUE(e1.ul); SX_OPAQUE(e1.cs); SX_OPAQUE(e1.ce); SX_OPAQUE(e1.half2);
         feed(e0);  // no event: every mask is zero
-        if (e1.kind) feed(e1);
+        if (e1.kind) {
+            // Second event of a byte: a char right behind a malformed sequence (the ASCII byte that ended a double-byte
+            // sequence, the BMP unit behind a lone surrogate).  The automaton has just started a segment, so the
+            // transitions are a few blends; the probe and q == 1 take the general path.
+            const uint32_t k_pf = 0u - ((ftab[(e1.lb >> 5) & 7u] >> (e1.lb & 31u)) & 1u);
+            const bool fresh = e0.kind == GE_MAL && run_n == 0;
+            if (fresh && q > 1 && !((fl & FF_PROBE) && e1.lb >= 0x80)) {
+                fl &= ~FF_PROBE;
+                run_s = (int32_t)SXG_BLEND((uint32_t)run_s, (uint32_t)e1.cs, k_pf);
+                run_e = (int32_t)SXG_BLEND((uint32_t)run_e, (uint32_t)e1.ce, k_pf);
+                fl = SXG_BLEND(fl, (fl & ~GF_HALF) | (e1.half2 ? GF_HALF : 0u), k_pf);
+                run_n = 1u & k_pf;
+                run_t = e1.ul & k_pf;
+                const uint32_t clr = (m == 2 ? FF_S2ALL : 0u) | FF_HOSTCARRY | FF_ATLEFT | GF_HALF;  // m >= 2, not in the first run
+                fl &= ~(clr & ~k_pf);
+            } else feed(e1);
+        }
     });
 
     // ---- end of the window's last segment (helper.rs:343-431 for the run touching the right boundary) ----
