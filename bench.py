@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sparse-mode", type=int, default=1, help="debug: 0 block kernel only, 1 default")
     ap.add_argument("--as-rank", type=int, default=-1, help="debug: a single process doing the work of rank R of a --gpus N job")
+    ap.add_argument("--mission-threads", type=int, default=1, help="1: one host thread + stream per mission of a rank (default); 0: the rank's missions one after the other")
     ap.add_argument("--only", default="", help="debug: comma-separated mission indices of the config to run (others are skipped)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -419,8 +420,8 @@ def main():
         """One step: every mission of this rank over its range of the stream (device pointer `ptr`)."""
         for ms in mstreams:
             ms.wait_stream(stream)  # e.g. the H2D copy of the e2e leg
-        if pool is None:
-            return [scan_one(0, ptr)]
+        if pool is None or args.mission_threads == 0:
+            return [scan_one(k, ptr) for k in range(len(states))]
         return list(pool.map(lambda k: scan_one(k, ptr), range(len(states))))
 
     def barrier():

@@ -1252,6 +1252,8 @@ struct PrefCfg {
     uint32_t refine;  // PF_UTF8: a long good-byte run only counts if it holds >= n_chars non-continuation bytes
     uint32_t pre_bytes;  // pre-roll length: longest possible trailing good run of an uninteresting window + slack
     uint32_t kill_trail; // --grep-char missions: a window behind >= this many trailing good bytes is listed (0: rule off)
+    uint32_t sb_rule;    // --same-unicode-block missions: a window is listed when its own trailing good run and the one of
+                         // the window before it may both hold a multi-byte char (PrefWin::trail_hi), see make_pref_cfg
     // PF_PAIR (Big5, EUC-JP): per byte value, bit 0: a passing single-byte char, bit 1: may be the lead (or, EUC-JP, the
     // middle byte) of a passing multi-byte char, bit 2: may be a trail byte.  A byte is good when it is a passing
     // single-byte char, a lead candidate followed by a trail candidate, or a trail candidate behind a lead candidate --
@@ -1293,35 +1295,40 @@ SX_HD bool pref_good(const ScanParams& P, const PrefCfg& c, const S& src, int64_
     return ((c.blkH >> (src.get(t) >> 5)) & 1u) != 0;
 }
 
-struct PrefWin { uint32_t lead, trail, maxrun, maxchars, kill; };  // kill: see PrefCfg::kill_trail  // maxchars: most non-continuation bytes in a run of >= T bytes
+struct PrefWin { uint32_t lead, trail, maxrun, maxchars, kill, trail_hi, lead_hi; };  // trail_hi, lead_hi: see PrefCfg::sb_rule  // kill: see PrefCfg::kill_trail  // maxchars: most non-continuation bytes in a run of >= T bytes
 // General missions that may use the prefilter (see make_pref_cfg: kill_trail); the others need every window scanned:
 // a stale lead byte survives ASCII junk under --same-unicode-block (helper.rs:327-330), n > q drops whole segments.
-SX_HD bool pref_general_ok(const ScanParams& P) { return P.grep_char >= 0 && !P.same_block && P.n <= P.q; }
+SX_HD bool pref_general_ok(const ScanParams& P) {
+    return P.n <= P.q && ((P.grep_char >= 0 && !P.same_block) || (P.grep_char < 0 && P.same_block));
+}
 
 template <class S>
 SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& src, int64_t ws, int64_t we) {
-    PrefWin r{0, 0, 0, 0, 0};
+    PrefWin r{0, 0, 0, 0, 0, 0, 0};
     uint32_t run = 0, chars = 0;
-    bool seen_bad = false;
+    bool seen_bad = false, run_hi = false;
     auto close_run = [&]() { if (run >= c.T && chars > r.maxchars) r.maxchars = chars; };
     for (int64_t i = ws; i < we; ++i) {
         if (pref_good(P, c, src, i, ws, we)) {
             run++;
             const uint32_t b = src.get(i);
             if (!(b >= 0x80 && b < 0xC0)) chars++;
+            if (b >= 0x80 || c.family == PF_UNIT) run_hi = true;  // may belong to a char outside ASCII
             if (run > r.maxrun) r.maxrun = run;
             // a good run of >= kill_trail bytes, or one that began at (before) the window's first byte, reaching one of
             // the last 4 bytes: the decoded text may end in >= q passing chars (up to 3 bytes stay pending in the decoder)
             if (c.kill_trail != 0 && i + 4 >= we && (run >= c.kill_trail || !seen_bad)) r.kill = 1;
         } else {
             close_run();
-            if (!seen_bad) { r.lead = run; seen_bad = true; }
-            run = 0; chars = 0;
+            if (!seen_bad) { r.lead = run; r.lead_hi = (run > 0 && run_hi) ? 1u : 0u; seen_bad = true; }
+            run = 0; chars = 0; run_hi = false;
         }
     }
     close_run();
     if (!seen_bad) r.lead = run;
     r.trail = run;
+    // the trailing good run may hold a char outside ASCII -- or reaches back beyond the window, where it may
+    r.trail_hi = (run > 0 && (run_hi || !seen_bad)) ? 1u : 0u;
     return r;
 }
 
@@ -1332,7 +1339,7 @@ SX_HD PrefWin pref_window_ref(const ScanParams& P, const PrefCfg& c, const S& sr
 inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned, const uint32_t* mb_a = nullptr, const uint32_t* mb_b = nullptr) {
     PrefCfg c;
     c.enabled = 0; c.family = PF_BYTE; c.blkA = 0; c.blkH = 0; c.multi = 0; c.T = P.n; c.unit = 1; c.hi_pos = 0;
-    c.n_chars = P.n; c.refine = 0; c.pre_bytes = 0; c.kill_trail = 0;
+    c.n_chars = P.n; c.refine = 0; c.pre_bytes = 0; c.kill_trail = 0; c.sb_rule = 0;
     for (uint32_t k = 0; k < 256; ++k) c.pair_cls[k] = 0;
     for (uint32_t k = 0; k < 4; ++k) {
         const uint64_t word = k < 2 ? P.af_lo : P.af_hi;
@@ -1421,6 +1428,18 @@ inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned, const 
     // window ever sees its first run filled up to q chars (trail + lead >= q * unit >= T lists it), and past its first
     // run an unlisted window holds nothing of its carry-in.  Other general missions: no prefilter (pref_general_ok).
     if (P.grep_char >= 0 && !P.same_block && P.n <= P.q) c.kill_trail = P.q * c.unit;
+    // --same-unicode-block (without --grep-char, chars_min_nb <= q): SplitStr keeps the lead byte of the last multi-byte
+    // char it saw across failing ASCII chars and short runs (helper.rs:221, :287-292, :327-330), and a leftover hands its
+    // own to the next window.  An unlisted window prints nothing (its runs are pieces of the plain mission's runs), but
+    // such a stale lead byte decides where its TRAILING run -- the carry-out -- begins: "abcΓΔ|" is kept whole behind a
+    // clean start and as "ΓΔ" behind a Cyrillic char.  That needs a multi-byte char in the leftover coming in (the trailing
+    // good run of the window before holds a byte >= 0x80, or covers that whole window) -- or one in the window's leading
+    // run, which a "cut" carry prints (the `break` forgets the lead byte, helper.rs:315-330) and any other carry drops
+    // (the lead byte stays); the cut flag survives junk, so the window before says nothing about it -- and one in the
+    // window's own trailing run: such a window is listed.  Every other unlisted window has a carry-out that depends on its own bytes
+    // only -- on ALL of them (the stale byte may stem from the window's first chars), so the pre-roll of a head is the
+    // whole window before it.
+    if (P.same_block && P.grep_char < 0 && P.n <= P.q) { c.sb_rule = 1; c.pre_bytes = P.W; }
     return c;
 }
 
@@ -1437,11 +1456,12 @@ SX_HD bool pref_interesting_ref(const ScanParams& P, const PrefCfg& c, const Geo
     if (w == 0 || w == total_windows - 1 || (uint32_t)(g.we - g.ws) < P.W || g.final_last) return true;
     const PrefWin a = pref_window_ref(P, c, src, g.ws, g.we);
     if (c.refine ? (a.maxrun >= c.T && a.maxchars >= c.n_chars) : (a.maxrun >= c.T)) return true;
-    if ((w % kPrefTileWin) == 0) return a.lead >= 1 || c.kill_trail != 0;  // previous window unknown to the tile
+    if ((w % kPrefTileWin) == 0) return a.lead >= 1 || c.kill_trail != 0 || (c.sb_rule && a.trail_hi);  // previous window unknown to the tile
     WinGeom gp;
     geo.window(w - 1, gp);
     const PrefWin b = pref_window_ref(P, c, src, gp.ws, gp.we);
     if (b.kill) return true;
+    if (c.sb_rule && a.trail_hi && (b.trail_hi || a.lead_hi)) return true;
     // A run of >= T good bytes touches the window's left boundary.  This includes a run that only starts at the
     // window's first byte (b.trail == 0): whatever its char count, it is the run a "cut" carry would complete,
     // and listing it keeps the carry-out of every UNLISTED window independent of its carry-in.

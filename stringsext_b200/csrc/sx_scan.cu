@@ -328,6 +328,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         uint32_t wlen = 0;
         if (valid) wlen = (uint32_t)(((ws + W) < P.len ? (ws + W) : P.len) - ws);
         uint32_t m[4] = {0, 0, 0, 0};
+        uint32_t mh[4] = {0, 0, 0, 0};  // PrefCfg::sb_rule: bytes >= 0x80 of the window
         bool sure = false, cand = false;
         if constexpr (FAST) {
             // ---- bit planes p7/p6/p5 of the window's 128 bytes (8 conflict-free LDS.128) ----------------------
@@ -437,6 +438,15 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             // acc[p] collects the flags of data words 2p and 2p+1 of the current 32-byte group (dp4a,
             // flags sit at bit 7 of each byte, so acc[p] = (8 flags) << 7).
             uint32_t acc[4] = {0, 0, 0, 0};
+            uint32_t acch[4] = {0, 0, 0, 0};
+            auto puth = [&](int widx, uint32_t x) {  // like put(): bit 7 of every byte of data word widx -> mh
+                const int k = widx & 7;
+                acch[k >> 1] = dp4a_u(x & 0x80808080u, (k & 1) ? 0x80402010u : 0x08040201u, acch[k >> 1]);
+                if (k == 7) {
+                    mh[widx >> 3] = (acch[0] >> 7) | (acch[1] << 1) | (acch[2] << 9) | (acch[3] << 17);
+                    acch[0] = acch[1] = acch[2] = acch[3] = 0;
+                }
+            };
             uint32_t pA = 0, pL = 0, pC = 0, ppLC = 0xFFFFFFFFu;  // PF_UTF8: classes of the word awaiting its right neighbour
             auto put = [&](int widx, uint32_t gflags) {  // widx is a compile-time constant at every call site
                 const int k = widx & 7;
@@ -455,6 +465,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t x = xs[j];
                         const uint32_t x1 = x << 1, x2 = x << 2;
+                        if (C.sb_rule) puth(4 * c + j, x);
                         if (FAMILY == PF_UTF8 || FAMILY == PF_PAIR) {
                             uint32_t cn, lp, ap;  // flags at bit 7 of every byte: trail candidate, lead candidate, passing single byte
                             if (FAMILY == PF_PAIR) {
@@ -486,6 +497,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                     }
                     if ((c & 1) == 0 && (uint32_t)c == nchunk - 1) {  // odd number of chunks: half a mask word is pending
                         m[c >> 1] = (acc[0] >> 7) | (acc[1] << 1);
+                        mh[c >> 1] = (acch[0] >> 7) | (acch[1] << 1);
                     }
                 }
             }
@@ -525,7 +537,7 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
             }
         }
         uint32_t lead = 0, trail = 0;
-        bool longrun = false;
+        bool longrun = false, sb_lead_hi = false;
         if (valid) {
             uint32_t nm[4] = {~m[0], ~m[1], ~m[2], ~m[3]};  // bad bytes of the window
             if (wlen < 128) {
@@ -556,6 +568,24 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                     }
                 }
             }
+            if (C.sb_rule) {
+                // PrefWin::lead_hi / trail_hi: the leading / trailing good run holds a byte >= 0x80 (any good byte for the
+                // unit families), or the trailing run covers the whole window
+                bool lh = false, th = false;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint32_t hw = (FAMILY == PF_UNIT) ? m[q4] : (mh[q4] & m[q4]);
+                    const int lo_bit = q4 * 32;
+                    const int nl = (int)lead - lo_bit;             // bits of this word inside the leading run
+                    const uint32_t lmask = nl <= 0 ? 0u : (nl >= 32 ? 0xFFFFFFFFu : ((1u << nl) - 1u));
+                    const int t0 = (int)(wlen - trail) - lo_bit;   // first bit of the trailing run, relative to this word
+                    const uint32_t tmask = t0 >= 32 ? 0u : (t0 <= 0 ? 0xFFFFFFFFu : ~((1u << t0) - 1u));
+                    lh = lh || (hw & lmask) != 0;
+                    th = th || (hw & tmask) != 0;               // bits beyond wlen are zero in m
+                }
+                if (trail > 0 && (th || trail == wlen)) trail |= 0x40000000u;
+                sb_lead_hi = lead > 0 && lead < wlen && lh;
+            }
 
         }
         s_trail[tid] = trail;
@@ -564,10 +594,11 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
         if (valid) {
             const bool forced = (w == O.w_first) || (piece_start && w == t_begin * (long long)kPrefTileWin) || (w == total_windows - 1) || (wlen < W) || (P.is_last && ws + wlen == P.len);
             if (forced) sure = true;
-            else if (tid == 0) sure = lead >= 1 || C.kill_trail != 0;
+            else if (tid == 0) sure = lead >= 1 || C.kill_trail != 0 || (trail & 0x40000000u) != 0;
             else {
-                const uint32_t pt = s_trail[tid - 1];  // bit 31: the previous window's kill flag
-                sure = (lead >= 1 && (pt & 0x7FFFFFFFu) + lead >= C.T) || (pt >> 31) != 0;
+                const uint32_t pt = s_trail[tid - 1];  // bit 31: the previous window's kill flag, bit 30: its trail_hi
+                sure = (lead >= 1 && (pt & 0x3FFFFFFFu) + lead >= C.T) || (pt >> 31) != 0 ||
+                       ((trail & 0x40000000u) != 0 && ((pt & 0x40000000u) != 0 || sb_lead_hi));  // PrefCfg::sb_rule
             }
             if (!sure && longrun) { if (do_refine) cand = true; else sure = true; }
         }
@@ -1376,7 +1407,7 @@ static cudaError_t launch_prefilter_t(const ScanParams& P, const PrefCfg& c, con
 static cudaError_t launch_prefilter(const ScanParams& P, const PrefCfg& c, const PrefK& k, const PrefOut& o, long long total_windows,
                                     int grid, cudaStream_t st, const CUtensorMap& tm, uint32_t use_tma) {
     const bool defshape = c.family == PF_UTF8 && c.blkA == 0xEu && c.blkH == (1u << 6) && !c.multi;
-    const bool fast = P.W == 128 && c.T <= 32 && c.kill_trail == 0;  // the bit-plane path keeps only T - 1 flags of the previous window
+    const bool fast = P.W == 128 && c.T <= 32 && c.kill_trail == 0 && c.sb_rule == 0;  // the bit-plane path keeps only T - 1 flags of the previous window
 #define SX_PREF(F, D) (fast ? launch_prefilter_t<F, D, true>(P, c, k, o, total_windows, grid, st, tm, use_tma) \
                             : launch_prefilter_t<F, D, false>(P, c, k, o, total_windows, grid, st, tm, use_tma))
     switch (c.family) {
@@ -1864,6 +1895,7 @@ static int run_block(CallCtx& c) {
             PrefOut po;
             po.list = ss->d_list; po.cta_count = ss->d_ccount; po.tiles_per_cta = tiles_per_cta;
             po.tile0 = tile_lo; po.tile_end = tile_hi; po.w_first = c.w_lo; po.w_lo = c.w_lo; po.w_hi = c.w_hi;
+            po.piece_ctas = 0;  // the block kernel takes the whole list at once
             CUtensorMap tmap;
             memset(&tmap, 0, sizeof tmap);
             const uint32_t use_tma = (ss->use_tma && make_tensor_map(&tmap, c.d_in, c.len, kPrefTileWin * P.W)) ? 1u : 0u;
@@ -2065,9 +2097,9 @@ static sx_finding_collection* scan_impl(sx_scanner_state* ss, int input_file_id,
     if (total_windows > 0x7FFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
     c.pc = make_pref_cfg(P, in_aligned16, host_mb_a, host_mb_b);
-    // General missions: an unlisted window's carry-out must not depend on its carry-in.  --grep-char alone gets there with
-    // one more listing rule (PrefCfg::kill_trail, sx_core.cuh); under --same-unicode-block a stale lead byte survives
-    // ASCII junk (helper.rs:327-330) and n > q drops whole segments: those run without the prefilter.  DESIGN.md 7.
+    // General missions: an unlisted window's carry-out must not depend on its carry-in.  --grep-char alone and
+    // --same-unicode-block alone get there with one more listing rule each (PrefCfg::kill_trail / sb_rule, sx_core.cuh);
+    // both together, and n > q (whole segments dropped), run without the prefilter.  DESIGN.md 7.
     if (!ss->use_prefilter || (P.general && !pref_general_ok(P))) c.pc.enabled = 0;
     c.ss = ss; c.fc = fc; c.input_file_id = input_file_id; c.d_in = d_in; c.len = len; c.st = st;
     c.total_windows = total_windows;

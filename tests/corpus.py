@@ -147,6 +147,24 @@ def gen(rng: random.Random, kind: str, n: int, enc: int) -> bytes:
     return bytes(out[:n])
 
 
+def gen_blocks(rng: random.Random, n: int, enc: int) -> bytes:
+    """Short runs that mix unicode blocks, separated by failing ASCII junk: what --same-unicode-block splits on, and
+    where SplitStr's stale lead byte (helper.rs:221, :327-330) decides how a run across a window boundary is cut."""
+    toks = ["Я", "ж", "Γ", "Δ", "é", "ü", "€", "日", "a", "b", "abc", "xy", " ", "\x01", "\x02", "\x01\x01", "Яa", "aΓ", "abЯ", "abcΓΔ", "éa€",
+            "\x7f", "0123", "ЯЯ", "ΓΓΓ"]
+    out = bytearray()
+    junk = rng.choice([0.1, 0.3, 0.5])
+    while len(out) < n:
+        t = rng.choice(["\x01", "\x02", "\x01\x01\x01"]) if rng.random() < junk else rng.choice(toks)
+        if rng.random() < 0.03:
+            out += rng.choice([b"\xff", b"\xc0", b"\x80", b"\xe2\x82", b"\xd8"])
+        b = encode_for(enc, t) if enc not in (0, 4) else t.encode("koi8-r" if enc == 4 else "latin-1", errors="ignore")
+        if enc in (0, 4) and rng.random() < 0.3:
+            b += bytes([rng.choice([0xC0, 0xE9, 0xA3, 0xB3, 0x80, 0x9F, 0xFF])])
+        out += b
+    return bytes(out[:n])
+
+
 KINDS = ["rand", "lowent", "text", "mixed", "runs"]
 LABELS = {0: "ascii", 1: "utf-8", 2: "utf-16le", 3: "utf-16be", 4: "koi8-r", 5: "utf-32le", 6: "utf-32be", 7: "big5", 8: "euc-jp"}
 

@@ -139,6 +139,41 @@ def test_prefilter_window_list_matches_spec_grep(label, n, q, grep, kind):
     check_state(gs, os_)
 
 
+@pytest.mark.parametrize("label,n,q,ubf,kind", [
+    ("utf-8", 6, 64, None, "rand"), ("utf-8", 10, 64, M.UBF_ALL, "rand"), ("utf-8", 8, 8, M.UBF_ALL, "blocks"), ("utf-8", 4, 16, M.UBF_ALL, "blocks"),
+    ("koi8-r", 6, 16, M.UBF_ALL, "blocks"), ("koi8-r", 6, 64, None, "rand"), ("ascii", 4, 8, None, "rand"), ("utf-16le", 4, 16, M.UBF_ALL, "blocks"),
+    ("utf-16be", 10, 64, None, "rand"), ("big5", 6, 16, M.UBF_ALL, "blocks"), ("euc-jp", 6, 64, None, "rand"), ("utf-8", 3, 8, None, "mixed"),
+    ("utf-32le", 4, 16, M.UBF_ALL, "blocks"), ("utf-8", 6, 32, M.UBF_ALL_VALID, "text"),
+])
+def test_prefilter_window_list_matches_spec_same_block(label, n, q, ubf, kind):
+    """--same-unicode-block alone keeps the prefilter with one more rule (PrefCfg::sb_rule: a window whose trailing good
+    run may hold a multi-byte char is listed when the trailing run of the window before it or its own leading run may
+    hold one too; the pre-roll of a head is the whole window before it): the kernel lists exactly the windows of the
+    byte-wise specification and the findings are the oracle's."""
+    import dataclasses
+
+    import emul
+
+    m = dataclasses.replace(M.Mission.for_label(label, n, None, ubf, None, q), require_same_unicode_block=True)
+    rng = random.Random(321)
+    size = (1 << 20) + 4096
+    if kind == "rand":
+        buf = corpus.sx_mix_bytes(19, 0, size)
+        corpus.plant(buf, 19, m.encoding_id, n, q, density=1 << 12)
+        buf = buf.tobytes()
+    elif kind == "blocks":
+        buf = corpus.gen_blocks(rng, size, m.encoding_id)
+    else:
+        buf = corpus.gen(rng, kind, size, m.encoding_id)
+    gs, es, os_ = sx.ScannerState(m), emul.EmulState(m, True), oracle_state(m)
+    got = gpu_findings(gs.scan_stream(buf, False, 4096))
+    exp, _ = es.scan_stream(buf, False, 4096)
+    assert gs.last_stats.prefilter_used == 1 and es.stats[7] == 1
+    assert gs.last_window_list() == es.last_list
+    assert got == exp == oracle_findings(os_.scan_stream(buf, False, 4096))
+    check_state(gs, os_)
+
+
 def test_killed_window_case():
     """corpus.KILLED_WINDOW_CASE (a window dropped because of its predecessor's leftover) on the GPU, also embedded in
     a larger stream so that the windows sit in the middle of a block."""
@@ -348,8 +383,8 @@ def test_prefilter_on_off_identical(enc):
 def test_general_missions_large_buffers_vs_oracle(enc):
     """--grep-char / --same-unicode-block / n > q on buffers of many 128-entry blocks (the block kernel's warm-up finds
     a known carry through the WT_GUARD rules, sx_core.cuh guard_benign / guard_known_behind): the oracle's findings,
-    on sparse input (random bytes + planted strings) and dense input, with and without the prefilter (which only
-    --grep-char alone may use, PrefCfg::kill_trail; DESIGN.md section 7)."""
+    on sparse input (random bytes + planted strings) and dense input, with and without the prefilter (which --grep-char
+    alone and --same-unicode-block alone may use, PrefCfg::kill_trail / sb_rule; DESIGN.md section 7)."""
     import dataclasses
 
     rng = random.Random(4242 + enc)
@@ -372,8 +407,8 @@ def test_general_missions_large_buffers_vs_oracle(enc):
                 continue
             ra = gpu_findings(a.scan_stream(part, False, 4096))
             rb = gpu_findings(b.scan_stream(part, False, 4096))
-            grep_only = m.filter.grep_char is not None and not m.require_same_unicode_block and n <= q
-            assert a.last_stats.prefilter_used == (1 if grep_only else 0) and b.last_stats.prefilter_used == 0
+            one_rule = (m.filter.grep_char is not None) != bool(m.require_same_unicode_block) and n <= q
+            assert a.last_stats.prefilter_used == (1 if one_rule else 0) and b.last_stats.prefilter_used == 0
             exp = oracle_findings(os_.scan_stream(part, False, 4096))
             assert ra == exp, (enc, m, len(part))
             assert rb == exp, (enc, m, len(part))

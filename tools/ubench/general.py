@@ -14,12 +14,13 @@ size = (int(sys.argv[1]) if len(sys.argv) > 1 else 1024) << 20
 g = torch.Generator(device="cuda").manual_seed(1)
 buf = torch.randint(0, 256, (size,), dtype=torch.uint8, device="cuda", generator=g)
 stream = torch.cuda.current_stream()
-# (label, grep, same block, prefilter, bytes scanned).  Of the general missions only --grep-char alone may use the prefilter
-# (PrefCfg::kill_trail); for the others the flag has no effect.
+# (label, grep, same block, prefilter, bytes scanned).  Of the general missions --grep-char alone and --same-unicode-block
+# alone may use the prefilter (PrefCfg::kill_trail / sb_rule); for the others the flag has no effect.
 small = min(size, 32 << 20)
 CASES = (("ascii", ord("e"), False, True, small), ("koi8-r", ord("e"), False, True, small), ("utf-8", ord("e"), False, True, size),
          ("utf-8", None, True, True, size), ("ascii", ord("e"), False, True, size), ("koi8-r", None, True, True, size),
-         ("utf-16le", ord("e"), True, True, size), ("utf-8", None, False, True, size))
+         ("utf-16le", ord("e"), True, True, size), ("utf-16le", None, True, True, size), ("ascii", None, True, True, size),
+         ("utf-8", None, True, False, small), ("utf-8", None, False, True, size))
 for label, grep, same, pref, nbytes in CASES:
     m = sx.Mission.for_label(label, 10)
     m = dataclasses.replace(m, filter=dataclasses.replace(m.filter, grep_char=grep), require_same_unicode_block=same)
