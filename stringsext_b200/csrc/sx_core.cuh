@@ -1296,10 +1296,10 @@ SX_HD bool pref_good(const ScanParams& P, const PrefCfg& c, const S& src, int64_
 }
 
 struct PrefWin { uint32_t lead, trail, maxrun, maxchars, kill, trail_hi, lead_hi; };  // trail_hi, lead_hi: see PrefCfg::sb_rule  // kill: see PrefCfg::kill_trail  // maxchars: most non-continuation bytes in a run of >= T bytes
-// General missions that may use the prefilter (see make_pref_cfg: kill_trail); the others need every window scanned:
-// a stale lead byte survives ASCII junk under --same-unicode-block (helper.rs:327-330), n > q drops whole segments.
+// General missions that may use the prefilter: --grep-char and --same-unicode-block, each with one more listing rule
+// (make_pref_cfg: kill_trail, sb_rule).  chars_min_nb > q drops whole segments (helper.rs:410-415): every window scanned.
 SX_HD bool pref_general_ok(const ScanParams& P) {
-    return P.n <= P.q && ((P.grep_char >= 0 && !P.same_block) || (P.grep_char < 0 && P.same_block));
+    return P.n <= P.q && (P.grep_char >= 0 || P.same_block);
 }
 
 template <class S>
@@ -1421,14 +1421,14 @@ inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned, const 
         c.pre_bytes = (c.refine ? P.n * maxlen : c.T) + 3 + c.unit;
     }
     c.enabled = (P.W % 16 == 0 && P.W <= 128 && P.slice_len % P.W == 0 && input_16b_aligned) ? 1u : 0u;
-    // --grep-char (without --same-unicode-block, chars_min_nb <= q): a leftover of q chars is possible (helper.rs:389-392)
+    // --grep-char (chars_min_nb <= q): a leftover of q chars is possible (helper.rs:389-392)
     // and is evaluated at the next window's first char -- dropped together with the rest of that segment if it lacks the
     // grep char (helper.rs:410-415), printed as a "maybe cut" string otherwise -- so the window behind >= q good chars
     // (>= q * unit bytes) has to be scanned exactly even if it holds no run itself.  With that window listed, no unlisted
     // window ever sees its first run filled up to q chars (trail + lead >= q * unit >= T lists it), and past its first
-    // run an unlisted window holds nothing of its carry-in.  Other general missions: no prefilter (pref_general_ok).
-    if (P.grep_char >= 0 && !P.same_block && P.n <= P.q) c.kill_trail = P.q * c.unit;
-    // --same-unicode-block (without --grep-char, chars_min_nb <= q): SplitStr keeps the lead byte of the last multi-byte
+    // run an unlisted window holds nothing of its carry-in.  chars_min_nb > q: no prefilter (pref_general_ok).
+    if (P.grep_char >= 0 && P.n <= P.q) c.kill_trail = P.q * c.unit;
+    // --same-unicode-block (chars_min_nb <= q; with --grep-char both rules apply): SplitStr keeps the lead byte of the last multi-byte
     // char it saw across failing ASCII chars and short runs (helper.rs:221, :287-292, :327-330), and a leftover hands its
     // own to the next window.  An unlisted window prints nothing (its runs are pieces of the plain mission's runs), but
     // such a stale lead byte decides where its TRAILING run -- the carry-out -- begins: "abcΓΔ|" is kept whole behind a
@@ -1439,7 +1439,7 @@ inline PrefCfg make_pref_cfg(const ScanParams& P, bool input_16b_aligned, const 
     // window's own trailing run: such a window is listed.  Every other unlisted window has a carry-out that depends on its own bytes
     // only -- on ALL of them (the stale byte may stem from the window's first chars), so the pre-roll of a head is the
     // whole window before it.
-    if (P.same_block && P.grep_char < 0 && P.n <= P.q) { c.sb_rule = 1; c.pre_bytes = P.W; }
+    if (P.same_block && P.n <= P.q) { c.sb_rule = 1; c.pre_bytes = P.W; }
     return c;
 }
 

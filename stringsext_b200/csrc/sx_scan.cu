@@ -572,18 +572,19 @@ sx_prefilter_kernel(const __grid_constant__ ScanParams P, const PrefCfg C, const
                 // PrefWin::lead_hi / trail_hi: the leading / trailing good run holds a byte >= 0x80 (any good byte for the
                 // unit families), or the trailing run covers the whole window
                 bool lh = false, th = false;
+                const uint32_t trail_len = trail & 0x3FFFFFFFu;  // bit 31 may hold the kill flag (both rules on)
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const uint32_t hw = (FAMILY == PF_UNIT) ? m[q4] : (mh[q4] & m[q4]);
                     const int lo_bit = q4 * 32;
                     const int nl = (int)lead - lo_bit;             // bits of this word inside the leading run
                     const uint32_t lmask = nl <= 0 ? 0u : (nl >= 32 ? 0xFFFFFFFFu : ((1u << nl) - 1u));
-                    const int t0 = (int)(wlen - trail) - lo_bit;   // first bit of the trailing run, relative to this word
+                    const int t0 = (int)(wlen - trail_len) - lo_bit;   // first bit of the trailing run, relative to this word
                     const uint32_t tmask = t0 >= 32 ? 0u : (t0 <= 0 ? 0xFFFFFFFFu : ~((1u << t0) - 1u));
                     lh = lh || (hw & lmask) != 0;
                     th = th || (hw & tmask) != 0;               // bits beyond wlen are zero in m
                 }
-                if (trail > 0 && (th || trail == wlen)) trail |= 0x40000000u;
+                if (trail_len > 0 && (th || trail_len == wlen)) trail |= 0x40000000u;
                 sb_lead_hi = lead > 0 && lead < wlen && lh;
             }
 
@@ -2097,9 +2098,9 @@ static sx_finding_collection* scan_impl(sx_scanner_state* ss, int input_file_id,
     if (total_windows > 0x7FFFFFF0LL) { set_err(SX_ERR_UNSUPPORTED, "stream too long for one call"); return fail; }
     const bool in_aligned16 = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
     c.pc = make_pref_cfg(P, in_aligned16, host_mb_a, host_mb_b);
-    // General missions: an unlisted window's carry-out must not depend on its carry-in.  --grep-char alone and
-    // --same-unicode-block alone get there with one more listing rule each (PrefCfg::kill_trail / sb_rule, sx_core.cuh);
-    // both together, and n > q (whole segments dropped), run without the prefilter.  DESIGN.md 7.
+    // General missions: an unlisted window's carry-out must not depend on its carry-in.  --grep-char and
+    // --same-unicode-block get there with one more listing rule each (PrefCfg::kill_trail / sb_rule, sx_core.cuh);
+    // n > q (whole segments dropped) runs without the prefilter.  DESIGN.md 7.
     if (!ss->use_prefilter || (P.general && !pref_general_ok(P))) c.pc.enabled = 0;
     c.ss = ss; c.fc = fc; c.input_file_id = input_file_id; c.d_in = d_in; c.len = len; c.st = st;
     c.total_windows = total_windows;

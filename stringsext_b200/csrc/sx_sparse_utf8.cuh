@@ -1,5 +1,7 @@
-// sx_sparse_utf8.cuh -- the exact stage for missions with a bit-parallel window engine (UTF-8 and the single-byte
-// family) as a pipeline of data-parallel kernels, one thread per listed window ("entry"), no barrier on the data path.
+// sx_sparse_utf8.cuh -- the exact stage of plain missions as a pipeline of data-parallel kernels, one thread per listed
+// window ("entry"), no barrier on the data path.  UTF-8 and the single-byte family run the bit-parallel window engine
+// (sx_mask_utf8.cuh) in it; UTF-16/32, Big5 and EUC-JP "decline" everywhere and run the convergent byte-wise engine
+// (sx_fast_generic.cuh) through the fallbacks every stage has.
 //
 // sx_exact_kernel (sx_exact.cuh) resolves the carries of a block of entries with block barriers between its stages;
 // on the sparse lists of binary input almost every stage has a handful of busy lanes, so the kernel is bound by the
@@ -11,26 +13,29 @@
 //                        entries whose predecessor window is not listed: carry-in from the 32 bytes in front of the
 //                        window (the pre-roll folded into the mask frame), ONE pass of the mask engine
 //                        (sx_mask_utf8.cuh) -> carry-out, counts, first records
+//   sx_sp_declined_kernel heads the mask engine declined (byte-wise engine): a few, on a side stream beside the members,
+//                        for the mask-engine decoders; ALL heads, in stream order in front of the members, for the others
 //   sx_sp_members_kernel members, in parallel: carry-in = carry-out of the entry before, taken from a resolved head or
-//                        recomputed from that window alone when it does not depend on ITS carry-in (WinResult.cut1)
-//   sx_sp_declined_kernel heads the mask engine declined (byte-wise engine), on a side stream beside the members
-//   sx_sp_fix_kernel     the rest, few: members behind a carry-dependent window (walked in order; a window that is one short run is passed in closed
-//                        form, eval_caseb, and resolved afterwards by sx_sp_late_kernel, in parallel)
+//                        recomputed from that window alone when it does not depend on ITS carry-in (WinResult.cut1 /
+//                        WinDesc.type == WT_CONST)
+//   sx_sp_fix_kernel     the rest, few: members behind a carry-dependent window (walked in order; a window that is one
+//                        short run is passed in closed form, eval_caseb, and resolved afterwards by sx_sp_late_kernel)
 //   sx_sp_ext_kernel     extension windows (a "cut" / long leftover carry reaching an unlisted successor),
 //                        per-entry totals -> per-chunk totals
 //   sx_sp_scan_kernel    exclusive scan of the per-chunk totals on top of the totals of the pieces before this one
-//   sx_sp_gather_kernel  records and text offsets in stream order (exactly the order FindingCollection::from pushes
-//                        them, finding_collection.rs:255-285); findings (C-ABI layout) and their text into device staging
-//                        buffers that the host copies to the collection's pinned memory piece by piece (copy engine,
-//                        overlapping the scan of the next piece); final carry for the ScannerState
+//   sx_sp_gather_kernel  records in stream order (exactly the order FindingCollection::from pushes them,
+//                        finding_collection.rs:255-285) as 8-byte wire records + their UTF-8 text, back to back, one
+//                        explicit text offset per page of 4096 records: straight into the collection's pinned,
+//                        device-mapped memory (little output) or into device staging that the copy engine moves part
+//                        by part (output-heavy calls); final carry for the ScannerState
 //
-// A call is cut into PIECES (window ranges, sx_scan.cu): each piece runs this pipeline on its own slices of the arrays
-// below while the prefilter already streams the next piece; the carry into a piece's first window comes from
-// sx_range_carry_kernel (sx_exact.cuh), so pieces do not wait for each other except for the record offsets.
+// A call may be cut into PIECES (window ranges, sx_scan.cu) behind ONE prefilter launch: each piece runs this pipeline
+// on its own slices of the arrays below; the carry into a piece's first window comes from sx_range_carry_kernel
+// (sx_exact.cuh), so pieces do not wait for each other except for the record offsets.
 //
 // Text-like input (every window listed, several findings per window) takes the same path: most windows' carry-out is
-// independent of their carry-in, so the members resolve in parallel too.  The block kernel remains for the other
-// encodings and for general missions (sx_scan.cu).
+// independent of their carry-in, so the members resolve in parallel too.  The block kernel remains for general missions
+// and for scans without the prefilter (sx_scan.cu).
 #pragma once
 #include "sx_exact.cuh"
 #include <algorithm>

@@ -41,7 +41,8 @@ class Slicer:
     def __iter__(self) -> Iterator[Tuple[bytes, Optional[int], bool]]:
         if self.from_stdin:
             while True:
-                b = self.stdin.read(INPUT_BUF_LEN)
+                # input.rs:118 is one Read::read() per slice: a short read from a pipe is a slice of its own
+                b = self.stdin.read1(INPUT_BUF_LEN) if hasattr(self.stdin, "read1") else self.stdin.read(INPUT_BUF_LEN)
                 if not b:
                     return  # input.rs:130-137: the consumer never sees is_last == true
                 yield b, None, False

@@ -84,9 +84,9 @@ def test_general_missions_guard_rules():
     the null carry unless the carried leftover fills that run up to q chars (guard_benign), and behind an adjacent
     guard / constant window that holds for every possible carry-in (guard_known_behind, what ends the block kernel's
     warm-up).  The harness checks both claims against the replay under the real carry on every window (stats[3]);
-    small q and n make the "killer" leftovers frequent.  Of the general missions --grep-char alone and
-    --same-unicode-block alone use the prefilter, each with the extra listing rule the fuzz's counterexamples asked for
-    (DESIGN.md section 7)."""
+    small q and n make the "killer" leftovers frequent.  --grep-char and --same-unicode-block missions use the
+    prefilter, each option with the extra listing rule the fuzz's counterexamples asked for (DESIGN.md section 7);
+    chars_min_nb > q does not."""
     import ctypes as C
     import dataclasses
 
@@ -107,9 +107,8 @@ def test_general_missions_guard_rules():
                 buf = corpus.gen(rng, rng.choice(corpus.KINDS), rng.randrange(1, 30000), enc)
                 f, _ = es.scan_stream(buf, False, 4096)
                 _cmp(es, os_, f, os_.scan_stream(buf, False, 4096).v)
-                one_rule = (m.filter.grep_char is not None) != bool(m.require_same_unicode_block) and m.chars_min_nb <= q
-                # prefilter for --grep-char alone (PrefCfg::kill_trail) and --same-unicode-block alone (PrefCfg::sb_rule)
-                assert es.stats[7] == (1 if one_rule else 0)
+                # prefilter for --grep-char (PrefCfg::kill_trail) and --same-unicode-block (PrefCfg::sb_rule), not for n > q
+                assert es.stats[7] == (1 if m.chars_min_nb <= q else 0)
             assert es.stats[3] == 0 and es.stats[4] == 0 and es.stats[5] == 0 and es.stats[6] == 0
     ok1, k1 = C.c_uint64(), C.c_uint64()
     L.sx_emul_guard_counts(C.byref(ok1), C.byref(k1))
@@ -145,7 +144,7 @@ def test_fuzz_grep_missions_with_prefilter(enc):
 
 @pytest.mark.parametrize("enc", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_fuzz_same_block_missions_with_prefilter(enc):
-    """--same-unicode-block alone keeps the prefilter (PrefCfg::sb_rule: a window whose trailing good run and the one
+    """--same-unicode-block (here: alone and, every third mission, together with --grep-char) keeps the prefilter (PrefCfg::sb_rule: a window whose trailing good run and the one
     of the window before it may both hold a multi-byte char is listed; the pre-roll of a head is the whole window before
     it).  Small q makes window boundaries frequent; corpus.gen_blocks mixes blocks inside runs behind ASCII junk."""
     import dataclasses
@@ -156,7 +155,8 @@ def test_fuzz_same_block_missions_with_prefilter(enc):
         m = corpus.random_mission(rng, enc, M)
         q = rng.choice([64, 32, 16, 8, 8, 8])
         ubf = rng.choice([M.UBF_ALL, M.UBF_ALL_VALID, M.UBF_ALL, m.filter.ubf])
-        m = dataclasses.replace(m, filter=dataclasses.replace(m.filter, grep_char=None, ubf=ubf), require_same_unicode_block=True,
+        grep = rng.choice([None, None, ord("a"), ord("e"), 0x20, ord("1")])
+        m = dataclasses.replace(m, filter=dataclasses.replace(m.filter, grep_char=grep, ubf=ubf), require_same_unicode_block=True,
                                 output_line_char_nb_max=q, chars_min_nb=min(rng.choice([1, 2, 3, 3, 4, 6, 8, 10]), q))
         es, os_ = emul.EmulState(m), oracle_state(m)
         for c in range(rng.choice([1, 1, 2, 3])):

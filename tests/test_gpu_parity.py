@@ -139,14 +139,17 @@ def test_prefilter_window_list_matches_spec_grep(label, n, q, grep, kind):
     check_state(gs, os_)
 
 
-@pytest.mark.parametrize("label,n,q,ubf,kind", [
-    ("utf-8", 6, 64, None, "rand"), ("utf-8", 10, 64, M.UBF_ALL, "rand"), ("utf-8", 8, 8, M.UBF_ALL, "blocks"), ("utf-8", 4, 16, M.UBF_ALL, "blocks"),
-    ("koi8-r", 6, 16, M.UBF_ALL, "blocks"), ("koi8-r", 6, 64, None, "rand"), ("ascii", 4, 8, None, "rand"), ("utf-16le", 4, 16, M.UBF_ALL, "blocks"),
-    ("utf-16be", 10, 64, None, "rand"), ("big5", 6, 16, M.UBF_ALL, "blocks"), ("euc-jp", 6, 64, None, "rand"), ("utf-8", 3, 8, None, "mixed"),
-    ("utf-32le", 4, 16, M.UBF_ALL, "blocks"), ("utf-8", 6, 32, M.UBF_ALL_VALID, "text"),
+@pytest.mark.parametrize("label,n,q,ubf,kind,grep", [
+    ("utf-8", 6, 64, None, "rand", None), ("utf-8", 10, 64, M.UBF_ALL, "rand", None), ("utf-8", 8, 8, M.UBF_ALL, "blocks", None),
+    ("utf-8", 4, 16, M.UBF_ALL, "blocks", None), ("koi8-r", 6, 16, M.UBF_ALL, "blocks", None), ("koi8-r", 6, 64, None, "rand", None),
+    ("ascii", 4, 8, None, "rand", None), ("utf-16le", 4, 16, M.UBF_ALL, "blocks", None), ("utf-16be", 10, 64, None, "rand", None),
+    ("big5", 6, 16, M.UBF_ALL, "blocks", None), ("euc-jp", 6, 64, None, "rand", None), ("utf-8", 3, 8, None, "mixed", None),
+    ("utf-32le", 4, 16, M.UBF_ALL, "blocks", None), ("utf-8", 6, 32, M.UBF_ALL_VALID, "text", None),
+    ("utf-8", 4, 8, M.UBF_ALL, "blocks", "a"), ("utf-8", 6, 64, None, "rand", "e"), ("koi8-r", 3, 8, M.UBF_ALL, "blocks", "b"),
+    ("utf-16le", 4, 16, M.UBF_ALL, "blocks", "1"), ("big5", 4, 8, M.UBF_ALL, "blocks", "a"),
 ])
-def test_prefilter_window_list_matches_spec_same_block(label, n, q, ubf, kind):
-    """--same-unicode-block alone keeps the prefilter with one more rule (PrefCfg::sb_rule: a window whose trailing good
+def test_prefilter_window_list_matches_spec_same_block(label, n, q, ubf, kind, grep):
+    """--same-unicode-block (alone or with --grep-char) keeps the prefilter with one more rule (PrefCfg::sb_rule: a window whose trailing good
     run may hold a multi-byte char is listed when the trailing run of the window before it or its own leading run may
     hold one too; the pre-roll of a head is the whole window before it): the kernel lists exactly the windows of the
     byte-wise specification and the findings are the oracle's."""
@@ -154,7 +157,7 @@ def test_prefilter_window_list_matches_spec_same_block(label, n, q, ubf, kind):
 
     import emul
 
-    m = dataclasses.replace(M.Mission.for_label(label, n, None, ubf, None, q), require_same_unicode_block=True)
+    m = dataclasses.replace(M.Mission.for_label(label, n, None, ubf, ord(grep) if grep else None, q), require_same_unicode_block=True)
     rng = random.Random(321)
     size = (1 << 20) + 4096
     if kind == "rand":
@@ -384,7 +387,7 @@ def test_general_missions_large_buffers_vs_oracle(enc):
     """--grep-char / --same-unicode-block / n > q on buffers of many 128-entry blocks (the block kernel's warm-up finds
     a known carry through the WT_GUARD rules, sx_core.cuh guard_benign / guard_known_behind): the oracle's findings,
     on sparse input (random bytes + planted strings) and dense input, with and without the prefilter (which --grep-char
-    alone and --same-unicode-block alone may use, PrefCfg::kill_trail / sb_rule; DESIGN.md section 7)."""
+    and --same-unicode-block missions use, PrefCfg::kill_trail / sb_rule, and n > q does not; DESIGN.md section 7)."""
     import dataclasses
 
     rng = random.Random(4242 + enc)
@@ -407,8 +410,7 @@ def test_general_missions_large_buffers_vs_oracle(enc):
                 continue
             ra = gpu_findings(a.scan_stream(part, False, 4096))
             rb = gpu_findings(b.scan_stream(part, False, 4096))
-            one_rule = (m.filter.grep_char is not None) != bool(m.require_same_unicode_block) and n <= q
-            assert a.last_stats.prefilter_used == (1 if one_rule else 0) and b.last_stats.prefilter_used == 0
+            assert a.last_stats.prefilter_used == (1 if n <= q else 0) and b.last_stats.prefilter_used == 0
             exp = oracle_findings(os_.scan_stream(part, False, 4096))
             assert ra == exp, (enc, m, len(part))
             assert rb == exp, (enc, m, len(part))
