@@ -6,7 +6,7 @@ scanner.py mirror the reference's Mission / ScannerState / FindingCollection / F
 on top of that ABI.  There is no CPU scanning path.
 """
 from .mission import *  # noqa: F401,F403
-from .mission import Mission, Utf8Filter  # noqa: F401
+from .mission import Mission, MissionError, Missions, Utf8Filter  # noqa: F401
 from .input import INPUT_BUF_LEN, Slicer, scan_files, scan_inputs  # noqa: F401
 from .scanner import (  # noqa: F401
     Finding,

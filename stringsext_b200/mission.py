@@ -7,10 +7,13 @@ Mirrors (names, meaning, defaults) of
   * default filters mission.rs:32-50 and the `ascii` emulation mission.rs:623-679
   * option defaults /root/reference/src/options.rs:17-33
 
-Only *resolved* missions are modelled here: parsing of the `-e ENC,MIN,AF,UBF,GREP`
-mini-language (mission.rs:514-749) is CLI work and out of scope.
+`Missions.new` (mission.rs:514-749) turns the reference's option strings -- `-e ENC,MIN,AF,UBF,GREP` items, filter
+aliases, hexadecimal filters -- into resolved `Mission`s with the reference's defaulting and error rules, so that a
+caller can hand over the flags it gave the reference; option parsing proper (clap, options.rs) stays out of scope.
 """
 from __future__ import annotations
+
+import re
 
 from dataclasses import dataclass, field
 from typing import Optional, Sequence, Tuple
@@ -176,3 +179,126 @@ class Mission:
 
 def known_labels() -> Sequence[str]:
     return sorted(_LABELS)
+
+
+# ---- filter aliases, mission.rs:163-212 / :245-268 (name, value); matched by PREFIX in this order (parse_filter_parameter!)
+UNICODE_BLOCK_FILTER_ALIASSE = (
+    ("African", UBF_AFRICAN), ("All-Asian", UBF_ALL & ~UBF_INVALID & ~UBF_ASIAN), ("All", UBF_ALL & ~UBF_INVALID),
+    ("Arabic", UBF_ARABIC | UBF_SYRIAC), ("Armenian", UBF_ARMENIAN), ("Asian", UBF_ASIAN), ("Cjk", UBF_CJK), ("Common", UBF_COMMON),
+    ("Cyrillic", UBF_CYRILLIC), ("Default", UBF_ALL & ~UBF_INVALID), ("Greek", UBF_GREEK), ("Hangul", UBF_HANGUL),
+    ("Hebrew", UBF_HEBREW), ("Kana", UBF_KANA), ("Latin", UBF_LATIN | UBF_ACCENTS), ("None", UBF_NONE), ("Private", UBF_PUA),
+    ("Uncommon", UBF_UNCOMMON | UBF_PUA),
+)
+ASCII_FILTER_ALIASSE = (
+    ("All", AF_ALL), ("All-Ctrl", AF_ALL & ~AF_CTRL), ("All-Ctrl+Wsp", AF_ALL & ~AF_CTRL | AF_WHITESPACE), ("Default", AF_DEFAULT),
+    ("None", AF_NONE), ("Wsp", AF_WHITESPACE),
+)
+_ALIAS_WIDTH = 12  # the reference pads every alias name to 12 bytes and compares the given string with that prefix
+
+
+class MissionError(ValueError):
+    """What Missions::new reports as an anyhow error."""
+
+
+def _rust_uint(text: str, radix: int, bits: int, what: str) -> int:
+    # {integer}::from_str / from_str_radix: optional '+', digits of the radix, nothing else; overflow is an error
+    digits = "0-9" if radix == 10 else "0-9a-fA-F"
+    if not re.fullmatch(rf"\+?[{digits}]+", text):
+        raise MissionError(f"failed to parse {what}: `{text}`")
+    v = int(text, radix)
+    if v >> bits:
+        raise MissionError(f"failed to parse {what}: `{text}` (number too large)")
+    return v
+
+
+def parse_integer(s: Optional[str], bits: int) -> Optional[int]:
+    """mission.rs:440-457 (parse_integer!): None / empty -> None, `0x..` -> hexadecimal, else decimal."""
+    if s is None or s == "":
+        return None
+    t = s.strip()
+    if len(t) >= 2 and t[:2] == "0x":
+        return _rust_uint(t[2:], 16, bits, "hexadecimal number")
+    return _rust_uint(t, 10, bits, "number")
+
+
+def parse_filter_parameter(s: Optional[str], bits: int, aliases) -> Optional[int]:
+    """mission.rs:468-500 (parse_filter_parameter!): `0x..` -> hexadecimal bitmap, empty -> None, else the first alias
+    the (trimmed) string is a prefix of."""
+    if s is None:
+        return None
+    t = s.strip()
+    if len(t) >= 2 and t[:2] == "0x":
+        return _rust_uint(t[2:], 16, bits, "hexadecimal number")
+    if s == "":
+        return None
+    for name, value in aliases:
+        if len(t) <= _ALIAS_WIDTH and name.ljust(_ALIAS_WIDTH).startswith(t):
+            return value
+    raise MissionError(f"filter name `{t}` is not valid, try `--list-encodings`")
+
+
+class Missions:
+    """mission.rs:424-749: the missions of one run, built from the reference's option strings."""
+
+    def __init__(self, v: Sequence[Mission]):
+        self.v = list(v)
+
+    def __len__(self) -> int:
+        return len(self.v)
+
+    @staticmethod
+    def parse_enc_opt(enc_opt: str):
+        """mission.rs:706-748: `ENC,MIN,AF,UBF,GREP` -> (enc_name, chars_min_nb, af, ubf, grep_char), None where absent."""
+        items = enc_opt.split(",")
+        if items and items[-1] == "":
+            items.pop()  # str::split_terminator
+        it = iter(items)
+        first = next(it, None)
+        enc_name = None if first in (None, "") else first.strip()
+        chars_min_nb = parse_integer(next(it, None), 8)
+        af = parse_filter_parameter(next(it, None), 128, ASCII_FILTER_ALIASSE)
+        ubf = parse_filter_parameter(next(it, None), 64, UNICODE_BLOCK_FILTER_ALIASSE)
+        grep_char = parse_integer(next(it, None), 8)
+        if next(it, None) is not None:
+            raise MissionError(f"Too many items in `{enc_opt}`.")
+        return enc_name, chars_min_nb, af, ubf, grep_char
+
+    @staticmethod
+    def new(flag_counter_offset: Optional[str] = None, flag_encoding: Sequence[str] = (), flag_chars_min_nb: Optional[str] = None,
+            flag_same_unicode_block: bool = False, flag_ascii_filter: Optional[str] = None, flag_unicode_block_filter: Optional[str] = None,
+            flag_grep_char: Optional[str] = None, flag_output_line_len: Optional[str] = None) -> "Missions":
+        """mission.rs:514-703.  Item values win over the global flags, those over the defaults (ASCII mode for `ascii`)."""
+        counter_offset = parse_integer(flag_counter_offset, 64)
+        chars_min = parse_integer(flag_chars_min_nb, 8)
+        g_af = parse_filter_parameter(flag_ascii_filter, 128, ASCII_FILTER_ALIASSE)
+        g_ubf = parse_filter_parameter(flag_unicode_block_filter, 64, UNICODE_BLOCK_FILTER_ALIASSE)
+        g_grep = parse_integer(flag_grep_char, 8)
+        if g_grep is not None and g_grep > 127:
+            raise MissionError(f"you can only `--grep-char` for ASCII codes < 128, you tried: `{g_grep}`.")
+        out_len = parse_integer(flag_output_line_len, 64)
+        if out_len is not None and out_len < OUTPUT_LINE_CHAR_NB_MIN:
+            raise MissionError(f"minimum for `--output-line-len` is `{OUTPUT_LINE_CHAR_NB_MIN}`, you tried: `{out_len}`.")
+        v = []
+        for mission_id, enc_opt in enumerate(list(flag_encoding) or [ENCODING_DEFAULT]):
+            enc_name, n, af, ubf, grep = Missions.parse_enc_opt(enc_opt)
+            scanner = chr(97 + mission_id)
+            grep = grep if grep is not None else g_grep
+            if grep is not None and grep > 127:
+                raise MissionError(f"Scanner {scanner}: you can only grep for ASCII codes < 128, you tried: `{grep}`.")
+            try:
+                v.append(Mission.for_label(
+                    enc_name or ENCODING_DEFAULT,
+                    n if n is not None else chars_min,
+                    af if af is not None else g_af,
+                    ubf if ubf is not None else g_ubf,
+                    grep,
+                    out_len,
+                    flag_same_unicode_block,
+                    COUNTER_OFFSET_DEFAULT if counter_offset is None else counter_offset,
+                    mission_id,
+                ))
+            except MissionError:
+                raise
+            except ValueError as e:
+                raise MissionError(f"Scanner {scanner}: {e}, try flag `--list-encodings`.") from None
+        return Missions(v)
