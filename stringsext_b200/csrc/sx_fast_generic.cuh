@@ -3,13 +3,14 @@
 //
 // Same semantics as scan_window<Dec> in sx_core.cuh (the streaming restatement of FindingCollection::from +
 // SplitStr::next, /root/reference/src/finding_collection.rs:84-342, /root/reference/src/helper.rs:210-432), organised
-// like sx_fast_utf8.cuh: the decoder's step is run against a recording emitter (at most two events per input byte:
-// "malformed, then the byte again", "char + second code point of a Big5 pair", "malformed + pending BMP unit"), and
-// the automaton's common transitions -- passing char, short run dropped at a breaker, malformed sequence with nothing
-// to print -- are predicated so the 32 lanes of a warp stay together; everything that prints, cuts or probes is the
-// rare slow path.  ncu on the generic automaton (profiles/r02_tuning.txt): 116 instructions per byte and lane with
-// 8.8 of 32 lanes active; this one exists because Big5 / EUC-JP / UTF-16 lists are scanned byte-wise.
-// tests/emul cross-checks it against the generic automaton's oracle results on the CPU.
+// like sx_fast_utf8.cuh.  Per input byte the decoder yields at most two events ("malformed, then the byte again",
+// "char + second code point of a Big5 pair", "malformed + pending BMP unit"): GenStep<Dec> computes them with selects
+// and one exit (UTF-32 runs its own step() against the recording emitter), and the automaton's common transitions --
+// passing char, short run dropped at a breaker, malformed sequence with nothing to print -- are blends under
+// all-ones / all-zero masks, so the 32 lanes of a warp stay together; everything that prints, cuts or probes is the
+// rare slow path.  ncu (profiles/r02_bytewise.txt): the generic automaton ran 116 instructions per byte and lane with
+// 8.8 of 32 lanes active, this one 22 lanes and 1.7x fewer warp instructions.
+// tests/emul runs plain missions of these decoders through it on the CPU, against the oracle.
 #pragma once
 #include "sx_fast_utf8.cuh"
 
@@ -20,11 +21,6 @@ enum : uint32_t { GE_CHAR = 1, GE_MAL = 2 };
 // (ncu: 8.8 of 32 lanes active through the whole automaton).  Passing the recorded events through an empty asm makes
 // them opaque at the join, so the automaton below is emitted once and the lanes meet again in front of it.
 #define SX_OPAQUE(x) asm volatile("" : "+r"(x))
-// pass_filter (sx_core.cuh; Utf8Filter::pass_af_filter / pass_ubf_filter, mission.rs:333-348) as two selects
-SX_HD bool pass_filter_sel(const ScanParams& P, uint32_t lb) {
-    const uint64_t word = lb < 64 ? P.af_lo : (lb < 128 ? P.af_hi : P.ubf);
-    return ((word >> (lb & 63u)) & 1u) != 0;
-}
 struct GenEvent {
     uint32_t kind;  // 0 none, GE_CHAR, GE_MAL
     uint32_t lb, ul;
